@@ -1,0 +1,536 @@
+"""ORACLE (test infrastructure, NOT product code) — CPU restatement of the reference's
+photometric view-synthesis loss path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module; the product package never does.
+
+What it restates
+----------------
+The reference (jianfenglihg/Unsupervised_depth_OpticalFlow_egomotion, mounted read-only at
+/root/reference while building) is pure Python; the arithmetic of this path lives in a
+third-party dependency that is absent from the reference tree: **PyTorch** (no version pinned in
+``requirements.txt:1-28``; effective pin = this image's torch 2.11.0, whose ``grid_sample`` default
+is ``align_corners=False``).  The library calls at the reference's call sites
+(``F.grid_sample``, ``nn.AvgPool2d``, ``F.interpolate``, ``softmax``, ``norm``, ``inverse``) are kept
+as library calls here so that the CPU baseline is as fast as the reference's own CPU path, and
+``grid_sample_restated`` / ``avg_pool3_restated`` additionally spell the published algorithms out in
+elementary tensor ops (tests pin one against the other).
+
+Every function cites the reference ``file:line`` (relative to ``core/networks/``) it follows.
+The code is organised functionally (no nn.Module, both directions share helpers) rather than as
+the reference's three copy-pasted classes.
+
+Parity pinning
+--------------
+The reference ships no tests / golden vectors for this path.  The oracle is
+pinned against *outputs of the reference itself executed in the build container*:
+``oracle/validate_against_reference.py`` imports the unmodified reference modules and compares
+every function below (values and autograd gradients), and ``tests/golden/make_golden.py`` stores
+reference outputs as fixtures that travel to the GPU box.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+# ----------------------------------------------------------------------------------------------
+# constants hard-coded in the reference
+# ----------------------------------------------------------------------------------------------
+SSIM_C1 = 0.01 ** 2            # pytorch_ssim/ssim.py:5
+SSIM_C2 = 0.03 ** 2            # pytorch_ssim/ssim.py:6
+WARP_MASK_THRES = 0.9999       # structures/net_utils.py:50
+OCC_HARD_THRES = 0.48          # model_geometry.py:127
+DEPTH_MIN = 1e-3               # structures/inverse_warp.py:247,301
+
+
+# ----------------------------------------------------------------------------------------------
+# sampling primitives
+# ----------------------------------------------------------------------------------------------
+def grid_sample_restated(x: Tensor, grid: Tensor) -> Tensor:
+    """Bilinear, zeros-padding, align_corners=False sampling spelled out.
+
+    Restates ATen ``grid_sampler_2d`` (torch/include/ATen/native/GridSampler.h:27-36 for the
+    un-normalisation ``((g+1)*size-1)/2``; corner order nw, ne, sw, se; out-of-range corners
+    contribute zero).  x: (B,C,H,W), grid: (B,h,w,2) in [-1,1] -> (B,C,h,w).
+    """
+    B, C, H, W = x.shape
+    gx, gy = grid[..., 0], grid[..., 1]
+    ix = ((gx + 1) * W - 1) / 2
+    iy = ((gy + 1) * H - 1) / 2
+    x0, y0 = torch.floor(ix), torch.floor(iy)
+    x1, y1 = x0 + 1, y0 + 1
+    w_nw = (x1 - ix) * (y1 - iy)
+    w_ne = (ix - x0) * (y1 - iy)
+    w_sw = (x1 - ix) * (iy - y0)
+    w_se = (ix - x0) * (iy - y0)
+    flat = x.reshape(B, C, H * W)
+
+    def corner(xc: Tensor, yc: Tensor, wgt: Tensor) -> Tensor:
+        inside = (xc >= 0) & (xc <= W - 1) & (yc >= 0) & (yc <= H - 1)
+        idx = (yc.clamp(0, H - 1) * W + xc.clamp(0, W - 1)).long().reshape(B, 1, -1).expand(B, C, -1)
+        val = torch.gather(flat, 2, idx).reshape(B, C, *gx.shape[1:])
+        return val * (wgt * inside.to(x.dtype)).unsqueeze(1)
+
+    return corner(x0, y0, w_nw) + corner(x1, y0, w_ne) + corner(x0, y1, w_sw) + corner(x1, y1, w_se)
+
+
+def _pixel_grid(B: int, H: int, W: int, like: Tensor) -> Tensor:
+    """(B,2,H,W) grid with channel 0 = column index j, channel 1 = row index i."""
+    jj = torch.arange(W, dtype=like.dtype, device=like.device).view(1, 1, 1, W).expand(B, 1, H, W)
+    ii = torch.arange(H, dtype=like.dtype, device=like.device).view(1, 1, H, 1).expand(B, 1, H, W)
+    return torch.cat([jj, ii], 1)
+
+
+def flow_backwarp(x: Tensor, flow: Tensor, use_mask: bool = False, restated: bool = False) -> Tensor:
+    """W1 — structures/net_utils.py:16-54 (``warp_flow``).
+
+    Sample ``x`` at (j+u, i+v); coordinates are normalised with the (W-1)/(H-1) convention
+    (:42-43) but sampled with align_corners=False (:46), so the effective source column is
+    ``(j+u)*W/(W-1) - 0.5``.  With ``use_mask`` the result is multiplied by the {0,1} map
+    ``[sampled ones >= 0.9999]`` (:47-52), which is a constant for autograd.
+    """
+    B, C, H, W = x.shape
+    if flow.shape != (B, 2, H, W):
+        raise ValueError("the shape of grid {0} is not equal to the shape of flow {1}.".format(
+            torch.Size((B, 2, H, W)), flow.shape))
+    tgt = _pixel_grid(B, H, W, flow) + flow
+    gx = 2.0 * tgt[:, 0] / max(W - 1, 1) - 1.0
+    gy = 2.0 * tgt[:, 1] / max(H - 1, 1) - 1.0
+    grid = torch.stack([gx, gy], dim=-1)
+    sampler = grid_sample_restated if restated else (
+        lambda a, g: F.grid_sample(a, g, mode="bilinear", padding_mode="zeros", align_corners=False))
+    out = sampler(x, grid)
+    if not use_mask:
+        return out
+    with torch.no_grad():
+        cover = sampler(torch.ones_like(x), grid)
+        keep = (cover >= WARP_MASK_THRES).to(x.dtype)   # "<0.9999 -> 0, then >0 -> 1"
+    return out * keep
+
+
+def avg_pool3_restated(x: Tensor) -> Tensor:
+    """3x3 stride-1 zero-padded box mean with divisor 9 everywhere (AvgPool2d(3,1,padding=1),
+    count_include_pad=True) — pytorch_ssim/ssim.py:8."""
+    xp = F.pad(x, (1, 1, 1, 1))
+    H, W = x.shape[-2:]
+    acc = torch.zeros_like(x)
+    for dy in range(3):
+        for dx in range(3):
+            acc = acc + xp[..., dy:dy + H, dx:dx + W]
+    return acc / 9.0
+
+
+def ssim_map(x: Tensor, y: Tensor, restated: bool = False) -> Tensor:
+    """L2 core — pytorch_ssim/ssim.py:4-19: 3x3 box-moment SSIM map (not clamped)."""
+    pool = avg_pool3_restated if restated else (lambda t: F.avg_pool2d(t, 3, 1, padding=1))
+    mu_x, mu_y = pool(x), pool(y)
+    var_x = pool(x * x) - mu_x * mu_x
+    var_y = pool(y * y) - mu_y * mu_y
+    cov = pool(x * y) - mu_x * mu_y
+    num = (2 * mu_x * mu_y + SSIM_C1) * (2 * cov + SSIM_C2)
+    den = (mu_x * mu_x + mu_y * mu_y + SSIM_C1) * (var_x + var_y + SSIM_C2)
+    return num / den
+
+
+# ----------------------------------------------------------------------------------------------
+# pyramids
+# ----------------------------------------------------------------------------------------------
+def box_pyramid(img: Tensor, levels: int) -> List[Tensor]:
+    """PY (flow mode) — model_flow.py:58-64: adaptive average pooling to (H/2^s, W/2^s),
+    detached (``.data``)."""
+    H, W = img.shape[2:]
+    return [F.adaptive_avg_pool2d(img, [int(H / 2 ** s), int(W / 2 ** s)]).detach() for s in range(levels)]
+
+
+def bilinear_pyramid(img: Tensor, levels: int) -> List[Tensor]:
+    """PY (depth/geom mode) — model_geometry.py:65-72, model_depth.py:44-50: bilinear resize,
+    align_corners=False (= mean of the central 2x2 of every 2^s block)."""
+    H, W = img.shape[2:]
+    return [F.interpolate(img, (int(H / 2 ** s), int(W / 2 ** s)), mode="bilinear", align_corners=False)
+            for s in range(levels)]
+
+
+# ----------------------------------------------------------------------------------------------
+# masked means
+# ----------------------------------------------------------------------------------------------
+def masked_mean(diff: Tensor, mask: Tensor) -> Tensor:
+    """P(d, m) for one level: mean_{c,h,w}(d * m) / (mean(m) + 1e-12) -> (B,).
+    model_geometry.py:148-150, model_flow.py:98-100 (mask is repeated over the channels of d)."""
+    divider = mask.mean((1, 2, 3))
+    return (diff * mask).mean((1, 2, 3)) / (divider + 1e-12)
+
+
+def photometric_l1(imgs: Sequence[Tensor], warped: Sequence[Tensor], masks: Sequence[Tensor], scales: int) -> Tensor:
+    """L1 — model_geometry.py:143-153 / model_flow.py:72-81 / model_depth.py:92-103."""
+    return sum(masked_mean((imgs[s] - warped[s]).abs(), masks[s]) for s in range(scales))
+
+
+def masked_diff_loss(diffs: Sequence[Tensor], masks: Sequence[Tensor], scales: int) -> Tensor:
+    """model_flow.py:94-103 (``compute_loss_with_mask``) and model_geometry.py:716-732
+    (``compute_depth_flow_consis_loss``): P(diff, mask) summed over levels."""
+    return sum(masked_mean(diffs[s], masks[s]) for s in range(scales))
+
+
+def ssim_loss(imgs: Sequence[Tensor], warped: Sequence[Tensor], masks: Sequence[Tensor], scales: int) -> Tensor:
+    """L2 — model_geometry.py:212-223 / model_flow.py:141-152: the mask multiplies both SSIM
+    *inputs*; loss = mean(clamp((1-ssim)/2, 0, 1)) / (mean(mask) + 1e-12), summed over levels."""
+    total = 0
+    for s in range(scales):
+        m = masks[s]
+        smap = ssim_map(imgs[s] * m, warped[s] * m)
+        total = total + torch.clamp((1.0 - smap) / 2.0, 0, 1).mean((1, 2, 3)) / (m.mean((1, 2, 3)) + 1e-12)
+    return total
+
+
+# ----------------------------------------------------------------------------------------------
+# flow-mode masks and regularisers
+# ----------------------------------------------------------------------------------------------
+def warp_valid(warped: Tensor) -> Tensor:
+    """M2 — model_geometry.py:113-114 / model_flow.py:115-116: 1 unless all channels are exactly 0."""
+    return 1 - (warped == 0).prod(1, keepdim=True).type_as(warped)
+
+
+def occlusion_weights(from_l: Sequence[Tensor], imgs: Sequence[Tensor], from_r: Sequence[Tensor],
+                      scales: int, soft: bool):
+    """M3 — hard: model_geometry.py:105-132 (``compute_occ_weight``);
+    soft: model_flow.py:105-138 (``compute_diff_weight``).
+
+    d_l, d_r = channel-mean absolute differences; wgt = 1 - softmax([d_l, d_r]) (constant for
+    autograd).  hard: [wgt > 0.48]; soft: 2*exp(-(wgt-0.5)^2/0.03) * valid.
+    Returns dict of per-level lists: diff_bwd, diff_fwd, w_bwd, w_fwd, valid_bwd, valid_fwd.
+    """
+    out = {k: [] for k in ("diff_bwd", "diff_fwd", "w_bwd", "w_fwd", "valid_bwd", "valid_fwd")}
+    for s in range(scales):
+        il, ic, ir = from_l[s], imgs[s], from_r[s]
+        v_f, v_b = warp_valid(ir), warp_valid(il)
+        d_l = (ic - il).abs().mean(1, True)
+        d_r = (ic - ir).abs().mean(1, True)
+        with torch.no_grad():
+            wgt = 1 - torch.softmax(torch.cat([d_l, d_r], 1), 1)
+            if soft:
+                wgt = 2 * torch.exp(-(wgt - 0.5) ** 2 / 0.03)
+                w_b, w_f = wgt[:, 0:1] * v_b, wgt[:, 1:2] * v_f
+            else:
+                wgt = (wgt > OCC_HARD_THRES).float()
+                w_b, w_f = wgt[:, 0:1], wgt[:, 1:2]
+        out["diff_bwd"].append(d_l); out["diff_fwd"].append(d_r)
+        out["w_bwd"].append(w_b); out["w_fwd"].append(w_f)
+        out["valid_bwd"].append(v_b); out["valid_fwd"].append(v_f)
+    return out
+
+
+def flow_l2_norm(flow: Tensor) -> Tensor:
+    """model_geometry.py:48-54: sqrt(u^2+v^2) + 1e-12, (B,1,h,w)."""
+    return torch.norm(flow, p=2, dim=1).unsqueeze(1) + 1e-12
+
+
+def second_order_smooth(flow: Tensor, img: Tensor) -> Tensor:
+    """L4 — model_geometry.py:254-269 / model_flow.py:156-171 (``cal_grad2_error``): edge-aware
+    second differences; the weight of edge (x+1,x+2) pairs with the second difference centred at x+1."""
+    gx_i = img[:, :, :, 1:] - img[:, :, :, :-1]
+    gy_i = img[:, :, 1:, :] - img[:, :, :-1, :]
+    wx = torch.exp(-10.0 * gx_i.abs().mean(1, keepdim=True))
+    wy = torch.exp(-10.0 * gy_i.abs().mean(1, keepdim=True))
+    fx = flow[:, :, :, 1:] - flow[:, :, :, :-1]
+    fy = flow[:, :, 1:, :] - flow[:, :, :-1, :]
+    fxx = fx[:, :, :, 1:] - fx[:, :, :, :-1]
+    fyy = fy[:, :, 1:, :] - fy[:, :, :-1, :]
+    return ((wx[:, :, :, 1:] * fxx.abs()).mean((1, 2, 3)) + (wy[:, :, 1:, :] * fyy.abs()).mean((1, 2, 3))) / 2.0
+
+
+def flow_smooth_loss(flows: Sequence[Tensor], imgs: Sequence[Tensor], scales: int) -> Tensor:
+    """L4 — model_geometry.py:271-279 / model_flow.py:173-181: flow/20 per level, summed."""
+    return sum(second_order_smooth(flows[s] / 20.0, imgs[s]) for s in range(scales))
+
+
+def flow_direction_consistency(fwd: Sequence[Tensor], bwd: Sequence[Tensor], occ: Sequence[Tensor], scales: int) -> Tensor:
+    """L5 — model_geometry.py:195-210 / model_flow.py:184-199: |f^_fwd + f^_bwd| (unit-normalised
+    flows, bwd detached) under mask (1 - occ)."""
+    total = 0
+    for s in range(scales):
+        f_hat = fwd[s] / flow_l2_norm(fwd[s])
+        b_hat = (bwd[s] / flow_l2_norm(bwd[s])).detach()
+        total = total + masked_mean((f_hat + b_hat).abs(), 1 - occ[s])
+    return total
+
+
+# ----------------------------------------------------------------------------------------------
+# depth + pose reprojection
+# ----------------------------------------------------------------------------------------------
+def euler_to_rotation(angles: Tensor) -> Tensor:
+    """structures/inverse_warp.py:110-145 (``euler2mat``): R = Rx @ Ry @ Rz, angles (B,3)=(rx,ry,rz)."""
+    rx, ry, rz = angles[:, 0], angles[:, 1], angles[:, 2]
+    zero = rz.detach() * 0
+    one = zero + 1
+    cz, sz, cy, sy, cx, sx = rz.cos(), rz.sin(), ry.cos(), ry.sin(), rx.cos(), rx.sin()
+    Rz = torch.stack([cz, -sz, zero, sz, cz, zero, zero, zero, one], 1).reshape(-1, 3, 3)
+    Ry = torch.stack([cy, zero, sy, zero, one, zero, -sy, zero, cy], 1).reshape(-1, 3, 3)
+    Rx = torch.stack([one, zero, zero, zero, cx, -sx, zero, sx, cx], 1).reshape(-1, 3, 3)
+    return Rx @ Ry @ Rz
+
+
+def pose_to_matrix(pose: Tensor) -> Tensor:
+    """structures/inverse_warp.py:172-187: pose (B,6) = [tx,ty,tz,rx,ry,rz] -> [R|t] (B,3,4)."""
+    return torch.cat([euler_to_rotation(pose[:, 3:]), pose[:, :3].unsqueeze(-1)], dim=2)
+
+
+def scale_intrinsics(K: Tensor, downscale: float) -> Tensor:
+    """model_geometry.py:92-93: rows 0-1 of K divided by the downscale factor, row 2 kept."""
+    return torch.cat((K[:, 0:2] / downscale, K[:, 2:]), dim=1)
+
+
+def _project(depth: Tensor, pose: Tensor, K: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """Backproject with K^-1 (torch.inverse, inverse_warp.py:284), rigid transform, project
+    with K[R|t] (:289); returns un-clamped X, Y and Z = max(p_z, 1e-3), each (B, h*w)."""
+    B, _, h, w = depth.shape
+    jj = torch.arange(w, dtype=depth.dtype, device=depth.device).view(1, 1, w).expand(1, h, w)
+    ii = torch.arange(h, dtype=depth.dtype, device=depth.device).view(1, h, 1).expand(1, h, w)
+    pix = torch.stack((jj, ii, torch.ones_like(jj)), dim=1).expand(B, 3, h, w).reshape(B, 3, -1)
+    cam = ((K.inverse() @ pix).reshape(B, 3, h, w) * depth).reshape(B, 3, -1)        # :30-45
+    P = K @ pose_to_matrix(pose)                                                       # :289
+    q = P[:, :, :3] @ cam + P[:, :, -1:]
+    return q[:, 0], q[:, 1], q[:, 2].clamp(min=DEPTH_MIN)
+
+
+def reproject(img: Tensor, depth: Tensor, ref_depth: Tensor, pose: Tensor, K: Tensor):
+    """R2 — structures/inverse_warp.py:263-303 (``inverse_warp2``) with ``cam2pixel2`` :227-260.
+
+    Returns (img', valid, projected_depth, computed_depth).  Normalised coordinates outside
+    [-1,1] are overwritten with the constant 2 (:252-257), valid = [max(|gx|,|gy|) <= 1]."""
+    B, _, h, w = depth.shape
+    X, Y, Z = _project(depth, pose, K)
+    gx = 2 * (X / Z) / (w - 1) - 1
+    gy = 2 * (Y / Z) / (h - 1) - 1
+    gx = torch.where(((gx > 1) | (gx < -1)).detach(), torch.full_like(gx, 2.0), gx)
+    gy = torch.where(((gy > 1) | (gy < -1)).detach(), torch.full_like(gy, 2.0), gy)
+    grid = torch.stack([gx, gy], dim=2).reshape(B, h, w, 2)
+    warped = F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    valid = (grid.abs().max(dim=-1)[0] <= 1).unsqueeze(1).float()
+    proj_depth = F.grid_sample(ref_depth, grid, mode="bilinear", padding_mode="zeros",
+                               align_corners=False).clamp(min=DEPTH_MIN)
+    return warped, valid, proj_depth, Z.reshape(B, 1, h, w)
+
+
+def rigid_flow(depth: Tensor, pose: Tensor, K: Tensor) -> Tensor:
+    """R3 — structures/inverse_warp.py:311-342 with ``cam2pixel_change_shape`` :47-78:
+    (X/Z, Y/Z) - (j, i), un-normalised pixels."""
+    B, _, h, w = depth.shape
+    X, Y, Z = _project(depth, pose, K)
+    tgt = torch.stack([X / Z, Y / Z], 1).reshape(B, 2, h, w)
+    return tgt - _pixel_grid(B, h, w, depth)
+
+
+def reconstruct_pyramid(ref_img: Tensor, K: Tensor, depth: Sequence[Tensor], depth_ref: Sequence[Tensor],
+                        pose: Tensor, scales: int):
+    """R1 — model_geometry.py:80-103 / model_depth.py:59-82: area-resize the source image, scale
+    K rows 0-1 by H/h, reproject per level."""
+    rec, valid, proj, comp = [], [], [], []
+    for s in range(scales):
+        h, w = depth[s].shape[2:]
+        src = F.interpolate(ref_img, (h, w), mode="area")
+        Ks = scale_intrinsics(K, ref_img.size(2) / h)
+        a, b, c, d = reproject(src, depth[s], depth_ref[s], pose, Ks)
+        rec.append(a); valid.append(b); proj.append(c); comp.append(d)
+    return rec, valid, proj, comp
+
+
+def texture_mask(imgs: Sequence[Tensor], recon: Sequence[Tensor], src: Sequence[Tensor], scales: int) -> List[Tensor]:
+    """M4 — model_geometry.py:134-140 / model_depth.py:84-90 (monodepth2 auto-mask)."""
+    return [((imgs[s] - recon[s]).abs().mean(1, keepdim=True) < (imgs[s] - src[s]).abs().mean(1, keepdim=True)).float()
+            for s in range(scales)]
+
+
+def disparity_smooth_loss(img: Tensor, disps: Sequence[Tensor], scales: int) -> Tensor:
+    """L3 — model_geometry.py:225-252 / model_depth.py:220-247: every level is bilinearly
+    up-sampled to full resolution first; first differences weighted by exp(-mean_c|dI|)."""
+    H, W = img.shape[2:]
+    total = 0
+    wx = torch.exp(-(img[:, :, :, :-1] - img[:, :, :, 1:]).abs().mean(1, keepdim=True))
+    wy = torch.exp(-(img[:, :, :-1, :] - img[:, :, 1:, :]).abs().mean(1, keepdim=True))
+    for s in range(scales):
+        d = F.interpolate(disps[s], size=(H, W), mode="bilinear", align_corners=False)
+        gx = (d[:, :, :, :-1] - d[:, :, :, 1:]).abs() * wx
+        gy = (d[:, :, :-1, :] - d[:, :, 1:, :]).abs() * wy
+        total = total + gx.mean((1, 2, 3)) + gy.mean((1, 2, 3))
+    return total
+
+
+def depth_consistency_loss(proj: Sequence[Tensor], comp: Sequence[Tensor], scales: int,
+                           masks: Optional[Sequence[Tensor]] = None) -> Tensor:
+    """L8 — masked: model_geometry.py:182-193; unmasked: model_depth.py:154-163."""
+    total = 0
+    for s in range(scales):
+        d = ((comp[s] - proj[s]).abs() / (comp[s] + proj[s]).abs()).clamp(0, 1)
+        total = total + (d.mean((1, 2, 3)) if masks is None else masked_mean(d, masks[s]))
+    return total
+
+
+def dynamic_mask(K: Tensor, depth: Sequence[Tensor], pose: Tensor, flow: Sequence[Tensor], scales: int,
+                 alpha: float, beta: float):
+    """M6 — model_geometry.py:685-713: rigid flow vs. optical flow; returns per-level
+    (|rf - f| (differentiable), [n(fd)^2 < alpha*(n(f)^2+n(rf)^2)+beta], 1/(1e-4+n(fd)))."""
+    diffs, masks, scores = [], [], []
+    H0 = depth[0].size(2)
+    for s in range(scales):
+        h = depth[s].size(2)
+        rf = rigid_flow(depth[s], pose, scale_intrinsics(K, H0 / h))
+        bound = alpha * (flow_l2_norm(flow[s]).pow(2) + flow_l2_norm(rf).pow(2)) + beta
+        fd = (rf - flow[s]).abs()
+        diffs.append(fd)
+        with torch.no_grad():
+            masks.append((flow_l2_norm(fd).pow(2) < bound).float())
+            scores.append(1.0 / (1e-4 + flow_l2_norm(fd)))
+    return diffs, masks, scores
+
+
+def essential_matrix(pose: Tensor) -> Tensor:
+    """structures/inverse_warp.py:344-364: E = [t]x @ R."""
+    t = pose[:, :3]
+    zero = torch.zeros_like(t[:, 0])
+    tx = torch.stack([zero, -t[:, 2], t[:, 1], t[:, 2], zero, -t[:, 0], -t[:, 1], t[:, 0], zero], 1).view(-1, 3, 3)
+    return tx.bmm(euler_to_rotation(pose[:, 3:]))
+
+
+def epipolar_distance(pose: Tensor, flow: Tensor, K: Tensor, K_inv: Tensor) -> Tensor:
+    """L7 map — model_geometry.py:355-403: F = K^-T E K^-1; l = F [j,i,1]^T;
+    dist = |[j+u, i+v, 1] . l| / (sqrt(l0^2 + l1^2) + 1e-6) -> (B,1,h,w)."""
+    B, _, h, w = flow.shape
+    grid = _pixel_grid(B, h, w, flow)
+    one = torch.ones(B, 1, h * w, dtype=flow.dtype, device=flow.device)
+    p1 = torch.cat([grid.reshape(B, 2, -1), one], 1)
+    p2 = torch.cat([(grid + flow).reshape(B, 2, -1), one], 1)
+    Fm = K_inv.transpose(1, 2).bmm(essential_matrix(pose).bmm(K_inv))
+    line = Fm.bmm(p1)
+    div = torch.sqrt(line[:, 0:1] ** 2 + line[:, 1:2] ** 2) + 1e-6
+    return ((p2 * line).sum(1, keepdim=True).abs() / div).view(B, 1, h, w)
+
+
+def rigid_masks(dist: Tensor, rigid_thres: float = 0.5, inlier_thres: float = 0.1):
+    """M7 — model_geometry.py:420-425."""
+    with torch.no_grad():
+        rigid = (dist < rigid_thres).float()
+        return rigid, (dist < inlier_thres).float(), rigid / (1.0 + dist)
+
+
+# ----------------------------------------------------------------------------------------------
+# per-mode assembly (T0)
+# ----------------------------------------------------------------------------------------------
+def flow_mode_loss(img_l: Tensor, img: Tensor, img_r: Tensor, flows_fwd: Sequence[Tensor],
+                   flows_bwd: Sequence[Tensor], scales: int, return_aux: bool = False):
+    """T0/flow — model_flow.py:232-254.  ``scales`` plays the role of
+    ``self.num_scales``; pyramids have ``len(flows_fwd)`` levels."""
+    L = len(flows_fwd)
+    pl, pc, pr = box_pyramid(img_l, L), box_pyramid(img, L), box_pyramid(img_r, L)
+    from_l = [flow_backwarp(pl[s], flows_bwd[s], use_mask=True) for s in range(L)]
+    from_r = [flow_backwarp(pr[s], flows_fwd[s], use_mask=True) for s in range(L)]
+    occ = occlusion_weights(from_l, pc, from_r, scales, soft=True)
+    loss = {
+        "loss_flow_pixel": masked_diff_loss(occ["diff_fwd"], occ["w_fwd"], scales)
+                           + masked_diff_loss(occ["diff_bwd"], occ["w_bwd"], scales),
+        "loss_flow_ssim": ssim_loss(pc, from_r, occ["w_fwd"], scales) + ssim_loss(pc, from_l, occ["w_bwd"], scales),
+        "loss_flow_smooth": flow_smooth_loss(flows_fwd, pc, scales) + flow_smooth_loss(flows_bwd, pc, scales),
+        "loss_flow_consis": flow_direction_consistency(flows_fwd, flows_bwd, occ["w_fwd"], scales),
+    }
+    if return_aux:
+        return loss, dict(occ, from_l=from_l, from_r=from_r, pyr=pc)
+    return loss
+
+
+def depth_mode_loss(img_l: Tensor, img: Tensor, img_r: Tensor, disp: Sequence[Tensor], disp_l: Sequence[Tensor],
+                    disp_r: Sequence[Tensor], pose: Tensor, K: Tensor, scales: int,
+                    variant: str = "live", return_aux: bool = False):
+    """T0/depth.  ``variant='live'``: model_depth.py:281-335 (L1 under valid*texture + smoothness;
+    ssim/consis are zero placeholders of shape [2]).  ``variant='texture'``:
+    model_depth_texture.py:296-311 (L1 under valid*texture, SSIM under valid, unmasked depth
+    consistency, smoothness) — the SSIM-enabled configuration of BASELINE config 3."""
+    pl, pc, pr = bilinear_pyramid(img_l, scales), bilinear_pyramid(img, scales), bilinear_pyramid(img_r, scales)
+    rec_l, val_l, proj_l, comp_l = reconstruct_pyramid(img_l, K, disp, disp_l, pose[:, 0], scales)
+    rec_r, val_r, proj_r, comp_r = reconstruct_pyramid(img_r, K, disp, disp_r, pose[:, 1], scales)
+    tex_b, tex_f = texture_mask(pc, rec_l, pl, scales), texture_mask(pc, rec_r, pr, scales)
+    m_b = [val_l[s] * tex_b[s] for s in range(scales)]
+    m_f = [val_r[s] * tex_f[s] for s in range(scales)]
+    loss = {
+        "loss_depth_pixel": photometric_l1(pc, rec_l, m_b, scales) + photometric_l1(pc, rec_r, m_f, scales),
+        "loss_depth_smooth": disparity_smooth_loss(img, disp, scales) + disparity_smooth_loss(img_l, disp_l, scales)
+                             + disparity_smooth_loss(img_r, disp_r, scales),
+    }
+    if variant == "texture":
+        loss["loss_depth_ssim"] = ssim_loss(pc, rec_l, val_l, scales) + ssim_loss(pc, rec_r, val_r, scales)
+        loss["loss_depth_consis"] = depth_consistency_loss(proj_l, comp_l, scales) + depth_consistency_loss(proj_r, comp_r, scales)
+    else:
+        loss["loss_depth_ssim"] = torch.zeros([2], device=img.device)
+        loss["loss_depth_consis"] = torch.zeros([2], device=img.device)
+    if return_aux:
+        return loss, dict(rec_l=rec_l, rec_r=rec_r, valid_l=val_l, valid_r=val_r, tex_b=tex_b, tex_f=tex_f,
+                          proj_l=proj_l, proj_r=proj_r, comp_l=comp_l, comp_r=comp_r)
+    return loss
+
+
+def geom_mode_loss(img_l: Tensor, img: Tensor, img_r: Tensor, flows_fwd: Sequence[Tensor], flows_bwd: Sequence[Tensor],
+                   disp: Sequence[Tensor], disp_l: Sequence[Tensor], disp_r: Sequence[Tensor], pose: Tensor,
+                   K: Tensor, K_inv: Tensor, scales: int, alpha: float = 0.01, beta: float = 0.5,
+                   return_aux: bool = False):
+    """T0/geom — model_geometry.py:777-951.  Index b = centre->left
+    (bwd flow, pose[:,0]); f = centre->right (fwd flow, pose[:,1])."""
+    S = scales
+    pl, pc, pr = bilinear_pyramid(img_l, S), bilinear_pyramid(img, S), bilinear_pyramid(img_r, S)
+    rec_l, val_l, _, _ = reconstruct_pyramid(img_l, K, disp, disp_l, pose[:, 0], S)
+    rec_r, val_r, _, _ = reconstruct_pyramid(img_r, K, disp, disp_r, pose[:, 1], S)
+    tex_b, tex_f = texture_mask(pc, rec_l, pl, S), texture_mask(pc, rec_r, pr, S)
+    from_l = [flow_backwarp(pl[s], flows_bwd[s], use_mask=True) for s in range(S)]
+    from_r = [flow_backwarp(pr[s], flows_fwd[s], use_mask=True) for s in range(S)]
+    occ = occlusion_weights(from_l, pc, from_r, S, soft=False)
+    fd_b, dyn_b, _ = dynamic_mask(K, disp, pose[:, 0], flows_bwd, S, alpha, beta)
+    fd_f, dyn_f, _ = dynamic_mask(K, disp, pose[:, 1], flows_fwd, S, alpha, beta)
+    dist_b = epipolar_distance(pose[:, 0], flows_bwd[0], K, K_inv)
+    dist_f = epipolar_distance(pose[:, 1], flows_fwd[0], K, K_inv)
+
+    vo_b = [occ["valid_bwd"][s] * occ["w_bwd"][s] for s in range(S)]
+    vo_f = [occ["valid_fwd"][s] * occ["w_fwd"][s] for s in range(S)]
+    m_b = [vo_b[s] * dyn_b[s] for s in range(S)]            # fusion_mask :847-848
+    m_f = [vo_f[s] * dyn_f[s] for s in range(S)]
+    mt_b = [m_b[s] * tex_b[s] for s in range(S)]            # :854-855
+    mt_f = [m_f[s] * tex_f[s] for s in range(S)]
+    dy_b = [vo_b[s] * (1 - dyn_b[s]) for s in range(S)]     # :863-864
+    dy_f = [vo_f[s] * (1 - dyn_f[s]) for s in range(S)]
+
+    z2 = lambda: torch.zeros([2], device=img.device)
+    loss = {
+        "loss_depth_pixel": photometric_l1(pc, rec_l, mt_b, S) + photometric_l1(pc, rec_r, mt_f, S),
+        "loss_depth_ssim": z2(),
+        "loss_depth_smooth": disparity_smooth_loss(img, disp, S) + disparity_smooth_loss(img_l, disp_l, S)
+                             + disparity_smooth_loss(img_r, disp_r, S),
+        "loss_depth_consis": z2(),
+        "loss_flow_pixel": photometric_l1(pc, from_l, m_b, S) + photometric_l1(pc, from_r, m_f, S)
+                           + 2 * photometric_l1(pc, from_l, dy_b, S) + 2 * photometric_l1(pc, from_r, dy_f, S),
+        "loss_flow_ssim": ssim_loss(pc, from_l, vo_b, S) + ssim_loss(pc, from_r, vo_f, S),
+        "loss_flow_smooth": flow_smooth_loss(flows_fwd, pc, S) + flow_smooth_loss(flows_bwd, pc, S),
+        "loss_flow_consis": flow_direction_consistency(flows_fwd, flows_bwd, occ["w_fwd"], S),
+        "loss_depth_flow_consis": masked_diff_loss(fd_b, m_b, 1) + masked_diff_loss(fd_f, m_f, 1),
+        "loss_epipolar": dist_b.mean((1, 2, 3)) + dist_f.mean((1, 2, 3)),   # :415-416 (mask ignored)
+        "loss_triangle": z2(), "loss_pnp": z2(), "loss_eight_point": z2(),
+    }
+    if return_aux:
+        return loss, dict(occ_b=occ["w_bwd"], occ_f=occ["w_fwd"], valid_b=occ["valid_bwd"], valid_f=occ["valid_fwd"],
+                          dyn_b=dyn_b, dyn_f=dyn_f, tex_b=tex_b, tex_f=tex_f, val_l=val_l, val_r=val_r,
+                          dist_b=dist_b, dist_f=dist_f, fd_b=fd_b, fd_f=fd_f, rec_l=rec_l, rec_r=rec_r,
+                          from_l=from_l, from_r=from_r)
+    return loss
+
+
+# loss weights: config/kitti.yaml:18-21 (flow) and config/kitti_geom.yaml:20-34 (geom)
+FLOW_WEIGHTS = {"loss_flow_pixel": 0.15, "loss_flow_ssim": 0.85, "loss_flow_smooth": 10.0, "loss_flow_consis": 0.01}
+GEOM_WEIGHTS = {"loss_flow_pixel": 0.15, "loss_flow_ssim": 0.85, "loss_flow_smooth": 10.0, "loss_flow_consis": 0.01,
+                "loss_depth_pixel": 1.0, "loss_depth_ssim": 0.85, "loss_depth_smooth": 0.5, "loss_depth_consis": 0.1,
+                "loss_depth_flow_consis": 1.0, "loss_epipolar": 0.1, "loss_triangle": 0.001, "loss_pnp": 0.1,
+                "loss_eight_point": 0.1}
+
+
+def weighted_total(loss_pack: Dict[str, Tensor], weights: Dict[str, float]) -> Tensor:
+    """train.py:211-214: sum_k w_k * mean_B(loss_k)."""
+    return sum(weights[k] * v.mean() for k, v in loss_pack.items())
