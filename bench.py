@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — frame-pairs/s of the photometric loss path, forward + backward.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU loss path (oracle port)
+
+Workload (BASELINE.json configs[1]): flow-mode 4-level pyramid loss (warp + soft occlusion + L1 + SSIM +
+second-order smoothness + fwd/bwd consistency), 256x832, batch 8 per GPU (weak scaling), synthetic
+KITTI-shaped inputs.  One training sample (l, c, r) = 2 frame pairs.  A step = fused forward + finalize +
+backward (d total / d flows) over one batch.
+
+Prints ONE JSON line (rank 0).  `value` = inputs resident in HBM, L2 flushed between steps, timed with
+CUDA events on the launching stream, max over ranks.  `e2e` = the same step through the host-buffer API
+(H2D of frames + flows from pinned memory, pyramid build, forward, backward, D2H of the losses).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, LEVELS, BATCH = 256, 832, 4, 8
+METRIC = "frame_pairs_per_sec_loss_fwd_bwd"
+UNIT = "frame-pairs/s"
+WORKLOAD = "flow-mode 4-level pyramid loss fwd+bwd, synthetic 256x832, batch 8 per GPU"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(batch: int, fwd: bool, bwd: bool) -> int:
+    """per sample and level fwd reads 13 N floats (3 images x 3 ch + 2 flows x 2 ch);
+    bwd re-reads 13 N and writes 4 N gradient floats."""
+    n = sum((H >> l) * (W >> l) for l in range(LEVELS))
+    floats = (13 * n if fwd else 0) + (17 * n if bwd else 0)
+    return floats * 4 * batch
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        busy = [c for c in sm if c >= 0.5 * max(sm)]
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(sample_batch: int, steps: int, warmup: int, threads: int):
+    """The reference's CPU loss path (oracle port of model_flow.py:232-254) on the host cores."""
+    from oracle import loss_port as P
+    from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
+    torch.set_num_threads(threads)
+    t = make_triplet(sample_batch, H, W, LEVELS, 1, seed=1234)
+    keys = list(P.FLOW_WEIGHTS)
+    times = []
+    for it in range(warmup + steps):
+        for f in t.flows_fwd + t.flows_bwd:
+            f.requires_grad_(True); f.grad = None
+        t0 = time.perf_counter()
+        loss = P.flow_mode_loss(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd, LEVELS)
+        total = sum(P.FLOW_WEIGHTS[k] * loss[k].mean() for k in keys)
+        total.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return 2.0 * sample_batch / statistics.median(times), statistics.median(times)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_b = 1
+    steps = max(1, min(args.steps, 20))
+    rate, sec = cpu_reference_rate(sample_b, steps, min(args.warmup, 2), cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "height": H, "width": W, "levels": LEVELS, "global_batch": BATCH * args.gpus},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "batch %d of the batch-%d workload per step (oracle/loss_port.py, torch CPU, %d threads)" % (sample_b, BATCH, cores)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="samples per GPU")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from unsupervised_depth_opticalflow_egomotion_b200 import _cabi, ops, build as ugl_build
+    from unsupervised_depth_opticalflow_egomotion_b200.step import FlowLossStep, FLOW_WEIGHTS, weight_matrix
+    from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the loss path has no CPU implementation); "
+                         "use --impl reference for the CPU baseline")
+    if rank == 0:
+        ugl_build.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    _cabi.lib()
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+
+    # ---- inputs resident in HBM -------------------------------------------------------------------------
+    host = make_triplet(B, H, W, LEVELS, 1, seed=1234 + rank, flow_px=10.0)
+    t = host.to(dev)
+    pl, pc, pr = (ops.image_pyramid(x, LEVELS, "box") for x in (t.img_l, t.img, t.img_r))
+    ff = [f.requires_grad_(True) for f in t.flows_fwd]
+    fb = [f.requires_grad_(True) for f in t.flows_bwd]
+    wmat = weight_matrix(FLOW_WEIGHTS, ops.FLOW_LOSS_KEYS, B, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step():
+        loss = ops.flow_loss(pl, pc, pr, ff, fb, LEVELS, as_matrix=True)
+        grads = torch.autograd.grad(loss, ff + fb, grad_outputs=wmat)
+        return loss, grads
+
+    n0 = ops.LAUNCH_COUNTER["n"]
+    loss, grads = step()
+    launches_per_step = ops.LAUNCH_COUNTER["n"] - n0
+    torch.cuda.synchronize()
+
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss, grads = step()
+        except Exception as e:   # pragma: no cover - reported in the JSON line
+            graph = None
+            sys.stderr.write("CUDA graph capture failed, timing eager launches: %r\n" % (e,))
+    run = (lambda: graph.replay()) if graph is not None else (lambda: step())
+
+    def timed(fn, n, warm):
+        for _ in range(warm):
+            fn(); flush.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(n):
+            flush.zero_()                         # L2 flush, outside the event pair
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    with ClockSampler(local) as clk:
+        ms = timed(run, K, Wm)
+        # per-kernel timing (eager, same stream) for the roofline of the dominant kernel
+        stats_ms = {"fwd": [], "bwd": []}
+        for _ in range(min(K, 20)):
+            flush.zero_()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            lmat = ops.flow_loss(pl, pc, pr, ff, fb, LEVELS, as_matrix=True)
+            e[1].record()
+            torch.autograd.grad(lmat, ff + fb, grad_outputs=wmat)
+            e[2].record()
+            torch.cuda.synchronize()
+            stats_ms["fwd"].append(e[0].elapsed_time(e[1]))
+            stats_ms["bwd"].append(e[1].elapsed_time(e[2]))
+    clocks = clk.summary()
+    total_ms = sum(ms)
+
+    # ---- e2e: host buffers -> losses on the host, through the public step API ------------------------------
+    pin = lambda x: x.pin_memory()
+    h_imgs = [pin(host.img_l), pin(host.img), pin(host.img_r)]
+    h_ff, h_fb = [pin(f.detach()) for f in host.flows_fwd], [pin(f.detach()) for f in host.flows_bwd]
+    stepper = FlowLossStep(B, H, W, LEVELS, device=dev)
+    e2e_ms = timed(lambda: stepper(h_imgs[0], h_imgs[1], h_imgs[2], h_ff, h_fb, sync=True), max(5, min(K, 20)), 3)
+    e2e_total = sum(e2e_ms)
+
+    # ---- max over ranks ------------------------------------------------------------------------------------
+    red = torch.tensor([total_ms, e2e_total / len(e2e_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms_per_step = float(red[0]), float(red[1])
+    ms_per_step = total_ms / K
+    value = 2.0 * B * world / (ms_per_step * 1e-3)
+    e2e_value = 2.0 * B * world / (e2e_ms_per_step * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        fwd_ms, bwd_ms = statistics.mean(stats_ms["fwd"]), statistics.mean(stats_ms["bwd"])
+        dom = "bwd" if bwd_ms >= fwd_ms else "fwd"
+        dom_ms = max(fwd_ms, bwd_ms)
+        dom_bytes = algorithmic_bytes(B, dom == "fwd", dom == "bwd")
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        step_achieved = algorithmic_bytes(B, True, True) / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "height": H, "width": W, "levels": LEVELS, "batch_per_gpu": B,
+                       "global_batch": B * world, "launch": "cuda-graph" if graph is not None else "eager",
+                       "l2": "flushed between steps (256 MiB memset outside the event pair)",
+                       "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step,
+                    "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": stepper.d2h_bytes},
+            "gpu_launches": launches_per_step * K,
+            "roofline": {"bound": "hbm", "kernel": "flow_loss_%s_kernel" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+                         "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                         "step": {"achieved": step_achieved, "frac": step_achieved / peak,
+                                  "algorithmic_bytes_per_step": algorithmic_bytes(B, True, True)}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            rate, sec = cpu_reference_rate(1, 8, 2, cores)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "batch 1 of the batch-%d workload, 8 timed steps (oracle/loss_port.py, torch CPU)" % B}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

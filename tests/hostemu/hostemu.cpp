@@ -1,0 +1,143 @@
+// TEST INFRASTRUCTURE — host emulator of the CUDA kernels' per-tile logic.
+//
+// The kernels' phase functions are `__host__ __device__`; this file drives them tile by tile on
+// the CPU (threads emulated sequentially, shared memory = a heap buffer) so that indexing and
+// arithmetic can be checked against the oracle on the GPU-less build box.  It is compiled by
+// tests/test_hostemu.py with g++ (-ffp-contract=off), is never part of libugl_b200.so and is never
+// imported by the product package: the product has no CPU path.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/ugl.h"
+#include "../../unsupervised_depth_opticalflow_egomotion_b200/csrc/ugl_flow_loss.cuh"
+#include "../../unsupervised_depth_opticalflow_egomotion_b200/csrc/ugl_primitives.cuh"
+
+using namespace ugl;
+
+template <int TW, int TH>
+static void fill_params(const UglFlowLossArgs* a, bool backward, FlowLossParams& p) {
+  p.B = a->batch;
+  p.scales = a->scales;
+  int tiles = 0;
+  for (int l = 0; l < a->scales; ++l) {
+    FlowLevelDesc& L = p.lv[l];
+    L.h = a->height[l]; L.w = a->width[l];
+    L.img_l = a->img_l[l]; L.img = a->img[l]; L.img_r = a->img_r[l];
+    L.flow_f = a->flow_fwd[l]; L.flow_b = a->flow_bwd[l];
+    L.gflow_f = backward ? a->grad_flow_fwd[l] : nullptr;
+    L.gflow_b = backward ? a->grad_flow_bwd[l] : nullptr;
+    L.tiles_x = (L.w + TW - 1) / TW;
+    L.tiles_y = (L.h + TH - 1) / TH;
+    L.tile_begin = tiles;
+    tiles += L.tiles_x * L.tiles_y * a->batch;
+  }
+  p.total_tiles = tiles;
+  p.stats = a->stats;
+  p.loss = a->loss;
+  p.gloss = a->grad_loss;
+  p.partials = nullptr;
+}
+
+extern "C" int emu_flow_loss_forward(const UglFlowLossArgs* a) {
+  FlowLossParams p;
+  fill_params<kFTW, kFTH>(a, false, p);
+  using Tile = FlowFwdTile<kFTW, kFTH>;
+  std::vector<float> partials((size_t)p.total_tiles * FA_COUNT, 0.f), sm(Tile::kSmemFloats);
+  for (int tile = 0; tile < p.total_tiles; ++tile) {
+    const TileCoord tc = decode_tile<kFTW, kFTH>(p, tile);
+    float acc[FA_COUNT] = {0};
+    Tile::phase1(p, tc, 0, 1, sm.data(), acc);
+    Tile::phase2(p, tc, 0, 1, sm.data(), acc);
+    for (int k = 0; k < FA_COUNT; ++k) partials[(size_t)tile * FA_COUNT + k] = acc[k];
+  }
+  for (int b = 0; b < p.B; ++b) {
+    float tot[4] = {0, 0, 0, 0};
+    for (int l = 0; l < p.scales; ++l) {
+      const FlowLevelDesc& L = p.lv[l];
+      const int per_img = L.tiles_x * L.tiles_y;
+      double s[FA_COUNT] = {0};
+      for (int t = 0; t < per_img; ++t)
+        for (int k = 0; k < FA_COUNT; ++k) s[k] += partials[((size_t)L.tile_begin + (size_t)b * per_img + t) * FA_COUNT + k];
+      float S[FA_COUNT], out[4];
+      for (int k = 0; k < FA_COUNT; ++k) { S[k] = (float)s[k]; p.stats[((size_t)b * p.scales + l) * FA_COUNT + k] = S[k]; }
+      flow_level_losses(S, L.h, L.w, out);
+      for (int k = 0; k < 4; ++k) tot[k] += out[k];
+    }
+    for (int k = 0; k < 4; ++k) p.loss[k * p.B + b] = tot[k];
+  }
+  return 0;
+}
+
+extern "C" int emu_flow_loss_backward(const UglFlowLossArgs* a) {
+  FlowLossParams p;
+  fill_params<kBTW, kBTH>(a, true, p);
+  using Tile = FlowBwdTile<kBTW, kBTH>;
+  std::vector<float> sm(Tile::kSmemFloats);
+  for (int tile = 0; tile < p.total_tiles; ++tile) {
+    const TileCoord tc = decode_tile<kBTW, kBTH>(p, tile);
+    const FlowLevelDesc& L = p.lv[tc.level];
+    const FlowBwdCoef k = flow_bwd_coef(p.stats + ((size_t)tc.b * p.scales + tc.level) * FA_COUNT, L.h, L.w, p.gloss, p.B, tc.b);
+    Tile::phase1(p, tc, 0, 1, sm.data());
+    Tile::phase2(p, tc, 0, 1, sm.data());
+    Tile::phase3(p, tc, k, 0, 1, sm.data());
+  }
+  return 0;
+}
+
+extern "C" int emu_image_pyramid(const float* img, int B, int C, int H, int W, int levels, int mode, float* const* out) {
+  for (int l = 1; l < levels; ++l) {
+    const int oh = H >> l, ow = W >> l;
+    for (long pl = 0; pl < (long)B * C; ++pl)
+      for (int oi = 0; oi < oh; ++oi)
+        for (int oj = 0; oj < ow; ++oj)
+          out[l][(pl * oh + oi) * ow + oj] = pyramid_pixel(img + pl * (long)H * W, W, l, mode, oi, oj);
+  }
+  return 0;
+}
+
+extern "C" int emu_warp_flow_forward(const float* x, const float* flow, int B, int C, int H, int W, int use_mask,
+                                     float* out, float* mask) {
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < H; ++i)
+      for (int j = 0; j < W; ++j) {
+        const float keep = warp_pixel_forward(x, flow, C, H, W, b, i, j, use_mask, out);
+        if (mask) mask[((long)b * H + i) * W + j] = keep;
+      }
+  return 0;
+}
+
+extern "C" int emu_warp_flow_backward(const float* x, const float* flow, const float* gout, int B, int C, int H, int W,
+                                      int use_mask, float* gflow, float* gx) {
+  const long plane = (long)H * W;
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < H; ++i)
+      for (int j = 0; j < W; ++j) warp_pixel_backward_flow(x, flow, gout, C, H, W, b, i, j, use_mask, gflow);
+  if (gx) {
+    const long nx = (long)B * C * plane;
+    float m = 0.f;
+    for (long k = 0; k < nx; ++k) { const float a = fabsf(gout[k]); if (a > m && a <= 3.0e38f) m = a; }
+    const int e = fixed_point_exponent(m, plane);
+    std::vector<long long> acc(nx, 0);
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+          const long pix = (long)i * W + j;
+          const Tap t = flow_tap(j, i, flow[((long)b * 2) * plane + pix], flow[((long)b * 2 + 1) * plane + pix], W, H);
+          const float keep = use_mask ? tap_keep(t) : 1.0f;
+          if (keep == 0.f || t.inb == 0u) continue;
+          const float wgt[4] = {t.wnw, t.wne, t.wsw, t.wse};
+          const long off[4] = {0, 1, W, (long)W + 1};
+          for (int c = 0; c < C; ++c) {
+            const float g = gout[((long)b * C + c) * plane + pix] * keep;
+            for (int k = 0; k < 4; ++k)
+              if (t.inb & (1u << k))
+                acc[((long)b * C + c) * plane + (long)t.y0 * W + t.x0 + off[k]] += llrint(ldexp((double)(g * wgt[k]), e));
+          }
+        }
+    for (long k = 0; k < nx; ++k) gx[k] = (float)ldexp((double)acc[k], -e);
+  }
+  return 0;
+}

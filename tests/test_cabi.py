@@ -1,0 +1,74 @@
+"""The C-ABI library builds, loads, and exports every symbol include/ugl.h declares (no compute
+calls here — those need a GPU); argument validation that runs before any launch is exercised too."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from unsupervised_depth_opticalflow_egomotion_b200 import _cabi, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _cabi.lib()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ugl.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ugl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib, s), "missing export: " + s
+        assert s in _cabi.SIGNATURES, "no ctypes signature for " + s
+    assert set(_cabi.SIGNATURES) == set(syms)
+
+
+def test_version(lib):
+    assert lib.ugl_version() == 100
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_struct_layout_matches_header(lib):
+    # 3 ints + 2*6 ints, then pointer arrays: the C compiler pads to 8 before the first pointer
+    a = _cabi.UglFlowLossArgs
+    assert a.height.offset == 12 and a.width.offset == 36
+    assert a.img_l.offset == 64 and a.img_l.size == 48
+    assert C.sizeof(a) == 64 + 5 * 48 + 3 * 8 + 2 * 48 + 8 + 8 + 8
+
+
+def test_argument_validation_happens_before_launch(lib):
+    a = _cabi.UglFlowLossArgs()
+    a.batch, a.levels, a.scales = 1, 1, 2            # scales > levels
+    assert lib.ugl_flow_loss_forward(C.byref(a)) == -1
+    assert b"scales" in lib.ugl_last_error()
+    a.scales = 1
+    a.height[0], a.width[0] = 2, 2                   # too small for the second-order stencil
+    assert lib.ugl_flow_loss_forward(C.byref(a)) == -4
+    a.height[0], a.width[0] = 8, 8                   # null input pointers
+    assert lib.ugl_flow_loss_forward(C.byref(a)) == -1
+    assert lib.ugl_image_pyramid(None, 1, 3, 8, 8, 2, 0, None, None) == -1
+    assert lib.ugl_warp_flow_forward(None, None, 1, 3, 8, 8, 0, None, None, None) == -1
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from unsupervised_depth_opticalflow_egomotion_b200 import ops
+    x = torch.rand(1, 3, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        ops.warp_flow(x, torch.zeros(1, 2, 8, 8))
+    with pytest.raises(ValueError, match="not equal to the shape of flow"):
+        ops.warp_flow(x, torch.zeros(1, 2, 8, 9))

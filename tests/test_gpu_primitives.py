@@ -1,0 +1,53 @@
+"""GPU parity tests of the primitive ops (warp_flow, image pyramid) through the C-ABI."""
+import pytest
+import torch
+
+from oracle import loss_port as P
+from unsupervised_depth_opticalflow_egomotion_b200 import ops
+from util import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_warp_flow_vs_reference_golden(cuda_device, use_mask):
+    d = load_golden("primitives")
+    x = d["warp_x"].to(cuda_device).requires_grad_(True)
+    flow = d["warp_flow"].to(cuda_device).requires_grad_(True)
+    out = ops.warp_flow(x, flow, use_mask)
+    gx, gf = torch.autograd.grad((out * d["warp_go"].to(cuda_device)).sum(), [x, flow])
+    tag = "warp_mask%d_" % int(use_mask)
+    assert rel_err(out, d[tag + "out"]) < 1e-6
+    assert rel_err(gf, d[tag + "grad_flow"]) < 1e-5
+    assert rel_err(gx, d[tag + "grad_x"]) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,W,px", [(2, 3, 64, 208, 8.0), (1, 32, 32, 104, 3.0), (2, 1, 17, 23, 30.0), (1, 128, 16, 52, 1.0)])
+def test_warp_flow_vs_oracle(cuda_device, B, C, H, W, px):
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    x = torch.rand(B, C, H, W, generator=g)
+    flow = px * torch.randn(B, 2, H, W, generator=g)
+    go = torch.randn(B, C, H, W, generator=g)
+    for use_mask in (False, True):
+        xc, fc = x.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+        ref = P.flow_backwarp(xc, fc, use_mask)
+        rgx, rgf = torch.autograd.grad((ref * go).sum(), [xc, fc])
+        xd, fd = x.to(cuda_device).requires_grad_(True), flow.to(cuda_device).requires_grad_(True)
+        out = ops.warp_flow(xd, fd, use_mask)
+        gx, gf = torch.autograd.grad((out * go.to(cuda_device)).sum(), [xd, fd])
+        assert rel_err(out, ref) < 1e-6
+        assert torch.equal(out.cpu() == 0, ref == 0)            # the keep mask zeroes exactly the same pixels
+        assert rel_err(gf, rgf) < 1e-5 and rel_err(gx, rgx) < 1e-5
+        gx2, = torch.autograd.grad((ops.warp_flow(xd, fd, use_mask) * go.to(cuda_device)).sum(), [xd])
+        assert torch.equal(gx, gx2)                               # deterministic scatter (no fp atomics)
+
+
+@pytest.mark.parametrize("mode", ["box", "bilinear"])
+def test_image_pyramid_bit_exact(cuda_device, mode):
+    img = torch.rand(2, 3, 256, 832, generator=torch.Generator().manual_seed(4))
+    ref = P.box_pyramid(img, 4) if mode == "box" else P.bilinear_pyramid(img, 4)
+    out = ops.image_pyramid(img.to(cuda_device), 4, mode)
+    for l in range(4):
+        assert torch.equal(out[l].cpu(), ref[l]), l
+    with pytest.raises(ValueError):
+        ops.image_pyramid(torch.rand(1, 3, 30, 64, device=cuda_device), 4, mode)

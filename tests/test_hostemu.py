@@ -1,0 +1,91 @@
+"""CPU tests of the CUDA kernels' tile logic through the host emulator (tests/hostemu/): the same
+__host__ __device__ phase functions the kernels run, driven tile by tile on the CPU and compared
+with the oracle.  The real kernels are tested on the B200 in the -m gpu files."""
+import ctypes as C
+
+import pytest
+import torch
+
+import hostemu_util as H
+from oracle import loss_port as P
+from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
+from util import load_golden, golden_triplet, rel_err, loss_rel_err, LOSS_RTOL, GRAD_RTOL
+
+KEYS = ["loss_flow_pixel", "loss_flow_ssim", "loss_flow_smooth", "loss_flow_consis"]
+
+
+def _oracle_flow(t, scales, gl):
+    for f in t.flows_fwd + t.flows_bwd:
+        f.requires_grad_(True)
+    loss = P.flow_mode_loss(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd, scales)
+    tot = sum((gl[k] * loss[KEYS[k]]).sum() for k in range(4))
+    g = torch.autograd.grad(tot, t.flows_fwd[:scales] + t.flows_bwd[:scales])
+    return loss, g[:scales], g[scales:]
+
+
+@pytest.mark.parametrize("B,Hh,W,scales,px,oob", [(2, 64, 208, 4, 6.0, 0.0), (1, 48, 80, 4, 3.0, 0.3), (2, 40, 72, 3, 1.0, 0.0),
+                                                   (1, 34, 50, 2, 2.0, 0.1)])
+def test_flow_loss_tiles_vs_oracle(B, Hh, W, scales, px, oob):
+    L = 4 if Hh % 8 == 0 else 2
+    t = make_triplet(B, Hh, W, L, 1, seed=11, flow_px=px, oob_fraction=oob)
+    gl = torch.rand(4, B, generator=torch.Generator().manual_seed(1)) + 0.5
+    loss, gf, gb = _oracle_flow(t, scales, gl)
+    pl, pc, pr = P.box_pyramid(t.img_l, L), P.box_pyramid(t.img, L), P.box_pyramid(t.img_r, L)
+    ff = [f.detach().contiguous() for f in t.flows_fwd]
+    fb = [f.detach().contiguous() for f in t.flows_bwd]
+    el, egf, egb, _ = H.emu_flow_loss(pl, pc, pr, ff, fb, scales, gl)
+    for k in range(4):
+        assert loss_rel_err(el[k], loss[KEYS[k]]) < LOSS_RTOL, KEYS[k]
+    for l in range(scales):
+        assert rel_err(egf[l], gf[l]) < GRAD_RTOL, ("fwd", l)
+        assert rel_err(egb[l], gb[l]) < GRAD_RTOL * 1.5, ("bwd", l)   # SSIM-dominated: fp32 noise of the formula itself
+
+
+def test_flow_loss_tiles_vs_golden():
+    d = load_golden("flow_mode_s4")
+    t = golden_triplet(d)
+    B = t.img.shape[0]
+    w = torch.tensor([P.FLOW_WEIGHTS[k] for k in KEYS]).view(4, 1).repeat(1, B) / B
+    pl, pc, pr = P.box_pyramid(t.img_l, 4), P.box_pyramid(t.img, 4), P.box_pyramid(t.img_r, 4)
+    el, egf, egb, _ = H.emu_flow_loss(pl, pc, pr, t.flows_fwd, t.flows_bwd, 4, w.contiguous())
+    for k in range(4):
+        assert loss_rel_err(el[k], d["out_" + KEYS[k]]) < LOSS_RTOL
+    for l in range(4):
+        assert rel_err(egf[l], d["grad_flows_fwd_%d" % l]) < GRAD_RTOL
+        assert rel_err(egb[l], d["grad_flows_bwd_%d" % l]) < GRAD_RTOL * 1.5
+
+
+def test_pyramid_pixels_bit_exact():
+    img = torch.rand(2, 3, 32, 64)
+    for mode, ref in ((0, P.box_pyramid(img, 4)), (1, P.bilinear_pyramid(img, 4))):
+        outs = [img] + [torch.empty(2, 3, 32 >> l, 64 >> l) for l in range(1, 4)]
+        arr = (C.c_void_p * 4)(*[o.data_ptr() for o in outs])
+        H.emu().emu_image_pyramid(C.c_void_p(img.data_ptr()), 2, 3, 32, 64, 4, mode, arr)
+        for l in range(1, 4):
+            assert torch.equal(outs[l], ref[l]), (mode, l)
+
+
+@pytest.mark.parametrize("use_mask", [0, 1])
+def test_warp_pixels_vs_oracle(use_mask):
+    d = load_golden("primitives")
+    x, flow, go = d["warp_x"].contiguous(), d["warp_flow"].contiguous(), d["warp_go"].contiguous()
+    B, Cc, Hh, W = x.shape
+    out, mask = torch.empty_like(x), torch.empty(B, 1, Hh, W)
+    gflow, gx = torch.empty_like(flow), torch.empty_like(x)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    H.emu().emu_warp_flow_forward(p(x), p(flow), B, Cc, Hh, W, use_mask, p(out), p(mask))
+    H.emu().emu_warp_flow_backward(p(x), p(flow), p(go), B, Cc, Hh, W, use_mask, p(gflow), p(gx))
+    tag = "warp_mask%d_" % use_mask
+    assert rel_err(out, d[tag + "out"]) < 1e-6
+    assert rel_err(gflow, d[tag + "grad_flow"]) < 1e-5
+    assert rel_err(gx, d[tag + "grad_x"]) < 1e-5
+    # the keep mask is bit-exact against the oracle's
+    with torch.no_grad():
+        cover = P.grid_sample_restated(torch.ones(B, 1, Hh, W), _grid(flow))
+    assert torch.equal(mask, (cover >= 0.9999).float() if use_mask else torch.ones_like(mask))
+
+
+def _grid(flow):
+    B, _, Hh, W = flow.shape
+    tgt = P._pixel_grid(B, Hh, W, flow) + flow
+    return torch.stack([2.0 * tgt[:, 0] / max(W - 1, 1) - 1.0, 2.0 * tgt[:, 1] / max(Hh - 1, 1) - 1.0], -1)

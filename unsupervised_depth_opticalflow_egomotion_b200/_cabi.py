@@ -1,0 +1,97 @@
+"""ctypes binding of ``libugl_b200.so`` (the C-ABI declared in ``include/ugl.h``).
+
+The library is the product: there is no CPU or pure-PyTorch fallback.  ``lib()`` raises
+``RuntimeError`` if the shared object has not been built (``python -m <pkg>.build``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+MAX_LEVELS = 6
+FLOW_NSTATS = 12
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libugl_b200.so")
+
+_fp = C.POINTER(C.c_float)
+
+
+class UglFlowLossArgs(C.Structure):
+    """Mirror of ``struct UglFlowLossArgs`` (include/ugl.h)."""
+
+    _fields_ = [
+        ("batch", C.c_int32),
+        ("levels", C.c_int32),
+        ("scales", C.c_int32),
+        ("height", C.c_int32 * MAX_LEVELS),
+        ("width", C.c_int32 * MAX_LEVELS),
+        ("img_l", C.c_void_p * MAX_LEVELS),
+        ("img", C.c_void_p * MAX_LEVELS),
+        ("img_r", C.c_void_p * MAX_LEVELS),
+        ("flow_fwd", C.c_void_p * MAX_LEVELS),
+        ("flow_bwd", C.c_void_p * MAX_LEVELS),
+        ("loss", C.c_void_p),
+        ("stats", C.c_void_p),
+        ("grad_loss", C.c_void_p),
+        ("grad_flow_fwd", C.c_void_p * MAX_LEVELS),
+        ("grad_flow_bwd", C.c_void_p * MAX_LEVELS),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_uint64),
+        ("stream", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/ugl.h declares
+SIGNATURES = {
+    "ugl_version": (C.c_int, []),
+    "ugl_last_error": (C.c_char_p, []),
+    "ugl_flow_loss_workspace_bytes": (C.c_uint64, [C.POINTER(UglFlowLossArgs)]),
+    "ugl_flow_loss_forward": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
+    "ugl_flow_loss_backward": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
+    "ugl_flow_loss_launches": (C.c_int, [C.c_int]),
+    "ugl_image_pyramid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_void_p), C.c_void_p]),
+    "ugl_warp_flow_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ugl_warp_flow_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "ugl_warp_flow_backward_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def bind(cdll: C.CDLL, signatures=SIGNATURES) -> C.CDLL:
+    for name, (res, args) in signatures.items():
+        fn = getattr(cdll, name)   # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return cdll
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the bound library; fail loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libugl_b200.so is not built (%s). Run `python -m unsupervised_depth_opticalflow_egomotion_b200.build`; "
+                "this package has no CPU / PyTorch fallback." % LIB_PATH)
+        _lib = bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+class UglError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    msg = lib().ugl_last_error()
+    text = msg.decode("utf-8", "replace") if msg else ""
+    if rc in (-1, -4):
+        raise ValueError("%s failed (%d): %s" % (what, rc, text))
+    raise UglError("%s failed (%d): %s" % (what, rc, text))

@@ -1,0 +1,233 @@
+// Shared device/host math for the photometric view-synthesis loss kernels (sm_100a).
+//
+// Everything here is `__host__ __device__` so that the per-tile logic of every kernel can also be
+// compiled by g++ into the host emulator under tests/hostemu/ (test infrastructure that checks the
+// kernels' indexing and arithmetic on the CPU-only build box; it is never linked into the shipped
+// library and the product has no CPU path).
+//
+// Arithmetic conventions (verified against the oracle):
+//  * sampling = ATen grid_sampler_2d, bilinear, zeros padding, align_corners=False
+//    (torch/include/ATen/native/GridSampler.h:27-36): ix = ((gx+1)*W-1)/2, which both the CPU
+//    (vectorised fma) and the CUDA (nvcc-contracted) builds of torch evaluate with a single
+//    rounding as fma(gx+1, W/2, -0.5).  We pin exactly that sequence with *_rn intrinsics so the
+//    bilinear cell (floor) is bit-identical to the oracle's.
+//  * coordinates that feed masks or floor() are computed with explicitly rounded operations
+//    (no compiler FMA contraction); plain loss arithmetic may be contracted.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define UGL_HD __host__ __device__ __forceinline__
+#define UGL_D __device__ __forceinline__
+#else
+#define UGL_HD inline
+#define UGL_D inline
+#endif
+
+namespace ugl {
+
+constexpr int kMaxLevels = 6;
+
+// ---- explicitly rounded fp32 ops (identical results on device and in the host emulator, which is
+// ---- compiled with -ffp-contract=off) --------------------------------------------------------
+UGL_HD float add_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b; return r;
+#endif
+}
+UGL_HD float sub_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  volatile float r = a - b; return r;
+#endif
+}
+UGL_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  volatile float r = a * b; return r;
+#endif
+}
+UGL_HD float div_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdiv_rn(a, b);
+#else
+  volatile float r = a / b; return r;
+#endif
+}
+UGL_HD float fma_rn(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+UGL_HD float sqrt_rn(float a) {
+#if defined(__CUDA_ARCH__)
+  return __fsqrt_rn(a);
+#else
+  return sqrtf(a);
+#endif
+}
+UGL_HD float sgnf(float v) { return (float)((v > 0.f) - (v < 0.f)); }
+
+// ---- bilinear footprint ------------------------------------------------------------------------
+// One backward-warp lookup: the nw corner, the four weights and which corners are inside the image.
+struct Tap {
+  int x0, y0;                 // nw corner (may be out of range)
+  float wnw, wne, wsw, wse;   // (x1-ix)(y1-iy), (ix-x0)(y1-iy), (x1-ix)(iy-y0), (ix-x0)(iy-y0)
+  float tx, ty;               // ix-x0, iy-y0
+  unsigned inb;               // bit0 nw, bit1 ne, bit2 sw, bit3 se inside the image
+};
+
+// un-normalise a [-1,1] coordinate exactly like ATen (see header comment)
+UGL_HD float unnormalize(float g, int size) { return fma_rn(add_rn(g, 1.0f), 0.5f * (float)size, -0.5f); }
+
+UGL_HD Tap make_tap(float ix, float iy, int W, int H) {
+  Tap t;
+  // guard the float->int conversion (ATen's is UB for huge values; everything out there is zeros)
+  const bool sane = (ix > -2.0f) && (ix < (float)W + 1.0f) && (iy > -2.0f) && (iy < (float)H + 1.0f);
+  const float fx = sane ? floorf(ix) : -2.0f;
+  const float fy = sane ? floorf(iy) : -2.0f;
+  t.x0 = (int)fx;
+  t.y0 = (int)fy;
+  const float ex = sane ? ix : -2.0f, ey = sane ? iy : -2.0f;
+  t.tx = ex - fx;
+  t.ty = ey - fy;
+  const float ox = (fx + 1.0f) - ex, oy = (fy + 1.0f) - ey;
+  t.wnw = ox * oy;
+  t.wne = t.tx * oy;
+  t.wsw = ox * t.ty;
+  t.wse = t.tx * t.ty;
+  const bool xl = (t.x0 >= 0) && (t.x0 < W), xr = (t.x0 + 1 >= 0) && (t.x0 + 1 < W);
+  const bool yt = (t.y0 >= 0) && (t.y0 < H), yb = (t.y0 + 1 >= 0) && (t.y0 + 1 < H);
+  t.inb = (unsigned)(xl && yt) | ((unsigned)(xr && yt) << 1) | ((unsigned)(xl && yb) << 2) | ((unsigned)(xr && yb) << 3);
+  return t;
+}
+
+// structures/net_utils.py:39-46: target (j+u, i+v) -> normalised with (W-1) -> un-normalised with W.
+// Each Python-level op of the reference rounds to fp32, so every step here is an explicit *_rn op.
+UGL_HD Tap flow_tap(int j, int i, float u, float v, int W, int H) {
+  const float dw = (float)(W - 1 > 1 ? W - 1 : 1), dh = (float)(H - 1 > 1 ? H - 1 : 1);
+  const float gx = sub_rn(div_rn(mul_rn(2.0f, add_rn((float)j, u)), dw), 1.0f);
+  const float gy = sub_rn(div_rn(mul_rn(2.0f, add_rn((float)i, v)), dh), 1.0f);
+  return make_tap(unnormalize(gx, W), unnormalize(gy, H), W, H);
+}
+
+// coverage of a ones-image = sum of the in-bounds weights in corner order nw, ne, sw, se
+UGL_HD float tap_coverage(const Tap& t) {
+  float s = 0.f;
+  if (t.inb & 1u) s = add_rn(s, t.wnw);
+  if (t.inb & 2u) s = add_rn(s, t.wne);
+  if (t.inb & 4u) s = add_rn(s, t.wsw);
+  if (t.inb & 8u) s = add_rn(s, t.wse);
+  return s;
+}
+
+// structures/net_utils.py:47-51: keep = [coverage >= 0.9999]
+UGL_HD float tap_keep(const Tap& t) { return tap_coverage(t) >= 0.9999f ? 1.0f : 0.0f; }
+
+struct Corners { float nw, ne, sw, se; };
+
+UGL_HD Corners tap_fetch(const float* __restrict__ plane, int W, const Tap& t) {
+  Corners c;
+  const float* p = plane + (long)t.y0 * W + t.x0;
+  c.nw = (t.inb & 1u) ? p[0] : 0.f;
+  c.ne = (t.inb & 2u) ? p[1] : 0.f;
+  c.sw = (t.inb & 4u) ? p[W] : 0.f;
+  c.se = (t.inb & 8u) ? p[W + 1] : 0.f;
+  return c;
+}
+
+UGL_HD float corners_value(const Corners& c, const Tap& t) {
+  float o = c.nw * t.wnw;
+  o += c.ne * t.wne;
+  o += c.sw * t.wsw;
+  o += c.se * t.wse;
+  return o;
+}
+// d value / d ix and d value / d iy (ATen grid_sampler_2d_backward: out-of-range corners count as 0)
+UGL_HD float corners_ddx(const Corners& c, const Tap& t) { return (c.ne - c.nw) * (1.0f - t.ty) + (c.se - c.sw) * t.ty; }
+UGL_HD float corners_ddy(const Corners& c, const Tap& t) { return (c.sw - c.nw) * (1.0f - t.tx) + (c.se - c.ne) * t.tx; }
+
+// ---- SSIM (pytorch_ssim/ssim.py:4-19) ----------------------------------------------------------
+constexpr float kC1 = 0.0001f;   // 0.01^2
+constexpr float kC2 = 0.0009f;   // 0.03^2
+
+struct Moments { float sx, sy, sxx, syy, sxy; };   // 3x3 window sums (not yet divided by 9)
+
+// One window tap.  Every step is explicitly rounded so the sums equal ATen's avg_pool2d
+// accumulation (row-major over the window, fp32) of the separately rounded x*x, y*y, x*y tensors.
+UGL_HD void moments_add(Moments& m, float x, float y) {
+  m.sx = add_rn(m.sx, x);
+  m.sy = add_rn(m.sy, y);
+  m.sxx = add_rn(m.sxx, mul_rn(x, x));
+  m.syy = add_rn(m.syy, mul_rn(y, y));
+  m.sxy = add_rn(m.sxy, mul_rn(x, y));
+}
+
+// The SSIM terms in the reference's own operation order (ssim.py:8-18), each op rounded to fp32:
+// cancellation in E[x^2]-mu^2 amplifies any re-association, so this is pinned, not contracted.
+struct SsimTerms { float mx, my, n1, n2, d1, d2, S; };
+
+UGL_HD SsimTerms ssim_terms(const Moments& m) {
+  SsimTerms t;
+  t.mx = div_rn(m.sx, 9.0f);
+  t.my = div_rn(m.sy, 9.0f);
+  const float mxx = mul_rn(t.mx, t.mx), myy = mul_rn(t.my, t.my), mxy = mul_rn(t.mx, t.my);
+  const float vx = sub_rn(div_rn(m.sxx, 9.0f), mxx);
+  const float vy = sub_rn(div_rn(m.syy, 9.0f), myy);
+  const float cxy = sub_rn(div_rn(m.sxy, 9.0f), mxy);
+  t.n1 = add_rn(mul_rn(mul_rn(2.0f, t.mx), t.my), kC1);
+  t.n2 = add_rn(mul_rn(2.0f, cxy), kC2);
+  t.d1 = add_rn(add_rn(mxx, myy), kC1);
+  t.d2 = add_rn(add_rn(vx, vy), kC2);
+  t.S = div_rn(mul_rn(t.n1, t.n2), mul_rn(t.d1, t.d2));
+  return t;
+}
+
+UGL_HD float ssim_from_sums(const Moments& m) { return ssim_terms(m).S; }
+
+// loss value clamp((1-S)/2, 0, 1)
+UGL_HD float ssim_loss_value(float S) {
+  const float v = div_rn(sub_rn(1.0f, S), 2.0f);
+  return v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+}
+// d S / d(mu_x), d(E[x^2]), d(mu_y), d(E[y^2]), d(E[xy]) of one window, scaled by g.
+UGL_HD void ssim_partials(const SsimTerms& t, float g, float& ax, float& bx, float& ay, float& by, float& cxy) {
+  const float invD = g / (t.d1 * t.d2);
+  ax = (2.f * t.my * (t.n2 - t.n1) - t.S * 2.f * t.mx * (t.d2 - t.d1)) * invD;
+  ay = (2.f * t.mx * (t.n2 - t.n1) - t.S * 2.f * t.my * (t.d2 - t.d1)) * invD;
+  bx = by = (-t.S * t.d1) * invD;
+  cxy = (2.f * t.n1) * invD;
+}
+// Given window sums, produce g * dS/d(mu_y), g * dS/d(E[y^2]), g * dS/d(E[xy]) where g = d loss / dS
+// (= -1/2 inside the clamp range [0,1] inclusive, 0 outside — torch.clamp backward).
+UGL_HD void ssim_backward_coeffs(const Moments& m, float& cA, float& cB, float& cC) {
+  const SsimTerms t = ssim_terms(m);
+  const float v = div_rn(sub_rn(1.0f, t.S), 2.0f);
+  const float g = (v >= 0.f && v <= 1.f) ? -0.5f : 0.f;
+  float ax, bx;
+  ssim_partials(t, g, ax, bx, cA, cB, cC);
+}
+
+// ---- soft / hard occlusion weights (model_flow.py:105-138, model_geometry.py:105-132) ----------
+// wgt = 1 - softmax([d_l, d_r]) evaluated like ATen's softmax: exp(x - max) / sum.
+UGL_HD void one_minus_softmax2(float d_l, float d_r, float& wl, float& wr) {
+  const float m = d_l > d_r ? d_l : d_r;
+  const float el = expf(sub_rn(d_l, m)), er = expf(sub_rn(d_r, m));
+  const float s = add_rn(el, er);
+  wl = sub_rn(1.0f, div_rn(el, s));
+  wr = sub_rn(1.0f, div_rn(er, s));
+}
+UGL_HD float soft_occ_weight(float wgt) {   // 2*exp(-(wgt-0.5)^2/0.03)
+  const float c = wgt - 0.5f;
+  return 2.0f * expf(-(c * c) / 0.03f);
+}
+
+}  // namespace ugl

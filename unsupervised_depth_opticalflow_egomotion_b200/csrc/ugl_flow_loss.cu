@@ -1,0 +1,168 @@
+// CUDA kernels + C-ABI for the fused flow-mode loss (see ugl_flow_loss.cuh for the math and the
+// reference citations).  Three launches per training step: forward, finalize, backward.
+#include "ugl_flow_loss.cuh"
+#include "ugl_host.cuh"
+
+namespace ugl {
+
+constexpr int kFNT = 256;   // forward  threads per CTA (one CTA per tile)
+constexpr int kBNT = 256;   // backward threads per CTA
+
+template <int TW, int TH, int NT>
+__global__ void __launch_bounds__(NT) flow_loss_fwd_kernel(const __grid_constant__ FlowLossParams p) {
+  extern __shared__ float sm[];
+  __shared__ float red[(NT / 32) * FA_COUNT];
+  using Tile = FlowFwdTile<TW, TH>;
+  const int tile = blockIdx.x;
+  const TileCoord tc = decode_tile<TW, TH>(p, tile);
+  float acc[FA_COUNT];
+#pragma unroll
+  for (int k = 0; k < FA_COUNT; ++k) acc[k] = 0.f;
+  Tile::phase1(p, tc, threadIdx.x, NT, sm, acc);
+  __syncthreads();
+  Tile::phase2(p, tc, threadIdx.x, NT, sm, acc);
+  const float v = block_reduce_n<NT, FA_COUNT>(acc, red);
+  if (threadIdx.x < FA_COUNT) p.partials[(long)tile * FA_COUNT + threadIdx.x] = v;
+}
+
+// one CTA per sample, one warp per level: ordered (deterministic) fp64 sum of the tile partials
+__global__ void flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p) {
+  __shared__ float lvl_loss[kMaxLevels][4];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, l = threadIdx.x >> 5;
+  if (l < p.scales) {
+    const FlowLevelDesc& L = p.lv[l];
+    const int per_img = L.tiles_x * L.tiles_y;
+    const float* base = p.partials + ((long)L.tile_begin + (long)b * per_img) * FA_COUNT;
+    double s[FA_COUNT];
+#pragma unroll
+    for (int k = 0; k < FA_COUNT; ++k) s[k] = 0.0;
+    for (int t = lane; t < per_img; t += 32) {
+#pragma unroll
+      for (int k = 0; k < FA_COUNT; ++k) s[k] += (double)base[(long)t * FA_COUNT + k];
+    }
+    float S[FA_COUNT];
+#pragma unroll
+    for (int k = 0; k < FA_COUNT; ++k) {
+      double v = s[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      S[k] = (float)__shfl_sync(0xffffffffu, v, 0);
+    }
+    if (lane == 0) {
+      float* st = p.stats + ((long)b * p.scales + l) * FA_COUNT;
+#pragma unroll
+      for (int k = 0; k < FA_COUNT; ++k) st[k] = S[k];
+      float out[4];
+      flow_level_losses(S, L.h, L.w, out);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lvl_loss[l][k] = out[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float t = 0.f;
+    for (int l2 = 0; l2 < p.scales; ++l2) t += lvl_loss[l2][threadIdx.x];
+    p.loss[threadIdx.x * p.B + b] = t;
+  }
+}
+
+template <int TW, int TH, int NT>
+__global__ void __launch_bounds__(NT) flow_loss_bwd_kernel(const __grid_constant__ FlowLossParams p) {
+  extern __shared__ float sm[];
+  using Tile = FlowBwdTile<TW, TH>;
+  const int tile = blockIdx.x;
+  const TileCoord tc = decode_tile<TW, TH>(p, tile);
+  const FlowLevelDesc& L = p.lv[tc.level];
+  const FlowBwdCoef k = flow_bwd_coef(p.stats + ((long)tc.b * p.scales + tc.level) * FA_COUNT, L.h, L.w, p.gloss, p.B, tc.b);
+  Tile::phase1(p, tc, threadIdx.x, NT, sm);
+  __syncthreads();
+  Tile::phase2(p, tc, threadIdx.x, NT, sm);
+  __syncthreads();
+  Tile::phase3(p, tc, k, threadIdx.x, NT, sm);
+}
+
+// ---- host side --------------------------------------------------------------------------------
+template <int TW, int TH>
+static int build_params(const UglFlowLossArgs* a, bool backward, FlowLossParams& p) {
+  if (!a) return fail(UGL_EINVAL, "flow_loss: null args");
+  if (a->batch <= 0 || a->levels <= 0 || a->levels > UGL_MAX_LEVELS || a->scales <= 0 || a->scales > a->levels)
+    return fail(UGL_EINVAL, "flow_loss: bad batch/levels/scales (%d/%d/%d)", a->batch, a->levels, a->scales);
+  p.B = a->batch;
+  p.scales = a->scales;
+  int tiles = 0;
+  for (int l = 0; l < a->scales; ++l) {
+    FlowLevelDesc& L = p.lv[l];
+    L.h = a->height[l];
+    L.w = a->width[l];
+    if (L.h < 3 || L.w < 3) return fail(UGL_EUNSUPPORTED, "flow_loss: level %d is %dx%d; need >= 3x3", l, L.h, L.w);
+    const void* ptrs[5] = {a->img_l[l], a->img[l], a->img_r[l], a->flow_fwd[l], a->flow_bwd[l]};
+    for (int k = 0; k < 5; ++k) {
+      if (!ptrs[k]) return fail(UGL_EINVAL, "flow_loss: null input pointer at level %d", l);
+      if (!aligned4(ptrs[k])) return fail(UGL_EALIGN, "flow_loss: misaligned input pointer at level %d", l);
+    }
+    L.img_l = a->img_l[l]; L.img = a->img[l]; L.img_r = a->img_r[l];
+    L.flow_f = a->flow_fwd[l]; L.flow_b = a->flow_bwd[l];
+    L.gflow_f = backward ? a->grad_flow_fwd[l] : nullptr;
+    L.gflow_b = backward ? a->grad_flow_bwd[l] : nullptr;
+    if (backward && (!L.gflow_f || !L.gflow_b)) return fail(UGL_EINVAL, "flow_loss: null grad_flow pointer at level %d", l);
+    L.tiles_x = (L.w + TW - 1) / TW;
+    L.tiles_y = (L.h + TH - 1) / TH;
+    L.tile_begin = tiles;
+    tiles += L.tiles_x * L.tiles_y * a->batch;
+  }
+  p.total_tiles = tiles;
+  if (!a->stats) return fail(UGL_EINVAL, "flow_loss: null stats");
+  p.stats = a->stats;
+  p.loss = a->loss;
+  p.gloss = a->grad_loss;
+  p.partials = static_cast<float*>(a->workspace);
+  return UGL_OK;
+}
+
+}  // namespace ugl
+
+using namespace ugl;
+
+extern "C" uint64_t ugl_flow_loss_workspace_bytes(const UglFlowLossArgs* a) {
+  if (!a) return 0;
+  uint64_t tiles = 0;   // only the shapes matter here
+  for (int l = 0; l < a->scales && l < UGL_MAX_LEVELS; ++l)
+    tiles += (uint64_t)((a->width[l] + kFTW - 1) / kFTW) * ((a->height[l] + kFTH - 1) / kFTH) * a->batch;
+  return tiles * FA_COUNT * sizeof(float);
+}
+
+extern "C" int ugl_flow_loss_launches(int backward) { return backward ? 1 : 2; }
+
+extern "C" int ugl_flow_loss_forward(const UglFlowLossArgs* a) {
+  FlowLossParams p;
+  int rc = build_params<kFTW, kFTH>(a, false, p);
+  if (rc) return rc;
+  if (!a->loss) return fail(UGL_EINVAL, "flow_loss_forward: null loss");
+  if (!a->workspace || a->workspace_bytes < (uint64_t)p.total_tiles * FA_COUNT * sizeof(float))
+    return fail(UGL_EWORKSPACE, "flow_loss_forward: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  using Tile = FlowFwdTile<kFTW, kFTH>;
+  constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
+  auto kern = flow_loss_fwd_kernel<kFTW, kFTH, kFNT>;
+  static_assert(smem <= 227 * 1024, "forward tile does not fit in shared memory");
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<p.total_tiles, kFNT, smem, st>>>(p);
+  if ((rc = check_launch("flow_loss_fwd_kernel"))) return rc;
+  flow_loss_finalize_kernel<<<p.B, 32 * kMaxLevels, 0, st>>>(p);
+  return check_launch("flow_loss_finalize_kernel");
+}
+
+extern "C" int ugl_flow_loss_backward(const UglFlowLossArgs* a) {
+  FlowLossParams p;
+  int rc = build_params<kBTW, kBTH>(a, true, p);
+  if (rc) return rc;
+  if (!a->grad_loss) return fail(UGL_EINVAL, "flow_loss_backward: null grad_loss");
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  using Tile = FlowBwdTile<kBTW, kBTH>;
+  constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
+  static_assert(smem <= 227 * 1024, "backward tile does not fit in shared memory");
+  auto kern = flow_loss_bwd_kernel<kBTW, kBTH, kBNT>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<p.total_tiles, kBNT, smem, st>>>(p);
+  return check_launch("flow_loss_bwd_kernel");
+}

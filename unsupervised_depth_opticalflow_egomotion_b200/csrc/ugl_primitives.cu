@@ -1,0 +1,170 @@
+// Primitive ops behind the reference's free functions: image pyramid and warp_flow (forward,
+// d/d flow, deterministic d/d x).  See include/ugl.h for the C-ABI contract.
+#include "ugl_host.cuh"
+#include "ugl_primitives.cuh"
+
+namespace ugl {
+
+constexpr int kPrimThreads = 256;
+
+__global__ void __launch_bounds__(kPrimThreads)
+pyramid_kernel(const float* __restrict__ img, int planes, int H, int W, int l, int mode, float* __restrict__ out) {
+  const int oh = H >> l, ow = W >> l;
+  const long n = (long)planes * oh * ow;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    const int oj = (int)(idx % ow);
+    const long r = idx / ow;
+    const int oi = (int)(r % oh);
+    const long pl = r / oh;
+    out[idx] = pyramid_pixel(img + pl * (long)H * W, W, l, mode, oi, oj);
+  }
+}
+
+__global__ void __launch_bounds__(kPrimThreads)
+warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow, int B, int C, int H, int W, int use_mask,
+                float* __restrict__ out, float* __restrict__ mask) {
+  const long n = (long)B * H * W;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % W);
+    const long r = idx / W;
+    const int i = (int)(r % H), b = (int)(r / H);
+    const float keep = warp_pixel_forward(x, flow, C, H, W, b, i, j, use_mask, out);
+    if (mask) mask[idx] = keep;
+  }
+}
+
+__global__ void __launch_bounds__(kPrimThreads)
+warp_bwd_flow_kernel(const float* __restrict__ x, const float* __restrict__ flow, const float* __restrict__ gout, int B,
+                     int C, int H, int W, int use_mask, float* __restrict__ gflow) {
+  const long n = (long)B * H * W;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % W);
+    const long r = idx / W;
+    const int i = (int)(r % H), b = (int)(r / H);
+    warp_pixel_backward_flow(x, flow, gout, C, H, W, b, i, j, use_mask, gflow);
+  }
+}
+
+// max |grad_out| as the bit pattern of a non-negative float (unsigned order == float order)
+__global__ void __launch_bounds__(kPrimThreads) absmax_kernel(const float* __restrict__ g, long n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    const float a = fabsf(g[idx]);
+    m = (a > m && a <= 3.0e38f) ? a : m;   // ignores NaN/inf (they poison the result anyway)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+__global__ void __launch_bounds__(kPrimThreads)
+warp_bwd_scatter_kernel(const float* __restrict__ flow, const float* __restrict__ gout, int B, int C, int H, int W,
+                        int use_mask, const unsigned* __restrict__ maxbits, unsigned long long* __restrict__ acc) {
+  const long n = (long)B * H * W, plane = (long)H * W;
+  const int e = fixed_point_exponent(__uint_as_float(*maxbits), plane);
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % W);
+    const long r = idx / W;
+    const int i = (int)(r % H), b = (int)(r / H);
+    const long pix = (long)i * W + j;
+    const float u = flow[((long)b * 2) * plane + pix], v = flow[((long)b * 2 + 1) * plane + pix];
+    const Tap t = flow_tap(j, i, u, v, W, H);
+    const float keep = use_mask ? tap_keep(t) : 1.0f;
+    if (keep == 0.f || t.inb == 0u) continue;
+    const float wgt[4] = {t.wnw, t.wne, t.wsw, t.wse};
+    const long off[4] = {0, 1, W, (long)W + 1};
+    const long base = (long)t.y0 * W + t.x0;
+    for (int c = 0; c < C; ++c) {
+      const float g = gout[((long)b * C + c) * plane + pix] * keep;
+      unsigned long long* a = acc + ((long)b * C + c) * plane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (t.inb & (1u << k)) {
+          const long long q = __double2ll_rn(ldexp((double)(g * wgt[k]), e));
+          atomicAdd(a + base + off[k], (unsigned long long)q);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPrimThreads)
+fixed_to_float_kernel(const unsigned long long* __restrict__ acc, long n, long plane, const unsigned* __restrict__ maxbits,
+                      float* __restrict__ out) {
+  const int e = fixed_point_exponent(__uint_as_float(*maxbits), plane);
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x)
+    out[idx] = (float)ldexp((double)(long long)acc[idx], -e);
+}
+
+static int grid_for(long n) {
+  long g = (n + kPrimThreads - 1) / kPrimThreads;
+  const long cap = 148L * 16;   // 148 SMs x a few resident CTAs, grid-stride beyond that
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace ugl
+
+using namespace ugl;
+
+extern "C" int ugl_image_pyramid(const float* img, int32_t B, int32_t C, int32_t H, int32_t W, int32_t levels,
+                                 int32_t mode, float* const* out, void* stream) {
+  if (!img || !out) return fail(UGL_EINVAL, "image_pyramid: null pointer");
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || levels < 1 || levels > UGL_MAX_LEVELS || (mode != 0 && mode != 1))
+    return fail(UGL_EINVAL, "image_pyramid: bad arguments");
+  const int f = 1 << (levels - 1);
+  if (H % f || W % f) return fail(UGL_EUNSUPPORTED, "image_pyramid: %dx%d not divisible by 2^%d", H, W, levels - 1);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int l = 1; l < levels; ++l) {
+    if (!out[l]) return fail(UGL_EINVAL, "image_pyramid: null output for level %d", l);
+    const long n = (long)B * C * (H >> l) * (W >> l);
+    pyramid_kernel<<<grid_for(n), kPrimThreads, 0, st>>>(img, B * C, H, W, l, mode, out[l]);
+    int rc = check_launch("pyramid_kernel");
+    if (rc) return rc;
+  }
+  return UGL_OK;
+}
+
+extern "C" int ugl_warp_flow_forward(const float* x, const float* flow, int32_t B, int32_t C, int32_t H, int32_t W,
+                                     int32_t use_mask, float* out, float* mask, void* stream) {
+  if (!x || !flow || !out) return fail(UGL_EINVAL, "warp_flow_forward: null pointer");
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(UGL_EINVAL, "warp_flow_forward: bad shape");
+  const long n = (long)B * H * W;
+  warp_fwd_kernel<<<grid_for(n), kPrimThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, flow, B, C, H, W, use_mask, out, mask);
+  return check_launch("warp_fwd_kernel");
+}
+
+extern "C" uint64_t ugl_warp_flow_backward_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W, int32_t need_grad_x) {
+  if (!need_grad_x) return 0;
+  return (uint64_t)B * C * H * W * sizeof(unsigned long long) + 256;
+}
+
+extern "C" int ugl_warp_flow_backward(const float* x, const float* flow, const float* grad_out, int32_t B, int32_t C,
+                                      int32_t H, int32_t W, int32_t use_mask, float* grad_flow, float* grad_x,
+                                      void* workspace, uint64_t workspace_bytes, void* stream) {
+  if (!x || !flow || !grad_out) return fail(UGL_EINVAL, "warp_flow_backward: null pointer");
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(UGL_EINVAL, "warp_flow_backward: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long n = (long)B * H * W;
+  int rc;
+  if (grad_flow) {
+    warp_bwd_flow_kernel<<<grid_for(n), kPrimThreads, 0, st>>>(x, flow, grad_out, B, C, H, W, use_mask, grad_flow);
+    if ((rc = check_launch("warp_bwd_flow_kernel"))) return rc;
+  }
+  if (grad_x) {
+    const uint64_t need = ugl_warp_flow_backward_workspace_bytes(B, C, H, W, 1);
+    if (!workspace || workspace_bytes < need) return fail(UGL_EWORKSPACE, "warp_flow_backward: workspace too small");
+    if (reinterpret_cast<uintptr_t>(workspace) & 7u) return fail(UGL_EALIGN, "warp_flow_backward: workspace not 8-byte aligned");
+    const long nx = (long)B * C * H * W;
+    unsigned long long* acc = static_cast<unsigned long long*>(workspace);
+    unsigned* maxbits = reinterpret_cast<unsigned*>(acc + nx);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
+    if (e != cudaSuccess) return fail((int)e, "warp_flow_backward: memset: %s", cudaGetErrorString(e));
+    absmax_kernel<<<grid_for(nx), kPrimThreads, 0, st>>>(grad_out, nx, maxbits);
+    if ((rc = check_launch("absmax_kernel"))) return rc;
+    warp_bwd_scatter_kernel<<<grid_for(n), kPrimThreads, 0, st>>>(flow, grad_out, B, C, H, W, use_mask, maxbits, acc);
+    if ((rc = check_launch("warp_bwd_scatter_kernel"))) return rc;
+    fixed_to_float_kernel<<<grid_for(nx), kPrimThreads, 0, st>>>(acc, nx, (long)H * W, maxbits, grad_x);
+    if ((rc = check_launch("fixed_to_float_kernel"))) return rc;
+  }
+  return UGL_OK;
+}

@@ -1,0 +1,75 @@
+// Per-pixel logic of the primitive ops (pyramid, warp_flow) as host/device functions, shared by
+// ugl_primitives.cu and the host emulator.
+#pragma once
+
+#include "ugl_common.cuh"
+
+namespace ugl {
+
+// ---- image pyramid -------------------------------------------------------------------------------
+// mode 0: box mean of the 2^l x 2^l block, accumulated row-major then divided by the count
+//         (adaptive_avg_pool2d / interpolate 'area'; model_flow.py:62, model_geometry.py:91).
+// mode 1: bilinear align_corners=False at an exact power-of-two ratio = the central 2x2 of the block
+//         with weights 1/4 (model_geometry.py:70).
+UGL_HD float pyramid_pixel(const float* __restrict__ plane, int W, int l, int mode, int oi, int oj) {
+  const int f = 1 << l;
+  if (mode == 0) {
+    float s = 0.f;
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) s = add_rn(s, plane[(long)(oi * f + dy) * W + (oj * f + dx)]);
+    return div_rn(s, (float)(f * f));
+  }
+  const int y = oi * f + f / 2 - 1, x = oj * f + f / 2 - 1;
+  const float* p = plane + (long)y * W + x;
+  // ATen's CPU upsample_bilinear2d accumulates the four 1/4-weighted taps sequentially (probed bit-exact)
+  return add_rn(add_rn(add_rn(mul_rn(0.25f, p[0]), mul_rn(0.25f, p[1])), mul_rn(0.25f, p[W])), mul_rn(0.25f, p[W + 1]));
+}
+
+// ---- warp_flow (structures/net_utils.py:16-54) ------------------------------------------------------
+// forward for one pixel, all channels; returns the keep value (1 when use_mask == 0)
+UGL_HD float warp_pixel_forward(const float* __restrict__ x, const float* __restrict__ flow, int C, int H, int W,
+                                int b, int i, int j, int use_mask, float* __restrict__ out) {
+  const long plane = (long)H * W, pix = (long)i * W + j;
+  const float u = flow[((long)b * 2) * plane + pix], v = flow[((long)b * 2 + 1) * plane + pix];
+  const Tap t = flow_tap(j, i, u, v, W, H);
+  const float keep = use_mask ? tap_keep(t) : 1.0f;
+  for (int c = 0; c < C; ++c) {
+    const Corners k = tap_fetch(x + ((long)b * C + c) * plane, W, t);
+    const float val = corners_value(k, t);
+    out[((long)b * C + c) * plane + pix] = use_mask ? val * keep : val;
+  }
+  return keep;
+}
+
+// backward w.r.t. the flow for one pixel
+UGL_HD void warp_pixel_backward_flow(const float* __restrict__ x, const float* __restrict__ flow,
+                                     const float* __restrict__ gout, int C, int H, int W, int b, int i, int j,
+                                     int use_mask, float* __restrict__ gflow) {
+  const long plane = (long)H * W, pix = (long)i * W + j;
+  const float u = flow[((long)b * 2) * plane + pix], v = flow[((long)b * 2 + 1) * plane + pix];
+  const Tap t = flow_tap(j, i, u, v, W, H);
+  const float keep = use_mask ? tap_keep(t) : 1.0f;
+  float gx = 0.f, gy = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const Corners k = tap_fetch(x + ((long)b * C + c) * plane, W, t);
+    const float g = gout[((long)b * C + c) * plane + pix] * keep;
+    gx += g * corners_ddx(k, t);
+    gy += g * corners_ddy(k, t);
+  }
+  const float sx = (float)W / (float)(W - 1 > 1 ? W - 1 : 1), sy = (float)H / (float)(H - 1 > 1 ? H - 1 : 1);
+  gflow[((long)b * 2) * plane + pix] = gx * sx;
+  gflow[((long)b * 2 + 1) * plane + pix] = gy * sy;
+}
+
+// Fixed-point encoding for the deterministic scatter of d loss / d x: integer addition is
+// associative, so the accumulated value does not depend on the order in which threads arrive.
+// scale = 2^e chosen from max|grad_out| so that H*W worst-case contributions cannot overflow 63 bits.
+UGL_HD int fixed_point_exponent(float max_abs, long n_contrib) {
+  if (!(max_abs > 0.f)) return 0;
+  int e_max, e_cnt;
+  frexpf(max_abs, &e_max);                       // max_abs < 2^e_max
+  frexpf((float)n_contrib, &e_cnt);              // n_contrib < 2^e_cnt
+  return 61 - e_max - e_cnt;                     // |sum| * 2^e < 2^61
+}
+
+}  // namespace ugl
