@@ -184,15 +184,21 @@ def main():
     wmat = weight_matrix(FLOW_WEIGHTS, ops.FLOW_LOSS_KEYS, B, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    state = {"out": None}
+
     def step():
-        loss = ops.flow_loss(pl, pc, pr, ff, fb, LEVELS, as_matrix=True)
-        grads = torch.autograd.grad(loss, ff + fb, grad_outputs=wmat)
-        return loss, grads
+        # forward + finalize + backward with d total / d loss = w_k / B (train.py:211-215): 3 launches
+        state["out"] = ops.flow_loss_step(pl, pc, pr, ff, fb, wmat, LEVELS, out=state["out"])
+        return state["out"]
 
     n0 = ops.LAUNCH_COUNTER["n"]
-    loss, grads = step()
+    res = step()
     launches_per_step = ops.LAUNCH_COUNTER["n"] - n0
     torch.cuda.synchronize()
+    # the autograd surface must give the same numbers as the direct step
+    chk = ops.flow_loss(pl, pc, pr, ff, fb, LEVELS, as_matrix=True)
+    chk_g = torch.autograd.grad(chk, ff + fb, grad_outputs=wmat)
+    assert torch.equal(chk, res["loss"]) and all(torch.equal(a, b) for a, b in zip(chk_g, res["gf"] + res["gb"]))
 
     graph = None
     if not args.no_graph:
@@ -205,7 +211,7 @@ def main():
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                loss, grads = step()
+                step()
         except Exception as e:   # pragma: no cover - reported in the JSON line
             graph = None
             sys.stderr.write("CUDA graph capture failed, timing eager launches: %r\n" % (e,))

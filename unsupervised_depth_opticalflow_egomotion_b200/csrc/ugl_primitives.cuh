@@ -21,17 +21,22 @@ UGL_HD float pyramid_pixel(const float* __restrict__ plane, int W, int l, int mo
   }
   const int y = oi * f + f / 2 - 1, x = oj * f + f / 2 - 1;
   const float* p = plane + (long)y * W + x;
-  // ATen's CPU upsample_bilinear2d accumulates the four 1/4-weighted taps sequentially (probed bit-exact)
-  return add_rn(add_rn(add_rn(mul_rn(0.25f, p[0]), mul_rn(0.25f, p[1])), mul_rn(0.25f, p[W])), mul_rn(0.25f, p[W + 1]));
+  // Horizontal lerp, then vertical: the order of ATen's CUDA kernel and of its vectorised multi-threaded CPU
+  // kernel at production sizes.  (ATen's CPU result is itself not bit-stable: small or single-threaded
+  // calls take a path that accumulates the four taps sequentially and differs in the last ulp.)
+  const float top = add_rn(mul_rn(0.5f, p[0]), mul_rn(0.5f, p[1]));
+  const float bot = add_rn(mul_rn(0.5f, p[W]), mul_rn(0.5f, p[W + 1]));
+  return add_rn(mul_rn(0.5f, top), mul_rn(0.5f, bot));
 }
 
 // ---- warp_flow (structures/net_utils.py:16-54) ------------------------------------------------------
 // forward for one pixel, all channels; returns the keep value (1 when use_mask == 0)
-UGL_HD float warp_pixel_forward(const float* __restrict__ x, const float* __restrict__ flow, int C, int H, int W,
+UGL_HD float warp_pixel_forward(const float* __restrict__ x, const float* __restrict__ flow, int C, const WarpGeom& geom,
                                 int b, int i, int j, int use_mask, float* __restrict__ out) {
+  const int H = geom.H, W = geom.W;
   const long plane = (long)H * W, pix = (long)i * W + j;
   const float u = flow[((long)b * 2) * plane + pix], v = flow[((long)b * 2 + 1) * plane + pix];
-  const Tap t = flow_tap(j, i, u, v, W, H);
+  const Tap t = flow_tap(j, i, u, v, geom);
   const float keep = use_mask ? tap_keep(t) : 1.0f;
   for (int c = 0; c < C; ++c) {
     const Corners k = tap_fetch(x + ((long)b * C + c) * plane, W, t);
@@ -43,11 +48,12 @@ UGL_HD float warp_pixel_forward(const float* __restrict__ x, const float* __rest
 
 // backward w.r.t. the flow for one pixel
 UGL_HD void warp_pixel_backward_flow(const float* __restrict__ x, const float* __restrict__ flow,
-                                     const float* __restrict__ gout, int C, int H, int W, int b, int i, int j,
+                                     const float* __restrict__ gout, int C, const WarpGeom& geom, int b, int i, int j,
                                      int use_mask, float* __restrict__ gflow) {
+  const int H = geom.H, W = geom.W;
   const long plane = (long)H * W, pix = (long)i * W + j;
   const float u = flow[((long)b * 2) * plane + pix], v = flow[((long)b * 2 + 1) * plane + pix];
-  const Tap t = flow_tap(j, i, u, v, W, H);
+  const Tap t = flow_tap(j, i, u, v, geom);
   const float keep = use_mask ? tap_keep(t) : 1.0f;
   float gx = 0.f, gy = 0.f;
   for (int c = 0; c < C; ++c) {
@@ -56,9 +62,8 @@ UGL_HD void warp_pixel_backward_flow(const float* __restrict__ x, const float* _
     gx += g * corners_ddx(k, t);
     gy += g * corners_ddy(k, t);
   }
-  const float sx = (float)W / (float)(W - 1 > 1 ? W - 1 : 1), sy = (float)H / (float)(H - 1 > 1 ? H - 1 : 1);
-  gflow[((long)b * 2) * plane + pix] = gx * sx;
-  gflow[((long)b * 2 + 1) * plane + pix] = gy * sy;
+  gflow[((long)b * 2) * plane + pix] = gx * geom.sx;
+  gflow[((long)b * 2 + 1) * plane + pix] = gy * geom.sy;
 }
 
 // Fixed-point encoding for the deterministic scatter of d loss / d x: integer addition is

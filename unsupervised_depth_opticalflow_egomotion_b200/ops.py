@@ -176,6 +176,35 @@ class _FlowLossFn(torch.autograd.Function):
         return (None, None, *none_l, *none_l, *none_l, *gf, *pad, *gb, *pad)
 
 
+def flow_loss_step(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r_pyr: Sequence[Tensor],
+                   flows_fwd: Sequence[Tensor], flows_bwd: Sequence[Tensor], grad_loss: Tensor,
+                   num_scales: Optional[int] = None, out: Optional[dict] = None):
+    """Forward + backward of the fused flow-mode loss in one call, without the autograd engine: for
+    the training step where the upstream gradient is known up front (``train.py:211-215``:
+    ``d total / d loss_k[b] = w_k / B``).  Returns ``(loss (4,B), grads_fwd, grads_bwd)``; pass the
+    previous result as ``out`` to reuse its buffers (CUDA-graph friendly: 3 kernel launches, no
+    allocation)."""
+    L = len(flows_fwd)
+    scales = L if num_scales is None else int(num_scales)
+    ts = [_dev(t, "input") for t in (*img_l_pyr[:L], *img_pyr[:L], *img_r_pyr[:L], *flows_fwd, *flows_bwd)]
+    img_l, img, img_r, ff, fb = (ts[k * L:(k + 1) * L] for k in range(5))
+    gloss = _dev(grad_loss, "grad_loss")
+    B, dev = img[0].shape[0], img[0].device
+    if out is None:
+        out = {"loss": torch.empty((4, B), device=dev, dtype=torch.float32),
+               "stats": torch.empty((B, scales, _cabi.FLOW_NSTATS), device=dev, dtype=torch.float32),
+               "gf": [torch.empty_like(ff[l]) for l in range(scales)], "gb": [torch.empty_like(fb[l]) for l in range(scales)]}
+        a = _flow_args(img_l, img, img_r, ff, fb, scales, out["loss"], out["stats"], None)
+        out["ws"] = torch.empty(max(int(_cabi.lib().ugl_flow_loss_workspace_bytes(C.byref(a))) // 4, 1), device=dev,
+                                dtype=torch.float32)
+    a = _flow_args(img_l, img, img_r, ff, fb, scales, out["loss"], out["stats"], out["ws"], gloss, out["gf"], out["gb"])
+    with torch.cuda.device_of(img[0]):
+        _cabi.check(_cabi.lib().ugl_flow_loss_forward(C.byref(a)), "ugl_flow_loss_forward")
+        _cabi.check(_cabi.lib().ugl_flow_loss_backward(C.byref(a)), "ugl_flow_loss_backward")
+    _count(3)
+    return out
+
+
 def flow_loss(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r_pyr: Sequence[Tensor],
               flows_fwd: Sequence[Tensor], flows_bwd: Sequence[Tensor], num_scales: Optional[int] = None,
               as_matrix: bool = False):

@@ -53,8 +53,8 @@ class FlowLossStep:
         for dst, src in zip(self.d_ff + self.d_fb, list(h_flows_fwd) + list(h_flows_bwd)):
             dst.copy_(src, non_blocking=True)
         pl, pc, pr = (ops.image_pyramid(x, self.L, "box") for x in self.d_imgs)
-        ff = [f.requires_grad_(True) for f in self.d_ff]
-        fb = [f.requires_grad_(True) for f in self.d_fb]
+        ff = [f.detach().requires_grad_(True) for f in self.d_ff]   # fresh leaves over the staging buffers
+        fb = [f.detach().requires_grad_(True) for f in self.d_fb]
         loss = ops.flow_loss(pl, pc, pr, ff, fb, self.scales, as_matrix=True)
         self.grads = list(torch.autograd.grad(loss, ff[:self.scales] + fb[:self.scales], grad_outputs=self.wmat))
         self.h_loss.copy_(loss.detach(), non_blocking=True)
