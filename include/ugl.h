@@ -99,6 +99,124 @@ int ugl_warp_flow_backward(const float* x, const float* flow, const float* grad_
 uint64_t ugl_warp_flow_backward_workspace_bytes(int32_t batch, int32_t channels, int32_t height, int32_t width,
                                                 int32_t need_grad_x);
 
+/* ---------------------------------------------------------------------------------------------
+ * Generic per-sample reductions: workspace for every *_forward / *_backward below that takes one
+ * (>= ugl_reduce_workspace_bytes(B,H,W) bytes, 8-byte aligned).
+ * ------------------------------------------------------------------------------------------- */
+uint64_t ugl_reduce_workspace_bytes(int32_t batch, int32_t height, int32_t width);
+
+/* P(d, m) = mean_{c,h,w}(d*m) / (mean_{h,w}(m) + 1e-12), one pyramid level -> out (B,), den (B,) kept
+ * for backward.  mode 0: d = |a - b| — compute_photometric_loss (model_geometry.py:143-153,
+ * model_depth.py:92-103), compute_loss_pixel (model_flow.py:72-81).  mode 1: d = a —
+ * compute_loss_with_mask (model_flow.py:94-103), compute_depth_flow_consis_loss
+ * (model_geometry.py:716-732), compute_consis_loss (model_geometry.py:182-193), and with
+ * mask == NULL the plain mean of compute_epipolar_loss (model_geometry.py:413-418).
+ * mask is (B,1,H,W) and is repeated over the C channels of d. */
+int ugl_masked_mean_forward(const float* a, const float* b, const float* mask, int32_t batch, int32_t channels, int32_t height,
+                            int32_t width, int32_t mode, float* out, float* den, void* workspace, uint64_t workspace_bytes,
+                            void* stream);
+int ugl_masked_mean_backward(const float* a, const float* b, const float* mask, const float* den, const float* grad_out,
+                             int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t mode, float* grad_a,
+                             float* grad_b, void* stream);
+
+/* compute_occ_weight (model_geometry.py:105-132, soft = 0: [1 - softmax > 0.48]) and
+ * compute_diff_weight (model_flow.py:105-138, soft = 1: 2 exp(-(w-0.5)^2/0.03) * valid); all outputs
+ * (B,1,H,W); diff_* = mean_c |img - from_*| may be NULL.  The diffs are differentiable w.r.t. the
+ * warped images through ugl_channel_mean_abs_diff_backward. */
+int ugl_occlusion_weights(const float* from_l, const float* img, const float* from_r, int32_t batch, int32_t height, int32_t width,
+                          int32_t soft, float* w_bwd, float* w_fwd, float* valid_bwd, float* valid_fwd, float* diff_bwd,
+                          float* diff_fwd, void* stream);
+int ugl_channel_mean_abs_diff_backward(const float* img, const float* warped, const float* grad_diff, int32_t batch,
+                                       int32_t channels, int32_t height, int32_t width, float* grad_warped, void* stream);
+
+/* compute_texture_mask (model_geometry.py:134-140, model_depth.py:84-90) */
+int ugl_texture_mask(const float* img, const float* rec, const float* src, int32_t batch, int32_t height, int32_t width, float* mask,
+                     void* stream);
+
+/* compute_dynamic_mask body (model_geometry.py:698-711) given the rigid flow: flow_diff = |rf - f| (B,2,H,W),
+ * dyn = [n(fd)^2 < alpha (n(f)^2 + n(rf)^2) + beta], score = 1/(1e-4 + n(fd)) (may be NULL).
+ * ugl_abs_diff_backward is the backward of d = |a - b| (element-wise). */
+int ugl_dynamic_mask_forward(const float* flow, const float* rigid_flow, int32_t batch, int32_t height, int32_t width, float alpha,
+                             float beta, float* flow_diff, float* dyn_mask, float* score, void* stream);
+int ugl_abs_diff_backward(const float* a, const float* b, const float* grad_out, int64_t n, float* grad_a, float* grad_b, void* stream);
+
+/* fusion_mask / fusion_mask_2item / fusion_mask_4item (model_geometry.py:735-765, model_depth.py:262-269):
+ * product of up to 4 maps, optionally inverted (1 - m).  get_rigid_mask (model_geometry.py:420-425). */
+int ugl_mask_product(const float* const* masks, const int32_t* invert, int32_t n_masks, int64_t n, float* out, void* stream);
+int ugl_rigid_mask(const float* dist, int64_t n, float rigid_thres, float inlier_thres, float* rigid, float* inlier, float* score,
+                   void* stream);
+
+/* cal_grad2_error(flow/20, img) for one level (model_geometry.py:254-279, model_flow.py:156-181) -> (B,) */
+int ugl_flow_smooth_forward(const float* flow, const float* img, int32_t batch, int32_t height, int32_t width, float* out,
+                            void* workspace, uint64_t workspace_bytes, void* stream);
+int ugl_flow_smooth_backward(const float* flow, const float* img, const float* grad_out, int32_t batch, int32_t height, int32_t width,
+                             float* grad_flow, void* stream);
+
+/* compute_loss_flow_consis for one level (model_geometry.py:195-210, model_flow.py:184-199): mask = 1 - occ,
+ * gradient reaches the forward flow only. */
+int ugl_flow_consis_forward(const float* fwd, const float* bwd, const float* occ, int32_t batch, int32_t height, int32_t width,
+                            float* out, float* den, void* workspace, uint64_t workspace_bytes, void* stream);
+int ugl_flow_consis_backward(const float* fwd, const float* bwd, const float* occ, const float* den, const float* grad_out,
+                             int32_t batch, int32_t height, int32_t width, float* grad_fwd, void* stream);
+
+/* depth difference map of compute_consis_loss (model_geometry.py:186-188, model_depth.py:158-160):
+ * clamp(|comp - proj| / |comp + proj|, 0, 1), element-wise. */
+int ugl_depth_diff_forward(const float* comp, const float* proj, int64_t n, float* out, void* stream);
+int ugl_depth_diff_backward(const float* comp, const float* proj, const float* grad_out, int64_t n, float* grad_comp, float* grad_proj,
+                            void* stream);
+
+/* compute_smooth_loss (model_geometry.py:225-252, model_depth.py:220-247): all `levels` disparity maps
+ * (B,1,h_l,w_l) are bilinearly up-sampled to (H,W) inside the kernel; out (B,) = sum over levels. */
+int ugl_disp_smooth_forward(const float* img, const float* const* disps, const int32_t* heights, const int32_t* widths, int32_t levels,
+                            int32_t batch, int32_t height, int32_t width, float* out, void* workspace, uint64_t workspace_bytes,
+                            void* stream);
+uint64_t ugl_disp_smooth_backward_workspace_bytes(int32_t batch, int32_t height, int32_t width);
+int ugl_disp_smooth_backward(const float* img, const float* const* disps, const int32_t* heights, const int32_t* widths, int32_t levels,
+                             const float* grad_out, int32_t batch, int32_t height, int32_t width, float* const* grad_disps,
+                             void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * inverse_warp2 (structures/inverse_warp.py:263-303 with pixel2cam :30-45 and cam2pixel2 :227-260).
+ * Kinv (B,3,3) = intrinsics.inverse() and P (B,3,4) = intrinsics @ pose_vec2mat(pose) are built by the
+ * caller; backward returns grad_depth (B,1,H,W), grad_P (B,3,4) and, if requested, the deterministic
+ * scatter gradients grad_img (B,C,H,W) / grad_ref_depth (B,1,H,W).  go_* may be NULL (= zero).
+ * calculate_rigid_flow (:311-342) shares the projection.
+ * ------------------------------------------------------------------------------------------- */
+int ugl_reproject_forward(const float* img, const float* depth, const float* ref_depth, const float* Kinv, const float* P,
+                          int32_t batch, int32_t channels, int32_t height, int32_t width, float* out, float* valid,
+                          float* proj_depth, float* comp_depth, void* stream);
+uint64_t ugl_reproject_backward_workspace_bytes(int32_t batch, int32_t channels, int32_t height, int32_t width,
+                                                int32_t need_grad_img, int32_t need_grad_ref);
+int ugl_reproject_backward(const float* img, const float* depth, const float* ref_depth, const float* Kinv, const float* P,
+                           const float* go_img, const float* go_proj, const float* go_comp, int32_t batch, int32_t channels,
+                           int32_t height, int32_t width, float* grad_depth, float* grad_P, float* grad_img, float* grad_ref_depth,
+                           void* workspace, uint64_t workspace_bytes, void* stream);
+int ugl_rigid_flow_forward(const float* depth, const float* Kinv, const float* P, int32_t batch, int32_t height, int32_t width,
+                           float* out, void* stream);
+int ugl_rigid_flow_backward(const float* depth, const float* Kinv, const float* P, const float* grad_out, int32_t batch, int32_t height,
+                            int32_t width, float* grad_depth, float* grad_P, void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* compute_epipolar_map (model_geometry.py:355-403) given F (B,3,3) = K^-T [t]x R K^-1: dist (B,1,H,W);
+ * backward: grad_flow (B,2,H,W, may be NULL) and grad_F (B,3,3). */
+int ugl_epipolar_forward(const float* flow, const float* F, int32_t batch, int32_t height, int32_t width, float* out, void* stream);
+int ugl_epipolar_backward(const float* flow, const float* F, const float* grad_out, int32_t batch, int32_t height, int32_t width,
+                          float* grad_flow, float* grad_F, void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SSIM (pytorch_ssim/ssim.py:4-19): the map and its backward; and the masked SSIM loss of
+ * compute_ssim_loss / compute_loss_ssim (model_geometry.py:212-223, model_flow.py:141-152, one level).
+ * ------------------------------------------------------------------------------------------- */
+int ugl_ssim_forward(const float* x, const float* y, int32_t batch, int32_t channels, int32_t height, int32_t width, float* out,
+                     void* stream);
+int ugl_ssim_backward(const float* x, const float* y, const float* grad_out, int32_t batch, int32_t channels, int32_t height,
+                      int32_t width, float* grad_x, float* grad_y, void* stream);
+uint64_t ugl_ssim_loss_workspace_bytes(int32_t batch, int32_t channels, int32_t height, int32_t width);
+int ugl_ssim_loss_forward(const float* img, const float* warped, const float* mask, int32_t batch, int32_t channels, int32_t height,
+                          int32_t width, float* out, float* den, void* workspace, uint64_t workspace_bytes, void* stream);
+int ugl_ssim_loss_backward(const float* img, const float* warped, const float* mask, const float* den, const float* grad_out,
+                           int32_t batch, int32_t channels, int32_t height, int32_t width, float* grad_img, float* grad_warped,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

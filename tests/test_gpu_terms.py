@@ -1,0 +1,265 @@
+"""GPU parity tests of the stand-alone loss terms, masks and geometry ops, and of the depth / geom mode
+assemblies (losses.DepthLoss / GeometryLoss) against the oracle and the reference-generated fixtures."""
+import pytest
+import torch
+
+from oracle import loss_port as P
+from unsupervised_depth_opticalflow_egomotion_b200 import losses, ops, structures
+from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
+from util import load_golden, golden_triplet, rel_err, loss_rel_err, LOSS_RTOL, GRAD_RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ---- primitives against the reference's own outputs ---------------------------------------------------
+def test_ssim_vs_reference_golden(cuda_device):
+    d = load_golden("primitives")
+    x, y = d["ssim_x"].to(cuda_device).requires_grad_(True), d["ssim_y"].to(cuda_device).requires_grad_(True)
+    s = structures.SSIM(x, y)
+    gx, gy = torch.autograd.grad((s * d["ssim_go"].to(cuda_device)).sum(), [x, y])
+    assert rel_err(s, d["ssim_out"]) < 1e-5
+    assert rel_err(gx, d["ssim_grad_x"]) < GRAD_RTOL and rel_err(gy, d["ssim_grad_y"]) < GRAD_RTOL
+
+
+def test_inverse_warp2_and_rigid_flow_vs_reference_golden(cuda_device):
+    d = load_golden("primitives")
+    dev = cuda_device
+    img = d["iw_img"].to(dev).requires_grad_(True)
+    depth = d["iw_depth"].to(dev).requires_grad_(True)
+    refd = d["iw_ref_depth"].to(dev).requires_grad_(True)
+    pose = d["iw_pose"].to(dev).requires_grad_(True)
+    K = d["iw_K"].to(dev)
+    rec, valid, proj, comp = structures.inverse_warp2(img, depth, refd, pose, K)
+    assert rel_err(rec, d["iw_rec"]) < 1e-5 and torch.equal(valid.cpu(), d["iw_valid"])
+    assert rel_err(proj, d["iw_proj"]) < 1e-5 and rel_err(comp, d["iw_comp"]) < 1e-6
+    tot = (rec * d["iw_go_rec"].to(dev)).sum() + (proj * d["iw_go_proj"].to(dev)).sum() + (comp * d["iw_go_comp"].to(dev)).sum()
+    gd, gr, gp, gi = torch.autograd.grad(tot, [depth, refd, pose, img])
+    assert rel_err(gd, d["iw_grad_depth"]) < GRAD_RTOL
+    assert rel_err(gr, d["iw_grad_ref_depth"]) < GRAD_RTOL
+    assert rel_err(gp, d["iw_grad_pose"]) < GRAD_RTOL
+    assert rel_err(gi, d["iw_grad_img"]) < GRAD_RTOL
+    rf = structures.calculate_rigid_flow(depth, pose, K)
+    gd2, gp2 = torch.autograd.grad((rf * d["rf_go"].to(dev)).sum(), [depth, pose])
+    assert rel_err(rf, d["rf_out"]) < 1e-5
+    assert rel_err(gd2, d["rf_grad_depth"]) < GRAD_RTOL and rel_err(gp2, d["rf_grad_pose"]) < GRAD_RTOL
+    with pytest.raises(AssertionError, match="wrong size for depth"):
+        structures.inverse_warp2(img, depth[:, 0], refd, pose, K)
+
+
+# ---- terms against the oracle on random inputs ---------------------------------------------------------
+@pytest.mark.parametrize("B,C,H,W", [(2, 3, 40, 72), (1, 2, 33, 50), (3, 1, 16, 24)])
+def test_masked_means_vs_oracle(cuda_device, B, C, H, W):
+    g = _g(B * 100 + C)
+    a, b = torch.rand(B, C, H, W, generator=g), torch.rand(B, C, H, W, generator=g)
+    m = (torch.rand(B, 1, H, W, generator=g) > 0.4).float()
+    m[0] = 0 if B > 1 else m[0]                       # a fully masked sample: loss must be exactly 0
+    go = torch.rand(B, generator=g) + 0.5
+    bc = b.clone().requires_grad_(True)
+    ref = P.masked_mean((a - bc).abs(), m)
+    rg, = torch.autograd.grad((ref * go).sum(), [bc])
+    bd = b.to(cuda_device).requires_grad_(True)
+    out = ops.masked_l1(a.to(cuda_device), bd, m.to(cuda_device))
+    og, = torch.autograd.grad((out * go.to(cuda_device)).sum(), [bd])
+    assert torch.allclose(out.cpu(), ref.detach(), rtol=LOSS_RTOL, atol=0) and rel_err(og, rg) < 1e-5
+    ac = a.clone().requires_grad_(True)
+    ref2 = P.masked_mean(ac, m)
+    rg2, = torch.autograd.grad((ref2 * go).sum(), [ac])
+    ad = a.to(cuda_device).requires_grad_(True)
+    out2 = ops.masked_mean(ad, m.to(cuda_device))
+    og2, = torch.autograd.grad((out2 * go.to(cuda_device)).sum(), [ad])
+    assert torch.allclose(out2.cpu(), ref2.detach(), rtol=LOSS_RTOL, atol=0) and rel_err(og2, rg2) < 1e-5
+    assert loss_rel_err(ops.masked_mean(ad, None), a.mean((1, 2, 3))) < LOSS_RTOL
+
+
+@pytest.mark.parametrize("B,H,W,masked", [(2, 40, 72, True), (1, 33, 50, False), (2, 9, 11, True)])
+def test_ssim_loss_vs_oracle(cuda_device, B, H, W, masked):
+    g = _g(H)
+    img = torch.rand(B, 3, H, W, generator=g)
+    wr = (img + 0.1 * torch.randn(B, 3, H, W, generator=g))
+    m = (torch.rand(B, 1, H, W, generator=g) > 0.3).float() if masked else torch.ones(B, 1, H, W)
+    go = torch.rand(B, generator=g) + 0.5
+    wc = wr.clone().requires_grad_(True)
+    ref = P.ssim_loss([img], [wc], [m], 1)
+    rg, = torch.autograd.grad((ref * go).sum(), [wc])
+    w64 = wr.double().requires_grad_(True)
+    r64, = torch.autograd.grad((P.ssim_loss([img.double()], [w64], [m.double()], 1) * go.double()).sum(), [w64])
+    wd = wr.to(cuda_device).requires_grad_(True)
+    out = ops.ssim_loss(img.to(cuda_device), wd, m.to(cuda_device))
+    og, = torch.autograd.grad((out * go.to(cuda_device)).sum(), [wd])
+    assert loss_rel_err(out, ref) < LOSS_RTOL
+    assert rel_err(og, rg) < GRAD_RTOL or rel_err(og, r64) <= 1.25 * rel_err(rg, r64)
+
+
+@pytest.mark.parametrize("soft", [False, True])
+def test_occlusion_weights_vs_oracle(cuda_device, soft):
+    t = make_triplet(2, 64, 208, 1, 1, seed=31, flow_px=5.0, oob_fraction=0.1)
+    from_l = P.flow_backwarp(t.img_l, t.flows_bwd[0], True)
+    from_r = P.flow_backwarp(t.img_r, t.flows_fwd[0], True)
+    o = P.occlusion_weights([from_l], [t.img], [from_r], 1, soft=soft)
+    w_b, w_f, v_b, v_f, d_b, d_f = ops.occlusion_weights(from_l.to(cuda_device), t.img.to(cuda_device), from_r.to(cuda_device), soft)
+    assert torch.equal(v_b.cpu(), o["valid_bwd"][0]) and torch.equal(v_f.cpu(), o["valid_fwd"][0])
+    if soft:
+        assert rel_err(w_b, o["w_bwd"][0]) < 1e-5 and rel_err(w_f, o["w_fwd"][0]) < 1e-5
+    else:
+        assert torch.equal(w_b.cpu(), o["w_bwd"][0]) and torch.equal(w_f.cpu(), o["w_fwd"][0])   # bit-exact hard masks
+    assert torch.equal(d_b.cpu(), o["diff_bwd"][0]) and torch.equal(d_f.cpu(), o["diff_fwd"][0])
+
+
+def test_flow_regularisers_vs_oracle(cuda_device):
+    t = make_triplet(2, 48, 80, 1, 1, seed=32, flow_px=4.0)
+    occ = (torch.rand(2, 1, 48, 80, generator=_g(1)) > 0.5).float()
+    go = torch.tensor([0.7, 1.3])
+    f, b = t.flows_fwd[0].clone().requires_grad_(True), t.flows_bwd[0].clone()
+    ref_s = P.flow_smooth_loss([f], [t.img], 1)
+    ref_c = P.flow_direction_consistency([f], [b], [occ], 1)
+    rgs, = torch.autograd.grad((ref_s * go).sum(), [f], retain_graph=True)
+    rgc, = torch.autograd.grad((ref_c * go).sum(), [f])
+    fd = t.flows_fwd[0].to(cuda_device).requires_grad_(True)
+    out_s = ops.flow_smooth(fd, t.img.to(cuda_device))
+    out_c = ops.flow_consis(fd, b.to(cuda_device), occ.to(cuda_device))
+    ogs, = torch.autograd.grad((out_s * go.to(cuda_device)).sum(), [fd])
+    ogc, = torch.autograd.grad((out_c * go.to(cuda_device)).sum(), [fd])
+    assert loss_rel_err(out_s, ref_s) < LOSS_RTOL and loss_rel_err(out_c, ref_c) < LOSS_RTOL
+    assert rel_err(ogs, rgs) < 1e-5 and rel_err(ogc, rgc) < 1e-5
+
+
+@pytest.mark.parametrize("S", [1, 3])
+def test_disp_smooth_vs_oracle(cuda_device, S):
+    t = make_triplet(2, 64, 208, 1, S, seed=33)
+    go = torch.tensor([0.6, 1.4])
+    ds = [d.clone().requires_grad_(True) for d in t.disp]
+    ref = P.disparity_smooth_loss(t.img, ds, S)
+    rg = torch.autograd.grad((ref * go).sum(), ds)
+    dd = [d.to(cuda_device).requires_grad_(True) for d in t.disp]
+    out = ops.disp_smooth(t.img.to(cuda_device), dd)
+    og = torch.autograd.grad((out * go.to(cuda_device)).sum(), dd)
+    assert loss_rel_err(out, ref) < LOSS_RTOL
+    for a, b in zip(og, rg):
+        assert rel_err(a, b) < GRAD_RTOL
+
+
+def test_epipolar_and_depth_diff_vs_oracle(cuda_device):
+    t = make_triplet(2, 32, 64, 1, 1, seed=34, flow_mode="rigid")
+    f = t.flows_fwd[0].clone().requires_grad_(True)
+    pose = (3.0 * t.pose[:, 1]).clone().requires_grad_(True)
+    ref = P.epipolar_distance(pose, f, t.K, t.K_inv)
+    go = torch.rand(ref.shape, generator=_g(2))
+    rgf, rgp = torch.autograd.grad((ref * go).sum(), [f, pose])
+    gl = losses.GeometryLoss(1)
+    fd, pd = t.flows_fwd[0].to(cuda_device).requires_grad_(True), (3.0 * t.pose[:, 1]).to(cuda_device).requires_grad_(True)
+    out = gl.compute_epipolar_map(pd, fd, t.K.to(cuda_device), t.K_inv.to(cuda_device))
+    ogf, ogp = torch.autograd.grad((out * go.to(cuda_device)).sum(), [fd, pd])
+    assert rel_err(out, ref) < 1e-5 and rel_err(ogf, rgf) < GRAD_RTOL and rel_err(ogp, rgp) < GRAD_RTOL
+    c, p = (torch.rand(2, 1, 8, 9, generator=_g(3)) + 0.1).requires_grad_(True), (torch.rand(2, 1, 8, 9, generator=_g(4)) + 0.1).requires_grad_(True)
+    refd = ((c - p).abs() / (c + p).abs()).clamp(0, 1)
+    rgc, rgp2 = torch.autograd.grad(refd.sum(), [c, p])
+    cd, pd2 = c.detach().to(cuda_device).requires_grad_(True), p.detach().to(cuda_device).requires_grad_(True)
+    outd = ops.depth_diff(cd, pd2)
+    ogc, ogp2 = torch.autograd.grad(outd.sum(), [cd, pd2])
+    assert rel_err(outd, refd) < 1e-6 and rel_err(ogc, rgc) < 1e-5 and rel_err(ogp2, rgp2) < 1e-5
+
+
+# ---- mode assemblies ------------------------------------------------------------------------------------
+def _leaf_list(xs, dev):
+    return [x.detach().to(dev).requires_grad_(True) for x in xs]
+
+
+def _check_mode(loss, d, leaves, names, weights):
+    for k, v in loss.items():
+        if "out_" + k in d:
+            assert loss_rel_err(v, d["out_" + k]) < LOSS_RTOL, k
+    total = sum(weights[k] * v.mean() for k, v in loss.items() if "out_" + k in d)
+    grads = torch.autograd.grad(total, leaves, allow_unused=True)
+    for n, g in zip(names, grads):
+        ref = d["grad_" + n]
+        g = torch.zeros_like(ref) if g is None else g.cpu()
+        if ref.abs().max() == 0:
+            assert g.abs().max() == 0, n
+        else:
+            assert rel_err(g, ref) < 1.5 * GRAD_RTOL, (n, rel_err(g, ref))
+
+
+@pytest.mark.parametrize("name,variant", [("depth_mode_live", "live"), ("depth_mode_texture", "texture")])
+def test_depth_mode_vs_reference_golden(cuda_device, name, variant):
+    d = load_golden(name)
+    t = golden_triplet(d)
+    dev = cuda_device
+    disp, disp_l, disp_r = _leaf_list(t.disp, dev), _leaf_list(t.disp_l, dev), _leaf_list(t.disp_r, dev)
+    pose = t.pose.to(dev).requires_grad_(True)
+    loss, masks = losses.DepthLoss(3, variant).forward_losses(t.img_l.to(dev), t.img.to(dev), t.img_r.to(dev), disp, disp_l, disp_r,
+                                                               pose, t.K.to(dev))
+    names = ["disp_%d" % i for i in range(3)] + ["disp_l_%d" % i for i in range(3)] + ["disp_r_%d" % i for i in range(3)] + ["pose"]
+    _check_mode(loss, d, disp + disp_l + disp_r + [pose], names, P.GEOM_WEIGHTS)
+    for l in range(3):
+        assert torch.equal(masks["valid_l"][l].cpu(), d["aux_valid_l_%d" % l])
+        assert torch.equal(masks["valid_r"][l].cpu(), d["aux_valid_r_%d" % l])
+        if variant == "live":
+            assert torch.equal(masks["tex_b"][l].cpu(), d["aux_tex_b_%d" % l])
+            assert torch.equal(masks["tex_f"][l].cpu(), d["aux_tex_f_%d" % l])
+
+
+def test_geom_mode_vs_reference_golden(cuda_device):
+    d = load_golden("geom_mode_s3")
+    t = golden_triplet(d)
+    dev = cuda_device
+    ff, fb = _leaf_list(t.flows_fwd, dev), _leaf_list(t.flows_bwd, dev)
+    disp, disp_l, disp_r = _leaf_list(t.disp, dev), _leaf_list(t.disp_l, dev), _leaf_list(t.disp_r, dev)
+    pose = t.pose.to(dev).requires_grad_(True)
+    loss, masks = losses.GeometryLoss(3).forward_losses(t.img_l.to(dev), t.img.to(dev), t.img_r.to(dev), ff, fb, disp, disp_l, disp_r,
+                                                        pose, t.K.to(dev), t.K_inv.to(dev))
+    names = (["flows_fwd_%d" % i for i in range(4)] + ["flows_bwd_%d" % i for i in range(4)] + ["disp_%d" % i for i in range(3)]
+             + ["disp_l_%d" % i for i in range(3)] + ["disp_r_%d" % i for i in range(3)] + ["pose"])
+    _check_mode(loss, d, ff + fb + disp + disp_l + disp_r + [pose], names, P.GEOM_WEIGHTS)
+    for key in ("occ_b", "occ_f", "valid_b", "valid_f", "dyn_b", "dyn_f", "tex_b", "tex_f", "val_l", "val_r"):
+        for l in range(3):
+            assert torch.equal(masks[key][l].cpu(), d["aux_%s_%d" % (key, l)]), (key, l)      # masks bit-exact
+    assert loss["loss_pnp"].shape == torch.Size([2])
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 208), (1, 128, 416)])
+def test_geom_mode_vs_oracle(cuda_device, B, H, W):
+    t = make_triplet(B, H, W, 4, 3, seed=41, flow_mode="rigid")
+    dev = cuda_device
+    cpu_leaves = [x.requires_grad_(True) for x in t.flows_fwd + t.flows_bwd + t.disp + t.disp_l + t.disp_r + [t.pose]]
+    ref, raux = P.geom_mode_loss(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd, t.disp, t.disp_l, t.disp_r, t.pose, t.K, t.K_inv, 3,
+                                 return_aux=True)
+    keys = [k for k, v in ref.items() if v.shape == torch.Size([B]) and v.requires_grad]
+    rtot = sum(P.GEOM_WEIGHTS[k] * ref[k].mean() for k in keys)
+    rg = torch.autograd.grad(rtot, cpu_leaves, allow_unused=True)
+    ff, fb = _leaf_list(t.flows_fwd, dev), _leaf_list(t.flows_bwd, dev)
+    disp, disp_l, disp_r = _leaf_list(t.disp, dev), _leaf_list(t.disp_l, dev), _leaf_list(t.disp_r, dev)
+    pose = t.pose.detach().to(dev).requires_grad_(True)
+    loss, masks = losses.GeometryLoss(3).forward_losses(t.img_l.to(dev), t.img.to(dev), t.img_r.to(dev), ff, fb, disp, disp_l, disp_r,
+                                                        pose, t.K.to(dev), t.K_inv.to(dev))
+    for k in keys:
+        assert loss_rel_err(loss[k], ref[k]) < LOSS_RTOL, k
+    flips = 0
+    for key in ("occ_b", "occ_f", "valid_b", "valid_f", "dyn_b", "dyn_f", "tex_b", "tex_f", "val_l", "val_r"):
+        for l in range(3):
+            flips += int((masks[key][l].cpu() != raux[key][l]).sum())
+    assert flips == 0
+    tot = sum(P.GEOM_WEIGHTS[k] * loss[k].mean() for k in keys)
+    og = torch.autograd.grad(tot, ff + fb + disp + disp_l + disp_r + [pose], allow_unused=True)
+    for a, b in zip(og, rg):
+        if b is None:
+            assert a is None or a.abs().max() == 0
+        else:
+            assert rel_err(a, b) < 1.5 * GRAD_RTOL
+
+
+def test_flow_mode_composed_equals_fused(cuda_device):
+    t = make_triplet(2, 64, 208, 4, 1, seed=51, flow_px=5.0).to(cuda_device)
+    fl = losses.FlowLoss(4)
+    ff, fb = [f.requires_grad_(True) for f in t.flows_fwd], [f.requires_grad_(True) for f in t.flows_bwd]
+    a = fl.forward_losses(t.img_l, t.img, t.img_r, ff, fb, fused=True)
+    b = fl.forward_losses(t.img_l, t.img, t.img_r, ff, fb, fused=False)
+    ga = torch.autograd.grad(sum(P.FLOW_WEIGHTS[k] * a[k].mean() for k in a), ff + fb)
+    gb = torch.autograd.grad(sum(P.FLOW_WEIGHTS[k] * b[k].mean() for k in b), ff + fb)
+    for k in a:
+        assert loss_rel_err(a[k], b[k]) < LOSS_RTOL, k
+    for x, y in zip(ga, gb):
+        assert rel_err(x, y) < GRAD_RTOL

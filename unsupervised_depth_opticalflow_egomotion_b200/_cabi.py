@@ -60,6 +60,43 @@ SIGNATURES = {
     "ugl_warp_flow_backward_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
 }
 
+_i, _u64, _p, _f, _i64 = C.c_int32, C.c_uint64, C.c_void_p, C.c_float, C.c_int64
+_pp = C.POINTER(C.c_void_p)
+_ip = C.POINTER(C.c_int32)
+SIGNATURES.update({
+    "ugl_reduce_workspace_bytes": (_u64, [_i, _i, _i]),
+    "ugl_masked_mean_forward": (C.c_int, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _u64, _p]),
+    "ugl_masked_mean_backward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "ugl_occlusion_weights": (C.c_int, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "ugl_channel_mean_abs_diff_backward": (C.c_int, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "ugl_texture_mask": (C.c_int, [_p, _p, _p, _i, _i, _i, _p, _p]),
+    "ugl_dynamic_mask_forward": (C.c_int, [_p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p]),
+    "ugl_abs_diff_backward": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
+    "ugl_mask_product": (C.c_int, [_pp, _ip, _i, _i64, _p, _p]),
+    "ugl_rigid_mask": (C.c_int, [_p, _i64, _f, _f, _p, _p, _p, _p]),
+    "ugl_flow_smooth_forward": (C.c_int, [_p, _p, _i, _i, _i, _p, _p, _u64, _p]),
+    "ugl_flow_smooth_backward": (C.c_int, [_p, _p, _p, _i, _i, _i, _p, _p]),
+    "ugl_flow_consis_forward": (C.c_int, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _u64, _p]),
+    "ugl_flow_consis_backward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "ugl_depth_diff_forward": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "ugl_depth_diff_backward": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
+    "ugl_disp_smooth_forward": (C.c_int, [_p, _pp, _ip, _ip, _i, _i, _i, _i, _p, _p, _u64, _p]),
+    "ugl_disp_smooth_backward_workspace_bytes": (_u64, [_i, _i, _i]),
+    "ugl_disp_smooth_backward": (C.c_int, [_p, _pp, _ip, _ip, _i, _p, _i, _i, _i, _pp, _p, _u64, _p]),
+    "ugl_reproject_forward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "ugl_reproject_backward_workspace_bytes": (_u64, [_i, _i, _i, _i, _i, _i]),
+    "ugl_reproject_backward": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _u64, _p]),
+    "ugl_rigid_flow_forward": (C.c_int, [_p, _p, _p, _i, _i, _i, _p, _p]),
+    "ugl_rigid_flow_backward": (C.c_int, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _u64, _p]),
+    "ugl_epipolar_forward": (C.c_int, [_p, _p, _i, _i, _i, _p, _p]),
+    "ugl_epipolar_backward": (C.c_int, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _u64, _p]),
+    "ugl_ssim_forward": (C.c_int, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "ugl_ssim_backward": (C.c_int, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "ugl_ssim_loss_workspace_bytes": (_u64, [_i, _i, _i, _i]),
+    "ugl_ssim_loss_forward": (C.c_int, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _u64, _p]),
+    "ugl_ssim_loss_backward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+})
+
 _lib: Optional[C.CDLL] = None
 
 

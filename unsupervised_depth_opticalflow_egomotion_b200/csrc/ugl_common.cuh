@@ -94,6 +94,16 @@ UGL_HD float fast_div(float a, float b) {
 #endif
 }
 
+// Fixed-point scale exponent of the deterministic scatter (ugl_scatter.cuh): |sum| * 2^e < 2^61 for up
+// to n_contrib contributions of magnitude <= max_abs.
+UGL_HD int fixed_point_exponent(float max_abs, long n_contrib) {
+  if (!(max_abs > 0.f)) return 0;
+  int e_max, e_cnt;
+  frexpf(max_abs, &e_max);
+  frexpf((float)n_contrib, &e_cnt);
+  return 61 - e_max - e_cnt;
+}
+
 // ---- bilinear footprint ------------------------------------------------------------------------
 // One backward-warp lookup: the nw corner, the four weights and which corners are inside the image.
 struct Tap {

@@ -2,6 +2,7 @@
 // d/d flow, deterministic d/d x).  See include/ugl.h for the C-ABI contract.
 #include "ugl_host.cuh"
 #include "ugl_primitives.cuh"
+#include "ugl_scatter.cuh"
 
 namespace ugl {
 
@@ -47,18 +48,6 @@ warp_bwd_flow_kernel(const float* __restrict__ x, const float* __restrict__ flow
   }
 }
 
-// max |grad_out| as the bit pattern of a non-negative float (unsigned order == float order)
-__global__ void __launch_bounds__(kPrimThreads) absmax_kernel(const float* __restrict__ g, long n, unsigned* __restrict__ out) {
-  float m = 0.f;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
-    const float a = fabsf(g[idx]);
-    m = (a > m && a <= 3.0e38f) ? a : m;   // ignores NaN/inf (they poison the result anyway)
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
-}
-
 __global__ void __launch_bounds__(kPrimThreads)
 warp_bwd_scatter_kernel(const float* __restrict__ flow, const float* __restrict__ gout, int B, int C, int H, int W,
                         int use_mask, const unsigned* __restrict__ maxbits, unsigned long long* __restrict__ acc) {
@@ -74,29 +63,9 @@ warp_bwd_scatter_kernel(const float* __restrict__ flow, const float* __restrict_
     const Tap t = flow_tap(j, i, u, v, geom);
     const float keep = use_mask ? tap_keep(t) : 1.0f;
     if (keep == 0.f || t.inb == 0u) continue;
-    const float wgt[4] = {t.wnw, t.wne, t.wsw, t.wse};
-    const long off[4] = {0, 1, W, (long)W + 1};
-    const long base = (long)t.y0 * W + t.x0;
-    for (int c = 0; c < C; ++c) {
-      const float g = gout[((long)b * C + c) * plane + pix] * keep;
-      unsigned long long* a = acc + ((long)b * C + c) * plane;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (t.inb & (1u << k)) {
-          const long long q = __double2ll_rn(ldexp((double)(g * wgt[k]), e));
-          atomicAdd(a + base + off[k], (unsigned long long)q);
-        }
-      }
-    }
+    for (int c = 0; c < C; ++c)
+      scatter_tap(acc + ((long)b * C + c) * plane, W, t, gout[((long)b * C + c) * plane + pix] * keep, e);
   }
-}
-
-__global__ void __launch_bounds__(kPrimThreads)
-fixed_to_float_kernel(const unsigned long long* __restrict__ acc, long n, long plane, const unsigned* __restrict__ maxbits,
-                      float* __restrict__ out) {
-  const int e = fixed_point_exponent(__uint_as_float(*maxbits), plane);
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x)
-    out[idx] = (float)ldexp((double)(long long)acc[idx], -e);
 }
 
 static int grid_for(long n) {

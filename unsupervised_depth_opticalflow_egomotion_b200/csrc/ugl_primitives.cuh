@@ -66,15 +66,4 @@ UGL_HD void warp_pixel_backward_flow(const float* __restrict__ x, const float* _
   gflow[((long)b * 2 + 1) * plane + pix] = gy * geom.sy;
 }
 
-// Fixed-point encoding for the deterministic scatter of d loss / d x: integer addition is
-// associative, so the accumulated value does not depend on the order in which threads arrive.
-// scale = 2^e chosen from max|grad_out| so that H*W worst-case contributions cannot overflow 63 bits.
-UGL_HD int fixed_point_exponent(float max_abs, long n_contrib) {
-  if (!(max_abs > 0.f)) return 0;
-  int e_max, e_cnt;
-  frexpf(max_abs, &e_max);                       // max_abs < 2^e_max
-  frexpf((float)n_contrib, &e_cnt);              // n_contrib < 2^e_cnt
-  return 61 - e_max - e_cnt;                     // |sum| * 2^e < 2^61
-}
-
 }  // namespace ugl

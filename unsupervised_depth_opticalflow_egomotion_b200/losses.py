@@ -1,0 +1,273 @@
+"""The reference's loss *methods* (``Model_flow`` / ``Model_depth`` / ``Model_geometry`` in
+``core/networks``), re-hosted on the sm_100a kernels with the same names, argument meaning and
+return shapes, plus ``forward_losses`` = the loss body of each ``forward`` given the network outputs.
+
+The networks (PWC-Net, ResNet depth net, PoseCNN) are not part of this package: a trainer keeps the
+reference's modules and swaps its loss methods for these.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .structures import calculate_rigid_flow, compute_essential_matrix, inverse_warp2, warp_flow
+
+Tensor = torch.Tensor
+
+
+def _zeros2(like: Tensor) -> Tensor:
+    """The reference's disabled-term placeholder ``torch.zeros([2]).to(device).requires_grad_()``."""
+    return torch.zeros([2], device=like.device).requires_grad_()
+
+
+class _LossBase:
+    def __init__(self, num_scales: int):
+        self.num_scales = int(num_scales)
+
+    # ---- shared helpers (identical bodies in the three reference classes) --------------------------------
+    def warp_flow_pyramid(self, img_pyramid, flow_pyramid):
+        """model_geometry.py:74-78 / model_flow.py:66-70"""
+        return [warp_flow(img, flow, use_mask=True) for img, flow in zip(img_pyramid, flow_pyramid)]
+
+    def compute_photometric_loss(self, img_list, img_warped_list, mask_list):
+        """model_geometry.py:143-153 / model_depth.py:92-103 / model_flow.py:72-81 (compute_loss_pixel)"""
+        return sum(ops.masked_l1(img_list[s], img_warped_list[s], mask_list[s]) for s in range(self.num_scales))
+
+    compute_loss_pixel = compute_photometric_loss
+
+    def compute_ssim_loss(self, img_list, img_warped_list, mask_list):
+        """model_geometry.py:212-223 / model_flow.py:141-152"""
+        return sum(ops.ssim_loss(img_list[s], img_warped_list[s], mask_list[s]) for s in range(self.num_scales))
+
+    compute_loss_ssim = compute_ssim_loss
+
+    def compute_loss_flow_smooth(self, optical_flows, img_pyramid):
+        """model_geometry.py:271-279 / model_flow.py:173-181"""
+        return sum(ops.flow_smooth(optical_flows[s], img_pyramid[s]) for s in range(self.num_scales))
+
+    def compute_loss_flow_consis(self, fwd_flow_pyramid, bwd_flow_pyramid, occ_mask_list):
+        """model_geometry.py:195-210 / model_flow.py:184-199"""
+        return sum(ops.flow_consis(fwd_flow_pyramid[s], bwd_flow_pyramid[s], occ_mask_list[s]) for s in range(self.num_scales))
+
+    def compute_smooth_loss(self, img, disps):
+        """model_geometry.py:225-252 / model_depth.py:220-247"""
+        return ops.disp_smooth(img, list(disps[:self.num_scales]))
+
+    def compute_texture_mask(self, img_list, img_warped_list, img_list_source):
+        """model_geometry.py:134-140 / model_depth.py:84-90"""
+        return [ops.texture_mask(img_list[s], img_warped_list[s], img_list_source[s]) for s in range(self.num_scales)]
+
+    def reconstruction(self, ref_img, intrinsics, depth, depth_ref, pose, padding_mode="zeros"):
+        """model_geometry.py:80-103 / model_depth.py:59-82: area-resized source, K rows 0-1 / downscale, inverse_warp2."""
+        rec, valid, proj, comp = [], [], [], []
+        H = ref_img.size(2)
+        area = ops.image_pyramid(ref_img, self.num_scales, "area")
+        for s in range(self.num_scales):
+            h, w = depth[s].shape[2:]
+            if (h, w) != tuple(area[s].shape[2:]):
+                raise ValueError("reconstruction: depth level %d is %dx%d, expected %s" % (s, h, w, tuple(area[s].shape[2:])))
+            Ks = torch.cat((intrinsics[:, 0:2] / (H / h), intrinsics[:, 2:]), dim=1)
+            a, b, c, d = inverse_warp2(area[s], depth[s], depth_ref[s], pose, Ks, padding_mode)
+            rec.append(a); valid.append(b); proj.append(c); comp.append(d)
+        return rec, valid, proj, comp
+
+
+class FlowLoss(_LossBase):
+    """Loss methods of ``Model_flow`` (model_flow.py)."""
+
+    def generate_img_pyramid(self, img, num_pyramid):
+        """model_flow.py:58-64 (adaptive average pooling, detached)"""
+        return ops.image_pyramid(img, num_pyramid, "box")
+
+    def compute_diff_weight(self, img_pyramid_from_l, img_pyramid, img_pyramid_from_r):
+        """model_flow.py:105-138 -> (diff_bwd, diff_fwd, weight_bwd, weight_fwd)"""
+        out = [ops.occlusion_weights(img_pyramid_from_l[s], img_pyramid[s], img_pyramid_from_r[s], soft=True)
+               for s in range(self.num_scales)]
+        return [o[4] for o in out], [o[5] for o in out], [o[0] for o in out], [o[1] for o in out]
+
+    def compute_loss_with_mask(self, diff_list, occ_mask_list):
+        """model_flow.py:94-103"""
+        return sum(ops.masked_mean(diff_list[s], occ_mask_list[s]) for s in range(self.num_scales))
+
+    def forward_losses(self, imgl, img, imgr, optical_flows_fwd, optical_flows_bwd, fused: bool = True) -> Dict[str, Tensor]:
+        """Loss body of ``Model_flow.forward`` (model_flow.py:232-254).  ``fused=True`` runs the single fused
+        kernel pair; ``fused=False`` composes the per-method kernels exactly like the reference does."""
+        L = len(optical_flows_fwd)
+        pl, pc, pr = (self.generate_img_pyramid(x, L) for x in (imgl, img, imgr))
+        if fused:
+            return ops.flow_loss(pl, pc, pr, optical_flows_fwd, optical_flows_bwd, self.num_scales)
+        from_l = self.warp_flow_pyramid(pl, optical_flows_bwd)
+        from_r = self.warp_flow_pyramid(pr, optical_flows_fwd)
+        diff_bwd, diff_fwd, w_bwd, w_fwd = self.compute_diff_weight(from_l, pc, from_r)
+        return {
+            "loss_flow_pixel": self.compute_loss_with_mask(diff_fwd, w_fwd) + self.compute_loss_with_mask(diff_bwd, w_bwd),
+            "loss_flow_ssim": self.compute_loss_ssim(pc, from_r, w_fwd) + self.compute_loss_ssim(pc, from_l, w_bwd),
+            "loss_flow_smooth": self.compute_loss_flow_smooth(optical_flows_fwd, pc) + self.compute_loss_flow_smooth(optical_flows_bwd, pc),
+            "loss_flow_consis": self.compute_loss_flow_consis(optical_flows_fwd, optical_flows_bwd, w_fwd),
+        }
+
+
+class DepthLoss(_LossBase):
+    """Loss methods of ``Model_depth`` (model_depth.py; ``variant='texture'`` = model_depth_texture.py:296-311)."""
+
+    def __init__(self, num_scales: int, variant: str = "live"):
+        super().__init__(num_scales)
+        if variant not in ("live", "texture"):
+            raise ValueError("variant must be 'live' or 'texture'")
+        self.variant = variant
+
+    def generate_img_pyramid(self, img, num_pyramid):
+        """model_depth.py:44-50 (bilinear)"""
+        return ops.image_pyramid(img, num_pyramid, "bilinear")
+
+    def fusion_mask(self, valid_mask, texture_mask):
+        """model_depth.py:262-269"""
+        return [ops.mask_product([valid_mask[s], texture_mask[s]]) for s in range(self.num_scales)]
+
+    def compute_consis_loss(self, predicted_depth_list, computed_depth_list):
+        """model_depth.py:154-163 (unmasked)"""
+        return sum(ops.masked_mean(ops.depth_diff(computed_depth_list[s], predicted_depth_list[s]), None) for s in range(self.num_scales))
+
+    def forward_losses(self, img_l, img, img_r, disp_list, disp_l_list, disp_r_list, pose_vectors, K) -> Tuple[Dict[str, Tensor], Dict]:
+        """Loss body of ``Model_depth.forward`` (model_depth.py:281-335) / model_depth_texture.py:262-311."""
+        S = self.num_scales
+        pl, pc, pr = (self.generate_img_pyramid(x, S) for x in (img_l, img, img_r))
+        pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
+        rec_l, val_l, proj_l, comp_l = self.reconstruction(img_l, K, disp_list, disp_l_list, pose_bwd)
+        rec_r, val_r, proj_r, comp_r = self.reconstruction(img_r, K, disp_list, disp_r_list, pose_fwd)
+        tex_b = self.compute_texture_mask(pc, rec_l, pl)
+        tex_f = self.compute_texture_mask(pc, rec_r, pr)
+        m_b, m_f = self.fusion_mask(val_l, tex_b), self.fusion_mask(val_r, tex_f)
+        loss = {"loss_depth_pixel": self.compute_photometric_loss(pc, rec_l, m_b) + self.compute_photometric_loss(pc, rec_r, m_f)}
+        if self.variant == "texture":
+            loss["loss_depth_ssim"] = self.compute_ssim_loss(pc, rec_l, val_l) + self.compute_ssim_loss(pc, rec_r, val_r)
+            loss["loss_depth_consis"] = self.compute_consis_loss(proj_l, comp_l) + self.compute_consis_loss(proj_r, comp_r)
+        else:
+            loss["loss_depth_ssim"] = _zeros2(img)
+            loss["loss_depth_consis"] = _zeros2(img)
+        loss["loss_depth_smooth"] = (self.compute_smooth_loss(img, disp_list) + self.compute_smooth_loss(img_l, disp_l_list)
+                                     + self.compute_smooth_loss(img_r, disp_r_list))
+        masks = dict(valid_l=val_l, valid_r=val_r, tex_b=tex_b, tex_f=tex_f)
+        return loss, masks
+
+
+class GeometryLoss(_LossBase):
+    """Loss methods of ``Model_geometry`` (model_geometry.py)."""
+
+    def __init__(self, num_scales: int, flow_consist_alpha: float = 0.01, flow_consist_beta: float = 0.5,
+                 rigid_thres: float = 0.5, inlier_thres: float = 0.1):
+        super().__init__(num_scales)
+        self.flow_consist_alpha, self.flow_consist_beta = flow_consist_alpha, flow_consist_beta
+        self.rigid_thres, self.inlier_thres = rigid_thres, inlier_thres
+
+    def generate_img_pyramid(self, img, num_pyramid):
+        """model_geometry.py:65-72 (bilinear)"""
+        return ops.image_pyramid(img, num_pyramid, "bilinear")
+
+    def compute_occ_weight(self, img_pyramid_from_l, img_pyramid, img_pyramid_from_r):
+        """model_geometry.py:105-132 -> (weight_bwd, weight_fwd, valid_bwd, valid_fwd)"""
+        out = [ops.occlusion_weights(img_pyramid_from_l[s], img_pyramid[s], img_pyramid_from_r[s], soft=False)
+               for s in range(self.num_scales)]
+        return [o[0] for o in out], [o[1] for o in out], [o[2] for o in out], [o[3] for o in out]
+
+    def compute_consis_loss(self, predicted_depth_list, computed_depth_list, mask_list):
+        """model_geometry.py:182-193 (masked)"""
+        return sum(ops.masked_mean(ops.depth_diff(computed_depth_list[s], predicted_depth_list[s]), mask_list[s])
+                   for s in range(self.num_scales))
+
+    def compute_dynamic_mask(self, intrinsics, depth, pose, flow):
+        """model_geometry.py:685-713 -> (flow_diffs, dynamic_masks, flow_diff_scores)"""
+        diffs, masks, scores = [], [], []
+        H0 = depth[0].size(2)
+        for s in range(self.num_scales):
+            h = depth[s].size(2)
+            Ks = torch.cat((intrinsics[:, 0:2] / (H0 / h), intrinsics[:, 2:]), dim=1)
+            rf = calculate_rigid_flow(depth[s], pose, Ks)
+            fd, dyn, score = ops.dynamic_mask(flow[s], rf, self.flow_consist_alpha, self.flow_consist_beta)
+            diffs.append(fd); masks.append(dyn); scores.append(score)
+        return diffs, masks, scores
+
+    def compute_depth_flow_consis_loss(self, flow_diffs, masks=None, scales=3):
+        """model_geometry.py:716-732"""
+        return sum(ops.masked_mean(flow_diffs[s], None if masks is None else masks[s]) for s in range(scales))
+
+    def compute_epipolar_map(self, pose, flow, intrinsics, intrinsics_inverse):
+        """model_geometry.py:355-403 -> (B,1,h,w) point-to-epipolar-line distance"""
+        E = compute_essential_matrix(pose)
+        Fm = intrinsics_inverse.transpose(1, 2).bmm(E.bmm(intrinsics_inverse))
+        return ops.epipolar_distance(flow, Fm.contiguous())
+
+    def compute_epipolar_loss(self, dist_map, rigid_mask):
+        """model_geometry.py:413-418: the masked value is overwritten by the plain mean (:416)."""
+        return ops.masked_mean(dist_map, None)
+
+    def get_rigid_mask(self, dist_map):
+        """model_geometry.py:420-425"""
+        return ops.rigid_mask(dist_map, self.rigid_thres, self.inlier_thres)
+
+    def fusion_mask(self, valid_mask, occ_mask, dynamic_mask):
+        """model_geometry.py:735-745"""
+        return [ops.mask_product([valid_mask[s], occ_mask[s], dynamic_mask[s]]) for s in range(self.num_scales)]
+
+    def fusion_mask_4item(self, valid_mask, occ_mask, dynamic_mask, texture_mask):
+        """model_geometry.py:747-756"""
+        return [ops.mask_product([valid_mask[s], occ_mask[s], dynamic_mask[s], texture_mask[s]]) for s in range(self.num_scales)]
+
+    def fusion_mask_2item(self, valid_mask, occ_mask, invert_second: bool = False):
+        """model_geometry.py:757-765 (``invert_second`` fuses the ``[1-mask for mask in ...]`` of :863-864)"""
+        return [ops.mask_product([valid_mask[s], occ_mask[s]], [False, invert_second]) for s in range(self.num_scales)]
+
+    def forward_losses(self, img_l, img, img_r, optical_flows_fwd, optical_flows_bwd, disp_list, disp_l_list, disp_r_list,
+                       pose_vectors, K, K_inv) -> Tuple[Dict[str, Tensor], Dict]:
+        """Loss body of ``Model_geometry.forward`` (model_geometry.py:777-951) given the network outputs.
+        The second return value holds the device-side masks (the reference's ``mask_pack`` without its
+        unconditional D2H copies, :871-880)."""
+        S = self.num_scales
+        pc, pl, pr = (self.generate_img_pyramid(x, S) for x in (img, img_l, img_r))
+        pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
+        rec_l, val_l, _, _ = self.reconstruction(img_l, K, disp_list, disp_l_list, pose_bwd)
+        rec_r, val_r, _, _ = self.reconstruction(img_r, K, disp_list, disp_r_list, pose_fwd)
+        tex_b = self.compute_texture_mask(pc, rec_l, pl)
+        tex_f = self.compute_texture_mask(pc, rec_r, pr)
+        from_l = self.warp_flow_pyramid(pl, optical_flows_bwd)
+        from_r = self.warp_flow_pyramid(pr, optical_flows_fwd)
+        occ_b, occ_f, valid_b, valid_f = self.compute_occ_weight(from_l, pc, from_r)
+        fd_b, dyn_b, _ = self.compute_dynamic_mask(K, disp_list, pose_bwd, optical_flows_bwd)
+        fd_f, dyn_f, _ = self.compute_dynamic_mask(K, disp_list, pose_fwd, optical_flows_fwd)
+        dist_b = self.compute_epipolar_map(pose_bwd, optical_flows_bwd[0], K, K_inv)
+        dist_f = self.compute_epipolar_map(pose_fwd, optical_flows_fwd[0], K, K_inv)
+        rigid_f, inlier_f, _ = self.get_rigid_mask(dist_f)
+
+        fwd_mask = self.fusion_mask(valid_f, occ_f, dyn_f)
+        bwd_mask = self.fusion_mask(valid_b, occ_b, dyn_b)
+        fwd_mask_tex = self.fusion_mask_2item(fwd_mask, tex_f)
+        bwd_mask_tex = self.fusion_mask_2item(bwd_mask, tex_b)
+        fwd_vo = self.fusion_mask_2item(valid_f, occ_f)
+        bwd_vo = self.fusion_mask_2item(valid_b, occ_b)
+        fwd_vo_rigid = self.fusion_mask_2item(fwd_vo, dyn_f)
+        bwd_vo_rigid = self.fusion_mask_2item(bwd_vo, dyn_b)
+        fwd_vo_dyna = self.fusion_mask_2item(fwd_vo, dyn_f, invert_second=True)
+        bwd_vo_dyna = self.fusion_mask_2item(bwd_vo, dyn_b, invert_second=True)
+
+        P = self.compute_photometric_loss
+        loss = {
+            "loss_depth_pixel": P(pc, rec_l, bwd_mask_tex) + P(pc, rec_r, fwd_mask_tex),
+            "loss_depth_ssim": _zeros2(img),
+            "loss_depth_smooth": self.compute_smooth_loss(img, disp_list) + self.compute_smooth_loss(img_l, disp_l_list)
+                                 + self.compute_smooth_loss(img_r, disp_r_list),
+            "loss_depth_consis": _zeros2(img),
+            "loss_flow_pixel": P(pc, from_l, bwd_vo_rigid) + P(pc, from_r, fwd_vo_rigid)
+                               + 2 * P(pc, from_l, bwd_vo_dyna) + 2 * P(pc, from_r, fwd_vo_dyna),
+            "loss_flow_ssim": self.compute_ssim_loss(pc, from_l, bwd_vo) + self.compute_ssim_loss(pc, from_r, fwd_vo),
+            "loss_flow_smooth": self.compute_loss_flow_smooth(optical_flows_fwd, pc) + self.compute_loss_flow_smooth(optical_flows_bwd, pc),
+            "loss_flow_consis": self.compute_loss_flow_consis(optical_flows_fwd, optical_flows_bwd, occ_f),
+            "loss_depth_flow_consis": self.compute_depth_flow_consis_loss(fd_b, bwd_mask, 1)
+                                      + self.compute_depth_flow_consis_loss(fd_f, fwd_mask, 1),
+            "loss_epipolar": self.compute_epipolar_loss(dist_b, dyn_b[0]) + self.compute_epipolar_loss(dist_f, dyn_f[0]),
+            "loss_triangle": _zeros2(img), "loss_pnp": _zeros2(img), "loss_eight_point": _zeros2(img),
+        }
+        masks = dict(occ_b=occ_b, occ_f=occ_f, valid_b=valid_b, valid_f=valid_f, dyn_b=dyn_b, dyn_f=dyn_f, tex_b=tex_b, tex_f=tex_f,
+                     val_l=val_l, val_r=val_r, dist_b=dist_b, dist_f=dist_f, rigid_f=rigid_f, inlier_f=inlier_f, fwd_mask=fwd_mask)
+        return loss, masks

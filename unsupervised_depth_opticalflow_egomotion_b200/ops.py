@@ -224,3 +224,463 @@ def flow_loss(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r_pyr:
     if as_matrix:
         return loss
     return {k: loss[i] for i, k in enumerate(FLOW_LOSS_KEYS)}
+
+
+# ================================================================================================
+# stand-alone terms, masks and geometry (one kernel family per reference method)
+# ================================================================================================
+def _call(name: str, *args, launches: int = 1) -> None:
+    _cabi.check(getattr(_cabi.lib(), name)(*args), name)
+    _count(launches)
+
+
+def _reduce_ws(B: int, H: int, W: int, device) -> Tensor:
+    n = int(_cabi.lib().ugl_reduce_workspace_bytes(B, H, W))
+    return torch.empty((n + 7) // 8, dtype=torch.int64, device=device)
+
+
+def _nbytes(t: Tensor) -> int:
+    return t.numel() * t.element_size()
+
+
+class _MaskedMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, mask, mode):
+        a = _dev(a, "a")
+        b = _dev(b, "b") if b is not None else None
+        mask = _dev(mask, "mask").detach() if mask is not None else None
+        B, Cc, H, W = a.shape
+        if b is not None and b.shape != a.shape:
+            raise ValueError("masked_mean: a %s and b %s differ" % (tuple(a.shape), tuple(b.shape)))
+        if mask is not None and tuple(mask.shape) != (B, 1, H, W):
+            raise ValueError("masked_mean: mask must be (B,1,H,W), got %s" % (tuple(mask.shape),))
+        out = torch.empty(B, device=a.device, dtype=torch.float32)
+        den = torch.empty_like(out)
+        ws = _reduce_ws(B, H, W, a.device)
+        with torch.cuda.device_of(a):
+            _call("ugl_masked_mean_forward", a.data_ptr(), _ptr(b), _ptr(mask), B, Cc, H, W, mode, out.data_ptr(), den.data_ptr(),
+                  ws.data_ptr(), _nbytes(ws), _stream_ptr(), launches=2)
+        ctx.save_for_backward(a, b, mask, den)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b, mask, den = ctx.saved_tensors
+        B, Cc, H, W = a.shape
+        gout = _dev(gout, "grad_out")
+        need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and b is not None
+        ga = torch.empty_like(a) if need_a else None
+        gb = torch.empty_like(b) if need_b else None
+        if ga is not None or gb is not None:
+            with torch.cuda.device_of(a):
+                _call("ugl_masked_mean_backward", a.data_ptr(), _ptr(b), _ptr(mask), den.data_ptr(), gout.data_ptr(), B, Cc, H, W,
+                      ctx.mode, _ptr(ga), _ptr(gb), _stream_ptr())
+        return ga, gb, None, None
+
+
+def masked_l1(img: Tensor, warped: Tensor, mask: Optional[Tensor]) -> Tensor:
+    """One level of ``compute_photometric_loss`` (model_geometry.py:143-153): P(|img - warped|, mask) -> (B,)."""
+    return _MaskedMeanFn.apply(img, warped, mask, 0)
+
+
+def masked_mean(diff: Tensor, mask: Optional[Tensor]) -> Tensor:
+    """One level of ``compute_loss_with_mask`` / ``compute_depth_flow_consis_loss``: P(diff, mask) -> (B,);
+    ``mask=None`` is the plain per-sample mean."""
+    return _MaskedMeanFn.apply(diff, None, mask, 1)
+
+
+class _SsimFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = _dev(x, "x"), _dev(y, "y")
+        if x.shape != y.shape or x.dim() != 4:
+            raise ValueError("SSIM: x %s and y %s must be equal 4-d shapes" % (tuple(x.shape), tuple(y.shape)))
+        B, Cc, H, W = x.shape
+        out = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _call("ugl_ssim_forward", x.data_ptr(), y.data_ptr(), B, Cc, H, W, out.data_ptr(), _stream_ptr())
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, y = ctx.saved_tensors
+        B, Cc, H, W = x.shape
+        gout = _dev(gout, "grad_out")
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device_of(x):
+            _call("ugl_ssim_backward", x.data_ptr(), y.data_ptr(), gout.data_ptr(), B, Cc, H, W, _ptr(gx), _ptr(gy), _stream_ptr())
+        return gx, gy
+
+
+def ssim(x: Tensor, y: Tensor) -> Tensor:
+    """Drop-in for ``SSIM(x, y)`` (pytorch_ssim/ssim.py:4-19)."""
+    return _SsimFn.apply(x, y)
+
+
+class _SsimLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, warped, mask):
+        img, warped = _dev(img, "img"), _dev(warped, "warped")
+        mask = _dev(mask, "mask").detach() if mask is not None else None
+        B, Cc, H, W = img.shape
+        out = torch.empty(B, device=img.device, dtype=torch.float32)
+        den = torch.empty_like(out)
+        n = int(_cabi.lib().ugl_ssim_loss_workspace_bytes(B, Cc, H, W))
+        ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=img.device)
+        with torch.cuda.device_of(img):
+            _call("ugl_ssim_loss_forward", img.data_ptr(), warped.data_ptr(), _ptr(mask), B, Cc, H, W, out.data_ptr(), den.data_ptr(),
+                  ws.data_ptr(), _nbytes(ws), _stream_ptr(), launches=2)
+        ctx.save_for_backward(img, warped, mask, den)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        img, warped, mask, den = ctx.saved_tensors
+        B, Cc, H, W = img.shape
+        gout = _dev(gout, "grad_out")
+        gi = torch.empty_like(img) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(warped) if ctx.needs_input_grad[1] else None
+        if gi is not None or gw is not None:
+            with torch.cuda.device_of(img):
+                _call("ugl_ssim_loss_backward", img.data_ptr(), warped.data_ptr(), _ptr(mask), den.data_ptr(), gout.data_ptr(), B, Cc,
+                      H, W, _ptr(gi), _ptr(gw), _stream_ptr())
+        return gi, gw, None
+
+
+def ssim_loss(img: Tensor, warped: Tensor, mask: Optional[Tensor]) -> Tensor:
+    """One level of ``compute_ssim_loss`` / ``compute_loss_ssim`` (model_geometry.py:212-223) -> (B,)."""
+    return _SsimLossFn.apply(img, warped, mask)
+
+
+class _OccWeightsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, from_l, img, from_r, soft):
+        from_l, img, from_r = _dev(from_l, "from_l"), _dev(img, "img"), _dev(from_r, "from_r")
+        B, Cc, H, W = img.shape
+        if Cc != 3:
+            raise ValueError("occlusion weights expect 3-channel images")
+        o = [torch.empty((B, 1, H, W), device=img.device, dtype=torch.float32) for _ in range(6)]
+        with torch.cuda.device_of(img):
+            _call("ugl_occlusion_weights", from_l.data_ptr(), img.data_ptr(), from_r.data_ptr(), B, H, W, int(soft),
+                  *[t.data_ptr() for t in o], _stream_ptr())
+        ctx.save_for_backward(from_l, img, from_r)
+        ctx.mark_non_differentiable(*o[:4])
+        return tuple(o)
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2, g3, g_db, g_df):
+        from_l, img, from_r = ctx.saved_tensors
+        B, Cc, H, W = img.shape
+        gl = gr = None
+        with torch.cuda.device_of(img):
+            if ctx.needs_input_grad[0] and g_db is not None:
+                gl = torch.empty_like(from_l)
+                _call("ugl_channel_mean_abs_diff_backward", img.data_ptr(), from_l.data_ptr(), _dev(g_db, "g").data_ptr(), B, Cc, H, W,
+                      gl.data_ptr(), _stream_ptr())
+            if ctx.needs_input_grad[2] and g_df is not None:
+                gr = torch.empty_like(from_r)
+                _call("ugl_channel_mean_abs_diff_backward", img.data_ptr(), from_r.data_ptr(), _dev(g_df, "g").data_ptr(), B, Cc, H, W,
+                      gr.data_ptr(), _stream_ptr())
+        return gl, None, gr, None
+
+
+def occlusion_weights(from_l: Tensor, img: Tensor, from_r: Tensor, soft: bool):
+    """(w_bwd, w_fwd, valid_bwd, valid_fwd, diff_bwd, diff_fwd) for one level — ``compute_occ_weight``
+    (soft=False, model_geometry.py:105-132) / ``compute_diff_weight`` (soft=True, model_flow.py:105-138).
+    The weights / valid maps are constants; the diffs are differentiable w.r.t. the warped images."""
+    return _OccWeightsFn.apply(from_l, img, from_r, bool(soft))
+
+
+def texture_mask(img: Tensor, rec: Tensor, src: Tensor) -> Tensor:
+    """One level of ``compute_texture_mask`` (model_geometry.py:134-140); constant for autograd."""
+    img, rec, src = _dev(img, "img").detach(), _dev(rec, "rec").detach(), _dev(src, "src").detach()
+    B, Cc, H, W = img.shape
+    out = torch.empty((B, 1, H, W), device=img.device, dtype=torch.float32)
+    with torch.cuda.device_of(img):
+        _call("ugl_texture_mask", img.data_ptr(), rec.data_ptr(), src.data_ptr(), B, H, W, out.data_ptr(), _stream_ptr())
+    return out
+
+
+class _DynamicMaskFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, rflow, alpha, beta):
+        flow, rflow = _dev(flow, "flow"), _dev(rflow, "rigid_flow")
+        B, _, H, W = flow.shape
+        fd = torch.empty_like(flow)
+        dyn = torch.empty((B, 1, H, W), device=flow.device, dtype=torch.float32)
+        score = torch.empty_like(dyn)
+        with torch.cuda.device_of(flow):
+            _call("ugl_dynamic_mask_forward", flow.data_ptr(), rflow.data_ptr(), B, H, W, float(alpha), float(beta), fd.data_ptr(),
+                  dyn.data_ptr(), score.data_ptr(), _stream_ptr())
+        ctx.save_for_backward(flow, rflow)
+        ctx.mark_non_differentiable(dyn, score)
+        return fd, dyn, score
+
+    @staticmethod
+    def backward(ctx, g_fd, g_dyn, g_score):
+        flow, rflow = ctx.saved_tensors
+        g_fd = _dev(g_fd, "grad")
+        gf = torch.empty_like(flow) if ctx.needs_input_grad[0] else None
+        gr = torch.empty_like(rflow) if ctx.needs_input_grad[1] else None
+        if gf is not None or gr is not None:
+            with torch.cuda.device_of(flow):   # fd = |rflow - flow|
+                _call("ugl_abs_diff_backward", rflow.data_ptr(), flow.data_ptr(), g_fd.data_ptr(), flow.numel(), _ptr(gr), _ptr(gf),
+                      _stream_ptr())
+        return gf, gr, None, None
+
+
+def dynamic_mask(flow: Tensor, rigid_flow: Tensor, alpha: float, beta: float):
+    """Body of ``compute_dynamic_mask`` for one level (model_geometry.py:698-711): (flow_diff, dyn_mask, score)."""
+    return _DynamicMaskFn.apply(flow, rigid_flow, alpha, beta)
+
+
+def mask_product(masks: Sequence[Tensor], invert: Optional[Sequence[bool]] = None) -> Tensor:
+    """``fusion_mask*`` (model_geometry.py:735-765): product of up to four maps, ``invert[k]`` uses 1 - m."""
+    ms = [_dev(m, "mask").detach() for m in masks]
+    if not 1 <= len(ms) <= 4 or any(m.shape != ms[0].shape for m in ms):
+        raise ValueError("mask_product: need 1..4 maps of one shape")
+    out = torch.empty_like(ms[0])
+    arr = (C.c_void_p * len(ms))(*[m.data_ptr() for m in ms])
+    inv = (C.c_int32 * len(ms))(*[int(bool(v)) for v in (invert or [False] * len(ms))])
+    with torch.cuda.device_of(out):
+        _call("ugl_mask_product", arr, inv, len(ms), out.numel(), out.data_ptr(), _stream_ptr())
+    return out
+
+
+def rigid_mask(dist: Tensor, rigid_thres: float = 0.5, inlier_thres: float = 0.1):
+    """``get_rigid_mask`` (model_geometry.py:420-425): (rigid, inlier, score), constants for autograd."""
+    dist = _dev(dist, "dist").detach()
+    o = [torch.empty_like(dist) for _ in range(3)]
+    with torch.cuda.device_of(dist):
+        _call("ugl_rigid_mask", dist.data_ptr(), dist.numel(), float(rigid_thres), float(inlier_thres), *[t.data_ptr() for t in o],
+              _stream_ptr())
+    return tuple(o)
+
+
+class _FlowSmoothFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, img):
+        flow, img = _dev(flow, "flow"), _dev(img, "img").detach()
+        B, _, H, W = flow.shape
+        out = torch.empty(B, device=flow.device, dtype=torch.float32)
+        ws = _reduce_ws(B, H, W, flow.device)
+        with torch.cuda.device_of(flow):
+            _call("ugl_flow_smooth_forward", flow.data_ptr(), img.data_ptr(), B, H, W, out.data_ptr(), ws.data_ptr(), _nbytes(ws),
+                  _stream_ptr(), launches=2)
+        ctx.save_for_backward(flow, img)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        flow, img = ctx.saved_tensors
+        B, _, H, W = flow.shape
+        g = torch.empty_like(flow)
+        with torch.cuda.device_of(flow):
+            _call("ugl_flow_smooth_backward", flow.data_ptr(), img.data_ptr(), _dev(gout, "g").data_ptr(), B, H, W, g.data_ptr(), _stream_ptr())
+        return g, None
+
+
+def flow_smooth(flow: Tensor, img: Tensor) -> Tensor:
+    """``cal_grad2_error(flow/20, img)`` for one level (model_geometry.py:254-279) -> (B,)."""
+    return _FlowSmoothFn.apply(flow, img)
+
+
+class _FlowConsisFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fwd, bwd, occ):
+        fwd, bwd, occ = _dev(fwd, "fwd"), _dev(bwd, "bwd").detach(), _dev(occ, "occ").detach()
+        B, _, H, W = fwd.shape
+        out = torch.empty(B, device=fwd.device, dtype=torch.float32)
+        den = torch.empty_like(out)
+        ws = _reduce_ws(B, H, W, fwd.device)
+        with torch.cuda.device_of(fwd):
+            _call("ugl_flow_consis_forward", fwd.data_ptr(), bwd.data_ptr(), occ.data_ptr(), B, H, W, out.data_ptr(), den.data_ptr(),
+                  ws.data_ptr(), _nbytes(ws), _stream_ptr(), launches=2)
+        ctx.save_for_backward(fwd, bwd, occ, den)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        fwd, bwd, occ, den = ctx.saved_tensors
+        B, _, H, W = fwd.shape
+        g = torch.empty_like(fwd)
+        with torch.cuda.device_of(fwd):
+            _call("ugl_flow_consis_backward", fwd.data_ptr(), bwd.data_ptr(), occ.data_ptr(), den.data_ptr(), _dev(gout, "g").data_ptr(),
+                  B, H, W, g.data_ptr(), _stream_ptr())
+        return g, None, None
+
+
+def flow_consis(fwd: Tensor, bwd: Tensor, occ: Tensor) -> Tensor:
+    """One level of ``compute_loss_flow_consis`` (model_geometry.py:195-210) -> (B,)."""
+    return _FlowConsisFn.apply(fwd, bwd, occ)
+
+
+class _DepthDiffFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, comp, proj):
+        comp, proj = _dev(comp, "computed_depth"), _dev(proj, "predicted_depth")
+        out = torch.empty_like(comp)
+        with torch.cuda.device_of(comp):
+            _call("ugl_depth_diff_forward", comp.data_ptr(), proj.data_ptr(), comp.numel(), out.data_ptr(), _stream_ptr())
+        ctx.save_for_backward(comp, proj)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        comp, proj = ctx.saved_tensors
+        gc = torch.empty_like(comp) if ctx.needs_input_grad[0] else None
+        gp = torch.empty_like(proj) if ctx.needs_input_grad[1] else None
+        if gc is not None or gp is not None:
+            with torch.cuda.device_of(comp):
+                _call("ugl_depth_diff_backward", comp.data_ptr(), proj.data_ptr(), _dev(g, "g").data_ptr(), comp.numel(), _ptr(gc), _ptr(gp),
+                      _stream_ptr())
+        return gc, gp
+
+
+def depth_diff(comp: Tensor, proj: Tensor) -> Tensor:
+    """clamp(|comp - proj| / |comp + proj|, 0, 1) of ``compute_consis_loss`` (model_geometry.py:186-188)."""
+    return _DepthDiffFn.apply(comp, proj)
+
+
+class _DispSmoothFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, *disps):
+        img = _dev(img, "img").detach()
+        disps = [_dev(d, "disp") for d in disps]
+        B, _, H, W = img.shape
+        L = len(disps)
+        out = torch.empty(B, device=img.device, dtype=torch.float32)
+        ws = _reduce_ws(B, H, W, img.device)
+        arr = (C.c_void_p * L)(*[d.data_ptr() for d in disps])
+        hs = (C.c_int32 * L)(*[d.shape[2] for d in disps])
+        wsz = (C.c_int32 * L)(*[d.shape[3] for d in disps])
+        with torch.cuda.device_of(img):
+            _call("ugl_disp_smooth_forward", img.data_ptr(), arr, hs, wsz, L, B, H, W, out.data_ptr(), ws.data_ptr(), _nbytes(ws),
+                  _stream_ptr(), launches=2)
+        ctx.save_for_backward(img, *disps)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        img, *disps = ctx.saved_tensors
+        B, _, H, W = img.shape
+        L = len(disps)
+        grads = [torch.empty_like(d) for d in disps]
+        n = int(_cabi.lib().ugl_disp_smooth_backward_workspace_bytes(B, H, W))
+        ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=img.device)
+        arr = (C.c_void_p * L)(*[d.data_ptr() for d in disps])
+        garr = (C.c_void_p * L)(*[g.data_ptr() for g in grads])
+        hs = (C.c_int32 * L)(*[d.shape[2] for d in disps])
+        wsz = (C.c_int32 * L)(*[d.shape[3] for d in disps])
+        with torch.cuda.device_of(img):
+            _call("ugl_disp_smooth_backward", img.data_ptr(), arr, hs, wsz, L, _dev(gout, "g").data_ptr(), B, H, W, garr, ws.data_ptr(),
+                  _nbytes(ws), _stream_ptr(), launches=2 * L - 1)
+        return (None, *grads)
+
+
+def disp_smooth(img: Tensor, disps: Sequence[Tensor]) -> Tensor:
+    """``compute_smooth_loss(img, disps)`` (model_geometry.py:225-252) for ``len(disps)`` levels -> (B,)."""
+    return _DispSmoothFn.apply(img, *disps)
+
+
+class _ReprojectFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, depth, ref_depth, Kinv, P):
+        img, depth, ref_depth = _dev(img, "img"), _dev(depth, "depth"), _dev(ref_depth, "ref_depth")
+        Kinv, P = _dev(Kinv, "Kinv").detach(), _dev(P, "P")
+        B, Cc, H, W = img.shape
+        out = torch.empty_like(img)
+        valid, proj, comp = (torch.empty((B, 1, H, W), device=img.device, dtype=torch.float32) for _ in range(3))
+        with torch.cuda.device_of(img):
+            _call("ugl_reproject_forward", img.data_ptr(), depth.data_ptr(), ref_depth.data_ptr(), Kinv.data_ptr(), P.data_ptr(), B, Cc, H,
+                  W, out.data_ptr(), valid.data_ptr(), proj.data_ptr(), comp.data_ptr(), _stream_ptr())
+        ctx.save_for_backward(img, depth, ref_depth, Kinv, P)
+        ctx.mark_non_differentiable(valid)
+        return out, valid, proj, comp
+
+    @staticmethod
+    def backward(ctx, g_img, g_valid, g_proj, g_comp):
+        img, depth, ref_depth, Kinv, P = ctx.saved_tensors
+        B, Cc, H, W = img.shape
+        need_img, need_depth, need_ref, _, need_P = ctx.needs_input_grad
+        g_img = _dev(g_img, "g") if g_img is not None else None
+        g_proj = _dev(g_proj, "g") if g_proj is not None else None
+        g_comp = _dev(g_comp, "g") if g_comp is not None else None
+        gd = torch.empty_like(depth) if need_depth else None
+        gP = torch.empty((B, 3, 4), device=img.device, dtype=torch.float32)
+        gi = torch.empty_like(img) if need_img else None
+        gr = torch.empty_like(ref_depth) if need_ref else None
+        n = int(_cabi.lib().ugl_reproject_backward_workspace_bytes(B, Cc, H, W, int(need_img), int(need_ref)))
+        ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=img.device)
+        with torch.cuda.device_of(img):
+            _call("ugl_reproject_backward", img.data_ptr(), depth.data_ptr(), ref_depth.data_ptr(), Kinv.data_ptr(), P.data_ptr(),
+                  _ptr(g_img), _ptr(g_proj), _ptr(g_comp), B, Cc, H, W, _ptr(gd), gP.data_ptr(), _ptr(gi), _ptr(gr), ws.data_ptr(),
+                  _nbytes(ws), _stream_ptr(), launches=2 + (5 if (need_img or need_ref) else 0))
+        return gi, gd, gr, None, (gP if need_P else None)
+
+
+def reproject(img: Tensor, depth: Tensor, ref_depth: Tensor, Kinv: Tensor, P: Tensor):
+    """Core of ``inverse_warp2`` (structures/inverse_warp.py:284-303) given K^-1 and P = K [R|t]:
+    (projected_img, valid_mask, projected_depth, computed_depth)."""
+    return _ReprojectFn.apply(img, depth, ref_depth, Kinv, P)
+
+
+class _RigidFlowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, Kinv, P):
+        depth, Kinv, P = _dev(depth, "depth"), _dev(Kinv, "Kinv").detach(), _dev(P, "P")
+        B, _, H, W = depth.shape
+        out = torch.empty((B, 2, H, W), device=depth.device, dtype=torch.float32)
+        with torch.cuda.device_of(depth):
+            _call("ugl_rigid_flow_forward", depth.data_ptr(), Kinv.data_ptr(), P.data_ptr(), B, H, W, out.data_ptr(), _stream_ptr())
+        ctx.save_for_backward(depth, Kinv, P)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        depth, Kinv, P = ctx.saved_tensors
+        B, _, H, W = depth.shape
+        gd = torch.empty_like(depth) if ctx.needs_input_grad[0] else None
+        gP = torch.empty((B, 3, 4), device=depth.device, dtype=torch.float32)
+        ws = _reduce_ws(B, H, W, depth.device)
+        with torch.cuda.device_of(depth):
+            _call("ugl_rigid_flow_backward", depth.data_ptr(), Kinv.data_ptr(), P.data_ptr(), _dev(g, "g").data_ptr(), B, H, W, _ptr(gd),
+                  gP.data_ptr(), ws.data_ptr(), _nbytes(ws), _stream_ptr(), launches=2)
+        return gd, None, (gP if ctx.needs_input_grad[2] else None)
+
+
+def rigid_flow(depth: Tensor, Kinv: Tensor, P: Tensor) -> Tensor:
+    """Core of ``calculate_rigid_flow`` (structures/inverse_warp.py:329-342) given K^-1 and P."""
+    return _RigidFlowFn.apply(depth, Kinv, P)
+
+
+class _EpipolarFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, Fm):
+        flow, Fm = _dev(flow, "flow"), _dev(Fm, "F")
+        B, _, H, W = flow.shape
+        out = torch.empty((B, 1, H, W), device=flow.device, dtype=torch.float32)
+        with torch.cuda.device_of(flow):
+            _call("ugl_epipolar_forward", flow.data_ptr(), Fm.data_ptr(), B, H, W, out.data_ptr(), _stream_ptr())
+        ctx.save_for_backward(flow, Fm)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        flow, Fm = ctx.saved_tensors
+        B, _, H, W = flow.shape
+        gf = torch.empty_like(flow) if ctx.needs_input_grad[0] else None
+        gF = torch.empty((B, 3, 3), device=flow.device, dtype=torch.float32)
+        ws = _reduce_ws(B, H, W, flow.device)
+        with torch.cuda.device_of(flow):
+            _call("ugl_epipolar_backward", flow.data_ptr(), Fm.data_ptr(), _dev(g, "g").data_ptr(), B, H, W, _ptr(gf), gF.data_ptr(),
+                  ws.data_ptr(), _nbytes(ws), _stream_ptr(), launches=2)
+        return gf, (gF if ctx.needs_input_grad[1] else None)
+
+
+def epipolar_distance(flow: Tensor, Fm: Tensor) -> Tensor:
+    """Core of ``compute_epipolar_map`` (model_geometry.py:381-391) given the fundamental matrix F (B,3,3)."""
+    return _EpipolarFn.apply(flow, Fm)
