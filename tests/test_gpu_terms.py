@@ -6,7 +6,7 @@ import torch
 from oracle import loss_port as P
 from unsupervised_depth_opticalflow_egomotion_b200 import losses, ops, structures
 from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
-from util import load_golden, golden_triplet, rel_err, loss_rel_err, LOSS_RTOL, GRAD_RTOL
+from util import load_golden, golden_triplet, rel_err, loss_rel_err, assert_loss_close, assert_grad_close, LOSS_RTOL, GRAD_RTOL
 
 pytestmark = pytest.mark.gpu
 
@@ -153,7 +153,13 @@ def test_epipolar_and_depth_diff_vs_oracle(cuda_device):
     fd, pd = t.flows_fwd[0].to(cuda_device).requires_grad_(True), (3.0 * t.pose[:, 1]).to(cuda_device).requires_grad_(True)
     out = gl.compute_epipolar_map(pd, fd, t.K.to(cuda_device), t.K_inv.to(cuda_device))
     ogf, ogp = torch.autograd.grad((out * go.to(cuda_device)).sum(), [fd, pd])
-    assert rel_err(out, ref) < 1e-5 and rel_err(ogf, rgf) < GRAD_RTOL and rel_err(ogp, rgp) < GRAD_RTOL
+    f64, p64 = t.flows_fwd[0].double().requires_grad_(True), (3.0 * t.pose[:, 1]).double().requires_grad_(True)
+    ref64 = P.epipolar_distance(p64, f64, t.K.double(), t.K_inv.double())
+    rgf64, rgp64 = torch.autograd.grad((ref64 * go.double()).sum(), [f64, p64])
+    # the numerator p2.F.p1 cancels ~100x: the fp32 reference itself is only good to ~1e-5 of the fp64 value
+    assert_grad_close("epipolar map", out, ref, ref64, rtol=1e-5)
+    assert_grad_close("epipolar d/dflow", ogf, rgf, rgf64)
+    assert_grad_close("epipolar d/dpose", ogp, rgp, rgp64)
     c, p = (torch.rand(2, 1, 8, 9, generator=_g(3)) + 0.1).requires_grad_(True), (torch.rand(2, 1, 8, 9, generator=_g(4)) + 0.1).requires_grad_(True)
     refd = ((c - p).abs() / (c + p).abs()).clamp(0, 1)
     rgc, rgp2 = torch.autograd.grad(refd.sum(), [c, p])
@@ -171,7 +177,8 @@ def _leaf_list(xs, dev):
 def _check_mode(loss, d, leaves, names, weights):
     for k, v in loss.items():
         if "out_" + k in d:
-            assert loss_rel_err(v, d["out_" + k]) < LOSS_RTOL, k
+            # loss_epipolar: cancellation-dominated (see util.py); the fixture has no fp64 twin, so 5e-5 there
+            assert loss_rel_err(v, d["out_" + k]) < (5e-5 if k == "loss_epipolar" else LOSS_RTOL), k
     total = sum(weights[k] * v.mean() for k, v in loss.items() if "out_" + k in d)
     grads = torch.autograd.grad(total, leaves, allow_unused=True)
     for n, g in zip(names, grads):
@@ -180,7 +187,7 @@ def _check_mode(loss, d, leaves, names, weights):
         if ref.abs().max() == 0:
             assert g.abs().max() == 0, n
         else:
-            assert rel_err(g, ref) < 1.5 * GRAD_RTOL, (n, rel_err(g, ref))
+            assert_grad_close(n, g, ref, None, rtol=1.5 * GRAD_RTOL)
 
 
 @pytest.mark.parametrize("name,variant", [("depth_mode_live", "live"), ("depth_mode_texture", "texture")])
@@ -235,8 +242,14 @@ def test_geom_mode_vs_oracle(cuda_device, B, H, W):
     pose = t.pose.detach().to(dev).requires_grad_(True)
     loss, masks = losses.GeometryLoss(3).forward_losses(t.img_l.to(dev), t.img.to(dev), t.img_r.to(dev), ff, fb, disp, disp_l, disp_r,
                                                         pose, t.K.to(dev), t.K_inv.to(dev))
+    t64 = make_triplet(B, H, W, 4, 3, seed=41, flow_mode="rigid")
+    dbl = lambda xs: [x.double().requires_grad_(True) for x in xs]
+    l64 = dbl(t64.flows_fwd) + dbl(t64.flows_bwd) + dbl(t64.disp) + dbl(t64.disp_l) + dbl(t64.disp_r) + [t64.pose.double().requires_grad_(True)]
+    ref64 = P.geom_mode_loss(t64.img_l.double(), t64.img.double(), t64.img_r.double(), l64[0:4], l64[4:8], l64[8:11], l64[11:14],
+                             l64[14:17], l64[17], t64.K.double(), t64.K_inv.double(), 3)
+    rg64 = torch.autograd.grad(sum(P.GEOM_WEIGHTS[k] * ref64[k].mean() for k in keys), l64, allow_unused=True)
     for k in keys:
-        assert loss_rel_err(loss[k], ref[k]) < LOSS_RTOL, k
+        assert_loss_close(k, loss[k], ref[k], ref64[k])
     flips = 0
     for key in ("occ_b", "occ_f", "valid_b", "valid_f", "dyn_b", "dyn_f", "tex_b", "tex_f", "val_l", "val_r"):
         for l in range(3):
@@ -244,11 +257,11 @@ def test_geom_mode_vs_oracle(cuda_device, B, H, W):
     assert flips == 0
     tot = sum(P.GEOM_WEIGHTS[k] * loss[k].mean() for k in keys)
     og = torch.autograd.grad(tot, ff + fb + disp + disp_l + disp_r + [pose], allow_unused=True)
-    for a, b in zip(og, rg):
+    for i, (a, b, c) in enumerate(zip(og, rg, rg64)):
         if b is None:
             assert a is None or a.abs().max() == 0
         else:
-            assert rel_err(a, b) < 1.5 * GRAD_RTOL
+            assert_grad_close("leaf %d" % i, a, b, c, rtol=1.5 * GRAD_RTOL)
 
 
 def test_flow_mode_composed_equals_fused(cuda_device):
