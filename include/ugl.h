@@ -67,6 +67,7 @@ typedef struct UglFlowLossArgs {
   void* workspace;
   uint64_t workspace_bytes;
   void* stream;                                /* cudaStream_t                                   */
+  float* basis[UGL_MAX_LEVELS];                /* (B,14,h,w) gradient basis maps  [single-pass mode] */
 } UglFlowLossArgs;
 
 uint64_t ugl_flow_loss_workspace_bytes(const UglFlowLossArgs* args);
@@ -74,6 +75,13 @@ int ugl_flow_loss_forward(const UglFlowLossArgs* args);
 int ugl_flow_loss_backward(const UglFlowLossArgs* args);
 /* number of kernel launches one forward / backward call issues (for launch accounting) */
 int ugl_flow_loss_launches(int backward);
+/* Single-pass mode: forward_grad computes the losses AND the un-normalised gradient of every term w.r.t. both
+ * flows into basis[l] (B,UGL_FLOW_BASIS_PLANES,h,w) in one stencil kernel (+ finalize); combine is the element-wise
+ * backward  grad = sum_k scale_k(sample, level) * basis_k.  Same results as forward + backward (recompute) with the
+ * photometry / SSIM work executed once instead of twice; costs 14 floats per pixel of saved state. */
+#define UGL_FLOW_BASIS_PLANES 14
+int ugl_flow_loss_forward_grad(const UglFlowLossArgs* args);
+int ugl_flow_loss_combine(const UglFlowLossArgs* args);
 
 /* ---------------------------------------------------------------------------------------------
  * Image pyramid — replaces generate_img_pyramid: model_flow.py:58-64 (mode 0: adaptive average

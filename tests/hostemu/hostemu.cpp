@@ -13,6 +13,7 @@
 
 #include "../../include/ugl.h"
 #include "../../unsupervised_depth_opticalflow_egomotion_b200/csrc/ugl_flow_loss.cuh"
+#include "../../unsupervised_depth_opticalflow_egomotion_b200/csrc/ugl_flow_grad.cuh"
 #include "../../unsupervised_depth_opticalflow_egomotion_b200/csrc/ugl_primitives.cuh"
 
 using namespace ugl;
@@ -89,6 +90,63 @@ extern "C" int emu_flow_loss_backward(const UglFlowLossArgs* a) {
       Tile::phase3(p, tc, k, dir, 0, 1, sm.data(), g);
     }
     Tile::phase4(p, tc, k, 0, 1, sm.data(), g);
+  }
+  return 0;
+}
+
+static void emu_finalize(const FlowLossParams& p, const std::vector<float>& partials) {
+  for (int b = 0; b < p.B; ++b) {
+    float tot[4] = {0, 0, 0, 0};
+    for (int l = 0; l < p.scales; ++l) {
+      const FlowLevelDesc& L = p.lv[l];
+      const int per_img = L.tiles_x * L.tiles_y;
+      double s[FA_COUNT] = {0};
+      for (int t = 0; t < per_img; ++t)
+        for (int k = 0; k < FA_COUNT; ++k) s[k] += partials[((size_t)L.tile_begin + (size_t)b * per_img + t) * FA_COUNT + k];
+      float S[FA_COUNT], out[4];
+      for (int k = 0; k < FA_COUNT; ++k) { S[k] = (float)s[k]; p.stats[((size_t)b * p.scales + l) * FA_COUNT + k] = S[k]; }
+      flow_level_losses(S, L.h, L.w, out);
+      for (int k = 0; k < 4; ++k) tot[k] += out[k];
+    }
+    for (int k = 0; k < 4; ++k) p.loss[k * p.B + b] = tot[k];
+  }
+}
+
+// single-pass mode: losses + gradient basis, then the element-wise combine
+extern "C" int emu_flow_loss_forward_grad(const UglFlowLossArgs* a) {
+  FlowGradParams gp;
+  fill_params<kBTW, kBTH>(a, false, gp.base);
+  for (int l = 0; l < a->scales; ++l) gp.basis[l] = a->basis[l];
+  using Tile = FlowGradTile<kBTW, kBTH, 1>;
+  std::vector<float> partials((size_t)gp.base.total_tiles * FA_COUNT, 0.f), sm(Tile::kSmemFloats);
+  for (int tile = 0; tile < gp.base.total_tiles; ++tile) {
+    const TileCoord tc = decode_tile<kBTW, kBTH>(gp.base, tile);
+    float acc[FA_COUNT] = {0};
+    Tile::phase1(gp, tc, 0, 1, sm.data(), acc);
+    for (int dir = 0; dir < 2; ++dir) {
+      Tile::phase2(gp, tc, dir, 0, 1, sm.data(), acc);
+      Tile::phase3(gp, tc, dir, 0, 1, sm.data());
+    }
+    Tile::phase4(gp, tc, 0, 1, sm.data(), acc);
+    for (int k = 0; k < FA_COUNT; ++k) partials[(size_t)tile * FA_COUNT + k] = acc[k];
+  }
+  emu_finalize(gp.base, partials);
+  return 0;
+}
+
+extern "C" int emu_flow_loss_combine(const UglFlowLossArgs* a) {
+  FlowGradParams gp;
+  fill_params<kBTW, kBTH>(a, true, gp.base);
+  const FlowLossParams& p = gp.base;
+  for (int l = 0; l < p.scales; ++l) {
+    const FlowLevelDesc& L = p.lv[l];
+    const int plane = L.h * L.w;
+    for (int b = 0; b < p.B; ++b) {
+      const FlowCombineScales k = flow_combine_scales(p.stats + ((size_t)b * p.scales + l) * FA_COUNT, L.h, L.w, p.gloss, p.B, b);
+      for (int pix = 0; pix < plane; ++pix)
+        flow_combine_pixel(a->basis[l] + (size_t)b * kBasisPlanes * plane, plane, pix, k, L.gflow_f + (size_t)b * 2 * plane,
+                           L.gflow_b + (size_t)b * 2 * plane);
+    }
   }
   return 0;
 }

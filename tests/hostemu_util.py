@@ -57,3 +57,19 @@ def emu_flow_loss(img_l, img, img_r, flows_fwd, flows_bwd, scales, gloss):
     emu().emu_flow_loss_forward(C.byref(a))
     emu().emu_flow_loss_backward(C.byref(a))
     return loss, gf, gb, stats
+
+
+def emu_flow_loss_single_pass(img_l, img, img_r, flows_fwd, flows_bwd, scales, gloss):
+    """single-pass mode (forward_grad + combine) via the host emulator"""
+    B = img[0].shape[0]
+    loss = torch.zeros(4, B)
+    stats = torch.zeros(B, scales, _cabi.FLOW_NSTATS)
+    gf = [torch.zeros_like(f) for f in flows_fwd[:scales]]
+    gb = [torch.zeros_like(f) for f in flows_bwd[:scales]]
+    basis = [torch.zeros(B, _cabi.FLOW_BASIS_PLANES, f.shape[2], f.shape[3]) for f in flows_fwd[:scales]]
+    a = flow_loss_args(img_l, img, img_r, flows_fwd, flows_bwd, scales, loss, stats, gloss, gf, gb)
+    for l in range(scales):
+        a.basis[l] = basis[l].data_ptr()
+    emu().emu_flow_loss_forward_grad(C.byref(a))
+    emu().emu_flow_loss_combine(C.byref(a))
+    return loss, gf, gb, stats

@@ -47,7 +47,7 @@ def test_struct_layout_matches_header(lib):
     a = _cabi.UglFlowLossArgs
     assert a.height.offset == 12 and a.width.offset == 36
     assert a.img_l.offset == 64 and a.img_l.size == 48
-    assert C.sizeof(a) == 64 + 5 * 48 + 3 * 8 + 2 * 48 + 8 + 8 + 8
+    assert C.sizeof(a) == 64 + 5 * 48 + 3 * 8 + 2 * 48 + 8 + 8 + 8 + 48
 
 
 def test_argument_validation_happens_before_launch(lib):

@@ -12,13 +12,13 @@ pytestmark = pytest.mark.gpu
 KEYS = list(ops.FLOW_LOSS_KEYS)
 
 
-def _cuda_flow(t, scales, gl, dev):
+def _cuda_flow(t, scales, gl, dev, mode="single_pass"):
     L = len(t.flows_fwd)
     t = t.to(dev)
     pl, pc, pr = (ops.image_pyramid(x, L, "box") for x in (t.img_l, t.img, t.img_r))
     ff = [f.detach().clone().requires_grad_(True) for f in t.flows_fwd]
     fb = [f.detach().clone().requires_grad_(True) for f in t.flows_bwd]
-    loss = ops.flow_loss(pl, pc, pr, ff, fb, scales, as_matrix=True)
+    loss = ops.flow_loss(pl, pc, pr, ff, fb, scales, as_matrix=True, mode=mode)
     g = torch.autograd.grad(loss, ff[:scales] + fb[:scales], grad_outputs=gl.to(dev))
     return loss.cpu(), [x.cpu() for x in g[:scales]], [x.cpu() for x in g[scales:]]
 
@@ -49,14 +49,15 @@ def _assert_grad(name, cuda_g, ref32, ref64):
 def test_flow_loss_vs_oracle(cuda_device, B, Hh, W, L, scales, px, oob, mode):
     t = make_triplet(B, Hh, W, L, 1, seed=21, flow_px=px, oob_fraction=oob, flow_mode=mode)
     gl = torch.rand(4, B, generator=torch.Generator().manual_seed(1)) + 0.5
-    loss, gf, gb = _cuda_flow(t, scales, gl, cuda_device)
     ref, rf, rb = _oracle_flow(t, scales, gl)
     _, rf64, rb64 = _oracle_flow(t, scales, gl, torch.float64)
-    for k in range(4):
-        assert loss_rel_err(loss[k], ref[KEYS[k]]) < LOSS_RTOL, KEYS[k]
-    for l in range(scales):
-        _assert_grad("fwd%d" % l, gf[l], rf[l], rf64[l])
-        _assert_grad("bwd%d" % l, gb[l], rb[l], rb64[l])
+    for kernel_mode in ("single_pass", "recompute"):
+        loss, gf, gb = _cuda_flow(t, scales, gl, cuda_device, kernel_mode)
+        for k in range(4):
+            assert loss_rel_err(loss[k], ref[KEYS[k]]) < LOSS_RTOL, (kernel_mode, KEYS[k])
+        for l in range(scales):
+            _assert_grad("%s fwd%d" % (kernel_mode, l), gf[l], rf[l], rf64[l])
+            _assert_grad("%s bwd%d" % (kernel_mode, l), gb[l], rb[l], rb64[l])
 
 
 @pytest.mark.parametrize("name,scales", [("flow_mode_s4", 4), ("flow_mode_s4_oob", 4), ("flow_mode_s3", 3)])
@@ -111,6 +112,16 @@ def test_full_size_properties(cuda_device):
     l3, f3, b3 = _cuda_flow(t, 4, g1 + g2, cuda_device)
     for x, y, z in zip(fa + ba, f2 + b2, f3 + b3):
         assert rel_err(x + y, z) < 1e-5
+
+
+def test_single_pass_and_recompute_agree_at_full_size(cuda_device):
+    t = make_triplet(4, 256, 832, 4, 1, seed=99, flow_px=10.0, oob_fraction=0.05)
+    gl = torch.rand(4, 4, generator=torch.Generator().manual_seed(5)) + 0.1
+    la, fa, ba = _cuda_flow(t, 4, gl, cuda_device, "single_pass")
+    lb, fb_, bb = _cuda_flow(t, 4, gl, cuda_device, "recompute")
+    assert loss_rel_err(la, lb) < 1e-6
+    for x, y in zip(fa + ba, fb_ + bb):
+        assert rel_err(x, y) < 2e-5
 
 
 def test_unused_levels_get_no_gradient(cuda_device):

@@ -33,12 +33,13 @@ def test_flow_loss_tiles_vs_oracle(B, Hh, W, scales, px, oob):
     pl, pc, pr = P.box_pyramid(t.img_l, L), P.box_pyramid(t.img, L), P.box_pyramid(t.img_r, L)
     ff = [f.detach().contiguous() for f in t.flows_fwd]
     fb = [f.detach().contiguous() for f in t.flows_bwd]
-    el, egf, egb, _ = H.emu_flow_loss(pl, pc, pr, ff, fb, scales, gl)
-    for k in range(4):
-        assert loss_rel_err(el[k], loss[KEYS[k]]) < LOSS_RTOL, KEYS[k]
-    for l in range(scales):
-        assert rel_err(egf[l], gf[l]) < GRAD_RTOL, ("fwd", l)
-        assert rel_err(egb[l], gb[l]) < GRAD_RTOL * 1.5, ("bwd", l)   # SSIM-dominated: fp32 noise of the formula itself
+    for emu_fn in (H.emu_flow_loss, H.emu_flow_loss_single_pass):       # recompute kernels, single-pass kernels
+        el, egf, egb, _ = emu_fn(pl, pc, pr, ff, fb, scales, gl)
+        for k in range(4):
+            assert loss_rel_err(el[k], loss[KEYS[k]]) < LOSS_RTOL, KEYS[k]
+        for l in range(scales):
+            assert rel_err(egf[l], gf[l]) < GRAD_RTOL, ("fwd", l)
+            assert rel_err(egb[l], gb[l]) < GRAD_RTOL * 1.5, ("bwd", l)   # SSIM-dominated: fp32 noise of the formula itself
 
 
 def test_flow_loss_tiles_vs_golden():

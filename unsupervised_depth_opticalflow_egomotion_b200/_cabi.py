@@ -11,6 +11,7 @@ from typing import Optional
 
 MAX_LEVELS = 6
 FLOW_NSTATS = 12
+FLOW_BASIS_PLANES = 14
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libugl_b200.so")
@@ -40,6 +41,7 @@ class UglFlowLossArgs(C.Structure):
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_uint64),
         ("stream", C.c_void_p),
+        ("basis", C.c_void_p * MAX_LEVELS),
     ]
 
 
@@ -51,6 +53,8 @@ SIGNATURES = {
     "ugl_flow_loss_forward": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_backward": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_launches": (C.c_int, [C.c_int]),
+    "ugl_flow_loss_forward_grad": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
+    "ugl_flow_loss_combine": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_image_pyramid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.POINTER(C.c_void_p), C.c_void_p]),
     "ugl_warp_flow_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

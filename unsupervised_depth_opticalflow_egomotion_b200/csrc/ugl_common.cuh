@@ -26,9 +26,17 @@
 #define UGL_D inline
 #endif
 
+#if !defined(__CUDACC__)
+struct float2 { float x, y; };
+inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+
 namespace ugl {
 
 constexpr int kMaxLevels = 6;
+
+UGL_HD int imin(int a, int b) { return a < b ? a : b; }
+UGL_HD int imax(int a, int b) { return a > b ? a : b; }
 
 // ---- explicitly rounded fp32 ops (identical results on device and in the host emulator, which is
 // ---- compiled with -ffp-contract=off) --------------------------------------------------------

@@ -1,0 +1,400 @@
+// Single-pass variant of the fused flow-mode loss: ONE stencil kernel computes the loss sums AND the
+// un-normalised gradient of every term w.r.t. both flows ("gradient basis maps"); the backward pass is
+// then an element-wise combine  grad = sum_k scale_k(sample, level) * basis_k  once the per-sample
+// normalisers (mean of the occlusion weights) and the upstream gradients are known.
+//
+// Why: the kernels are instruction-issue bound (profiles/), and the recompute scheme of ugl_flow_loss.cuh
+// executes the photometry and the SSIM moments twice (forward, then backward).  This variant executes them
+// once, trading 14 floats/pixel of extra HBM traffic (far from binding) for ~1/3 fewer instructions.
+//
+// Basis planes per level, layout (B, 14, h, w):
+//   0,1  Gp_f  = w_f * sum_c sign(Wf_c - I_c) * keep * dWf_c/d(u,v)            x g_pix  / (3 hw den_f)
+//   2,3  Gs_f  = w_f * sum_c (sA + 2 y sB + x sC) * keep * dWf_c/d(u,v)        x g_ssim / (27 hw den_f)
+//   4,5  Gm_f  = sum_t coef_t (wx_t sign(dxx_t) / nx + wy_t sign(dyy_t) / ny)  x g_smooth / 40
+//   6,7  Gc    = (1 - w_f) * d(|f^_f + f^_b|_1)/d(u_f, v_f)                    x g_consis / (2 hw den_c)
+//   8,9  Gp_b, 10,11 Gs_b, 12,13 Gm_b  (same for the backward flow; the consistency term has no bwd gradient)
+#pragma once
+
+#include "ugl_flow_loss.cuh"
+
+namespace ugl {
+
+constexpr int kBasisPlanes = 14;
+
+// ---- unconditional clamped gather ---------------------------------------------------------------------------
+// Same numbers as tap_fetch/corners_value (out-of-range corners contribute an exact +0), but the four loads are
+// unconditional (clamped addresses) and the in-bounds tests are folded into the weights once per tap instead of
+// once per channel.
+struct TapC {
+  int o00, o01, o10, o11;     // clamped plane offsets of nw, ne, sw, se
+  float w[4];                 // masked weights
+  float dx[4], dy[4];         // masked d w / d ix, d w / d iy
+  float keep;
+};
+
+template <bool kGrad>
+UGL_HD TapC flow_tap_clamped(int j, int i, float u, float v, const WarpGeom& g) {
+  const float gx = sub_rn(div_c(mul_rn(2.0f, add_rn((float)j, u)), g.dw, g.rdw), 1.0f);
+  const float gy = sub_rn(div_c(mul_rn(2.0f, add_rn((float)i, v)), g.dh, g.rdh), 1.0f);
+  float ix = unnormalize(gx, g.W), iy = unnormalize(gy, g.H);
+  ix = fminf(fmaxf(ix, -2.0f), (float)g.W + 1.0f);      // beyond that every corner is out of range anyway
+  iy = fminf(fmaxf(iy, -2.0f), (float)g.H + 1.0f);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float tx = ix - fx, ty = iy - fy;
+  const float ox = (fx + 1.0f) - ix, oy = (fy + 1.0f) - iy;
+  const float ml = (x0 >= 0 && x0 < g.W) ? 1.f : 0.f, mr = (x0 + 1 >= 0 && x0 + 1 < g.W) ? 1.f : 0.f;
+  const float mt = (y0 >= 0 && y0 < g.H) ? 1.f : 0.f, mb = (y0 + 1 >= 0 && y0 + 1 < g.H) ? 1.f : 0.f;
+  const float m00 = ml * mt, m01 = mr * mt, m10 = ml * mb, m11 = mr * mb;
+  TapC t;
+  t.w[0] = (ox * oy) * m00; t.w[1] = (tx * oy) * m01; t.w[2] = (ox * ty) * m10; t.w[3] = (tx * ty) * m11;
+  const int xa = imin(imax(x0, 0), g.W - 1), xb = imin(imax(x0 + 1, 0), g.W - 1);
+  const int ya = imin(imax(y0, 0), g.H - 1) * g.W, yb = imin(imax(y0 + 1, 0), g.H - 1) * g.W;
+  t.o00 = ya + xa; t.o01 = ya + xb; t.o10 = yb + xa; t.o11 = yb + xb;
+  t.keep = add_rn(add_rn(add_rn(t.w[0], t.w[1]), t.w[2]), t.w[3]) >= 0.9999f ? 1.0f : 0.0f;
+  if (kGrad) {
+    const float uy = 1.0f - ty, ux = 1.0f - tx;
+    t.dx[0] = -uy * m00; t.dx[1] = uy * m01; t.dx[2] = -ty * m10; t.dx[3] = ty * m11;
+    t.dy[0] = -ux * m00; t.dy[1] = -tx * m01; t.dy[2] = ux * m10; t.dy[3] = tx * m11;
+  }
+  return t;
+}
+
+template <bool kGrad>
+UGL_HD void flow_photo_pixel_c(const FlowLevelDesc& L, int b, int i, int j, float uf, float vf, float ub, float vb, Photo& P, float* dW) {
+  const int plane = L.h * L.w;
+  const int pix = i * L.w + j;
+  const float* ic = L.img + (long)b * 3 * plane;
+  const float* ir = L.img_r + (long)b * 3 * plane;
+  const float* il = L.img_l + (long)b * 3 * plane;
+  const TapC tf = flow_tap_clamped<kGrad>(j, i, uf, vf, L.geom);
+  const TapC tb = flow_tap_clamped<kGrad>(j, i, ub, vb, L.geom);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    P.I[c] = ic[c * plane + pix];
+    const float* pr = ir + c * plane;
+    const float* pl = il + c * plane;
+    const float f0 = pr[tf.o00], f1 = pr[tf.o01], f2 = pr[tf.o10], f3 = pr[tf.o11];
+    const float b0 = pl[tb.o00], b1 = pl[tb.o01], b2 = pl[tb.o10], b3 = pl[tb.o11];
+    float vfw = f0 * tf.w[0]; vfw += f1 * tf.w[1]; vfw += f2 * tf.w[2]; vfw += f3 * tf.w[3];
+    float vbw = b0 * tb.w[0]; vbw += b1 * tb.w[1]; vbw += b2 * tb.w[2]; vbw += b3 * tb.w[3];
+    P.Wf[c] = vfw * tf.keep;
+    P.Wb[c] = vbw * tb.keep;
+    if (kGrad) {
+      dW[2 * c + 0] = tf.keep * L.geom.sx * (f0 * tf.dx[0] + f1 * tf.dx[1] + f2 * tf.dx[2] + f3 * tf.dx[3]);
+      dW[2 * c + 1] = tf.keep * L.geom.sy * (f0 * tf.dy[0] + f1 * tf.dy[1] + f2 * tf.dy[2] + f3 * tf.dy[3]);
+      dW[6 + 2 * c + 0] = tb.keep * L.geom.sx * (b0 * tb.dx[0] + b1 * tb.dx[1] + b2 * tb.dx[2] + b3 * tb.dx[3]);
+      dW[6 + 2 * c + 1] = tb.keep * L.geom.sy * (b0 * tb.dy[0] + b1 * tb.dy[1] + b2 * tb.dy[2] + b3 * tb.dy[3]);
+    }
+  }
+  const float valid_f = (P.Wf[0] == 0.f && P.Wf[1] == 0.f && P.Wf[2] == 0.f) ? 0.f : 1.f;
+  const float valid_b = (P.Wb[0] == 0.f && P.Wb[1] == 0.f && P.Wb[2] == 0.f) ? 0.f : 1.f;
+  P.d_f = mean3_abs_diff(P.I, P.Wf);
+  P.d_b = mean3_abs_diff(P.I, P.Wb);
+  float wl, wr;
+  one_minus_softmax2(P.d_b, P.d_f, wl, wr);
+  P.w_b = soft_occ_weight(wl) * valid_b;
+  P.w_f = soft_occ_weight(wr) * valid_f;
+}
+
+struct FlowGradParams {
+  FlowLossParams base;
+  float* basis[kMaxLevels];   // (B, 14, h, w) per level
+};
+
+// ================================================================================================
+// the single-pass stencil kernel's tile logic
+// ================================================================================================
+template <int TW, int TH, int NT>
+struct FlowGradTile {
+  static_assert(TW % 2 == 0, "1x2 micro-tiles need an even tile width");
+  static constexpr int R = 2;
+  static constexpr int PW = TW + 2 * R, PH = TH + 2 * R, PN = PW * PH;   // photometry planes (halo 2)
+  static constexpr int CW = TW + 2, CH = TH + 2, CN = CW * CH;           // coefficient / edge planes (halo 1)
+  static constexpr int TN = TW * TH;
+  static constexpr int kOffCoef = PL_COUNT * PN;                          // 9 planes [c][A,B,C], current direction
+  static constexpr int kOffEdge = kOffCoef + 9 * CN;                      // wx, wy
+  static constexpr int kOffDW = kOffEdge + 2 * CN;                        // 12 planes keep*dW/d(u,v) + 4 planes L1 sign sums
+  static constexpr int kSmemFloats = kOffDW + 16 * TN;
+  static_assert(PN % 2 == 0 && CN % 2 == 0 && (PL_COUNT * PN) % 2 == 0, "planes must stay 8-byte aligned for float2 access");
+
+  // phase 1: photometry on the halo-2 tile; interior pixels also: L1/weight/consistency sums, warp Jacobians,
+  // L1 sign sums (shared memory) and the consistency basis (global)
+  static UGL_HD void phase1(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, float* sm, float* acc) {
+    const FlowLossParams& p = gp.base;
+    const FlowLevelDesc& L = p.lv[tc.level];
+    const int plane = L.h * L.w;
+    float* basis = gp.basis[tc.level] + (long)tc.b * kBasisPlanes * plane;
+    for (int idx = tid; idx < PN; idx += nt) {
+      const int ly = idx / PW, lx = idx - ly * PW;
+      const int i = tc.y0 - R + ly, j = tc.x0 - R + lx;
+      Photo P;
+      float uf = 0.f, vf = 0.f, ub = 0.f, vb = 0.f;
+      if (i >= 0 && i < L.h && j >= 0 && j < L.w) {
+        const int pix = i * L.w + j;
+        const float* ff = L.flow_f + (long)tc.b * 2 * plane;
+        const float* fb = L.flow_b + (long)tc.b * 2 * plane;
+        uf = ff[pix]; vf = ff[plane + pix];
+        ub = fb[pix]; vb = fb[plane + pix];
+        const bool interior = (ly >= R && ly < R + TH && lx >= R && lx < R + TW);
+        if (interior) {
+          float dW[12];
+          flow_photo_pixel_c<true>(L, tc.b, i, j, uf, vf, ub, vb, P, dW);
+          const int t = (ly - R) * TW + (lx - R);
+          float* o = sm + kOffDW + t;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) o[k * TN] = dW[k];
+#pragma unroll
+          for (int dir = 0; dir < 2; ++dir) {
+            float su = 0.f, sv = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float sg = sgnf((dir == 0 ? P.Wf[c] : P.Wb[c]) - P.I[c]);
+              su += sg * dW[6 * dir + 2 * c];
+              sv += sg * dW[6 * dir + 2 * c + 1];
+            }
+            o[(12 + 2 * dir) * TN] = su;
+            o[(13 + 2 * dir) * TN] = sv;
+          }
+          acc[FA_PIX_F] += P.d_f * P.w_f;
+          acc[FA_W_F] += P.w_f;
+          acc[FA_PIX_B] += P.d_b * P.w_b;
+          acc[FA_W_B] += P.w_b;
+          // direction consistency: value and un-normalised gradient w.r.t. the forward flow
+          const float rf = sqrt_rn(uf * uf + vf * vf), rb = sqrt_rn(ub * ub + vb * vb);
+          const float inf_ = fast_div(1.0f, rf + 1e-12f), inb_ = fast_div(1.0f, rb + 1e-12f);
+          const float cu = uf * inf_ + ub * inb_, cv = vf * inf_ + vb * inb_;
+          const float om = 1.0f - P.w_f;
+          acc[FA_CONS] += (fabsf(cu) + fabsf(cv)) * om;
+          acc[FA_CONS_W] += om;
+          const float su = sgnf(cu) * om, sv = sgnf(cv) * om;
+          const float gn = -(su * uf + sv * vf) * inf_ * inf_;
+          const float ir = rf > 0.f ? fast_div(1.0f, rf) : 0.f;
+          basis[6 * plane + pix] = su * inf_ + gn * uf * ir;
+          basis[7 * plane + pix] = sv * inf_ + gn * vf * ir;
+        } else {
+          flow_photo_pixel_c<false>(L, tc.b, i, j, uf, vf, ub, vb, P, nullptr);
+        }
+      } else {
+        zero_photo(P);
+      }
+      store_photo_planes<PN>(sm, idx, P, uf, vf, ub, vb);
+    }
+  }
+
+  // phase 2 (per direction): 1x2 strips over the halo-1 region.  Each strip loads the 3x4 taps it needs once,
+  // forms x = I*w, y = W*w and their products once, and accumulates the two 3x3 windows in the reference's
+  // row-major order (bit-identical SSIM).  Writes the SSIM backward coefficients; window centres that are interior
+  // pixels also add their SSIM loss value; the first direction also stores the smoothness edge weights.
+  static UGL_HD void phase2(const FlowGradParams& gp, const TileCoord& tc, int dir, int tid, int nt, float* sm, float* acc) {
+    const FlowLevelDesc& L = gp.base.lv[tc.level];
+    constexpr int SW = CW / 2;                       // strips per row
+    const float* wpl = sm + (dir == 0 ? PL_WF : PL_WB) * PN;
+    float ssim_sum = 0.f;
+    for (int s = tid; s < SW * CH; s += nt) {
+      const int ly = s / SW, lx = (s - ly * SW) * 2;          // halo-1 coordinates of the left centre
+      const int i = tc.y0 - 1 + ly, j0 = tc.x0 - 1 + lx;
+      const int c0 = (ly + 1) * PW + (lx + 1);                // photometry-plane index of the left centre
+      const bool row_in = (i >= 0 && i < L.h);
+      const bool in0 = row_in && j0 >= 0 && j0 < L.w, in1 = row_in && j0 + 1 >= 0 && j0 + 1 < L.w;
+      float wt[3][4];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float2 a = *reinterpret_cast<const float2*>(wpl + c0 + (r - 1) * PW - 1);
+        const float2 b2 = *reinterpret_cast<const float2*>(wpl + c0 + (r - 1) * PW + 1);
+        wt[r][0] = a.x; wt[r][1] = a.y; wt[r][2] = b2.x; wt[r][3] = b2.y;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* ipl = sm + (PL_I0 + c) * PN;
+        const float* ypl = sm + ((dir == 0 ? PL_F0 : PL_B0) + c) * PN;
+        float x[3][4], y[3][4], xx[3][4], yy[3][4], xy[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float2 ia = *reinterpret_cast<const float2*>(ipl + c0 + (r - 1) * PW - 1);
+          const float2 ib = *reinterpret_cast<const float2*>(ipl + c0 + (r - 1) * PW + 1);
+          const float2 ya = *reinterpret_cast<const float2*>(ypl + c0 + (r - 1) * PW - 1);
+          const float2 yb = *reinterpret_cast<const float2*>(ypl + c0 + (r - 1) * PW + 1);
+          const float iv[4] = {ia.x, ia.y, ib.x, ib.y}, yv[4] = {ya.x, ya.y, yb.x, yb.y};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            x[r][k] = mul_rn(iv[k], wt[r][k]);
+            y[r][k] = mul_rn(yv[k], wt[r][k]);
+            xx[r][k] = mul_rn(x[r][k], x[r][k]);
+            yy[r][k] = mul_rn(y[r][k], y[r][k]);
+            xy[r][k] = mul_rn(x[r][k], y[r][k]);
+          }
+        }
+        float cA[2] = {0.f, 0.f}, cB[2] = {0.f, 0.f}, cC[2] = {0.f, 0.f};
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          if (o == 0 ? in0 : in1) {
+            Moments m = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                m.sx = add_rn(m.sx, x[r][o + k]); m.sy = add_rn(m.sy, y[r][o + k]);
+                m.sxx = add_rn(m.sxx, xx[r][o + k]); m.syy = add_rn(m.syy, yy[r][o + k]); m.sxy = add_rn(m.sxy, xy[r][o + k]);
+              }
+            const SsimTerms t = ssim_terms(m);
+            const float v = mul_rn(sub_rn(1.0f, t.S), 0.5f);
+            const float g = (v >= 0.f && v <= 1.f) ? -0.5f : 0.f;
+            float ax, bx;
+            ssim_partials(t, g, ax, bx, cA[o], cB[o], cC[o]);
+            const bool interior = (ly >= 1 && ly <= TH && lx + o >= 1 && lx + o <= TW);
+            if (interior) ssim_sum += (v < 0.f ? 0.f : (v > 1.f ? 1.f : v));
+          }
+        }
+        float* oc = sm + kOffCoef + (c * 3) * CN + ly * CW + lx;
+        *reinterpret_cast<float2*>(oc) = make_float2(cA[0], cA[1]);
+        *reinterpret_cast<float2*>(oc + CN) = make_float2(cB[0], cB[1]);
+        *reinterpret_cast<float2*>(oc + 2 * CN) = make_float2(cC[0], cC[1]);
+      }
+      if (dir == 0) {
+        float wx[2] = {0.f, 0.f}, wy[2] = {0.f, 0.f};
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          if (o == 0 ? in0 : in1) {
+            const int cc = c0 + o, j = j0 + o;
+            const float Ic[3] = {sm[PL_I0 * PN + cc], sm[PL_I1 * PN + cc], sm[PL_I2 * PN + cc]};
+            if (j >= 1 && j <= L.w - 2) {
+              const float Iq[3] = {sm[PL_I0 * PN + cc + 1], sm[PL_I1 * PN + cc + 1], sm[PL_I2 * PN + cc + 1]};
+              wx[o] = edge_weight10(Ic, Iq);
+            }
+            if (i >= 1 && i <= L.h - 2) {
+              const float Iq[3] = {sm[PL_I0 * PN + cc + PW], sm[PL_I1 * PN + cc + PW], sm[PL_I2 * PN + cc + PW]};
+              wy[o] = edge_weight10(Ic, Iq);
+            }
+          }
+        }
+        *reinterpret_cast<float2*>(sm + kOffEdge + ly * CW + lx) = make_float2(wx[0], wx[1]);
+        *reinterpret_cast<float2*>(sm + kOffEdge + CN + ly * CW + lx) = make_float2(wy[0], wy[1]);
+      }
+    }
+    acc[dir == 0 ? FA_SSIM_F : FA_SSIM_B] += ssim_sum;
+  }
+
+  // phase 3 (per direction): 1x2 strips over the interior: 3x3 box sums of the coefficients (vertical sums shared by
+  // the two outputs), chain through the warp Jacobian, store the L1 and SSIM basis of this direction
+  static UGL_HD void phase3(const FlowGradParams& gp, const TileCoord& tc, int dir, int tid, int nt, const float* sm) {
+    const FlowLevelDesc& L = gp.base.lv[tc.level];
+    const int plane = L.h * L.w;
+    float* basis = gp.basis[tc.level] + ((long)tc.b * kBasisPlanes + (dir == 0 ? 0 : 8)) * plane;
+    constexpr int SW = TW / 2;
+    for (int s = tid; s < SW * TH; s += nt) {
+      const int ty = s / SW, tx = (s - ty * SW) * 2;
+      const int i = tc.y0 + ty, j = tc.x0 + tx;
+      if (i >= L.h || j >= L.w) continue;
+      const int c0 = (ty + R) * PW + (tx + R);       // photometry planes, left pixel
+      const int q0 = (ty + 1) * CW + (tx + 1);       // coefficient planes, left pixel
+      const int t0 = ty * TW + tx;
+      const float2 wq = *reinterpret_cast<const float2*>(sm + (dir == 0 ? PL_WF : PL_WB) * PN + c0);
+      const float wv[2] = {wq.x, wq.y};
+      float gsu[2] = {0.f, 0.f}, gsv[2] = {0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float sum[3][2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {                 // A, B, C planes
+          const float* cf = sm + kOffCoef + (c * 3 + k) * CN + q0 - 1;
+          float col[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int r = -1; r <= 1; ++r) {
+            const float2 a = *reinterpret_cast<const float2*>(cf + r * CW);
+            const float2 b2 = *reinterpret_cast<const float2*>(cf + r * CW + 2);
+            col[0] += a.x; col[1] += a.y; col[2] += b2.x; col[3] += b2.y;
+          }
+          sum[k][0] = col[0] + col[1] + col[2];
+          sum[k][1] = col[1] + col[2] + col[3];
+        }
+        const float2 Iv = *reinterpret_cast<const float2*>(sm + (PL_I0 + c) * PN + c0);
+        const float2 Wv = *reinterpret_cast<const float2*>(sm + ((dir == 0 ? PL_F0 : PL_B0) + c) * PN + c0);
+        const float2 du = *reinterpret_cast<const float2*>(sm + kOffDW + (6 * dir + 2 * c) * TN + t0);
+        const float2 dv = *reinterpret_cast<const float2*>(sm + kOffDW + (6 * dir + 2 * c + 1) * TN + t0);
+        const float I2[2] = {Iv.x, Iv.y}, W2[2] = {Wv.x, Wv.y}, du2[2] = {du.x, du.y}, dv2[2] = {dv.x, dv.y};
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const float gW = (sum[0][o] + 2.0f * (W2[o] * wv[o]) * sum[1][o] + (I2[o] * wv[o]) * sum[2][o]) * wv[o];
+          gsu[o] += gW * du2[o];
+          gsv[o] += gW * dv2[o];
+        }
+      }
+      const float2 pu = *reinterpret_cast<const float2*>(sm + kOffDW + (12 + 2 * dir) * TN + t0);
+      const float2 pv = *reinterpret_cast<const float2*>(sm + kOffDW + (13 + 2 * dir) * TN + t0);
+      const int pix = i * L.w + j;
+      const bool two = (j + 1 < L.w);
+      basis[0 * plane + pix] = pu.x * wv[0]; basis[1 * plane + pix] = pv.x * wv[0];
+      basis[2 * plane + pix] = gsu[0];       basis[3 * plane + pix] = gsv[0];
+      if (two) {
+        basis[0 * plane + pix + 1] = pu.y * wv[1]; basis[1 * plane + pix + 1] = pv.y * wv[1];
+        basis[2 * plane + pix + 1] = gsu[1];       basis[3 * plane + pix + 1] = gsv[1];
+      }
+    }
+  }
+
+  // phase 4: smoothness value + basis for the interior pixels
+  static UGL_HD void phase4(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, const float* sm, float* acc) {
+    const FlowLevelDesc& L = gp.base.lv[tc.level];
+    const int plane = L.h * L.w;
+    float* basis = gp.basis[tc.level] + (long)tc.b * kBasisPlanes * plane;
+    const float inx = 1.0f / (2.0f * (float)L.h * (float)(L.w - 2)), iny = 1.0f / (2.0f * (float)(L.h - 2) * (float)L.w);
+    for (int idx = tid; idx < TN; idx += nt) {
+      const int ty = idx / TW, tx = idx - ty * TW;
+      const int i = tc.y0 + ty, j = tc.x0 + tx;
+      if (i >= L.h || j >= L.w) continue;
+      const int c0 = (ty + R) * PW + (tx + R);
+      const int q0 = (ty + 1) * CW + (tx + 1);
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = -1; t <= 1; ++t) {
+        const float coef = (t == 0) ? -2.0f : 1.0f;
+        const float wx = sm[kOffEdge + q0 + t], wy = sm[kOffEdge + CN + q0 + t * CW];   // zero where the centre does not exist
+#pragma unroll
+        for (int f4 = 0; f4 < 4; ++f4) {
+          const float* f = sm + (PL_UF + f4) * PN + c0;
+          const float dxx = second_diff(f + t, 1), dyy = second_diff(f + t * PW, PW);
+          g[f4] += coef * (wx * inx * sgnf(dxx) + wy * iny * sgnf(dyy));
+          if (t == 0) {
+            acc[f4 < 2 ? FA_SMX_F : FA_SMX_B] += wx * fabsf(dxx);
+            acc[f4 < 2 ? FA_SMY_F : FA_SMY_B] += wy * fabsf(dyy);
+          }
+        }
+      }
+      const int pix = i * L.w + j;
+      basis[4 * plane + pix] = g[0]; basis[5 * plane + pix] = g[1];
+      basis[12 * plane + pix] = g[2]; basis[13 * plane + pix] = g[3];
+    }
+  }
+};
+
+// ---- backward = element-wise combine -----------------------------------------------------------------------------
+// grad_f = kp_f Gp_f + ks_f Gs_f + ksm Gm_f + kc Gc ;  grad_b = kp_b Gp_b + ks_b Gs_b + ksm Gm_b
+struct FlowCombineScales { float pix[2], ssim[2], sm, cons; };
+
+UGL_HD FlowCombineScales flow_combine_scales(const float* S, int h, int w, const float* gloss, int B, int b) {
+  FlowCombineScales k;
+  const float hw = (float)h * (float)w;
+  const float den_f = S[FA_W_F] / hw + 1e-12f, den_b = S[FA_W_B] / hw + 1e-12f;
+  const float g_pix = gloss[0 * B + b], g_ssim = gloss[1 * B + b], g_sm = gloss[2 * B + b], g_cons = gloss[3 * B + b];
+  k.pix[0] = g_pix / hw / den_f / 3.0f;
+  k.pix[1] = g_pix / hw / den_b / 3.0f;
+  k.ssim[0] = g_ssim / (3.0f * hw) / den_f / 9.0f;
+  k.ssim[1] = g_ssim / (3.0f * hw) / den_b / 9.0f;
+  k.sm = g_sm * 0.5f / 20.0f;
+  k.cons = g_cons / (2.0f * hw) / (S[FA_CONS_W] / hw + 1e-12f);
+  return k;
+}
+
+UGL_HD void flow_combine_pixel(const float* __restrict__ basis, int plane, int pix, const FlowCombineScales& k,
+                               float* __restrict__ gf, float* __restrict__ gb) {
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    gf[ch * plane + pix] = k.pix[0] * basis[(0 + ch) * plane + pix] + k.ssim[0] * basis[(2 + ch) * plane + pix]
+                           + k.sm * basis[(4 + ch) * plane + pix] + k.cons * basis[(6 + ch) * plane + pix];
+    gb[ch * plane + pix] = k.pix[1] * basis[(8 + ch) * plane + pix] + k.ssim[1] * basis[(10 + ch) * plane + pix]
+                           + k.sm * basis[(12 + ch) * plane + pix];
+  }
+}
+
+}  // namespace ugl

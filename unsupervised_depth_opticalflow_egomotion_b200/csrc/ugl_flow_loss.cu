@@ -1,6 +1,7 @@
 // CUDA kernels + C-ABI for the fused flow-mode loss (see ugl_flow_loss.cuh for the math and the
 // reference citations).  Three launches per training step: forward, finalize, backward.
 #include "ugl_flow_loss.cuh"
+#include "ugl_flow_grad.cuh"
 #include "ugl_host.cuh"
 
 namespace ugl {
@@ -10,7 +11,7 @@ constexpr int kBNT = 256;   // backward threads per CTA
 
 template <int TW, int TH, int NT>
 __global__ void __launch_bounds__(NT) flow_loss_fwd_kernel(const __grid_constant__ FlowLossParams p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   __shared__ float red[(NT / 32) * FA_COUNT];
   using Tile = FlowFwdTile<TW, TH>;
   const int tile = blockIdx.x;
@@ -68,7 +69,7 @@ __global__ void flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams
 
 template <int TW, int TH, int NT>
 __global__ void __launch_bounds__(NT) flow_loss_bwd_kernel(const __grid_constant__ FlowLossParams p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   using Tile = FlowBwdTile<TW, TH, NT>;
   const int tile = blockIdx.x;
   const TileCoord tc = decode_tile<TW, TH>(p, tile);
@@ -85,6 +86,45 @@ __global__ void __launch_bounds__(NT) flow_loss_bwd_kernel(const __grid_constant
     if (dir == 0) __syncthreads();   // the coefficient planes are reused by the second direction
   }
   Tile::phase4(p, tc, k, threadIdx.x, NT, sm, g);
+}
+
+// single-pass: losses + gradient basis maps
+template <int TW, int TH, int NT>
+__global__ void __launch_bounds__(NT) flow_loss_fwdgrad_kernel(const __grid_constant__ FlowGradParams gp) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ float red[(NT / 32) * FA_COUNT];
+  using Tile = FlowGradTile<TW, TH, NT>;
+  const int tile = blockIdx.x;
+  const TileCoord tc = decode_tile<TW, TH>(gp.base, tile);
+  float acc[FA_COUNT];
+#pragma unroll
+  for (int k = 0; k < FA_COUNT; ++k) acc[k] = 0.f;
+  Tile::phase1(gp, tc, threadIdx.x, NT, sm, acc);
+  __syncthreads();
+#pragma unroll
+  for (int dir = 0; dir < 2; ++dir) {
+    Tile::phase2(gp, tc, dir, threadIdx.x, NT, sm, acc);
+    __syncthreads();
+    Tile::phase3(gp, tc, dir, threadIdx.x, NT, sm);
+    if (dir == 0) __syncthreads();   // the coefficient planes are reused by the second direction
+  }
+  Tile::phase4(gp, tc, threadIdx.x, NT, sm, acc);
+  const float v = block_reduce_n<NT, FA_COUNT>(acc, red);
+  if (threadIdx.x < FA_COUNT) gp.base.partials[(long)tile * FA_COUNT + threadIdx.x] = v;
+}
+
+// element-wise backward of the single-pass mode: grid (chunks, B, scales)
+__global__ void __launch_bounds__(256) flow_combine_kernel(const __grid_constant__ FlowGradParams gp) {
+  const FlowLossParams& p = gp.base;
+  const int b = blockIdx.y, l = blockIdx.z;
+  const FlowLevelDesc& L = p.lv[l];
+  const int plane = L.h * L.w;
+  const FlowCombineScales k = flow_combine_scales(p.stats + ((long)b * p.scales + l) * FA_COUNT, L.h, L.w, p.gloss, p.B, b);
+  const float* basis = gp.basis[l] + (long)b * kBasisPlanes * plane;
+  float* gf = L.gflow_f + (long)b * 2 * plane;
+  float* gb = L.gflow_b + (long)b * 2 * plane;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < plane; pix += gridDim.x * blockDim.x)
+    flow_combine_pixel(basis, plane, pix, k, gf, gb);
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -157,6 +197,48 @@ extern "C" int ugl_flow_loss_forward(const UglFlowLossArgs* a) {
   if ((rc = check_launch("flow_loss_fwd_kernel"))) return rc;
   flow_loss_finalize_kernel<<<p.B, 32 * kMaxLevels, 0, st>>>(p);
   return check_launch("flow_loss_finalize_kernel");
+}
+
+extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) {
+  FlowGradParams gp;
+  int rc = build_params<kBTW, kBTH>(a, false, gp.base);
+  if (rc) return rc;
+  if (!a->loss) return fail(UGL_EINVAL, "flow_loss_forward_grad: null loss");
+  for (int l = 0; l < a->scales; ++l) {
+    if (!a->basis[l]) return fail(UGL_EINVAL, "flow_loss_forward_grad: null basis pointer at level %d", l);
+    if (reinterpret_cast<uintptr_t>(a->basis[l]) & 7u) return fail(UGL_EALIGN, "flow_loss_forward_grad: basis not 8-byte aligned");
+    gp.basis[l] = a->basis[l];
+  }
+  if (!a->workspace || a->workspace_bytes < (uint64_t)gp.base.total_tiles * FA_COUNT * sizeof(float))
+    return fail(UGL_EWORKSPACE, "flow_loss_forward_grad: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  using Tile = FlowGradTile<kBTW, kBTH, kBNT>;
+  constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
+  static_assert(smem <= 227 * 1024, "single-pass tile does not fit in shared memory");
+  auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT>;
+  if ((rc = opt_in_smem(kern, smem))) return rc;
+  kern<<<gp.base.total_tiles, kBNT, smem, st>>>(gp);
+  if ((rc = check_launch("flow_loss_fwdgrad_kernel"))) return rc;
+  flow_loss_finalize_kernel<<<gp.base.B, 32 * kMaxLevels, 0, st>>>(gp.base);
+  return check_launch("flow_loss_finalize_kernel");
+}
+
+extern "C" int ugl_flow_loss_combine(const UglFlowLossArgs* a) {
+  FlowGradParams gp;
+  int rc = build_params<kBTW, kBTH>(a, true, gp.base);
+  if (rc) return rc;
+  if (!a->grad_loss) return fail(UGL_EINVAL, "flow_loss_combine: null grad_loss");
+  int max_plane = 0;
+  for (int l = 0; l < a->scales; ++l) {
+    if (!a->basis[l]) return fail(UGL_EINVAL, "flow_loss_combine: null basis pointer at level %d", l);
+    gp.basis[l] = a->basis[l];
+    const int pl = a->height[l] * a->width[l];
+    max_plane = pl > max_plane ? pl : max_plane;
+  }
+  int chunks = (max_plane + 256 * 4 - 1) / (256 * 4);
+  chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
+  flow_combine_kernel<<<dim3(chunks, gp.base.B, gp.base.scales), 256, 0, static_cast<cudaStream_t>(a->stream)>>>(gp);
+  return check_launch("flow_combine_kernel");
 }
 
 extern "C" int ugl_flow_loss_backward(const UglFlowLossArgs* a) {

@@ -115,8 +115,11 @@ def warp_flow(x: Tensor, flow: Tensor, use_mask: bool = False) -> Tensor:
 FLOW_LOSS_KEYS = ("loss_flow_pixel", "loss_flow_ssim", "loss_flow_smooth", "loss_flow_consis")
 
 
-def _flow_args(img_l, img, img_r, ff, fb, scales, loss, stats, ws, gloss=None, gf=None, gb=None) -> _cabi.UglFlowLossArgs:
+def _flow_args(img_l, img, img_r, ff, fb, scales, loss, stats, ws, gloss=None, gf=None, gb=None, basis=None) -> _cabi.UglFlowLossArgs:
     a = _cabi.UglFlowLossArgs()
+    if basis is not None:
+        for l in range(scales):
+            a.basis[l] = basis[l].data_ptr()
     L = len(img)
     a.batch, a.levels, a.scales = img[0].shape[0], L, scales
     for l in range(L):
@@ -132,9 +135,18 @@ def _flow_args(img_l, img, img_r, ff, fb, scales, loss, stats, ws, gloss=None, g
     return a
 
 
+def _alloc_basis(ff, scales):
+    return [torch.empty((f.shape[0], _cabi.FLOW_BASIS_PLANES, f.shape[2], f.shape[3]), device=f.device, dtype=torch.float32)
+            for f in ff[:scales]]
+
+
 class _FlowLossFn(torch.autograd.Function):
+    """mode 'single_pass' (default when a flow requires grad): the forward stencil kernel also writes the
+    un-normalised gradient maps, backward is an element-wise combine.  mode 'recompute': nothing per-pixel is
+    saved, the backward kernel recomputes the photometry (lower memory, ~1.4x the instructions)."""
+
     @staticmethod
-    def forward(ctx, scales: int, L: int, *ts: Tensor):
+    def forward(ctx, scales: int, L: int, mode: str, *ts: Tensor):
         ts = tuple(_dev(t, "input %d" % i) for i, t in enumerate(ts))
         img_l, img, img_r, ff, fb = (ts[k * L:(k + 1) * L] for k in range(5))
         B = img[0].shape[0]
@@ -145,40 +157,46 @@ class _FlowLossFn(torch.autograd.Function):
                 if tuple(t.shape) != (B, ch, h, w):
                     raise ValueError("flow_loss: %s[%d] has shape %s, expected %s" % (name, l, tuple(t.shape), (B, ch, h, w)))
         dev = img[0].device
+        need_grad = any(ctx.needs_input_grad[3 + 3 * L:])
+        single = need_grad and mode == "single_pass"
         loss = torch.empty((4, B), device=dev, dtype=torch.float32)
         stats = torch.empty((B, scales, _cabi.FLOW_NSTATS), device=dev, dtype=torch.float32)
-        a = _flow_args(img_l, img, img_r, ff, fb, scales, loss, stats, None)
+        basis = _alloc_basis(ff, scales) if single else None
+        a = _flow_args(img_l, img, img_r, ff, fb, scales, loss, stats, None, basis=basis)
         ws = torch.empty(max(int(_cabi.lib().ugl_flow_loss_workspace_bytes(C.byref(a))) // 4, 1), device=dev, dtype=torch.float32)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
         with torch.cuda.device_of(img[0]):
-            rc = _cabi.lib().ugl_flow_loss_forward(C.byref(a))
-        _cabi.check(rc, "ugl_flow_loss_forward")
-        _count(2)
-        ctx.save_for_backward(stats, *ts)
-        ctx.scales, ctx.L = scales, L
+            if single:
+                _call("ugl_flow_loss_forward_grad", C.byref(a), launches=2)
+            else:
+                _call("ugl_flow_loss_forward", C.byref(a), launches=2)
+        if single:
+            ctx.save_for_backward(stats, *ts, *basis)
+        else:
+            ctx.save_for_backward(stats, *ts)
+        ctx.scales, ctx.L, ctx.single = scales, L, single
         return loss
 
     @staticmethod
     def backward(ctx, gloss: Tensor):
-        stats, *ts = ctx.saved_tensors
+        stats, *rest = ctx.saved_tensors
         L, scales = ctx.L, ctx.scales
+        ts, basis = rest[:5 * L], (rest[5 * L:] if ctx.single else None)
         img_l, img, img_r, ff, fb = (ts[k * L:(k + 1) * L] for k in range(5))
         gloss = _dev(gloss, "grad_loss")
         gf = [torch.empty_like(ff[l]) for l in range(scales)]
         gb = [torch.empty_like(fb[l]) for l in range(scales)]
-        a = _flow_args(img_l, img, img_r, ff, fb, scales, None, stats, None, gloss, gf, gb)
+        a = _flow_args(img_l, img, img_r, ff, fb, scales, None, stats, None, gloss, gf, gb, basis=basis)
         with torch.cuda.device_of(gloss):
-            rc = _cabi.lib().ugl_flow_loss_backward(C.byref(a))
-        _cabi.check(rc, "ugl_flow_loss_backward")
-        _count(1)
+            _call("ugl_flow_loss_combine" if ctx.single else "ugl_flow_loss_backward", C.byref(a))
         none_l = [None] * L
         pad = [None] * (L - scales)
-        return (None, None, *none_l, *none_l, *none_l, *gf, *pad, *gb, *pad)
+        return (None, None, None, *none_l, *none_l, *none_l, *gf, *pad, *gb, *pad)
 
 
 def flow_loss_step(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r_pyr: Sequence[Tensor],
                    flows_fwd: Sequence[Tensor], flows_bwd: Sequence[Tensor], grad_loss: Tensor,
-                   num_scales: Optional[int] = None, out: Optional[dict] = None):
+                   num_scales: Optional[int] = None, out: Optional[dict] = None, mode: str = "single_pass"):
     """Forward + backward of the fused flow-mode loss in one call, without the autograd engine: for
     the training step where the upstream gradient is known up front (``train.py:211-215``:
     ``d total / d loss_k[b] = w_k / B``).  Returns ``(loss (4,B), grads_fwd, grads_bwd)``; pass the
@@ -193,21 +211,27 @@ def flow_loss_step(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r
     if out is None:
         out = {"loss": torch.empty((4, B), device=dev, dtype=torch.float32),
                "stats": torch.empty((B, scales, _cabi.FLOW_NSTATS), device=dev, dtype=torch.float32),
-               "gf": [torch.empty_like(ff[l]) for l in range(scales)], "gb": [torch.empty_like(fb[l]) for l in range(scales)]}
+               "gf": [torch.empty_like(ff[l]) for l in range(scales)], "gb": [torch.empty_like(fb[l]) for l in range(scales)],
+               "basis": _alloc_basis(ff, scales) if mode == "single_pass" else None}
         a = _flow_args(img_l, img, img_r, ff, fb, scales, out["loss"], out["stats"], None)
         out["ws"] = torch.empty(max(int(_cabi.lib().ugl_flow_loss_workspace_bytes(C.byref(a))) // 4, 1), device=dev,
                                 dtype=torch.float32)
-    a = _flow_args(img_l, img, img_r, ff, fb, scales, out["loss"], out["stats"], out["ws"], gloss, out["gf"], out["gb"])
+    a = _flow_args(img_l, img, img_r, ff, fb, scales, out["loss"], out["stats"], out["ws"], gloss, out["gf"], out["gb"],
+                   basis=out["basis"])
     with torch.cuda.device_of(img[0]):
-        _cabi.check(_cabi.lib().ugl_flow_loss_forward(C.byref(a)), "ugl_flow_loss_forward")
-        _cabi.check(_cabi.lib().ugl_flow_loss_backward(C.byref(a)), "ugl_flow_loss_backward")
+        if out["basis"] is not None:
+            _cabi.check(_cabi.lib().ugl_flow_loss_forward_grad(C.byref(a)), "ugl_flow_loss_forward_grad")
+            _cabi.check(_cabi.lib().ugl_flow_loss_combine(C.byref(a)), "ugl_flow_loss_combine")
+        else:
+            _cabi.check(_cabi.lib().ugl_flow_loss_forward(C.byref(a)), "ugl_flow_loss_forward")
+            _cabi.check(_cabi.lib().ugl_flow_loss_backward(C.byref(a)), "ugl_flow_loss_backward")
     _count(3)
     return out
 
 
 def flow_loss(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r_pyr: Sequence[Tensor],
               flows_fwd: Sequence[Tensor], flows_bwd: Sequence[Tensor], num_scales: Optional[int] = None,
-              as_matrix: bool = False):
+              as_matrix: bool = False, mode: str = "single_pass"):
     """Fused loss body of ``Model_flow.forward`` (model_flow.py:232-254).
 
     Takes the three image pyramids (``generate_img_pyramid`` outputs) and the forward / backward flow
@@ -220,7 +244,9 @@ def flow_loss(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r_pyr:
     scales = L if num_scales is None else int(num_scales)
     if not 1 <= scales <= L or L > _cabi.MAX_LEVELS:
         raise ValueError("flow_loss: num_scales=%d outside [1, %d]" % (scales, L))
-    loss = _FlowLossFn.apply(scales, L, *img_l_pyr[:L], *img_pyr[:L], *img_r_pyr[:L], *flows_fwd, *flows_bwd)
+    if mode not in ("single_pass", "recompute"):
+        raise ValueError("flow_loss: mode must be 'single_pass' or 'recompute'")
+    loss = _FlowLossFn.apply(scales, L, mode, *img_l_pyr[:L], *img_pyr[:L], *img_r_pyr[:L], *flows_fwd, *flows_bwd)
     if as_matrix:
         return loss
     return {k: loss[i] for i, k in enumerate(FLOW_LOSS_KEYS)}
