@@ -137,9 +137,11 @@ struct FlowGradTile {
         uf = ff[pix]; vf = ff[plane + pix];
         ub = fb[pix]; vb = fb[plane + pix];
         const bool interior = (ly >= R && ly < R + TH && lx >= R && lx < R + TW);
+        // one uniform code path for interior and halo pixels (a warp straddling both would otherwise execute the
+        // gradient and the non-gradient variant back to back, and the second copy doubles the I-cache footprint)
+        float dW[12];
+        flow_photo_pixel_c<true>(L, tc.b, i, j, uf, vf, ub, vb, P, dW);
         if (interior) {
-          float dW[12];
-          flow_photo_pixel_c<true>(L, tc.b, i, j, uf, vf, ub, vb, P, dW);
           const int t = (ly - R) * TW + (lx - R);
           float* o = sm + kOffDW + t;
 #pragma unroll
@@ -172,8 +174,6 @@ struct FlowGradTile {
           const float ir = rf > 0.f ? fast_div(1.0f, rf) : 0.f;
           basis[6 * plane + pix] = su * inf_ + gn * uf * ir;
           basis[7 * plane + pix] = sv * inf_ + gn * vf * ir;
-        } else {
-          flow_photo_pixel_c<false>(L, tc.b, i, j, uf, vf, ub, vb, P, nullptr);
         }
       } else {
         zero_photo(P);
@@ -189,7 +189,8 @@ struct FlowGradTile {
   static UGL_HD void phase2(const FlowGradParams& gp, const TileCoord& tc, int dir, int tid, int nt, float* sm, float* acc) {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     constexpr int SW = CW / 2;                       // strips per row
-    const float* wpl = sm + (dir == 0 ? PL_WF : PL_WB) * PN;
+    const float* wpl = sm + (PL_WF + dir) * PN;
+    const float* ybase = sm + (PL_F0 + 3 * dir) * PN;       // PL_B0 = PL_F0 + 3
     float ssim_sum = 0.f;
     for (int s = tid; s < SW * CH; s += nt) {
       const int ly = s / SW, lx = (s - ly * SW) * 2;          // halo-1 coordinates of the left centre
@@ -204,10 +205,10 @@ struct FlowGradTile {
         const float2 b2 = *reinterpret_cast<const float2*>(wpl + c0 + (r - 1) * PW + 1);
         wt[r][0] = a.x; wt[r][1] = a.y; wt[r][2] = b2.x; wt[r][3] = b2.y;
       }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {           // rolled on purpose: keeps the kernel inside the instruction cache
         const float* ipl = sm + (PL_I0 + c) * PN;
-        const float* ypl = sm + ((dir == 0 ? PL_F0 : PL_B0) + c) * PN;
+        const float* ypl = ybase + c * PN;
         float x[3][4], y[3][4], xx[3][4], yy[3][4], xy[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -272,7 +273,7 @@ struct FlowGradTile {
         *reinterpret_cast<float2*>(sm + kOffEdge + CN + ly * CW + lx) = make_float2(wy[0], wy[1]);
       }
     }
-    acc[dir == 0 ? FA_SSIM_F : FA_SSIM_B] += ssim_sum;
+    if (dir == 0) acc[FA_SSIM_F] += ssim_sum; else acc[FA_SSIM_B] += ssim_sum;
   }
 
   // phase 3 (per direction): 1x2 strips over the interior: 3x3 box sums of the coefficients (vertical sums shared by
@@ -280,7 +281,7 @@ struct FlowGradTile {
   static UGL_HD void phase3(const FlowGradParams& gp, const TileCoord& tc, int dir, int tid, int nt, const float* sm) {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     const int plane = L.h * L.w;
-    float* basis = gp.basis[tc.level] + ((long)tc.b * kBasisPlanes + (dir == 0 ? 0 : 8)) * plane;
+    float* basis = gp.basis[tc.level] + ((long)tc.b * kBasisPlanes + 8 * dir) * plane;
     constexpr int SW = TW / 2;
     for (int s = tid; s < SW * TH; s += nt) {
       const int ty = s / SW, tx = (s - ty * SW) * 2;
@@ -289,10 +290,10 @@ struct FlowGradTile {
       const int c0 = (ty + R) * PW + (tx + R);       // photometry planes, left pixel
       const int q0 = (ty + 1) * CW + (tx + 1);       // coefficient planes, left pixel
       const int t0 = ty * TW + tx;
-      const float2 wq = *reinterpret_cast<const float2*>(sm + (dir == 0 ? PL_WF : PL_WB) * PN + c0);
+      const float2 wq = *reinterpret_cast<const float2*>(sm + (PL_WF + dir) * PN + c0);
       const float wv[2] = {wq.x, wq.y};
       float gsu[2] = {0.f, 0.f}, gsv[2] = {0.f, 0.f};
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 3; ++c) {
         float sum[3][2];
 #pragma unroll
@@ -309,7 +310,7 @@ struct FlowGradTile {
           sum[k][1] = col[1] + col[2] + col[3];
         }
         const float2 Iv = *reinterpret_cast<const float2*>(sm + (PL_I0 + c) * PN + c0);
-        const float2 Wv = *reinterpret_cast<const float2*>(sm + ((dir == 0 ? PL_F0 : PL_B0) + c) * PN + c0);
+        const float2 Wv = *reinterpret_cast<const float2*>(sm + (PL_F0 + 3 * dir + c) * PN + c0);
         const float2 du = *reinterpret_cast<const float2*>(sm + kOffDW + (6 * dir + 2 * c) * TN + t0);
         const float2 dv = *reinterpret_cast<const float2*>(sm + kOffDW + (6 * dir + 2 * c + 1) * TN + t0);
         const float I2[2] = {Iv.x, Iv.y}, W2[2] = {Wv.x, Wv.y}, du2[2] = {du.x, du.y}, dv2[2] = {dv.x, dv.y};

@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(NT) flow_loss_fwdgrad_kernel(const __grid_cons
   for (int k = 0; k < FA_COUNT; ++k) acc[k] = 0.f;
   Tile::phase1(gp, tc, threadIdx.x, NT, sm, acc);
   __syncthreads();
-#pragma unroll
-  for (int dir = 0; dir < 2; ++dir) {
+#pragma unroll 1
+  for (int dir = 0; dir < 2; ++dir) {          // rolled: one copy of the stencil phases in the instruction cache
     Tile::phase2(gp, tc, dir, threadIdx.x, NT, sm, acc);
     __syncthreads();
     Tile::phase3(gp, tc, dir, threadIdx.x, NT, sm);

@@ -150,6 +150,7 @@ UGL_HD float consis_value(float uf, float vf, float ub, float vb) {
 // shared-memory planes of the halo'd tile (structure of arrays).  Flows are stored pre-divided by 20
 // (model_flow.py:177 `flow/20.0`), the only form the stencils need.
 enum FlowPlane { PL_I0 = 0, PL_I1, PL_I2, PL_F0, PL_F1, PL_F2, PL_B0, PL_B1, PL_B2, PL_WF, PL_WB, PL_UF, PL_VF, PL_UB, PL_VB, PL_COUNT };
+static_assert(PL_B0 == PL_F0 + 3 && PL_WB == PL_WF + 1, "the single-pass kernel indexes the direction planes arithmetically");
 
 template <int PN>
 UGL_HD void store_photo_planes(float* sm, int idx, const Photo& P, float uf, float vf, float ub, float vb) {
