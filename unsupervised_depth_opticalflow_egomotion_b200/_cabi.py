@@ -14,7 +14,7 @@ FLOW_NSTATS = 12
 FLOW_BASIS_PLANES = 14
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libugl_b200.so")
+LIB_PATH = os.environ.get("UGL_LIB_PATH") or os.path.join(_HERE, "libugl_b200.so")   # override: tuning experiments only
 
 _fp = C.POINTER(C.c_float)
 

@@ -226,6 +226,7 @@ UGL_HD void moments_add(Moments& m, float x, float y) {
 // cancellation in E[x^2]-mu^2 amplifies any re-association, so this is pinned, not contracted.
 struct SsimTerms { float mx, my, n1, n2, d1, d2, S; };
 
+template <bool kExactDiv = true>
 UGL_HD SsimTerms ssim_terms(const Moments& m) {
   SsimTerms t;
   constexpr float r9 = 1.0f / 9.0f;
@@ -239,11 +240,13 @@ UGL_HD SsimTerms ssim_terms(const Moments& m) {
   t.n2 = add_rn(mul_rn(2.0f, cxy), kC2);
   t.d1 = add_rn(add_rn(mxx, myy), kC1);
   t.d2 = add_rn(add_rn(vx, vy), kC2);
-  t.S = div_rn(mul_rn(t.n1, t.n2), mul_rn(t.d1, t.d2));
+  // kExactDiv = false: the moments stay bit-identical to ATen's, only the last quotient uses the ~1-ulp
+  // reciprocal (2 instructions instead of the ~15 of the IEEE division subroutine)
+  t.S = kExactDiv ? div_rn(mul_rn(t.n1, t.n2), mul_rn(t.d1, t.d2)) : fast_div(mul_rn(t.n1, t.n2), mul_rn(t.d1, t.d2));
   return t;
 }
 
-UGL_HD float ssim_from_sums(const Moments& m) { return ssim_terms(m).S; }
+UGL_HD float ssim_from_sums(const Moments& m) { return ssim_terms<true>(m).S; }
 
 // loss value clamp((1-S)/2, 0, 1)
 UGL_HD float ssim_loss_value(float S) {
@@ -261,7 +264,7 @@ UGL_HD void ssim_partials(const SsimTerms& t, float g, float& ax, float& bx, flo
 // Given window sums, produce g * dS/d(mu_y), g * dS/d(E[y^2]), g * dS/d(E[xy]) where g = d loss / dS
 // (= -1/2 inside the clamp range [0,1] inclusive, 0 outside — torch.clamp backward).
 UGL_HD void ssim_backward_coeffs(const Moments& m, float& cA, float& cB, float& cC) {
-  const SsimTerms t = ssim_terms(m);
+  const SsimTerms t = ssim_terms<true>(m);
   const float v = mul_rn(sub_rn(1.0f, t.S), 0.5f);
   const float g = (v >= 0.f && v <= 1.f) ? -0.5f : 0.f;
   float ax, bx;

@@ -182,45 +182,42 @@ struct FlowGradTile {
     }
   }
 
-  // phase 2 (per direction): 1x2 strips over the halo-1 region.  Each strip loads the 3x4 taps it needs once,
-  // forms x = I*w, y = W*w and their products once, and accumulates the two 3x3 windows in the reference's
-  // row-major order (bit-identical SSIM).  Writes the SSIM backward coefficients; window centres that are interior
-  // pixels also add their SSIM loss value; the first direction also stores the smoothness edge weights.
+  // phase 2 (per direction): work units = (channel, 1x2 strip of the halo-1 region), flattened so that the 3 x 306
+  // units spread evenly over the CTA (per-strip loops left two warps with double work and six waiting at the barrier).
+  // A unit loads the 3x4 taps it needs once, forms x = I*w, y = W*w and their products once, and accumulates the two
+  // 3x3 windows in the reference's row-major order (bit-identical SSIM).  It writes the SSIM backward coefficients;
+  // window centres that are interior pixels also add their SSIM loss value.  In the first direction a fourth unit
+  // type computes the smoothness edge weights of the strip.
   static UGL_HD void phase2(const FlowGradParams& gp, const TileCoord& tc, int dir, int tid, int nt, float* sm, float* acc) {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     constexpr int SW = CW / 2;                       // strips per row
+    constexpr int NS = SW * CH;                      // strips per tile
     const float* wpl = sm + (PL_WF + dir) * PN;
     const float* ybase = sm + (PL_F0 + 3 * dir) * PN;       // PL_B0 = PL_F0 + 3
     float ssim_sum = 0.f;
-    for (int s = tid; s < SW * CH; s += nt) {
+    const int units = (dir == 0 ? 4 : 3) * NS;
+    for (int u = tid; u < units; u += nt) {
+      const int c = u / NS, s = u - c * NS;
       const int ly = s / SW, lx = (s - ly * SW) * 2;          // halo-1 coordinates of the left centre
       const int i = tc.y0 - 1 + ly, j0 = tc.x0 - 1 + lx;
       const int c0 = (ly + 1) * PW + (lx + 1);                // photometry-plane index of the left centre
       const bool row_in = (i >= 0 && i < L.h);
       const bool in0 = row_in && j0 >= 0 && j0 < L.w, in1 = row_in && j0 + 1 >= 0 && j0 + 1 < L.w;
-      float wt[3][4];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const float2 a = *reinterpret_cast<const float2*>(wpl + c0 + (r - 1) * PW - 1);
-        const float2 b2 = *reinterpret_cast<const float2*>(wpl + c0 + (r - 1) * PW + 1);
-        wt[r][0] = a.x; wt[r][1] = a.y; wt[r][2] = b2.x; wt[r][3] = b2.y;
-      }
-#pragma unroll 1
-      for (int c = 0; c < 3; ++c) {           // rolled on purpose: keeps the kernel inside the instruction cache
+      if (c < 3) {
         const float* ipl = sm + (PL_I0 + c) * PN;
         const float* ypl = ybase + c * PN;
         float x[3][4], y[3][4], xx[3][4], yy[3][4], xy[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          const float2 ia = *reinterpret_cast<const float2*>(ipl + c0 + (r - 1) * PW - 1);
-          const float2 ib = *reinterpret_cast<const float2*>(ipl + c0 + (r - 1) * PW + 1);
-          const float2 ya = *reinterpret_cast<const float2*>(ypl + c0 + (r - 1) * PW - 1);
-          const float2 yb = *reinterpret_cast<const float2*>(ypl + c0 + (r - 1) * PW + 1);
-          const float iv[4] = {ia.x, ia.y, ib.x, ib.y}, yv[4] = {ya.x, ya.y, yb.x, yb.y};
+          const int o = c0 + (r - 1) * PW;
+          const float2 wa = *reinterpret_cast<const float2*>(wpl + o - 1), wb = *reinterpret_cast<const float2*>(wpl + o + 1);
+          const float2 ia = *reinterpret_cast<const float2*>(ipl + o - 1), ib = *reinterpret_cast<const float2*>(ipl + o + 1);
+          const float2 ya = *reinterpret_cast<const float2*>(ypl + o - 1), yb = *reinterpret_cast<const float2*>(ypl + o + 1);
+          const float wv[4] = {wa.x, wa.y, wb.x, wb.y}, iv[4] = {ia.x, ia.y, ib.x, ib.y}, yv[4] = {ya.x, ya.y, yb.x, yb.y};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            x[r][k] = mul_rn(iv[k], wt[r][k]);
-            y[r][k] = mul_rn(yv[k], wt[r][k]);
+            x[r][k] = mul_rn(iv[k], wv[k]);
+            y[r][k] = mul_rn(yv[k], wv[k]);
             xx[r][k] = mul_rn(x[r][k], x[r][k]);
             yy[r][k] = mul_rn(y[r][k], y[r][k]);
             xy[r][k] = mul_rn(x[r][k], y[r][k]);
@@ -238,7 +235,7 @@ struct FlowGradTile {
                 m.sx = add_rn(m.sx, x[r][o + k]); m.sy = add_rn(m.sy, y[r][o + k]);
                 m.sxx = add_rn(m.sxx, xx[r][o + k]); m.syy = add_rn(m.syy, yy[r][o + k]); m.sxy = add_rn(m.sxy, xy[r][o + k]);
               }
-            const SsimTerms t = ssim_terms(m);
+            const SsimTerms t = ssim_terms<false>(m);
             const float v = mul_rn(sub_rn(1.0f, t.S), 0.5f);
             const float g = (v >= 0.f && v <= 1.f) ? -0.5f : 0.f;
             float ax, bx;
@@ -251,8 +248,7 @@ struct FlowGradTile {
         *reinterpret_cast<float2*>(oc) = make_float2(cA[0], cA[1]);
         *reinterpret_cast<float2*>(oc + CN) = make_float2(cB[0], cB[1]);
         *reinterpret_cast<float2*>(oc + 2 * CN) = make_float2(cC[0], cC[1]);
-      }
-      if (dir == 0) {
+      } else {
         float wx[2] = {0.f, 0.f}, wy[2] = {0.f, 0.f};
 #pragma unroll
         for (int o = 0; o < 2; ++o) {

@@ -7,7 +7,10 @@
 namespace ugl {
 
 constexpr int kFNT = 256;   // forward  threads per CTA (one CTA per tile)
-constexpr int kBNT = 256;   // backward threads per CTA
+#ifndef UGL_BNT
+#define UGL_BNT 256
+#endif
+constexpr int kBNT = UGL_BNT;   // backward / single-pass threads per CTA
 
 template <int TW, int TH, int NT>
 __global__ void __launch_bounds__(NT) flow_loss_fwd_kernel(const __grid_constant__ FlowLossParams p) {
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(NT) flow_loss_bwd_kernel(const __grid_constant
 
 // single-pass: losses + gradient basis maps
 template <int TW, int TH, int NT>
-__global__ void __launch_bounds__(NT) flow_loss_fwdgrad_kernel(const __grid_constant__ FlowGradParams gp) {
+__global__ void __launch_bounds__(NT, UGL_BMINB) flow_loss_fwdgrad_kernel(const __grid_constant__ FlowGradParams gp) {
   extern __shared__ __align__(16) float sm[];
   __shared__ float red[(NT / 32) * FA_COUNT];
   using Tile = FlowGradTile<TW, TH, NT>;
@@ -172,10 +175,12 @@ using namespace ugl;
 
 extern "C" uint64_t ugl_flow_loss_workspace_bytes(const UglFlowLossArgs* a) {
   if (!a) return 0;
-  uint64_t tiles = 0;   // only the shapes matter here
-  for (int l = 0; l < a->scales && l < UGL_MAX_LEVELS; ++l)
-    tiles += (uint64_t)((a->width[l] + kFTW - 1) / kFTW) * ((a->height[l] + kFTH - 1) / kFTH) * a->batch;
-  return tiles * FA_COUNT * sizeof(float);
+  uint64_t tf = 0, tb = 0;   // only the shapes matter here; cover the forward and the single-pass tile shapes
+  for (int l = 0; l < a->scales && l < UGL_MAX_LEVELS; ++l) {
+    tf += (uint64_t)((a->width[l] + kFTW - 1) / kFTW) * ((a->height[l] + kFTH - 1) / kFTH) * a->batch;
+    tb += (uint64_t)((a->width[l] + kBTW - 1) / kBTW) * ((a->height[l] + kBTH - 1) / kBTH) * a->batch;
+  }
+  return (tf > tb ? tf : tb) * FA_COUNT * sizeof(float);
 }
 
 extern "C" int ugl_flow_loss_launches(int backward) { return backward ? 1 : 2; }

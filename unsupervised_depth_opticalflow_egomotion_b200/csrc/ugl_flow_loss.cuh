@@ -23,8 +23,17 @@
 namespace ugl {
 
 // tile shapes (interior pixels per CTA) of the forward and backward kernels
+#ifndef UGL_BTW
+#define UGL_BTW 32
+#endif
+#ifndef UGL_BTH
+#define UGL_BTH 12     /* swept on B200 (profiles/r1e_tile_sweep.txt): 32x12x256 is the fastest single-pass tile */
+#endif
+#ifndef UGL_BMINB
+#define UGL_BMINB 2
+#endif
 constexpr int kFTW = 32, kFTH = 16;
-constexpr int kBTW = 32, kBTH = 16;
+constexpr int kBTW = UGL_BTW, kBTH = UGL_BTH;   // backward / single-pass tiles (tunable at build time for experiments)
 
 // per-(sample, level) accumulators
 enum FlowAcc {

@@ -108,7 +108,7 @@ ssim_bwd_kernel(SsimArgs a, const float* __restrict__ gout, const float* __restr
     const int i = y0 - 1 + ly, j = x0 - 1 + lx;
     float ax = 0.f, bx = 0.f, ay = 0.f, by = 0.f, cxy = 0.f;
     if (i >= 0 && i < a.H && j >= 0 && j < a.W) {
-      const SsimTerms t = ssim_terms(tile_moments<PW>(sx, sy, (ly + 1) * PW + lx + 1));
+      const SsimTerms t = ssim_terms<true>(tile_moments<PW>(sx, sy, (ly + 1) * PW + lx + 1));
       float g;
       if (kLoss) {
         const float v = mul_rn(sub_rn(1.0f, t.S), 0.5f);
