@@ -29,45 +29,69 @@ __global__ void __launch_bounds__(NT) flow_loss_fwd_kernel(const __grid_constant
   if (threadIdx.x < FA_COUNT) p.partials[(long)tile * FA_COUNT + threadIdx.x] = v;
 }
 
-// one CTA per sample, one warp per level: ordered (deterministic) fp64 sum of the tile partials
-__global__ void flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p) {
-  __shared__ float lvl_loss[kMaxLevels][4];
-  const int b = blockIdx.x, lane = threadIdx.x & 31, l = threadIdx.x >> 5;
-  if (l < p.scales) {
-    const FlowLevelDesc& L = p.lv[l];
-    const int per_img = L.tiles_x * L.tiles_y;
-    const float* base = p.partials + ((long)L.tile_begin + (long)b * per_img) * FA_COUNT;
-    double s[FA_COUNT];
+// Finalize: one CTA per (level, sample).  256 threads stride over that sample-level's tile partials (fp64, fixed
+// order), a shuffle + shared-memory tree reduces them (deterministic), thread 0 applies the closing formulas and
+// stores the level sums for backward.  The CTA that finishes a sample last (ticket counter, zeroed by a memset node
+// before the launch) adds the levels up in level order -> loss (4,B).
+constexpr int kFinThreads = 256;
+__global__ void __launch_bounds__(kFinThreads)
+flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __restrict__ lvl_loss /* [B][scales][4] */,
+                          unsigned* __restrict__ tickets /* [B] */) {
+  __shared__ double red[kFinThreads / 32][FA_COUNT];
+  __shared__ bool last;
+  const int l = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const FlowLevelDesc& L = p.lv[l];
+  const int per_img = L.tiles_x * L.tiles_y;
+  const float* base = p.partials + ((long)L.tile_begin + (long)b * per_img) * FA_COUNT;
+  double s[FA_COUNT];
 #pragma unroll
-    for (int k = 0; k < FA_COUNT; ++k) s[k] = 0.0;
-    for (int t = lane; t < per_img; t += 32) {
+  for (int k = 0; k < FA_COUNT; ++k) s[k] = 0.0;
+  for (int t = threadIdx.x; t < per_img; t += kFinThreads) {
 #pragma unroll
-      for (int k = 0; k < FA_COUNT; ++k) s[k] += (double)base[(long)t * FA_COUNT + k];
-    }
-    float S[FA_COUNT];
+    for (int k = 0; k < FA_COUNT; ++k) s[k] += (double)base[(long)t * FA_COUNT + k];
+  }
 #pragma unroll
-    for (int k = 0; k < FA_COUNT; ++k) {
-      double v = s[k];
+  for (int k = 0; k < FA_COUNT; ++k) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      S[k] = (float)__shfl_sync(0xffffffffu, v, 0);
-    }
-    if (lane == 0) {
-      float* st = p.stats + ((long)b * p.scales + l) * FA_COUNT;
-#pragma unroll
-      for (int k = 0; k < FA_COUNT; ++k) st[k] = S[k];
-      float out[4];
-      flow_level_losses(S, L.h, L.w, out);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) lvl_loss[l][k] = out[k];
-    }
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_down_sync(0xffffffffu, s[k], o);
+    if (lane == 0) red[warp][k] = s[k];
   }
   __syncthreads();
-  if (threadIdx.x < 4) {
+  if (threadIdx.x == 0) {
+    float S[FA_COUNT], out[4];
+    float* st = p.stats + ((long)b * p.scales + l) * FA_COUNT;
+#pragma unroll
+    for (int k = 0; k < FA_COUNT; ++k) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kFinThreads / 32; ++w) v += red[w][k];
+      S[k] = (float)v;
+      st[k] = S[k];
+    }
+    flow_level_losses(S, L.h, L.w, out);
+    float* ll = lvl_loss + ((long)b * p.scales + l) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ll[k] = out[k];
+    __threadfence();
+    last = (atomicAdd(&tickets[b], 1u) == (unsigned)(p.scales - 1));
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 4) {
+    __threadfence();
     float t = 0.f;
-    for (int l2 = 0; l2 < p.scales; ++l2) t += lvl_loss[l2][threadIdx.x];
+    for (int l2 = 0; l2 < p.scales; ++l2) t += __ldcg(lvl_loss + ((long)b * p.scales + l2) * 4 + threadIdx.x);
     p.loss[threadIdx.x * p.B + b] = t;
   }
+}
+
+static int launch_finalize(const FlowLossParams& p, cudaStream_t st) {
+  // scratch behind the tile partials: [B][scales][4] level losses, then B ticket counters
+  float* lvl_loss = p.partials + (size_t)p.total_tiles * FA_COUNT;
+  unsigned* tickets = reinterpret_cast<unsigned*>(lvl_loss + (size_t)p.B * p.scales * 4);
+  const cudaError_t e = cudaMemsetAsync(tickets, 0, sizeof(unsigned) * p.B, st);
+  if (e != cudaSuccess) return fail((int)e, "flow_loss finalize: memset: %s", cudaGetErrorString(e));
+  flow_loss_finalize_kernel<<<dim3(p.scales, p.B), kFinThreads, 0, st>>>(p, lvl_loss, tickets);
+  return check_launch("flow_loss_finalize_kernel");
 }
 
 template <int TW, int TH, int NT>
@@ -126,8 +150,34 @@ __global__ void __launch_bounds__(256) flow_combine_kernel(const __grid_constant
   const float* basis = gp.basis[l] + (long)b * kBasisPlanes * plane;
   float* gf = L.gflow_f + (long)b * 2 * plane;
   float* gb = L.gflow_b + (long)b * 2 * plane;
-  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < plane; pix += gridDim.x * blockDim.x)
-    flow_combine_pixel(basis, plane, pix, k, gf, gb);
+  if ((plane & 3) == 0) {   // 128-bit path (every plane start is then 16-byte aligned: torch allocations are 512-byte aligned)
+    const float4* b4 = reinterpret_cast<const float4*>(basis);
+    float4* gf4 = reinterpret_cast<float4*>(gf);
+    float4* gb4 = reinterpret_cast<float4*>(gb);
+    const int q = plane >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q; i += gridDim.x * blockDim.x) {
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const float4 a0 = __ldcs(b4 + (0 + ch) * q + i), a1 = __ldcs(b4 + (2 + ch) * q + i), a2 = __ldcs(b4 + (4 + ch) * q + i),
+                     a3 = __ldcs(b4 + (6 + ch) * q + i);
+        const float4 c0 = __ldcs(b4 + (8 + ch) * q + i), c1 = __ldcs(b4 + (10 + ch) * q + i), c2 = __ldcs(b4 + (12 + ch) * q + i);
+        float4 f, g;
+        f.x = k.pix[0] * a0.x + k.ssim[0] * a1.x + k.sm * a2.x + k.cons * a3.x;
+        f.y = k.pix[0] * a0.y + k.ssim[0] * a1.y + k.sm * a2.y + k.cons * a3.y;
+        f.z = k.pix[0] * a0.z + k.ssim[0] * a1.z + k.sm * a2.z + k.cons * a3.z;
+        f.w = k.pix[0] * a0.w + k.ssim[0] * a1.w + k.sm * a2.w + k.cons * a3.w;
+        g.x = k.pix[1] * c0.x + k.ssim[1] * c1.x + k.sm * c2.x;
+        g.y = k.pix[1] * c0.y + k.ssim[1] * c1.y + k.sm * c2.y;
+        g.z = k.pix[1] * c0.z + k.ssim[1] * c1.z + k.sm * c2.z;
+        g.w = k.pix[1] * c0.w + k.ssim[1] * c1.w + k.sm * c2.w;
+        gf4[ch * q + i] = f;
+        gb4[ch * q + i] = g;
+      }
+    }
+  } else {
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < plane; pix += gridDim.x * blockDim.x)
+      flow_combine_pixel(basis, plane, pix, k, gf, gb);
+  }
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -180,7 +230,8 @@ extern "C" uint64_t ugl_flow_loss_workspace_bytes(const UglFlowLossArgs* a) {
     tf += (uint64_t)((a->width[l] + kFTW - 1) / kFTW) * ((a->height[l] + kFTH - 1) / kFTH) * a->batch;
     tb += (uint64_t)((a->width[l] + kBTW - 1) / kBTW) * ((a->height[l] + kBTH - 1) / kBTH) * a->batch;
   }
-  return (tf > tb ? tf : tb) * FA_COUNT * sizeof(float);
+  // tile partials + [B][scales][4] level losses + B ticket counters (finalize scratch)
+  return (tf > tb ? tf : tb) * FA_COUNT * sizeof(float) + (uint64_t)a->batch * a->scales * 4 * sizeof(float) + (uint64_t)a->batch * sizeof(unsigned);
 }
 
 extern "C" int ugl_flow_loss_launches(int backward) { return backward ? 1 : 2; }
@@ -190,7 +241,7 @@ extern "C" int ugl_flow_loss_forward(const UglFlowLossArgs* a) {
   int rc = build_params<kFTW, kFTH>(a, false, p);
   if (rc) return rc;
   if (!a->loss) return fail(UGL_EINVAL, "flow_loss_forward: null loss");
-  if (!a->workspace || a->workspace_bytes < (uint64_t)p.total_tiles * FA_COUNT * sizeof(float))
+  if (!a->workspace || a->workspace_bytes < ugl_flow_loss_workspace_bytes(a))
     return fail(UGL_EWORKSPACE, "flow_loss_forward: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   using Tile = FlowFwdTile<kFTW, kFTH>;
@@ -200,8 +251,7 @@ extern "C" int ugl_flow_loss_forward(const UglFlowLossArgs* a) {
   if ((rc = opt_in_smem(kern, smem))) return rc;
   kern<<<p.total_tiles, kFNT, smem, st>>>(p);
   if ((rc = check_launch("flow_loss_fwd_kernel"))) return rc;
-  flow_loss_finalize_kernel<<<p.B, 32 * kMaxLevels, 0, st>>>(p);
-  return check_launch("flow_loss_finalize_kernel");
+  return launch_finalize(p, st);
 }
 
 extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) {
@@ -214,7 +264,7 @@ extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) {
     if (reinterpret_cast<uintptr_t>(a->basis[l]) & 7u) return fail(UGL_EALIGN, "flow_loss_forward_grad: basis not 8-byte aligned");
     gp.basis[l] = a->basis[l];
   }
-  if (!a->workspace || a->workspace_bytes < (uint64_t)gp.base.total_tiles * FA_COUNT * sizeof(float))
+  if (!a->workspace || a->workspace_bytes < ugl_flow_loss_workspace_bytes(a))
     return fail(UGL_EWORKSPACE, "flow_loss_forward_grad: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   using Tile = FlowGradTile<kBTW, kBTH, kBNT>;
@@ -224,8 +274,7 @@ extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) {
   if ((rc = opt_in_smem(kern, smem))) return rc;
   kern<<<gp.base.total_tiles, kBNT, smem, st>>>(gp);
   if ((rc = check_launch("flow_loss_fwdgrad_kernel"))) return rc;
-  flow_loss_finalize_kernel<<<gp.base.B, 32 * kMaxLevels, 0, st>>>(gp.base);
-  return check_launch("flow_loss_finalize_kernel");
+  return launch_finalize(gp.base, st);
 }
 
 extern "C" int ugl_flow_loss_combine(const UglFlowLossArgs* a) {

@@ -196,7 +196,7 @@ class _FlowLossFn(torch.autograd.Function):
 
 def flow_loss_step(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r_pyr: Sequence[Tensor],
                    flows_fwd: Sequence[Tensor], flows_bwd: Sequence[Tensor], grad_loss: Tensor,
-                   num_scales: Optional[int] = None, out: Optional[dict] = None, mode: str = "single_pass"):
+                   num_scales: Optional[int] = None, out: Optional[dict] = None, mode: str = "single_pass", phase: str = "both"):
     """Forward + backward of the fused flow-mode loss in one call, without the autograd engine: for
     the training step where the upstream gradient is known up front (``train.py:211-215``:
     ``d total / d loss_k[b] = w_k / B``).  Returns ``(loss (4,B), grads_fwd, grads_bwd)``; pass the
@@ -218,14 +218,19 @@ def flow_loss_step(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r
                                 dtype=torch.float32)
     a = _flow_args(img_l, img, img_r, ff, fb, scales, out["loss"], out["stats"], out["ws"], gloss, out["gf"], out["gb"],
                    basis=out["basis"])
+    fwd, bwd = phase in ("both", "forward"), phase in ("both", "backward")   # 'forward'/'backward': one half only (kernel timing)
     with torch.cuda.device_of(img[0]):
         if out["basis"] is not None:
-            _cabi.check(_cabi.lib().ugl_flow_loss_forward_grad(C.byref(a)), "ugl_flow_loss_forward_grad")
-            _cabi.check(_cabi.lib().ugl_flow_loss_combine(C.byref(a)), "ugl_flow_loss_combine")
+            if fwd:
+                _cabi.check(_cabi.lib().ugl_flow_loss_forward_grad(C.byref(a)), "ugl_flow_loss_forward_grad")
+            if bwd:
+                _cabi.check(_cabi.lib().ugl_flow_loss_combine(C.byref(a)), "ugl_flow_loss_combine")
         else:
-            _cabi.check(_cabi.lib().ugl_flow_loss_forward(C.byref(a)), "ugl_flow_loss_forward")
-            _cabi.check(_cabi.lib().ugl_flow_loss_backward(C.byref(a)), "ugl_flow_loss_backward")
-    _count(3)
+            if fwd:
+                _cabi.check(_cabi.lib().ugl_flow_loss_forward(C.byref(a)), "ugl_flow_loss_forward")
+            if bwd:
+                _cabi.check(_cabi.lib().ugl_flow_loss_backward(C.byref(a)), "ugl_flow_loss_backward")
+    _count((2 if fwd else 0) + (1 if bwd else 0))
     return out
 
 

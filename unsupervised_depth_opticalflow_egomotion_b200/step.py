@@ -24,8 +24,27 @@ def weight_matrix(weights: Dict[str, float], keys: Sequence[str], batch: int, de
     return w.to(device).contiguous()
 
 
+class _Slot:
+    """One set of device staging buffers + the events that order its reuse."""
+
+    def __init__(self, batch, height, width, levels, device):
+        f32 = torch.float32
+        self.imgs = [torch.empty((batch, 3, height, width), device=device, dtype=f32) for _ in range(3)]
+        self.ff = [torch.empty((batch, 2, height >> l, width >> l), device=device, dtype=f32) for l in range(levels)]
+        self.fb = [torch.empty((batch, 2, height >> l, width >> l), device=device, dtype=f32) for l in range(levels)]
+        self.h_loss = torch.empty((4, batch), dtype=f32).pin_memory()
+        self.h2d_done = torch.cuda.Event()
+        self.compute_done = torch.cuda.Event()
+        self.grads: List[torch.Tensor] = []
+        self.busy = False
+
+
 class FlowLossStep:
-    """Flow-mode loss step (Model_flow.forward loss body, model_flow.py:232-254) from host buffers."""
+    """Flow-mode loss step (Model_flow.forward loss body, model_flow.py:232-254) from host buffers.
+
+    Two staging slots and a copy stream: ``submit`` enqueues the H2D copy of a step on the copy stream and its
+    pyramids + fused forward/backward + D2H of the losses on the compute stream, so the copy of step k+1 overlaps
+    the kernels of step k.  ``result(slot)`` waits for that step only.  ``__call__`` = submit + result."""
 
     def __init__(self, batch: int, height: int, width: int, levels: int = 4, num_scales: Optional[int] = None,
                  weights: Optional[Dict[str, float]] = None, device="cuda:0"):
@@ -34,30 +53,52 @@ class FlowLossStep:
             raise RuntimeError("FlowLossStep needs a CUDA device: the loss path has no CPU implementation")
         self.B, self.H, self.W, self.L = batch, height, width, levels
         self.scales = levels if num_scales is None else num_scales
-        d, f32 = self.device, torch.float32
-        self.d_imgs = [torch.empty((batch, 3, height, width), device=d, dtype=f32) for _ in range(3)]
-        self.d_ff = [torch.empty((batch, 2, height >> l, width >> l), device=d, dtype=f32) for l in range(levels)]
-        self.d_fb = [torch.empty((batch, 2, height >> l, width >> l), device=d, dtype=f32) for l in range(levels)]
-        self.h_loss = torch.empty((4, batch), dtype=f32).pin_memory()
-        self.wmat = weight_matrix(weights or FLOW_WEIGHTS, ops.FLOW_LOSS_KEYS, batch, d)
-        self.h2d_bytes = sum(t.numel() * 4 for t in self.d_imgs + self.d_ff + self.d_fb)
-        self.d2h_bytes = self.h_loss.numel() * 4
-        self.grads: List[torch.Tensor] = []
+        with torch.cuda.device(self.device):
+            self.slots = [_Slot(batch, height, width, levels, self.device) for _ in range(2)]
+            self.copy_stream = torch.cuda.Stream()
+        self.wmat = weight_matrix(weights or FLOW_WEIGHTS, ops.FLOW_LOSS_KEYS, batch, self.device)
+        s0 = self.slots[0]
+        self.h2d_bytes = sum(t.numel() * 4 for t in s0.imgs + s0.ff + s0.fb)
+        self.d2h_bytes = s0.h_loss.numel() * 4
+        self._next = 0
 
-    def __call__(self, h_img_l: torch.Tensor, h_img: torch.Tensor, h_img_r: torch.Tensor, h_flows_fwd: Sequence[torch.Tensor],
-                 h_flows_bwd: Sequence[torch.Tensor], sync: bool = True) -> torch.Tensor:
-        """Host tensors in (pinned for async copies), per-sample losses (4,B) back on the host.
-        Flow gradients of d(total)/d(flow) stay on the device in ``self.grads`` (fwd levels, then bwd)."""
-        for dst, src in zip(self.d_imgs, (h_img_l, h_img, h_img_r)):
-            dst.copy_(src, non_blocking=True)
-        for dst, src in zip(self.d_ff + self.d_fb, list(h_flows_fwd) + list(h_flows_bwd)):
-            dst.copy_(src, non_blocking=True)
-        pl, pc, pr = (ops.image_pyramid(x, self.L, "box") for x in self.d_imgs)
-        ff = [f.detach().requires_grad_(True) for f in self.d_ff]   # fresh leaves over the staging buffers
-        fb = [f.detach().requires_grad_(True) for f in self.d_fb]
+    def submit(self, h_img_l: torch.Tensor, h_img: torch.Tensor, h_img_r: torch.Tensor, h_flows_fwd: Sequence[torch.Tensor],
+               h_flows_bwd: Sequence[torch.Tensor]) -> int:
+        """Enqueue one step (host tensors, pinned for truly asynchronous copies); returns the slot to pass to ``result``."""
+        idx = self._next
+        self._next ^= 1
+        sl = self.slots[idx]
+        main = torch.cuda.current_stream(self.device)
+        if sl.busy:
+            self.copy_stream.wait_event(sl.compute_done)          # the slot's previous step must have consumed its buffers
+        with torch.cuda.stream(self.copy_stream):
+            for dst, src in zip(sl.imgs, (h_img_l, h_img, h_img_r)):
+                dst.copy_(src, non_blocking=True)
+            for dst, src in zip(sl.ff + sl.fb, list(h_flows_fwd) + list(h_flows_bwd)):
+                dst.copy_(src, non_blocking=True)
+            sl.h2d_done.record(self.copy_stream)
+        main.wait_event(sl.h2d_done)
+        pl, pc, pr = (ops.image_pyramid(x, self.L, "box") for x in sl.imgs)
+        ff = [f.detach().requires_grad_(True) for f in sl.ff]       # fresh leaves over the staging buffers
+        fb = [f.detach().requires_grad_(True) for f in sl.fb]
         loss = ops.flow_loss(pl, pc, pr, ff, fb, self.scales, as_matrix=True)
-        self.grads = list(torch.autograd.grad(loss, ff[:self.scales] + fb[:self.scales], grad_outputs=self.wmat))
-        self.h_loss.copy_(loss.detach(), non_blocking=True)
-        if sync:
-            torch.cuda.current_stream().synchronize()
-        return self.h_loss
+        sl.grads = list(torch.autograd.grad(loss, ff[:self.scales] + fb[:self.scales], grad_outputs=self.wmat))
+        sl.h_loss.copy_(loss.detach(), non_blocking=True)
+        sl.compute_done.record(main)
+        sl.busy = True
+        return idx
+
+    def result(self, slot: int) -> torch.Tensor:
+        """Per-sample losses (4,B) of a submitted step on the host; d(total)/d(flow) stays on the device in
+        ``self.slots[slot].grads`` (forward levels, then backward levels)."""
+        sl = self.slots[slot]
+        sl.compute_done.synchronize()
+        return sl.h_loss
+
+    @property
+    def grads(self) -> List[torch.Tensor]:
+        return self.slots[self._next ^ 1].grads
+
+    def __call__(self, h_img_l, h_img, h_img_r, h_flows_fwd, h_flows_bwd, sync: bool = True) -> torch.Tensor:
+        slot = self.submit(h_img_l, h_img, h_img_r, h_flows_fwd, h_flows_bwd)
+        return self.result(slot) if sync else self.slots[slot].h_loss
