@@ -138,6 +138,52 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_mode_workload(args, rank, world, local):
+    """Extra measurement (not the driver's line): the depth- / geom-mode loss bodies (BASELINE configs[2] / [3]) as
+    composed from the per-method kernels under autograd, eager launches, 256x832, batch 8 per GPU, S=3."""
+    from unsupervised_depth_opticalflow_egomotion_b200 import losses, ops
+    from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, S = args.batch, 3
+    t = make_triplet(B, H, W, 4, S, seed=1234 + rank, flow_mode="rigid").to(dev)
+    leaves = [x.requires_grad_(True) for x in t.flows_fwd + t.flows_bwd + t.disp + t.disp_l + t.disp_r + [t.pose]]
+    weights = {"loss_flow_pixel": 0.15, "loss_flow_ssim": 0.85, "loss_flow_smooth": 10.0, "loss_flow_consis": 0.01, "loss_depth_pixel": 1.0,
+               "loss_depth_ssim": 0.85, "loss_depth_smooth": 0.5, "loss_depth_consis": 0.1, "loss_depth_flow_consis": 1.0, "loss_epipolar": 0.1,
+               "loss_triangle": 0.001, "loss_pnp": 0.1, "loss_eight_point": 0.1}
+    if args.workload == "geom":
+        mod = losses.GeometryLoss(S)
+        fwd = lambda: mod.forward_losses(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd, t.disp, t.disp_l, t.disp_r, t.pose, t.K, t.K_inv)[0]
+    else:
+        mod = losses.DepthLoss(S, "texture")
+        fwd = lambda: mod.forward_losses(t.img_l, t.img, t.img_r, t.disp, t.disp_l, t.disp_r, t.pose, t.K)[0]
+
+    def step():
+        for x in leaves:
+            x.grad = None
+        loss = fwd()
+        sum(weights[k] * v.mean() for k, v in loss.items()).backward()
+
+    n0 = ops.LAUNCH_COUNTER["n"]
+    step()
+    launches = ops.LAUNCH_COUNTER["n"] - n0
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": 2.0 * B * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "ms_per_step": ms, "dtype": "f32", "data": "synthetic", "gpu_launches": launches * args.steps,
+                          "config": {"workload": "%s-mode loss body fwd+bwd (per-method kernels composed under autograd, eager), 256x832, "
+                                                 "batch %d per GPU, S=3" % (args.workload, B)}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,6 +193,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="samples per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="flow", choices=["flow", "depth", "geom"],
+                    help="flow = BASELINE configs[1] (the driver's line); depth / geom = configs[2] / [3] loss bodies (extra, eager)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -155,6 +203,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload != "flow":
+        run_mode_workload(args, rank, world, local)
         return
 
     import torch.distributed as dist

@@ -1,0 +1,20 @@
+import sys, torch
+sys.path.insert(0, ".")
+from unsupervised_depth_opticalflow_egomotion_b200 import ops, losses
+from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
+dev = torch.device("cuda:0")
+t = make_triplet(2, 40, 72, 4, 3, seed=3, flow_mode="rigid", oob_fraction=0.1).to(dev)
+for mode in ("single_pass", "recompute"):
+    pl, pc, pr = (ops.image_pyramid(x, 4, "box") for x in (t.img_l, t.img, t.img_r))
+    ff = [f.detach().requires_grad_(True) for f in t.flows_fwd]; fb = [f.detach().requires_grad_(True) for f in t.flows_bwd]
+    loss = ops.flow_loss(pl, pc, pr, ff, fb, 4, as_matrix=True, mode=mode)
+    g = torch.autograd.grad(loss.sum(), ff + fb)
+leaves = [x.detach().requires_grad_(True) for x in t.flows_fwd + t.flows_bwd + t.disp + t.disp_l + t.disp_r + [t.pose]]
+ff, fb, d, dl, dr, pose = leaves[0:4], leaves[4:8], leaves[8:11], leaves[11:14], leaves[14:17], leaves[17]
+loss, _ = losses.GeometryLoss(3).forward_losses(t.img_l, t.img, t.img_r, ff, fb, d, dl, dr, pose, t.K, t.K_inv)
+sum(v.mean() for v in loss.values()).backward()
+loss, _ = losses.DepthLoss(3, "texture").forward_losses(t.img_l, t.img, t.img_r, d, dl, dr, pose, t.K)
+sum(v.mean() for v in loss.values()).backward()
+x = torch.rand(1, 8, 20, 30, device=dev, requires_grad=True); fl = (3 * torch.randn(1, 2, 20, 30, device=dev)).requires_grad_(True)
+ops.warp_flow(x, fl, True).sum().backward()
+torch.cuda.synchronize(); print("sanitizer workload done")
