@@ -138,6 +138,38 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_torch_cuda(args, rank, local):
+    """Extra comparator: the reference's op sequence (oracle port = F.grid_sample / avg_pool2d / softmax ... under autograd)
+    executed by stock PyTorch on the same B200, same workload and batch as the driver's line, eager launches."""
+    if rank != 0:
+        return
+    from oracle import loss_port as P
+    from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    t = make_triplet(args.batch, H, W, LEVELS, 1, seed=1234, flow_px=10.0).to(dev)
+    flows = [f.requires_grad_(True) for f in t.flows_fwd + t.flows_bwd]
+
+    def step():
+        loss = P.flow_mode_loss(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd, LEVELS)
+        total = sum(P.FLOW_WEIGHTS[k] * loss[k].mean() for k in loss)
+        return torch.autograd.grad(total, flows)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"impl": "torch-cuda", "metric": METRIC, "value": 2.0 * args.batch / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+                      "steps": args.steps, "ms_per_step": ms, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "launch": "eager (stock PyTorch ops, autograd)"}}), flush=True)
+
+
 def run_mode_workload(args, rank, world, local):
     """Extra measurement (not the driver's line): the depth- / geom-mode loss bodies (BASELINE configs[2] / [3]) as
     composed from the per-method kernels under autograd, eager launches, 256x832, batch 8 per GPU, S=3."""
@@ -209,7 +241,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch-cuda"],
+                    help="reference = the reference's CPU loss path (oracle port); torch-cuda = the same torch op sequence on the GPU "
+                         "(extra comparator: 'stock PyTorch on B200', SURVEY 8(d))")
     ap.add_argument("--batch", type=int, default=BATCH, help="samples per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -223,6 +257,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.impl == "torch-cuda":
+        run_torch_cuda(args, rank, local)
         return
     if args.workload != "flow":
         run_mode_workload(args, rank, world, local)

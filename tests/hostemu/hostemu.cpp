@@ -127,7 +127,8 @@ extern "C" int emu_flow_loss_forward_grad(const UglFlowLossArgs* a) {
       Tile::phase2(gp, tc, dir, 0, 1, sm.data(), acc);
       Tile::phase3(gp, tc, dir, 0, 1, sm.data());
     }
-    Tile::phase4(gp, tc, 0, 1, sm.data(), acc);
+    Tile::phase4a(gp, tc, 0, 1, sm.data(), acc);
+    Tile::phase4b(gp, tc, 0, 1, sm.data());
     for (int k = 0; k < FA_COUNT; ++k) partials[(size_t)tile * FA_COUNT + k] = acc[k];
   }
   emu_finalize(gp.base, partials);

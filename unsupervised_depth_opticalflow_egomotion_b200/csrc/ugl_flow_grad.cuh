@@ -330,8 +330,34 @@ struct FlowGradTile {
     }
   }
 
-  // phase 4: smoothness value + basis for the interior pixels
-  static UGL_HD void phase4(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, const float* sm, float* acc) {
+  // phase 4a: every centre of the halo-1 region computes its signed, edge-weighted second differences ONCE
+  // (s = w * sign(d2 f) per flow component and axis, 8 planes written over the no longer needed coefficient planes);
+  // interior centres also add the smoothness loss value.  phase 4b then gathers 3 taps per axis instead of re-deriving
+  // the second differences of its neighbours.
+  static UGL_HD void phase4a(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, float* sm, float* acc) {
+    const FlowLevelDesc& L = gp.base.lv[tc.level];
+    for (int idx = tid; idx < CN; idx += nt) {
+      const int ly = idx / CW, lx = idx - ly * CW;
+      const int c0 = (ly + 1) * PW + (lx + 1);
+      const float wx = sm[kOffEdge + idx], wy = sm[kOffEdge + CN + idx];      // zero where the centre does not exist
+      const bool interior = (ly >= 1 && ly <= TH && lx >= 1 && lx <= TW) && (tc.y0 + ly - 1 < L.h) && (tc.x0 + lx - 1 < L.w);
+#pragma unroll
+      for (int f4 = 0; f4 < 4; ++f4) {
+        const float* f = sm + (PL_UF + f4) * PN + c0;
+        // the edge weight is 0 for centres whose neighbours fall outside the image, so the reads below stay inside the
+        // halo-2 planes and contribute nothing there
+        const float dxx = second_diff(f, 1), dyy = second_diff(f, PW);
+        sm[kOffCoef + (2 * f4) * CN + idx] = wx * sgnf(dxx);
+        sm[kOffCoef + (2 * f4 + 1) * CN + idx] = wy * sgnf(dyy);
+        if (interior) {
+          acc[f4 < 2 ? FA_SMX_F : FA_SMX_B] += wx * fabsf(dxx);
+          acc[f4 < 2 ? FA_SMY_F : FA_SMY_B] += wy * fabsf(dyy);
+        }
+      }
+    }
+  }
+
+  static UGL_HD void phase4b(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, const float* sm) {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     const int plane = L.h * L.w;
     float* basis = gp.basis[tc.level] + (long)tc.b * kBasisPlanes * plane;
@@ -340,23 +366,13 @@ struct FlowGradTile {
       const int ty = idx / TW, tx = idx - ty * TW;
       const int i = tc.y0 + ty, j = tc.x0 + tx;
       if (i >= L.h || j >= L.w) continue;
-      const int c0 = (ty + R) * PW + (tx + R);
       const int q0 = (ty + 1) * CW + (tx + 1);
-      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      float g[4];
 #pragma unroll
-      for (int t = -1; t <= 1; ++t) {
-        const float coef = (t == 0) ? -2.0f : 1.0f;
-        const float wx = sm[kOffEdge + q0 + t], wy = sm[kOffEdge + CN + q0 + t * CW];   // zero where the centre does not exist
-#pragma unroll
-        for (int f4 = 0; f4 < 4; ++f4) {
-          const float* f = sm + (PL_UF + f4) * PN + c0;
-          const float dxx = second_diff(f + t, 1), dyy = second_diff(f + t * PW, PW);
-          g[f4] += coef * (wx * inx * sgnf(dxx) + wy * iny * sgnf(dyy));
-          if (t == 0) {
-            acc[f4 < 2 ? FA_SMX_F : FA_SMX_B] += wx * fabsf(dxx);
-            acc[f4 < 2 ? FA_SMY_F : FA_SMY_B] += wy * fabsf(dyy);
-          }
-        }
+      for (int f4 = 0; f4 < 4; ++f4) {
+        const float* sx = sm + kOffCoef + (2 * f4) * CN + q0;
+        const float* sy = sm + kOffCoef + (2 * f4 + 1) * CN + q0;
+        g[f4] = (sx[-1] - 2.0f * sx[0] + sx[1]) * inx + (sy[-CW] - 2.0f * sy[0] + sy[CW]) * iny;
       }
       const int pix = i * L.w + j;
       basis[4 * plane + pix] = g[0]; basis[5 * plane + pix] = g[1];

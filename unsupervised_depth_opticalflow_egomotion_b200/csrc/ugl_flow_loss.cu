@@ -133,9 +133,11 @@ __global__ void __launch_bounds__(NT, UGL_BMINB) flow_loss_fwdgrad_kernel(const 
     Tile::phase2(gp, tc, dir, threadIdx.x, NT, sm, acc);
     __syncthreads();
     Tile::phase3(gp, tc, dir, threadIdx.x, NT, sm);
-    if (dir == 0) __syncthreads();   // the coefficient planes are reused by the second direction
+    __syncthreads();                 // the coefficient planes are reused by the second direction / by phase 4
   }
-  Tile::phase4(gp, tc, threadIdx.x, NT, sm, acc);
+  Tile::phase4a(gp, tc, threadIdx.x, NT, sm, acc);
+  __syncthreads();
+  Tile::phase4b(gp, tc, threadIdx.x, NT, sm);
   const float v = block_reduce_n<NT, FA_COUNT>(acc, red);
   if (threadIdx.x < FA_COUNT) gp.base.partials[(long)tile * FA_COUNT + threadIdx.x] = v;
 }
