@@ -21,14 +21,17 @@ namespace ugl {
 
 constexpr int kBasisPlanes = 14;
 
-// ---- unconditional clamped gather ---------------------------------------------------------------------------
-// Same numbers as tap_fetch/corners_value (out-of-range corners contribute an exact +0), but the four loads are
-// unconditional (clamped addresses) and the in-bounds tests are folded into the weights once per tap instead of
-// once per channel.
+// ---- unconditional clamped 2x2 gather ----------------------------------------------------------------------------
+// Bilinear weights and the in-bounds tests are separable (w_nw = ox*oy, mask = [x0 in range]*[y0 in range]).  The kernel
+// always loads the in-image 2x2 block at columns (xa, xa+1), rows (ya, ya+1) with xa = clamp(x0, 0, W-2), ya likewise, so
+// the three neighbours are fixed offsets (+1, +W, +W+1) of ONE address per channel, and folds "which of my two columns is
+// x0 / x0+1, if any" into per-column weights cw[2] (rows: rw[2]).  The products cw*rw are exactly the ATen weights
+// (ox*oy etc.) or exact zeros, accumulated in ATen's nw, ne, sw, se order, so the sampled value is bit-identical to
+// tap_fetch/corners_value; out-of-range corners contribute an exact +0.
 struct TapC {
-  int o00, o01, o10, o11;     // clamped plane offsets of nw, ne, sw, se
-  float w[4];                 // masked weights
-  float dx[4], dy[4];         // masked d w / d ix, d w / d iy
+  int off;                    // ya * W + xa
+  float w[4];                 // nw, ne, sw, se weights of the loaded block
+  float dx[4], dy[4];         // d w / d ix, d w / d iy
   float keep;
 };
 
@@ -43,39 +46,71 @@ UGL_HD TapC flow_tap_clamped(int j, int i, float u, float v, const WarpGeom& g) 
   const int x0 = (int)fx, y0 = (int)fy;
   const float tx = ix - fx, ty = iy - fy;
   const float ox = (fx + 1.0f) - ix, oy = (fy + 1.0f) - iy;
-  const float ml = (x0 >= 0 && x0 < g.W) ? 1.f : 0.f, mr = (x0 + 1 >= 0 && x0 + 1 < g.W) ? 1.f : 0.f;
-  const float mt = (y0 >= 0 && y0 < g.H) ? 1.f : 0.f, mb = (y0 + 1 >= 0 && y0 + 1 < g.H) ? 1.f : 0.f;
-  const float m00 = ml * mt, m01 = mr * mt, m10 = ml * mb, m11 = mr * mb;
+  const int xa = imin(imax(x0, 0), g.W - 2), ya = imin(imax(y0, 0), g.H - 2);
+  // column xa holds x0 (weight ox) or x0+1 (weight tx) or neither; column xa+1 likewise
+  const float l0 = (x0 == xa) ? 1.f : 0.f, r0 = (x0 + 1 == xa) ? 1.f : 0.f;
+  const float l1 = (x0 == xa + 1) ? 1.f : 0.f, r1 = (x0 == xa) ? 1.f : 0.f;
+  const float t0 = (y0 == ya) ? 1.f : 0.f, b0 = (y0 + 1 == ya) ? 1.f : 0.f;
+  const float t1 = (y0 == ya + 1) ? 1.f : 0.f, b1 = (y0 == ya) ? 1.f : 0.f;
+  // per-corner weights as ATen forms them: (x-part) * (y-part); exactly one of the two terms of a part is non-zero
+  const float cx0 = ox * l0 + tx * r0, cx1 = ox * l1 + tx * r1;
+  const float ry0 = oy * t0 + ty * b0, ry1 = oy * t1 + ty * b1;
   TapC t;
-  t.w[0] = (ox * oy) * m00; t.w[1] = (tx * oy) * m01; t.w[2] = (ox * ty) * m10; t.w[3] = (tx * ty) * m11;
-  const int xa = imin(imax(x0, 0), g.W - 1), xb = imin(imax(x0 + 1, 0), g.W - 1);
-  const int ya = imin(imax(y0, 0), g.H - 1) * g.W, yb = imin(imax(y0 + 1, 0), g.H - 1) * g.W;
-  t.o00 = ya + xa; t.o01 = ya + xb; t.o10 = yb + xa; t.o11 = yb + xb;
-  t.keep = add_rn(add_rn(add_rn(t.w[0], t.w[1]), t.w[2]), t.w[3]) >= 0.9999f ? 1.0f : 0.0f;
+  t.off = ya * g.W + xa;
+  t.w[0] = cx0 * ry0; t.w[1] = cx1 * ry0; t.w[2] = cx0 * ry1; t.w[3] = cx1 * ry1;
+  // coverage = sum of the in-bounds weights in ATen's corner order (nw, ne, sw, se of the ORIGINAL footprint): the
+  // original corners map to block positions in the same relative order, zeros are exact
+  const float wnw = (ox * oy) * ((x0 >= 0 && x0 < g.W && y0 >= 0 && y0 < g.H) ? 1.f : 0.f);
+  const float wne = (tx * oy) * ((x0 + 1 >= 0 && x0 + 1 < g.W && y0 >= 0 && y0 < g.H) ? 1.f : 0.f);
+  const float wsw = (ox * ty) * ((x0 >= 0 && x0 < g.W && y0 + 1 >= 0 && y0 + 1 < g.H) ? 1.f : 0.f);
+  const float wse = (tx * ty) * ((x0 + 1 >= 0 && x0 + 1 < g.W && y0 + 1 >= 0 && y0 + 1 < g.H) ? 1.f : 0.f);
+  t.keep = add_rn(add_rn(add_rn(wnw, wne), wsw), wse) >= 0.9999f ? 1.0f : 0.0f;
   if (kGrad) {
-    const float uy = 1.0f - ty, ux = 1.0f - tx;
-    t.dx[0] = -uy * m00; t.dx[1] = uy * m01; t.dx[2] = -ty * m10; t.dx[3] = ty * m11;
-    t.dy[0] = -ux * m00; t.dy[1] = -tx * m01; t.dy[2] = ux * m10; t.dy[3] = tx * m11;
+    const float dcx0 = r0 - l0, dcx1 = r1 - l1;          // d cx / d ix  (d ox = -1, d tx = +1)
+    const float dry0 = b0 - t0, dry1 = b1 - t1;
+    t.dx[0] = dcx0 * ry0; t.dx[1] = dcx1 * ry0; t.dx[2] = dcx0 * ry1; t.dx[3] = dcx1 * ry1;
+    t.dy[0] = cx0 * dry0; t.dy[1] = cx1 * dry0; t.dy[2] = cx0 * dry1; t.dy[3] = cx1 * dry1;
   }
   return t;
 }
 
+struct DirectLoads { float uf, vf, ub, vb, I[3]; bool inside; };
+
+// the coalesced (non-gather) loads of one halo pixel: issued one pixel ahead of use to overlap their latency
+template <int PW, int R>
+UGL_HD DirectLoads load_direct(const FlowLevelDesc& L, const TileCoord& tc, int idx, int& i, int& j) {
+  DirectLoads d;
+  const int ly = idx / PW, lx = idx - ly * PW;
+  i = tc.y0 - R + ly; j = tc.x0 - R + lx;
+  d.inside = (i >= 0 && i < L.h && j >= 0 && j < L.w);
+  d.uf = d.vf = d.ub = d.vb = 0.f; d.I[0] = d.I[1] = d.I[2] = 0.f;
+  if (d.inside) {
+    const int plane = L.h * L.w, pix = i * L.w + j;
+    const float* ff = L.flow_f + (long)tc.b * 2 * plane;
+    const float* fb = L.flow_b + (long)tc.b * 2 * plane;
+    const float* ic = L.img + (long)tc.b * 3 * plane;
+    d.uf = ff[pix]; d.vf = ff[plane + pix];
+    d.ub = fb[pix]; d.vb = fb[plane + pix];
+    d.I[0] = ic[pix]; d.I[1] = ic[plane + pix]; d.I[2] = ic[2 * plane + pix];
+  }
+  return d;
+}
+
 template <bool kGrad>
-UGL_HD void flow_photo_pixel_c(const FlowLevelDesc& L, int b, int i, int j, float uf, float vf, float ub, float vb, Photo& P, float* dW) {
-  const int plane = L.h * L.w;
-  const int pix = i * L.w + j;
-  const float* ic = L.img + (long)b * 3 * plane;
+UGL_HD void flow_photo_pixel_c(const FlowLevelDesc& L, int b, int i, int j, const DirectLoads& d, Photo& P, float* dW) {
+  const int plane = L.h * L.w, W = L.w;
   const float* ir = L.img_r + (long)b * 3 * plane;
   const float* il = L.img_l + (long)b * 3 * plane;
-  const TapC tf = flow_tap_clamped<kGrad>(j, i, uf, vf, L.geom);
-  const TapC tb = flow_tap_clamped<kGrad>(j, i, ub, vb, L.geom);
+  const TapC tf = flow_tap_clamped<kGrad>(j, i, d.uf, d.vf, L.geom);
+  const TapC tb = flow_tap_clamped<kGrad>(j, i, d.ub, d.vb, L.geom);
+  const float* pr = ir + tf.off;
+  const float* pl = il + tb.off;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    P.I[c] = ic[c * plane + pix];
-    const float* pr = ir + c * plane;
-    const float* pl = il + c * plane;
-    const float f0 = pr[tf.o00], f1 = pr[tf.o01], f2 = pr[tf.o10], f3 = pr[tf.o11];
-    const float b0 = pl[tb.o00], b1 = pl[tb.o01], b2 = pl[tb.o10], b3 = pl[tb.o11];
+    P.I[c] = d.I[c];
+    const float f0 = pr[0], f1 = pr[1], f2 = pr[W], f3 = pr[W + 1];
+    const float b0 = pl[0], b1 = pl[1], b2 = pl[W], b3 = pl[W + 1];
+    pr += plane; pl += plane;
     float vfw = f0 * tf.w[0]; vfw += f1 * tf.w[1]; vfw += f2 * tf.w[2]; vfw += f3 * tf.w[3];
     float vbw = b0 * tb.w[0]; vbw += b1 * tb.w[1]; vbw += b2 * tb.w[2]; vbw += b3 * tb.w[3];
     P.Wf[c] = vfw * tf.keep;
@@ -125,22 +160,23 @@ struct FlowGradTile {
     const FlowLevelDesc& L = p.lv[tc.level];
     const int plane = L.h * L.w;
     float* basis = gp.basis[tc.level] + (long)tc.b * kBasisPlanes * plane;
+    int i = 0, j = 0, ni = 0, nj = 0;
+    DirectLoads cur = load_direct<PW, R>(L, tc, tid < PN ? tid : 0, i, j);
     for (int idx = tid; idx < PN; idx += nt) {
+      // software pipeline: the coalesced loads of this thread's NEXT pixel are in flight while this one is processed
+      const int nidx = idx + nt;
+      DirectLoads nxt = cur;
+      if (nidx < PN) nxt = load_direct<PW, R>(L, tc, nidx, ni, nj);
       const int ly = idx / PW, lx = idx - ly * PW;
-      const int i = tc.y0 - R + ly, j = tc.x0 - R + lx;
       Photo P;
-      float uf = 0.f, vf = 0.f, ub = 0.f, vb = 0.f;
-      if (i >= 0 && i < L.h && j >= 0 && j < L.w) {
+      const float uf = cur.uf, vf = cur.vf, ub = cur.ub, vb = cur.vb;
+      if (cur.inside) {
         const int pix = i * L.w + j;
-        const float* ff = L.flow_f + (long)tc.b * 2 * plane;
-        const float* fb = L.flow_b + (long)tc.b * 2 * plane;
-        uf = ff[pix]; vf = ff[plane + pix];
-        ub = fb[pix]; vb = fb[plane + pix];
         const bool interior = (ly >= R && ly < R + TH && lx >= R && lx < R + TW);
         // one uniform code path for interior and halo pixels (a warp straddling both would otherwise execute the
         // gradient and the non-gradient variant back to back, and the second copy doubles the I-cache footprint)
         float dW[12];
-        flow_photo_pixel_c<true>(L, tc.b, i, j, uf, vf, ub, vb, P, dW);
+        flow_photo_pixel_c<true>(L, tc.b, i, j, cur, P, dW);
         if (interior) {
           const int t = (ly - R) * TW + (lx - R);
           float* o = sm + kOffDW + t;
@@ -179,6 +215,7 @@ struct FlowGradTile {
         zero_photo(P);
       }
       store_photo_planes<PN>(sm, idx, P, uf, vf, ub, vb);
+      cur = nxt; i = ni; j = nj;
     }
   }
 
