@@ -132,6 +132,30 @@ UGL_HD void flow_photo_pixel_c(const FlowLevelDesc& L, int b, int i, int j, cons
   P.w_f = soft_occ_weight(wr) * valid_f;
 }
 
+// shared-memory planes of the single-pass kernel (halo-2 tile).  x = I*w and y = W*w are stored pre-multiplied per
+// direction so the SSIM units do not re-form them for each of their 12 taps.
+enum GradPlane { GP_I0 = 0, GP_X0 = 3, GP_Y0 = 6, /* direction d: GP_X0 + 6 d, GP_Y0 + 6 d */ GP_WF = 15, GP_WB = 16,
+                 GP_UF = 17, GP_VF, GP_UB, GP_VB, GP_COUNT };
+
+template <int PN>
+UGL_HD void store_grad_planes(float* sm, int idx, const Photo& P, float uf, float vf, float ub, float vb) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    sm[(GP_I0 + c) * PN + idx] = P.I[c];
+    sm[(GP_X0 + c) * PN + idx] = mul_rn(P.I[c], P.w_f);
+    sm[(GP_Y0 + c) * PN + idx] = mul_rn(P.Wf[c], P.w_f);
+    sm[(GP_X0 + 6 + c) * PN + idx] = mul_rn(P.I[c], P.w_b);
+    sm[(GP_Y0 + 6 + c) * PN + idx] = mul_rn(P.Wb[c], P.w_b);
+  }
+  sm[GP_WF * PN + idx] = P.w_f;
+  sm[GP_WB * PN + idx] = P.w_b;
+  constexpr float r20 = 1.0f / 20.0f;
+  sm[GP_UF * PN + idx] = div_c(uf, 20.0f, r20);
+  sm[GP_VF * PN + idx] = div_c(vf, 20.0f, r20);
+  sm[GP_UB * PN + idx] = div_c(ub, 20.0f, r20);
+  sm[GP_VB * PN + idx] = div_c(vb, 20.0f, r20);
+}
+
 struct FlowGradParams {
   FlowLossParams base;
   float* basis[kMaxLevels];   // (B, 14, h, w) per level
@@ -147,11 +171,11 @@ struct FlowGradTile {
   static constexpr int PW = TW + 2 * R, PH = TH + 2 * R, PN = PW * PH;   // photometry planes (halo 2)
   static constexpr int CW = TW + 2, CH = TH + 2, CN = CW * CH;           // coefficient / edge planes (halo 1)
   static constexpr int TN = TW * TH;
-  static constexpr int kOffCoef = PL_COUNT * PN;                          // 9 planes [c][A,B,C], current direction
+  static constexpr int kOffCoef = GP_COUNT * PN;                          // 9 planes [c][A,B,C], current direction
   static constexpr int kOffEdge = kOffCoef + 9 * CN;                      // wx, wy
   static constexpr int kOffDW = kOffEdge + 2 * CN;                        // 12 planes keep*dW/d(u,v) + 4 planes L1 sign sums
   static constexpr int kSmemFloats = kOffDW + 16 * TN;
-  static_assert(PN % 2 == 0 && CN % 2 == 0 && (PL_COUNT * PN) % 2 == 0, "planes must stay 8-byte aligned for float2 access");
+  static_assert(PN % 2 == 0 && CN % 2 == 0 && (GP_COUNT * PN) % 2 == 0, "planes must stay 8-byte aligned for float2 access");
 
   // phase 1: photometry on the halo-2 tile; interior pixels also: L1/weight/consistency sums, warp Jacobians,
   // L1 sign sums (shared memory) and the consistency basis (global)
@@ -214,7 +238,7 @@ struct FlowGradTile {
       } else {
         zero_photo(P);
       }
-      store_photo_planes<PN>(sm, idx, P, uf, vf, ub, vb);
+      store_grad_planes<PN>(sm, idx, P, uf, vf, ub, vb);
       cur = nxt; i = ni; j = nj;
     }
   }
@@ -229,8 +253,8 @@ struct FlowGradTile {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     constexpr int SW = CW / 2;                       // strips per row
     constexpr int NS = SW * CH;                      // strips per tile
-    const float* wpl = sm + (PL_WF + dir) * PN;
-    const float* ybase = sm + (PL_F0 + 3 * dir) * PN;       // PL_B0 = PL_F0 + 3
+    const float* xbase = sm + (GP_X0 + 6 * dir) * PN;
+    const float* ybase = sm + (GP_Y0 + 6 * dir) * PN;
     float ssim_sum = 0.f;
     const int units = (dir == 0 ? 4 : 3) * NS;
     for (int u = tid; u < units; u += nt) {
@@ -241,20 +265,18 @@ struct FlowGradTile {
       const bool row_in = (i >= 0 && i < L.h);
       const bool in0 = row_in && j0 >= 0 && j0 < L.w, in1 = row_in && j0 + 1 >= 0 && j0 + 1 < L.w;
       if (c < 3) {
-        const float* ipl = sm + (PL_I0 + c) * PN;
+        const float* xpl = xbase + c * PN;
         const float* ypl = ybase + c * PN;
         float x[3][4], y[3][4], xx[3][4], yy[3][4], xy[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const int o = c0 + (r - 1) * PW;
-          const float2 wa = *reinterpret_cast<const float2*>(wpl + o - 1), wb = *reinterpret_cast<const float2*>(wpl + o + 1);
-          const float2 ia = *reinterpret_cast<const float2*>(ipl + o - 1), ib = *reinterpret_cast<const float2*>(ipl + o + 1);
+          const float2 xa = *reinterpret_cast<const float2*>(xpl + o - 1), xb = *reinterpret_cast<const float2*>(xpl + o + 1);
           const float2 ya = *reinterpret_cast<const float2*>(ypl + o - 1), yb = *reinterpret_cast<const float2*>(ypl + o + 1);
-          const float wv[4] = {wa.x, wa.y, wb.x, wb.y}, iv[4] = {ia.x, ia.y, ib.x, ib.y}, yv[4] = {ya.x, ya.y, yb.x, yb.y};
+          x[r][0] = xa.x; x[r][1] = xa.y; x[r][2] = xb.x; x[r][3] = xb.y;
+          y[r][0] = ya.x; y[r][1] = ya.y; y[r][2] = yb.x; y[r][3] = yb.y;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            x[r][k] = mul_rn(iv[k], wv[k]);
-            y[r][k] = mul_rn(yv[k], wv[k]);
             xx[r][k] = mul_rn(x[r][k], x[r][k]);
             yy[r][k] = mul_rn(y[r][k], y[r][k]);
             xy[r][k] = mul_rn(x[r][k], y[r][k]);
@@ -291,13 +313,13 @@ struct FlowGradTile {
         for (int o = 0; o < 2; ++o) {
           if (o == 0 ? in0 : in1) {
             const int cc = c0 + o, j = j0 + o;
-            const float Ic[3] = {sm[PL_I0 * PN + cc], sm[PL_I1 * PN + cc], sm[PL_I2 * PN + cc]};
+            const float Ic[3] = {sm[GP_I0 * PN + cc], sm[(GP_I0 + 1) * PN + cc], sm[(GP_I0 + 2) * PN + cc]};
             if (j >= 1 && j <= L.w - 2) {
-              const float Iq[3] = {sm[PL_I0 * PN + cc + 1], sm[PL_I1 * PN + cc + 1], sm[PL_I2 * PN + cc + 1]};
+              const float Iq[3] = {sm[GP_I0 * PN + cc + 1], sm[(GP_I0 + 1) * PN + cc + 1], sm[(GP_I0 + 2) * PN + cc + 1]};
               wx[o] = edge_weight10(Ic, Iq);
             }
             if (i >= 1 && i <= L.h - 2) {
-              const float Iq[3] = {sm[PL_I0 * PN + cc + PW], sm[PL_I1 * PN + cc + PW], sm[PL_I2 * PN + cc + PW]};
+              const float Iq[3] = {sm[GP_I0 * PN + cc + PW], sm[(GP_I0 + 1) * PN + cc + PW], sm[(GP_I0 + 2) * PN + cc + PW]};
               wy[o] = edge_weight10(Ic, Iq);
             }
           }
@@ -323,7 +345,7 @@ struct FlowGradTile {
       const int c0 = (ty + R) * PW + (tx + R);       // photometry planes, left pixel
       const int q0 = (ty + 1) * CW + (tx + 1);       // coefficient planes, left pixel
       const int t0 = ty * TW + tx;
-      const float2 wq = *reinterpret_cast<const float2*>(sm + (PL_WF + dir) * PN + c0);
+      const float2 wq = *reinterpret_cast<const float2*>(sm + (GP_WF + dir) * PN + c0);
       const float wv[2] = {wq.x, wq.y};
       float gsu[2] = {0.f, 0.f}, gsv[2] = {0.f, 0.f};
 #pragma unroll 1
@@ -342,14 +364,14 @@ struct FlowGradTile {
           sum[k][0] = col[0] + col[1] + col[2];
           sum[k][1] = col[1] + col[2] + col[3];
         }
-        const float2 Iv = *reinterpret_cast<const float2*>(sm + (PL_I0 + c) * PN + c0);
-        const float2 Wv = *reinterpret_cast<const float2*>(sm + (PL_F0 + 3 * dir + c) * PN + c0);
+        const float2 Xv = *reinterpret_cast<const float2*>(sm + (GP_X0 + 6 * dir + c) * PN + c0);
+        const float2 Yv = *reinterpret_cast<const float2*>(sm + (GP_Y0 + 6 * dir + c) * PN + c0);
         const float2 du = *reinterpret_cast<const float2*>(sm + kOffDW + (6 * dir + 2 * c) * TN + t0);
         const float2 dv = *reinterpret_cast<const float2*>(sm + kOffDW + (6 * dir + 2 * c + 1) * TN + t0);
-        const float I2[2] = {Iv.x, Iv.y}, W2[2] = {Wv.x, Wv.y}, du2[2] = {du.x, du.y}, dv2[2] = {dv.x, dv.y};
+        const float X2[2] = {Xv.x, Xv.y}, Y2[2] = {Yv.x, Yv.y}, du2[2] = {du.x, du.y}, dv2[2] = {dv.x, dv.y};
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
-          const float gW = (sum[0][o] + 2.0f * (W2[o] * wv[o]) * sum[1][o] + (I2[o] * wv[o]) * sum[2][o]) * wv[o];
+          const float gW = (sum[0][o] + 2.0f * Y2[o] * sum[1][o] + X2[o] * sum[2][o]) * wv[o];
           gsu[o] += gW * du2[o];
           gsv[o] += gW * dv2[o];
         }
@@ -380,7 +402,7 @@ struct FlowGradTile {
       const bool interior = (ly >= 1 && ly <= TH && lx >= 1 && lx <= TW) && (tc.y0 + ly - 1 < L.h) && (tc.x0 + lx - 1 < L.w);
 #pragma unroll
       for (int f4 = 0; f4 < 4; ++f4) {
-        const float* f = sm + (PL_UF + f4) * PN + c0;
+        const float* f = sm + (GP_UF + f4) * PN + c0;
         // the edge weight is 0 for centres whose neighbours fall outside the image, so the reads below stay inside the
         // halo-2 planes and contribute nothing there
         const float dxx = second_diff(f, 1), dyy = second_diff(f, PW);
