@@ -53,49 +53,82 @@ def algorithmic_bytes(batch: int, fwd: bool, bwd: bool) -> int:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled WHILE the timed region runs: in-process NVML polling on a background thread
+    (every ~2 ms; the timed region is only tens of milliseconds, shorter than nvidia-smi's start-up), nvidia-smi as fallback."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, cuda_index: int):
+        self.cuda_index, self.samples, self.mask, self.max_mhz = cuda_index, [], 0, None
+        self._stop = threading.Event()
+        self._thread, self._proc, self._nvml = None, None, None
+
+    def _handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        self._nvml = pynvml
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.cuda_index).uuid)
+            return pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.cuda_index]) if vis and vis.split(",")[self.cuda_index].isdigit() else self.cuda_index
+            return pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll(self, h):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                except Exception:
+                    pass
+            time.sleep(0.002)
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            h = self._handle()
+            self.max_mhz = float(self._nvml.nvmlDeviceGetMaxClockInfo(h, self._nvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, args=(h,), daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._thread = None
+            try:
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.cuda_index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                               "-lms", "20"], stdout=subprocess.PIPE, text=True)
+                self._thread = threading.Thread(target=self._read_smi, daemon=True)
+                self._thread.start()
+            except Exception:
+                self._proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def __exit__(self, *a):
-        if self.proc:
-            self.proc.terminate()
+    def _read_smi(self):
+        for line in self._proc.stdout:
+            c = [x.strip() for x in line.split(",")]
             try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-
-    def summary(self):
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = float(r[1])
+                self.samples.append(float(c[0])); self.max_mhz = float(c[1])
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            for (name, bit), v in zip(self.REASONS, c[2:6]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        busy = [c for c in sm if c >= 0.5 * max(sm)]
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+                    self.mask |= bit
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._proc:
+            self._proc.terminate()
+        if self._thread:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        busy = [c for c in self.samples if c >= 0.5 * max(self.samples)]
+        return {"sm_mhz": float(statistics.median(busy)), "sm_max_mhz": self.max_mhz, "samples": len(self.samples),
+                "reasons": [name for name, bit in self.REASONS if self.mask & bit]}
 
 
 def cpu_reference_rate(sample_batch: int, steps: int, warmup: int, threads: int):

@@ -107,6 +107,14 @@ int ugl_warp_flow_backward(const float* x, const float* flow, const float* grad_
 uint64_t ugl_warp_flow_backward_workspace_bytes(int32_t batch, int32_t channels, int32_t height, int32_t width,
                                                 int32_t need_grad_x);
 
+/* EXTENSION — forward splat (`transformerFwd`): Model_flow.get_occlusion_mask_from_flow (model_flow.py:33-39) calls it but
+ * the reference never defines it (dead code; upstream TrianFlow semantics, parity unpinned).  out[b,c,y',x'] accumulates
+ * x[b,c,i,j] * bilinear weight over the four integer neighbours of (j+u, i+v); out-of-range corners are dropped;
+ * clamp01 != 0 applies clamp(., 0, 1) (:37-38).  Deterministic.  Not differentiable. */
+uint64_t ugl_forward_splat_workspace_bytes(int32_t batch, int32_t channels, int32_t height, int32_t width);
+int ugl_forward_splat(const float* x, const float* flow, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                      int32_t clamp01, float* out, void* workspace, uint64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Generic per-sample reductions: workspace for every *_forward / *_backward below that takes one
  * (>= ugl_reduce_workspace_bytes(B,H,W) bytes, 8-byte aligned).

@@ -137,6 +137,26 @@ def ssim_map(x: Tensor, y: Tensor, restated: bool = False) -> Tensor:
     return num / den
 
 
+def forward_splat(x: Tensor, flow: Tensor) -> Tensor:
+    """EXTENSION oracle (parity unpinned: ``transformerFwd`` is called at model_flow.py:36 but defined nowhere in the
+    reference; semantics of upstream TrianFlow): every source pixel adds x * bilinear weight to the four integer
+    neighbours of (j+u, i+v); corners outside the image are dropped.  Accumulated in fp64."""
+    B, C, H, W = x.shape
+    tgt = _pixel_grid(B, H, W, flow) + flow
+    tx, ty = tgt[:, 0], tgt[:, 1]
+    x0, y0 = torch.floor(tx), torch.floor(ty)
+    out = torch.zeros(B, C, H * W, dtype=torch.float64)
+    for dx, dy in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        xc, yc = x0 + dx, y0 + dy
+        wx = (x0 + 1 - tx) if dx == 0 else (tx - x0)
+        wy = (y0 + 1 - ty) if dy == 0 else (ty - y0)
+        inside = (xc >= 0) & (xc <= W - 1) & (yc >= 0) & (yc <= H - 1)
+        idx = (yc.clamp(0, H - 1) * W + xc.clamp(0, W - 1)).long().reshape(B, 1, -1).expand(B, C, -1)
+        val = (x * (wx * wy * inside.to(x.dtype)).unsqueeze(1)).reshape(B, C, -1).double()
+        out.scatter_add_(2, idx, val)
+    return out.reshape(B, C, H, W).to(x.dtype)
+
+
 # ----------------------------------------------------------------------------------------------
 # pyramids
 # ----------------------------------------------------------------------------------------------

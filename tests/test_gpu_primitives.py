@@ -54,3 +54,23 @@ def test_image_pyramid_bit_exact(cuda_device, mode):
             assert (out[l].cpu() - ref[l]).abs().max() <= 1.2e-7, l
     with pytest.raises(ValueError):
         ops.image_pyramid(torch.rand(1, 3, 30, 64, device=cuda_device), 4, mode)
+
+
+def test_forward_splat_extension(cuda_device):
+    """`transformerFwd` is undefined in the reference (dead code): independent CPU oracle + known answers."""
+    from unsupervised_depth_opticalflow_egomotion_b200 import losses
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(2, 3, 24, 40, generator=g)
+    flow = 4.0 * torch.randn(2, 2, 24, 40, generator=g)
+    ref = P.forward_splat(x, flow)
+    out = ops.forward_splat(x.to(cuda_device), flow.to(cuda_device))
+    assert rel_err(out, ref) < 1e-5
+    assert torch.equal(out, ops.forward_splat(x.to(cuda_device), flow.to(cuda_device)))          # deterministic
+    zero = torch.zeros(2, 2, 24, 40, device=cuda_device)
+    assert torch.allclose(ops.forward_splat(x.to(cuda_device), zero), x.to(cuda_device), atol=1e-6)   # zero flow = identity
+    shift = zero.clone(); shift[:, 0] = 3.0                                                            # integer shift
+    moved = ops.forward_splat(x.to(cuda_device), shift).cpu()
+    assert torch.allclose(moved[..., 3:], x[..., :-3], atol=1e-6) and moved[..., :3].abs().max() == 0
+    occ = losses.FlowLoss(1).get_occlusion_mask_from_flow((2, 1, 24, 40), flow.to(cuda_device))
+    assert occ.shape == (2, 1, 24, 40) and float(occ.min()) >= 0.0 and float(occ.max()) <= 1.0
+    assert rel_err(occ, P.forward_splat(torch.ones(2, 1, 24, 40), flow).clamp(0, 1)) < 1e-5

@@ -68,6 +68,8 @@ _i, _u64, _p, _f, _i64 = C.c_int32, C.c_uint64, C.c_void_p, C.c_float, C.c_int64
 _pp = C.POINTER(C.c_void_p)
 _ip = C.POINTER(C.c_int32)
 SIGNATURES.update({
+    "ugl_forward_splat_workspace_bytes": (_u64, [_i, _i, _i, _i]),
+    "ugl_forward_splat": (C.c_int, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _u64, _p]),
     "ugl_reduce_workspace_bytes": (_u64, [_i, _i, _i]),
     "ugl_masked_mean_forward": (C.c_int, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _u64, _p]),
     "ugl_masked_mean_backward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),

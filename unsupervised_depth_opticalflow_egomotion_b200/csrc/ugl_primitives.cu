@@ -68,6 +68,38 @@ warp_bwd_scatter_kernel(const float* __restrict__ flow, const float* __restrict_
   }
 }
 
+// EXTENSION (parity unpinned): forward splat = the `transformerFwd` that Model_flow.get_occlusion_mask_from_flow
+// (model_flow.py:33-39) calls but the reference never defines.  Semantics of upstream TrianFlow: every source pixel (j,i)
+// adds x[b,c,i,j] * bilinear weight to the four integer neighbours of (j+u, i+v) in pixel units; corners outside the image
+// are dropped.  Deterministic (64-bit fixed-point accumulation, order independent).
+__global__ void __launch_bounds__(kPrimThreads)
+splat_scatter_kernel(const float* __restrict__ x, const float* __restrict__ flow, int B, int C, int H, int W,
+                     const unsigned* __restrict__ maxbits, unsigned long long* __restrict__ acc) {
+  const long n = (long)B * H * W, plane = (long)H * W;
+  const int e = fixed_point_exponent(__uint_as_float(*maxbits), plane);
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % W);
+    const long r = idx / W;
+    const int i = (int)(r % H), b = (int)(r / H);
+    const long pix = (long)i * W + j;
+    const float tx = add_rn((float)j, flow[((long)b * 2) * plane + pix]), ty = add_rn((float)i, flow[((long)b * 2 + 1) * plane + pix]);
+    const Tap t = make_tap(tx, ty, W, H);
+    if (t.inb == 0u) continue;
+    for (int c = 0; c < C; ++c) scatter_tap(acc + ((long)b * C + c) * plane, W, t, x[((long)b * C + c) * plane + pix], e);
+  }
+}
+
+__global__ void __launch_bounds__(kPrimThreads)
+fixed_to_float_clamp_kernel(const unsigned long long* __restrict__ acc, long n, long n_contrib, const unsigned* __restrict__ maxbits,
+                            int clamp01, float* __restrict__ out) {
+  const int e = fixed_point_exponent(__uint_as_float(*maxbits), n_contrib);
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    float v = (float)ldexp((double)(long long)acc[idx], -e);
+    if (clamp01) v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+    out[idx] = v;
+  }
+}
+
 static int grid_for(long n) {
   long g = (n + kPrimThreads - 1) / kPrimThreads;
   const long cap = 148L * 16;   // 148 SMs x a few resident CTAs, grid-stride beyond that
@@ -139,4 +171,30 @@ extern "C" int ugl_warp_flow_backward(const float* x, const float* flow, const f
     if ((rc = check_launch("fixed_to_float_kernel"))) return rc;
   }
   return UGL_OK;
+}
+
+extern "C" uint64_t ugl_forward_splat_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
+  return (uint64_t)B * C * H * W * sizeof(unsigned long long) + 256;
+}
+
+extern "C" int ugl_forward_splat(const float* x, const float* flow, int32_t B, int32_t C, int32_t H, int32_t W, int32_t clamp01,
+                                 float* out, void* workspace, uint64_t workspace_bytes, void* stream) {
+  if (!x || !flow || !out) return fail(UGL_EINVAL, "forward_splat: null pointer");
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(UGL_EINVAL, "forward_splat: bad shape");
+  const uint64_t need = ugl_forward_splat_workspace_bytes(B, C, H, W);
+  if (!workspace || workspace_bytes < need) return fail(UGL_EWORKSPACE, "forward_splat: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 7u) return fail(UGL_EALIGN, "forward_splat: workspace not 8-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long nx = (long)B * C * H * W, n = (long)B * H * W;
+  unsigned long long* acc = static_cast<unsigned long long*>(workspace);
+  unsigned* maxbits = reinterpret_cast<unsigned*>(acc + nx);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
+  if (e != cudaSuccess) return fail((int)e, "forward_splat: memset: %s", cudaGetErrorString(e));
+  int rc;
+  absmax_kernel<<<grid_for(nx), kPrimThreads, 0, st>>>(x, nx, maxbits);
+  if ((rc = check_launch("absmax_kernel"))) return rc;
+  splat_scatter_kernel<<<grid_for(n), kPrimThreads, 0, st>>>(x, flow, B, C, H, W, maxbits, acc);
+  if ((rc = check_launch("splat_scatter_kernel"))) return rc;
+  fixed_to_float_clamp_kernel<<<grid_for(nx), kPrimThreads, 0, st>>>(acc, nx, (long)H * W, maxbits, clamp01, out);
+  return check_launch("fixed_to_float_clamp_kernel");
 }

@@ -98,6 +98,12 @@ class FlowLoss(_LossBase):
         """model_flow.py:58-64 (adaptive average pooling, detached)"""
         return ops.image_pyramid(img, num_pyramid, "box")
 
+    def get_occlusion_mask_from_flow(self, tensor_size, flow):
+        """model_flow.py:33-39 — EXTENSION: the reference calls an undefined ``transformerFwd`` here (dead code); this is the
+        upstream TrianFlow forward splat of a ones map, clamped to [0,1]."""
+        ones = torch.ones(tuple(tensor_size), device=flow.device, dtype=torch.float32)
+        return ops.forward_splat(ones, flow, clamp01=True)
+
     def compute_diff_weight(self, img_pyramid_from_l, img_pyramid, img_pyramid_from_r):
         """model_flow.py:105-138 -> (diff_bwd, diff_fwd, weight_bwd, weight_fwd)"""
         out = [ops.occlusion_weights(img_pyramid_from_l[s], img_pyramid[s], img_pyramid_from_r[s], soft=True)

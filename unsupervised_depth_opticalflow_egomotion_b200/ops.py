@@ -715,3 +715,19 @@ class _EpipolarFn(torch.autograd.Function):
 def epipolar_distance(flow: Tensor, Fm: Tensor) -> Tensor:
     """Core of ``compute_epipolar_map`` (model_geometry.py:381-391) given the fundamental matrix F (B,3,3)."""
     return _EpipolarFn.apply(flow, Fm)
+
+
+def forward_splat(x: Tensor, flow: Tensor, clamp01: bool = False) -> Tensor:
+    """EXTENSION — ``transformerFwd`` (undefined in the reference, model_flow.py:36): forward-splat ``x`` (B,C,H,W) by ``flow``
+    (B,2,H,W, pixels) with bilinear weights, out-of-range corners dropped.  Constant for autograd, deterministic."""
+    x, flow = _dev(x, "x").detach(), _dev(flow, "flow").detach()
+    B, Cc, H, W = x.shape
+    if tuple(flow.shape) != (B, 2, H, W):
+        raise ValueError("forward_splat: flow must be (B,2,H,W), got %s" % (tuple(flow.shape),))
+    out = torch.empty_like(x)
+    n = int(_cabi.lib().ugl_forward_splat_workspace_bytes(B, Cc, H, W))
+    ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=x.device)
+    with torch.cuda.device_of(x):
+        _call("ugl_forward_splat", x.data_ptr(), flow.data_ptr(), B, Cc, H, W, int(clamp01), out.data_ptr(), ws.data_ptr(), _nbytes(ws),
+              _stream_ptr(), launches=3)
+    return out
