@@ -88,6 +88,20 @@ def test_full_size_b1_vs_oracle(cuda_device):
         _assert_grad("bwd%d" % l, gb[l], rb[l], rb64[l])
 
 
+def test_high_res_b1_vs_oracle(cuda_device):
+    """BASELINE config 5 resolution (384x1280), batch 1, 4 levels."""
+    t = make_triplet(1, 384, 1280, 4, 1, seed=4321, flow_px=12.0, oob_fraction=0.02)
+    gl = torch.tensor([[0.15], [0.85], [10.0], [0.01]])
+    loss, gf, gb = _cuda_flow(t, 4, gl, cuda_device)
+    ref, rf, rb = _oracle_flow(t, 4, gl)
+    _, rf64, rb64 = _oracle_flow(t, 4, gl, torch.float64)
+    for k in range(4):
+        assert loss_rel_err(loss[k], ref[KEYS[k]]) < LOSS_RTOL, KEYS[k]
+    for l in range(4):
+        _assert_grad("fwd%d" % l, gf[l], rf[l], rf64[l])
+        _assert_grad("bwd%d" % l, gb[l], rb[l], rb64[l])
+
+
 def test_full_size_properties(cuda_device):
     """BASELINE config 2 shape (256x832, batch 8): determinism, batch-shard invariance, linearity of the
     backward pass in the upstream gradient, zero gradient for unused levels."""

@@ -227,7 +227,7 @@ def test_geom_mode_vs_reference_golden(cuda_device):
     assert loss["loss_pnp"].shape == torch.Size([2])
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 64, 208), (1, 128, 416)])
+@pytest.mark.parametrize("B,H,W", [(2, 64, 208), (1, 128, 416), (1, 256, 832)])
 def test_geom_mode_vs_oracle(cuda_device, B, H, W):
     t = make_triplet(B, H, W, 4, 3, seed=41, flow_mode="rigid")
     dev = cuda_device
@@ -261,11 +261,14 @@ def test_geom_mode_vs_oracle(cuda_device, B, H, W):
         if b is None:
             assert a is None or a.abs().max() == 0
         elif i == len(og) - 1:
-            # pose (B,2,6): a SUM over every pixel of signed, largely cancelling terms.  One bilinear-cell knife-edge pixel
-            # (K^-1 / sin / cos / matmul differ in the last ulp between the CPU oracle and the GPU) changes its term by O(1),
-            # i.e. the sum by ~1/sqrt(N): 1e-2 on these small random images.  The op-level tests against the reference's
-            # own outputs (test_inverse_warp2_and_rigid_flow_vs_reference_golden) hold the pose gradient to 1e-4.
-            assert rel_err(a, b) < 2e-2
+            # pose (B,2,6): a SUM over every pixel of signed, largely cancelling terms, dominated in its noise by the
+            # depth-flow-consistency term d|rigid_flow - flow|: wherever rf - f is within rounding of 0 the sign (an O(1)
+            # per-pixel factor) is arbitrary, and the synthetic flows are rigid flow + smooth noise, i.e. full of such zero
+            # crossings.  Measured on the B200 box at 256x832 (per-term pose gradients, relative to max): torch-CUDA vs
+            # torch-CPU 4e-3, fp32 vs fp64 oracle 3e-2, ours vs fp64 1e-2; for the depth-L1 and epipolar terms ours matches the
+            # CPU oracle to 3e-6 / 4e-5.  So: within 5e-2 of the fp32 oracle AND at least as close to fp64 as the oracle is.
+            assert rel_err(a, b) < 5e-2
+            assert rel_err(a, c) <= 1.5 * rel_err(b, c) + 1e-3
         else:
             assert_grad_close("leaf %d" % i, a, b, c, rtol=1.5 * GRAD_RTOL)
 

@@ -399,6 +399,7 @@ class _OccWeightsFn(torch.autograd.Function):
                   *[t.data_ptr() for t in o], _stream_ptr())
         ctx.save_for_backward(from_l, img, from_r)
         ctx.mark_non_differentiable(*o[:4])
+        ctx.set_materialize_grads(False)
         return tuple(o)
 
     @staticmethod
@@ -448,11 +449,14 @@ class _DynamicMaskFn(torch.autograd.Function):
                   dyn.data_ptr(), score.data_ptr(), _stream_ptr())
         ctx.save_for_backward(flow, rflow)
         ctx.mark_non_differentiable(dyn, score)
+        ctx.set_materialize_grads(False)
         return fd, dyn, score
 
     @staticmethod
     def backward(ctx, g_fd, g_dyn, g_score):
         flow, rflow = ctx.saved_tensors
+        if g_fd is None:
+            return None, None, None, None
         g_fd = _dev(g_fd, "grad")
         gf = torch.empty_like(flow) if ctx.needs_input_grad[0] else None
         gr = torch.empty_like(rflow) if ctx.needs_input_grad[1] else None
@@ -630,6 +634,7 @@ class _ReprojectFn(torch.autograd.Function):
                   W, out.data_ptr(), valid.data_ptr(), proj.data_ptr(), comp.data_ptr(), _stream_ptr())
         ctx.save_for_backward(img, depth, ref_depth, Kinv, P)
         ctx.mark_non_differentiable(valid)
+        ctx.set_materialize_grads(False)     # unused outputs arrive as None, not as zero maps to scatter
         return out, valid, proj, comp
 
     @staticmethod
@@ -637,6 +642,10 @@ class _ReprojectFn(torch.autograd.Function):
         img, depth, ref_depth, Kinv, P = ctx.saved_tensors
         B, Cc, H, W = img.shape
         need_img, need_depth, need_ref, _, need_P = ctx.needs_input_grad
+        if g_img is None and g_proj is None and g_comp is None:
+            return None, None, None, None, None
+        need_img = need_img and g_img is not None          # d/d img only flows through the sampled image,
+        need_ref = need_ref and g_proj is not None         # d/d ref_depth only through the projected depth
         g_img = _dev(g_img, "g") if g_img is not None else None
         g_proj = _dev(g_proj, "g") if g_proj is not None else None
         g_comp = _dev(g_comp, "g") if g_comp is not None else None
