@@ -212,6 +212,42 @@ int ugl_rigid_flow_forward(const float* depth, const float* Kinv, const float* P
 int ugl_rigid_flow_backward(const float* depth, const float* Kinv, const float* P, const float* grad_out, int32_t batch, int32_t height,
                             int32_t width, float* grad_depth, float* grad_P, void* workspace, uint64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused reprojection-photometric term of the depth / geom modes: for every level and both directions
+ * reconstruction (model_geometry.py:80-103 -> inverse_warp2, structures/inverse_warp.py:263-303) +
+ * compute_texture_mask (:134-140) + mask fusion (model_depth.py:262-269 valid * texture, or the flow-branch
+ * mask * texture of model_geometry.py:854-855 when ext_mask is given) + compute_photometric_loss (:143-153),
+ * summed over directions and levels -> loss (B,) = loss_depth_pixel.  dir 0 = left source frame / pose[:,0],
+ * dir 1 = right source frame / pose[:,1].  backward: grad_loss (B,) -> grad_disp[l] (B,1,h,w), grad_P[dir][l] (B,3,4).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct UglDepthPhotoArgs {
+  int32_t batch;
+  int32_t scales;
+  int32_t height[UGL_MAX_LEVELS];
+  int32_t width[UGL_MAX_LEVELS];
+  const float* img[UGL_MAX_LEVELS];            /* (B,3,h,w) centre frame, bilinear pyramid                 */
+  const float* src_area[2][UGL_MAX_LEVELS];    /* (B,3,h,w) source frames, area pyramid (sampled)          */
+  const float* src_bil[2][UGL_MAX_LEVELS];     /* (B,3,h,w) source frames, bilinear pyramid (texture mask) */
+  const float* disp[UGL_MAX_LEVELS];           /* (B,1,h,w) centre disparity                                */
+  const float* Kinv[UGL_MAX_LEVELS];           /* (B,3,3) inverse of the level's intrinsics                 */
+  const float* P[2][UGL_MAX_LEVELS];           /* (B,3,4) K_s [R|t]                                         */
+  const float* ext_mask[2][UGL_MAX_LEVELS];    /* (B,1,h,w) or NULL (= use the reprojection valid mask)     */
+  float* valid_out[2][UGL_MAX_LEVELS];         /* optional (B,1,h,w) reprojection valid mask                */
+  float* tex_out[2][UGL_MAX_LEVELS];           /* optional (B,1,h,w) texture mask                           */
+  float* loss;                                 /* (B,)                                                      */
+  float* den;                                  /* (B,scales,2) written by forward, read by backward         */
+  const float* grad_loss;                      /* (B,)            [backward]                                */
+  float* grad_disp[UGL_MAX_LEVELS];            /* (B,1,h,w)       [backward]                                */
+  float* grad_P[2][UGL_MAX_LEVELS];            /* (B,3,4)         [backward]                                */
+  void* workspace;
+  uint64_t workspace_bytes;
+  void* stream;
+} UglDepthPhotoArgs;
+
+uint64_t ugl_depth_photo_workspace_bytes(const UglDepthPhotoArgs* args);
+int ugl_depth_photo_forward(const UglDepthPhotoArgs* args);
+int ugl_depth_photo_backward(const UglDepthPhotoArgs* args);
+
 /* compute_epipolar_map (model_geometry.py:355-403) given F (B,3,3) = K^-T [t]x R K^-1: dist (B,1,H,W);
  * backward: grad_flow (B,2,H,W, may be NULL) and grad_F (B,3,3). */
 int ugl_epipolar_forward(const float* flow, const float* F, int32_t batch, int32_t height, int32_t width, float* out, void* stream);

@@ -285,3 +285,36 @@ def test_flow_mode_composed_equals_fused(cuda_device):
         assert loss_rel_err(a[k], b[k]) < LOSS_RTOL, k
     for x, y in zip(ga, gb):
         assert rel_err(x, y) < GRAD_RTOL
+
+
+def test_fused_depth_branch_equals_composed(cuda_device):
+    """ops.depth_photo_loss (one fused kernel) against the composition of the per-method kernels it replaces."""
+    t = make_triplet(2, 64, 208, 4, 3, seed=61, flow_mode="rigid").to(cuda_device)
+    W = P.GEOM_WEIGHTS
+    res = {}
+    for fused in (True, False):
+        disp, disp_l, disp_r = _leaf_list(t.disp, cuda_device), _leaf_list(t.disp_l, cuda_device), _leaf_list(t.disp_r, cuda_device)
+        pose = t.pose.detach().clone().requires_grad_(True)
+        loss, masks = losses.DepthLoss(3, "live").forward_losses(t.img_l, t.img, t.img_r, disp, disp_l, disp_r, pose, t.K, fused=fused)
+        g = torch.autograd.grad(sum(W[k] * v.mean() for k, v in loss.items()), disp + [pose])
+        res[fused] = (loss, masks, g)
+    assert loss_rel_err(res[True][0]["loss_depth_pixel"], res[False][0]["loss_depth_pixel"]) < 1e-6
+    for k in ("valid_l", "valid_r", "tex_b", "tex_f"):
+        for a, b in zip(res[True][1][k], res[False][1][k]):
+            assert torch.equal(a, b), k
+    for a, b in zip(res[True][2], res[False][2]):
+        assert rel_err(a, b) < 2e-5
+    for fused in (True, False):
+        ff, fb = _leaf_list(t.flows_fwd, cuda_device), _leaf_list(t.flows_bwd, cuda_device)
+        disp, disp_l, disp_r = _leaf_list(t.disp, cuda_device), _leaf_list(t.disp_l, cuda_device), _leaf_list(t.disp_r, cuda_device)
+        pose = t.pose.detach().clone().requires_grad_(True)
+        loss, masks = losses.GeometryLoss(3).forward_losses(t.img_l, t.img, t.img_r, ff, fb, disp, disp_l, disp_r, pose, t.K, t.K_inv, fused=fused)
+        keys = [k for k, v in loss.items() if v.numel() == 2 and v.requires_grad and k not in ("loss_depth_ssim", "loss_depth_consis", "loss_triangle", "loss_pnp", "loss_eight_point")]
+        g = torch.autograd.grad(sum(W[k] * loss[k].mean() for k in keys), disp + [pose] + ff[:3] + fb[:3])
+        res[fused] = (loss, masks, g)
+    assert loss_rel_err(res[True][0]["loss_depth_pixel"], res[False][0]["loss_depth_pixel"]) < 1e-6
+    for k in ("val_l", "val_r", "tex_b", "tex_f"):
+        for a, b in zip(res[True][1][k], res[False][1][k]):
+            assert torch.equal(a, b), k
+    for a, b in zip(res[True][2], res[False][2]):
+        assert rel_err(a, b) < 2e-5

@@ -45,6 +45,21 @@ class UglFlowLossArgs(C.Structure):
     ]
 
 
+class UglDepthPhotoArgs(C.Structure):
+    """Mirror of ``struct UglDepthPhotoArgs`` (include/ugl.h)."""
+
+    _L, _L2 = C.c_void_p * MAX_LEVELS, (C.c_void_p * MAX_LEVELS) * 2
+    _fields_ = [
+        ("batch", C.c_int32), ("scales", C.c_int32),
+        ("height", C.c_int32 * MAX_LEVELS), ("width", C.c_int32 * MAX_LEVELS),
+        ("img", _L), ("src_area", _L2), ("src_bil", _L2), ("disp", _L), ("Kinv", _L), ("P", _L2), ("ext_mask", _L2),
+        ("valid_out", _L2), ("tex_out", _L2),
+        ("loss", C.c_void_p), ("den", C.c_void_p), ("grad_loss", C.c_void_p),
+        ("grad_disp", _L), ("grad_P", _L2),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("stream", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/ugl.h declares
 SIGNATURES = {
     "ugl_version": (C.c_int, []),
@@ -70,6 +85,9 @@ _ip = C.POINTER(C.c_int32)
 SIGNATURES.update({
     "ugl_forward_splat_workspace_bytes": (_u64, [_i, _i, _i, _i]),
     "ugl_forward_splat": (C.c_int, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _u64, _p]),
+    "ugl_depth_photo_workspace_bytes": (_u64, [C.POINTER(UglDepthPhotoArgs)]),
+    "ugl_depth_photo_forward": (C.c_int, [C.POINTER(UglDepthPhotoArgs)]),
+    "ugl_depth_photo_backward": (C.c_int, [C.POINTER(UglDepthPhotoArgs)]),
     "ugl_reduce_workspace_bytes": (_u64, [_i, _i, _i]),
     "ugl_masked_mean_forward": (C.c_int, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _u64, _p]),
     "ugl_masked_mean_backward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),

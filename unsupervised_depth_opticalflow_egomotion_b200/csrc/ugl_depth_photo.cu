@@ -1,0 +1,259 @@
+// Fused reprojection-photometric term of the depth / geom modes, both directions and all pyramid levels in one launch:
+//   reconstruction (model_geometry.py:80-103 -> inverse_warp2, structures/inverse_warp.py:263-303): backproject the
+//   centre disparity with K_s^-1, transform + project with P = K_s [R|t], normalise, out-of-range -> 2, bilinear sample of
+//   the area-resized source frame, reprojection valid mask;
+//   compute_texture_mask (model_geometry.py:134-140);
+//   mask fusion (model_depth.py:262-269: valid * texture; model_geometry.py:854-855: flow-branch mask * texture);
+//   compute_photometric_loss (model_geometry.py:143-153) summed over directions and levels.
+// Forward = per-(sample, level, chunk) partial sums + finalize; backward recomputes the per-pixel quantities (nothing
+// per-pixel is saved) and writes d loss / d disparity densely and d loss / d P through the deterministic two-stage reduction.
+#include "ugl_common.cuh"
+#include "ugl_geometry.cuh"
+#include "ugl_reduce.cuh"
+
+namespace ugl {
+
+struct DepthPhotoLevel {
+  int h, w;
+  const float* img;            // (B,3,h,w) centre frame, bilinear pyramid
+  const float* src_area[2];    // (B,3,h,w) source frame (0: left / bwd pose, 1: right / fwd pose), area pyramid
+  const float* src_bil[2];     // (B,3,h,w) source frame, bilinear pyramid (texture mask)
+  const float* disp;           // (B,1,h,w)
+  const float* Kinv;           // (B,3,3)
+  const float* P[2];           // (B,3,4)
+  const float* ext_mask[2];    // (B,1,h,w) or null: mask from the flow branch (geom mode) instead of the reprojection valid
+  float* valid_out[2];         // optional (B,1,h,w)
+  float* tex_out[2];           // optional (B,1,h,w)
+  float* grad_disp;            // (B,1,h,w)   [backward]
+};
+
+struct DepthPhotoParams {
+  int B, scales, chunks;
+  DepthPhotoLevel lv[kMaxLevels];
+  float* partials;             // fwd: [B][scales][chunks][4]; bwd: [B][scales][chunks][24]
+  float* den;                  // [B][scales][2]  mean(mask) + 1e-12, kept for backward
+  float* loss;                 // (B,)
+  const float* gloss;          // (B,)            [backward]
+  float* grad_P[2][kMaxLevels];// (B,3,4)         [backward]
+};
+
+struct DepthPixel {
+  float I[3], rec[3];
+  float mask;                  // fused {0,1} mask of this direction
+  Projected pr;
+  NormCoord nc;
+  Tap tap;
+};
+
+// everything the forward and the backward need for one pixel and one direction
+template <bool kGrad>
+__device__ __forceinline__ void depth_pixel(const DepthPhotoLevel& L, const float* sK, const float* sP, int b, int dir, int i, int j,
+                                            long p, const WarpGeom& g, DepthPixel& o, float* gix, float* giy, float k_scale) {
+  const long plane = (long)L.h * L.w;
+  o.pr = project_pixel(sK, sP, L.disp[(long)b * plane + p], j, i);
+  o.nc = normalise(o.pr, g);
+  o.tap = make_tap(unnormalize(o.nc.gx, L.w), unnormalize(o.nc.gy, L.h), L.w, L.h);
+  const float valid = (fabsf(o.nc.gx) <= 1.0f && fabsf(o.nc.gy) <= 1.0f) ? 1.f : 0.f;
+  float a = 0.f, s = 0.f;
+  Corners cs[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const long o3 = ((long)b * 3 + c) * plane;
+    o.I[c] = L.img[o3 + p];
+    cs[c] = tap_fetch(L.src_area[dir] + o3, L.w, o.tap);
+    o.rec[c] = corners_value(cs[c], o.tap);
+    a = add_rn(a, fabsf(sub_rn(o.I[c], o.rec[c])));
+    s = add_rn(s, fabsf(sub_rn(o.I[c], L.src_bil[dir][o3 + p])));
+  }
+  const float r3 = 1.0f / 3.0f;
+  const float tex = div_c(a, 3.0f, r3) < div_c(s, 3.0f, r3) ? 1.f : 0.f;
+  const float base = L.ext_mask[dir] ? L.ext_mask[dir][(long)b * plane + p] : valid;
+  o.mask = mul_rn(base, tex);
+  if (!kGrad) {
+    if (L.valid_out[dir]) L.valid_out[dir][(long)b * plane + p] = valid;
+    if (L.tex_out[dir]) L.tex_out[dir][(long)b * plane + p] = tex;
+  } else {
+    float gx = 0.f, gy = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float gr = k_scale * o.mask * sgnf(o.rec[c] - o.I[c]);      // d loss / d rec_c
+      gx += gr * corners_ddx(cs[c], o.tap);
+      gy += gr * corners_ddy(cs[c], o.tap);
+    }
+    *gix = gx; *giy = gy;
+  }
+}
+
+__global__ void __launch_bounds__(kRedThreads) depth_photo_fwd_kernel(const __grid_constant__ DepthPhotoParams p) {
+  __shared__ float sK[9], sP[2][12];
+  __shared__ float red[(kRedThreads / 32) * 4];
+  const int b = blockIdx.y, l = blockIdx.z;
+  const DepthPhotoLevel& L = p.lv[l];
+  if (threadIdx.x < 9) sK[threadIdx.x] = L.Kinv[b * 9 + threadIdx.x];
+  if (threadIdx.x < 24) sP[threadIdx.x / 12][threadIdx.x % 12] = L.P[threadIdx.x / 12][b * 12 + threadIdx.x % 12];
+  __syncthreads();
+  const WarpGeom g = make_warp_geom(L.w, L.h);
+  const long plane = (long)L.h * L.w;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
+    const int i = (int)(px / L.w), j = (int)(px % L.w);
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      DepthPixel o;
+      depth_pixel<false>(L, sK, sP[dir], b, dir, i, j, px, g, o, nullptr, nullptr, 0.f);
+      acc[2 * dir] += (fabsf(o.I[0] - o.rec[0]) + fabsf(o.I[1] - o.rec[1]) + fabsf(o.I[2] - o.rec[2])) * o.mask;
+      acc[2 * dir + 1] += o.mask;
+    }
+  }
+  const float v = block_reduce_n<kRedThreads, 4>(acc, red);
+  if (threadIdx.x < 4) p.partials[(((long)b * p.scales + l) * p.chunks + blockIdx.x) * 4 + threadIdx.x] = v;
+}
+
+// one warp per sample: per level fixed-order fp64 sum of the chunk partials, closing formula, sum over levels
+__global__ void depth_photo_finalize_kernel(const __grid_constant__ DepthPhotoParams p) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= p.B) return;
+  float total = 0.f;
+  for (int l = 0; l < p.scales; ++l) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = lane; c < p.chunks; c += 32) {
+      const float* r = p.partials + (((long)b * p.scales + l) * p.chunks + c) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] += (double)r[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_down_sync(0xffffffffu, s[k], o);
+    }
+    if (lane == 0) {
+      const float hw = (float)p.lv[l].h * (float)p.lv[l].w;
+#pragma unroll
+      for (int dir = 0; dir < 2; ++dir) {
+        const float den = (float)(s[2 * dir + 1] / hw) + 1e-12f;
+        p.den[((long)b * p.scales + l) * 2 + dir] = den;
+        total += (float)(s[2 * dir] / (3.0 * hw)) / den;
+      }
+    }
+  }
+  if (lane == 0) p.loss[b] = total;
+}
+
+__global__ void __launch_bounds__(kRedThreads) depth_photo_bwd_kernel(const __grid_constant__ DepthPhotoParams p) {
+  __shared__ float sK[9], sP[2][12];
+  __shared__ float red[(kRedThreads / 32) * 24];
+  const int b = blockIdx.y, l = blockIdx.z;
+  const DepthPhotoLevel& L = p.lv[l];
+  if (threadIdx.x < 9) sK[threadIdx.x] = L.Kinv[b * 9 + threadIdx.x];
+  if (threadIdx.x < 24) sP[threadIdx.x / 12][threadIdx.x % 12] = L.P[threadIdx.x / 12][b * 12 + threadIdx.x % 12];
+  __syncthreads();
+  const WarpGeom g = make_warp_geom(L.w, L.h);
+  const long plane = (long)L.h * L.w;
+  const float hw = (float)L.h * (float)L.w;
+  float ks[2];
+#pragma unroll
+  for (int dir = 0; dir < 2; ++dir) ks[dir] = p.gloss[b] / (3.0f * hw) / p.den[((long)b * p.scales + l) * 2 + dir];
+  float acc[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) acc[k] = 0.f;
+  for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
+    const int i = (int)(px / L.w), j = (int)(px % L.w);
+    float gD = 0.f;
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      DepthPixel o;
+      float gix, giy;
+      depth_pixel<true>(L, sK, sP[dir], b, dir, i, j, px, g, o, &gix, &giy, ks[dir]);
+      const float g_u = o.nc.ox ? 0.f : gix * g.sx;
+      const float g_v = o.nc.oy ? 0.f : giy * g.sy;
+      gD += project_backward(o.pr, sP[dir], g_u, g_v, 0.f, acc + 12 * dir);
+    }
+    L.grad_disp[(long)b * plane + px] = gD;
+  }
+  const float v = block_reduce_n<kRedThreads, 24>(acc, red);
+  if (threadIdx.x < 24) p.partials[(((long)b * p.scales + l) * p.chunks + blockIdx.x) * 24 + threadIdx.x] = v;
+}
+
+// one warp per (sample, level): grad_P[dir][level][b] = fixed-order sum of the chunk partials
+__global__ void depth_photo_bwd_finalize_kernel(const __grid_constant__ DepthPhotoParams p) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= p.B * p.scales) return;
+  const int b = w / p.scales, l = w % p.scales;
+  if (lane < 24) {
+    double s = 0.0;
+    for (int c = 0; c < p.chunks; ++c) s += (double)p.partials[(((long)b * p.scales + l) * p.chunks + c) * 24 + lane];
+    p.grad_P[lane / 12][l][b * 12 + lane % 12] = (float)s;
+  }
+}
+
+}  // namespace ugl
+
+using namespace ugl;
+
+static int depth_photo_fill(const UglDepthPhotoArgs* a, bool backward, DepthPhotoParams& p) {
+  if (!a) return fail(UGL_EINVAL, "depth_photo: null args");
+  if (a->batch <= 0 || a->batch > 65535 || a->scales <= 0 || a->scales > UGL_MAX_LEVELS)
+    return fail(UGL_EINVAL, "depth_photo: bad batch/scales (%d/%d)", a->batch, a->scales);
+  p.B = a->batch; p.scales = a->scales;
+  long max_plane = 0;
+  for (int l = 0; l < a->scales; ++l) {
+    DepthPhotoLevel& L = p.lv[l];
+    L.h = a->height[l]; L.w = a->width[l];
+    if (L.h < 2 || L.w < 2) return fail(UGL_EUNSUPPORTED, "depth_photo: level %d is %dx%d", l, L.h, L.w);
+    L.img = a->img[l]; L.disp = a->disp[l]; L.Kinv = a->Kinv[l];
+    if (!L.img || !L.disp || !L.Kinv) return fail(UGL_EINVAL, "depth_photo: null input at level %d", l);
+    for (int d = 0; d < 2; ++d) {
+      L.src_area[d] = a->src_area[d][l]; L.src_bil[d] = a->src_bil[d][l]; L.P[d] = a->P[d][l];
+      L.ext_mask[d] = a->ext_mask[d][l]; L.valid_out[d] = a->valid_out[d][l]; L.tex_out[d] = a->tex_out[d][l];
+      if (!L.src_area[d] || !L.src_bil[d] || !L.P[d]) return fail(UGL_EINVAL, "depth_photo: null input at level %d", l);
+      p.grad_P[d][l] = backward ? a->grad_P[d][l] : nullptr;
+      if (backward && !p.grad_P[d][l]) return fail(UGL_EINVAL, "depth_photo: null grad_P at level %d", l);
+    }
+    L.grad_disp = backward ? a->grad_disp[l] : nullptr;
+    if (backward && !L.grad_disp) return fail(UGL_EINVAL, "depth_photo: null grad_disp at level %d", l);
+    const long pl = (long)L.h * L.w;
+    max_plane = pl > max_plane ? pl : max_plane;
+  }
+  p.chunks = reduce_chunks(max_plane);
+  if (!a->den) return fail(UGL_EINVAL, "depth_photo: null den");
+  p.den = a->den; p.loss = a->loss; p.gloss = a->grad_loss;
+  p.partials = static_cast<float*>(a->workspace);
+  const uint64_t need = (uint64_t)p.B * p.scales * p.chunks * 24 * sizeof(float);
+  if (!a->workspace || a->workspace_bytes < need) return fail(UGL_EWORKSPACE, "depth_photo: workspace too small (%llu < %llu)",
+                                                              (unsigned long long)a->workspace_bytes, (unsigned long long)need);
+  return UGL_OK;
+}
+
+extern "C" uint64_t ugl_depth_photo_workspace_bytes(const UglDepthPhotoArgs* a) {
+  if (!a) return 0;
+  long max_plane = 0;
+  for (int l = 0; l < a->scales && l < UGL_MAX_LEVELS; ++l) {
+    const long pl = (long)a->height[l] * a->width[l];
+    max_plane = pl > max_plane ? pl : max_plane;
+  }
+  return (uint64_t)a->batch * a->scales * reduce_chunks(max_plane) * 24 * sizeof(float);
+}
+
+extern "C" int ugl_depth_photo_forward(const UglDepthPhotoArgs* a) {
+  DepthPhotoParams p;
+  int rc = depth_photo_fill(a, false, p);
+  if (rc) return rc;
+  if (!a->loss) return fail(UGL_EINVAL, "depth_photo_forward: null loss");
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  depth_photo_fwd_kernel<<<dim3(p.chunks, p.B, p.scales), kRedThreads, 0, st>>>(p);
+  if ((rc = check_launch("depth_photo_fwd_kernel"))) return rc;
+  depth_photo_finalize_kernel<<<(p.B + 3) / 4, 128, 0, st>>>(p);
+  return check_launch("depth_photo_finalize_kernel");
+}
+
+extern "C" int ugl_depth_photo_backward(const UglDepthPhotoArgs* a) {
+  DepthPhotoParams p;
+  int rc = depth_photo_fill(a, true, p);
+  if (rc) return rc;
+  if (!a->grad_loss) return fail(UGL_EINVAL, "depth_photo_backward: null grad_loss");
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  depth_photo_bwd_kernel<<<dim3(p.chunks, p.B, p.scales), kRedThreads, 0, st>>>(p);
+  if ((rc = check_launch("depth_photo_bwd_kernel"))) return rc;
+  depth_photo_bwd_finalize_kernel<<<(p.B * p.scales + 3) / 4, 128, 0, st>>>(p);
+  return check_launch("depth_photo_bwd_finalize_kernel");
+}

@@ -153,12 +153,20 @@ class DepthLoss(_LossBase):
         """model_depth.py:154-163 (unmasked)"""
         return sum(ops.masked_mean(ops.depth_diff(computed_depth_list[s], predicted_depth_list[s]), None) for s in range(self.num_scales))
 
-    def forward_losses(self, img_l, img, img_r, disp_list, disp_l_list, disp_r_list, pose_vectors, K) -> Tuple[Dict[str, Tensor], Dict]:
-        """Loss body of ``Model_depth.forward`` (model_depth.py:281-335) / model_depth_texture.py:262-311."""
+    def forward_losses(self, img_l, img, img_r, disp_list, disp_l_list, disp_r_list, pose_vectors, K, fused: bool = True) -> Tuple[Dict[str, Tensor], Dict]:
+        """Loss body of ``Model_depth.forward`` (model_depth.py:281-335) / model_depth_texture.py:262-311.  ``fused=True``
+        (live variant) runs the reprojection + texture mask + masked L1 of both directions and all levels as one kernel."""
         S = self.num_scales
         pl, pc, pr = (self.generate_img_pyramid(x, S) for x in (img_l, img, img_r))
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
         Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
+        if fused and self.variant == "live":
+            area = (ops.image_pyramid(img_l, S, "area"), ops.image_pyramid(img_r, S, "area"))
+            pix, valid, tex = ops.depth_photo_loss(pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f))
+            loss = {"loss_depth_pixel": pix, "loss_depth_ssim": _zeros2(img), "loss_depth_consis": _zeros2(img),
+                    "loss_depth_smooth": (self.compute_smooth_loss(img, disp_list) + self.compute_smooth_loss(img_l, disp_l_list)
+                                          + self.compute_smooth_loss(img_r, disp_r_list))}
+            return loss, dict(valid_l=valid[0], valid_r=valid[1], tex_b=tex[0], tex_f=tex[1])
         rec_l, val_l, proj_l, comp_l = self._reconstruction_with(img_l, disp_list, disp_l_list, Kinv, P_b)
         rec_r, val_r, proj_r, comp_r = self._reconstruction_with(img_r, disp_list, disp_r_list, Kinv, P_f)
         tex_b = self.compute_texture_mask(pc, rec_l, pl)
@@ -251,7 +259,7 @@ class GeometryLoss(_LossBase):
         return [ops.mask_product([valid_mask[s], occ_mask[s]], [False, invert_second]) for s in range(self.num_scales)]
 
     def forward_losses(self, img_l, img, img_r, optical_flows_fwd, optical_flows_bwd, disp_list, disp_l_list, disp_r_list,
-                       pose_vectors, K, K_inv) -> Tuple[Dict[str, Tensor], Dict]:
+                       pose_vectors, K, K_inv, fused: bool = True) -> Tuple[Dict[str, Tensor], Dict]:
         """Loss body of ``Model_geometry.forward`` (model_geometry.py:777-951) given the network outputs.
         The second return value holds the device-side masks (the reference's ``mask_pack`` without its
         unconditional D2H copies, :871-880)."""
@@ -259,10 +267,11 @@ class GeometryLoss(_LossBase):
         pc, pl, pr = (self.generate_img_pyramid(x, S) for x in (img, img_l, img_r))
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
         Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
-        rec_l, val_l, _, _ = self._reconstruction_with(img_l, disp_list, disp_l_list, Kinv, P_b)
-        rec_r, val_r, _, _ = self._reconstruction_with(img_r, disp_list, disp_r_list, Kinv, P_f)
-        tex_b = self.compute_texture_mask(pc, rec_l, pl)
-        tex_f = self.compute_texture_mask(pc, rec_r, pr)
+        if not fused:
+            rec_l, val_l, _, _ = self._reconstruction_with(img_l, disp_list, disp_l_list, Kinv, P_b)
+            rec_r, val_r, _, _ = self._reconstruction_with(img_r, disp_list, disp_r_list, Kinv, P_f)
+            tex_b = self.compute_texture_mask(pc, rec_l, pl)
+            tex_f = self.compute_texture_mask(pc, rec_r, pr)
         from_l = self.warp_flow_pyramid(pl, optical_flows_bwd)
         from_r = self.warp_flow_pyramid(pr, optical_flows_fwd)
         occ_b, occ_f, valid_b, valid_f = self.compute_occ_weight(from_l, pc, from_r)
@@ -274,8 +283,13 @@ class GeometryLoss(_LossBase):
 
         fwd_mask = self.fusion_mask(valid_f, occ_f, dyn_f)
         bwd_mask = self.fusion_mask(valid_b, occ_b, dyn_b)
-        fwd_mask_tex = self.fusion_mask_2item(fwd_mask, tex_f)
-        bwd_mask_tex = self.fusion_mask_2item(bwd_mask, tex_b)
+        if fused:   # reprojection + texture mask + (flow-branch mask * texture) + L1, both directions, all levels: one kernel
+            area = (ops.image_pyramid(img_l, S, "area"), ops.image_pyramid(img_r, S, "area"))
+            depth_pixel, (val_l, val_r), (tex_b, tex_f) = ops.depth_photo_loss(pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f),
+                                                                                 ext_mask=(bwd_mask, fwd_mask))
+        else:
+            fwd_mask_tex = self.fusion_mask_2item(fwd_mask, tex_f)
+            bwd_mask_tex = self.fusion_mask_2item(bwd_mask, tex_b)
         fwd_vo = self.fusion_mask_2item(valid_f, occ_f)
         bwd_vo = self.fusion_mask_2item(valid_b, occ_b)
         fwd_vo_rigid = self.fusion_mask_2item(fwd_vo, dyn_f)
@@ -285,7 +299,7 @@ class GeometryLoss(_LossBase):
 
         P = self.compute_photometric_loss
         loss = {
-            "loss_depth_pixel": P(pc, rec_l, bwd_mask_tex) + P(pc, rec_r, fwd_mask_tex),
+            "loss_depth_pixel": depth_pixel if fused else P(pc, rec_l, bwd_mask_tex) + P(pc, rec_r, fwd_mask_tex),
             "loss_depth_ssim": _zeros2(img),
             "loss_depth_smooth": self.compute_smooth_loss(img, disp_list) + self.compute_smooth_loss(img_l, disp_l_list)
                                  + self.compute_smooth_loss(img_r, disp_r_list),

@@ -740,3 +740,101 @@ def forward_splat(x: Tensor, flow: Tensor, clamp01: bool = False) -> Tensor:
         _call("ugl_forward_splat", x.data_ptr(), flow.data_ptr(), B, Cc, H, W, int(clamp01), out.data_ptr(), ws.data_ptr(), _nbytes(ws),
               _stream_ptr(), launches=3)
     return out
+
+
+# ================================================================================================
+# fused reprojection-photometric term (depth / geom modes)
+# ================================================================================================
+def _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, loss, den, ws, valid_out=None, tex_out=None, gloss=None, gdisp=None, gP=None):
+    a = _cabi.UglDepthPhotoArgs()
+    a.batch, a.scales = img[0].shape[0], S
+    for l in range(S):
+        a.height[l], a.width[l] = img[l].shape[2], img[l].shape[3]
+        a.img[l], a.disp[l], a.Kinv[l] = img[l].data_ptr(), disp[l].data_ptr(), Kinv[l].data_ptr()
+        for d in range(2):
+            a.src_area[d][l], a.src_bil[d][l], a.P[d][l] = area[d][l].data_ptr(), bil[d][l].data_ptr(), P[d][l].data_ptr()
+            if ext is not None:
+                a.ext_mask[d][l] = ext[d][l].data_ptr()
+            if valid_out is not None:
+                a.valid_out[d][l], a.tex_out[d][l] = valid_out[d][l].data_ptr(), tex_out[d][l].data_ptr()
+            if gP is not None:
+                a.grad_P[d][l] = gP[d][l].data_ptr()
+        if gdisp is not None:
+            a.grad_disp[l] = gdisp[l].data_ptr()
+    a.loss, a.den, a.grad_loss = _ptr(loss), _ptr(den), _ptr(gloss)
+    a.workspace, a.workspace_bytes = _ptr(ws), (_nbytes(ws) if ws is not None else 0)
+    a.stream = torch.cuda.current_stream().cuda_stream
+    return a
+
+
+class _DepthPhotoFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, S, has_ext, *ts):
+        ts = [_dev(t, "input %d" % i) for i, t in enumerate(ts)]
+        # layout: img[S], area_b[S], area_f[S], bil_b[S], bil_f[S], disp[S], Kinv[S], P_b[S], P_f[S], (ext_b[S], ext_f[S])
+        g = lambda k: ts[k * S:(k + 1) * S]
+        img, area, bil, disp, Kinv, P = g(0), (g(1), g(2)), (g(3), g(4)), g(5), g(6), (g(7), g(8))
+        ext = (g(9), g(10)) if has_ext else None
+        B, dev = img[0].shape[0], img[0].device
+        for l in range(S):
+            h, w = img[l].shape[2:]
+            if tuple(disp[l].shape) != (B, 1, h, w) or tuple(area[0][l].shape) != (B, 3, h, w) or tuple(P[0][l].shape) != (B, 3, 4):
+                raise ValueError("depth_photo_loss: inconsistent shapes at level %d" % l)
+        loss = torch.empty(B, device=dev, dtype=torch.float32)
+        den = torch.empty((B, S, 2), device=dev, dtype=torch.float32)
+        mk = lambda: [[torch.empty((B, 1) + tuple(img[l].shape[2:]), device=dev, dtype=torch.float32) for l in range(S)] for _ in range(2)]
+        valid_out, tex_out = mk(), mk()
+        a = _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, loss, den, None, valid_out, tex_out)
+        n = int(_cabi.lib().ugl_depth_photo_workspace_bytes(C.byref(a)))
+        ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), _nbytes(ws)
+        with torch.cuda.device_of(img[0]):
+            _call("ugl_depth_photo_forward", C.byref(a), launches=2)
+        ctx.save_for_backward(den, *ts)
+        ctx.S, ctx.has_ext = S, has_ext
+        masks = [m for grp in (valid_out, tex_out) for d in grp for m in d]
+        ctx.mark_non_differentiable(*masks)
+        ctx.set_materialize_grads(False)
+        return (loss, *masks)
+
+    @staticmethod
+    def backward(ctx, gloss, *unused):
+        den, *ts = ctx.saved_tensors
+        S = ctx.S
+        if gloss is None:
+            return (None,) * (2 + len(ts))
+        g = lambda k: ts[k * S:(k + 1) * S]
+        img, area, bil, disp, Kinv, P = g(0), (g(1), g(2)), (g(3), g(4)), g(5), g(6), (g(7), g(8))
+        ext = (g(9), g(10)) if ctx.has_ext else None
+        B, dev = img[0].shape[0], img[0].device
+        gloss = _dev(gloss, "grad_loss")
+        gdisp = [torch.empty_like(d) for d in disp]
+        gP = [[torch.empty((B, 3, 4), device=dev, dtype=torch.float32) for _ in range(S)] for _ in range(2)]
+        a = _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, None, den, None, gloss=gloss, gdisp=gdisp, gP=gP)
+        n = int(_cabi.lib().ugl_depth_photo_workspace_bytes(C.byref(a)))
+        ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), _nbytes(ws)
+        with torch.cuda.device_of(gloss):
+            _call("ugl_depth_photo_backward", C.byref(a), launches=2)
+        none = [None] * S
+        out = [None, None, *none, *none, *none, *none, *none, *gdisp, *none, *gP[0], *gP[1]]
+        if ctx.has_ext:
+            out += none + none
+        return tuple(out)
+
+
+def depth_photo_loss(img_pyr, src_area, src_bil, disps, Kinv, P, ext_mask=None):
+    """Fused ``loss_depth_pixel`` of the depth / geom modes (reconstruction + texture mask + mask fusion +
+    ``compute_photometric_loss`` for both directions and all ``len(disps)`` levels).
+
+    ``src_area`` / ``src_bil`` / ``P`` / ``ext_mask`` are pairs ``(left|bwd, right|fwd)`` of per-level lists.  Returns
+    ``(loss (B,), valid[2][S], tex[2][S])``; the loss is differentiable w.r.t. ``disps`` and ``P``."""
+    S = len(disps)
+    flat = [*img_pyr[:S], *src_area[0][:S], *src_area[1][:S], *src_bil[0][:S], *src_bil[1][:S], *disps, *Kinv[:S], *P[0][:S], *P[1][:S]]
+    if ext_mask is not None:
+        flat += [*ext_mask[0][:S], *ext_mask[1][:S]]
+    out = _DepthPhotoFn.apply(S, ext_mask is not None, *flat)
+    loss, masks = out[0], out[1:]
+    valid = [list(masks[0:S]), list(masks[S:2 * S])]
+    tex = [list(masks[2 * S:3 * S]), list(masks[3 * S:4 * S])]
+    return loss, valid, tex
