@@ -84,6 +84,37 @@ int ugl_flow_loss_forward_grad(const UglFlowLossArgs* args);
 int ugl_flow_loss_combine(const UglFlowLossArgs* args);
 
 /* ---------------------------------------------------------------------------------------------
+ * Flow branch of the geom-mode loss — replaces, per level of Model_geometry.forward's loop (model_geometry.py:845-919):
+ *   warp_flow x2 (:847-848), compute_occ_weight (:850 -> :105-132, hard masks [1 - softmax > 0.48]), calculate_rigid_flow
+ *   + compute_dynamic_mask (:866-870 -> :698-707), the masked L1 terms split by the dynamic mask with weights 1 / 2
+ *   (:905-908), the masked SSIM terms (:910-911), compute_loss_flow_smooth (:913-914) and compute_loss_flow_consis with
+ *   mask 1 - occ_fwd (:917-918).  Same single-pass structure as ugl_flow_loss_forward_grad / _combine (gradients flow to
+ *   the two flows only: every mask is detached in the reference).
+ *   flow.loss (4,B): flow_pixel, flow_ssim, flow_smooth, flow_consis summed over levels;  flow.stats (B,scales,UGL_GEOM_NSTATS)
+ *   mask_bytes[l] (B,h,w) uint8 OUTPUT (read again by _combine and by ugl_depth_photo_*): bit0 valid_bwd, bit1 valid_fwd,
+ *   bit2 occ_bwd, bit3 occ_fwd, bit4 dyn_bwd, bit5 dyn_fwd  (bwd = centre->left flow, fwd = centre->right flow).
+ *   disp[l] (B,1,h,w), Kinv[l] (B,3,3), P_bwd/P_fwd[l] (B,3,4) = K_l [R|t] of the centre->left / centre->right pose.
+ * ------------------------------------------------------------------------------------------- */
+#define UGL_GEOM_NSTATS 16
+#define UGL_MASK_VALID_BWD 1
+#define UGL_MASK_VALID_FWD 2
+#define UGL_MASK_OCC_BWD 4
+#define UGL_MASK_OCC_FWD 8
+#define UGL_MASK_DYN_BWD 16
+#define UGL_MASK_DYN_FWD 32
+typedef struct UglGeomFlowArgs {
+  UglFlowLossArgs flow;                        /* images, flows, loss, stats, grads, workspace, stream, basis */
+  const float* disp[UGL_MAX_LEVELS];
+  const float* Kinv[UGL_MAX_LEVELS];
+  const float* P_bwd[UGL_MAX_LEVELS];
+  const float* P_fwd[UGL_MAX_LEVELS];
+  uint8_t* mask_bytes[UGL_MAX_LEVELS];
+  float alpha, beta;                           /* flow_consist_alpha / flow_consist_beta */
+} UglGeomFlowArgs;
+int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* args);
+int ugl_geom_flow_combine(const UglGeomFlowArgs* args);
+
+/* ---------------------------------------------------------------------------------------------
  * Image pyramid — replaces generate_img_pyramid: model_flow.py:58-64 (mode 0: adaptive average
  * pooling = 2^s x 2^s box mean) and model_geometry.py:65-72 / model_depth.py:44-50 (mode 1:
  * bilinear, align_corners=False = mean of the central 2x2 of every 2^s block), and the 'area'
@@ -242,6 +273,10 @@ typedef struct UglDepthPhotoArgs {
   void* workspace;
   uint64_t workspace_bytes;
   void* stream;
+  /* geom mode, instead of ext_mask: packed masks written by ugl_geom_flow_forward_grad; the base mask of direction d is
+   * [ (ext_bytes & ext_need[d]) == ext_need[d] ]  (model_geometry.py:857-858: valid * occ * dyn = bits 1|4|16 / 2|8|32) */
+  const uint8_t* ext_bytes[UGL_MAX_LEVELS];    /* (B,h,w) or NULL */
+  int32_t ext_need[2];
 } UglDepthPhotoArgs;
 
 uint64_t ugl_depth_photo_workspace_bytes(const UglDepthPhotoArgs* args);

@@ -152,6 +152,69 @@ extern "C" int emu_flow_loss_combine(const UglFlowLossArgs* a) {
   return 0;
 }
 
+// geom mode (Model_geometry's flow branch): same tile logic with kGeom = true
+extern "C" int emu_geom_flow_forward_grad(const UglGeomFlowArgs* g) {
+  const UglFlowLossArgs* a = &g->flow;
+  FlowGradParams gp;
+  fill_params<kBTW, kBTH>(a, false, gp.base);
+  for (int l = 0; l < a->scales; ++l) {
+    gp.basis[l] = a->basis[l]; gp.disp[l] = g->disp[l]; gp.Kinv[l] = g->Kinv[l];
+    gp.P[0][l] = g->P_bwd[l]; gp.P[1][l] = g->P_fwd[l]; gp.mask_bytes[l] = g->mask_bytes[l];
+  }
+  gp.alpha = g->alpha; gp.beta = g->beta;
+  using Tile = FlowGradTile<kBTW, kBTH, 1, true>;
+  const FlowLossParams& p = gp.base;
+  std::vector<float> partials((size_t)p.total_tiles * GA_COUNT, 0.f), sm(Tile::kSmemFloats);
+  for (int tile = 0; tile < p.total_tiles; ++tile) {
+    const TileCoord tc = decode_tile<kBTW, kBTH>(p, tile);
+    float acc[GA_COUNT] = {0}, mats[33];
+    for (int k = 0; k < 9; ++k) mats[k] = gp.Kinv[tc.level][tc.b * 9 + k];
+    for (int k = 0; k < 12; ++k) { mats[9 + k] = gp.P[0][tc.level][tc.b * 12 + k]; mats[21 + k] = gp.P[1][tc.level][tc.b * 12 + k]; }
+    Tile::phase1(gp, tc, 0, 1, sm.data(), acc, mats);
+    for (int dir = 0; dir < 2; ++dir) {
+      Tile::phase2(gp, tc, dir, 0, 1, sm.data(), acc);
+      Tile::phase3(gp, tc, dir, 0, 1, sm.data());
+    }
+    Tile::phase4a(gp, tc, 0, 1, sm.data(), acc);
+    Tile::phase4b(gp, tc, 0, 1, sm.data());
+    for (int k = 0; k < GA_COUNT; ++k) partials[(size_t)tile * GA_COUNT + k] = acc[k];
+  }
+  for (int b = 0; b < p.B; ++b) {
+    float tot[4] = {0, 0, 0, 0};
+    for (int l = 0; l < p.scales; ++l) {
+      const FlowLevelDesc& L = p.lv[l];
+      const int per_img = L.tiles_x * L.tiles_y;
+      double s[GA_COUNT] = {0};
+      for (int t = 0; t < per_img; ++t)
+        for (int k = 0; k < GA_COUNT; ++k) s[k] += partials[((size_t)L.tile_begin + (size_t)b * per_img + t) * GA_COUNT + k];
+      float S[GA_COUNT], out[4];
+      for (int k = 0; k < GA_COUNT; ++k) { S[k] = (float)s[k]; p.stats[((size_t)b * p.scales + l) * GA_COUNT + k] = S[k]; }
+      geom_level_losses(S, L.h, L.w, out);
+      for (int k = 0; k < 4; ++k) tot[k] += out[k];
+    }
+    for (int k = 0; k < 4; ++k) p.loss[k * p.B + b] = tot[k];
+  }
+  return 0;
+}
+
+extern "C" int emu_geom_flow_combine(const UglGeomFlowArgs* g) {
+  const UglFlowLossArgs* a = &g->flow;
+  FlowGradParams gp;
+  fill_params<kBTW, kBTH>(a, true, gp.base);
+  const FlowLossParams& p = gp.base;
+  for (int l = 0; l < p.scales; ++l) {
+    const FlowLevelDesc& L = p.lv[l];
+    const int plane = L.h * L.w;
+    for (int b = 0; b < p.B; ++b) {
+      const GeomCombineScales k = geom_combine_scales(p.stats + ((size_t)b * p.scales + l) * GA_COUNT, L.h, L.w, p.gloss, p.B, b);
+      for (int pix = 0; pix < plane; ++pix)
+        geom_combine_pixel(a->basis[l] + (size_t)b * kBasisPlanes * plane, g->mask_bytes[l] + (size_t)b * plane, plane, pix, k,
+                           L.gflow_f + (size_t)b * 2 * plane, L.gflow_b + (size_t)b * 2 * plane);
+    }
+  }
+  return 0;
+}
+
 extern "C" int emu_image_pyramid(const float* img, int B, int C, int H, int W, int levels, int mode, float* const* out) {
   for (int l = 1; l < levels; ++l) {
     const int oh = H >> l, ow = W >> l;

@@ -73,3 +73,24 @@ def emu_flow_loss_single_pass(img_l, img, img_r, flows_fwd, flows_bwd, scales, g
     emu().emu_flow_loss_forward_grad(C.byref(a))
     emu().emu_flow_loss_combine(C.byref(a))
     return loss, gf, gb, stats
+
+
+def emu_geom_flow(img_l, img, img_r, flows_fwd, flows_bwd, disp, Kinv, P_b, P_f, alpha, beta, scales, gloss):
+    """geom-mode flow branch (forward_grad + combine) via the host emulator -> loss (4,B), grads, mask bytes"""
+    B = img[0].shape[0]
+    loss = torch.zeros(4, B)
+    stats = torch.zeros(B, scales, _cabi.GEOM_NSTATS)
+    gf = [torch.zeros_like(f) for f in flows_fwd[:scales]]
+    gb = [torch.zeros_like(f) for f in flows_bwd[:scales]]
+    basis = [torch.zeros(B, _cabi.FLOW_BASIS_PLANES, f.shape[2], f.shape[3]) for f in flows_fwd[:scales]]
+    masks = [torch.zeros(B, f.shape[2], f.shape[3], dtype=torch.uint8) for f in flows_fwd[:scales]]
+    g = _cabi.UglGeomFlowArgs()
+    g.flow = flow_loss_args(img_l, img, img_r, flows_fwd, flows_bwd, scales, loss, stats, gloss, gf, gb)
+    for l in range(scales):
+        g.flow.basis[l] = basis[l].data_ptr()
+        g.disp[l], g.Kinv[l], g.P_bwd[l], g.P_fwd[l] = disp[l].data_ptr(), Kinv[l].data_ptr(), P_b[l].data_ptr(), P_f[l].data_ptr()
+        g.mask_bytes[l] = masks[l].data_ptr()
+    g.alpha, g.beta = alpha, beta
+    emu().emu_geom_flow_forward_grad(C.byref(g))
+    emu().emu_geom_flow_combine(C.byref(g))
+    return loss, gf, gb, masks

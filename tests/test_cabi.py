@@ -50,6 +50,28 @@ def test_struct_layout_matches_header(lib):
     assert C.sizeof(a) == 64 + 5 * 48 + 3 * 8 + 2 * 48 + 8 + 8 + 8 + 48
 
 
+def test_struct_layouts_match_the_c_compiler(tmp_path):
+    """sizeof / offsetof of every argument struct as gcc lays out include/ugl.h == the ctypes mirrors"""
+    import os
+    import subprocess
+    structs = {"UglFlowLossArgs": _cabi.UglFlowLossArgs, "UglDepthPhotoArgs": _cabi.UglDepthPhotoArgs, "UglGeomFlowArgs": _cabi.UglGeomFlowArgs}
+    lines = []
+    for name, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for field in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, field[0], name, field[0]))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ugl.h"\nint main(void) {\n%s\nreturn 0; }\n' % "\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(__file__), "..", "include")
+    subprocess.check_call(["gcc", "-I", inc, "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == C.sizeof(cls), name
+        for field in cls._fields_:
+            assert int(got["%s.%s" % (name, field[0])]) == getattr(cls, field[0]).offset, (name, field[0])
+
+
 def test_argument_validation_happens_before_launch(lib):
     a = _cabi.UglFlowLossArgs()
     a.batch, a.levels, a.scales = 1, 1, 2            # scales > levels

@@ -312,9 +312,11 @@ def test_fused_depth_branch_equals_composed(cuda_device):
         keys = [k for k, v in loss.items() if v.numel() == 2 and v.requires_grad and k not in ("loss_depth_ssim", "loss_depth_consis", "loss_triangle", "loss_pnp", "loss_eight_point")]
         g = torch.autograd.grad(sum(W[k] * loss[k].mean() for k in keys), disp + [pose] + ff[:3] + fb[:3])
         res[fused] = (loss, masks, g)
-    assert loss_rel_err(res[True][0]["loss_depth_pixel"], res[False][0]["loss_depth_pixel"]) < 1e-6
-    for k in ("val_l", "val_r", "tex_b", "tex_f"):
+    # geom mode: fused = geom single-pass flow kernel + reprojection-photometric kernel reading its packed masks
+    for k in keys:
+        assert loss_rel_err(res[True][0][k], res[False][0][k]) < LOSS_RTOL, k
+    for k in ("val_l", "val_r", "tex_b", "tex_f", "occ_b", "occ_f", "valid_b", "valid_f", "dyn_b", "dyn_f", "fwd_mask", "bwd_mask"):
         for a, b in zip(res[True][1][k], res[False][1][k]):
             assert torch.equal(a, b), k
-    for a, b in zip(res[True][2], res[False][2]):
-        assert rel_err(a, b) < 2e-5
+    for i, (a, b) in enumerate(zip(res[True][2], res[False][2])):
+        assert rel_err(a, b) < (2e-5 if i < 4 else GRAD_RTOL), i      # flow gradients: SSIM sums in a different order

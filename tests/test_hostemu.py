@@ -93,3 +93,41 @@ def _grid(flow):
     B, _, Hh, W = flow.shape
     tgt = P._pixel_grid(B, Hh, W, flow) + flow
     return torch.stack([2.0 * tgt[:, 0] / max(W - 1, 1) - 1.0, 2.0 * tgt[:, 1] / max(Hh - 1, 1) - 1.0], -1)
+
+
+def _geom_projections(t, S):
+    """K_s^-1 and K_s [R|t] per level, as the oracle forms them (scale_intrinsics + pose_to_matrix)"""
+    H0 = t.img.shape[2]
+    Kinv, Pb, Pf = [], [], []
+    for s in range(S):
+        Ks = P.scale_intrinsics(t.K, H0 / (H0 >> s))
+        Kinv.append(Ks.inverse().contiguous())
+        Pb.append((Ks @ P.pose_to_matrix(t.pose[:, 0])).contiguous())
+        Pf.append((Ks @ P.pose_to_matrix(t.pose[:, 1])).contiguous())
+    return Kinv, Pb, Pf
+
+
+@pytest.mark.parametrize("B,Hh,W,S", [(2, 48, 96, 3), (1, 40, 72, 2), (1, 34, 50, 1)])
+def test_geom_flow_tiles_vs_oracle(B, Hh, W, S):
+    """geom-mode variant of the single-pass kernel: flow-branch losses, flow gradients and the packed masks"""
+    t = make_triplet(B, Hh, W, flow_levels=S, depth_scales=S, seed=11, flow_mode="rigid", flow_px=1.5)
+    keys = ("loss_flow_pixel", "loss_flow_ssim", "loss_flow_smooth", "loss_flow_consis")
+    gl = torch.rand(4, B, generator=torch.Generator().manual_seed(2)) + 0.5
+    ff = [f.detach().clone().requires_grad_(True) for f in t.flows_fwd]
+    fb = [f.detach().clone().requires_grad_(True) for f in t.flows_bwd]
+    loss, aux = P.geom_mode_loss(t.img_l, t.img, t.img_r, ff, fb, t.disp, t.disp_l, t.disp_r, t.pose, t.K, t.K_inv, S, return_aux=True)
+    sum((loss[k] * gl[i]).sum() for i, k in enumerate(keys)).backward()
+    pl, pc, pr = P.bilinear_pyramid(t.img_l, S), P.bilinear_pyramid(t.img, S), P.bilinear_pyramid(t.img_r, S)
+    Kinv, Pb, Pf = _geom_projections(t, S)
+    el, egf, egb, masks = H.emu_geom_flow(pl, pc, pr, [f.detach().contiguous() for f in ff], [f.detach().contiguous() for f in fb],
+                                          [d.detach().contiguous() for d in t.disp[:S]], Kinv, Pb, Pf, 0.01, 0.5, S, gl)
+    for bit, name in ((1, "valid_b"), (2, "valid_f"), (4, "occ_b"), (8, "occ_f"), (16, "dyn_b"), (32, "dyn_f")):
+        for s in range(S):
+            got = ((masks[s] & bit) != 0).float().unsqueeze(1)
+            flips = int((got != aux[name][s]).sum())
+            assert flips == 0, (name, s, flips)     # the emulator runs without fma contraction: bit-exact masks
+    for i, k in enumerate(keys):
+        assert loss_rel_err(el[i], loss[k]) < LOSS_RTOL, k
+    for l in range(S):
+        assert rel_err(egf[l], ff[l].grad) < GRAD_RTOL, ("fwd", l)
+        assert rel_err(egb[l], fb[l].grad) < GRAD_RTOL * 1.5, ("bwd", l)

@@ -11,6 +11,7 @@ from typing import Optional
 
 MAX_LEVELS = 6
 FLOW_NSTATS = 12
+GEOM_NSTATS = 16
 FLOW_BASIS_PLANES = 14
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -57,6 +58,18 @@ class UglDepthPhotoArgs(C.Structure):
         ("loss", C.c_void_p), ("den", C.c_void_p), ("grad_loss", C.c_void_p),
         ("grad_disp", _L), ("grad_P", _L2),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("stream", C.c_void_p),
+        ("ext_bytes", _L), ("ext_need", C.c_int32 * 2),
+    ]
+
+
+class UglGeomFlowArgs(C.Structure):
+    """Mirror of ``struct UglGeomFlowArgs`` (include/ugl.h)."""
+
+    _L = C.c_void_p * MAX_LEVELS
+    _fields_ = [
+        ("flow", UglFlowLossArgs),
+        ("disp", _L), ("Kinv", _L), ("P_bwd", _L), ("P_fwd", _L), ("mask_bytes", _L),
+        ("alpha", C.c_float), ("beta", C.c_float),
     ]
 
 
@@ -68,6 +81,8 @@ SIGNATURES = {
     "ugl_flow_loss_forward": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_backward": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_launches": (C.c_int, [C.c_int]),
+    "ugl_geom_flow_forward_grad": (C.c_int, [C.POINTER(UglGeomFlowArgs)]),
+    "ugl_geom_flow_combine": (C.c_int, [C.POINTER(UglGeomFlowArgs)]),
     "ugl_flow_loss_forward_grad": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_combine": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_image_pyramid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

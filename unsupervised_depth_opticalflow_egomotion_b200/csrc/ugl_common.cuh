@@ -271,6 +271,15 @@ UGL_HD void ssim_backward_coeffs(const Moments& m, float& cA, float& cB, float& 
   ssim_partials(t, g, ax, bx, cA, cB, cC);
 }
 
+// ---- dynamic mask (model_geometry.py:698-707): n(x) = sqrt(x0^2 + x1^2) + 1e-12 ; dyn = [n(|rf-f|)^2 < alpha (n(f)^2 + n(rf)^2) + beta]
+UGL_HD float norm2_eps(float u, float v) { return add_rn(sqrt_rn(add_rn(mul_rn(u, u), mul_rn(v, v))), 1e-12f); }
+UGL_HD float dynamic_mask_value(float fu, float fv, float ru, float rv, float alpha, float beta) {
+  const float nf = norm2_eps(fu, fv), nr = norm2_eps(ru, rv);
+  const float bound = add_rn(mul_rn(alpha, add_rn(mul_rn(nf, nf), mul_rn(nr, nr))), beta);
+  const float nd = norm2_eps(fabsf(sub_rn(ru, fu)), fabsf(sub_rn(rv, fv)));
+  return mul_rn(nd, nd) < bound ? 1.f : 0.f;
+}
+
 // ---- soft / hard occlusion weights (model_flow.py:105-138, model_geometry.py:105-132) ----------
 // wgt = 1 - softmax([d_l, d_r]) evaluated like ATen's softmax: exp(x - max) / sum.
 UGL_HD void one_minus_softmax2(float d_l, float d_r, float& wl, float& wr) {

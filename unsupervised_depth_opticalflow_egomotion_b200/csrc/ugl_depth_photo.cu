@@ -22,6 +22,8 @@ struct DepthPhotoLevel {
   const float* Kinv;           // (B,3,3)
   const float* P[2];           // (B,3,4)
   const float* ext_mask[2];    // (B,1,h,w) or null: mask from the flow branch (geom mode) instead of the reprojection valid
+  const unsigned char* ext_bytes;  // (B,h,w) or null: packed masks of ugl_geom_flow_forward_grad; base = all ext_need[dir] bits set
+  unsigned ext_need[2];
   float* valid_out[2];         // optional (B,1,h,w)
   float* tex_out[2];           // optional (B,1,h,w)
   float* grad_disp;            // (B,1,h,w)   [backward]
@@ -67,7 +69,9 @@ __device__ __forceinline__ void depth_pixel(const DepthPhotoLevel& L, const floa
   }
   const float r3 = 1.0f / 3.0f;
   const float tex = div_c(a, 3.0f, r3) < div_c(s, 3.0f, r3) ? 1.f : 0.f;
-  const float base = L.ext_mask[dir] ? L.ext_mask[dir][(long)b * plane + p] : valid;
+  float base = valid;
+  if (L.ext_bytes) base = ((unsigned)L.ext_bytes[(long)b * plane + p] & L.ext_need[dir]) == L.ext_need[dir] ? 1.f : 0.f;
+  else if (L.ext_mask[dir]) base = L.ext_mask[dir][(long)b * plane + p];
   o.mask = mul_rn(base, tex);
   if (!kGrad) {
     if (L.valid_out[dir]) L.valid_out[dir][(long)b * plane + p] = valid;
@@ -201,6 +205,7 @@ static int depth_photo_fill(const UglDepthPhotoArgs* a, bool backward, DepthPhot
     L.h = a->height[l]; L.w = a->width[l];
     if (L.h < 2 || L.w < 2) return fail(UGL_EUNSUPPORTED, "depth_photo: level %d is %dx%d", l, L.h, L.w);
     L.img = a->img[l]; L.disp = a->disp[l]; L.Kinv = a->Kinv[l];
+    L.ext_bytes = a->ext_bytes[l]; L.ext_need[0] = (unsigned)a->ext_need[0]; L.ext_need[1] = (unsigned)a->ext_need[1];
     if (!L.img || !L.disp || !L.Kinv) return fail(UGL_EINVAL, "depth_photo: null input at level %d", l);
     for (int d = 0; d < 2; ++d) {
       L.src_area[d] = a->src_area[d][l]; L.src_bil[d] = a->src_bil[d][l]; L.P[d] = a->P[d][l];

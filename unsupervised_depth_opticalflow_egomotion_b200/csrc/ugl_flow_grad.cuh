@@ -16,6 +16,7 @@
 #pragma once
 
 #include "ugl_flow_loss.cuh"
+#include "ugl_geometry.cuh"
 
 namespace ugl {
 
@@ -96,7 +97,8 @@ UGL_HD DirectLoads load_direct(const FlowLevelDesc& L, const TileCoord& tc, int 
   return d;
 }
 
-template <bool kGrad>
+// kGeom = false: Model_flow weights (soft, model_flow.py:105-138); true: Model_geometry (hard occlusion * valid, model_geometry.py:105-132, 857-858)
+template <bool kGrad, bool kGeom>
 UGL_HD void flow_photo_pixel_c(const FlowLevelDesc& L, int b, int i, int j, const DirectLoads& d, Photo& P, float* dW) {
   const int plane = L.h * L.w, W = L.w;
   const float* ir = L.img_r + (long)b * 3 * plane;
@@ -128,8 +130,16 @@ UGL_HD void flow_photo_pixel_c(const FlowLevelDesc& L, int b, int i, int j, cons
   P.d_b = mean3_abs_diff(P.I, P.Wb);
   float wl, wr;
   one_minus_softmax2(P.d_b, P.d_f, wl, wr);
-  P.w_b = soft_occ_weight(wl) * valid_b;
-  P.w_f = soft_occ_weight(wr) * valid_f;
+  if (kGeom) {
+    P.occ_b = wl > 0.48f ? 1.f : 0.f;
+    P.occ_f = wr > 0.48f ? 1.f : 0.f;
+    P.valid_b = valid_b; P.valid_f = valid_f;
+    P.w_b = valid_b * P.occ_b;
+    P.w_f = valid_f * P.occ_f;
+  } else {
+    P.w_b = soft_occ_weight(wl) * valid_b;
+    P.w_f = soft_occ_weight(wr) * valid_f;
+  }
 }
 
 // shared-memory planes of the single-pass kernel (halo-2 tile).  x = I*w and y = W*w are stored pre-multiplied per
@@ -159,13 +169,24 @@ UGL_HD void store_grad_planes(float* sm, int idx, const Photo& P, float uf, floa
 struct FlowGradParams {
   FlowLossParams base;
   float* basis[kMaxLevels];   // (B, 14, h, w) per level
+  // geom mode only (Model_geometry): in-kernel rigid flow -> dynamic mask, packed masks out
+  const float* disp[kMaxLevels];          // (B,1,h,w) centre disparity
+  const float* Kinv[kMaxLevels];          // (B,3,3)
+  const float* P[2][kMaxLevels];          // (B,3,4): 0 = centre->left (bwd flow), 1 = centre->right (fwd flow)
+  unsigned char* mask_bytes[kMaxLevels];  // (B,h,w): bit0 valid_b, bit1 valid_f, bit2 occ_b, bit3 occ_f, bit4 dyn_b, bit5 dyn_f
+  float alpha, beta;                      // flow_consist_alpha / beta
 };
+
+// geom mode splits the L1 term by the dynamic mask (weights 1 and 2, model_geometry.py:905-908): four more accumulators
+enum GeomAcc { GA_PIXD_F = FA_COUNT, GA_WD_F, GA_PIXD_B, GA_WD_B, GA_COUNT };
+constexpr unsigned kMaskValidB = 1u, kMaskValidF = 2u, kMaskOccB = 4u, kMaskOccF = 8u, kMaskDynB = 16u, kMaskDynF = 32u;
 
 // ================================================================================================
 // the single-pass stencil kernel's tile logic
 // ================================================================================================
-template <int TW, int TH, int NT>
+template <int TW, int TH, int NT, bool kGeom = false>
 struct FlowGradTile {
+  static constexpr int kAcc = kGeom ? (int)GA_COUNT : (int)FA_COUNT;
   static_assert(TW % 2 == 0, "1x2 micro-tiles need an even tile width");
   static constexpr int R = 2;
   static constexpr int PW = TW + 2 * R, PH = TH + 2 * R, PN = PW * PH;   // photometry planes (halo 2)
@@ -179,7 +200,8 @@ struct FlowGradTile {
 
   // phase 1: photometry on the halo-2 tile; interior pixels also: L1/weight/consistency sums, warp Jacobians,
   // L1 sign sums (shared memory) and the consistency basis (global)
-  static UGL_HD void phase1(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, float* sm, float* acc) {
+  // mats (geom mode): K^-1 (9) then P_bwd (12), P_fwd (12) of this sample and level
+  static UGL_HD void phase1(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, float* sm, float* acc, const float* mats = nullptr) {
     const FlowLossParams& p = gp.base;
     const FlowLevelDesc& L = p.lv[tc.level];
     const int plane = L.h * L.w;
@@ -200,7 +222,7 @@ struct FlowGradTile {
         // one uniform code path for interior and halo pixels (a warp straddling both would otherwise execute the
         // gradient and the non-gradient variant back to back, and the second copy doubles the I-cache footprint)
         float dW[12];
-        flow_photo_pixel_c<true>(L, tc.b, i, j, cur, P, dW);
+        flow_photo_pixel_c<true, kGeom>(L, tc.b, i, j, cur, P, dW);
         if (interior) {
           const int t = (ly - R) * TW + (lx - R);
           float* o = sm + kOffDW + t;
@@ -218,15 +240,33 @@ struct FlowGradTile {
             o[(12 + 2 * dir) * TN] = su;
             o[(13 + 2 * dir) * TN] = sv;
           }
-          acc[FA_PIX_F] += P.d_f * P.w_f;
-          acc[FA_W_F] += P.w_f;
-          acc[FA_PIX_B] += P.d_b * P.w_b;
-          acc[FA_W_B] += P.w_b;
+          float om;   // mask of the direction-consistency term: 1 - w_f (flow mode) / 1 - occ_f (geom mode)
+          if (kGeom) {
+            // rigid flow of the centre disparity under both poses -> dynamic masks; L1 split into rigid / dynamic parts
+            const float D = gp.disp[tc.level][(long)tc.b * plane + pix];
+            const Projected qb = project_pixel(mats, mats + 9, D, j, i), qf = project_pixel(mats, mats + 21, D, j, i);
+            const float dyn_b = dynamic_mask_value(ub, vb, sub_rn(qb.u, (float)j), sub_rn(qb.v, (float)i), gp.alpha, gp.beta);
+            const float dyn_f = dynamic_mask_value(uf, vf, sub_rn(qf.u, (float)j), sub_rn(qf.v, (float)i), gp.alpha, gp.beta);
+            acc[FA_PIX_F] += P.d_f * (P.w_f * dyn_f);           acc[FA_W_F] += P.w_f * dyn_f;
+            acc[GA_PIXD_F] += P.d_f * (P.w_f * (1.f - dyn_f));  acc[GA_WD_F] += P.w_f * (1.f - dyn_f);
+            acc[FA_PIX_B] += P.d_b * (P.w_b * dyn_b);           acc[FA_W_B] += P.w_b * dyn_b;
+            acc[GA_PIXD_B] += P.d_b * (P.w_b * (1.f - dyn_b));  acc[GA_WD_B] += P.w_b * (1.f - dyn_b);
+            const unsigned bits = (P.valid_b != 0.f ? kMaskValidB : 0u) | (P.valid_f != 0.f ? kMaskValidF : 0u) |
+                                  (P.occ_b != 0.f ? kMaskOccB : 0u) | (P.occ_f != 0.f ? kMaskOccF : 0u) |
+                                  (dyn_b != 0.f ? kMaskDynB : 0u) | (dyn_f != 0.f ? kMaskDynF : 0u);
+            gp.mask_bytes[tc.level][(long)tc.b * plane + pix] = (unsigned char)bits;
+            om = 1.0f - P.occ_f;
+          } else {
+            acc[FA_PIX_F] += P.d_f * P.w_f;
+            acc[FA_W_F] += P.w_f;
+            acc[FA_PIX_B] += P.d_b * P.w_b;
+            acc[FA_W_B] += P.w_b;
+            om = 1.0f - P.w_f;
+          }
           // direction consistency: value and un-normalised gradient w.r.t. the forward flow
           const float rf = sqrt_rn(uf * uf + vf * vf), rb = sqrt_rn(ub * ub + vb * vb);
           const float inf_ = fast_div(1.0f, rf + 1e-12f), inb_ = fast_div(1.0f, rb + 1e-12f);
           const float cu = uf * inf_ + ub * inb_, cv = vf * inf_ + vb * inb_;
-          const float om = 1.0f - P.w_f;
           acc[FA_CONS] += (fabsf(cu) + fabsf(cv)) * om;
           acc[FA_CONS_W] += om;
           const float su = sgnf(cu) * om, sv = sgnf(cv) * om;
@@ -439,6 +479,49 @@ struct FlowGradTile {
     }
   }
 };
+
+// ---- geom mode closing formulas (model_geometry.py:905-919): out = flow_pixel, flow_ssim, flow_smooth, flow_consis of one level
+UGL_HD void geom_level_losses(const float* S, int h, int w, float* out) {
+  const float hw = (float)h * (float)w;
+  const float den_rf = S[FA_W_F] / hw + 1e-12f, den_df = S[GA_WD_F] / hw + 1e-12f;
+  const float den_rb = S[FA_W_B] / hw + 1e-12f, den_db = S[GA_WD_B] / hw + 1e-12f;
+  const float den_sf = (S[FA_W_F] + S[GA_WD_F]) / hw + 1e-12f, den_sb = (S[FA_W_B] + S[GA_WD_B]) / hw + 1e-12f;   // mean(valid * occ)
+  out[0] = (S[FA_PIX_B] / hw) / den_rb + (S[FA_PIX_F] / hw) / den_rf + 2.0f * ((S[GA_PIXD_B] / hw) / den_db) + 2.0f * ((S[GA_PIXD_F] / hw) / den_df);
+  out[1] = (S[FA_SSIM_B] / (3.0f * hw)) / den_sb + (S[FA_SSIM_F] / (3.0f * hw)) / den_sf;
+  const float nx = 2.0f * (float)h * (float)(w - 2), ny = 2.0f * (float)(h - 2) * (float)w;
+  out[2] = (S[FA_SMX_F] / nx + S[FA_SMY_F] / ny) * 0.5f + (S[FA_SMX_B] / nx + S[FA_SMY_B] / ny) * 0.5f;
+  out[3] = (S[FA_CONS] / (2.0f * hw)) / (S[FA_CONS_W] / hw + 1e-12f);
+}
+
+struct GeomCombineScales { float pix_r[2], pix_d[2], ssim[2], sm, cons; };   // [0] = fwd flow, [1] = bwd flow
+
+UGL_HD GeomCombineScales geom_combine_scales(const float* S, int h, int w, const float* gloss, int B, int b) {
+  GeomCombineScales k;
+  const float hw = (float)h * (float)w;
+  const float g_pix = gloss[0 * B + b], g_ssim = gloss[1 * B + b], g_sm = gloss[2 * B + b], g_cons = gloss[3 * B + b];
+  k.pix_r[0] = g_pix / hw / (S[FA_W_F] / hw + 1e-12f) / 3.0f;
+  k.pix_r[1] = g_pix / hw / (S[FA_W_B] / hw + 1e-12f) / 3.0f;
+  k.pix_d[0] = 2.0f * g_pix / hw / (S[GA_WD_F] / hw + 1e-12f) / 3.0f;
+  k.pix_d[1] = 2.0f * g_pix / hw / (S[GA_WD_B] / hw + 1e-12f) / 3.0f;
+  k.ssim[0] = g_ssim / (3.0f * hw) / ((S[FA_W_F] + S[GA_WD_F]) / hw + 1e-12f) / 9.0f;
+  k.ssim[1] = g_ssim / (3.0f * hw) / ((S[FA_W_B] + S[GA_WD_B]) / hw + 1e-12f) / 9.0f;
+  k.sm = g_sm * 0.5f / 20.0f;
+  k.cons = g_cons / (2.0f * hw) / (S[FA_CONS_W] / hw + 1e-12f);
+  return k;
+}
+
+UGL_HD void geom_combine_pixel(const float* __restrict__ basis, const unsigned char* __restrict__ mask, int plane, int pix,
+                               const GeomCombineScales& k, float* __restrict__ gf, float* __restrict__ gb) {
+  const unsigned bits = mask[pix];
+  const float kpf = (bits & kMaskDynF) ? k.pix_r[0] : k.pix_d[0], kpb = (bits & kMaskDynB) ? k.pix_r[1] : k.pix_d[1];
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    gf[ch * plane + pix] = kpf * basis[(0 + ch) * plane + pix] + k.ssim[0] * basis[(2 + ch) * plane + pix]
+                           + k.sm * basis[(4 + ch) * plane + pix] + k.cons * basis[(6 + ch) * plane + pix];
+    gb[ch * plane + pix] = kpb * basis[(8 + ch) * plane + pix] + k.ssim[1] * basis[(10 + ch) * plane + pix]
+                           + k.sm * basis[(12 + ch) * plane + pix];
+  }
+}
 
 // ---- backward = element-wise combine -----------------------------------------------------------------------------
 // grad_f = kp_f Gp_f + ks_f Gs_f + ksm Gm_f + kc Gc ;  grad_b = kp_b Gp_b + ks_b Gs_b + ksm Gm_b

@@ -34,9 +34,11 @@ __global__ void __launch_bounds__(NT) flow_loss_fwd_kernel(const __grid_constant
 // stores the level sums for backward.  The CTA that finishes a sample last (ticket counter, zeroed by a memset node
 // before the launch) adds the levels up in level order -> loss (4,B).
 constexpr int kFinThreads = 256;
+template <bool kGeom>
 __global__ void __launch_bounds__(kFinThreads)
 flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __restrict__ lvl_loss /* [B][scales][4] */,
                           unsigned* __restrict__ tickets /* [B] */) {
+  constexpr int FA_COUNT = kGeom ? (int)GA_COUNT : (int)ugl::FA_COUNT;   // geom mode carries four more sums
   __shared__ double red[kFinThreads / 32][FA_COUNT];
   __shared__ bool last;
   const int l = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -68,7 +70,7 @@ flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __res
       S[k] = (float)v;
       st[k] = S[k];
     }
-    flow_level_losses(S, L.h, L.w, out);
+    if (kGeom) geom_level_losses(S, L.h, L.w, out); else flow_level_losses(S, L.h, L.w, out);
     float* ll = lvl_loss + ((long)b * p.scales + l) * 4;
 #pragma unroll
     for (int k = 0; k < 4; ++k) ll[k] = out[k];
@@ -84,13 +86,14 @@ flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __res
   }
 }
 
+template <bool kGeom = false>
 static int launch_finalize(const FlowLossParams& p, cudaStream_t st) {
   // scratch behind the tile partials: [B][scales][4] level losses, then B ticket counters
-  float* lvl_loss = p.partials + (size_t)p.total_tiles * FA_COUNT;
+  float* lvl_loss = p.partials + (size_t)p.total_tiles * (kGeom ? (int)GA_COUNT : (int)FA_COUNT);
   unsigned* tickets = reinterpret_cast<unsigned*>(lvl_loss + (size_t)p.B * p.scales * 4);
   const cudaError_t e = cudaMemsetAsync(tickets, 0, sizeof(unsigned) * p.B, st);
   if (e != cudaSuccess) return fail((int)e, "flow_loss finalize: memset: %s", cudaGetErrorString(e));
-  flow_loss_finalize_kernel<<<dim3(p.scales, p.B), kFinThreads, 0, st>>>(p, lvl_loss, tickets);
+  flow_loss_finalize_kernel<kGeom><<<dim3(p.scales, p.B), kFinThreads, 0, st>>>(p, lvl_loss, tickets);
   return check_launch("flow_loss_finalize_kernel");
 }
 
@@ -116,17 +119,25 @@ __global__ void __launch_bounds__(NT) flow_loss_bwd_kernel(const __grid_constant
 }
 
 // single-pass: losses + gradient basis maps
-template <int TW, int TH, int NT>
+template <int TW, int TH, int NT, bool kGeom>
 __global__ void __launch_bounds__(NT, UGL_BMINB) flow_loss_fwdgrad_kernel(const __grid_constant__ FlowGradParams gp) {
   extern __shared__ __align__(16) float sm[];
+  using Tile = FlowGradTile<TW, TH, NT, kGeom>;
+  constexpr int FA_COUNT = Tile::kAcc;
   __shared__ float red[(NT / 32) * FA_COUNT];
-  using Tile = FlowGradTile<TW, TH, NT>;
+  __shared__ float mats[kGeom ? 33 : 1];   // geom mode: K^-1, P_bwd, P_fwd of this tile's sample and level
   const int tile = blockIdx.x;
   const TileCoord tc = decode_tile<TW, TH>(gp.base, tile);
+  if (kGeom) {
+    if (threadIdx.x < 9) mats[threadIdx.x] = gp.Kinv[tc.level][tc.b * 9 + threadIdx.x];
+    else if (threadIdx.x < 21) mats[threadIdx.x] = gp.P[0][tc.level][tc.b * 12 + threadIdx.x - 9];
+    else if (threadIdx.x < 33) mats[threadIdx.x] = gp.P[1][tc.level][tc.b * 12 + threadIdx.x - 21];
+    __syncthreads();
+  }
   float acc[FA_COUNT];
 #pragma unroll
   for (int k = 0; k < FA_COUNT; ++k) acc[k] = 0.f;
-  Tile::phase1(gp, tc, threadIdx.x, NT, sm, acc);
+  Tile::phase1(gp, tc, threadIdx.x, NT, sm, acc, mats);
   __syncthreads();
 #pragma unroll 1
   for (int dir = 0; dir < 2; ++dir) {          // rolled: one copy of the stencil phases in the instruction cache
@@ -143,15 +154,23 @@ __global__ void __launch_bounds__(NT, UGL_BMINB) flow_loss_fwdgrad_kernel(const 
 }
 
 // element-wise backward of the single-pass mode: grid (chunks, B, scales)
+template <bool kGeom>
 __global__ void __launch_bounds__(256) flow_combine_kernel(const __grid_constant__ FlowGradParams gp) {
   const FlowLossParams& p = gp.base;
   const int b = blockIdx.y, l = blockIdx.z;
   const FlowLevelDesc& L = p.lv[l];
   const int plane = L.h * L.w;
-  const FlowCombineScales k = flow_combine_scales(p.stats + ((long)b * p.scales + l) * FA_COUNT, L.h, L.w, p.gloss, p.B, b);
   const float* basis = gp.basis[l] + (long)b * kBasisPlanes * plane;
   float* gf = L.gflow_f + (long)b * 2 * plane;
   float* gb = L.gflow_b + (long)b * 2 * plane;
+  if (kGeom) {   // the L1 scale depends on the pixel's dynamic-mask bit
+    const GeomCombineScales kg = geom_combine_scales(p.stats + ((long)b * p.scales + l) * GA_COUNT, L.h, L.w, p.gloss, p.B, b);
+    const unsigned char* mask = gp.mask_bytes[l] + (long)b * plane;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < plane; pix += gridDim.x * blockDim.x)
+      geom_combine_pixel(basis, mask, plane, pix, kg, gf, gb);
+    return;
+  }
+  const FlowCombineScales k = flow_combine_scales(p.stats + ((long)b * p.scales + l) * FA_COUNT, L.h, L.w, p.gloss, p.B, b);
   if ((plane & 3) == 0) {   // 128-bit path (every plane start is then 16-byte aligned: torch allocations are 512-byte aligned)
     const float4* b4 = reinterpret_cast<const float4*>(basis);
     float4* gf4 = reinterpret_cast<float4*>(gf);
@@ -233,7 +252,7 @@ extern "C" uint64_t ugl_flow_loss_workspace_bytes(const UglFlowLossArgs* a) {
     tb += (uint64_t)((a->width[l] + kBTW - 1) / kBTW) * ((a->height[l] + kBTH - 1) / kBTH) * a->batch;
   }
   // tile partials + [B][scales][4] level losses + B ticket counters (finalize scratch)
-  return (tf > tb ? tf : tb) * FA_COUNT * sizeof(float) + (uint64_t)a->batch * a->scales * 4 * sizeof(float) + (uint64_t)a->batch * sizeof(unsigned);
+  return (tf > tb ? tf : tb) * GA_COUNT * sizeof(float) + (uint64_t)a->batch * a->scales * 4 * sizeof(float) + (uint64_t)a->batch * sizeof(unsigned);
 }
 
 extern "C" int ugl_flow_loss_launches(int backward) { return backward ? 1 : 2; }
@@ -272,11 +291,70 @@ extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) {
   using Tile = FlowGradTile<kBTW, kBTH, kBNT>;
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
   static_assert(smem <= 227 * 1024, "single-pass tile does not fit in shared memory");
-  auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT>;
+  auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, false>;
   if ((rc = opt_in_smem(kern, smem))) return rc;
   kern<<<gp.base.total_tiles, kBNT, smem, st>>>(gp);
   if ((rc = check_launch("flow_loss_fwdgrad_kernel"))) return rc;
   return launch_finalize(gp.base, st);
+}
+
+// ---- geom mode (Model_geometry's flow branch) -----------------------------------------------------
+static int geom_params(const UglGeomFlowArgs* g, bool backward, FlowGradParams& gp) {
+  if (!g) return fail(UGL_EINVAL, "geom_flow: null args");
+  const UglFlowLossArgs* a = &g->flow;
+  int rc = build_params<kBTW, kBTH>(a, backward, gp.base);
+  if (rc) return rc;
+  for (int l = 0; l < a->scales; ++l) {
+    if (!a->basis[l] || !g->mask_bytes[l]) return fail(UGL_EINVAL, "geom_flow: null basis / mask_bytes pointer at level %d", l);
+    if (reinterpret_cast<uintptr_t>(a->basis[l]) & 7u) return fail(UGL_EALIGN, "geom_flow: basis not 8-byte aligned");
+    gp.basis[l] = a->basis[l];
+    gp.mask_bytes[l] = g->mask_bytes[l];
+    if (!backward) {
+      const void* ptrs[4] = {g->disp[l], g->Kinv[l], g->P_bwd[l], g->P_fwd[l]};
+      for (int k = 0; k < 4; ++k) {
+        if (!ptrs[k]) return fail(UGL_EINVAL, "geom_flow: null disp / Kinv / P pointer at level %d", l);
+        if (!aligned4(ptrs[k])) return fail(UGL_EALIGN, "geom_flow: misaligned disp / Kinv / P pointer at level %d", l);
+      }
+      gp.disp[l] = g->disp[l]; gp.Kinv[l] = g->Kinv[l]; gp.P[0][l] = g->P_bwd[l]; gp.P[1][l] = g->P_fwd[l];
+    }
+  }
+  gp.alpha = g->alpha; gp.beta = g->beta;
+  return UGL_OK;
+}
+
+extern "C" int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* g) {
+  FlowGradParams gp;
+  int rc = geom_params(g, false, gp);
+  if (rc) return rc;
+  const UglFlowLossArgs* a = &g->flow;
+  if (!a->loss) return fail(UGL_EINVAL, "geom_flow_forward_grad: null loss");
+  if (!a->workspace || a->workspace_bytes < ugl_flow_loss_workspace_bytes(a))
+    return fail(UGL_EWORKSPACE, "geom_flow_forward_grad: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  using Tile = FlowGradTile<kBTW, kBTH, kBNT, true>;
+  constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
+  auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, true>;
+  if ((rc = opt_in_smem(kern, smem))) return rc;
+  kern<<<gp.base.total_tiles, kBNT, smem, st>>>(gp);
+  if ((rc = check_launch("flow_loss_fwdgrad_kernel<geom>"))) return rc;
+  return launch_finalize<true>(gp.base, st);
+}
+
+extern "C" int ugl_geom_flow_combine(const UglGeomFlowArgs* g) {
+  FlowGradParams gp;
+  int rc = geom_params(g, true, gp);
+  if (rc) return rc;
+  const UglFlowLossArgs* a = &g->flow;
+  if (!a->grad_loss) return fail(UGL_EINVAL, "geom_flow_combine: null grad_loss");
+  int max_plane = 0;
+  for (int l = 0; l < a->scales; ++l) {
+    const int pl = a->height[l] * a->width[l];
+    max_plane = pl > max_plane ? pl : max_plane;
+  }
+  int chunks = (max_plane + 256 * 4 - 1) / (256 * 4);
+  chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
+  flow_combine_kernel<true><<<dim3(chunks, gp.base.B, gp.base.scales), 256, 0, static_cast<cudaStream_t>(a->stream)>>>(gp);
+  return check_launch("flow_combine_kernel<geom>");
 }
 
 extern "C" int ugl_flow_loss_combine(const UglFlowLossArgs* a) {
@@ -293,7 +371,7 @@ extern "C" int ugl_flow_loss_combine(const UglFlowLossArgs* a) {
   }
   int chunks = (max_plane + 256 * 4 - 1) / (256 * 4);
   chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
-  flow_combine_kernel<<<dim3(chunks, gp.base.B, gp.base.scales), 256, 0, static_cast<cudaStream_t>(a->stream)>>>(gp);
+  flow_combine_kernel<false><<<dim3(chunks, gp.base.B, gp.base.scales), 256, 0, static_cast<cudaStream_t>(a->stream)>>>(gp);
   return check_launch("flow_combine_kernel");
 }
 

@@ -99,7 +99,9 @@ UGL_HD TileCoord decode_tile(const FlowLossParams& p, int tile) {
 struct Photo {
   float I[3], Wf[3], Wb[3];   // centre image, warped-from-right (fwd flow), warped-from-left (bwd flow)
   float d_f, d_b;             // mean_c |I - Wf|, mean_c |I - Wb|  (reference: img_diff_r, img_diff_l)
-  float w_f, w_b;             // soft occlusion weights * valid
+  float w_f, w_b;             // flow mode: soft occlusion weights * valid; geom mode: valid * hard occlusion mask
+  float occ_f, occ_b;         // geom mode: hard occlusion masks [1 - softmax > 0.48]
+  float valid_f, valid_b;     // geom mode: warp valid masks
 };
 
 UGL_HD float mean3_abs_diff(const float* a, const float* b) {

@@ -133,7 +133,6 @@ struct TextureMask {
 // ================================================================================================
 // dynamic mask (M6) : n(x) = sqrt(x0^2 + x1^2) + 1e-12 ; dyn = [n(fd)^2 < alpha (n(f)^2 + n(rf)^2) + beta]
 // ================================================================================================
-__device__ __forceinline__ float norm2_eps(float u, float v) { return add_rn(sqrt_rn(add_rn(mul_rn(u, u), mul_rn(v, v))), 1e-12f); }
 
 struct DynamicMask {
   const float *flow, *rflow;

@@ -185,6 +185,31 @@ class DepthLoss(_LossBase):
         return loss, masks
 
 
+class GeomMasks(dict):
+    """``mask_pack`` of the fused geom path (model_geometry.py:871-880): the float maps the kernels wrote are plain dict
+    entries; the flow-branch masks (``occ_b/f, valid_b/f, dyn_b/f, fwd_mask, bwd_mask, rigid_f, inlier_f``) are unpacked from
+    the packed byte maps only when asked for — the training step never reads them."""
+
+    _BITS = dict(valid_b=ops.MASK_VALID_BWD, valid_f=ops.MASK_VALID_FWD, occ_b=ops.MASK_OCC_BWD, occ_f=ops.MASK_OCC_FWD,
+                 dyn_b=ops.MASK_DYN_BWD, dyn_f=ops.MASK_DYN_FWD, bwd_mask=ops.MASK_ALL_BWD, fwd_mask=ops.MASK_ALL_FWD)
+
+    def __init__(self, mask_bytes, maps, owner):
+        super().__init__(maps)
+        self.mask_bytes, self._owner = mask_bytes, owner
+
+    def __missing__(self, key):
+        if key in self._BITS:
+            val = [ops.unpack_mask(m, self._BITS[key]) for m in self.mask_bytes]
+        elif key in ("rigid_f", "inlier_f"):
+            rigid, inlier, _ = self._owner.get_rigid_mask(self["dist_f"])
+            self["rigid_f"], self["inlier_f"] = rigid, inlier
+            return self[key]
+        else:
+            raise KeyError(key)
+        self[key] = val
+        return val
+
+
 class GeometryLoss(_LossBase):
     """Loss methods of ``Model_geometry`` (model_geometry.py)."""
 
@@ -258,6 +283,36 @@ class GeometryLoss(_LossBase):
         """model_geometry.py:757-765 (``invert_second`` fuses the ``[1-mask for mask in ...]`` of :863-864)"""
         return [ops.mask_product([valid_mask[s], occ_mask[s]], [False, invert_second]) for s in range(self.num_scales)]
 
+    def _forward_losses_fused(self, img, img_l, img_r, pc, pl, pr, flows_fwd, flows_bwd, disp_list, disp_l_list, disp_r_list,
+                              pose_fwd, pose_bwd, K, K_inv, Kinv, P_b, P_f):
+        """Two stencil kernels carry the loss loop: the geom-mode single-pass flow kernel (warps, every mask, the four flow
+        terms; masks leave as one packed byte map per level) and the reprojection-photometric kernel (reads the byte maps).
+        The level-0 point-wise terms (depth-flow consistency, epipolar) and the disparity smoothness stay on their ops."""
+        S = self.num_scales
+        flow4, mbytes = ops.geom_flow_loss(pl, pc, pr, list(flows_fwd), list(flows_bwd), list(disp_list[:S]), Kinv, P_b, P_f,
+                                           self.flow_consist_alpha, self.flow_consist_beta, S)
+        area = (ops.image_pyramid(img_l, S, "area"), ops.image_pyramid(img_r, S, "area"))
+        depth_pixel, (val_l, val_r), (tex_b, tex_f) = ops.depth_photo_loss(
+            pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f), ext_bytes=mbytes, ext_need=(ops.MASK_ALL_BWD, ops.MASK_ALL_FWD))
+        # level 0: |rigid flow - flow| under valid * occ * dyn (:921-923), epipolar distance mean (:925-935)
+        fd_b, _, _ = ops.dynamic_mask(flows_bwd[0], ops.rigid_flow(disp_list[0], Kinv[0], P_b[0]), self.flow_consist_alpha, self.flow_consist_beta)
+        fd_f, _, _ = ops.dynamic_mask(flows_fwd[0], ops.rigid_flow(disp_list[0], Kinv[0], P_f[0]), self.flow_consist_alpha, self.flow_consist_beta)
+        bwd0, fwd0 = ops.unpack_mask(mbytes[0], ops.MASK_ALL_BWD), ops.unpack_mask(mbytes[0], ops.MASK_ALL_FWD)
+        dist_b = self.compute_epipolar_map(pose_bwd, flows_bwd[0], K, K_inv)
+        dist_f = self.compute_epipolar_map(pose_fwd, flows_fwd[0], K, K_inv)
+        loss = {
+            "loss_depth_pixel": depth_pixel,
+            "loss_depth_ssim": _zeros2(img),
+            "loss_depth_smooth": self.compute_smooth_loss(img, disp_list) + self.compute_smooth_loss(img_l, disp_l_list)
+                                 + self.compute_smooth_loss(img_r, disp_r_list),
+            "loss_depth_consis": _zeros2(img),
+            "loss_flow_pixel": flow4[0], "loss_flow_ssim": flow4[1], "loss_flow_smooth": flow4[2], "loss_flow_consis": flow4[3],
+            "loss_depth_flow_consis": ops.masked_mean(fd_b, bwd0) + ops.masked_mean(fd_f, fwd0),
+            "loss_epipolar": self.compute_epipolar_loss(dist_b, None) + self.compute_epipolar_loss(dist_f, None),
+            "loss_triangle": _zeros2(img), "loss_pnp": _zeros2(img), "loss_eight_point": _zeros2(img),
+        }
+        return loss, GeomMasks(mbytes, dict(tex_b=tex_b, tex_f=tex_f, val_l=val_l, val_r=val_r, dist_b=dist_b, dist_f=dist_f), self)
+
     def forward_losses(self, img_l, img, img_r, optical_flows_fwd, optical_flows_bwd, disp_list, disp_l_list, disp_r_list,
                        pose_vectors, K, K_inv, fused: bool = True) -> Tuple[Dict[str, Tensor], Dict]:
         """Loss body of ``Model_geometry.forward`` (model_geometry.py:777-951) given the network outputs.
@@ -267,11 +322,14 @@ class GeometryLoss(_LossBase):
         pc, pl, pr = (self.generate_img_pyramid(x, S) for x in (img, img_l, img_r))
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
         Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
-        if not fused:
-            rec_l, val_l, _, _ = self._reconstruction_with(img_l, disp_list, disp_l_list, Kinv, P_b)
-            rec_r, val_r, _, _ = self._reconstruction_with(img_r, disp_list, disp_r_list, Kinv, P_f)
-            tex_b = self.compute_texture_mask(pc, rec_l, pl)
-            tex_f = self.compute_texture_mask(pc, rec_r, pr)
+        if fused:
+            return self._forward_losses_fused(img, img_l, img_r, pc, pl, pr, optical_flows_fwd, optical_flows_bwd, disp_list, disp_l_list,
+                                              disp_r_list, pose_fwd, pose_bwd, K, K_inv, Kinv, P_b, P_f)
+        # composed path: one kernel per reference method (kept as the cross-check of the fused kernels)
+        rec_l, val_l, _, _ = self._reconstruction_with(img_l, disp_list, disp_l_list, Kinv, P_b)
+        rec_r, val_r, _, _ = self._reconstruction_with(img_r, disp_list, disp_r_list, Kinv, P_f)
+        tex_b = self.compute_texture_mask(pc, rec_l, pl)
+        tex_f = self.compute_texture_mask(pc, rec_r, pr)
         from_l = self.warp_flow_pyramid(pl, optical_flows_bwd)
         from_r = self.warp_flow_pyramid(pr, optical_flows_fwd)
         occ_b, occ_f, valid_b, valid_f = self.compute_occ_weight(from_l, pc, from_r)
@@ -283,13 +341,8 @@ class GeometryLoss(_LossBase):
 
         fwd_mask = self.fusion_mask(valid_f, occ_f, dyn_f)
         bwd_mask = self.fusion_mask(valid_b, occ_b, dyn_b)
-        if fused:   # reprojection + texture mask + (flow-branch mask * texture) + L1, both directions, all levels: one kernel
-            area = (ops.image_pyramid(img_l, S, "area"), ops.image_pyramid(img_r, S, "area"))
-            depth_pixel, (val_l, val_r), (tex_b, tex_f) = ops.depth_photo_loss(pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f),
-                                                                                 ext_mask=(bwd_mask, fwd_mask))
-        else:
-            fwd_mask_tex = self.fusion_mask_2item(fwd_mask, tex_f)
-            bwd_mask_tex = self.fusion_mask_2item(bwd_mask, tex_b)
+        fwd_mask_tex = self.fusion_mask_2item(fwd_mask, tex_f)
+        bwd_mask_tex = self.fusion_mask_2item(bwd_mask, tex_b)
         fwd_vo = self.fusion_mask_2item(valid_f, occ_f)
         bwd_vo = self.fusion_mask_2item(valid_b, occ_b)
         fwd_vo_rigid = self.fusion_mask_2item(fwd_vo, dyn_f)
@@ -299,7 +352,7 @@ class GeometryLoss(_LossBase):
 
         P = self.compute_photometric_loss
         loss = {
-            "loss_depth_pixel": depth_pixel if fused else P(pc, rec_l, bwd_mask_tex) + P(pc, rec_r, fwd_mask_tex),
+            "loss_depth_pixel": P(pc, rec_l, bwd_mask_tex) + P(pc, rec_r, fwd_mask_tex),
             "loss_depth_ssim": _zeros2(img),
             "loss_depth_smooth": self.compute_smooth_loss(img, disp_list) + self.compute_smooth_loss(img_l, disp_l_list)
                                  + self.compute_smooth_loss(img_r, disp_r_list),
@@ -315,5 +368,6 @@ class GeometryLoss(_LossBase):
             "loss_triangle": _zeros2(img), "loss_pnp": _zeros2(img), "loss_eight_point": _zeros2(img),
         }
         masks = dict(occ_b=occ_b, occ_f=occ_f, valid_b=valid_b, valid_f=valid_f, dyn_b=dyn_b, dyn_f=dyn_f, tex_b=tex_b, tex_f=tex_f,
-                     val_l=val_l, val_r=val_r, dist_b=dist_b, dist_f=dist_f, rigid_f=rigid_f, inlier_f=inlier_f, fwd_mask=fwd_mask)
+                     val_l=val_l, val_r=val_r, dist_b=dist_b, dist_f=dist_f, rigid_f=rigid_f, inlier_f=inlier_f, fwd_mask=fwd_mask,
+                     bwd_mask=bwd_mask)
         return loss, masks

@@ -37,6 +37,12 @@ def _dev(t: Tensor, name: str) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _dev_u8(t: Tensor, name: str) -> Tensor:
+    if not isinstance(t, Tensor) or not t.is_cuda or t.dtype != torch.uint8 or not t.is_contiguous():
+        raise TypeError("%s must be a contiguous CUDA uint8 tensor" % name)
+    return t
+
+
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -255,6 +261,102 @@ def flow_loss(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r_pyr:
     if as_matrix:
         return loss
     return {k: loss[i] for i, k in enumerate(FLOW_LOSS_KEYS)}
+
+
+# ================================================================================================
+# flow branch of the geom-mode loss (same single-pass kernel, Model_geometry's masks)
+# ================================================================================================
+MASK_VALID_BWD, MASK_VALID_FWD, MASK_OCC_BWD, MASK_OCC_FWD, MASK_DYN_BWD, MASK_DYN_FWD = 1, 2, 4, 8, 16, 32
+MASK_ALL_BWD = MASK_VALID_BWD | MASK_OCC_BWD | MASK_DYN_BWD    # model_geometry.py:857
+MASK_ALL_FWD = MASK_VALID_FWD | MASK_OCC_FWD | MASK_DYN_FWD    # model_geometry.py:858
+
+
+def _geom_args(S, L, img_l, img, img_r, ff, fb, disp, Kinv, P_b, P_f, masks, alpha, beta, loss, stats, ws, basis, gloss=None, gf=None,
+               gb=None) -> _cabi.UglGeomFlowArgs:
+    g = _cabi.UglGeomFlowArgs()
+    g.flow = _flow_args(img_l, img, img_r, ff, fb, S, loss, stats, ws, gloss, gf, gb, basis=basis)
+    for l in range(S):
+        g.disp[l], g.Kinv[l], g.P_bwd[l], g.P_fwd[l] = disp[l].data_ptr(), Kinv[l].data_ptr(), P_b[l].data_ptr(), P_f[l].data_ptr()
+        g.mask_bytes[l] = masks[l].data_ptr()
+    g.alpha, g.beta = float(alpha), float(beta)
+    return g
+
+
+class _GeomFlowLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, S: int, L: int, alpha: float, beta: float, *ts: Tensor):
+        ts = tuple(_dev(t, "input %d" % i) for i, t in enumerate(ts))
+        img_l, img, img_r, ff, fb = (ts[k * L:(k + 1) * L] for k in range(5))
+        disp, Kinv, P_b, P_f = (ts[5 * L + k * S:5 * L + (k + 1) * S] for k in range(4))
+        B, dev = img[0].shape[0], img[0].device
+        for l in range(S):
+            h, w = img[l].shape[2], img[l].shape[3]
+            for name, t, shp in (("img_l", img_l[l], (B, 3, h, w)), ("img_r", img_r[l], (B, 3, h, w)), ("flow_fwd", ff[l], (B, 2, h, w)),
+                                 ("flow_bwd", fb[l], (B, 2, h, w)), ("disp", disp[l], (B, 1, h, w)), ("Kinv", Kinv[l], (B, 3, 3)),
+                                 ("P_bwd", P_b[l], (B, 3, 4)), ("P_fwd", P_f[l], (B, 3, 4))):
+                if tuple(t.shape) != shp:
+                    raise ValueError("geom_flow_loss: %s[%d] has shape %s, expected %s" % (name, l, tuple(t.shape), shp))
+        loss = torch.empty((4, B), device=dev, dtype=torch.float32)
+        stats = torch.empty((B, S, _cabi.GEOM_NSTATS), device=dev, dtype=torch.float32)
+        basis = _alloc_basis(ff, S)
+        masks = [torch.empty((B,) + tuple(img[l].shape[2:]), device=dev, dtype=torch.uint8) for l in range(S)]
+        g = _geom_args(S, L, img_l, img, img_r, ff, fb, disp, Kinv, P_b, P_f, masks, alpha, beta, loss, stats, None, basis)
+        ws = torch.empty(max(int(_cabi.lib().ugl_flow_loss_workspace_bytes(C.byref(g.flow))) // 4, 1), device=dev, dtype=torch.float32)
+        g.flow.workspace, g.flow.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+        with torch.cuda.device_of(img[0]):
+            _call("ugl_geom_flow_forward_grad", C.byref(g), launches=2)
+        ctx.save_for_backward(stats, *ts, *basis, *masks)
+        ctx.S, ctx.L, ctx.ab = S, L, (alpha, beta)
+        ctx.mark_non_differentiable(*masks)
+        ctx.set_materialize_grads(False)
+        return (loss, *masks)
+
+    @staticmethod
+    def backward(ctx, gloss, *unused):
+        stats, *rest = ctx.saved_tensors
+        S, L = ctx.S, ctx.L
+        n_in = 5 * L + 4 * S
+        if gloss is None:
+            return (None,) * (4 + n_in)
+        ts, basis, masks = rest[:n_in], rest[n_in:n_in + S], rest[n_in + S:]
+        img_l, img, img_r, ff, fb = (ts[k * L:(k + 1) * L] for k in range(5))
+        disp, Kinv, P_b, P_f = (ts[5 * L + k * S:5 * L + (k + 1) * S] for k in range(4))
+        gloss = _dev(gloss, "grad_loss")
+        gf = [torch.empty_like(ff[l]) for l in range(S)]
+        gb = [torch.empty_like(fb[l]) for l in range(S)]
+        g = _geom_args(S, L, img_l, img, img_r, ff, fb, disp, Kinv, P_b, P_f, masks, *ctx.ab, None, stats, None, basis, gloss, gf, gb)
+        with torch.cuda.device_of(gloss):
+            _call("ugl_geom_flow_combine", C.byref(g))
+        none_l, pad, none_s = [None] * L, [None] * (L - S), [None] * S
+        return (None, None, None, None, *none_l, *none_l, *none_l, *gf, *pad, *gb, *pad, *none_s, *none_s, *none_s, *none_s)
+
+
+def geom_flow_loss(img_l_pyr, img_pyr, img_r_pyr, flows_fwd, flows_bwd, disps, Kinv, P_bwd, P_fwd, alpha: float, beta: float,
+                   num_scales: Optional[int] = None):
+    """Flow branch of ``Model_geometry.forward``'s loss loop (model_geometry.py:845-919) in one stencil kernel: warps, hard
+    occlusion + valid masks, rigid flow -> dynamic mask, the L1 terms split by the dynamic mask (weights 1 / 2), masked SSIM,
+    second-order smoothness and direction consistency (mask ``1 - occ_fwd``), all ``num_scales`` levels.
+
+    Returns ``(loss (4,B), mask_bytes[S])``: rows flow_pixel, flow_ssim, flow_smooth, flow_consis; ``mask_bytes[l]`` is a
+    ``(B,h,w)`` uint8 map with the ``MASK_*`` bits (see :func:`unpack_mask`).  Differentiable w.r.t. the flows only (the
+    reference detaches every mask)."""
+    S = len(disps) if num_scales is None else int(num_scales)
+    if not (1 <= S <= _cabi.MAX_LEVELS) or min(len(x) for x in (img_l_pyr, img_pyr, img_r_pyr, flows_fwd, flows_bwd, disps, Kinv, P_bwd,
+                                                                 P_fwd)) < S:
+        raise ValueError("geom_flow_loss: every pyramid / per-scale list needs at least num_scales=%d levels" % S)
+    # only the first num_scales levels carry a loss (the flow pyramids of the reference have one more, unused here)
+    out = _GeomFlowLossFn.apply(S, S, float(alpha), float(beta), *img_l_pyr[:S], *img_pyr[:S], *img_r_pyr[:S], *flows_fwd[:S],
+                                *flows_bwd[:S], *disps[:S], *Kinv[:S], *P_bwd[:S], *P_fwd[:S])
+    return out[0], list(out[1:])
+
+
+def unpack_mask(mask_bytes: Tensor, bits: int, invert: bool = False) -> Tensor:
+    """``(B,h,w)`` packed map -> ``(B,1,h,w)`` float {0,1} mask: 1 where every bit of ``bits`` is set (plain torch; off the
+    hot path — the kernels consume the packed maps directly)."""
+    m = (mask_bytes & bits) == bits
+    if invert:
+        m = ~m
+    return m.unsqueeze(1).float()
 
 
 # ================================================================================================
@@ -745,10 +847,14 @@ def forward_splat(x: Tensor, flow: Tensor, clamp01: bool = False) -> Tensor:
 # ================================================================================================
 # fused reprojection-photometric term (depth / geom modes)
 # ================================================================================================
-def _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, loss, den, ws, valid_out=None, tex_out=None, gloss=None, gdisp=None, gP=None):
+def _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, loss, den, ws, valid_out=None, tex_out=None, gloss=None, gdisp=None, gP=None,
+                      ext_bytes=None, ext_need=(0, 0)):
     a = _cabi.UglDepthPhotoArgs()
     a.batch, a.scales = img[0].shape[0], S
+    a.ext_need[0], a.ext_need[1] = int(ext_need[0]), int(ext_need[1])
     for l in range(S):
+        if ext_bytes is not None:
+            a.ext_bytes[l] = ext_bytes[l].data_ptr()
         a.height[l], a.width[l] = img[l].shape[2], img[l].shape[3]
         a.img[l], a.disp[l], a.Kinv[l] = img[l].data_ptr(), disp[l].data_ptr(), Kinv[l].data_ptr()
         for d in range(2):
@@ -769,12 +875,15 @@ def _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, loss, den, ws, vali
 
 class _DepthPhotoFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, S, has_ext, *ts):
-        ts = [_dev(t, "input %d" % i) for i, t in enumerate(ts)]
+    def forward(ctx, S, has_ext, ext_need, *ts):
+        # has_ext: 0 none, 1 float masks (ext_b[S], ext_f[S]), 2 packed uint8 masks (bytes[S]) + ext_need
+        nb = S if has_ext == 2 else 0
+        ext_bytes = [_dev_u8(t, "ext_bytes") for t in ts[len(ts) - nb:]] if nb else None
+        ts = [_dev(t, "input %d" % i) for i, t in enumerate(ts[:len(ts) - nb])]
         # layout: img[S], area_b[S], area_f[S], bil_b[S], bil_f[S], disp[S], Kinv[S], P_b[S], P_f[S], (ext_b[S], ext_f[S])
         g = lambda k: ts[k * S:(k + 1) * S]
         img, area, bil, disp, Kinv, P = g(0), (g(1), g(2)), (g(3), g(4)), g(5), g(6), (g(7), g(8))
-        ext = (g(9), g(10)) if has_ext else None
+        ext = (g(9), g(10)) if has_ext == 1 else None
         B, dev = img[0].shape[0], img[0].device
         for l in range(S):
             h, w = img[l].shape[2:]
@@ -784,14 +893,14 @@ class _DepthPhotoFn(torch.autograd.Function):
         den = torch.empty((B, S, 2), device=dev, dtype=torch.float32)
         mk = lambda: [[torch.empty((B, 1) + tuple(img[l].shape[2:]), device=dev, dtype=torch.float32) for l in range(S)] for _ in range(2)]
         valid_out, tex_out = mk(), mk()
-        a = _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, loss, den, None, valid_out, tex_out)
+        a = _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, loss, den, None, valid_out, tex_out, ext_bytes=ext_bytes, ext_need=ext_need)
         n = int(_cabi.lib().ugl_depth_photo_workspace_bytes(C.byref(a)))
         ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
         a.workspace, a.workspace_bytes = ws.data_ptr(), _nbytes(ws)
         with torch.cuda.device_of(img[0]):
             _call("ugl_depth_photo_forward", C.byref(a), launches=2)
-        ctx.save_for_backward(den, *ts)
-        ctx.S, ctx.has_ext = S, has_ext
+        ctx.save_for_backward(den, *ts, *(ext_bytes or []))
+        ctx.S, ctx.has_ext, ctx.ext_need = S, has_ext, ext_need
         masks = [m for grp in (valid_out, tex_out) for d in grp for m in d]
         ctx.mark_non_differentiable(*masks)
         ctx.set_materialize_grads(False)
@@ -802,38 +911,48 @@ class _DepthPhotoFn(torch.autograd.Function):
         den, *ts = ctx.saved_tensors
         S = ctx.S
         if gloss is None:
-            return (None,) * (2 + len(ts))
+            return (None,) * (3 + len(ts))
+        ext_bytes = ts[len(ts) - S:] if ctx.has_ext == 2 else None
         g = lambda k: ts[k * S:(k + 1) * S]
         img, area, bil, disp, Kinv, P = g(0), (g(1), g(2)), (g(3), g(4)), g(5), g(6), (g(7), g(8))
-        ext = (g(9), g(10)) if ctx.has_ext else None
+        ext = (g(9), g(10)) if ctx.has_ext == 1 else None
         B, dev = img[0].shape[0], img[0].device
         gloss = _dev(gloss, "grad_loss")
         gdisp = [torch.empty_like(d) for d in disp]
         gP = [[torch.empty((B, 3, 4), device=dev, dtype=torch.float32) for _ in range(S)] for _ in range(2)]
-        a = _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, None, den, None, gloss=gloss, gdisp=gdisp, gP=gP)
+        a = _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, None, den, None, gloss=gloss, gdisp=gdisp, gP=gP,
+                              ext_bytes=ext_bytes, ext_need=ctx.ext_need)
         n = int(_cabi.lib().ugl_depth_photo_workspace_bytes(C.byref(a)))
         ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
         a.workspace, a.workspace_bytes = ws.data_ptr(), _nbytes(ws)
         with torch.cuda.device_of(gloss):
             _call("ugl_depth_photo_backward", C.byref(a), launches=2)
         none = [None] * S
-        out = [None, None, *none, *none, *none, *none, *none, *gdisp, *none, *gP[0], *gP[1]]
-        if ctx.has_ext:
+        out = [None, None, None, *none, *none, *none, *none, *none, *gdisp, *none, *gP[0], *gP[1]]
+        if ctx.has_ext == 1:
             out += none + none
+        elif ctx.has_ext == 2:
+            out += none
         return tuple(out)
 
 
-def depth_photo_loss(img_pyr, src_area, src_bil, disps, Kinv, P, ext_mask=None):
+def depth_photo_loss(img_pyr, src_area, src_bil, disps, Kinv, P, ext_mask=None, ext_bytes=None, ext_need=(0, 0)):
     """Fused ``loss_depth_pixel`` of the depth / geom modes (reconstruction + texture mask + mask fusion +
     ``compute_photometric_loss`` for both directions and all ``len(disps)`` levels).
 
     ``src_area`` / ``src_bil`` / ``P`` / ``ext_mask`` are pairs ``(left|bwd, right|fwd)`` of per-level lists.  Returns
-    ``(loss (B,), valid[2][S], tex[2][S])``; the loss is differentiable w.r.t. ``disps`` and ``P``."""
+    ``(loss (B,), valid[2][S], tex[2][S])``; the loss is differentiable w.r.t. ``disps`` and ``P``.
+    ``ext_bytes`` (per-level uint8 maps of :func:`geom_flow_loss`) + ``ext_need`` (bit pattern per direction) replace
+    ``ext_mask`` without unpacking the masks to float maps."""
     S = len(disps)
     flat = [*img_pyr[:S], *src_area[0][:S], *src_area[1][:S], *src_bil[0][:S], *src_bil[1][:S], *disps, *Kinv[:S], *P[0][:S], *P[1][:S]]
+    if ext_mask is not None and ext_bytes is not None:
+        raise ValueError("depth_photo_loss: give ext_mask or ext_bytes, not both")
     if ext_mask is not None:
         flat += [*ext_mask[0][:S], *ext_mask[1][:S]]
-    out = _DepthPhotoFn.apply(S, ext_mask is not None, *flat)
+    if ext_bytes is not None:
+        flat += [*ext_bytes[:S]]
+    out = _DepthPhotoFn.apply(S, 1 if ext_mask is not None else (2 if ext_bytes is not None else 0), tuple(ext_need), *flat)
     loss, masks = out[0], out[1:]
     valid = [list(masks[0:S]), list(masks[S:2 * S])]
     tex = [list(masks[2 * S:3 * S]), list(masks[3 * S:4 * S])]
