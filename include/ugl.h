@@ -222,6 +222,29 @@ int ugl_disp_smooth_backward(const float* img, const float* const* disps, const 
                              const float* grad_out, int32_t batch, int32_t height, int32_t width, float* const* grad_disps,
                              void* workspace, uint64_t workspace_bytes, void* stream);
 
+/* Single-pass form of the same term for up to UGL_DISP_SMOOTH_MAX_LISTS (image, disparity pyramid) lists at once — the
+ * three compute_smooth_loss calls of model_geometry.py:938-940 / model_depth.py:281-283 in one launch:
+ *   forward_grad: out (lists,B) and, where G[list][l] is non-NULL, G (B,1,H,W) = d out / d up_l(Y,X) at full resolution
+ *                 (un-normalised: without the upstream gradient), the image edge weights formed once per tile for all levels;
+ *   combine:      grad_disp[list][l] (B,1,h_l,w_l) = grad_out[list,b] * (bilinear up-sampling)^T G[list][l]. */
+#define UGL_DISP_SMOOTH_MAX_LISTS 3
+typedef struct UglDispSmoothArgs {
+  int32_t batch, lists, levels, height, width;
+  int32_t lheight[UGL_MAX_LEVELS], lwidth[UGL_MAX_LEVELS];
+  const float* img[UGL_DISP_SMOOTH_MAX_LISTS];                   /* (B,3,H,W)                 */
+  const float* disp[UGL_DISP_SMOOTH_MAX_LISTS][UGL_MAX_LEVELS];  /* (B,1,h_l,w_l)             */
+  float* out;                                                    /* (lists,B)                 */
+  float* G[UGL_DISP_SMOOTH_MAX_LISTS][UGL_MAX_LEVELS];           /* (B,1,H,W) or NULL         */
+  const float* grad_out;                                         /* (lists,B)      [combine]  */
+  float* grad_disp[UGL_DISP_SMOOTH_MAX_LISTS][UGL_MAX_LEVELS];   /* (B,1,h_l,w_l)  [combine]  */
+  void* workspace;
+  uint64_t workspace_bytes;
+  void* stream;
+} UglDispSmoothArgs;
+uint64_t ugl_disp_smooth_fused_workspace_bytes(const UglDispSmoothArgs* args);
+int ugl_disp_smooth_forward_grad(const UglDispSmoothArgs* args);
+int ugl_disp_smooth_combine(const UglDispSmoothArgs* args);
+
 /* ---------------------------------------------------------------------------------------------
  * inverse_warp2 (structures/inverse_warp.py:263-303 with pixel2cam :30-45 and cam2pixel2 :227-260).
  * Kinv (B,3,3) = intrinsics.inverse() and P (B,3,4) = intrinsics @ pose_vec2mat(pose) are built by the

@@ -134,12 +134,37 @@ def test_disp_smooth_vs_oracle(cuda_device, S):
     ds = [d.clone().requires_grad_(True) for d in t.disp]
     ref = P.disparity_smooth_loss(t.img, ds, S)
     rg = torch.autograd.grad((ref * go).sum(), ds)
-    dd = [d.to(cuda_device).requires_grad_(True) for d in t.disp]
-    out = ops.disp_smooth(t.img.to(cuda_device), dd)
-    og = torch.autograd.grad((out * go.to(cuda_device)).sum(), dd)
-    assert loss_rel_err(out, ref) < LOSS_RTOL
-    for a, b in zip(og, rg):
-        assert rel_err(a, b) < GRAD_RTOL
+    for mode in ("single_pass", "recompute"):
+        dd = [d.to(cuda_device).requires_grad_(True) for d in t.disp]
+        out = ops.disp_smooth(t.img.to(cuda_device), dd, mode=mode)
+        og = torch.autograd.grad((out * go.to(cuda_device)).sum(), dd)
+        assert loss_rel_err(out, ref) < LOSS_RTOL, mode
+        for a, b in zip(og, rg):
+            assert rel_err(a, b) < GRAD_RTOL, mode
+
+
+@pytest.mark.parametrize("H,W,S", [(64, 208, 3), (48, 80, 4), (34, 50, 2)])
+def test_disp_smooth_three_lists_one_launch(cuda_device, H, W, S):
+    """ops.disp_smooth_multi: the centre / left / right compute_smooth_loss calls in one launch; sizes that do not fill a tile"""
+    t = make_triplet(2, H, W, 1, S, seed=35)
+    imgs, lists = (t.img, t.img_l, t.img_r), (t.disp, t.disp_l, t.disp_r)
+    go = torch.tensor([[0.6, 1.4], [1.1, 0.3], [0.8, 0.9]])
+    refs, rgs = [], []
+    for i in range(3):
+        ds = [d.clone().requires_grad_(True) for d in lists[i]]
+        r = P.disparity_smooth_loss(imgs[i], ds, S)
+        refs.append(r)
+        rgs.append(torch.autograd.grad((r * go[i]).sum(), ds))
+    dd = [[d.to(cuda_device).requires_grad_(True) for d in lists[i]] for i in range(3)]
+    out = ops.disp_smooth_multi([x.to(cuda_device) for x in imgs], dd)
+    og = torch.autograd.grad((out * go.to(cuda_device)).sum(), [d for row in dd for d in row])
+    for i in range(3):
+        assert loss_rel_err(out[i], refs[i]) < LOSS_RTOL, i
+        for l in range(S):
+            assert rel_err(og[i * S + l], rgs[i][l]) < GRAD_RTOL, (i, l)
+    # forward only (no gradient requested): no G maps are written
+    out2 = ops.disp_smooth_multi([x.to(cuda_device) for x in imgs], [[d.detach() for d in row] for row in dd])
+    assert torch.equal(out2, out.detach())
 
 
 def test_epipolar_and_depth_diff_vs_oracle(cuda_device):

@@ -73,6 +73,19 @@ class UglGeomFlowArgs(C.Structure):
     ]
 
 
+class UglDispSmoothArgs(C.Structure):
+    """Mirror of ``struct UglDispSmoothArgs`` (include/ugl.h)."""
+
+    MAX_LISTS = 3
+    _LL = (C.c_void_p * MAX_LEVELS) * MAX_LISTS
+    _fields_ = [
+        ("batch", C.c_int32), ("lists", C.c_int32), ("levels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("lheight", C.c_int32 * MAX_LEVELS), ("lwidth", C.c_int32 * MAX_LEVELS),
+        ("img", C.c_void_p * MAX_LISTS), ("disp", _LL), ("out", C.c_void_p), ("G", _LL), ("grad_out", C.c_void_p), ("grad_disp", _LL),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("stream", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/ugl.h declares
 SIGNATURES = {
     "ugl_version": (C.c_int, []),
@@ -121,6 +134,9 @@ SIGNATURES.update({
     "ugl_depth_diff_backward": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
     "ugl_disp_smooth_forward": (C.c_int, [_p, _pp, _ip, _ip, _i, _i, _i, _i, _p, _p, _u64, _p]),
     "ugl_disp_smooth_backward_workspace_bytes": (_u64, [_i, _i, _i]),
+    "ugl_disp_smooth_fused_workspace_bytes": (_u64, [C.POINTER(UglDispSmoothArgs)]),
+    "ugl_disp_smooth_forward_grad": (C.c_int, [C.POINTER(UglDispSmoothArgs)]),
+    "ugl_disp_smooth_combine": (C.c_int, [C.POINTER(UglDispSmoothArgs)]),
     "ugl_disp_smooth_backward": (C.c_int, [_p, _pp, _ip, _ip, _i, _p, _i, _i, _i, _pp, _p, _u64, _p]),
     "ugl_reproject_forward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ugl_reproject_backward_workspace_bytes": (_u64, [_i, _i, _i, _i, _i, _i]),

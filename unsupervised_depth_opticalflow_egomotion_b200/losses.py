@@ -52,9 +52,13 @@ class _LossBase:
         """model_geometry.py:195-210 / model_flow.py:184-199"""
         return sum(ops.flow_consis(fwd_flow_pyramid[s], bwd_flow_pyramid[s], occ_mask_list[s]) for s in range(self.num_scales))
 
-    def compute_smooth_loss(self, img, disps):
+    def compute_smooth_loss(self, img, disps, mode: str = "single_pass"):
         """model_geometry.py:225-252 / model_depth.py:220-247"""
-        return ops.disp_smooth(img, list(disps[:self.num_scales]))
+        return ops.disp_smooth(img, list(disps[:self.num_scales]), mode=mode)
+
+    def compute_smooth_loss3(self, imgs, disp_lists):
+        """the three back-to-back ``compute_smooth_loss`` calls (model_geometry.py:938-940 / model_depth.py:281-283), one launch"""
+        return ops.disp_smooth_multi(list(imgs), [list(d[:self.num_scales]) for d in disp_lists]).sum(0)
 
     def compute_texture_mask(self, img_list, img_warped_list, img_list_source):
         """model_geometry.py:134-140 / model_depth.py:84-90"""
@@ -164,8 +168,7 @@ class DepthLoss(_LossBase):
             area = (ops.image_pyramid(img_l, S, "area"), ops.image_pyramid(img_r, S, "area"))
             pix, valid, tex = ops.depth_photo_loss(pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f))
             loss = {"loss_depth_pixel": pix, "loss_depth_ssim": _zeros2(img), "loss_depth_consis": _zeros2(img),
-                    "loss_depth_smooth": (self.compute_smooth_loss(img, disp_list) + self.compute_smooth_loss(img_l, disp_l_list)
-                                          + self.compute_smooth_loss(img_r, disp_r_list))}
+                    "loss_depth_smooth": self.compute_smooth_loss3((img, img_l, img_r), (disp_list, disp_l_list, disp_r_list))}
             return loss, dict(valid_l=valid[0], valid_r=valid[1], tex_b=tex[0], tex_f=tex[1])
         rec_l, val_l, proj_l, comp_l = self._reconstruction_with(img_l, disp_list, disp_l_list, Kinv, P_b)
         rec_r, val_r, proj_r, comp_r = self._reconstruction_with(img_r, disp_list, disp_r_list, Kinv, P_f)
@@ -179,8 +182,11 @@ class DepthLoss(_LossBase):
         else:
             loss["loss_depth_ssim"] = _zeros2(img)
             loss["loss_depth_consis"] = _zeros2(img)
-        loss["loss_depth_smooth"] = (self.compute_smooth_loss(img, disp_list) + self.compute_smooth_loss(img_l, disp_l_list)
-                                     + self.compute_smooth_loss(img_r, disp_r_list))
+        if fused:
+            loss["loss_depth_smooth"] = self.compute_smooth_loss3((img, img_l, img_r), (disp_list, disp_l_list, disp_r_list))
+        else:
+            loss["loss_depth_smooth"] = (self.compute_smooth_loss(img, disp_list, "recompute") + self.compute_smooth_loss(img_l, disp_l_list, "recompute")
+                                         + self.compute_smooth_loss(img_r, disp_r_list, "recompute"))
         masks = dict(valid_l=val_l, valid_r=val_r, tex_b=tex_b, tex_f=tex_f)
         return loss, masks
 
@@ -303,8 +309,7 @@ class GeometryLoss(_LossBase):
         loss = {
             "loss_depth_pixel": depth_pixel,
             "loss_depth_ssim": _zeros2(img),
-            "loss_depth_smooth": self.compute_smooth_loss(img, disp_list) + self.compute_smooth_loss(img_l, disp_l_list)
-                                 + self.compute_smooth_loss(img_r, disp_r_list),
+            "loss_depth_smooth": self.compute_smooth_loss3((img, img_l, img_r), (disp_list, disp_l_list, disp_r_list)),
             "loss_depth_consis": _zeros2(img),
             "loss_flow_pixel": flow4[0], "loss_flow_ssim": flow4[1], "loss_flow_smooth": flow4[2], "loss_flow_consis": flow4[3],
             "loss_depth_flow_consis": ops.masked_mean(fd_b, bwd0) + ops.masked_mean(fd_f, fwd0),
@@ -354,8 +359,8 @@ class GeometryLoss(_LossBase):
         loss = {
             "loss_depth_pixel": P(pc, rec_l, bwd_mask_tex) + P(pc, rec_r, fwd_mask_tex),
             "loss_depth_ssim": _zeros2(img),
-            "loss_depth_smooth": self.compute_smooth_loss(img, disp_list) + self.compute_smooth_loss(img_l, disp_l_list)
-                                 + self.compute_smooth_loss(img_r, disp_r_list),
+            "loss_depth_smooth": self.compute_smooth_loss(img, disp_list, "recompute") + self.compute_smooth_loss(img_l, disp_l_list, "recompute")
+                                 + self.compute_smooth_loss(img_r, disp_r_list, "recompute"),
             "loss_depth_consis": _zeros2(img),
             "loss_flow_pixel": P(pc, from_l, bwd_vo_rigid) + P(pc, from_r, fwd_vo_rigid)
                                + 2 * P(pc, from_l, bwd_vo_dyna) + 2 * P(pc, from_r, fwd_vo_dyna),

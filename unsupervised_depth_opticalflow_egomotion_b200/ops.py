@@ -43,8 +43,8 @@ def _dev_u8(t: Tensor, name: str) -> Tensor:
     return t
 
 
-def _ptr(t: Optional[Tensor]) -> Optional[int]:
-    return None if t is None else t.data_ptr()
+def _ptr(t) -> Optional[int]:
+    return t.data_ptr() if isinstance(t, Tensor) else None
 
 
 # ================================================================================================
@@ -718,9 +718,92 @@ class _DispSmoothFn(torch.autograd.Function):
         return (None, *grads)
 
 
-def disp_smooth(img: Tensor, disps: Sequence[Tensor]) -> Tensor:
-    """``compute_smooth_loss(img, disps)`` (model_geometry.py:225-252) for ``len(disps)`` levels -> (B,)."""
-    return _DispSmoothFn.apply(img, *disps)
+def _disp_smooth_args(imgs, disps, out, G, gout=None, gdisp=None) -> _cabi.UglDispSmoothArgs:
+    a = _cabi.UglDispSmoothArgs()
+    nl, L = len(imgs), len(disps[0])
+    a.batch, a.lists, a.levels, a.height, a.width = imgs[0].shape[0], nl, L, imgs[0].shape[2], imgs[0].shape[3]
+    for l in range(L):
+        a.lheight[l], a.lwidth[l] = disps[0][l].shape[2], disps[0][l].shape[3]
+    for i in range(nl):
+        a.img[i] = _ptr(imgs[i])
+        for l in range(L):
+            a.disp[i][l] = _ptr(disps[i][l])
+            if G is not None:
+                a.G[i][l] = G[i][l].data_ptr()
+            if gdisp is not None:
+                a.grad_disp[i][l] = gdisp[i][l].data_ptr()
+    a.out, a.grad_out = _ptr(out), _ptr(gout)
+    a.stream = torch.cuda.current_stream().cuda_stream
+    return a
+
+
+class _DispSmoothMultiFn(torch.autograd.Function):
+    """single-pass form: forward also writes G = d loss / d (up-sampled disparity); backward = transpose-gather of G"""
+
+    @staticmethod
+    def forward(ctx, nl, L, *ts):
+        imgs = [_dev(t, "img").detach() for t in ts[:nl]]
+        disps = [[_dev(t, "disp") for t in ts[nl + i * L:nl + (i + 1) * L]] for i in range(nl)]
+        B, _, H, W = imgs[0].shape
+        dev = imgs[0].device
+        for i in range(nl):
+            if tuple(imgs[i].shape) != (B, 3, H, W):
+                raise ValueError("disp_smooth: images must share one (B,3,H,W) shape")
+            for l in range(L):
+                if tuple(disps[i][l].shape) != tuple(disps[0][l].shape) or disps[i][l].shape[:2] != (B, 1):
+                    raise ValueError("disp_smooth: disparity pyramids of all lists must share their (B,1,h,w) shapes")
+        need = any(ctx.needs_input_grad[2 + nl:])
+        out = torch.empty((nl, B), device=dev, dtype=torch.float32)
+        G = [[torch.empty((B, 1, H, W), device=dev, dtype=torch.float32) for _ in range(L)] for _ in range(nl)] if need else None
+        a = _disp_smooth_args(imgs, disps, out, G)
+        n = int(_cabi.lib().ugl_disp_smooth_fused_workspace_bytes(C.byref(a)))
+        ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), _nbytes(ws)
+        with torch.cuda.device_of(imgs[0]):
+            _call("ugl_disp_smooth_forward_grad", C.byref(a), launches=2)
+        if need:
+            ctx.save_for_backward(*[g for row in G for g in row])
+        ctx.nl, ctx.L, ctx.shapes, ctx.full = nl, L, [tuple(d.shape) for d in disps[0]], (B, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        nl, L = ctx.nl, ctx.L
+        Gs = ctx.saved_tensors
+        if not Gs:
+            return (None,) * (2 + nl + nl * L)
+        G = [list(Gs[i * L:(i + 1) * L]) for i in range(nl)]
+        gout = _dev(gout, "grad_out")
+        dev = gout.device
+        gd = [[torch.empty(ctx.shapes[l], device=dev, dtype=torch.float32) for l in range(L)] for _ in range(nl)]
+
+        class _Shape:   # shapes only: combine reads G, not the images / disparities
+            def __init__(self, shape):
+                self.shape = shape
+
+        B, H, W = ctx.full
+        a = _disp_smooth_args([_Shape((B, 3, H, W))] * nl, [[_Shape(s) for s in ctx.shapes]] * nl, None, G, gout, gd)
+        with torch.cuda.device_of(gout):
+            _call("ugl_disp_smooth_combine", C.byref(a))
+        return (None, None, *([None] * nl), *[g for row in gd for g in row])
+
+
+def disp_smooth_multi(imgs: Sequence[Tensor], disps: Sequence[Sequence[Tensor]]) -> Tensor:
+    """``compute_smooth_loss`` for up to three (image, disparity pyramid) lists in one launch -> (lists, B)
+    (model_geometry.py:938-940 calls it for the centre, left and right frames back to back)."""
+    nl = len(imgs)
+    if not 1 <= nl <= _cabi.UglDispSmoothArgs.MAX_LISTS or len(disps) != nl or any(len(d) != len(disps[0]) for d in disps):
+        raise ValueError("disp_smooth_multi: 1..3 lists with equally many levels each")
+    L = len(disps[0])
+    return _DispSmoothMultiFn.apply(nl, L, *imgs, *[d for row in disps for d in row])
+
+
+def disp_smooth(img: Tensor, disps: Sequence[Tensor], mode: str = "single_pass") -> Tensor:
+    """``compute_smooth_loss(img, disps)`` (model_geometry.py:225-252) for ``len(disps)`` levels -> (B,).
+    ``mode='recompute'`` keeps nothing per pixel between forward and backward (the per-method kernels)."""
+    if mode == "recompute":
+        return _DispSmoothFn.apply(img, *disps)
+    return disp_smooth_multi([img], [list(disps)])[0]
 
 
 class _ReprojectFn(torch.autograd.Function):
