@@ -306,6 +306,17 @@ uint64_t ugl_depth_photo_workspace_bytes(const UglDepthPhotoArgs* args);
 int ugl_depth_photo_forward(const UglDepthPhotoArgs* args);
 int ugl_depth_photo_backward(const UglDepthPhotoArgs* args);
 
+/* Per-step matrix set-up of the depth / geom modes, one launch for every level and both poses:
+ *   K_s = K with rows 0-1 divided by downscales[s] (model_geometry.py:92-93); Kinv_out[s] (B,3,3) = K_s^-1 (inverse_warp.py:284);
+ *   [R|t] = pose_vec2mat(pose[:,k]) (euler, inverse_warp.py:110-145, 172-187); P_out[k*S+s] (B,3,4) = K_s [R|t] (:289);
+ *   F_out[k] (B,3,3) = K_inv^T [t]x R K_inv (compute_essential_matrix :354-364 + model_geometry.py:355-370), optional.
+ * pose (B,n,6) = [tx,ty,tz,rx,ry,rz], n <= 2.  backward: grad_P[k*S+s] / grad_F[k] (entries may be NULL = zero)
+ * -> grad_pose (B,n,6).  downscales is a HOST array of S floats. */
+int ugl_pose_setup_forward(const float* pose, const float* K, const float* K_inv, const float* downscales, int32_t batch, int32_t poses,
+                           int32_t levels, float* const* Kinv_out, float* const* P_out, float* const* F_out, void* stream);
+int ugl_pose_setup_backward(const float* pose, const float* K, const float* K_inv, const float* downscales, int32_t batch, int32_t poses,
+                            int32_t levels, const float* const* grad_P, const float* const* grad_F, float* grad_pose, void* stream);
+
 /* compute_epipolar_map (model_geometry.py:355-403) given F (B,3,3) = K^-T [t]x R K^-1: dist (B,1,H,W);
  * backward: grad_flow (B,2,H,W, may be NULL) and grad_F (B,3,3). */
 int ugl_epipolar_forward(const float* flow, const float* F, int32_t batch, int32_t height, int32_t width, float* out, void* stream);

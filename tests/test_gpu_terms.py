@@ -345,3 +345,48 @@ def test_fused_depth_branch_equals_composed(cuda_device):
             assert torch.equal(a, b), k
     for i, (a, b) in enumerate(zip(res[True][2], res[False][2])):
         assert rel_err(a, b) < (2e-5 if i < 4 else GRAD_RTOL), i      # flow gradients: SSIM sums in a different order
+
+
+@pytest.mark.parametrize("n,S,want_F", [(2, 3, True), (1, 4, False), (2, 1, True)])
+def test_pose_setup_vs_composed_torch(cuda_device, n, S, want_F):
+    """ops.pose_setup (one launch fwd, one bwd) against the reference's chain of small torch ops (structures.projection_pyramid,
+    compute_essential_matrix) and against the CPU oracle's matrices"""
+    B = 3
+    t = make_triplet(B, 64, 208, 1, 1, seed=71)
+    g = _g(5)
+    pose_cpu = (torch.rand(B, n, 6, generator=g) - 0.5) * torch.tensor([0.4, 0.4, 0.4, 0.2, 0.2, 0.2])
+    downs = [float(2 ** s) for s in range(S)]
+    K, Kin = t.K.to(cuda_device), t.K_inv.to(cuda_device)
+    pa = pose_cpu.to(cuda_device).requires_grad_(True)
+    Kinv, P_, F_ = ops.pose_setup(pa, K, downs, Kin if want_F else None, fundamental=want_F)
+    pb = pose_cpu.to(cuda_device).requires_grad_(True)
+    rKinv, rP = structures.projection_pyramid(K, [pb[:, k] for k in range(n)], downs)
+    rF = [Kin.transpose(1, 2).bmm(structures.compute_essential_matrix(pb[:, k]).bmm(Kin)) for k in range(n)] if want_F else []
+    wP = [[torch.rand(B, 3, 4, generator=g).to(cuda_device) for _ in range(S)] for _ in range(n)]
+    wF = [torch.rand(B, 3, 3, generator=g).to(cuda_device) for _ in range(n)]
+    tot_a = sum((P_[k][s] * wP[k][s]).sum() for k in range(n) for s in range(S))
+    tot_b = sum((rP[k][s] * wP[k][s]).sum() for k in range(n) for s in range(S))
+    if want_F:
+        tot_a = tot_a + sum((F_[k] * wF[k]).sum() for k in range(n))
+        tot_b = tot_b + sum((rF[k] * wF[k]).sum() for k in range(n))
+    ga, = torch.autograd.grad(tot_a, pa)
+    gb, = torch.autograd.grad(tot_b, pb)
+    for s in range(S):
+        assert rel_err(Kinv[s], rKinv[s]) < 1e-6
+        Ks = P.scale_intrinsics(t.K, downs[s])
+        assert rel_err(Kinv[s].cpu(), Ks.inverse()) < 1e-5
+        for k in range(n):
+            assert rel_err(P_[k][s], rP[k][s]) < 1e-6
+            assert rel_err(P_[k][s].cpu(), Ks @ P.pose_to_matrix(pose_cpu[:, k])) < 1e-6
+    for k in range(n if want_F else 0):
+        assert rel_err(F_[k], rF[k]) < 1e-5
+        assert rel_err(F_[k].cpu(), t.K_inv.transpose(1, 2) @ P.essential_matrix(pose_cpu[:, k]) @ t.K_inv) < 1e-5
+    assert rel_err(ga, gb) < 1e-5
+    # unused outputs: no gradient requested for some P / F entries
+    pc_ = pose_cpu.to(cuda_device).requires_grad_(True)
+    _, P2, _ = ops.pose_setup(pc_, K, downs, Kin if want_F else None, fundamental=want_F)
+    g2, = torch.autograd.grad((P2[0][0] * wP[0][0]).sum(), pc_)
+    pd = pose_cpu.to(cuda_device).requires_grad_(True)
+    _, rP2 = structures.projection_pyramid(K, [pd[:, k] for k in range(n)], downs)
+    g3, = torch.autograd.grad((rP2[0][0] * wP[0][0]).sum(), pd)
+    assert rel_err(g2, g3) < 1e-5

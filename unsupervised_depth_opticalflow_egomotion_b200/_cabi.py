@@ -132,6 +132,8 @@ SIGNATURES.update({
     "ugl_flow_consis_backward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "ugl_depth_diff_forward": (C.c_int, [_p, _p, _i64, _p, _p]),
     "ugl_depth_diff_backward": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
+    "ugl_pose_setup_forward": (C.c_int, [_p, _p, _p, _fp, _i, _i, _i, _pp, _pp, _pp, _p]),
+    "ugl_pose_setup_backward": (C.c_int, [_p, _p, _p, _fp, _i, _i, _i, _pp, _pp, _p, _p]),
     "ugl_disp_smooth_forward": (C.c_int, [_p, _pp, _ip, _ip, _i, _i, _i, _i, _p, _p, _u64, _p]),
     "ugl_disp_smooth_backward_workspace_bytes": (_u64, [_i, _i, _i]),
     "ugl_disp_smooth_fused_workspace_bytes": (_u64, [C.POINTER(UglDispSmoothArgs)]),

@@ -84,6 +84,12 @@ class _LossBase:
         downs = [ref_h / depth[s].shape[2] for s in range(self.num_scales)]
         return projection_pyramid(intrinsics, poses, downs)
 
+    def _pose_setup(self, ref_h: int, intrinsics, depth, pose_vectors, K_inv=None, fundamental=False):
+        """one-launch form of :meth:`_projections` (+ the fundamental matrices of compute_epipolar_map): pose index 0 = centre->left
+        (bwd), 1 = centre->right (fwd)"""
+        downs = [ref_h / depth[s].shape[2] for s in range(self.num_scales)]
+        return ops.pose_setup(pose_vectors, intrinsics, downs, K_inv, fundamental)
+
     def _reconstruction_with(self, ref_img, depth, depth_ref, Kinv, P):
         rec, valid, proj, comp = [], [], [], []
         area = ops.image_pyramid(ref_img, self.num_scales, "area")
@@ -163,7 +169,10 @@ class DepthLoss(_LossBase):
         S = self.num_scales
         pl, pc, pr = (self.generate_img_pyramid(x, S) for x in (img_l, img, img_r))
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
-        Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
+        if fused:
+            Kinv, (P_b, P_f), _ = self._pose_setup(img.size(2), K, disp_list, pose_vectors)
+        else:
+            Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
         if fused and self.variant == "live":
             area = (ops.image_pyramid(img_l, S, "area"), ops.image_pyramid(img_r, S, "area"))
             pix, valid, tex = ops.depth_photo_loss(pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f))
@@ -290,7 +299,7 @@ class GeometryLoss(_LossBase):
         return [ops.mask_product([valid_mask[s], occ_mask[s]], [False, invert_second]) for s in range(self.num_scales)]
 
     def _forward_losses_fused(self, img, img_l, img_r, pc, pl, pr, flows_fwd, flows_bwd, disp_list, disp_l_list, disp_r_list,
-                              pose_fwd, pose_bwd, K, K_inv, Kinv, P_b, P_f):
+                              Fm, Kinv, P_b, P_f):
         """Two stencil kernels carry the loss loop: the geom-mode single-pass flow kernel (warps, every mask, the four flow
         terms; masks leave as one packed byte map per level) and the reprojection-photometric kernel (reads the byte maps).
         The level-0 point-wise terms (depth-flow consistency, epipolar) and the disparity smoothness stay on their ops."""
@@ -304,8 +313,8 @@ class GeometryLoss(_LossBase):
         fd_b, _, _ = ops.dynamic_mask(flows_bwd[0], ops.rigid_flow(disp_list[0], Kinv[0], P_b[0]), self.flow_consist_alpha, self.flow_consist_beta)
         fd_f, _, _ = ops.dynamic_mask(flows_fwd[0], ops.rigid_flow(disp_list[0], Kinv[0], P_f[0]), self.flow_consist_alpha, self.flow_consist_beta)
         bwd0, fwd0 = ops.unpack_mask(mbytes[0], ops.MASK_ALL_BWD), ops.unpack_mask(mbytes[0], ops.MASK_ALL_FWD)
-        dist_b = self.compute_epipolar_map(pose_bwd, flows_bwd[0], K, K_inv)
-        dist_f = self.compute_epipolar_map(pose_fwd, flows_fwd[0], K, K_inv)
+        dist_b = ops.epipolar_distance(flows_bwd[0], Fm[0])      # compute_epipolar_map with F from the pose set-up kernel
+        dist_f = ops.epipolar_distance(flows_fwd[0], Fm[1])
         loss = {
             "loss_depth_pixel": depth_pixel,
             "loss_depth_ssim": _zeros2(img),
@@ -326,10 +335,11 @@ class GeometryLoss(_LossBase):
         S = self.num_scales
         pc, pl, pr = (self.generate_img_pyramid(x, S) for x in (img, img_l, img_r))
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
-        Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
         if fused:
+            Kinv, (P_b, P_f), Fm = self._pose_setup(img.size(2), K, disp_list, pose_vectors, K_inv, fundamental=True)
             return self._forward_losses_fused(img, img_l, img_r, pc, pl, pr, optical_flows_fwd, optical_flows_bwd, disp_list, disp_l_list,
-                                              disp_r_list, pose_fwd, pose_bwd, K, K_inv, Kinv, P_b, P_f)
+                                              disp_r_list, Fm, Kinv, P_b, P_f)
+        Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
         # composed path: one kernel per reference method (kept as the cross-check of the fused kernels)
         rec_l, val_l, _, _ = self._reconstruction_with(img_l, disp_list, disp_l_list, Kinv, P_b)
         rec_r, val_r, _, _ = self._reconstruction_with(img_r, disp_list, disp_r_list, Kinv, P_f)

@@ -882,6 +882,66 @@ def rigid_flow(depth: Tensor, Kinv: Tensor, P: Tensor) -> Tensor:
     return _RigidFlowFn.apply(depth, Kinv, P)
 
 
+class _PoseSetupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pose, K, K_inv, downs, want_F):
+        pose, K = _dev(pose, "pose"), _dev(K, "K").detach()
+        K_inv = _dev(K_inv, "K_inv").detach() if K_inv is not None else None
+        if pose.dim() != 3 or pose.shape[2] != 6 or not 1 <= pose.shape[1] <= 2:
+            raise ValueError("pose_setup: pose must be (B,n,6) with n <= 2, got %s" % (tuple(pose.shape),))
+        B, n, _ = pose.shape
+        if tuple(K.shape) != (B, 3, 3) or (K_inv is not None and tuple(K_inv.shape) != (B, 3, 3)):
+            raise ValueError("pose_setup: K / K_inv must be (B,3,3)")
+        if want_F and K_inv is None:
+            raise ValueError("pose_setup: the fundamental matrices need K_inv")
+        S, dev = len(downs), pose.device
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        Kinv = [new(B, 3, 3) for _ in range(S)]
+        Ps = [new(B, 3, 4) for _ in range(n * S)]
+        Fs = [new(B, 3, 3) for _ in range(n)] if want_F else []
+        darr = (C.c_float * S)(*[float(d) for d in downs])
+        arr = lambda ts: (C.c_void_p * max(len(ts), 1))(*[t.data_ptr() for t in ts])
+        with torch.cuda.device_of(pose):
+            _call("ugl_pose_setup_forward", pose.data_ptr(), K.data_ptr(), _ptr(K_inv), darr, B, n, S, arr(Kinv), arr(Ps),
+                  arr(Fs) if want_F else None, _stream_ptr())
+        ctx.save_for_backward(pose, K, K_inv)
+        ctx.downs, ctx.want_F = tuple(float(d) for d in downs), want_F
+        ctx.mark_non_differentiable(*Kinv)
+        ctx.set_materialize_grads(False)
+        return (*Kinv, *Ps, *Fs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        pose, K, K_inv = ctx.saved_tensors
+        B, n, _ = pose.shape
+        S = len(ctx.downs)
+        gP, gF = grads[S:S + n * S], grads[S + n * S:]
+        if all(g is None for g in (*gP, *gF)):
+            return None, None, None, None, None
+        gP = [(_dev(g, "grad_P") if g is not None else None) for g in gP]
+        gF = [(_dev(g, "grad_F") if g is not None else None) for g in gF]
+        ptrs = lambda gs: (C.c_void_p * max(len(gs), 1))(*[_ptr(g) for g in gs])
+        gpose = torch.empty_like(pose)
+        darr = (C.c_float * S)(*ctx.downs)
+        with torch.cuda.device_of(pose):
+            _call("ugl_pose_setup_backward", pose.data_ptr(), K.data_ptr(), _ptr(K_inv), darr, B, n, S, ptrs(gP),
+                  ptrs(gF) if ctx.want_F else None, gpose.data_ptr(), _stream_ptr())
+        return gpose, None, None, None, None
+
+
+def pose_setup(pose: Tensor, K: Tensor, downscales: Sequence[float], K_inv: Optional[Tensor] = None, fundamental: bool = False):
+    """Every 3x3 / 3x4 matrix a depth / geom step needs, in one launch: ``Kinv[s]`` (B,3,3) = inverse of the level's
+    intrinsics, ``P[k][s]`` (B,3,4) = K_s [R|t] of ``pose[:,k]`` and, with ``fundamental=True``, ``F[k]`` (B,3,3) =
+    K^-T [t]x R K^-1 (inverse_warp.py:110-145, 172-187, 284-289, 354-364; model_geometry.py:92-93).  Differentiable
+    w.r.t. ``pose`` (analytic backward, one launch)."""
+    n, S = pose.shape[1], len(downscales)
+    out = _PoseSetupFn.apply(pose, K, K_inv, tuple(downscales), bool(fundamental))
+    Kinv = list(out[:S])
+    P = [list(out[S + k * S:S + (k + 1) * S]) for k in range(n)]
+    F = list(out[S + n * S:]) if fundamental else None
+    return Kinv, P, F
+
+
 class _EpipolarFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, flow, Fm):
