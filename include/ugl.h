@@ -317,6 +317,32 @@ int ugl_pose_setup_forward(const float* pose, const float* K, const float* K_inv
 int ugl_pose_setup_backward(const float* pose, const float* K, const float* K_inv, const float* downscales, int32_t batch, int32_t poses,
                             int32_t levels, const float* const* grad_P, const float* const* grad_F, float* grad_pose, void* stream);
 
+/* Level-0 rigid-consistency terms of Model_geometry.forward in one forward / one backward kernel (+ finalize each):
+ *   loss_dfc (B,) = loss_depth_flow_consis: calculate_rigid_flow (inverse_warp.py:311-342) for both poses, |rigid - flow| (2 ch,
+ *                   compute_dynamic_mask's flow_diff, model_geometry.py:698-700) under valid*occ*dyn (mask_bytes & need[d] == need[d]),
+ *                   compute_depth_flow_consis_loss with scales=1 (:716-732, called at :925-926);
+ *   loss_epi (B,) = loss_epipolar: compute_epipolar_map (:355-403) for both poses, plain per-sample mean (:413-418).
+ * den (B,2) is written by forward and read by backward.  backward: grad_dfc / grad_epi (B,) (either may be NULL = zero) ->
+ * grad_flow_bwd/fwd (B,2,H,W), grad_disp (B,1,H,W), grad_P_bwd/fwd (B,3,4), grad_F_bwd/fwd (B,3,3). */
+typedef struct UglGeomRigidArgs {
+  int32_t batch, height, width;
+  int32_t need[2];                             /* mask bits per direction (bwd, fwd)             */
+  const float *flow_bwd, *flow_fwd;            /* (B,2,H,W) level-0 flows                        */
+  const float* disp;                           /* (B,1,H,W) centre disparity, level 0            */
+  const uint8_t* mask_bytes;                   /* (B,H,W) from ugl_geom_flow_forward_grad        */
+  const float *Kinv, *P_bwd, *P_fwd;           /* (B,3,3), (B,3,4) x2 of level 0                 */
+  const float *F_bwd, *F_fwd;                  /* (B,3,3) fundamental matrices                   */
+  float *loss_dfc, *loss_epi, *den;            /* (B,), (B,), (B,2)                              */
+  const float *grad_dfc, *grad_epi;            /* (B,)                      [backward]           */
+  float *grad_flow_bwd, *grad_flow_fwd, *grad_disp, *grad_P_bwd, *grad_P_fwd, *grad_F_bwd, *grad_F_fwd;
+  void* workspace;                             /* >= ugl_geom_rigid_workspace_bytes              */
+  uint64_t workspace_bytes;
+  void* stream;
+} UglGeomRigidArgs;
+uint64_t ugl_geom_rigid_workspace_bytes(int32_t batch, int32_t height, int32_t width);
+int ugl_geom_rigid_forward(const UglGeomRigidArgs* args);
+int ugl_geom_rigid_backward(const UglGeomRigidArgs* args);
+
 /* compute_epipolar_map (model_geometry.py:355-403) given F (B,3,3) = K^-T [t]x R K^-1: dist (B,1,H,W);
  * backward: grad_flow (B,2,H,W, may be NULL) and grad_F (B,3,3). */
 int ugl_epipolar_forward(const float* flow, const float* F, int32_t batch, int32_t height, int32_t width, float* out, void* stream);

@@ -54,7 +54,8 @@ def test_struct_layouts_match_the_c_compiler(tmp_path):
     """sizeof / offsetof of every argument struct as gcc lays out include/ugl.h == the ctypes mirrors"""
     import os
     import subprocess
-    structs = {"UglFlowLossArgs": _cabi.UglFlowLossArgs, "UglDepthPhotoArgs": _cabi.UglDepthPhotoArgs, "UglGeomFlowArgs": _cabi.UglGeomFlowArgs}
+    structs = {"UglFlowLossArgs": _cabi.UglFlowLossArgs, "UglDepthPhotoArgs": _cabi.UglDepthPhotoArgs, "UglGeomFlowArgs": _cabi.UglGeomFlowArgs,
+               "UglDispSmoothArgs": _cabi.UglDispSmoothArgs, "UglGeomRigidArgs": _cabi.UglGeomRigidArgs}
     lines = []
     for name, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))

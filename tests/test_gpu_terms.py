@@ -390,3 +390,41 @@ def test_pose_setup_vs_composed_torch(cuda_device, n, S, want_F):
     _, rP2 = structures.projection_pyramid(K, [pd[:, k] for k in range(n)], downs)
     g3, = torch.autograd.grad((rP2[0][0] * wP[0][0]).sum(), pd)
     assert rel_err(g2, g3) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 208), (1, 50, 70)])
+def test_geom_rigid_terms_equal_composed(cuda_device, B, H, W):
+    """ops.geom_rigid_terms (level-0 depth-flow consistency + epipolar, one kernel pair) against the per-method kernels"""
+    t = make_triplet(B, H, W, 1, 1, seed=81, flow_mode="rigid").to(cuda_device)
+    g = _g(7)
+    mbytes = torch.randint(0, 64, (B, H, W), generator=g, dtype=torch.uint8).to(cuda_device)
+    gd, ge = (torch.rand(B, generator=g) + 0.5).to(cuda_device), (torch.rand(B, generator=g) + 0.5).to(cuda_device)
+
+    def run(fused):
+        fb, ff = t.flows_bwd[0].detach().clone().requires_grad_(True), t.flows_fwd[0].detach().clone().requires_grad_(True)
+        disp, pose = t.disp[0].detach().clone().requires_grad_(True), t.pose.detach().clone().requires_grad_(True)
+        Kinv, (Pb, Pf), Fm = ops.pose_setup(pose, t.K, [1.0], t.K_inv, fundamental=True)
+        if fused:
+            dfc, epi = ops.geom_rigid_terms(fb, ff, disp, mbytes, Kinv[0], Pb[0], Pf[0], Fm[0], Fm[1])
+        else:
+            dfc, epi = 0, 0
+            for flow, Pm, F_, need in ((fb, Pb[0], Fm[0], ops.MASK_ALL_BWD), (ff, Pf[0], Fm[1], ops.MASK_ALL_FWD)):
+                fd, _, _ = ops.dynamic_mask(flow, ops.rigid_flow(disp, Kinv[0], Pm), 0.01, 0.5)
+                dfc = dfc + ops.masked_mean(fd, ops.unpack_mask(mbytes, need))
+                epi = epi + ops.masked_mean(ops.epipolar_distance(flow, F_), None)
+        grads = torch.autograd.grad((dfc * gd).sum() + (epi * ge).sum(), [fb, ff, disp, pose])
+        return dfc, epi, grads
+
+    a, b = run(True), run(False)
+    assert loss_rel_err(a[0], b[0]) < 1e-6 and loss_rel_err(a[1], b[1]) < 1e-6
+    for x, y in zip(a[2][:3], b[2][:3]):
+        assert rel_err(x, y) < 1e-6
+    assert rel_err(a[2][3], b[2][3]) < 1e-4          # pose: sums of cancelling per-pixel terms, different summation order
+    # only one of the two outputs used downstream
+    fb = t.flows_bwd[0].detach().clone().requires_grad_(True)
+    Kinv, (Pb, Pf), Fm = ops.pose_setup(t.pose, t.K, [1.0], t.K_inv, fundamental=True)
+    dfc, epi = ops.geom_rigid_terms(fb, t.flows_fwd[0], t.disp[0], mbytes, Kinv[0], Pb[0], Pf[0], Fm[0], Fm[1])
+    g1, = torch.autograd.grad(epi.sum(), fb)
+    fb2 = t.flows_bwd[0].detach().clone().requires_grad_(True)
+    g2, = torch.autograd.grad(ops.masked_mean(ops.epipolar_distance(fb2, Fm[0]), None).sum(), fb2)
+    assert rel_err(g1, g2) < 1e-6

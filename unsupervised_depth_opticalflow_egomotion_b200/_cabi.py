@@ -86,6 +86,16 @@ class UglDispSmoothArgs(C.Structure):
     ]
 
 
+class UglGeomRigidArgs(C.Structure):
+    """Mirror of ``struct UglGeomRigidArgs`` (include/ugl.h)."""
+
+    _fields_ = [("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("need", C.c_int32 * 2)] + [
+        (name, C.c_void_p) for name in (
+            "flow_bwd", "flow_fwd", "disp", "mask_bytes", "Kinv", "P_bwd", "P_fwd", "F_bwd", "F_fwd", "loss_dfc", "loss_epi", "den",
+            "grad_dfc", "grad_epi", "grad_flow_bwd", "grad_flow_fwd", "grad_disp", "grad_P_bwd", "grad_P_fwd", "grad_F_bwd", "grad_F_fwd",
+            "workspace")] + [("workspace_bytes", C.c_uint64), ("stream", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/ugl.h declares
 SIGNATURES = {
     "ugl_version": (C.c_int, []),
@@ -132,6 +142,9 @@ SIGNATURES.update({
     "ugl_flow_consis_backward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "ugl_depth_diff_forward": (C.c_int, [_p, _p, _i64, _p, _p]),
     "ugl_depth_diff_backward": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
+    "ugl_geom_rigid_workspace_bytes": (_u64, [_i, _i, _i]),
+    "ugl_geom_rigid_forward": (C.c_int, [C.POINTER(UglGeomRigidArgs)]),
+    "ugl_geom_rigid_backward": (C.c_int, [C.POINTER(UglGeomRigidArgs)]),
     "ugl_pose_setup_forward": (C.c_int, [_p, _p, _p, _fp, _i, _i, _i, _pp, _pp, _pp, _p]),
     "ugl_pose_setup_backward": (C.c_int, [_p, _p, _p, _fp, _i, _i, _i, _pp, _pp, _p, _p]),
     "ugl_disp_smooth_forward": (C.c_int, [_p, _pp, _ip, _ip, _i, _i, _i, _i, _p, _p, _u64, _p]),

@@ -152,20 +152,6 @@ struct RigidFlowBwdPixel {
 };
 
 // ---- epipolar distance map ---------------------------------------------------------------------------------
-struct Epi { float l[3], p2[3], n, r, d, dist; };
-__device__ __forceinline__ Epi epipolar_pixel(const float* __restrict__ F, float u, float v, int j, int i) {
-  Epi e;
-  const float fj = (float)j, fi = (float)i;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) e.l[k] = fma_rn(F[k * 3 + 2], 1.0f, fma_rn(F[k * 3 + 1], fi, mul_rn(F[k * 3 + 0], fj)));
-  e.p2[0] = add_rn(fj, u); e.p2[1] = add_rn(fi, v); e.p2[2] = 1.0f;
-  e.n = add_rn(add_rn(mul_rn(e.p2[0], e.l[0]), mul_rn(e.p2[1], e.l[1])), mul_rn(e.p2[2], e.l[2]));
-  e.r = sqrt_rn(add_rn(mul_rn(e.l[0], e.l[0]), mul_rn(e.l[1], e.l[1])));
-  e.d = add_rn(e.r, 1e-6f);
-  e.dist = div_rn(fabsf(e.n), e.d);
-  return e;
-}
-
 struct EpipolarFwd {
   const float *flow, *F;
   float* out;

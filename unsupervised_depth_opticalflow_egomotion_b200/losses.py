@@ -208,13 +208,18 @@ class GeomMasks(dict):
     _BITS = dict(valid_b=ops.MASK_VALID_BWD, valid_f=ops.MASK_VALID_FWD, occ_b=ops.MASK_OCC_BWD, occ_f=ops.MASK_OCC_FWD,
                  dyn_b=ops.MASK_DYN_BWD, dyn_f=ops.MASK_DYN_FWD, bwd_mask=ops.MASK_ALL_BWD, fwd_mask=ops.MASK_ALL_FWD)
 
-    def __init__(self, mask_bytes, maps, owner):
+    def __init__(self, mask_bytes, maps, owner, epi_inputs):
         super().__init__(maps)
-        self.mask_bytes, self._owner = mask_bytes, owner
+        self.mask_bytes, self._owner, self._epi = mask_bytes, owner, epi_inputs
 
     def __missing__(self, key):
         if key in self._BITS:
             val = [ops.unpack_mask(m, self._BITS[key]) for m in self.mask_bytes]
+        elif key in ("dist_b", "dist_f"):        # the epipolar distance maps are only materialised for mask_pack consumers
+            with torch.no_grad():
+                fb, ff, Fm = self._epi
+                self["dist_b"], self["dist_f"] = ops.epipolar_distance(fb, Fm[0]), ops.epipolar_distance(ff, Fm[1])
+            return self[key]
         elif key in ("rigid_f", "inlier_f"):
             rigid, inlier, _ = self._owner.get_rigid_mask(self["dist_f"])
             self["rigid_f"], self["inlier_f"] = rigid, inlier
@@ -309,23 +314,19 @@ class GeometryLoss(_LossBase):
         area = (ops.image_pyramid(img_l, S, "area"), ops.image_pyramid(img_r, S, "area"))
         depth_pixel, (val_l, val_r), (tex_b, tex_f) = ops.depth_photo_loss(
             pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f), ext_bytes=mbytes, ext_need=(ops.MASK_ALL_BWD, ops.MASK_ALL_FWD))
-        # level 0: |rigid flow - flow| under valid * occ * dyn (:921-923), epipolar distance mean (:925-935)
-        fd_b, _, _ = ops.dynamic_mask(flows_bwd[0], ops.rigid_flow(disp_list[0], Kinv[0], P_b[0]), self.flow_consist_alpha, self.flow_consist_beta)
-        fd_f, _, _ = ops.dynamic_mask(flows_fwd[0], ops.rigid_flow(disp_list[0], Kinv[0], P_f[0]), self.flow_consist_alpha, self.flow_consist_beta)
-        bwd0, fwd0 = ops.unpack_mask(mbytes[0], ops.MASK_ALL_BWD), ops.unpack_mask(mbytes[0], ops.MASK_ALL_FWD)
-        dist_b = ops.epipolar_distance(flows_bwd[0], Fm[0])      # compute_epipolar_map with F from the pose set-up kernel
-        dist_f = ops.epipolar_distance(flows_fwd[0], Fm[1])
+        # level 0: |rigid flow - flow| under valid * occ * dyn (:921-926) and the epipolar distance means (:928-935), one kernel
+        dfc, epi = ops.geom_rigid_terms(flows_bwd[0], flows_fwd[0], disp_list[0], mbytes[0], Kinv[0], P_b[0], P_f[0], Fm[0], Fm[1])
         loss = {
             "loss_depth_pixel": depth_pixel,
             "loss_depth_ssim": _zeros2(img),
             "loss_depth_smooth": self.compute_smooth_loss3((img, img_l, img_r), (disp_list, disp_l_list, disp_r_list)),
             "loss_depth_consis": _zeros2(img),
             "loss_flow_pixel": flow4[0], "loss_flow_ssim": flow4[1], "loss_flow_smooth": flow4[2], "loss_flow_consis": flow4[3],
-            "loss_depth_flow_consis": ops.masked_mean(fd_b, bwd0) + ops.masked_mean(fd_f, fwd0),
-            "loss_epipolar": self.compute_epipolar_loss(dist_b, None) + self.compute_epipolar_loss(dist_f, None),
+            "loss_depth_flow_consis": dfc,
+            "loss_epipolar": epi,
             "loss_triangle": _zeros2(img), "loss_pnp": _zeros2(img), "loss_eight_point": _zeros2(img),
         }
-        return loss, GeomMasks(mbytes, dict(tex_b=tex_b, tex_f=tex_f, val_l=val_l, val_r=val_r, dist_b=dist_b, dist_f=dist_f), self)
+        return loss, GeomMasks(mbytes, dict(tex_b=tex_b, tex_f=tex_f, val_l=val_l, val_r=val_r), self, (flows_bwd[0], flows_fwd[0], Fm))
 
     def forward_losses(self, img_l, img, img_r, optical_flows_fwd, optical_flows_bwd, disp_list, disp_l_list, disp_r_list,
                        pose_vectors, K, K_inv, fused: bool = True) -> Tuple[Dict[str, Tensor], Dict]:

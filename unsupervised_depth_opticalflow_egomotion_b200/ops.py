@@ -350,6 +350,72 @@ def geom_flow_loss(img_l_pyr, img_pyr, img_r_pyr, flows_fwd, flows_bwd, disps, K
     return out[0], list(out[1:])
 
 
+class _GeomRigidFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow_b, flow_f, disp, mask_bytes, Kinv, P_b, P_f, F_b, F_f, need):
+        ts = [_dev(t, n) for t, n in ((flow_b, "flow_bwd"), (flow_f, "flow_fwd"), (disp, "disp"), (Kinv, "Kinv"), (P_b, "P_bwd"),
+                                      (P_f, "P_fwd"), (F_b, "F_bwd"), (F_f, "F_fwd"))]
+        flow_b, flow_f, disp, Kinv, P_b, P_f, F_b, F_f = ts
+        mask_bytes = _dev_u8(mask_bytes, "mask_bytes")
+        B, _, H, W = flow_b.shape
+        if (tuple(flow_f.shape) != (B, 2, H, W) or tuple(disp.shape) != (B, 1, H, W) or tuple(mask_bytes.shape) != (B, H, W)
+                or any(tuple(t.shape) != (B, 3, 4) for t in (P_b, P_f)) or any(tuple(t.shape) != (B, 3, 3) for t in (Kinv, F_b, F_f))):
+            raise ValueError("geom_rigid_terms: inconsistent shapes")
+        dev = flow_b.device
+        dfc, epi = torch.empty(B, device=dev, dtype=torch.float32), torch.empty(B, device=dev, dtype=torch.float32)
+        den = torch.empty((B, 2), device=dev, dtype=torch.float32)
+        a = _GeomRigidFn._args(flow_b, flow_f, disp, mask_bytes, Kinv, P_b, P_f, F_b, F_f, need, den)
+        a.loss_dfc, a.loss_epi = dfc.data_ptr(), epi.data_ptr()
+        with torch.cuda.device_of(flow_b):
+            _call("ugl_geom_rigid_forward", C.byref(a), launches=2)
+        ctx.save_for_backward(flow_b, flow_f, disp, mask_bytes, Kinv, P_b, P_f, F_b, F_f, den)
+        ctx.need = need
+        ctx.set_materialize_grads(False)
+        return dfc, epi
+
+    @staticmethod
+    def _args(flow_b, flow_f, disp, mask_bytes, Kinv, P_b, P_f, F_b, F_f, need, den):
+        a = _cabi.UglGeomRigidArgs()
+        B, _, H, W = flow_b.shape
+        a.batch, a.height, a.width = B, H, W
+        a.need[0], a.need[1] = int(need[0]), int(need[1])
+        a.flow_bwd, a.flow_fwd, a.disp, a.mask_bytes = flow_b.data_ptr(), flow_f.data_ptr(), disp.data_ptr(), mask_bytes.data_ptr()
+        a.Kinv, a.P_bwd, a.P_fwd, a.F_bwd, a.F_fwd = Kinv.data_ptr(), P_b.data_ptr(), P_f.data_ptr(), F_b.data_ptr(), F_f.data_ptr()
+        a.den = den.data_ptr()
+        n = int(_cabi.lib().ugl_geom_rigid_workspace_bytes(B, H, W))
+        a._ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=flow_b.device)      # kept alive by the struct object
+        a.workspace, a.workspace_bytes = a._ws.data_ptr(), _nbytes(a._ws)
+        a.stream = torch.cuda.current_stream().cuda_stream
+        return a
+
+    @staticmethod
+    def backward(ctx, g_dfc, g_epi):
+        flow_b, flow_f, disp, mask_bytes, Kinv, P_b, P_f, F_b, F_f, den = ctx.saved_tensors
+        if g_dfc is None and g_epi is None:
+            return (None,) * 10
+        B, dev = flow_b.shape[0], flow_b.device
+        g_dfc = _dev(g_dfc, "grad_dfc") if g_dfc is not None else None
+        g_epi = _dev(g_epi, "grad_epi") if g_epi is not None else None
+        gfb, gff, gd = torch.empty_like(flow_b), torch.empty_like(flow_f), torch.empty_like(disp)
+        gPb, gPf = torch.empty_like(P_b), torch.empty_like(P_f)
+        gFb, gFf = torch.empty_like(F_b), torch.empty_like(F_f)
+        a = _GeomRigidFn._args(flow_b, flow_f, disp, mask_bytes, Kinv, P_b, P_f, F_b, F_f, ctx.need, den)
+        a.grad_dfc, a.grad_epi = _ptr(g_dfc), _ptr(g_epi)
+        a.grad_flow_bwd, a.grad_flow_fwd, a.grad_disp = gfb.data_ptr(), gff.data_ptr(), gd.data_ptr()
+        a.grad_P_bwd, a.grad_P_fwd, a.grad_F_bwd, a.grad_F_fwd = gPb.data_ptr(), gPf.data_ptr(), gFb.data_ptr(), gFf.data_ptr()
+        with torch.cuda.device_of(flow_b):
+            _call("ugl_geom_rigid_backward", C.byref(a), launches=2)
+        return gfb, gff, gd, None, None, gPb, gPf, gFb, gFf, None
+
+
+def geom_rigid_terms(flow_bwd: Tensor, flow_fwd: Tensor, disp: Tensor, mask_bytes: Tensor, Kinv: Tensor, P_bwd: Tensor, P_fwd: Tensor,
+                     F_bwd: Tensor, F_fwd: Tensor, need=(MASK_ALL_BWD, MASK_ALL_FWD)):
+    """``loss_depth_flow_consis`` and ``loss_epipolar`` of ``Model_geometry.forward`` (model_geometry.py:921-935) at level 0, both
+    directions, one forward and one backward kernel -> ``(dfc (B,), epi (B,))``.  ``mask_bytes`` is level 0 of
+    :func:`geom_flow_loss`; differentiable w.r.t. the flows, the disparity, ``P_*`` and ``F_*``."""
+    return _GeomRigidFn.apply(flow_bwd, flow_fwd, disp, mask_bytes, Kinv, P_bwd, P_fwd, F_bwd, F_fwd, tuple(need))
+
+
 def unpack_mask(mask_bytes: Tensor, bits: int, invert: bool = False) -> Tensor:
     """``(B,h,w)`` packed map -> ``(B,1,h,w)`` float {0,1} mask: 1 where every bit of ``bits`` is set (plain torch; off the
     hot path — the kernels consume the packed maps directly)."""
