@@ -125,6 +125,19 @@ int ugl_geom_flow_combine(const UglGeomFlowArgs* args);
 int ugl_image_pyramid(const float* img, int32_t batch, int32_t channels, int32_t height, int32_t width,
                       int32_t levels, int32_t mode, float* const* out, void* stream);
 
+/* The same pyramids for up to three images, both modes and all levels (2..4) in ONE launch: box[i][l] / bil[i][l] are the
+ * level-l outputs (B,C,H>>l,W>>l) of image i in mode 0 / mode 1, NULL = not wanted.  H*W planes must be 16-byte aligned
+ * (W divisible by 2^(levels-1) and a 16-byte aligned base).  Same per-output arithmetic as ugl_image_pyramid. */
+#define UGL_PYRAMID_MAX_IMAGES 3
+typedef struct UglPyramidArgs {
+  int32_t batch, channels, height, width, levels, images;
+  const float* img[UGL_PYRAMID_MAX_IMAGES];
+  float* box[UGL_PYRAMID_MAX_IMAGES][UGL_MAX_LEVELS];
+  float* bil[UGL_PYRAMID_MAX_IMAGES][UGL_MAX_LEVELS];
+  void* stream;
+} UglPyramidArgs;
+int ugl_image_pyramid_multi(const UglPyramidArgs* args);
+
 /* ---------------------------------------------------------------------------------------------
  * warp_flow — structures/net_utils.py:16-54.  out = grid_sample(x, (j+u, i+v)) [* keep mask].
  * backward: grad_flow (B,2,H,W) always; grad_x (B,C,H,W) if non-null (deterministic: fixed-point

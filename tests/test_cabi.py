@@ -55,7 +55,8 @@ def test_struct_layouts_match_the_c_compiler(tmp_path):
     import os
     import subprocess
     structs = {"UglFlowLossArgs": _cabi.UglFlowLossArgs, "UglDepthPhotoArgs": _cabi.UglDepthPhotoArgs, "UglGeomFlowArgs": _cabi.UglGeomFlowArgs,
-               "UglDispSmoothArgs": _cabi.UglDispSmoothArgs, "UglGeomRigidArgs": _cabi.UglGeomRigidArgs}
+               "UglDispSmoothArgs": _cabi.UglDispSmoothArgs, "UglGeomRigidArgs": _cabi.UglGeomRigidArgs,
+               "UglPyramidArgs": _cabi.UglPyramidArgs}
     lines = []
     for name, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))

@@ -74,3 +74,19 @@ def test_forward_splat_extension(cuda_device):
     occ = losses.FlowLoss(1).get_occlusion_mask_from_flow((2, 1, 24, 40), flow.to(cuda_device))
     assert occ.shape == (2, 1, 24, 40) and float(occ.min()) >= 0.0 and float(occ.max()) <= 1.0
     assert rel_err(occ, P.forward_splat(torch.ones(2, 1, 24, 40), flow).clamp(0, 1)) < 1e-5
+
+
+@pytest.mark.parametrize("levels,H,W", [(2, 34, 50), (3, 64, 208), (4, 64, 208), (4, 256, 832), (5, 64, 128)])
+def test_image_pyramids_one_launch_bit_equal(cuda_device, levels, H, W):
+    """ops.image_pyramids (all levels, both modes, three images in one launch; per-level fallback outside 2..4 levels or for
+    unaligned sizes) is bit-identical to the per-level kernel"""
+    g = torch.Generator().manual_seed(3)
+    imgs = [torch.rand(2, 3, H, W, generator=g).to(cuda_device) for _ in range(3)]
+    out = ops.image_pyramids(imgs, levels, ("bilinear", ("bilinear", "area"), "box"))
+    assert set(out[0]) == {"bilinear"} and set(out[1]) == {"bilinear", "area"} and set(out[2]) == {"box"}
+    for i, d in enumerate(out):
+        for mode, pyr in d.items():
+            ref = ops.image_pyramid(imgs[i], levels, mode)
+            assert len(pyr) == levels and pyr[0] is not None
+            for l in range(levels):
+                assert torch.equal(pyr[l], ref[l]), (i, mode, l)

@@ -86,6 +86,15 @@ class UglDispSmoothArgs(C.Structure):
     ]
 
 
+class UglPyramidArgs(C.Structure):
+    """Mirror of ``struct UglPyramidArgs`` (include/ugl.h)."""
+
+    MAX_IMAGES = 3
+    _LL = (C.c_void_p * MAX_LEVELS) * MAX_IMAGES
+    _fields_ = [("batch", C.c_int32), ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("levels", C.c_int32),
+                ("images", C.c_int32), ("img", C.c_void_p * MAX_IMAGES), ("box", _LL), ("bil", _LL), ("stream", C.c_void_p)]
+
+
 class UglGeomRigidArgs(C.Structure):
     """Mirror of ``struct UglGeomRigidArgs`` (include/ugl.h)."""
 
@@ -142,6 +151,7 @@ SIGNATURES.update({
     "ugl_flow_consis_backward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "ugl_depth_diff_forward": (C.c_int, [_p, _p, _i64, _p, _p]),
     "ugl_depth_diff_backward": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
+    "ugl_image_pyramid_multi": (C.c_int, [C.POINTER(UglPyramidArgs)]),
     "ugl_geom_rigid_workspace_bytes": (_u64, [_i, _i, _i]),
     "ugl_geom_rigid_forward": (C.c_int, [C.POINTER(UglGeomRigidArgs)]),
     "ugl_geom_rigid_backward": (C.c_int, [C.POINTER(UglGeomRigidArgs)]),

@@ -11,6 +11,13 @@
 #include "ugl_geometry.cuh"
 #include "ugl_reduce.cuh"
 
+#ifndef UGL_DP_FWD_MINB
+#define UGL_DP_FWD_MINB 3
+#endif
+#ifndef UGL_DP_BWD_MINB
+#define UGL_DP_BWD_MINB 2
+#endif
+
 namespace ugl {
 
 struct DepthPhotoLevel {
@@ -88,29 +95,28 @@ __device__ __forceinline__ void depth_pixel(const DepthPhotoLevel& L, const floa
   }
 }
 
-__global__ void __launch_bounds__(kRedThreads) depth_photo_fwd_kernel(const __grid_constant__ DepthPhotoParams p) {
-  __shared__ float sK[9], sP[2][12];
-  __shared__ float red[(kRedThreads / 32) * 4];
-  const int b = blockIdx.y, l = blockIdx.z;
+// grid (chunks, B, 2 * levels): the two directions of a level run in separate CTAs (half the live state per thread, twice the
+// CTAs in flight: the kernel is bound by the latency of its gathers, not by bytes)
+__global__ void __launch_bounds__(kRedThreads, UGL_DP_FWD_MINB) depth_photo_fwd_kernel(const __grid_constant__ DepthPhotoParams p) {
+  __shared__ float sK[9], sP[12];
+  __shared__ float red[(kRedThreads / 32) * 2];
+  const int b = blockIdx.y, l = blockIdx.z >> 1, dir = blockIdx.z & 1;
   const DepthPhotoLevel& L = p.lv[l];
   if (threadIdx.x < 9) sK[threadIdx.x] = L.Kinv[b * 9 + threadIdx.x];
-  if (threadIdx.x < 24) sP[threadIdx.x / 12][threadIdx.x % 12] = L.P[threadIdx.x / 12][b * 12 + threadIdx.x % 12];
+  if (threadIdx.x < 12) sP[threadIdx.x] = L.P[dir][b * 12 + threadIdx.x];
   __syncthreads();
   const WarpGeom g = make_warp_geom(L.w, L.h);
   const long plane = (long)L.h * L.w;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[2] = {0.f, 0.f};
   for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
     const int i = (int)(px / L.w), j = (int)(px % L.w);
-#pragma unroll
-    for (int dir = 0; dir < 2; ++dir) {
-      DepthPixel o;
-      depth_pixel<false>(L, sK, sP[dir], b, dir, i, j, px, g, o, nullptr, nullptr, 0.f);
-      acc[2 * dir] += (fabsf(o.I[0] - o.rec[0]) + fabsf(o.I[1] - o.rec[1]) + fabsf(o.I[2] - o.rec[2])) * o.mask;
-      acc[2 * dir + 1] += o.mask;
-    }
+    DepthPixel o;
+    depth_pixel<false>(L, sK, sP, b, dir, i, j, px, g, o, nullptr, nullptr, 0.f);
+    acc[0] += (fabsf(o.I[0] - o.rec[0]) + fabsf(o.I[1] - o.rec[1]) + fabsf(o.I[2] - o.rec[2])) * o.mask;
+    acc[1] += o.mask;
   }
-  const float v = block_reduce_n<kRedThreads, 4>(acc, red);
-  if (threadIdx.x < 4) p.partials[(((long)b * p.scales + l) * p.chunks + blockIdx.x) * 4 + threadIdx.x] = v;
+  const float v = block_reduce_n<kRedThreads, 2>(acc, red);
+  if (threadIdx.x < 2) p.partials[(((long)b * p.scales + l) * p.chunks + blockIdx.x) * 4 + 2 * dir + threadIdx.x] = v;
 }
 
 // one warp per sample: per level fixed-order fp64 sum of the chunk partials, closing formula, sum over levels
@@ -143,39 +149,35 @@ __global__ void depth_photo_finalize_kernel(const __grid_constant__ DepthPhotoPa
   if (lane == 0) p.loss[b] = total;
 }
 
-__global__ void __launch_bounds__(kRedThreads) depth_photo_bwd_kernel(const __grid_constant__ DepthPhotoParams p) {
-  __shared__ float sK[9], sP[2][12];
-  __shared__ float red[(kRedThreads / 32) * 24];
-  const int b = blockIdx.y, l = blockIdx.z;
+// grid (chunks, B, 2 * levels), one direction per CTA.  grad_disp receives exactly two contributions per pixel (one per
+// direction) by atomicAdd onto a zeroed map: fl(0 + a + b) == fl(0 + b + a), so the result does not depend on their order.
+__global__ void __launch_bounds__(kRedThreads, UGL_DP_BWD_MINB) depth_photo_bwd_kernel(const __grid_constant__ DepthPhotoParams p) {
+  __shared__ float sK[9], sP[12];
+  __shared__ float red[(kRedThreads / 32) * 12];
+  const int b = blockIdx.y, l = blockIdx.z >> 1, dir = blockIdx.z & 1;
   const DepthPhotoLevel& L = p.lv[l];
   if (threadIdx.x < 9) sK[threadIdx.x] = L.Kinv[b * 9 + threadIdx.x];
-  if (threadIdx.x < 24) sP[threadIdx.x / 12][threadIdx.x % 12] = L.P[threadIdx.x / 12][b * 12 + threadIdx.x % 12];
+  if (threadIdx.x < 12) sP[threadIdx.x] = L.P[dir][b * 12 + threadIdx.x];
   __syncthreads();
   const WarpGeom g = make_warp_geom(L.w, L.h);
   const long plane = (long)L.h * L.w;
   const float hw = (float)L.h * (float)L.w;
-  float ks[2];
+  const float ks = p.gloss[b] / (3.0f * hw) / p.den[((long)b * p.scales + l) * 2 + dir];
+  float acc[12];
 #pragma unroll
-  for (int dir = 0; dir < 2; ++dir) ks[dir] = p.gloss[b] / (3.0f * hw) / p.den[((long)b * p.scales + l) * 2 + dir];
-  float acc[24];
-#pragma unroll
-  for (int k = 0; k < 24; ++k) acc[k] = 0.f;
+  for (int k = 0; k < 12; ++k) acc[k] = 0.f;
   for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
     const int i = (int)(px / L.w), j = (int)(px % L.w);
-    float gD = 0.f;
-#pragma unroll
-    for (int dir = 0; dir < 2; ++dir) {
-      DepthPixel o;
-      float gix, giy;
-      depth_pixel<true>(L, sK, sP[dir], b, dir, i, j, px, g, o, &gix, &giy, ks[dir]);
-      const float g_u = o.nc.ox ? 0.f : gix * g.sx;
-      const float g_v = o.nc.oy ? 0.f : giy * g.sy;
-      gD += project_backward(o.pr, sP[dir], g_u, g_v, 0.f, acc + 12 * dir);
-    }
-    L.grad_disp[(long)b * plane + px] = gD;
+    DepthPixel o;
+    float gix, giy;
+    depth_pixel<true>(L, sK, sP, b, dir, i, j, px, g, o, &gix, &giy, ks);
+    const float g_u = o.nc.ox ? 0.f : gix * g.sx;
+    const float g_v = o.nc.oy ? 0.f : giy * g.sy;
+    const float gD = project_backward(o.pr, sP, g_u, g_v, 0.f, acc);
+    atomicAdd(&L.grad_disp[(long)b * plane + px], gD);
   }
-  const float v = block_reduce_n<kRedThreads, 24>(acc, red);
-  if (threadIdx.x < 24) p.partials[(((long)b * p.scales + l) * p.chunks + blockIdx.x) * 24 + threadIdx.x] = v;
+  const float v = block_reduce_n<kRedThreads, 12>(acc, red);
+  if (threadIdx.x < 12) p.partials[(((long)b * p.scales + l) * p.chunks + blockIdx.x) * 24 + 12 * dir + threadIdx.x] = v;
 }
 
 // one warp per (sample, level): grad_P[dir][level][b] = fixed-order sum of the chunk partials
@@ -245,7 +247,7 @@ extern "C" int ugl_depth_photo_forward(const UglDepthPhotoArgs* a) {
   if (rc) return rc;
   if (!a->loss) return fail(UGL_EINVAL, "depth_photo_forward: null loss");
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
-  depth_photo_fwd_kernel<<<dim3(p.chunks, p.B, p.scales), kRedThreads, 0, st>>>(p);
+  depth_photo_fwd_kernel<<<dim3(p.chunks, p.B, 2 * p.scales), kRedThreads, 0, st>>>(p);
   if ((rc = check_launch("depth_photo_fwd_kernel"))) return rc;
   depth_photo_finalize_kernel<<<(p.B + 3) / 4, 128, 0, st>>>(p);
   return check_launch("depth_photo_finalize_kernel");
@@ -257,7 +259,11 @@ extern "C" int ugl_depth_photo_backward(const UglDepthPhotoArgs* a) {
   if (rc) return rc;
   if (!a->grad_loss) return fail(UGL_EINVAL, "depth_photo_backward: null grad_loss");
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
-  depth_photo_bwd_kernel<<<dim3(p.chunks, p.B, p.scales), kRedThreads, 0, st>>>(p);
+  for (int l = 0; l < p.scales; ++l) {     // the two directions accumulate into grad_disp
+    const cudaError_t e = cudaMemsetAsync(p.lv[l].grad_disp, 0, sizeof(float) * (size_t)p.B * p.lv[l].h * p.lv[l].w, st);
+    if (e != cudaSuccess) return fail((int)e, "depth_photo_backward: memset: %s", cudaGetErrorString(e));
+  }
+  depth_photo_bwd_kernel<<<dim3(p.chunks, p.B, 2 * p.scales), kRedThreads, 0, st>>>(p);
   if ((rc = check_launch("depth_photo_bwd_kernel"))) return rc;
   depth_photo_bwd_finalize_kernel<<<(p.B * p.scales + 3) / 4, 128, 0, st>>>(p);
   return check_launch("depth_photo_bwd_finalize_kernel");

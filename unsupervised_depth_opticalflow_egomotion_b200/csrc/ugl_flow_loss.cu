@@ -166,6 +166,41 @@ __global__ void __launch_bounds__(256) flow_combine_kernel(const __grid_constant
   if (kGeom) {   // the L1 scale depends on the pixel's dynamic-mask bit
     const GeomCombineScales kg = geom_combine_scales(p.stats + ((long)b * p.scales + l) * GA_COUNT, L.h, L.w, p.gloss, p.B, b);
     const unsigned char* mask = gp.mask_bytes[l] + (long)b * plane;
+    if ((plane & 3) == 0) {   // four pixels per thread: 128-bit basis loads, one 32-bit load of the four mask bytes
+      const float4* b4 = reinterpret_cast<const float4*>(basis);
+      const unsigned* m4 = reinterpret_cast<const unsigned*>(mask);
+      float4* gf4 = reinterpret_cast<float4*>(gf);
+      float4* gb4 = reinterpret_cast<float4*>(gb);
+      const int q = plane >> 2;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q; i += gridDim.x * blockDim.x) {
+        const unsigned bits = m4[i];
+        float kf[4], kb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const unsigned bt = bits >> (8 * e);
+          kf[e] = (bt & kMaskDynF) ? kg.pix_r[0] : kg.pix_d[0];
+          kb[e] = (bt & kMaskDynB) ? kg.pix_r[1] : kg.pix_d[1];
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const float4 a0 = __ldcs(b4 + (0 + ch) * q + i), a1 = __ldcs(b4 + (2 + ch) * q + i), a2 = __ldcs(b4 + (4 + ch) * q + i),
+                       a3 = __ldcs(b4 + (6 + ch) * q + i);
+          const float4 c0 = __ldcs(b4 + (8 + ch) * q + i), c1 = __ldcs(b4 + (10 + ch) * q + i), c2 = __ldcs(b4 + (12 + ch) * q + i);
+          float4 f, g;
+          f.x = kf[0] * a0.x + kg.ssim[0] * a1.x + kg.sm * a2.x + kg.cons * a3.x;
+          f.y = kf[1] * a0.y + kg.ssim[0] * a1.y + kg.sm * a2.y + kg.cons * a3.y;
+          f.z = kf[2] * a0.z + kg.ssim[0] * a1.z + kg.sm * a2.z + kg.cons * a3.z;
+          f.w = kf[3] * a0.w + kg.ssim[0] * a1.w + kg.sm * a2.w + kg.cons * a3.w;
+          g.x = kb[0] * c0.x + kg.ssim[1] * c1.x + kg.sm * c2.x;
+          g.y = kb[1] * c0.y + kg.ssim[1] * c1.y + kg.sm * c2.y;
+          g.z = kb[2] * c0.z + kg.ssim[1] * c1.z + kg.sm * c2.z;
+          g.w = kb[3] * c0.w + kg.ssim[1] * c1.w + kg.sm * c2.w;
+          gf4[ch * q + i] = f;
+          gb4[ch * q + i] = g;
+        }
+      }
+      return;
+    }
     for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < plane; pix += gridDim.x * blockDim.x)
       geom_combine_pixel(basis, mask, plane, pix, kg, gf, gb);
     return;

@@ -38,30 +38,29 @@ __device__ __forceinline__ void rigid_load_mats(const RigidTermsParams& p, int b
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kRedThreads) rigid_terms_fwd_kernel(const __grid_constant__ RigidTermsParams p) {
+// grid (chunks, B, 2): one direction per CTA (the kernels are latency-bound: half the live state, twice the CTAs in flight)
+__global__ void __launch_bounds__(kRedThreads, 3) rigid_terms_fwd_kernel(const __grid_constant__ RigidTermsParams p) {
   __shared__ float sm[51];
-  __shared__ float red[(kRedThreads / 32) * 6];
-  const int b = blockIdx.y;
+  __shared__ float red[(kRedThreads / 32) * 3];
+  const int b = blockIdx.y, d = blockIdx.z;
   rigid_load_mats(p, b, sm);
   const long plane = (long)p.H * p.W;
-  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float acc[3] = {0.f, 0.f, 0.f};
   for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
     const int i = (int)(px / p.W), j = (int)(px % p.W);
     const float D = p.disp[(long)b * plane + px];
     const unsigned bits = p.mask[(long)b * plane + px];
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const float u = p.flow[d][((long)b * 2) * plane + px], v = p.flow[d][((long)b * 2 + 1) * plane + px];
-      const Projected r = project_pixel(sm, sm + 9 + 12 * d, D, j, i);
-      const float du = fabsf(sub_rn(sub_rn(r.u, (float)j), u)), dv = fabsf(sub_rn(sub_rn(r.v, (float)i), v));
-      const float m = (bits & p.need[d]) == p.need[d] ? 1.f : 0.f;
-      acc[2 * d] += (du + dv) * m;
-      acc[2 * d + 1] += m;
-      acc[4 + d] += epipolar_pixel(sm + 33 + 9 * d, u, v, j, i).dist;
-    }
+    const float u = p.flow[d][((long)b * 2) * plane + px], v = p.flow[d][((long)b * 2 + 1) * plane + px];
+    const Projected r = project_pixel(sm, sm + 9 + 12 * d, D, j, i);
+    const float du = fabsf(sub_rn(sub_rn(r.u, (float)j), u)), dv = fabsf(sub_rn(sub_rn(r.v, (float)i), v));
+    const float m = (bits & p.need[d]) == p.need[d] ? 1.f : 0.f;
+    acc[0] += (du + dv) * m;
+    acc[1] += m;
+    acc[2] += epipolar_pixel(sm + 33 + 9 * d, u, v, j, i).dist;
   }
-  const float v = block_reduce_n<kRedThreads, 6>(acc, red);
-  if (threadIdx.x < 6) p.partials[((long)b * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = v;
+  const float v = block_reduce_n<kRedThreads, 3>(acc, red);
+  // partial row layout [dfc_b, m_b, dfc_f, m_f, epi_b, epi_f]
+  if (threadIdx.x < 3) p.partials[((long)b * gridDim.x + blockIdx.x) * 6 + (threadIdx.x < 2 ? 2 * d + threadIdx.x : 4 + d)] = v;
 }
 
 struct RigidTermsFinal {
@@ -75,48 +74,47 @@ struct RigidTermsFinal {
   }
 };
 
-__global__ void __launch_bounds__(kRedThreads) rigid_terms_bwd_kernel(const __grid_constant__ RigidTermsParams p) {
+// grid (chunks, B, 2), one direction per CTA; grad_disp gets its two contributions by atomicAdd onto a zeroed map (order-free: two addends)
+__global__ void __launch_bounds__(kRedThreads, 2) rigid_terms_bwd_kernel(const __grid_constant__ RigidTermsParams p) {
   __shared__ float sm[51];
-  __shared__ float red[(kRedThreads / 32) * 42];
-  const int b = blockIdx.y;
+  __shared__ float red[(kRedThreads / 32) * 21];
+  const int b = blockIdx.y, d = blockIdx.z;
   rigid_load_mats(p, b, sm);
   const long plane = (long)p.H * p.W;
   const float hw = (float)p.H * (float)p.W;
   const float gd = p.g_dfc ? p.g_dfc[b] : 0.f, ge = (p.g_epi ? p.g_epi[b] : 0.f) / hw;
-  float acc[42];                                    // P_bwd (12), P_fwd (12), F_bwd (9), F_fwd (9)
+  const float kd = gd / (2.0f * hw) / p.den[b * 2 + d];
+  const float* Pd = sm + 9 + 12 * d;
+  float acc[21];                                    // P (12), F (9) of this direction
 #pragma unroll
-  for (int k = 0; k < 42; ++k) acc[k] = 0.f;
+  for (int k = 0; k < 21; ++k) acc[k] = 0.f;
   for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
     const int i = (int)(px / p.W), j = (int)(px % p.W);
     const float D = p.disp[(long)b * plane + px];
     const unsigned bits = p.mask[(long)b * plane + px];
-    float gD = 0.f;
+    const float u = p.flow[d][((long)b * 2) * plane + px], v = p.flow[d][((long)b * 2 + 1) * plane + px];
+    const Projected r = project_pixel(sm, Pd, D, j, i);
+    const float m = (bits & p.need[d]) == p.need[d] ? 1.f : 0.f;
+    const float k = kd * m;
+    const float su = sgnf(sub_rn(sub_rn(r.u, (float)j), u)) * k, sv = sgnf(sub_rn(sub_rn(r.v, (float)i), v)) * k;   // d/d rigid flow
+    const float gD = project_backward(r, Pd, su, sv, 0.f, acc);
+    atomicAdd(&p.gdisp[(long)b * plane + px], gD);
+    // epipolar distance
+    const Epi e = epipolar_pixel(sm + 33 + 9 * d, u, v, j, i);
+    const float s = sgnf(e.n) * ge / e.d;
+    p.gflow[d][((long)b * 2) * plane + px] = s * e.l[0] - su;
+    p.gflow[d][((long)b * 2 + 1) * plane + px] = s * e.l[1] - sv;
+    const float t = e.r > 0.f ? -ge * fabsf(e.n) / (e.d * e.d) / e.r : 0.f;
+    const float gl[3] = {s * e.p2[0] + t * e.l[0], s * e.p2[1] + t * e.l[1], s * e.p2[2]};
+    const float p1[3] = {(float)j, (float)i, 1.0f};
 #pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const float u = p.flow[d][((long)b * 2) * plane + px], v = p.flow[d][((long)b * 2 + 1) * plane + px];
-      const float* Pd = sm + 9 + 12 * d;
-      const Projected r = project_pixel(sm, Pd, D, j, i);
-      const float m = (bits & p.need[d]) == p.need[d] ? 1.f : 0.f;
-      const float k = gd / (2.0f * hw) / p.den[b * 2 + d] * m;
-      const float su = sgnf(sub_rn(sub_rn(r.u, (float)j), u)) * k, sv = sgnf(sub_rn(sub_rn(r.v, (float)i), v)) * k;   // d/d rigid flow
-      gD += project_backward(r, Pd, su, sv, 0.f, acc + 12 * d);
-      // epipolar distance
-      const Epi e = epipolar_pixel(sm + 33 + 9 * d, u, v, j, i);
-      const float s = sgnf(e.n) * ge / e.d;
-      p.gflow[d][((long)b * 2) * plane + px] = s * e.l[0] - su;
-      p.gflow[d][((long)b * 2 + 1) * plane + px] = s * e.l[1] - sv;
-      const float t = e.r > 0.f ? -ge * fabsf(e.n) / (e.d * e.d) / e.r : 0.f;
-      const float gl[3] = {s * e.p2[0] + t * e.l[0], s * e.p2[1] + t * e.l[1], s * e.p2[2]};
-      const float p1[3] = {(float)j, (float)i, 1.0f};
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[24 + 9 * d + a * 3 + c] += gl[a] * p1[c];
-    }
-    p.gdisp[(long)b * plane + px] = gD;
+      for (int c = 0; c < 3; ++c) acc[12 + a * 3 + c] += gl[a] * p1[c];
   }
-  const float v = block_reduce_n<kRedThreads, 42>(acc, red);
-  if (threadIdx.x < 42) p.partials[((long)b * gridDim.x + blockIdx.x) * 42 + threadIdx.x] = v;
+  const float v = block_reduce_n<kRedThreads, 21>(acc, red);
+  // partial row layout [P_bwd (12), P_fwd (12), F_bwd (9), F_fwd (9)]
+  if (threadIdx.x < 21) p.partials[((long)b * gridDim.x + blockIdx.x) * 42 + (threadIdx.x < 12 ? 12 * d + threadIdx.x : 24 + 9 * d + threadIdx.x - 12)] = v;
 }
 
 struct RigidTermsBwdFinal {
@@ -161,7 +159,7 @@ extern "C" int ugl_geom_rigid_forward(const UglGeomRigidArgs* a) {
   if (rc) return rc;
   if (!a->loss_dfc || !a->loss_epi) return fail(UGL_EINVAL, "geom_rigid_forward: null output");
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
-  rigid_terms_fwd_kernel<<<dim3(p.chunks, p.B), kRedThreads, 0, st>>>(p);
+  rigid_terms_fwd_kernel<<<dim3(p.chunks, p.B, 2), kRedThreads, 0, st>>>(p);
   if ((rc = check_launch("rigid_terms_fwd_kernel"))) return rc;
   RigidTermsFinal fin{a->loss_dfc, a->loss_epi, a->den, (float)p.H * (float)p.W};
   sample_finalize_kernel<6><<<(p.B + 3) / 4, 128, 0, st>>>(p.partials, p.chunks, p.B, fin);
@@ -178,7 +176,9 @@ extern "C" int ugl_geom_rigid_backward(const UglGeomRigidArgs* a) {
   p.g_dfc = a->grad_dfc; p.g_epi = a->grad_epi;     // either may be null (= zero upstream gradient)
   p.gflow[0] = a->grad_flow_bwd; p.gflow[1] = a->grad_flow_fwd; p.gdisp = a->grad_disp;
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
-  rigid_terms_bwd_kernel<<<dim3(p.chunks, p.B), kRedThreads, 0, st>>>(p);
+  const cudaError_t e = cudaMemsetAsync(p.gdisp, 0, sizeof(float) * (size_t)p.B * p.H * p.W, st);
+  if (e != cudaSuccess) return fail((int)e, "geom_rigid_backward: memset: %s", cudaGetErrorString(e));
+  rigid_terms_bwd_kernel<<<dim3(p.chunks, p.B, 2), kRedThreads, 0, st>>>(p);
   if ((rc = check_launch("rigid_terms_bwd_kernel"))) return rc;
   RigidTermsBwdFinal fin{a->grad_P_bwd, a->grad_P_fwd, a->grad_F_bwd, a->grad_F_fwd};
   sample_finalize_kernel<42><<<(p.B + 3) / 4, 128, 0, st>>>(p.partials, p.chunks, p.B, fin);

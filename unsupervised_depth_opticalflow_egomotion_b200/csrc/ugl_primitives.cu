@@ -100,6 +100,74 @@ fixed_to_float_clamp_kernel(const unsigned long long* __restrict__ acc, long n, 
   }
 }
 
+// All levels, both modes and up to three images in one launch: one thread per F x F block of a full-resolution plane
+// (F = 2^(levels-1)) keeps the block in registers and emits every level's outputs that fall inside it, with the same
+// per-output arithmetic as pyramid_pixel (row-major box sums / horizontal-then-vertical lerp).
+struct PyramidMultiParams {
+  int planes, H, W, levels, images;
+  const float* img[UGL_PYRAMID_MAX_IMAGES];
+  float* box[UGL_PYRAMID_MAX_IMAGES][kMaxLevels];
+  float* bil[UGL_PYRAMID_MAX_IMAGES][kMaxLevels];
+};
+
+template <int F>
+__global__ void __launch_bounds__(kPrimThreads) pyramid_multi_kernel(const __grid_constant__ PyramidMultiParams p) {
+  const int im = blockIdx.y;
+  const int ch = p.H / F, cw = p.W / F;
+  const long n = (long)p.planes * ch * cw;
+  const float* img = p.img[im];
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    const int cj = (int)(idx % cw);
+    const long r = idx / cw;
+    const int ci = (int)(r % ch);
+    const long pl = r / ch;
+    const float* src = img + pl * (long)p.H * p.W + (long)ci * F * p.W + (long)cj * F;
+    float v[F][F];
+#pragma unroll
+    for (int y = 0; y < F; ++y) {
+      if (F >= 4) {
+#pragma unroll
+        for (int x = 0; x < F; x += 4) {
+          const float4 q = *reinterpret_cast<const float4*>(src + (long)y * p.W + x);
+          v[y][x] = q.x; v[y][x + 1] = q.y; v[y][x + 2] = q.z; v[y][x + 3] = q.w;
+        }
+      } else {
+        const float2 q = *reinterpret_cast<const float2*>(src + (long)y * p.W);
+        v[y][0] = q.x; v[y][1] = q.y;
+      }
+    }
+#pragma unroll
+    for (int l = 1; l < 4; ++l) {
+      const int g = 1 << l;
+      if (g > F) break;
+      const int ow = p.W >> l;
+      const long obase = pl * (long)(p.H >> l) * ow;
+      float* ob = p.box[im][l];
+      float* ol = p.bil[im][l];
+#pragma unroll
+      for (int by = 0; by < F / g; ++by)
+#pragma unroll
+        for (int bx = 0; bx < F / g; ++bx) {
+          const long o = obase + (long)(ci * (F / g) + by) * ow + (cj * (F / g) + bx);
+          if (ob) {
+            float sum = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < g; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < g; ++dx) sum = add_rn(sum, v[by * g + dy][bx * g + dx]);
+            ob[o] = div_rn(sum, (float)(g * g));
+          }
+          if (ol) {
+            const int y = by * g + g / 2 - 1, x = bx * g + g / 2 - 1;
+            const float top = add_rn(mul_rn(0.5f, v[y][x]), mul_rn(0.5f, v[y][x + 1]));
+            const float bot = add_rn(mul_rn(0.5f, v[y + 1][x]), mul_rn(0.5f, v[y + 1][x + 1]));
+            ol[o] = add_rn(mul_rn(0.5f, top), mul_rn(0.5f, bot));
+          }
+        }
+    }
+  }
+}
+
 static int grid_for(long n) {
   long g = (n + kPrimThreads - 1) / kPrimThreads;
   const long cap = 148L * 16;   // 148 SMs x a few resident CTAs, grid-stride beyond that
@@ -126,6 +194,33 @@ extern "C" int ugl_image_pyramid(const float* img, int32_t B, int32_t C, int32_t
     if (rc) return rc;
   }
   return UGL_OK;
+}
+
+extern "C" int ugl_image_pyramid_multi(const UglPyramidArgs* a) {
+  if (!a) return fail(UGL_EINVAL, "image_pyramid_multi: null args");
+  if (a->batch <= 0 || a->channels <= 0 || a->height <= 0 || a->width <= 0 || a->images < 1 || a->images > UGL_PYRAMID_MAX_IMAGES)
+    return fail(UGL_EINVAL, "image_pyramid_multi: bad arguments");
+  if (a->levels < 2 || a->levels > 4) return fail(UGL_EUNSUPPORTED, "image_pyramid_multi: levels must be 2..4 (got %d)", a->levels);
+  const int f = 1 << (a->levels - 1);
+  if (a->height % f || a->width % f) return fail(UGL_EUNSUPPORTED, "image_pyramid_multi: %dx%d not divisible by %d", a->height, a->width, f);
+  PyramidMultiParams p;
+  p.planes = a->batch * a->channels; p.H = a->height; p.W = a->width; p.levels = a->levels; p.images = a->images;
+  for (int i = 0; i < a->images; ++i) {
+    if (!a->img[i]) return fail(UGL_EINVAL, "image_pyramid_multi: null image %d", i);
+    if (reinterpret_cast<uintptr_t>(a->img[i]) & 15u) return fail(UGL_EALIGN, "image_pyramid_multi: image %d not 16-byte aligned", i);
+    p.img[i] = a->img[i];
+    for (int l = 0; l < kMaxLevels; ++l) {
+      p.box[i][l] = (l >= 1 && l < a->levels) ? a->box[i][l] : nullptr;
+      p.bil[i][l] = (l >= 1 && l < a->levels) ? a->bil[i][l] : nullptr;
+    }
+  }
+  const long n = (long)p.planes * (p.H / f) * (p.W / f);
+  const dim3 grid(grid_for(n), a->images);
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  if (f == 2) pyramid_multi_kernel<2><<<grid, kPrimThreads, 0, st>>>(p);
+  else if (f == 4) pyramid_multi_kernel<4><<<grid, kPrimThreads, 0, st>>>(p);
+  else pyramid_multi_kernel<8><<<grid, kPrimThreads, 0, st>>>(p);
+  return check_launch("pyramid_multi_kernel");
 }
 
 extern "C" int ugl_warp_flow_forward(const float* x, const float* flow, int32_t B, int32_t C, int32_t H, int32_t W,

@@ -128,9 +128,10 @@ class FlowLoss(_LossBase):
         """Loss body of ``Model_flow.forward`` (model_flow.py:232-254).  ``fused=True`` runs the single fused
         kernel pair; ``fused=False`` composes the per-method kernels exactly like the reference does."""
         L = len(optical_flows_fwd)
-        pl, pc, pr = (self.generate_img_pyramid(x, L) for x in (imgl, img, imgr))
-        if fused:
+        if fused:   # the three box pyramids in one launch, then the fused kernels
+            pl, pc, pr = (d["box"] for d in ops.image_pyramids((imgl, img, imgr), L, ("box", "box", "box")))
             return ops.flow_loss(pl, pc, pr, optical_flows_fwd, optical_flows_bwd, self.num_scales)
+        pl, pc, pr = (self.generate_img_pyramid(x, L) for x in (imgl, img, imgr))
         from_l = self.warp_flow_pyramid(pl, optical_flows_bwd)
         from_r = self.warp_flow_pyramid(pr, optical_flows_fwd)
         diff_bwd, diff_fwd, w_bwd, w_fwd = self.compute_diff_weight(from_l, pc, from_r)
@@ -167,14 +168,16 @@ class DepthLoss(_LossBase):
         """Loss body of ``Model_depth.forward`` (model_depth.py:281-335) / model_depth_texture.py:262-311.  ``fused=True``
         (live variant) runs the reprojection + texture mask + masked L1 of both directions and all levels as one kernel."""
         S = self.num_scales
-        pl, pc, pr = (self.generate_img_pyramid(x, S) for x in (img_l, img, img_r))
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
         if fused:
             Kinv, (P_b, P_f), _ = self._pose_setup(img.size(2), K, disp_list, pose_vectors)
+            pyr = ops.image_pyramids((img, img_l, img_r), S, ("bilinear", ("bilinear", "area"), ("bilinear", "area")))   # one launch
+            pc, pl, pr = (d["bilinear"] for d in pyr)
         else:
             Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
+            pl, pc, pr = (self.generate_img_pyramid(x, S) for x in (img_l, img, img_r))
         if fused and self.variant == "live":
-            area = (ops.image_pyramid(img_l, S, "area"), ops.image_pyramid(img_r, S, "area"))
+            area = (pyr[1]["area"], pyr[2]["area"])
             pix, valid, tex = ops.depth_photo_loss(pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f))
             loss = {"loss_depth_pixel": pix, "loss_depth_ssim": _zeros2(img), "loss_depth_consis": _zeros2(img),
                     "loss_depth_smooth": self.compute_smooth_loss3((img, img_l, img_r), (disp_list, disp_l_list, disp_r_list))}
@@ -303,15 +306,16 @@ class GeometryLoss(_LossBase):
         """model_geometry.py:757-765 (``invert_second`` fuses the ``[1-mask for mask in ...]`` of :863-864)"""
         return [ops.mask_product([valid_mask[s], occ_mask[s]], [False, invert_second]) for s in range(self.num_scales)]
 
-    def _forward_losses_fused(self, img, img_l, img_r, pc, pl, pr, flows_fwd, flows_bwd, disp_list, disp_l_list, disp_r_list,
+    def _forward_losses_fused(self, img, img_l, img_r, pyr, flows_fwd, flows_bwd, disp_list, disp_l_list, disp_r_list,
                               Fm, Kinv, P_b, P_f):
         """Two stencil kernels carry the loss loop: the geom-mode single-pass flow kernel (warps, every mask, the four flow
         terms; masks leave as one packed byte map per level) and the reprojection-photometric kernel (reads the byte maps).
         The level-0 point-wise terms (depth-flow consistency, epipolar) and the disparity smoothness stay on their ops."""
         S = self.num_scales
+        pc, pl, pr = (d["bilinear"] for d in pyr)
         flow4, mbytes = ops.geom_flow_loss(pl, pc, pr, list(flows_fwd), list(flows_bwd), list(disp_list[:S]), Kinv, P_b, P_f,
                                            self.flow_consist_alpha, self.flow_consist_beta, S)
-        area = (ops.image_pyramid(img_l, S, "area"), ops.image_pyramid(img_r, S, "area"))
+        area = (pyr[1]["area"], pyr[2]["area"])
         depth_pixel, (val_l, val_r), (tex_b, tex_f) = ops.depth_photo_loss(
             pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f), ext_bytes=mbytes, ext_need=(ops.MASK_ALL_BWD, ops.MASK_ALL_FWD))
         # level 0: |rigid flow - flow| under valid * occ * dyn (:921-926) and the epipolar distance means (:928-935), one kernel
@@ -334,12 +338,13 @@ class GeometryLoss(_LossBase):
         The second return value holds the device-side masks (the reference's ``mask_pack`` without its
         unconditional D2H copies, :871-880)."""
         S = self.num_scales
-        pc, pl, pr = (self.generate_img_pyramid(x, S) for x in (img, img_l, img_r))
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
         if fused:
             Kinv, (P_b, P_f), Fm = self._pose_setup(img.size(2), K, disp_list, pose_vectors, K_inv, fundamental=True)
-            return self._forward_losses_fused(img, img_l, img_r, pc, pl, pr, optical_flows_fwd, optical_flows_bwd, disp_list, disp_l_list,
+            pyr = ops.image_pyramids((img, img_l, img_r), S, ("bilinear", ("bilinear", "area"), ("bilinear", "area")))   # one launch
+            return self._forward_losses_fused(img, img_l, img_r, pyr, optical_flows_fwd, optical_flows_bwd, disp_list, disp_l_list,
                                               disp_r_list, Fm, Kinv, P_b, P_f)
+        pc, pl, pr = (self.generate_img_pyramid(x, S) for x in (img, img_l, img_r))
         Kinv, (P_b, P_f) = self._projections(img.size(2), K, disp_list, [pose_bwd, pose_fwd])
         # composed path: one kernel per reference method (kept as the cross-check of the fused kernels)
         rec_l, val_l, _, _ = self._reconstruction_with(img_l, disp_list, disp_l_list, Kinv, P_b)

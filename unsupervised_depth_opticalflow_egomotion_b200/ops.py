@@ -69,6 +69,42 @@ def image_pyramid(img: Tensor, levels: int, mode: str) -> List[Tensor]:
     return outs
 
 
+def image_pyramids(imgs: Sequence[Tensor], levels: int, modes: Sequence[str]):
+    """The pyramids of up to three images in ONE launch.  ``modes[i]`` is a string or tuple of strings out of ``'box'`` /
+    ``'area'`` / ``'bilinear'``; returns, per image, a dict ``mode -> [level 0 .. levels-1]`` (level 0 = the input).  Same values
+    as :func:`image_pyramid` (which it falls back to for ``levels`` outside 2..4)."""
+    imgs = [_dev(t, "img").detach() for t in imgs]
+    modes = [(m,) if isinstance(m, str) else tuple(m) for m in modes]
+    if not 1 <= len(imgs) <= _cabi.UglPyramidArgs.MAX_IMAGES or len(modes) != len(imgs):
+        raise ValueError("image_pyramids: 1..3 images with one mode entry each")
+    B, Cc, H, W = imgs[0].shape
+    if any(tuple(t.shape) != (B, Cc, H, W) for t in imgs):
+        raise ValueError("image_pyramids: images must share one shape")
+    f = 1 << (levels - 1)
+    if not 2 <= levels <= 4 or H % f or W % f or (H * W) % 4 or any(t.data_ptr() % 16 for t in imgs):
+        return [{m: image_pyramid(t, levels, m) for m in ms} for t, ms in zip(imgs, modes)]
+    a = _cabi.UglPyramidArgs()
+    a.batch, a.channels, a.height, a.width, a.levels, a.images = B, Cc, H, W, levels, len(imgs)
+    out = []
+    for i, (t, ms) in enumerate(zip(imgs, modes)):
+        a.img[i] = t.data_ptr()
+        d = {}
+        for m in ms:
+            lv = [t] + [torch.empty((B, Cc, H >> l, W >> l), device=t.device, dtype=torch.float32) for l in range(1, levels)]
+            slot = a.bil if m == "bilinear" else a.box
+            if m not in ("box", "area", "bilinear"):
+                raise ValueError("image_pyramids: unknown mode %r" % (m,))
+            for l in range(1, levels):
+                slot[i][l] = lv[l].data_ptr()
+            d[m] = lv
+        out.append(d)
+    a.stream = torch.cuda.current_stream().cuda_stream
+    with torch.cuda.device_of(imgs[0]):
+        _cabi.check(_cabi.lib().ugl_image_pyramid_multi(C.byref(a)), "ugl_image_pyramid_multi")
+    _count(1)
+    return out
+
+
 # ================================================================================================
 # warp_flow (W1)
 # ================================================================================================

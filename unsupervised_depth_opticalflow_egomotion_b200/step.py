@@ -78,7 +78,7 @@ class FlowLossStep:
                 dst.copy_(src, non_blocking=True)
             sl.h2d_done.record(self.copy_stream)
         main.wait_event(sl.h2d_done)
-        pl, pc, pr = (ops.image_pyramid(x, self.L, "box") for x in sl.imgs)
+        pl, pc, pr = (d["box"] for d in ops.image_pyramids(sl.imgs, self.L, ("box", "box", "box")))     # one launch
         ff = [f.detach().requires_grad_(True) for f in sl.ff]       # fresh leaves over the staging buffers
         fb = [f.detach().requires_grad_(True) for f in sl.fb]
         loss = ops.flow_loss(pl, pc, pr, ff, fb, self.scales, as_matrix=True)
