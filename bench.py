@@ -204,13 +204,18 @@ def run_torch_cuda(args, rank, local):
 
 
 def run_mode_workload(args, rank, world, local):
-    """Extra measurement (not the driver's line): the depth- / geom-mode loss bodies (BASELINE configs[2] / [3]) as
-    composed from the per-method kernels under autograd, eager launches, 256x832, batch 8 per GPU, S=3."""
+    """Extra measurement (not the driver's line): the depth- / geom-mode loss bodies (BASELINE configs[2] / [3]) through
+    ``losses.*.forward_losses`` (fused kernels) under autograd + ``losses.total_loss`` (train.py:211-214), 256x832, batch 8 per GPU,
+    S=3, CUDA-graph replay unless --no-graph."""
     from unsupervised_depth_opticalflow_egomotion_b200 import losses, ops
     from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B, S = args.batch, 3
+    H, W = args.height, args.width
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     t = make_triplet(B, H, W, 4, S, seed=1234 + rank, flow_mode="rigid").to(dev)
     leaves = [x.requires_grad_(True) for x in t.flows_fwd + t.flows_bwd + t.disp + t.disp_l + t.disp_r + [t.pose]]
     weights = {"loss_flow_pixel": 0.15, "loss_flow_ssim": 0.85, "loss_flow_smooth": 10.0, "loss_flow_consis": 0.01, "loss_depth_pixel": 1.0,
@@ -219,15 +224,19 @@ def run_mode_workload(args, rank, world, local):
     if args.workload == "geom":
         mod = losses.GeometryLoss(S)
         fwd = lambda: mod.forward_losses(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd, t.disp, t.disp_l, t.disp_r, t.pose, t.K, t.K_inv)[0]
-    else:
-        mod = losses.DepthLoss(S, "texture")
+    elif args.workload in ("depth", "depth-live"):
+        mod = losses.DepthLoss(S, "texture" if args.workload == "depth" else "live")
         fwd = lambda: mod.forward_losses(t.img_l, t.img, t.img_r, t.disp, t.disp_l, t.disp_r, t.pose, t.K)[0]
+    else:   # flow+depth (BASELINE configs[4]): the flow-mode loss (4 levels) and the live depth-mode loss on the same triplet
+        fmod, dmod = losses.FlowLoss(4), losses.DepthLoss(S, "live")
+        fwd = lambda: {**fmod.forward_losses(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd),
+                       **dmod.forward_losses(t.img_l, t.img, t.img_r, t.disp, t.disp_l, t.disp_r, t.pose, t.K)[0]}
 
     def step():
         for x in leaves:
             x.grad = None
         loss = fwd()
-        sum(weights[k] * v.mean() for k, v in loss.items()).backward()
+        losses.total_loss(loss, weights).backward()
 
     n0 = ops.LAUNCH_COUNTER["n"]
     step()
@@ -247,7 +256,7 @@ def run_mode_workload(args, rank, world, local):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 loss = fwd()
-                sum(weights[k] * v.mean() for k, v in loss.items()).backward()
+                losses.total_loss(loss, weights).backward()
             run, how = g.replay, "cuda-graph"
         except Exception as e:
             sys.stderr.write("graph capture failed, eager: %r\n" % (e,))
@@ -255,6 +264,9 @@ def run_mode_workload(args, rank, world, local):
     for _ in range(max(args.warmup, 3)):
         run()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -262,11 +274,18 @@ def run_mode_workload(args, rank, world, local):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:       # weak scaling, no data-path collective: the job's step time is the slowest rank's
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        dist.barrier()
+        dist.destroy_process_group()
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": 2.0 * B * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "ms_per_step": ms, "dtype": "f32", "data": "synthetic", "gpu_launches": launches * args.steps,
-                          "config": {"workload": "%s-mode loss body fwd+bwd (per-method kernels composed under autograd), 256x832, "
-                                                 "batch %d per GPU, S=3" % (args.workload, B), "launch": how}}), flush=True)
+                          "config": {"workload": "%s-mode loss body fwd+bwd (fused kernels under autograd + the trainer's weighted total), %dx%d, "
+                                                 "batch %d per GPU, S=3" % (args.workload, H, W, B), "height": H, "width": W, "launch": how,
+                                     "timing": "one CUDA-event pair around all steps, max over ranks"}}), flush=True)
 
 
 def main():
@@ -280,8 +299,11 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="samples per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="flow", choices=["flow", "depth", "geom"],
-                    help="flow = BASELINE configs[1] (the driver's line); depth / geom = configs[2] / [3] loss bodies (extra, eager)")
+    ap.add_argument("--workload", default="flow", choices=["flow", "depth", "depth-live", "geom", "flow+depth"],
+                    help="flow = BASELINE configs[1] (the driver's line).  Extras: depth (model_depth_texture spec) / depth-live (model_depth) "
+                         "= configs[2], geom = configs[3], flow+depth = configs[4] (use --height 384 --width 1280)")
+    ap.add_argument("--height", type=int, default=H, help="extras only (the driver's line is always 256x832)")
+    ap.add_argument("--width", type=int, default=W)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -428,3 +428,20 @@ def test_geom_rigid_terms_equal_composed(cuda_device, B, H, W):
     fb2 = t.flows_bwd[0].detach().clone().requires_grad_(True)
     g2, = torch.autograd.grad(ops.masked_mean(ops.epipolar_distance(fb2, Fm[0]), None).sum(), fb2)
     assert rel_err(g1, g2) < 1e-6
+
+
+def test_total_loss_matches_per_key_loop(cuda_device):
+    """losses.total_loss == train.py:211-214's per-key loop, value and gradients (bit-identical gradients)"""
+    g = _g(9)
+    B = 6
+    w = {"a": 0.15, "b": 0.85, "c": 10.0, "z": 0.1}
+    mk = lambda: {k: torch.rand(B, generator=torch.Generator().manual_seed(i)).to(cuda_device).requires_grad_(True) for i, k in enumerate("abc")}
+    p1, p2 = mk(), mk()
+    p1["z"] = torch.zeros([2], device=cuda_device)
+    p2["z"] = torch.zeros([2], device=cuda_device)
+    t1 = losses.total_loss(p1, w)
+    t2 = sum(w[k] * v.mean() for k, v in p2.items())
+    assert abs(float(t1) - float(t2)) <= 1e-6 * abs(float(t2))
+    t1.backward(); t2.backward()
+    for k in "abc":
+        assert torch.equal(p1[k].grad, p2[k].grad), k

@@ -203,6 +203,26 @@ class DepthLoss(_LossBase):
         return loss, masks
 
 
+_WEIGHT_CACHE: Dict[tuple, Tensor] = {}
+
+
+def total_loss(loss_pack: Dict[str, Tensor], weights: Dict[str, float]) -> Tensor:
+    """``train.py:211-214``: ``sum_k weights[k] * loss_pack[k].mean()`` as four launches instead of four per key: the live
+    ``(B,)`` terms are stacked, averaged, weighted and summed at once.  The reference's constant ``zeros([2])`` placeholders add
+    exactly 0 and carry no gradient, so they are skipped.  Gradients are bit-identical to the per-key loop
+    (``d total / d loss_k[b] = fl(w_k / B)``)."""
+    items = list(loss_pack.items())
+    B = max(v.numel() for _, v in items)
+    live = [(k, v) for k, v in items if v.numel() == B]          # B == 2: the placeholders stack like any other term
+    if any(v.numel() not in (B, 2) for _, v in items):
+        return sum(weights[k] * v.mean() for k, v in items)
+    key = (tuple(k for k, _ in live), tuple(float(weights[k]) for k, _ in live), str(live[0][1].device))
+    w = _WEIGHT_CACHE.get(key)
+    if w is None:       # built once per (keys, weights, device): no host-to-device copy inside a captured step
+        w = _WEIGHT_CACHE[key] = torch.tensor(key[1], dtype=torch.float32, device=live[0][1].device)
+    return (torch.stack([v for _, v in live]).mean(1) * w).sum()
+
+
 class GeomMasks(dict):
     """``mask_pack`` of the fused geom path (model_geometry.py:871-880): the float maps the kernels wrote are plain dict
     entries; the flow-branch masks (``occ_b/f, valid_b/f, dyn_b/f, fwd_mask, bwd_mask, rigid_f, inlier_f``) are unpacked from
