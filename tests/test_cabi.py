@@ -88,6 +88,35 @@ def test_argument_validation_happens_before_launch(lib):
     assert lib.ugl_warp_flow_forward(None, None, 1, 3, 8, 8, 0, None, None, None) == -1
 
 
+def test_fused_entries_validate_before_launch(lib):
+    """every struct-taking entry rejects null / inconsistent arguments on the host (no GPU needed) with UGL_EINVAL and a message"""
+    for name in ("ugl_geom_flow_forward_grad", "ugl_geom_flow_combine", "ugl_depth_photo_forward", "ugl_depth_photo_backward",
+                 "ugl_disp_smooth_forward_grad", "ugl_disp_smooth_combine", "ugl_geom_rigid_forward", "ugl_geom_rigid_backward",
+                 "ugl_image_pyramid_multi", "ugl_flow_loss_forward_grad", "ugl_flow_loss_combine"):
+        assert getattr(lib, name)(None) == -1, name
+        assert b"null" in lib.ugl_last_error(), name
+    g = _cabi.UglGeomFlowArgs()
+    g.flow.batch, g.flow.levels, g.flow.scales = 1, 3, 4
+    assert lib.ugl_geom_flow_forward_grad(C.byref(g)) == -1 and b"scales" in lib.ugl_last_error()
+    d = _cabi.UglDispSmoothArgs()
+    d.batch, d.lists, d.levels, d.height, d.width = 1, 4, 1, 8, 8               # more lists than UGL_DISP_SMOOTH_MAX_LISTS
+    assert lib.ugl_disp_smooth_forward_grad(C.byref(d)) == -1
+    d.lists = 1
+    d.lheight[0], d.lwidth[0] = 3, 8                                              # level does not divide the full size
+    assert lib.ugl_disp_smooth_forward_grad(C.byref(d)) == -4
+    p = _cabi.UglPyramidArgs()
+    p.batch, p.channels, p.height, p.width, p.levels, p.images = 1, 3, 8, 8, 5, 1    # levels outside 2..4
+    assert lib.ugl_image_pyramid_multi(C.byref(p)) == -4
+    r = _cabi.UglGeomRigidArgs()
+    r.batch, r.height, r.width = 0, 8, 8
+    assert lib.ugl_geom_rigid_forward(C.byref(r)) == -1
+    down = (C.c_float * 1)(1.0)
+    assert lib.ugl_pose_setup_forward(None, None, None, down, 1, 2, 1, None, None, None, None) == -1
+    assert lib.ugl_pose_setup_forward(C.c_void_p(16), C.c_void_p(16), None, down, 1, 3, 1, None, None, None, None) == -1   # n > 2
+    assert lib.ugl_geom_rigid_workspace_bytes(2, 8, 8) == 2 * 1 * 42 * 4
+    assert lib.ugl_disp_smooth_fused_workspace_bytes(C.byref(d)) == 1 * 1 * 1 * 2 * 4
+
+
 def test_ops_refuse_cpu_tensors():
     import torch
     from unsupervised_depth_opticalflow_egomotion_b200 import ops
