@@ -319,6 +319,25 @@ uint64_t ugl_depth_photo_workspace_bytes(const UglDepthPhotoArgs* args);
 int ugl_depth_photo_forward(const UglDepthPhotoArgs* args);
 int ugl_depth_photo_backward(const UglDepthPhotoArgs* args);
 
+/* Depth mode WITH the SSIM term (model_depth_texture.py:296-301; BASELINE configs[2]): loss_depth_pixel (L1 under valid * texture,
+ * compute_photometric_depth_loss) AND loss_depth_ssim (compute_ssim_loss under the reprojection valid mask, model_depth.py /
+ * model_geometry.py:212-223 + pytorch_ssim/ssim.py:4-19) of both source frames and all levels in the single-pass tile kernel
+ * (reprojection warps in place of flow warps).  `photo` carries the inputs exactly as for ugl_depth_photo_* (ext_* unused; its
+ * `loss` / `den` / `grad_loss` fields are ignored).  forward_grad: loss4 (4,B) rows = depth_pixel, depth_ssim, 0, 0; stats
+ * (B,scales,UGL_GEOM_NSTATS); basis[l] (B,UGL_DEPTH_BASIS_PLANES,h,w) = un-normalised d loss / d (projected u, v) per term and
+ * direction.  combine: grad_loss4 (2,B) = upstream gradients of depth_pixel / depth_ssim -> photo.grad_disp[l], photo.grad_P[d][l]. */
+#define UGL_DEPTH_BASIS_PLANES 8
+typedef struct UglDepthSsimArgs {
+  UglDepthPhotoArgs photo;
+  float* loss4;                                /* (4,B)                                         */
+  float* stats;                                /* (B,scales,UGL_GEOM_NSTATS)                    */
+  float* basis[UGL_MAX_LEVELS];                /* (B,8,h,w)                                     */
+  const float* grad_loss4;                     /* (2,B)                 [combine]               */
+} UglDepthSsimArgs;
+uint64_t ugl_depth_ssim_workspace_bytes(const UglDepthSsimArgs* args);
+int ugl_depth_ssim_forward_grad(const UglDepthSsimArgs* args);
+int ugl_depth_ssim_combine(const UglDepthSsimArgs* args);
+
 /* Per-step matrix set-up of the depth / geom modes, one launch for every level and both poses:
  *   K_s = K with rows 0-1 divided by downscales[s] (model_geometry.py:92-93); Kinv_out[s] (B,3,3) = K_s^-1 (inverse_warp.py:284);
  *   [R|t] = pose_vec2mat(pose[:,k]) (euler, inverse_warp.py:110-145, 172-187); P_out[k*S+s] (B,3,4) = K_s [R|t] (:289);

@@ -215,6 +215,89 @@ extern "C" int emu_geom_flow_combine(const UglGeomFlowArgs* g) {
   return 0;
 }
 
+// depth mode (reprojection warps + L1 under valid*texture + SSIM under valid): tile logic with kModeDepth, then the combine
+extern "C" int emu_depth_ssim_forward_grad(const UglDepthSsimArgs* g) {
+  const UglDepthPhotoArgs* a = &g->photo;
+  FlowGradParams gp;
+  FlowLossParams& p = gp.base;
+  p.B = a->batch; p.scales = a->scales;
+  int tiles = 0;
+  for (int l = 0; l < a->scales; ++l) {
+    FlowLevelDesc& L = p.lv[l];
+    L.h = a->height[l]; L.w = a->width[l];
+    L.geom = make_warp_geom(L.w, L.h);
+    L.img = a->img[l];
+    L.tiles_x = (L.w + kBTW - 1) / kBTW; L.tiles_y = (L.h + kBTH - 1) / kBTH;
+    L.tile_begin = tiles;
+    tiles += L.tiles_x * L.tiles_y * a->batch;
+    gp.basis[l] = g->basis[l]; gp.disp[l] = a->disp[l]; gp.Kinv[l] = a->Kinv[l];
+    for (int d = 0; d < 2; ++d) {
+      gp.P[d][l] = a->P[d][l]; gp.src_area[d][l] = a->src_area[d][l]; gp.src_bil[d][l] = a->src_bil[d][l];
+      gp.valid_out[d][l] = a->valid_out[d][l]; gp.tex_out[d][l] = a->tex_out[d][l];
+    }
+  }
+  p.total_tiles = tiles; p.stats = g->stats; p.loss = g->loss4;
+  using Tile = FlowGradTile<kBTW, kBTH, 1, kModeDepth>;
+  std::vector<float> partials((size_t)tiles * GA_COUNT, 0.f), sm(Tile::kSmemFloats);
+  for (int tile = 0; tile < tiles; ++tile) {
+    const TileCoord tc = decode_tile<kBTW, kBTH>(p, tile);
+    float acc[GA_COUNT] = {0}, mats[33];
+    for (int k = 0; k < 9; ++k) mats[k] = gp.Kinv[tc.level][tc.b * 9 + k];
+    for (int k = 0; k < 12; ++k) { mats[9 + k] = gp.P[0][tc.level][tc.b * 12 + k]; mats[21 + k] = gp.P[1][tc.level][tc.b * 12 + k]; }
+    Tile::phase1_depth(gp, tc, 0, 1, sm.data(), acc, mats);
+    for (int dir = 0; dir < 2; ++dir) {
+      Tile::phase2(gp, tc, dir, 0, 1, sm.data(), acc);
+      Tile::phase3(gp, tc, dir, 0, 1, sm.data());
+    }
+    for (int k = 0; k < GA_COUNT; ++k) partials[(size_t)tile * GA_COUNT + k] = acc[k];
+  }
+  for (int b = 0; b < p.B; ++b) {
+    float tot[4] = {0, 0, 0, 0};
+    for (int l = 0; l < p.scales; ++l) {
+      const FlowLevelDesc& L = p.lv[l];
+      const int per_img = L.tiles_x * L.tiles_y;
+      double s[GA_COUNT] = {0};
+      for (int t = 0; t < per_img; ++t)
+        for (int k = 0; k < GA_COUNT; ++k) s[k] += partials[((size_t)L.tile_begin + (size_t)b * per_img + t) * GA_COUNT + k];
+      float S[GA_COUNT], out[4];
+      for (int k = 0; k < GA_COUNT; ++k) { S[k] = (float)s[k]; p.stats[((size_t)b * p.scales + l) * GA_COUNT + k] = S[k]; }
+      depth_level_losses(S, L.h, L.w, out);
+      for (int k = 0; k < 4; ++k) tot[k] += out[k];
+    }
+    for (int k = 0; k < 4; ++k) p.loss[k * p.B + b] = tot[k];
+  }
+  return 0;
+}
+
+extern "C" int emu_depth_ssim_combine(const UglDepthSsimArgs* g) {
+  const UglDepthPhotoArgs* a = &g->photo;
+  for (int l = 0; l < a->scales; ++l) {
+    const int h = a->height[l], w = a->width[l];
+    const size_t plane = (size_t)h * w;
+    for (int b = 0; b < a->batch; ++b) {
+      for (size_t px = 0; px < plane; ++px) a->grad_disp[l][b * plane + px] = 0.f;
+      for (int d = 0; d < 2; ++d) {
+        float k_pix, k_ssim;
+        depth_combine_scales(g->stats + ((size_t)b * a->scales + l) * GA_COUNT, h, w, g->grad_loss4, a->batch, b, d, k_pix, k_ssim);
+        const float* bs = g->basis[l] + ((size_t)b * 8 + 4 * d) * plane;
+        const float* P = a->P[d][l] + b * 12;
+        double accd[12] = {0};
+        for (size_t px = 0; px < plane; ++px) {
+          const int i = (int)(px / w), j = (int)(px % w);
+          const float gu = k_pix * bs[px] + k_ssim * bs[2 * plane + px];
+          const float gv = k_pix * bs[plane + px] + k_ssim * bs[3 * plane + px];
+          const Projected r = project_pixel(a->Kinv[l] + b * 9, P, a->disp[l][b * plane + px], j, i);
+          float acc[12] = {0};
+          a->grad_disp[l][b * plane + px] += project_backward(r, P, gu, gv, 0.f, acc);
+          for (int k = 0; k < 12; ++k) accd[k] += acc[k];
+        }
+        for (int k = 0; k < 12; ++k) a->grad_P[d][l][b * 12 + k] = (float)accd[k];
+      }
+    }
+  }
+  return 0;
+}
+
 extern "C" int emu_image_pyramid(const float* img, int B, int C, int H, int W, int levels, int mode, float* const* out) {
   for (int l = 1; l < levels; ++l) {
     const int oh = H >> l, ow = W >> l;

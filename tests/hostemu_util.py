@@ -94,3 +94,30 @@ def emu_geom_flow(img_l, img, img_r, flows_fwd, flows_bwd, disp, Kinv, P_b, P_f,
     emu().emu_geom_flow_forward_grad(C.byref(g))
     emu().emu_geom_flow_combine(C.byref(g))
     return loss, gf, gb, masks
+
+
+def emu_depth_ssim(img, area, bil, disp, Kinv, P, gloss):
+    """depth-mode single-pass kernel (forward_grad + combine) via the host emulator.  area / bil / P: pairs (left, right) of
+    per-level lists; gloss (2,B).  Returns loss4 (4,B), grad_disp[S], grad_P[2][S], valid[2][S], tex[2][S]"""
+    S, B = len(disp), img[0].shape[0]
+    loss4 = torch.zeros(4, B)
+    stats = torch.zeros(B, S, _cabi.GEOM_NSTATS)
+    basis = [torch.zeros(B, _cabi.DEPTH_BASIS_PLANES, d.shape[2], d.shape[3]) for d in disp]
+    gdisp = [torch.zeros_like(d) for d in disp]
+    gP = [[torch.zeros(B, 3, 4) for _ in range(S)] for _ in range(2)]
+    valid = [[torch.zeros_like(d) for d in disp] for _ in range(2)]
+    tex = [[torch.zeros_like(d) for d in disp] for _ in range(2)]
+    g = _cabi.UglDepthSsimArgs()
+    a = g.photo
+    a.batch, a.scales = B, S
+    for l in range(S):
+        a.height[l], a.width[l] = disp[l].shape[2], disp[l].shape[3]
+        a.img[l], a.disp[l], a.Kinv[l], a.grad_disp[l] = img[l].data_ptr(), disp[l].data_ptr(), Kinv[l].data_ptr(), gdisp[l].data_ptr()
+        g.basis[l] = basis[l].data_ptr()
+        for d in range(2):
+            a.src_area[d][l], a.src_bil[d][l], a.P[d][l] = area[d][l].data_ptr(), bil[d][l].data_ptr(), P[d][l].data_ptr()
+            a.valid_out[d][l], a.tex_out[d][l], a.grad_P[d][l] = valid[d][l].data_ptr(), tex[d][l].data_ptr(), gP[d][l].data_ptr()
+    g.loss4, g.stats, g.grad_loss4 = loss4.data_ptr(), stats.data_ptr(), gloss.data_ptr()
+    emu().emu_depth_ssim_forward_grad(C.byref(g))
+    emu().emu_depth_ssim_combine(C.byref(g))
+    return loss4, gdisp, gP, valid, tex

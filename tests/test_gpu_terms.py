@@ -445,3 +445,51 @@ def test_total_loss_matches_per_key_loop(cuda_device):
     t1.backward(); t2.backward()
     for k in "abc":
         assert torch.equal(p1[k].grad, p2[k].grad), k
+
+
+def test_fused_depth_ssim_equals_composed(cuda_device):
+    """DepthLoss('texture'): the depth-mode single-pass kernel (L1 + SSIM on the reprojections) against the per-method kernels"""
+    t = make_triplet(2, 64, 208, 4, 3, seed=63, flow_mode="rigid").to(cuda_device)
+    W = P.GEOM_WEIGHTS
+    res = {}
+    for fused in (True, False):
+        disp, disp_l, disp_r = _leaf_list(t.disp, cuda_device), _leaf_list(t.disp_l, cuda_device), _leaf_list(t.disp_r, cuda_device)
+        pose = t.pose.detach().clone().requires_grad_(True)
+        loss, masks = losses.DepthLoss(3, "texture").forward_losses(t.img_l, t.img, t.img_r, disp, disp_l, disp_r, pose, t.K, fused=fused)
+        g = torch.autograd.grad(sum(W[k] * v.mean() for k, v in loss.items()), disp + disp_l + disp_r + [pose])
+        res[fused] = (loss, masks, g)
+    for k in ("loss_depth_pixel", "loss_depth_ssim", "loss_depth_consis", "loss_depth_smooth"):
+        assert loss_rel_err(res[True][0][k], res[False][0][k]) < LOSS_RTOL, k
+    for k in ("valid_l", "valid_r", "tex_b", "tex_f"):
+        for a, b in zip(res[True][1][k], res[False][1][k]):
+            assert torch.equal(a, b), k
+    for i, (a, b) in enumerate(zip(res[True][2], res[False][2])):
+        assert rel_err(a, b) < GRAD_RTOL, i
+
+
+def test_depth_ssim_loss_single_level_and_odd_size(cuda_device):
+    """ops.depth_ssim_loss at a size that does not fill the tiles, one level, against the per-method ops"""
+    B, H, W = 1, 38, 54
+    t = make_triplet(B, H, W, 1, 1, seed=64, flow_mode="rigid").to(cuda_device)
+    pc, pl, pr = ([x] for x in (t.img, t.img_l, t.img_r))
+    gl = torch.tensor([[0.7], [1.3]], device=cuda_device)
+
+    def run(fused):
+        disp, pose = [t.disp[0].detach().clone().requires_grad_(True)], t.pose.detach().clone().requires_grad_(True)
+        Kinv, (Pb, Pf), _ = ops.pose_setup(pose, t.K, [1.0])
+        if fused:
+            l2, valid, tex = ops.depth_ssim_loss(pc, (pl, pr), (pl, pr), disp, Kinv, (Pb, Pf))
+        else:
+            pix, ssim = 0, 0
+            for src, Pm in ((t.img_l, Pb[0]), (t.img_r, Pf[0])):
+                rec, val, _, _ = ops.reproject(src, disp[0], t.disp_l[0], Kinv[0], Pm)
+                tex = ops.texture_mask(t.img, rec, src)
+                pix = pix + ops.masked_l1(t.img, rec, ops.mask_product([val, tex]))
+                ssim = ssim + ops.ssim_loss(t.img, rec, val)
+            l2 = torch.stack([pix, ssim])
+        return l2, torch.autograd.grad((l2 * gl).sum(), disp + [pose])
+
+    a, b = run(True), run(False)
+    assert loss_rel_err(a[0][0], b[0][0]) < LOSS_RTOL and loss_rel_err(a[0][1], b[0][1]) < LOSS_RTOL
+    for x, y in zip(a[1], b[1]):
+        assert rel_err(x, y) < GRAD_RTOL

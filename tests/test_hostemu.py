@@ -131,3 +131,51 @@ def test_geom_flow_tiles_vs_oracle(B, Hh, W, S):
     for l in range(S):
         assert rel_err(egf[l], ff[l].grad) < GRAD_RTOL, ("fwd", l)
         assert rel_err(egb[l], fb[l].grad) < GRAD_RTOL * 1.5, ("bwd", l)
+
+
+@pytest.mark.parametrize("B,Hh,W,S", [(2, 48, 96, 3), (1, 40, 72, 2)])
+def test_depth_ssim_tiles_vs_oracle(B, Hh, W, S):
+    """depth-mode variant of the single-pass kernel (reprojection warps): loss_depth_pixel + loss_depth_ssim of the
+    model_depth_texture spec, the masks, and the gradients w.r.t. the centre disparity and K_s [R|t]"""
+    t = make_triplet(B, Hh, W, flow_levels=S, depth_scales=S, seed=13, flow_mode="rigid")
+    gl = torch.rand(2, B, generator=torch.Generator().manual_seed(4)) + 0.5
+    disp = [d.detach().clone().requires_grad_(True) for d in t.disp]
+    Kinv, Pb, Pf = _geom_projections(t, S)
+    Pl = [[p.clone().requires_grad_(True) for p in Pb], [p.clone().requires_grad_(True) for p in Pf]]
+    # oracle terms with P as an explicit leaf: reproject through P directly
+    pc, pl, pr = P.bilinear_pyramid(t.img, S), P.bilinear_pyramid(t.img_l, S), P.bilinear_pyramid(t.img_r, S)
+    area = [P.box_pyramid(t.img_l, S), P.box_pyramid(t.img_r, S)]
+    bil = [pl, pr]
+    tot, pix, ssim, valid, tex = 0, 0, 0, [[], []], [[], []]
+    for d in range(2):
+        rec, val = [], []
+        for s in range(S):
+            h, w = disp[s].shape[2:]
+            jj = torch.arange(w, dtype=torch.float32).view(1, 1, w).expand(1, h, w)
+            ii = torch.arange(h, dtype=torch.float32).view(1, h, 1).expand(1, h, w)
+            pixg = torch.stack((jj, ii, torch.ones_like(jj)), 1).expand(B, 3, h, w).reshape(B, 3, -1)
+            cam = ((Kinv[s] @ pixg).reshape(B, 3, h, w) * disp[s]).reshape(B, 3, -1)
+            q = Pl[d][s][:, :, :3] @ cam + Pl[d][s][:, :, 3:]
+            Z = q[:, 2].clamp(min=1e-3)
+            gx, gy = 2 * (q[:, 0] / Z) / (w - 1) - 1, 2 * (q[:, 1] / Z) / (h - 1) - 1
+            gx = torch.where((gx > 1) | (gx < -1), torch.full_like(gx, 2.0), gx)
+            gy = torch.where((gy > 1) | (gy < -1), torch.full_like(gy, 2.0), gy)
+            grid = torch.stack([gx, gy], 2).reshape(B, h, w, 2)
+            rec.append(torch.nn.functional.grid_sample(area[d][s], grid, padding_mode="zeros", align_corners=False))
+            val.append((grid.abs().max(-1)[0] <= 1).unsqueeze(1).float())
+        tx = P.texture_mask(pc, rec, bil[d], S)
+        m = [val[s] * tx[s] for s in range(S)]
+        pix = pix + P.photometric_l1(pc, rec, m, S)
+        ssim = ssim + P.ssim_loss(pc, rec, val, S)
+        valid[d], tex[d] = val, tx
+    ((pix * gl[0]).sum() + (ssim * gl[1]).sum()).backward()
+    el, egd, egP, ev, et = H.emu_depth_ssim(pc, area, bil, [d.detach().contiguous() for d in disp], Kinv,
+                                            [[p.detach().contiguous() for p in Pl[0]], [p.detach().contiguous() for p in Pl[1]]], gl)
+    assert loss_rel_err(el[0], pix) < LOSS_RTOL and loss_rel_err(el[1], ssim) < LOSS_RTOL
+    assert float(el[2:].abs().max()) == 0.0
+    for d in range(2):
+        for s in range(S):
+            assert torch.equal(ev[d][s], valid[d][s]) and torch.equal(et[d][s], tex[d][s]), (d, s)      # masks bit-exact
+            assert rel_err(egP[d][s], Pl[d][s].grad) < GRAD_RTOL, ("P", d, s)
+    for s in range(S):
+        assert rel_err(egd[s], disp[s].grad) < GRAD_RTOL, ("disp", s)

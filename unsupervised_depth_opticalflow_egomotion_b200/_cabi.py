@@ -13,6 +13,7 @@ MAX_LEVELS = 6
 FLOW_NSTATS = 12
 GEOM_NSTATS = 16
 FLOW_BASIS_PLANES = 14
+DEPTH_BASIS_PLANES = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("UGL_LIB_PATH") or os.path.join(_HERE, "libugl_b200.so")   # override: tuning experiments only
@@ -60,6 +61,13 @@ class UglDepthPhotoArgs(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("stream", C.c_void_p),
         ("ext_bytes", _L), ("ext_need", C.c_int32 * 2),
     ]
+
+
+class UglDepthSsimArgs(C.Structure):
+    """Mirror of ``struct UglDepthSsimArgs`` (include/ugl.h)."""
+
+    _fields_ = [("photo", UglDepthPhotoArgs), ("loss4", C.c_void_p), ("stats", C.c_void_p), ("basis", C.c_void_p * MAX_LEVELS),
+                ("grad_loss4", C.c_void_p)]
 
 
 class UglGeomFlowArgs(C.Structure):
@@ -113,6 +121,9 @@ SIGNATURES = {
     "ugl_flow_loss_forward": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_backward": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_launches": (C.c_int, [C.c_int]),
+    "ugl_depth_ssim_workspace_bytes": (C.c_uint64, [C.POINTER(UglDepthSsimArgs)]),
+    "ugl_depth_ssim_forward_grad": (C.c_int, [C.POINTER(UglDepthSsimArgs)]),
+    "ugl_depth_ssim_combine": (C.c_int, [C.POINTER(UglDepthSsimArgs)]),
     "ugl_geom_flow_forward_grad": (C.c_int, [C.POINTER(UglGeomFlowArgs)]),
     "ugl_geom_flow_combine": (C.c_int, [C.POINTER(UglGeomFlowArgs)]),
     "ugl_flow_loss_forward_grad": (C.c_int, [C.POINTER(UglFlowLossArgs)]),

@@ -10,6 +10,7 @@
 #include "ugl_common.cuh"
 #include "ugl_geometry.cuh"
 #include "ugl_reduce.cuh"
+#include "ugl_flow_grad.cuh"   // accumulator layout + closing scales of the depth-mode single-pass kernel
 
 #ifndef UGL_DP_FWD_MINB
 #define UGL_DP_FWD_MINB 3
@@ -180,6 +181,42 @@ __global__ void __launch_bounds__(kRedThreads, UGL_DP_BWD_MINB) depth_photo_bwd_
   if (threadIdx.x < 12) p.partials[(((long)b * p.scales + l) * p.chunks + blockIdx.x) * 24 + 12 * dir + threadIdx.x] = v;
 }
 
+// backward of the depth-mode single-pass kernel (ugl_depth_ssim_forward_grad): the saved basis holds the un-normalised
+// d loss / d (u, v) of the L1 and SSIM terms per direction; scale, chain through the projection -> grad_disp (two atomic
+// contributions per pixel onto a zeroed map, order-free) and the grad_P partial sums.  grid (chunks, B, 2 * levels).
+struct DepthSsimCombine {
+  const float* basis[kMaxLevels];   // (B,8,h,w)
+  const float* stats;               // (B,scales,GA_COUNT)
+  const float* gloss;               // (2,B)
+};
+__global__ void __launch_bounds__(kRedThreads, 3) depth_ssim_combine_kernel(const __grid_constant__ DepthPhotoParams p,
+                                                                            const __grid_constant__ DepthSsimCombine q) {
+  __shared__ float sK[9], sP[12];
+  __shared__ float red[(kRedThreads / 32) * 12];
+  const int b = blockIdx.y, l = blockIdx.z >> 1, dir = blockIdx.z & 1;
+  const DepthPhotoLevel& L = p.lv[l];
+  if (threadIdx.x < 9) sK[threadIdx.x] = L.Kinv[b * 9 + threadIdx.x];
+  if (threadIdx.x < 12) sP[threadIdx.x] = L.P[dir][b * 12 + threadIdx.x];
+  __syncthreads();
+  const long plane = (long)L.h * L.w;
+  float k_pix, k_ssim;
+  depth_combine_scales(q.stats + ((long)b * p.scales + l) * GA_COUNT, L.h, L.w, q.gloss, p.B, b, dir, k_pix, k_ssim);
+  const float* bs = q.basis[l] + ((long)b * 8 + 4 * dir) * plane;
+  float acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+  for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
+    const int i = (int)(px / L.w), j = (int)(px % L.w);
+    const float gu = k_pix * __ldcs(bs + px) + k_ssim * __ldcs(bs + 2 * plane + px);
+    const float gv = k_pix * __ldcs(bs + plane + px) + k_ssim * __ldcs(bs + 3 * plane + px);
+    const Projected r = project_pixel(sK, sP, L.disp[(long)b * plane + px], j, i);
+    const float gD = project_backward(r, sP, gu, gv, 0.f, acc);
+    atomicAdd(&L.grad_disp[(long)b * plane + px], gD);
+  }
+  const float v = block_reduce_n<kRedThreads, 12>(acc, red);
+  if (threadIdx.x < 12) p.partials[(((long)b * p.scales + l) * p.chunks + blockIdx.x) * 24 + 12 * dir + threadIdx.x] = v;
+}
+
 // one warp per (sample, level): grad_P[dir][level][b] = fixed-order sum of the chunk partials
 __global__ void depth_photo_bwd_finalize_kernel(const __grid_constant__ DepthPhotoParams p) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -265,6 +302,48 @@ extern "C" int ugl_depth_photo_backward(const UglDepthPhotoArgs* a) {
   }
   depth_photo_bwd_kernel<<<dim3(p.chunks, p.B, 2 * p.scales), kRedThreads, 0, st>>>(p);
   if ((rc = check_launch("depth_photo_bwd_kernel"))) return rc;
+  depth_photo_bwd_finalize_kernel<<<(p.B * p.scales + 3) / 4, 128, 0, st>>>(p);
+  return check_launch("depth_photo_bwd_finalize_kernel");
+}
+
+extern "C" int ugl_depth_ssim_combine(const UglDepthSsimArgs* g) {
+  if (!g) return fail(UGL_EINVAL, "depth_ssim_combine: null args");
+  const UglDepthPhotoArgs* a = &g->photo;
+  DepthPhotoParams p;
+  // the combine reads disp, Kinv, P (and the level sizes) of the photo args; images are not needed
+  if (a->batch <= 0 || a->batch > 65535 || a->scales <= 0 || a->scales > UGL_MAX_LEVELS)
+    return fail(UGL_EINVAL, "depth_ssim_combine: bad batch/scales (%d/%d)", a->batch, a->scales);
+  if (!g->grad_loss4 || !g->stats) return fail(UGL_EINVAL, "depth_ssim_combine: null grad_loss / stats");
+  p.B = a->batch; p.scales = a->scales;
+  DepthSsimCombine q;
+  q.stats = g->stats; q.gloss = g->grad_loss4;
+  long max_plane = 0;
+  for (int l = 0; l < a->scales; ++l) {
+    DepthPhotoLevel& L = p.lv[l];
+    L.h = a->height[l]; L.w = a->width[l];
+    L.disp = a->disp[l]; L.Kinv = a->Kinv[l]; L.grad_disp = a->grad_disp[l];
+    if (!L.disp || !L.Kinv || !L.grad_disp || !g->basis[l]) return fail(UGL_EINVAL, "depth_ssim_combine: null pointer at level %d", l);
+    q.basis[l] = g->basis[l];
+    for (int d = 0; d < 2; ++d) {
+      L.P[d] = a->P[d][l]; p.grad_P[d][l] = a->grad_P[d][l];
+      if (!L.P[d] || !p.grad_P[d][l]) return fail(UGL_EINVAL, "depth_ssim_combine: null P / grad_P at level %d", l);
+    }
+    const long pl = (long)L.h * L.w;
+    max_plane = pl > max_plane ? pl : max_plane;
+  }
+  p.chunks = reduce_chunks(max_plane);
+  const uint64_t need = (uint64_t)p.B * p.scales * p.chunks * 24 * sizeof(float);
+  if (!a->workspace || a->workspace_bytes < need)
+    return fail(UGL_EWORKSPACE, "depth_ssim_combine: workspace too small (%llu < %llu)", (unsigned long long)a->workspace_bytes, (unsigned long long)need);
+  p.partials = static_cast<float*>(a->workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  for (int l = 0; l < p.scales; ++l) {
+    const cudaError_t e = cudaMemsetAsync(p.lv[l].grad_disp, 0, sizeof(float) * (size_t)p.B * p.lv[l].h * p.lv[l].w, st);
+    if (e != cudaSuccess) return fail((int)e, "depth_ssim_combine: memset: %s", cudaGetErrorString(e));
+  }
+  depth_ssim_combine_kernel<<<dim3(p.chunks, p.B, 2 * p.scales), kRedThreads, 0, st>>>(p, q);
+  int rc = check_launch("depth_ssim_combine_kernel");
+  if (rc) return rc;
   depth_photo_bwd_finalize_kernel<<<(p.B * p.scales + 3) / 4, 128, 0, st>>>(p);
   return check_launch("depth_photo_bwd_finalize_kernel");
 }

@@ -37,9 +37,7 @@ struct TapC {
 };
 
 template <bool kGrad>
-UGL_HD TapC flow_tap_clamped(int j, int i, float u, float v, const WarpGeom& g) {
-  const float gx = sub_rn(div_c(mul_rn(2.0f, add_rn((float)j, u)), g.dw, g.rdw), 1.0f);
-  const float gy = sub_rn(div_c(mul_rn(2.0f, add_rn((float)i, v)), g.dh, g.rdh), 1.0f);
+UGL_HD TapC tap_clamped_norm(float gx, float gy, const WarpGeom& g) {
   float ix = unnormalize(gx, g.W), iy = unnormalize(gy, g.H);
   ix = fminf(fmaxf(ix, -2.0f), (float)g.W + 1.0f);      // beyond that every corner is out of range anyway
   iy = fminf(fmaxf(iy, -2.0f), (float)g.H + 1.0f);
@@ -73,6 +71,13 @@ UGL_HD TapC flow_tap_clamped(int j, int i, float u, float v, const WarpGeom& g) 
     t.dy[0] = cx0 * dry0; t.dy[1] = cx1 * dry0; t.dy[2] = cx0 * dry1; t.dy[3] = cx1 * dry1;
   }
   return t;
+}
+
+template <bool kGrad>
+UGL_HD TapC flow_tap_clamped(int j, int i, float u, float v, const WarpGeom& g) {
+  const float gx = sub_rn(div_c(mul_rn(2.0f, add_rn((float)j, u)), g.dw, g.rdw), 1.0f);
+  const float gy = sub_rn(div_c(mul_rn(2.0f, add_rn((float)i, v)), g.dh, g.rdh), 1.0f);
+  return tap_clamped_norm<kGrad>(gx, gy, g);
 }
 
 struct DirectLoads { float uf, vf, ub, vb, I[3]; bool inside; };
@@ -175,7 +180,16 @@ struct FlowGradParams {
   const float* P[2][kMaxLevels];          // (B,3,4): 0 = centre->left (bwd flow), 1 = centre->right (fwd flow)
   unsigned char* mask_bytes[kMaxLevels];  // (B,h,w): bit0 valid_b, bit1 valid_f, bit2 occ_b, bit3 occ_f, bit4 dyn_b, bit5 dyn_f
   float alpha, beta;                      // flow_consist_alpha / beta
+  // depth mode only (Model_depth, SSIM variant): reprojection warps instead of flow warps.  Direction d = source frame d
+  // (0 = left / pose[:,0], 1 = right / pose[:,1]) with P[d]; uses disp, Kinv, P above and:
+  const float* src_area[2][kMaxLevels];   // (B,3,h,w) source frames, area pyramid (sampled)
+  const float* src_bil[2][kMaxLevels];    // (B,3,h,w) source frames, bilinear pyramid (texture mask)
+  float* valid_out[2][kMaxLevels];        // optional (B,1,h,w)
+  float* tex_out[2][kMaxLevels];          // optional (B,1,h,w)
 };
+
+// kernel modes of the single-pass tile kernel
+constexpr int kModeFlow = 0, kModeGeom = 1, kModeDepth = 2;
 
 // geom mode splits the L1 term by the dynamic mask (weights 1 and 2, model_geometry.py:905-908): four more accumulators
 enum GeomAcc { GA_PIXD_F = FA_COUNT, GA_WD_F, GA_PIXD_B, GA_WD_B, GA_COUNT };
@@ -184,9 +198,12 @@ constexpr unsigned kMaskValidB = 1u, kMaskValidF = 2u, kMaskOccB = 4u, kMaskOccF
 // ================================================================================================
 // the single-pass stencil kernel's tile logic
 // ================================================================================================
-template <int TW, int TH, int NT, bool kGeom = false>
+template <int TW, int TH, int NT, int kMode = kModeFlow>
 struct FlowGradTile {
-  static constexpr int kAcc = kGeom ? (int)GA_COUNT : (int)FA_COUNT;
+  static constexpr bool kGeom = (kMode == kModeGeom), kDepth = (kMode == kModeDepth);
+  static constexpr int kAcc = kMode == kModeFlow ? (int)FA_COUNT : (int)GA_COUNT;
+  // gradient-basis layout: flow / geom 14 planes (direction stride 8); depth 8 planes: [Gp_u, Gp_v, Gs_u, Gs_v] per direction
+  static constexpr int kPlanes = kDepth ? 8 : 14, kDirStride = kDepth ? 4 : 8;
   static_assert(TW % 2 == 0, "1x2 micro-tiles need an even tile width");
   static constexpr int R = 2;
   static constexpr int PW = TW + 2 * R, PH = TH + 2 * R, PN = PW * PH;   // photometry planes (halo 2)
@@ -205,7 +222,7 @@ struct FlowGradTile {
     const FlowLossParams& p = gp.base;
     const FlowLevelDesc& L = p.lv[tc.level];
     const int plane = L.h * L.w;
-    float* basis = gp.basis[tc.level] + (long)tc.b * kBasisPlanes * plane;
+    float* basis = gp.basis[tc.level] + (long)tc.b * kPlanes * plane;
     int i = 0, j = 0, ni = 0, nj = 0;
     DirectLoads cur = load_direct<PW, R>(L, tc, tid < PN ? tid : 0, i, j);
     for (int idx = tid; idx < PN; idx += nt) {
@@ -283,6 +300,82 @@ struct FlowGradTile {
     }
   }
 
+  // phase 1, depth mode: the warps are depth + pose reprojections (inverse_warp2, structures/inverse_warp.py:263-303) of the
+  // area-resized source frames; SSIM weight = valid (model_depth_texture.py:300-301 -> compute_ssim_loss), L1 weight = valid *
+  // texture mask (:296-297 -> compute_photometric_depth_loss).  Gradients are taken w.r.t. the projected pixel coordinates (u, v);
+  // the combine kernel chains them to the disparity and to P.  mats: K^-1 (9), P[0] (12), P[1] (12).
+  static UGL_HD void phase1_depth(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, float* sm, float* acc, const float* mats) {
+    const FlowLevelDesc& L = gp.base.lv[tc.level];
+    const int plane = L.h * L.w, W = L.w;
+    const float* ic = L.img + (long)tc.b * 3 * plane;
+    const float* dp = gp.disp[tc.level] + (long)tc.b * plane;
+    for (int idx = tid; idx < PN; idx += nt) {
+      const int ly = idx / PW, lx = idx - ly * PW;
+      const int i = tc.y0 - R + ly, j = tc.x0 - R + lx;
+      Photo P;
+      if (i >= 0 && i < L.h && j >= 0 && j < W) {
+        const int pix = i * W + j;
+        const bool interior = (ly >= R && ly < R + TH && lx >= R && lx < R + TW);
+        const float D = dp[pix];
+        P.I[0] = ic[pix]; P.I[1] = ic[plane + pix]; P.I[2] = ic[2 * plane + pix];
+        float dW[12], valid[2], Wd[2][3];
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const Projected pr = project_pixel(mats, mats + 9 + 12 * d, D, j, i);
+          const NormCoord nc = normalise(pr, L.geom);
+          valid[d] = (fabsf(nc.gx) <= 1.0f && fabsf(nc.gy) <= 1.0f) ? 1.f : 0.f;
+          const TapC t = tap_clamped_norm<true>(nc.gx, nc.gy, L.geom);
+          const float* ps = gp.src_area[d][tc.level] + (long)tc.b * 3 * plane + t.off;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float f0 = ps[0], f1 = ps[1], f2 = ps[W], f3 = ps[W + 1];
+            ps += plane;
+            float v = f0 * t.w[0]; v += f1 * t.w[1]; v += f2 * t.w[2]; v += f3 * t.w[3];
+            Wd[d][c] = v;
+            dW[6 * d + 2 * c + 0] = L.geom.sx * (f0 * t.dx[0] + f1 * t.dx[1] + f2 * t.dx[2] + f3 * t.dx[3]);
+            dW[6 * d + 2 * c + 1] = L.geom.sy * (f0 * t.dy[0] + f1 * t.dy[1] + f2 * t.dy[2] + f3 * t.dy[3]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { P.Wf[c] = Wd[0][c]; P.Wb[c] = Wd[1][c]; }
+        P.w_f = valid[0]; P.w_b = valid[1];
+        P.d_f = P.d_b = 0.f;
+        if (interior) {
+          const int t = (ly - R) * TW + (lx - R);
+          float* o = sm + kOffDW + t;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) o[k * TN] = dW[k];
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            const float* sb = gp.src_bil[d][tc.level] + (long)tc.b * 3 * plane + pix;
+            float a = 0.f, s = 0.f, su = 0.f, sv = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              a = add_rn(a, fabsf(sub_rn(P.I[c], Wd[d][c])));
+              s = add_rn(s, fabsf(sub_rn(P.I[c], sb[c * plane])));
+              const float sg = sgnf(Wd[d][c] - P.I[c]);
+              su += sg * dW[6 * d + 2 * c];
+              sv += sg * dW[6 * d + 2 * c + 1];
+            }
+            const float r3 = 1.0f / 3.0f;
+            const float tex = div_c(a, 3.0f, r3) < div_c(s, 3.0f, r3) ? 1.f : 0.f;     // compute_texture_mask
+            const float m = mul_rn(valid[d], tex);
+            o[(12 + 2 * d) * TN] = su * tex;          // phase 3 multiplies by the SSIM weight (valid): valid * tex in total
+            o[(13 + 2 * d) * TN] = sv * tex;
+            acc[d == 0 ? FA_PIX_F : FA_PIX_B] += a * m;
+            acc[d == 0 ? FA_W_F : FA_W_B] += valid[d];
+            acc[d == 0 ? GA_WD_F : GA_WD_B] += m;
+            if (gp.valid_out[d][tc.level]) gp.valid_out[d][tc.level][(long)tc.b * plane + pix] = valid[d];
+            if (gp.tex_out[d][tc.level]) gp.tex_out[d][tc.level][(long)tc.b * plane + pix] = tex;
+          }
+        }
+      } else {
+        zero_photo(P);
+      }
+      store_grad_planes<PN>(sm, idx, P, 0.f, 0.f, 0.f, 0.f);
+    }
+  }
+
   // phase 2 (per direction): work units = (channel, 1x2 strip of the halo-1 region), flattened so that the 3 x 306
   // units spread evenly over the CTA (per-strip loops left two warps with double work and six waiting at the barrier).
   // A unit loads the 3x4 taps it needs once, forms x = I*w, y = W*w and their products once, and accumulates the two
@@ -296,7 +389,7 @@ struct FlowGradTile {
     const float* xbase = sm + (GP_X0 + 6 * dir) * PN;
     const float* ybase = sm + (GP_Y0 + 6 * dir) * PN;
     float ssim_sum = 0.f;
-    const int units = (dir == 0 ? 4 : 3) * NS;
+    const int units = (dir == 0 && !kDepth ? 4 : 3) * NS;      // depth mode has no flow smoothness: no edge-weight units
     for (int u = tid; u < units; u += nt) {
       const int c = u / NS, s = u - c * NS;
       const int ly = s / SW, lx = (s - ly * SW) * 2;          // halo-1 coordinates of the left centre
@@ -376,7 +469,7 @@ struct FlowGradTile {
   static UGL_HD void phase3(const FlowGradParams& gp, const TileCoord& tc, int dir, int tid, int nt, const float* sm) {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     const int plane = L.h * L.w;
-    float* basis = gp.basis[tc.level] + ((long)tc.b * kBasisPlanes + 8 * dir) * plane;
+    float* basis = gp.basis[tc.level] + ((long)tc.b * kPlanes + kDirStride * dir) * plane;
     constexpr int SW = TW / 2;
     for (int s = tid; s < SW * TH; s += nt) {
       const int ty = s / SW, tx = (s - ty * SW) * 2;
@@ -521,6 +614,20 @@ UGL_HD void geom_combine_pixel(const float* __restrict__ basis, const unsigned c
     gb[ch * plane + pix] = kpb * basis[(8 + ch) * plane + pix] + k.ssim[1] * basis[(10 + ch) * plane + pix]
                            + k.sm * basis[(12 + ch) * plane + pix];
   }
+}
+
+// ---- depth mode closing formulas: out[0] = loss_depth_pixel, out[1] = loss_depth_ssim of one level (both directions) ----
+UGL_HD void depth_level_losses(const float* S, int h, int w, float* out) {
+  const float hw = (float)h * (float)w;
+  out[0] = (S[FA_PIX_F] / (3.0f * hw)) / (S[GA_WD_F] / hw + 1e-12f) + (S[FA_PIX_B] / (3.0f * hw)) / (S[GA_WD_B] / hw + 1e-12f);
+  out[1] = (S[FA_SSIM_F] / (3.0f * hw)) / (S[FA_W_F] / hw + 1e-12f) + (S[FA_SSIM_B] / (3.0f * hw)) / (S[FA_W_B] / hw + 1e-12f);
+  out[2] = 0.f; out[3] = 0.f;
+}
+// scales of the L1 / SSIM basis of direction d given the upstream gradients gloss (2,B)
+UGL_HD void depth_combine_scales(const float* S, int h, int w, const float* gloss, int B, int b, int d, float& k_pix, float& k_ssim) {
+  const float hw = (float)h * (float)w;
+  k_pix = gloss[0 * B + b] / hw / (S[d == 0 ? GA_WD_F : GA_WD_B] / hw + 1e-12f) / 3.0f;
+  k_ssim = gloss[1 * B + b] / (3.0f * hw) / (S[d == 0 ? FA_W_F : FA_W_B] / hw + 1e-12f) / 9.0f;
 }
 
 // ---- backward = element-wise combine -----------------------------------------------------------------------------

@@ -34,11 +34,11 @@ __global__ void __launch_bounds__(NT) flow_loss_fwd_kernel(const __grid_constant
 // stores the level sums for backward.  The CTA that finishes a sample last (ticket counter, zeroed by a memset node
 // before the launch) adds the levels up in level order -> loss (4,B).
 constexpr int kFinThreads = 256;
-template <bool kGeom>
+template <int kMode>
 __global__ void __launch_bounds__(kFinThreads)
 flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __restrict__ lvl_loss /* [B][scales][4] */,
                           unsigned* __restrict__ tickets /* [B] */) {
-  constexpr int FA_COUNT = kGeom ? (int)GA_COUNT : (int)ugl::FA_COUNT;   // geom mode carries four more sums
+  constexpr int FA_COUNT = kMode == kModeFlow ? (int)ugl::FA_COUNT : (int)GA_COUNT;   // geom / depth modes carry four more sums
   __shared__ double red[kFinThreads / 32][FA_COUNT];
   __shared__ bool last;
   const int l = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -70,7 +70,9 @@ flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __res
       S[k] = (float)v;
       st[k] = S[k];
     }
-    if (kGeom) geom_level_losses(S, L.h, L.w, out); else flow_level_losses(S, L.h, L.w, out);
+    if (kMode == kModeGeom) geom_level_losses(S, L.h, L.w, out);
+    else if (kMode == kModeDepth) depth_level_losses(S, L.h, L.w, out);
+    else flow_level_losses(S, L.h, L.w, out);
     float* ll = lvl_loss + ((long)b * p.scales + l) * 4;
 #pragma unroll
     for (int k = 0; k < 4; ++k) ll[k] = out[k];
@@ -86,14 +88,14 @@ flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __res
   }
 }
 
-template <bool kGeom = false>
+template <int kMode = kModeFlow>
 static int launch_finalize(const FlowLossParams& p, cudaStream_t st) {
   // scratch behind the tile partials: [B][scales][4] level losses, then B ticket counters
-  float* lvl_loss = p.partials + (size_t)p.total_tiles * (kGeom ? (int)GA_COUNT : (int)FA_COUNT);
+  float* lvl_loss = p.partials + (size_t)p.total_tiles * (kMode == kModeFlow ? (int)FA_COUNT : (int)GA_COUNT);
   unsigned* tickets = reinterpret_cast<unsigned*>(lvl_loss + (size_t)p.B * p.scales * 4);
   const cudaError_t e = cudaMemsetAsync(tickets, 0, sizeof(unsigned) * p.B, st);
   if (e != cudaSuccess) return fail((int)e, "flow_loss finalize: memset: %s", cudaGetErrorString(e));
-  flow_loss_finalize_kernel<kGeom><<<dim3(p.scales, p.B), kFinThreads, 0, st>>>(p, lvl_loss, tickets);
+  flow_loss_finalize_kernel<kMode><<<dim3(p.scales, p.B), kFinThreads, 0, st>>>(p, lvl_loss, tickets);
   return check_launch("flow_loss_finalize_kernel");
 }
 
@@ -119,16 +121,17 @@ __global__ void __launch_bounds__(NT) flow_loss_bwd_kernel(const __grid_constant
 }
 
 // single-pass: losses + gradient basis maps
-template <int TW, int TH, int NT, bool kGeom>
+template <int TW, int TH, int NT, int kMode>
 __global__ void __launch_bounds__(NT, UGL_BMINB) flow_loss_fwdgrad_kernel(const __grid_constant__ FlowGradParams gp) {
   extern __shared__ __align__(16) float sm[];
-  using Tile = FlowGradTile<TW, TH, NT, kGeom>;
+  using Tile = FlowGradTile<TW, TH, NT, kMode>;
   constexpr int FA_COUNT = Tile::kAcc;
+  constexpr bool kMats = (kMode != kModeFlow);
   __shared__ float red[(NT / 32) * FA_COUNT];
-  __shared__ float mats[kGeom ? 33 : 1];   // geom mode: K^-1, P_bwd, P_fwd of this tile's sample and level
+  __shared__ float mats[kMats ? 33 : 1];   // geom / depth modes: K^-1, P[0], P[1] of this tile's sample and level
   const int tile = blockIdx.x;
   const TileCoord tc = decode_tile<TW, TH>(gp.base, tile);
-  if (kGeom) {
+  if (kMats) {
     if (threadIdx.x < 9) mats[threadIdx.x] = gp.Kinv[tc.level][tc.b * 9 + threadIdx.x];
     else if (threadIdx.x < 21) mats[threadIdx.x] = gp.P[0][tc.level][tc.b * 12 + threadIdx.x - 9];
     else if (threadIdx.x < 33) mats[threadIdx.x] = gp.P[1][tc.level][tc.b * 12 + threadIdx.x - 21];
@@ -137,7 +140,8 @@ __global__ void __launch_bounds__(NT, UGL_BMINB) flow_loss_fwdgrad_kernel(const 
   float acc[FA_COUNT];
 #pragma unroll
   for (int k = 0; k < FA_COUNT; ++k) acc[k] = 0.f;
-  Tile::phase1(gp, tc, threadIdx.x, NT, sm, acc, mats);
+  if (kMode == kModeDepth) Tile::phase1_depth(gp, tc, threadIdx.x, NT, sm, acc, mats);
+  else Tile::phase1(gp, tc, threadIdx.x, NT, sm, acc, mats);
   __syncthreads();
 #pragma unroll 1
   for (int dir = 0; dir < 2; ++dir) {          // rolled: one copy of the stencil phases in the instruction cache
@@ -146,9 +150,11 @@ __global__ void __launch_bounds__(NT, UGL_BMINB) flow_loss_fwdgrad_kernel(const 
     Tile::phase3(gp, tc, dir, threadIdx.x, NT, sm);
     __syncthreads();                 // the coefficient planes are reused by the second direction / by phase 4
   }
-  Tile::phase4a(gp, tc, threadIdx.x, NT, sm, acc);
-  __syncthreads();
-  Tile::phase4b(gp, tc, threadIdx.x, NT, sm);
+  if (kMode != kModeDepth) {         // flow smoothness (flow / geom modes)
+    Tile::phase4a(gp, tc, threadIdx.x, NT, sm, acc);
+    __syncthreads();
+    Tile::phase4b(gp, tc, threadIdx.x, NT, sm);
+  }
   const float v = block_reduce_n<NT, FA_COUNT>(acc, red);
   if (threadIdx.x < FA_COUNT) gp.base.partials[(long)tile * FA_COUNT + threadIdx.x] = v;
 }
@@ -326,7 +332,7 @@ extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) {
   using Tile = FlowGradTile<kBTW, kBTH, kBNT>;
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
   static_assert(smem <= 227 * 1024, "single-pass tile does not fit in shared memory");
-  auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, false>;
+  auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, kModeFlow>;
   if ((rc = opt_in_smem(kern, smem))) return rc;
   kern<<<gp.base.total_tiles, kBNT, smem, st>>>(gp);
   if ((rc = check_launch("flow_loss_fwdgrad_kernel"))) return rc;
@@ -366,13 +372,13 @@ extern "C" int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* g) {
   if (!a->workspace || a->workspace_bytes < ugl_flow_loss_workspace_bytes(a))
     return fail(UGL_EWORKSPACE, "geom_flow_forward_grad: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
-  using Tile = FlowGradTile<kBTW, kBTH, kBNT, true>;
+  using Tile = FlowGradTile<kBTW, kBTH, kBNT, kModeGeom>;
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
-  auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, true>;
+  auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, kModeGeom>;
   if ((rc = opt_in_smem(kern, smem))) return rc;
   kern<<<gp.base.total_tiles, kBNT, smem, st>>>(gp);
   if ((rc = check_launch("flow_loss_fwdgrad_kernel<geom>"))) return rc;
-  return launch_finalize<true>(gp.base, st);
+  return launch_finalize<kModeGeom>(gp.base, st);
 }
 
 extern "C" int ugl_geom_flow_combine(const UglGeomFlowArgs* g) {
@@ -423,4 +429,71 @@ extern "C" int ugl_flow_loss_backward(const UglFlowLossArgs* a) {
   if ((rc = opt_in_smem(kern, smem))) return rc;
   kern<<<p.total_tiles, kBNT, smem, st>>>(p);
   return check_launch("flow_loss_bwd_kernel");
+}
+
+// ---- depth mode (Model_depth with SSIM: model_depth_texture.py:296-301) -----------------------------
+// forward: the single-pass tile kernel in depth mode + finalize.  The backward (chain of the (u,v) basis through the
+// projection to disp and P) lives in ugl_depth_photo.cu: ugl_depth_ssim_combine.
+extern "C" int ugl_depth_ssim_forward_grad(const UglDepthSsimArgs* g) {
+  if (!g) return fail(UGL_EINVAL, "depth_ssim: null args");
+  const UglDepthPhotoArgs* a = &g->photo;
+  if (a->batch <= 0 || a->scales <= 0 || a->scales > UGL_MAX_LEVELS) return fail(UGL_EINVAL, "depth_ssim: bad batch/scales (%d/%d)", a->batch, a->scales);
+  FlowGradParams gp;
+  FlowLossParams& p = gp.base;
+  p.B = a->batch; p.scales = a->scales;
+  int tiles = 0;
+  for (int l = 0; l < a->scales; ++l) {
+    FlowLevelDesc& L = p.lv[l];
+    L.h = a->height[l]; L.w = a->width[l];
+    if (L.h < 3 || L.w < 3) return fail(UGL_EUNSUPPORTED, "depth_ssim: level %d is %dx%d; need >= 3x3", l, L.h, L.w);
+    const void* ptrs[10] = {a->img[l], a->disp[l], a->Kinv[l], a->src_area[0][l], a->src_area[1][l], a->src_bil[0][l], a->src_bil[1][l],
+                            a->P[0][l], a->P[1][l], g->basis[l]};
+    for (int k = 0; k < 10; ++k) {
+      if (!ptrs[k]) return fail(UGL_EINVAL, "depth_ssim: null pointer (%d) at level %d", k, l);
+      if (!aligned4(ptrs[k])) return fail(UGL_EALIGN, "depth_ssim: misaligned pointer (%d) at level %d", k, l);
+    }
+    if (reinterpret_cast<uintptr_t>(g->basis[l]) & 7u) return fail(UGL_EALIGN, "depth_ssim: basis not 8-byte aligned");
+    L.geom = make_warp_geom(L.w, L.h);
+    L.img = a->img[l]; L.img_l = nullptr; L.img_r = nullptr; L.flow_f = nullptr; L.flow_b = nullptr; L.gflow_f = nullptr; L.gflow_b = nullptr;
+    L.tiles_x = (L.w + kBTW - 1) / kBTW;
+    L.tiles_y = (L.h + kBTH - 1) / kBTH;
+    L.tile_begin = tiles;
+    tiles += L.tiles_x * L.tiles_y * a->batch;
+    gp.basis[l] = g->basis[l]; gp.disp[l] = a->disp[l]; gp.Kinv[l] = a->Kinv[l];
+    for (int d = 0; d < 2; ++d) {
+      gp.P[d][l] = a->P[d][l]; gp.src_area[d][l] = a->src_area[d][l]; gp.src_bil[d][l] = a->src_bil[d][l];
+      gp.valid_out[d][l] = a->valid_out[d][l]; gp.tex_out[d][l] = a->tex_out[d][l];
+    }
+  }
+  p.total_tiles = tiles;
+  if (!g->stats || !g->loss4) return fail(UGL_EINVAL, "depth_ssim: null stats / loss");
+  p.stats = g->stats; p.loss = g->loss4; p.gloss = nullptr;
+  const uint64_t need = (uint64_t)tiles * GA_COUNT * sizeof(float) + (uint64_t)a->batch * a->scales * 4 * sizeof(float) + (uint64_t)a->batch * sizeof(unsigned);
+  if (!a->workspace || a->workspace_bytes < need)
+    return fail(UGL_EWORKSPACE, "depth_ssim_forward_grad: workspace too small (%llu < %llu)", (unsigned long long)a->workspace_bytes, (unsigned long long)need);
+  p.partials = static_cast<float*>(a->workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  using Tile = FlowGradTile<kBTW, kBTH, kBNT, kModeDepth>;
+  constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
+  auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, kModeDepth>;
+  int rc;
+  if ((rc = opt_in_smem(kern, smem))) return rc;
+  kern<<<p.total_tiles, kBNT, smem, st>>>(gp);
+  if ((rc = check_launch("flow_loss_fwdgrad_kernel<depth>"))) return rc;
+  return launch_finalize<kModeDepth>(p, st);
+}
+
+extern "C" uint64_t ugl_depth_ssim_workspace_bytes(const UglDepthSsimArgs* g) {
+  if (!g) return 0;
+  const UglDepthPhotoArgs* a = &g->photo;
+  uint64_t tiles = 0;
+  long max_plane = 0;
+  for (int l = 0; l < a->scales && l < UGL_MAX_LEVELS; ++l) {
+    tiles += (uint64_t)((a->width[l] + kBTW - 1) / kBTW) * ((a->height[l] + kBTH - 1) / kBTH) * a->batch;
+    const long pl = (long)a->height[l] * a->width[l];
+    max_plane = pl > max_plane ? pl : max_plane;
+  }
+  const uint64_t fwd = tiles * GA_COUNT * sizeof(float) + (uint64_t)a->batch * a->scales * 4 * sizeof(float) + (uint64_t)a->batch * sizeof(unsigned);
+  const uint64_t bwd = ugl_depth_photo_workspace_bytes(a);
+  return fwd > bwd ? fwd : bwd;
 }

@@ -1181,6 +1181,94 @@ class _DepthPhotoFn(torch.autograd.Function):
         return tuple(out)
 
 
+class _DepthSsimFn(torch.autograd.Function):
+    """depth mode with the SSIM term: single-pass tile kernel (reprojection warps) + combine"""
+
+    @staticmethod
+    def _args(S, img, area, bil, disp, Kinv, P, loss4, stats, basis, ws, valid_out=None, tex_out=None, gloss=None, gdisp=None, gP=None):
+        g = _cabi.UglDepthSsimArgs()
+        a = g.photo
+        a.batch, a.scales = disp[0].shape[0], S
+        for l in range(S):
+            a.height[l], a.width[l] = disp[l].shape[2], disp[l].shape[3]
+            a.img[l], a.disp[l], a.Kinv[l] = _ptr(img[l]), disp[l].data_ptr(), Kinv[l].data_ptr()
+            g.basis[l] = basis[l].data_ptr()
+            for d in range(2):
+                a.src_area[d][l], a.src_bil[d][l], a.P[d][l] = _ptr(area[d][l]), _ptr(bil[d][l]), P[d][l].data_ptr()
+                if valid_out is not None:
+                    a.valid_out[d][l], a.tex_out[d][l] = valid_out[d][l].data_ptr(), tex_out[d][l].data_ptr()
+                if gP is not None:
+                    a.grad_P[d][l] = gP[d][l].data_ptr()
+            if gdisp is not None:
+                a.grad_disp[l] = gdisp[l].data_ptr()
+        g.loss4, g.stats, g.grad_loss4 = _ptr(loss4), stats.data_ptr(), _ptr(gloss)
+        a.workspace, a.workspace_bytes = _ptr(ws), (_nbytes(ws) if ws is not None else 0)
+        a.stream = torch.cuda.current_stream().cuda_stream
+        return g
+
+    @staticmethod
+    def forward(ctx, S, *ts):
+        ts = [_dev(t, "input %d" % i) for i, t in enumerate(ts)]
+        g_ = lambda k: ts[k * S:(k + 1) * S]
+        img, area, bil, disp, Kinv, P = g_(0), (g_(1), g_(2)), (g_(3), g_(4)), g_(5), g_(6), (g_(7), g_(8))
+        B, dev = img[0].shape[0], img[0].device
+        for l in range(S):
+            h, w = img[l].shape[2:]
+            if tuple(disp[l].shape) != (B, 1, h, w) or tuple(area[0][l].shape) != (B, 3, h, w) or tuple(P[0][l].shape) != (B, 3, 4):
+                raise ValueError("depth_ssim_loss: inconsistent shapes at level %d" % l)
+        loss4 = torch.empty((4, B), device=dev, dtype=torch.float32)
+        stats = torch.empty((B, S, _cabi.GEOM_NSTATS), device=dev, dtype=torch.float32)
+        basis = [torch.empty((B, _cabi.DEPTH_BASIS_PLANES) + tuple(d.shape[2:]), device=dev, dtype=torch.float32) for d in disp]
+        mk = lambda: [[torch.empty_like(disp[l]) for l in range(S)] for _ in range(2)]
+        valid_out, tex_out = mk(), mk()
+        g = _DepthSsimFn._args(S, img, area, bil, disp, Kinv, P, loss4, stats, basis, None, valid_out, tex_out)
+        n = int(_cabi.lib().ugl_depth_ssim_workspace_bytes(C.byref(g)))
+        ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
+        g.photo.workspace, g.photo.workspace_bytes = ws.data_ptr(), _nbytes(ws)
+        with torch.cuda.device_of(img[0]):
+            _call("ugl_depth_ssim_forward_grad", C.byref(g), launches=2)
+        ctx.save_for_backward(stats, *disp, *Kinv, *P[0], *P[1], *basis)
+        ctx.S = S
+        masks = [m for grp in (valid_out, tex_out) for d in grp for m in d]
+        ctx.mark_non_differentiable(*masks)
+        ctx.set_materialize_grads(False)
+        return (loss4[:2], *masks)
+
+    @staticmethod
+    def backward(ctx, gloss, *unused):
+        stats, *ts = ctx.saved_tensors
+        S = ctx.S
+        if gloss is None:
+            return (None,) * (1 + 9 * S)
+        g_ = lambda k: ts[k * S:(k + 1) * S]
+        disp, Kinv, P, basis = g_(0), g_(1), (g_(2), g_(3)), g_(4)
+        B, dev = disp[0].shape[0], disp[0].device
+        gloss = _dev(gloss, "grad_loss")
+        gdisp = [torch.empty_like(d) for d in disp]
+        gP = [[torch.empty((B, 3, 4), device=dev, dtype=torch.float32) for _ in range(S)] for _ in range(2)]
+        none_l = [None] * S
+        g = _DepthSsimFn._args(S, none_l, (none_l, none_l), (none_l, none_l), disp, Kinv, P, None, stats, basis, None, gloss=gloss,
+                               gdisp=gdisp, gP=gP)
+        n = int(_cabi.lib().ugl_depth_ssim_workspace_bytes(C.byref(g)))
+        ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
+        g.photo.workspace, g.photo.workspace_bytes = ws.data_ptr(), _nbytes(ws)
+        with torch.cuda.device_of(gloss):
+            _call("ugl_depth_ssim_combine", C.byref(g), launches=2)
+        return (None, *none_l, *none_l, *none_l, *none_l, *none_l, *gdisp, *none_l, *gP[0], *gP[1])
+
+
+def depth_ssim_loss(img_pyr, src_area, src_bil, disps, Kinv, P):
+    """``loss_depth_pixel`` and ``loss_depth_ssim`` of the depth mode with the SSIM term (model_depth_texture.py:296-301) in the
+    single-pass tile kernel: reprojection of both source frames, valid + texture masks, masked L1 and masked 3x3 SSIM, all levels.
+    Same argument convention as :func:`depth_photo_loss`.  Returns ``(loss (2,B) = [pixel, ssim], valid[2][S], tex[2][S])``,
+    differentiable w.r.t. ``disps`` and ``P``."""
+    S = len(disps)
+    flat = [*img_pyr[:S], *src_area[0][:S], *src_area[1][:S], *src_bil[0][:S], *src_bil[1][:S], *disps, *Kinv[:S], *P[0][:S], *P[1][:S]]
+    out = _DepthSsimFn.apply(S, *flat)
+    loss, masks = out[0], out[1:]
+    return loss, [list(masks[0:S]), list(masks[S:2 * S])], [list(masks[2 * S:3 * S]), list(masks[3 * S:4 * S])]
+
+
 def depth_photo_loss(img_pyr, src_area, src_bil, disps, Kinv, P, ext_mask=None, ext_bytes=None, ext_need=(0, 0)):
     """Fused ``loss_depth_pixel`` of the depth / geom modes (reconstruction + texture mask + mask fusion +
     ``compute_photometric_loss`` for both directions and all ``len(disps)`` levels).
