@@ -13,8 +13,17 @@ leaves = [x.detach().requires_grad_(True) for x in t.flows_fwd + t.flows_bwd + t
 ff, fb, d, dl, dr, pose = leaves[0:4], leaves[4:8], leaves[8:11], leaves[11:14], leaves[14:17], leaves[17]
 loss, _ = losses.GeometryLoss(3).forward_losses(t.img_l, t.img, t.img_r, ff, fb, d, dl, dr, pose, t.K, t.K_inv)
 sum(v.mean() for v in loss.values()).backward()
-loss, _ = losses.DepthLoss(3, "texture").forward_losses(t.img_l, t.img, t.img_r, d, dl, dr, pose, t.K)
+for variant in ("texture", "live"):
+    for fused in (True, False):
+        loss, _ = losses.DepthLoss(3, variant).forward_losses(t.img_l, t.img, t.img_r, d, dl, dr, pose, t.K, fused=fused)
+        sum(v.mean() for v in loss.values()).backward()
+loss, masks = losses.GeometryLoss(3).forward_losses(t.img_l, t.img, t.img_r, ff, fb, d, dl, dr, pose, t.K, t.K_inv, fused=False)
 sum(v.mean() for v in loss.values()).backward()
+loss, masks = losses.GeometryLoss(3).forward_losses(t.img_l, t.img, t.img_r, ff, fb, d, dl, dr, pose, t.K, t.K_inv)
+_ = masks["occ_b"], masks["dist_f"], masks["rigid_f"]
+losses.total_loss(loss, {k: 1.0 for k in loss}).backward()
+ops.image_pyramids((t.img, t.img_l, t.img_r), 4, ("box", ("bilinear", "area"), "bilinear"))
+ops.forward_splat(torch.ones(2, 1, 40, 72, device=dev), t.flows_fwd[0].detach(), True)
 x = torch.rand(1, 8, 20, 30, device=dev, requires_grad=True); fl = (3 * torch.randn(1, 2, 20, 30, device=dev)).requires_grad_(True)
 ops.warp_flow(x, fl, True).sum().backward()
 torch.cuda.synchronize(); print("sanitizer workload done")
