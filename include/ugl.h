@@ -319,6 +319,31 @@ uint64_t ugl_depth_photo_workspace_bytes(const UglDepthPhotoArgs* args);
 int ugl_depth_photo_forward(const UglDepthPhotoArgs* args);
 int ugl_depth_photo_backward(const UglDepthPhotoArgs* args);
 
+/* Depth-consistency term of the depth mode for both source frames and all levels: compute_consis_loss (unmasked,
+ * model_depth.py:154-163; enabled at model_depth_texture.py:308-309) on the projected / computed depths of inverse_warp2
+ * (structures/inverse_warp.py:263-303): loss (B,) = sum_{frames, levels} mean(clamp(|comp - proj| / |comp + proj|, 0, 1)).
+ * ref_disp[d][l] (B,1,h,w) = the source frame's disparity pyramid (d = 0 left / pose[:,0], 1 = right).  backward:
+ * grad_loss (B,) -> grad_disp[l], grad_ref[d][l] (deterministic fixed-point scatter), grad_P[d][l]. */
+typedef struct UglDepthConsisArgs {
+  int32_t batch, scales;
+  int32_t height[UGL_MAX_LEVELS], width[UGL_MAX_LEVELS];
+  const float* disp[UGL_MAX_LEVELS];
+  const float* ref_disp[2][UGL_MAX_LEVELS];
+  const float* Kinv[UGL_MAX_LEVELS];
+  const float* P[2][UGL_MAX_LEVELS];
+  float* loss;
+  const float* grad_loss;
+  float* grad_disp[UGL_MAX_LEVELS];
+  float* grad_ref[2][UGL_MAX_LEVELS];
+  float* grad_P[2][UGL_MAX_LEVELS];
+  void* workspace;                             /* >= ugl_depth_consis_workspace_bytes, 8-byte aligned */
+  uint64_t workspace_bytes;
+  void* stream;
+} UglDepthConsisArgs;
+uint64_t ugl_depth_consis_workspace_bytes(const UglDepthConsisArgs* args);
+int ugl_depth_consis_forward(const UglDepthConsisArgs* args);
+int ugl_depth_consis_backward(const UglDepthConsisArgs* args);
+
 /* Depth mode WITH the SSIM term (model_depth_texture.py:296-301; BASELINE configs[2]): loss_depth_pixel (L1 under valid * texture,
  * compute_photometric_depth_loss) AND loss_depth_ssim (compute_ssim_loss under the reprojection valid mask, model_depth.py /
  * model_geometry.py:212-223 + pytorch_ssim/ssim.py:4-19) of both source frames and all levels in the single-pass tile kernel

@@ -56,7 +56,8 @@ def test_struct_layouts_match_the_c_compiler(tmp_path):
     import subprocess
     structs = {"UglFlowLossArgs": _cabi.UglFlowLossArgs, "UglDepthPhotoArgs": _cabi.UglDepthPhotoArgs, "UglGeomFlowArgs": _cabi.UglGeomFlowArgs,
                "UglDispSmoothArgs": _cabi.UglDispSmoothArgs, "UglGeomRigidArgs": _cabi.UglGeomRigidArgs,
-               "UglPyramidArgs": _cabi.UglPyramidArgs, "UglDepthSsimArgs": _cabi.UglDepthSsimArgs}
+               "UglPyramidArgs": _cabi.UglPyramidArgs, "UglDepthSsimArgs": _cabi.UglDepthSsimArgs,
+               "UglDepthConsisArgs": _cabi.UglDepthConsisArgs}
     lines = []
     for name, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))

@@ -63,6 +63,16 @@ class UglDepthPhotoArgs(C.Structure):
     ]
 
 
+class UglDepthConsisArgs(C.Structure):
+    """Mirror of ``struct UglDepthConsisArgs`` (include/ugl.h)."""
+
+    _L, _L2 = C.c_void_p * MAX_LEVELS, (C.c_void_p * MAX_LEVELS) * 2
+    _fields_ = [("batch", C.c_int32), ("scales", C.c_int32), ("height", C.c_int32 * MAX_LEVELS), ("width", C.c_int32 * MAX_LEVELS),
+                ("disp", _L), ("ref_disp", _L2), ("Kinv", _L), ("P", _L2), ("loss", C.c_void_p), ("grad_loss", C.c_void_p),
+                ("grad_disp", _L), ("grad_ref", _L2), ("grad_P", _L2),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("stream", C.c_void_p)]
+
+
 class UglDepthSsimArgs(C.Structure):
     """Mirror of ``struct UglDepthSsimArgs`` (include/ugl.h)."""
 
@@ -121,6 +131,9 @@ SIGNATURES = {
     "ugl_flow_loss_forward": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_backward": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_launches": (C.c_int, [C.c_int]),
+    "ugl_depth_consis_workspace_bytes": (C.c_uint64, [C.POINTER(UglDepthConsisArgs)]),
+    "ugl_depth_consis_forward": (C.c_int, [C.POINTER(UglDepthConsisArgs)]),
+    "ugl_depth_consis_backward": (C.c_int, [C.POINTER(UglDepthConsisArgs)]),
     "ugl_depth_ssim_workspace_bytes": (C.c_uint64, [C.POINTER(UglDepthSsimArgs)]),
     "ugl_depth_ssim_forward_grad": (C.c_int, [C.POINTER(UglDepthSsimArgs)]),
     "ugl_depth_ssim_combine": (C.c_int, [C.POINTER(UglDepthSsimArgs)]),

@@ -183,15 +183,11 @@ class DepthLoss(_LossBase):
                     "loss_depth_smooth": self.compute_smooth_loss3((img, img_l, img_r), (disp_list, disp_l_list, disp_r_list))}
             return loss, dict(valid_l=valid[0], valid_r=valid[1], tex_b=tex[0], tex_f=tex[1])
         if fused and self.variant == "texture":
-            # L1 + SSIM of both source frames and all levels: the single-pass tile kernel in depth mode.  The depth-consistency term
-            # (disabled in the live Model_depth, model_depth.py:333-335) keeps its per-method kernels and only needs proj / comp.
+            # L1 + SSIM of both source frames and all levels: the single-pass tile kernel in depth mode; the depth-consistency term
+            # (disabled in the live Model_depth, model_depth.py:333-335): one forward / backward kernel set for all levels
             area = (pyr[1]["area"], pyr[2]["area"])
             l2, valid, tex = ops.depth_ssim_loss(pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f))
-            consis = 0
-            for ar, dref, Pm in ((area[0], disp_l_list, P_b), (area[1], disp_r_list, P_f)):
-                for s in range(S):
-                    _, _, proj, comp = ops.reproject(ar[s], disp_list[s], dref[s], Kinv[s], Pm[s])
-                    consis = consis + ops.masked_mean(ops.depth_diff(comp, proj), None)
+            consis = ops.depth_consis_loss(list(disp_list[:S]), (list(disp_l_list[:S]), list(disp_r_list[:S])), Kinv, (P_b, P_f))
             loss = {"loss_depth_pixel": l2[0], "loss_depth_ssim": l2[1], "loss_depth_consis": consis,
                     "loss_depth_smooth": self.compute_smooth_loss3((img, img_l, img_r), (disp_list, disp_l_list, disp_r_list))}
             return loss, dict(valid_l=valid[0], valid_r=valid[1], tex_b=tex[0], tex_f=tex[1])

@@ -1181,6 +1181,68 @@ class _DepthPhotoFn(torch.autograd.Function):
         return tuple(out)
 
 
+class _DepthConsisFn(torch.autograd.Function):
+    @staticmethod
+    def _args(S, disp, ref, Kinv, P, loss=None, gloss=None, gdisp=None, gref=None, gP=None):
+        a = _cabi.UglDepthConsisArgs()
+        a.batch, a.scales = disp[0].shape[0], S
+        for l in range(S):
+            a.height[l], a.width[l] = disp[l].shape[2], disp[l].shape[3]
+            a.disp[l], a.Kinv[l] = disp[l].data_ptr(), Kinv[l].data_ptr()
+            if gdisp is not None:
+                a.grad_disp[l] = gdisp[l].data_ptr()
+            for d in range(2):
+                a.ref_disp[d][l], a.P[d][l] = ref[d][l].data_ptr(), P[d][l].data_ptr()
+                if gref is not None:
+                    a.grad_ref[d][l], a.grad_P[d][l] = gref[d][l].data_ptr(), gP[d][l].data_ptr()
+        a.loss, a.grad_loss = _ptr(loss), _ptr(gloss)
+        n = int(_cabi.lib().ugl_depth_consis_workspace_bytes(C.byref(a)))
+        a._ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=disp[0].device)
+        a.workspace, a.workspace_bytes = a._ws.data_ptr(), _nbytes(a._ws)
+        a.stream = torch.cuda.current_stream().cuda_stream
+        return a
+
+    @staticmethod
+    def forward(ctx, S, *ts):
+        ts = [_dev(t, "input %d" % i) for i, t in enumerate(ts)]
+        g_ = lambda k: ts[k * S:(k + 1) * S]
+        disp, ref, Kinv, P = g_(0), (g_(1), g_(2)), g_(3), (g_(4), g_(5))
+        B = disp[0].shape[0]
+        for l in range(S):
+            if tuple(ref[0][l].shape) != tuple(disp[l].shape) or tuple(ref[1][l].shape) != tuple(disp[l].shape) or tuple(P[0][l].shape) != (B, 3, 4):
+                raise ValueError("depth_consis_loss: inconsistent shapes at level %d" % l)
+        loss = torch.empty(B, device=disp[0].device, dtype=torch.float32)
+        a = _DepthConsisFn._args(S, disp, ref, Kinv, P, loss=loss)
+        with torch.cuda.device_of(loss):
+            _call("ugl_depth_consis_forward", C.byref(a), launches=2)
+        ctx.save_for_backward(*ts)
+        ctx.S = S
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        ts, S = ctx.saved_tensors, ctx.S
+        g_ = lambda k: ts[k * S:(k + 1) * S]
+        disp, ref, Kinv, P = g_(0), (g_(1), g_(2)), g_(3), (g_(4), g_(5))
+        gloss = _dev(gloss, "grad_loss")
+        gdisp = [torch.empty_like(d) for d in disp]
+        gref = [[torch.empty_like(d) for d in disp] for _ in range(2)]
+        gP = [[torch.empty_like(p) for p in P[d]] for d in range(2)]
+        a = _DepthConsisFn._args(S, disp, ref, Kinv, P, gloss=gloss, gdisp=gdisp, gref=gref, gP=gP)
+        with torch.cuda.device_of(gloss):
+            _call("ugl_depth_consis_backward", C.byref(a), launches=5)
+        return (None, *gdisp, *gref[0], *gref[1], *([None] * S), *gP[0], *gP[1])
+
+
+def depth_consis_loss(disps, ref_disps, Kinv, P):
+    """``loss_depth_consis`` of the depth mode (``compute_consis_loss`` on the projected / computed depths of both
+    ``reconstruction`` calls, model_depth_texture.py:289-292, 308-309) for all levels in one forward and one backward pass.
+    ``ref_disps`` / ``P``: pairs ``(left, right)`` of per-level lists.  Differentiable w.r.t. ``disps``, ``ref_disps`` (deterministic
+    scatter) and ``P``."""
+    S = len(disps)
+    return _DepthConsisFn.apply(S, *disps, *ref_disps[0][:S], *ref_disps[1][:S], *Kinv[:S], *P[0][:S], *P[1][:S])
+
+
 class _DepthSsimFn(torch.autograd.Function):
     """depth mode with the SSIM term: single-pass tile kernel (reprojection warps) + combine"""
 
