@@ -288,6 +288,64 @@ def run_mode_workload(args, rank, world, local):
                                      "timing": "one CUDA-event pair around all steps, max over ranks"}}), flush=True)
 
 
+def run_cost_volume(args, rank, local):
+    """Extra measurement: the ten PWC-Net cost volumes of one flow-mode step (5 pyramid levels x 2 directions,
+    pwc_tf.py:112-160) forward + backward at batch 8, ours vs the reference's corr_naive op sequence executed by PyTorch on the same GPU."""
+    import torch.nn.functional as F
+    from unsupervised_depth_opticalflow_egomotion_b200 import ops
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    shapes = [(196, 4, 13), (128, 8, 26), (96, 16, 52), (64, 32, 104), (32, 64, 208)]          # c16 .. c12 at 256x832
+    feats = [(torch.randn(B, c, h, w, generator=g).to(dev).requires_grad_(True), torch.randn(B, c, h, w, generator=g).to(dev).requires_grad_(True))
+             for c, h, w in shapes for _ in range(2)]
+    gos = [torch.randn(B, 81, a.shape[2], a.shape[3], generator=g).to(dev) for a, _ in feats]
+
+    def naive(f1, f2, d=4):                      # the reference's op sequence (pwc_tf.py:97-106), stock PyTorch
+        Hh, Ww = f1.shape[2:]
+        f2 = F.pad(f2, (d, d, d, d), value=0)
+        return torch.cat([(f1 * f2[:, :, i:i + Hh, j:j + Ww]).mean(1).unsqueeze(1) for i in range(2 * d + 1) for j in range(2 * d + 1)], 1)
+
+    def step(fn):
+        outs = [fn(a, b) for a, b in feats]
+        torch.autograd.grad([o for o in outs], [t for ab in feats for t in ab], grad_outputs=gos)
+
+    res = {}
+    for name, fn in (("ours", ops.cost_volume), ("torch_naive", naive)):
+        run = lambda: step(fn)
+        for _ in range(max(args.warmup, 3)):
+            run()
+        torch.cuda.synchronize()
+        if name == "ours" and not args.no_graph:          # 30 launches of 20-100 us each: replay them as one CUDA graph
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step(fn)
+            torch.cuda.current_stream().wait_stream(side)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                step(fn)
+            run = gr.replay
+            run()
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / args.steps
+    macs = 3 * 81 * B * sum(c * h * w for c, h, w in shapes) * 2
+    if rank == 0:
+        print(json.dumps({"metric": "cost_volume_ms_per_step", "value": res["ours"], "unit": "ms", "higher_is_better": False, "n_gpus": 1,
+                          "steps": args.steps, "torch_naive_ms": res["torch_naive"], "speedup_vs_torch_naive": res["torch_naive"] / res["ours"],
+                          "gmac_per_step": macs / 1e9, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "PWC-Net cost volumes of one step: 5 levels x 2 directions, fwd+bwd, batch %d" % B,
+                                     "launch": "ours: cuda-graph replay of 20 launches; torch_naive: eager (GPU-bound)"}}),
+              flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -299,7 +357,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="samples per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="flow", choices=["flow", "depth", "depth-live", "geom", "flow+depth"],
+    ap.add_argument("--workload", default="flow", choices=["flow", "depth", "depth-live", "geom", "flow+depth", "costvolume"],
                     help="flow = BASELINE configs[1] (the driver's line).  Extras: depth (model_depth_texture spec) / depth-live (model_depth) "
                          "= configs[2], geom = configs[3], flow+depth = configs[4] (use --height 384 --width 1280)")
     ap.add_argument("--height", type=int, default=H, help="extras only (the driver's line is always 256x832)")
@@ -315,6 +373,9 @@ def main():
         return
     if args.impl == "torch-cuda":
         run_torch_cuda(args, rank, local)
+        return
+    if args.workload == "costvolume":
+        run_cost_volume(args, rank, local)
         return
     if args.workload != "flow":
         run_mode_workload(args, rank, world, local)

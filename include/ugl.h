@@ -151,6 +151,15 @@ int ugl_warp_flow_backward(const float* x, const float* flow, const float* grad_
 uint64_t ugl_warp_flow_backward_workspace_bytes(int32_t batch, int32_t channels, int32_t height, int32_t width,
                                                 int32_t need_grad_x);
 
+/* PWC-Net cost volume — replaces PWC_tf.corr_naive (structures/pwc_tf.py:97-106; SURVEY 8(f) rank 2, the caller of warp_flow at
+ * pwc_tf.py:94-95, 121-160): out (B,(2d+1)^2,H,W), out[b, i*(2d+1)+j, y, x] = mean_c f1[b,c,y,x] * f2pad[b,c,y+i,x+j] with f2 zero-padded
+ * by d (1 <= d <= 4; the reference uses 4).  backward: grad_out -> grad_f1 / grad_f2 (B,C,H,W), either may be NULL; gather form,
+ * deterministic. */
+int ugl_cost_volume_forward(const float* f1, const float* f2, int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t d,
+                            float* out, void* stream);
+int ugl_cost_volume_backward(const float* f1, const float* f2, const float* grad_out, int32_t batch, int32_t channels, int32_t height,
+                             int32_t width, int32_t d, float* grad_f1, float* grad_f2, void* stream);
+
 /* EXTENSION — forward splat (`transformerFwd`): Model_flow.get_occlusion_mask_from_flow (model_flow.py:33-39) calls it but
  * the reference never defines it (dead code; upstream TrianFlow semantics, parity unpinned).  out[b,c,y',x'] accumulates
  * x[b,c,i,j] * bilinear weight over the four integer neighbours of (j+u, i+v); out-of-range corners are dropped;

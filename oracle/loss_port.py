@@ -137,6 +137,17 @@ def ssim_map(x: Tensor, y: Tensor, restated: bool = False) -> Tensor:
     return num / den
 
 
+def cost_volume(f1: Tensor, f2: Tensor, d: int = 4) -> Tensor:
+    """SURVEY 8(f) rank 2 — ``PWC_tf.corr_naive`` (structures/pwc_tf.py:97-106): channel-mean correlation of ``f1`` with the
+    (2d+1)^2 integer shifts of the zero-padded ``f2``; output channel ``i*(2d+1)+j`` pairs pixel (y, x) with (y+i-d, x+j-d)."""
+    if f1.shape != f2.shape:
+        raise AssertionError("cost_volume: input shapes differ")
+    H, W = f1.shape[2:]
+    f2p = F.pad(f2, (d, d, d, d), value=0)
+    n = 2 * d + 1
+    return torch.stack([(f1 * f2p[:, :, i:i + H, j:j + W]).mean(1) for i in range(n) for j in range(n)], dim=1)
+
+
 def forward_splat(x: Tensor, flow: Tensor) -> Tensor:
     """EXTENSION oracle (parity unpinned: ``transformerFwd`` is called at model_flow.py:36 but defined nowhere in the
     reference; semantics of upstream TrianFlow): every source pixel adds x * bilinear weight to the four integer

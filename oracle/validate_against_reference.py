@@ -106,6 +106,17 @@ def main(argv=None):
         ]
         for r in res:
             ok &= r["loss"] < 1e-6 and r["grad"] < 1e-5 and r["mask_flips"] == 0
+    # PWC-Net cost volume: PWC_tf.corr_naive called unbound
+    ref = R.load()
+    g = torch.Generator().manual_seed(a.seed)
+    f1 = torch.randn(a.batch, 24, a.height // 4, a.width // 4, generator=g).requires_grad_(True)
+    f2 = torch.randn(a.batch, 24, a.height // 4, a.width // 4, generator=g).requires_grad_(True)
+    go = torch.randn(a.batch, 81, a.height // 4, a.width // 4, generator=g)
+    o_r, o_p = ref.structures.PWC_tf.corr_naive(None, f1, f2), P.cost_volume(f1, f2)
+    g_r, g_p = torch.autograd.grad((o_r * go).sum(), [f1, f2]), torch.autograd.grad((o_p * go).sum(), [f1, f2])
+    cv = max(_rel(o_p.detach(), o_r.detach()), _rel(g_p[0], g_r[0]), _rel(g_p[1], g_r[1]))
+    print("%-14s worst rel err %.2e" % ("cost volume", cv))
+    ok &= cv < 1e-6
     print("PINNED" if ok else "MISMATCH")
     return 0 if ok else 1
 

@@ -131,7 +131,30 @@ def primitives():
     print("wrote %-28s %6.1f KB" % (os.path.basename(path), os.path.getsize(path) / 1024))
 
 
+def cost_volume():
+    """PWC_tf.corr_naive (structures/pwc_tf.py:97-106) called unbound: output and both input gradients"""
+    ref = R.load()
+    g = torch.Generator().manual_seed(9)
+    d = {}
+    for tag, (B, Cc, Hh, Ww) in (("a", (2, 6, 9, 14)), ("b", (1, 33, 5, 40))):
+        f1 = torch.randn(B, Cc, Hh, Ww, generator=g).requires_grad_(True)
+        f2 = torch.randn(B, Cc, Hh, Ww, generator=g).requires_grad_(True)
+        go = torch.randn(B, 81, Hh, Ww, generator=g)
+        out = ref.structures.PWC_tf.corr_naive(None, f1, f2)
+        g1, g2 = torch.autograd.grad((out * go).sum(), [f1, f2])
+        d.update({tag + "_f1": _np(f1), tag + "_f2": _np(f2), tag + "_go": _np(go), tag + "_out": _np(out), tag + "_g1": _np(g1),
+                  tag + "_g2": _np(g2)})
+    path = os.path.join(HERE, "cost_volume.npz")
+    np.savez_compressed(path, **d)
+    print("wrote %-28s %6.1f KB" % (os.path.basename(path), os.path.getsize(path) / 1024))
+
+
 def main():
+    if "--only-cost-volume" in sys.argv:
+        torch.manual_seed(0)
+        torch.set_num_threads(1)
+        cost_volume()
+        return 0
     if not R.available():
         print("reference tree not mounted; cannot (re)generate golden fixtures")
         return 1
@@ -148,6 +171,7 @@ def main():
     _run("geom_mode_s3", mk(seed=106, flow_mode="rigid"), GEOM_W, ["flows_fwd", "flows_bwd"] + dl,
          lambda t: R.reference_geom_mode(t, 3))
     primitives()
+    cost_volume()
     return 0
 
 

@@ -90,3 +90,36 @@ def test_image_pyramids_one_launch_bit_equal(cuda_device, levels, H, W):
             assert len(pyr) == levels and pyr[0] is not None
             for l in range(levels):
                 assert torch.equal(pyr[l], ref[l]), (i, mode, l)
+
+
+def test_cost_volume_vs_reference_golden(cuda_device):
+    d = load_golden("cost_volume")
+    for tag in ("a", "b"):
+        f1, f2 = d[tag + "_f1"].to(cuda_device).requires_grad_(True), d[tag + "_f2"].to(cuda_device).requires_grad_(True)
+        out = ops.cost_volume(f1, f2)
+        g1, g2 = torch.autograd.grad((out * d[tag + "_go"].to(cuda_device)).sum(), [f1, f2])
+        assert rel_err(out.cpu(), d[tag + "_out"]) < 1e-5
+        assert rel_err(g1.cpu(), d[tag + "_g1"]) < 1e-5 and rel_err(g2.cpu(), d[tag + "_g2"]) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,W,d", [(2, 32, 64, 208, 4), (1, 196, 4, 13, 4), (2, 7, 9, 33, 2), (1, 3, 2, 3, 1)])
+def test_cost_volume_vs_oracle(cuda_device, B, C, H, W, d):
+    """PWC pyramid shapes (level 2 and the 4x13 top level), sizes smaller than the search window, other radii"""
+    g = torch.Generator().manual_seed(11)
+    f1c, f2c = torch.randn(B, C, H, W, generator=g).requires_grad_(True), torch.randn(B, C, H, W, generator=g).requires_grad_(True)
+    go = torch.randn(B, (2 * d + 1) ** 2, H, W, generator=g)
+    ref = P.cost_volume(f1c, f2c, d)
+    r1, r2 = torch.autograd.grad((ref * go).sum(), [f1c, f2c])
+    f1, f2 = f1c.detach().to(cuda_device).requires_grad_(True), f2c.detach().to(cuda_device).requires_grad_(True)
+    out = ops.cost_volume(f1, f2, d)
+    g1, g2 = torch.autograd.grad((out * go.to(cuda_device)).sum(), [f1, f2])
+    assert rel_err(out.cpu(), ref.detach()) < 1e-5
+    assert rel_err(g1.cpu(), r1) < 1e-5 and rel_err(g2.cpu(), r2) < 1e-5
+    out2 = ops.cost_volume(f1, f2, d)
+    assert torch.equal(out, out2)
+    with pytest.raises(AssertionError):
+        ops.cost_volume(f1, f2[:, :, :, :-1].contiguous() if W > 1 else f2[:, :-1], d)
+    # only one input needs a gradient
+    f3 = f2c.detach().to(cuda_device)
+    g1b, = torch.autograd.grad((ops.cost_volume(f1, f3, d) * go.to(cuda_device)).sum(), [f1])
+    assert torch.equal(g1b, g1)

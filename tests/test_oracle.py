@@ -102,6 +102,28 @@ def test_primitives_vs_golden():
     assert rel_err(P.rigid_flow(d["iw_depth"], d["iw_pose"], d["iw_K"]), d["rf_out"]) < 1e-6
 
 
+def test_cost_volume_vs_golden():
+    """oracle cost volume against PWC_tf.corr_naive outputs / gradients recorded from the reference"""
+    d = load_golden("cost_volume")
+    for tag in ("a", "b"):
+        f1, f2 = d[tag + "_f1"].requires_grad_(True), d[tag + "_f2"].requires_grad_(True)
+        out = P.cost_volume(f1, f2)
+        g1, g2 = torch.autograd.grad((out * d[tag + "_go"]).sum(), [f1, f2])
+        assert rel_err(out, d[tag + "_out"]) < 1e-6
+        assert rel_err(g1, d[tag + "_g1"]) < 1e-6 and rel_err(g2, d[tag + "_g2"]) < 1e-6
+
+
+def test_cost_volume_known_answers():
+    f = torch.zeros(1, 2, 5, 6)
+    f[0, :, 2, 3] = torch.tensor([2.0, 4.0])
+    cv = P.cost_volume(f, f)                         # only the zero displacement (channel 40) sees the pixel against itself
+    assert float(cv[0, 40, 2, 3]) == 10.0 and float(cv.abs().sum()) == 10.0
+    g = torch.zeros(1, 2, 5, 6)
+    g[0, :, 0, 1] = 1.0                              # partner displaced by (-2, -2) -> channel (d-2)*9 + (d-2) = 20
+    cv = P.cost_volume(f, g)
+    assert float(cv[0, 20, 2, 3]) == 3.0 and float(cv.abs().sum()) == 3.0
+
+
 # ---- known-answer cases -------------------------------------------------------------------------------
 def test_zero_flow_resamples_with_the_half_pixel_shift():
     """even zero flow samples at ix = x*W/(W-1) - 0.5 (align_corners mismatch)."""

@@ -175,6 +175,8 @@ SIGNATURES.update({
     "ugl_flow_consis_backward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "ugl_depth_diff_forward": (C.c_int, [_p, _p, _i64, _p, _p]),
     "ugl_depth_diff_backward": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
+    "ugl_cost_volume_forward": (C.c_int, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "ugl_cost_volume_backward": (C.c_int, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "ugl_image_pyramid_multi": (C.c_int, [C.POINTER(UglPyramidArgs)]),
     "ugl_geom_rigid_workspace_bytes": (_u64, [_i, _i, _i]),
     "ugl_geom_rigid_forward": (C.c_int, [C.POINTER(UglGeomRigidArgs)]),

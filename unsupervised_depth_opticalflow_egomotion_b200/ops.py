@@ -152,6 +152,48 @@ def warp_flow(x: Tensor, flow: Tensor, use_mask: bool = False) -> Tensor:
 
 
 # ================================================================================================
+# PWC-Net cost volume (the caller of warp_flow inside the flow network)
+# ================================================================================================
+class _CostVolumeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1: Tensor, f2: Tensor, d: int):
+        f1, f2 = _dev(f1, "input1"), _dev(f2, "input2")
+        B, Cc, H, W = f1.shape
+        n = 2 * d + 1
+        out = torch.empty((B, n * n, H, W), device=f1.device, dtype=torch.float32)
+        with torch.cuda.device_of(f1):
+            _call("ugl_cost_volume_forward", f1.data_ptr(), f2.data_ptr(), B, Cc, H, W, d, out.data_ptr(), _stream_ptr())
+        ctx.save_for_backward(f1, f2)
+        ctx.d = d
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f1, f2 = ctx.saved_tensors
+        B, Cc, H, W = f1.shape
+        g = _dev(g, "grad_out")
+        g1 = torch.empty_like(f1) if ctx.needs_input_grad[0] else None
+        g2 = torch.empty_like(f2) if ctx.needs_input_grad[1] else None
+        if g1 is not None or g2 is not None:
+            with torch.cuda.device_of(f1):
+                _call("ugl_cost_volume_backward", f1.data_ptr(), f2.data_ptr(), g.data_ptr(), B, Cc, H, W, ctx.d, _ptr(g1), _ptr(g2),
+                      _stream_ptr(), launches=1)
+        return g1, g2, None
+
+
+def cost_volume(input1: Tensor, input2: Tensor, d: int = 4) -> Tensor:
+    """Drop-in for ``PWC_tf.corr_naive(input1, input2, d=4)`` (structures/pwc_tf.py:97-106): ``(B,(2d+1)^2,H,W)`` channel-mean
+    correlation of ``input1`` with the integer shifts of the zero-padded ``input2``; one kernel instead of 81 multiply / mean
+    pairs and a cat.  Same ``AssertionError`` on a shape mismatch (:99).  Differentiable w.r.t. both inputs (deterministic)."""
+    assert (input1.shape == input2.shape)
+    if input1.dim() != 4:
+        raise ValueError("cost_volume: inputs must be (B,C,H,W)")
+    if not 1 <= int(d) <= 4:
+        raise ValueError("cost_volume: d must be in [1, 4]")
+    return _CostVolumeFn.apply(input1, input2, int(d))
+
+
+# ================================================================================================
 # fused flow-mode loss (T0 / flow)
 # ================================================================================================
 FLOW_LOSS_KEYS = ("loss_flow_pixel", "loss_flow_ssim", "loss_flow_smooth", "loss_flow_consis")

@@ -106,6 +106,12 @@ def calculate_rigid_flow(depth: Tensor, pose: Tensor, intrinsics: Tensor) -> Ten
     return ops.rigid_flow(depth, Kinv, P)
 
 
+def corr_naive(input1: Tensor, input2: Tensor, d: int = 4) -> Tensor:
+    """``PWC_tf.corr_naive`` (structures/pwc_tf.py:97-106) as a free function: bind with ``PWC_tf.corr = staticmethod(corr_naive)``
+    or ``self.corr = corr_naive`` (:19)."""
+    return ops.cost_volume(input1, input2, d)
+
+
 def skewsymmetric(t: Tensor) -> Tensor:
     zero = torch.zeros_like(t[:, 0])
     return torch.stack([zero, -t[:, 2], t[:, 1], t[:, 2], zero, -t[:, 0], -t[:, 1], t[:, 0], zero], dim=1).view(-1, 3, 3)
