@@ -523,3 +523,41 @@ def test_depth_consis_fused_equals_composed(cuda_device, B, H, W, S):
         assert rel_err(x, y) < (2e-5 if i < 3 * S else GRAD_RTOL), i
     for x, y in zip(a[1], c[1]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("mode", ["geom", "depth-texture", "depth-live"])
+def test_mode_steps_full_size_determinism_and_shard_invariance(cuda_device, mode):
+    """BASELINE full size (256x832): the fused mode steps are bit-reproducible run to run (two-contribution atomics, fixed-point
+    scatter, fixed-order reductions) and every sample's losses / gradients do not depend on which batch shard it is computed in
+    (the property multi-GPU sharding relies on)."""
+    B = 4
+    t = make_triplet(B, 256, 832, 4, 3, seed=91, flow_mode="rigid").to(cuda_device)
+    W = P.GEOM_WEIGHTS
+
+    def run(lo, hi):
+        sl = lambda xs: [x[lo:hi].detach().clone().requires_grad_(True) for x in xs]
+        ff, fb, d, dl, dr = sl(t.flows_fwd), sl(t.flows_bwd), sl(t.disp), sl(t.disp_l), sl(t.disp_r)
+        pose = t.pose[lo:hi].detach().clone().requires_grad_(True)
+        il, ic, ir, K, Ki = t.img_l[lo:hi], t.img[lo:hi], t.img_r[lo:hi], t.K[lo:hi], t.K_inv[lo:hi]
+        if mode == "geom":
+            loss, _ = losses.GeometryLoss(3).forward_losses(il, ic, ir, ff, fb, d, dl, dr, pose, K, Ki)
+            leaves = ff[:3] + fb[:3] + d + dl + dr + [pose]
+        else:
+            loss, _ = losses.DepthLoss(3, mode.split("-")[1]).forward_losses(il, ic, ir, d, dl, dr, pose, K)
+            leaves = d + dl + dr + [pose]
+        live = {k: v for k, v in loss.items() if v.numel() == hi - lo and v.requires_grad}
+        # sum (not mean) over the batch so that a sample's gradient does not depend on the shard size
+        g = torch.autograd.grad(sum(W[k] * v.sum() for k, v in live.items()), leaves, allow_unused=True)
+        return live, g
+
+    a, b = run(0, B), run(0, B)
+    for k in a[0]:
+        assert torch.equal(a[0][k], b[0][k]), k
+    for x, y in zip(a[1], b[1]):
+        assert (x is None and y is None) or torch.equal(x, y)
+    h0, h1 = run(0, B // 2), run(B // 2, B)
+    for k in a[0]:
+        assert torch.equal(a[0][k], torch.cat([h0[0][k], h1[0][k]])), k
+    for x, y0, y1 in zip(a[1], h0[1], h1[1]):
+        if x is not None:
+            assert torch.equal(x, torch.cat([y0, y1])), tuple(x.shape)
