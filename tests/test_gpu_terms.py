@@ -561,3 +561,32 @@ def test_mode_steps_full_size_determinism_and_shard_invariance(cuda_device, mode
     for x, y0, y1 in zip(a[1], h0[1], h1[1]):
         if x is not None:
             assert torch.equal(x, torch.cat([y0, y1])), tuple(x.shape)
+
+
+@pytest.mark.parametrize("S,H,W", [(1, 40, 72), (2, 52, 100), (4, 64, 208)])
+def test_other_scale_counts_fused_equal_composed(cuda_device, S, H, W):
+    """num_scales other than the yaml's 3 (1, 2 and 4 levels: the 8x up-sampling path of the smoothness kernel, the 8x8 pyramid kernel,
+    sizes that are not multiples of the tiles): fused geom / depth steps against the per-method composition"""
+    t = make_triplet(2, H, W, S, S, seed=93, flow_mode="rigid").to(cuda_device)
+    Wt = P.GEOM_WEIGHTS
+    for which in ("geom", "depth"):
+        res = {}
+        for fused in (True, False):
+            sl = lambda xs: [x.detach().clone().requires_grad_(True) for x in xs]
+            ff, fb, d, dl, dr = sl(t.flows_fwd), sl(t.flows_bwd), sl(t.disp), sl(t.disp_l), sl(t.disp_r)
+            pose = t.pose.detach().clone().requires_grad_(True)
+            if which == "geom":
+                loss, _ = losses.GeometryLoss(S).forward_losses(t.img_l, t.img, t.img_r, ff, fb, d, dl, dr, pose, t.K, t.K_inv, fused=fused)
+                leaves = ff + fb + d + dl + dr + [pose]
+            else:
+                loss, _ = losses.DepthLoss(S, "texture").forward_losses(t.img_l, t.img, t.img_r, d, dl, dr, pose, t.K, fused=fused)
+                leaves = d + dl + dr + [pose]
+            live = {k: v for k, v in loss.items() if v.requires_grad and v.numel() == 2}
+            g = torch.autograd.grad(sum(Wt[k] * v.mean() for k, v in live.items()), leaves, allow_unused=True)
+            res[fused] = (live, g)
+        for k in res[True][0]:
+            assert loss_rel_err(res[True][0][k], res[False][0][k]) < LOSS_RTOL, (which, k)
+        for i, (a, b) in enumerate(zip(res[True][1], res[False][1])):
+            assert (a is None) == (b is None), (which, i)
+            if a is not None:
+                assert rel_err(a, b) < GRAD_RTOL, (which, i)
