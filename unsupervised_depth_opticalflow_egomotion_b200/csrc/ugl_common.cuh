@@ -224,7 +224,7 @@ UGL_HD void moments_add(Moments& m, float x, float y) {
 
 // The SSIM terms in the reference's own operation order (ssim.py:8-18), each op rounded to fp32:
 // cancellation in E[x^2]-mu^2 amplifies any re-association, so this is pinned, not contracted.
-struct SsimTerms { float mx, my, n1, n2, d1, d2, S; };
+struct SsimTerms { float mx, my, n1, n2, d1, d2, S, rD; };   // rD = 1 / (d1 d2), shared by the value and its derivatives
 
 template <bool kExactDiv = true>
 UGL_HD SsimTerms ssim_terms(const Moments& m) {
@@ -242,7 +242,9 @@ UGL_HD SsimTerms ssim_terms(const Moments& m) {
   t.d2 = add_rn(add_rn(vx, vy), kC2);
   // kExactDiv = false: the moments stay bit-identical to ATen's, only the last quotient uses the ~1-ulp
   // reciprocal (2 instructions instead of the ~15 of the IEEE division subroutine)
-  t.S = kExactDiv ? div_rn(mul_rn(t.n1, t.n2), mul_rn(t.d1, t.d2)) : fast_div(mul_rn(t.n1, t.n2), mul_rn(t.d1, t.d2));
+  const float dd = mul_rn(t.d1, t.d2);
+  t.rD = fast_div(1.0f, dd);
+  t.S = kExactDiv ? div_rn(mul_rn(t.n1, t.n2), dd) : mul_rn(mul_rn(t.n1, t.n2), t.rD);
   return t;
 }
 
@@ -255,7 +257,7 @@ UGL_HD float ssim_loss_value(float S) {
 }
 // d S / d(mu_x), d(E[x^2]), d(mu_y), d(E[y^2]), d(E[xy]) of one window, scaled by g.
 UGL_HD void ssim_partials(const SsimTerms& t, float g, float& ax, float& bx, float& ay, float& by, float& cxy) {
-  const float invD = fast_div(g, t.d1 * t.d2);
+  const float invD = g * t.rD;
   ax = (2.f * t.my * (t.n2 - t.n1) - t.S * 2.f * t.mx * (t.d2 - t.d1)) * invD;
   ay = (2.f * t.mx * (t.n2 - t.n1) - t.S * 2.f * t.my * (t.d2 - t.d1)) * invD;
   bx = by = (-t.S * t.d1) * invD;

@@ -418,23 +418,24 @@ struct FlowGradTile {
         float cA[2] = {0.f, 0.f}, cB[2] = {0.f, 0.f}, cC[2] = {0.f, 0.f};
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
-          if (o == 0 ? in0 : in1) {
-            Moments m = {0.f, 0.f, 0.f, 0.f, 0.f};
+          // both windows are evaluated unconditionally (a window centred outside the image sees zero planes: finite values) and
+          // masked afterwards: no divergent region around 60 % of the phase's arithmetic
+          const bool in = (o == 0 ? in0 : in1);
+          Moments m = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                m.sx = add_rn(m.sx, x[r][o + k]); m.sy = add_rn(m.sy, y[r][o + k]);
-                m.sxx = add_rn(m.sxx, xx[r][o + k]); m.syy = add_rn(m.syy, yy[r][o + k]); m.sxy = add_rn(m.sxy, xy[r][o + k]);
-              }
-            const SsimTerms t = ssim_terms<false>(m);
-            const float v = mul_rn(sub_rn(1.0f, t.S), 0.5f);
-            const float g = (v >= 0.f && v <= 1.f) ? -0.5f : 0.f;
-            float ax, bx;
-            ssim_partials(t, g, ax, bx, cA[o], cB[o], cC[o]);
-            const bool interior = (ly >= 1 && ly <= TH && lx + o >= 1 && lx + o <= TW);
-            if (interior) ssim_sum += (v < 0.f ? 0.f : (v > 1.f ? 1.f : v));
-          }
+            for (int k = 0; k < 3; ++k) {
+              m.sx = add_rn(m.sx, x[r][o + k]); m.sy = add_rn(m.sy, y[r][o + k]);
+              m.sxx = add_rn(m.sxx, xx[r][o + k]); m.syy = add_rn(m.syy, yy[r][o + k]); m.sxy = add_rn(m.sxy, xy[r][o + k]);
+            }
+          const SsimTerms t = ssim_terms<false>(m);
+          const float v = mul_rn(sub_rn(1.0f, t.S), 0.5f);
+          const float g = (in && v >= 0.f && v <= 1.f) ? -0.5f : 0.f;      // g = 0 zeroes every coefficient of a masked window
+          float ax, bx;
+          ssim_partials(t, g, ax, bx, cA[o], cB[o], cC[o]);
+          const bool interior = in && (ly >= 1 && ly <= TH && lx + o >= 1 && lx + o <= TW);
+          ssim_sum += interior ? (v < 0.f ? 0.f : (v > 1.f ? 1.f : v)) : 0.f;
         }
         float* oc = sm + kOffCoef + (c * 3) * CN + ly * CW + lx;
         *reinterpret_cast<float2*>(oc) = make_float2(cA[0], cA[1]);
