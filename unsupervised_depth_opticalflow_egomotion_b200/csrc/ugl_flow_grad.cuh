@@ -389,14 +389,17 @@ struct FlowGradTile {
     const float* xbase = sm + (GP_X0 + 6 * dir) * PN;
     const float* ybase = sm + (GP_Y0 + 6 * dir) * PN;
     float ssim_sum = 0.f;
-    const int units = (dir == 0 && !kDepth ? 4 : 3) * NS;      // depth mode has no flow smoothness: no edge-weight units
-    for (int u = tid; u < units; u += nt) {
-      const int c = u / NS, s = u - c * NS;
+    const int nunit = (dir == 0 && !kDepth) ? 4 : 3;           // depth mode has no flow smoothness: no edge-weight units
+    // strip-outer, unit-inner: with NS <= NT (the 32x12 tile has 238 strips) every thread owns one strip, decodes it once and
+    // runs its 3 (4) units back to back; the unit type is uniform across the CTA
+    for (int s = tid; s < NS; s += nt) {
       const int ly = s / SW, lx = (s - ly * SW) * 2;          // halo-1 coordinates of the left centre
       const int i = tc.y0 - 1 + ly, j0 = tc.x0 - 1 + lx;
       const int c0 = (ly + 1) * PW + (lx + 1);                // photometry-plane index of the left centre
       const bool row_in = (i >= 0 && i < L.h);
       const bool in0 = row_in && j0 >= 0 && j0 < L.w, in1 = row_in && j0 + 1 >= 0 && j0 + 1 < L.w;
+#pragma unroll 1
+      for (int c = 0; c < nunit; ++c) {
       if (c < 3) {
         const float* xpl = xbase + c * PN;
         const float* ypl = ybase + c * PN;
@@ -460,6 +463,7 @@ struct FlowGradTile {
         }
         *reinterpret_cast<float2*>(sm + kOffEdge + ly * CW + lx) = make_float2(wx[0], wx[1]);
         *reinterpret_cast<float2*>(sm + kOffEdge + CN + ly * CW + lx) = make_float2(wy[0], wy[1]);
+      }
       }
     }
     if (dir == 0) acc[FA_SSIM_F] += ssim_sum; else acc[FA_SSIM_B] += ssim_sum;
