@@ -123,10 +123,14 @@ extern "C" int emu_flow_loss_forward_grad(const UglFlowLossArgs* a) {
     const TileCoord tc = decode_tile<kBTW, kBTH>(gp.base, tile);
     float acc[FA_COUNT] = {0};
     Tile::phase1(gp, tc, 0, 1, sm.data(), acc);
-    for (int dir = 0; dir < 2; ++dir) {
-      Tile::phase2(gp, tc, dir, 0, 1, sm.data(), acc);
-      Tile::phase3(gp, tc, dir, 0, 1, sm.data());
+    std::vector<float2> g3v((size_t)Tile::kP3 * 4, make_float2(0.f, 0.f));
+    float2 (*g3)[4] = reinterpret_cast<float2 (*)[4]>(g3v.data());
+    for (int c = 0; c < 3; ++c) {
+      Tile::phase2(gp, tc, c, 0, 1, sm.data(), acc);
+      if (c == 0 && !Tile::kDepth) Tile::phase2(gp, tc, 3, 0, 1, sm.data(), acc);
+      Tile::phase3_accumulate(gp, tc, c, 0, 1, sm.data(), g3);
     }
+    Tile::phase3_store(gp, tc, 0, 1, sm.data(), g3);
     Tile::phase4a(gp, tc, 0, 1, sm.data(), acc);
     Tile::phase4b(gp, tc, 0, 1, sm.data());
     for (int k = 0; k < FA_COUNT; ++k) partials[(size_t)tile * FA_COUNT + k] = acc[k];
@@ -171,10 +175,14 @@ extern "C" int emu_geom_flow_forward_grad(const UglGeomFlowArgs* g) {
     for (int k = 0; k < 9; ++k) mats[k] = gp.Kinv[tc.level][tc.b * 9 + k];
     for (int k = 0; k < 12; ++k) { mats[9 + k] = gp.P[0][tc.level][tc.b * 12 + k]; mats[21 + k] = gp.P[1][tc.level][tc.b * 12 + k]; }
     Tile::phase1(gp, tc, 0, 1, sm.data(), acc, mats);
-    for (int dir = 0; dir < 2; ++dir) {
-      Tile::phase2(gp, tc, dir, 0, 1, sm.data(), acc);
-      Tile::phase3(gp, tc, dir, 0, 1, sm.data());
+    std::vector<float2> g3v((size_t)Tile::kP3 * 4, make_float2(0.f, 0.f));
+    float2 (*g3)[4] = reinterpret_cast<float2 (*)[4]>(g3v.data());
+    for (int c = 0; c < 3; ++c) {
+      Tile::phase2(gp, tc, c, 0, 1, sm.data(), acc);
+      if (c == 0 && !Tile::kDepth) Tile::phase2(gp, tc, 3, 0, 1, sm.data(), acc);
+      Tile::phase3_accumulate(gp, tc, c, 0, 1, sm.data(), g3);
     }
+    Tile::phase3_store(gp, tc, 0, 1, sm.data(), g3);
     Tile::phase4a(gp, tc, 0, 1, sm.data(), acc);
     Tile::phase4b(gp, tc, 0, 1, sm.data());
     for (int k = 0; k < GA_COUNT; ++k) partials[(size_t)tile * GA_COUNT + k] = acc[k];
@@ -245,10 +253,14 @@ extern "C" int emu_depth_ssim_forward_grad(const UglDepthSsimArgs* g) {
     for (int k = 0; k < 9; ++k) mats[k] = gp.Kinv[tc.level][tc.b * 9 + k];
     for (int k = 0; k < 12; ++k) { mats[9 + k] = gp.P[0][tc.level][tc.b * 12 + k]; mats[21 + k] = gp.P[1][tc.level][tc.b * 12 + k]; }
     Tile::phase1_depth(gp, tc, 0, 1, sm.data(), acc, mats);
-    for (int dir = 0; dir < 2; ++dir) {
-      Tile::phase2(gp, tc, dir, 0, 1, sm.data(), acc);
-      Tile::phase3(gp, tc, dir, 0, 1, sm.data());
+    std::vector<float2> g3v((size_t)Tile::kP3 * 4, make_float2(0.f, 0.f));
+    float2 (*g3)[4] = reinterpret_cast<float2 (*)[4]>(g3v.data());
+    for (int c = 0; c < 3; ++c) {
+      Tile::phase2(gp, tc, c, 0, 1, sm.data(), acc);
+      if (c == 0 && !Tile::kDepth) Tile::phase2(gp, tc, 3, 0, 1, sm.data(), acc);
+      Tile::phase3_accumulate(gp, tc, c, 0, 1, sm.data(), g3);
     }
+    Tile::phase3_store(gp, tc, 0, 1, sm.data(), g3);
     for (int k = 0; k < GA_COUNT; ++k) partials[(size_t)tile * GA_COUNT + k] = acc[k];
   }
   for (int b = 0; b < p.B; ++b) {

@@ -29,6 +29,8 @@
 #if !defined(__CUDACC__)
 struct float2 { float x, y; };
 inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+struct alignas(16) float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #endif
 
 namespace ugl {
@@ -83,6 +85,57 @@ UGL_HD float sqrt_rn(float a) {
 #endif
 }
 UGL_HD float sgnf(float v) { return (float)((v > 0.f) - (v < 0.f)); }
+
+// ---- packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2 = add/mul/fma.rn.f32x2) ---------------------------------------
+// One instruction produces two individually IEEE-rounded fp32 results from 64-bit register pairs.  The fp32 pipe still
+// needs two passes, so a pure fp32 stream gains nothing (profiles/microbench/f32x2_issue.cu: 123 vs 126 results/clk/SM), but
+// an ISSUE-bound mix does: the packed form frees every second issue slot for the integer / shared-memory instructions
+// around it (51 -> 66 results/clk/SM with two integer ops per pair).  The stencil phases of the single-pass kernel carry
+// the two warp directions of a pixel as such a pair (.x = forward-flow / frame-0 direction, .y = the other), which keeps
+// every rounding of the scalar formulation and halves the fp32 instruction count.  The host emulator gets the scalar ops.
+UGL_HD float2 add2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(add_rn(a.x, b.x), add_rn(a.y, b.y));
+#endif
+}
+UGL_HD float2 mul2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul2_rn(a, b);
+#else
+  return make_float2(mul_rn(a.x, b.x), mul_rn(a.y, b.y));
+#endif
+}
+UGL_HD float2 fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+UGL_HD float2 splat2(float v) { return make_float2(v, v); }
+// acc + prod where prod is the (separately rounded) result of a mul2.  ptxas 12.9 contracts `mul.rn.f32x2` followed by
+// `add.rn.f32x2` into one FFMA2 although both carry .rn (it does not do that to the scalar forms; -fmad=false, a volatile asm and
+// a literal 1.0 do not stop it; checked in the SASS), which would drop the product's rounding and break the bit-identity of the
+// SSIM moments with ATen's.  fma(prod, one, acc) with a 1.0 the compiler cannot see (a kernel parameter) is the same single
+// rounding of prod + acc, costs the same one instruction and cannot be contracted (it would need two multiplies).
+UGL_HD float2 acc2_rn(float2 acc, float2 prod, float2 one) {
+#if defined(__CUDA_ARCH__)
+  return __ffma2_rn(prod, one, acc);
+#else
+  (void)one;
+  return make_float2(add_rn(acc.x, prod.x), add_rn(acc.y, prod.y));
+#endif
+}
+// a - b with one rounding: fma(b, -1, a) (the product is exact)
+UGL_HD float2 sub2(float2 a, float2 b) { return fma2(b, splat2(-1.0f), a); }
+UGL_HD float2 div_c2(float2 a, float c, float rc) {
+  const float2 q = mul2(a, splat2(rc));
+  return fma2(fma2(splat2(-c), q, a), splat2(rc), q);
+}
+UGL_HD float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+UGL_HD float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
 // a / c for a divisor whose correctly rounded reciprocal rc = RN(1/c) is known: multiply, one FMA
 // residual, one FMA correction.  Gives the correctly rounded quotient (same bits as IEEE division;
@@ -257,11 +310,14 @@ UGL_HD float ssim_loss_value(float S) {
 }
 // d S / d(mu_x), d(E[x^2]), d(mu_y), d(E[y^2]), d(E[xy]) of one window, scaled by g.
 UGL_HD void ssim_partials(const SsimTerms& t, float g, float& ax, float& bx, float& ay, float& by, float& cxy) {
-  const float invD = g * t.rD;
-  ax = (2.f * t.my * (t.n2 - t.n1) - t.S * 2.f * t.mx * (t.d2 - t.d1)) * invD;
-  ay = (2.f * t.mx * (t.n2 - t.n1) - t.S * 2.f * t.my * (t.d2 - t.d1)) * invD;
-  bx = by = (-t.S * t.d1) * invD;
-  cxy = (2.f * t.n1) * invD;
+  // explicit operation order (no compiler contraction): the packed variant ssim_partials2 below performs the same roundings,
+  // so the single-pass, recompute and per-method kernels agree on these cancellation-prone coefficients
+  const float invD = mul_rn(g, t.rD), invD2 = add_rn(invD, invD);
+  const float nS = -t.S, dn = sub_rn(t.n2, t.n1), dd = sub_rn(t.d2, t.d1);
+  ax = mul_rn(fma_rn(t.my, dn, mul_rn(mul_rn(nS, t.mx), dd)), invD2);
+  ay = mul_rn(fma_rn(t.mx, dn, mul_rn(mul_rn(nS, t.my), dd)), invD2);
+  bx = by = mul_rn(mul_rn(nS, t.d1), invD);
+  cxy = mul_rn(t.n1, invD2);
 }
 // Given window sums, produce g * dS/d(mu_y), g * dS/d(E[y^2]), g * dS/d(E[xy]) where g = d loss / dS
 // (= -1/2 inside the clamp range [0,1] inclusive, 0 outside — torch.clamp backward).
@@ -271,6 +327,40 @@ UGL_HD void ssim_backward_coeffs(const Moments& m, float& cA, float& cB, float& 
   const float g = (v >= 0.f && v <= 1.f) ? -0.5f : 0.f;
   float ax, bx;
   ssim_partials(t, g, ax, bx, cA, cB, cC);
+}
+
+// ---- the same SSIM terms for a pair of windows (the two warp directions of one window position): identical roundings,
+// packed instructions.  n1 = 2 mx my + C1 and n2 = 2 cxy + C2 use one FMA each: the doubling is exact, so the single
+// rounding equals the scalar add_rn(mul_rn(2, .), C).
+struct Moments2 { float2 sx, sy, sxx, syy, sxy; };
+struct SsimTerms2 { float2 mx, my, n1, n2, d1, d2, S, rD; };
+
+UGL_HD SsimTerms2 ssim_terms2(const Moments2& m, float2 one) {
+  SsimTerms2 t;
+  constexpr float r9 = 1.0f / 9.0f;
+  t.mx = div_c2(m.sx, 9.0f, r9);
+  t.my = div_c2(m.sy, 9.0f, r9);
+  const float2 mxx = mul2(t.mx, t.mx), myy = mul2(t.my, t.my), mxy = mul2(t.mx, t.my);
+  const float2 vx = sub2(div_c2(m.sxx, 9.0f, r9), mxx);
+  const float2 vy = sub2(div_c2(m.syy, 9.0f, r9), myy);
+  const float2 cxy = sub2(div_c2(m.sxy, 9.0f, r9), mxy);
+  t.n1 = fma2(splat2(2.0f), mxy, splat2(kC1));
+  t.n2 = fma2(splat2(2.0f), cxy, splat2(kC2));
+  t.d1 = add2(acc2_rn(myy, mxx, one), splat2(kC1));     // mxx + myy: a sum of products (see acc2_rn)
+  t.d2 = add2(add2(vx, vy), splat2(kC2));
+  const float2 dd = mul2(t.d1, t.d2);
+  t.rD = make_float2(fast_div(1.0f, dd.x), fast_div(1.0f, dd.y));
+  t.S = mul2(mul2(t.n1, t.n2), t.rD);
+  return t;
+}
+// g * dS/d(mu_y), g * dS/d(E[y^2]), g * dS/d(E[xy]) of both windows (ssim_partials' ay, by, cxy)
+UGL_HD void ssim_partials2(const SsimTerms2& t, float2 g, float2& cA, float2& cB, float2& cC) {
+  const float2 invD = mul2(g, t.rD), invD2 = mul2(invD, splat2(2.0f));
+  const float2 nS = mul2(t.S, splat2(-1.0f));
+  const float2 e = fma2(t.mx, sub2(t.n2, t.n1), mul2(mul2(nS, t.my), sub2(t.d2, t.d1)));
+  cA = mul2(e, invD2);
+  cB = mul2(mul2(nS, t.d1), invD);
+  cC = mul2(t.n1, invD2);
 }
 
 // ---- dynamic mask (model_geometry.py:698-707): n(x) = sqrt(x0^2 + x1^2) + 1e-12 ; dyn = [n(|rf-f|)^2 < alpha (n(f)^2 + n(rf)^2) + beta]

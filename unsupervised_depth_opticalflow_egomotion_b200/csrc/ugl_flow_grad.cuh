@@ -147,23 +147,22 @@ UGL_HD void flow_photo_pixel_c(const FlowLevelDesc& L, int b, int i, int j, cons
   }
 }
 
-// shared-memory planes of the single-pass kernel (halo-2 tile).  x = I*w and y = W*w are stored pre-multiplied per
-// direction so the SSIM units do not re-form them for each of their 12 taps.
-enum GradPlane { GP_I0 = 0, GP_X0 = 3, GP_Y0 = 6, /* direction d: GP_X0 + 6 d, GP_Y0 + 6 d */ GP_WF = 15, GP_WB = 16,
-                 GP_UF = 17, GP_VF, GP_UB, GP_VB, GP_COUNT };
+// shared-memory planes of the single-pass kernel (halo-2 tile).  x = I*w and y = W*w are stored pre-multiplied, and the two
+// warp directions of a pixel sit side by side as one float2 (.x = direction 0: forward flow / frame 0, .y = direction 1), the
+// operand form of the packed fp32 instructions (add2 / mul2 / fma2) the stencil phases run on.
+//   scalar planes: I (3), pre-scaled flows (4);  pair planes (2 floats per pixel): X[c], Y[c] (c = 0..2), W
+enum GradPlane { GP_I0 = 0, GP_UF = 3, GP_VF, GP_UB, GP_VB, GP_X2 = 7 /* pair planes X[c] at GP_X2 + 2c */, GP_Y2 = 13, GP_W2 = 19, GP_COUNT = 21 };
 
 template <int PN>
 UGL_HD void store_grad_planes(float* sm, int idx, const Photo& P, float uf, float vf, float ub, float vb) {
+  const float2 w2 = make_float2(P.w_f, P.w_b);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     sm[(GP_I0 + c) * PN + idx] = P.I[c];
-    sm[(GP_X0 + c) * PN + idx] = mul_rn(P.I[c], P.w_f);
-    sm[(GP_Y0 + c) * PN + idx] = mul_rn(P.Wf[c], P.w_f);
-    sm[(GP_X0 + 6 + c) * PN + idx] = mul_rn(P.I[c], P.w_b);
-    sm[(GP_Y0 + 6 + c) * PN + idx] = mul_rn(P.Wb[c], P.w_b);
+    *reinterpret_cast<float2*>(sm + (GP_X2 + 2 * c) * PN + 2 * idx) = mul2(splat2(P.I[c]), w2);
+    *reinterpret_cast<float2*>(sm + (GP_Y2 + 2 * c) * PN + 2 * idx) = mul2(make_float2(P.Wf[c], P.Wb[c]), w2);
   }
-  sm[GP_WF * PN + idx] = P.w_f;
-  sm[GP_WB * PN + idx] = P.w_b;
+  *reinterpret_cast<float2*>(sm + GP_W2 * PN + 2 * idx) = w2;
   constexpr float r20 = 1.0f / 20.0f;
   sm[GP_UF * PN + idx] = div_c(uf, 20.0f, r20);
   sm[GP_VF * PN + idx] = div_c(vf, 20.0f, r20);
@@ -173,6 +172,7 @@ UGL_HD void store_grad_planes(float* sm, int idx, const Photo& P, float uf, floa
 
 struct FlowGradParams {
   FlowLossParams base;
+  float one = 1.0f;           // an opaque 1.0 for acc2_rn (ugl_common.cuh): keeps ptxas from contracting packed products into their sums
   float* basis[kMaxLevels];   // (B, 14, h, w) per level
   // geom mode only (Model_geometry): in-kernel rigid flow -> dynamic mask, packed masks out
   const float* disp[kMaxLevels];          // (B,1,h,w) centre disparity
@@ -209,11 +209,14 @@ struct FlowGradTile {
   static constexpr int PW = TW + 2 * R, PH = TH + 2 * R, PN = PW * PH;   // photometry planes (halo 2)
   static constexpr int CW = TW + 2, CH = TH + 2, CN = CW * CH;           // coefficient / edge planes (halo 1)
   static constexpr int TN = TW * TH;
-  static constexpr int kOffCoef = GP_COUNT * PN;                          // 9 planes [c][A,B,C], current direction
-  static constexpr int kOffEdge = kOffCoef + 9 * CN;                      // wx, wy
-  static constexpr int kOffDW = kOffEdge + 2 * CN;                        // 12 planes keep*dW/d(u,v) + 4 planes L1 sign sums
+  static constexpr int kOffCoef = GP_COUNT * PN;                          // 3 pair planes A, B, C of the CURRENT channel (both directions)
+  static constexpr int kOffEdge = kOffCoef + 6 * CN;                      // wx, wy
+  static constexpr int kOffS4 = GP_X2 * PN;                               // phase 4: 8 planes of signed weights over the (dead) X / Y pair planes
+  static_assert(8 * CN <= 12 * PN, "phase-4 planes must fit into the X / Y pair planes");
+  static constexpr int kOffDW = kOffEdge + 2 * CN;                        // 6 pair planes keep*dW_c/d(u|v) [2c+uv] + 2 pair planes L1 sign sums (u, v)
   static constexpr int kSmemFloats = kOffDW + 16 * TN;
-  static_assert(PN % 2 == 0 && CN % 2 == 0 && (GP_COUNT * PN) % 2 == 0, "planes must stay 8-byte aligned for float2 access");
+  static_assert(PW % 2 == 0 && CW % 2 == 0 && PN % 4 == 0 && CN % 2 == 0 && TN % 2 == 0,
+                "pair planes are read as float4 (two pixels x two directions): every plane must start 16-byte aligned");
 
   // phase 1: photometry on the halo-2 tile; interior pixels also: L1/weight/consistency sums, warp Jacobians,
   // L1 sign sums (shared memory) and the consistency basis (global)
@@ -242,9 +245,10 @@ struct FlowGradTile {
         flow_photo_pixel_c<true, kGeom>(L, tc.b, i, j, cur, P, dW);
         if (interior) {
           const int t = (ly - R) * TW + (lx - R);
-          float* o = sm + kOffDW + t;
+          float* o = sm + kOffDW + 2 * t;
 #pragma unroll
-          for (int k = 0; k < 12; ++k) o[k * TN] = dW[k];
+          for (int k = 0; k < 6; ++k) *reinterpret_cast<float2*>(o + k * 2 * TN) = make_float2(dW[k], dW[6 + k]);
+          float sgu[2], sgv[2];
 #pragma unroll
           for (int dir = 0; dir < 2; ++dir) {
             float su = 0.f, sv = 0.f;
@@ -254,9 +258,10 @@ struct FlowGradTile {
               su += sg * dW[6 * dir + 2 * c];
               sv += sg * dW[6 * dir + 2 * c + 1];
             }
-            o[(12 + 2 * dir) * TN] = su;
-            o[(13 + 2 * dir) * TN] = sv;
+            sgu[dir] = su; sgv[dir] = sv;
           }
+          *reinterpret_cast<float2*>(o + 12 * TN) = make_float2(sgu[0], sgu[1]);
+          *reinterpret_cast<float2*>(o + 14 * TN) = make_float2(sgv[0], sgv[1]);
           float om;   // mask of the direction-consistency term: 1 - w_f (flow mode) / 1 - occ_f (geom mode)
           if (kGeom) {
             // rigid flow of the centre disparity under both poses -> dynamic masks; L1 split into rigid / dynamic parts
@@ -342,9 +347,9 @@ struct FlowGradTile {
         P.d_f = P.d_b = 0.f;
         if (interior) {
           const int t = (ly - R) * TW + (lx - R);
-          float* o = sm + kOffDW + t;
+          float* o = sm + kOffDW + 2 * t;
 #pragma unroll
-          for (int k = 0; k < 12; ++k) o[k * TN] = dW[k];
+          for (int k = 0; k < 6; ++k) *reinterpret_cast<float2*>(o + k * 2 * TN) = make_float2(dW[k], dW[6 + k]);
 #pragma unroll
           for (int d = 0; d < 2; ++d) {
             const float* sb = gp.src_bil[d][tc.level] + (long)tc.b * 3 * plane + pix;
@@ -360,8 +365,8 @@ struct FlowGradTile {
             const float r3 = 1.0f / 3.0f;
             const float tex = div_c(a, 3.0f, r3) < div_c(s, 3.0f, r3) ? 1.f : 0.f;     // compute_texture_mask
             const float m = mul_rn(valid[d], tex);
-            o[(12 + 2 * d) * TN] = su * tex;          // phase 3 multiplies by the SSIM weight (valid): valid * tex in total
-            o[(13 + 2 * d) * TN] = sv * tex;
+            o[12 * TN + d] = su * tex;                // phase 3 multiplies by the SSIM weight (valid): valid * tex in total
+            o[14 * TN + d] = sv * tex;
             acc[d == 0 ? FA_PIX_F : FA_PIX_B] += a * m;
             acc[d == 0 ? FA_W_F : FA_W_B] += valid[d];
             acc[d == 0 ? GA_WD_F : GA_WD_B] += m;
@@ -376,74 +381,71 @@ struct FlowGradTile {
     }
   }
 
-  // phase 2 (per direction): work units = (channel, 1x2 strip of the halo-1 region), flattened so that the 3 x 306
-  // units spread evenly over the CTA (per-strip loops left two warps with double work and six waiting at the barrier).
-  // A unit loads the 3x4 taps it needs once, forms x = I*w, y = W*w and their products once, and accumulates the two
-  // 3x3 windows in the reference's row-major order (bit-identical SSIM).  It writes the SSIM backward coefficients;
-  // window centres that are interior pixels also add their SSIM loss value.  In the first direction a fourth unit
-  // type computes the smoothness edge weights of the strip.
-  static UGL_HD void phase2(const FlowGradParams& gp, const TileCoord& tc, int dir, int tid, int nt, float* sm, float* acc) {
+  // phase 2, unit c (both directions at once).  c = 0..2: SSIM of channel c for every 1x2 strip of the halo-1 region.  A unit
+  // loads its 3x4 taps once as (direction 0, direction 1) pairs (128-bit shared loads: two pixels x two directions), forms the
+  // products once and accumulates the two 3x3 windows in the reference's row-major order (bit-identical SSIM), all in packed
+  // fp32 instructions: one FADD2 / FMUL2 / FFMA2 does the work of both directions.  It writes the SSIM backward coefficients
+  // of this channel as pairs; window centres that are interior pixels also add their SSIM loss value.  c = 3: the smoothness
+  // edge weights of the strip (flow / geom modes).  The kernel runs channel by channel (phase 2 -> phase 3 accumulate) so only
+  // ONE channel's coefficient planes live in shared memory: 88 KB per CTA keeps two CTAs per SM inside the 196 KB carve-out and
+  // leaves 60 KB of L1 for the warps' gathers (with all three channels resident the carve-out grows to 228 KB and the gathers
+  // of phase 1 miss: measured 0.424 vs 0.347 ms).
+  static UGL_HD void phase2(const FlowGradParams& gp, const TileCoord& tc, int c, int tid, int nt, float* sm, float* acc) {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     constexpr int SW = CW / 2;                       // strips per row
-    constexpr int NS = SW * CH;                      // strips per tile
-    const float* xbase = sm + (GP_X0 + 6 * dir) * PN;
-    const float* ybase = sm + (GP_Y0 + 6 * dir) * PN;
-    float ssim_sum = 0.f;
-    const int nunit = (dir == 0 && !kDepth) ? 4 : 3;           // depth mode has no flow smoothness: no edge-weight units
-    // strip-outer, unit-inner: with NS <= NT (the 32x12 tile has 238 strips) every thread owns one strip, decodes it once and
-    // runs its 3 (4) units back to back; the unit type is uniform across the CTA
+    constexpr int NS = SW * CH;                      // strips per tile (238 for the 32x12 tile: one per thread)
+    float2 ssim_sum = make_float2(0.f, 0.f);
+    const float2 one = splat2(gp.one);
     for (int s = tid; s < NS; s += nt) {
       const int ly = s / SW, lx = (s - ly * SW) * 2;          // halo-1 coordinates of the left centre
       const int i = tc.y0 - 1 + ly, j0 = tc.x0 - 1 + lx;
-      const int c0 = (ly + 1) * PW + (lx + 1);                // photometry-plane index of the left centre
+      const int c0 = (ly + 1) * PW + (lx + 1);                // photometry-plane index of the left centre (odd: c0 - 1 is 16-byte aligned in a pair plane)
       const bool row_in = (i >= 0 && i < L.h);
       const bool in0 = row_in && j0 >= 0 && j0 < L.w, in1 = row_in && j0 + 1 >= 0 && j0 + 1 < L.w;
-#pragma unroll 1
-      for (int c = 0; c < nunit; ++c) {
       if (c < 3) {
-        const float* xpl = xbase + c * PN;
-        const float* ypl = ybase + c * PN;
-        float x[3][4], y[3][4], xx[3][4], yy[3][4], xy[3][4];
+        const float* xpl = sm + (GP_X2 + 2 * c) * PN + 2 * (c0 - 1);
+        const float* ypl = sm + (GP_Y2 + 2 * c) * PN + 2 * (c0 - 1);
+        Moments2 m[2];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          const int o = c0 + (r - 1) * PW;
-          const float2 xa = *reinterpret_cast<const float2*>(xpl + o - 1), xb = *reinterpret_cast<const float2*>(xpl + o + 1);
-          const float2 ya = *reinterpret_cast<const float2*>(ypl + o - 1), yb = *reinterpret_cast<const float2*>(ypl + o + 1);
-          x[r][0] = xa.x; x[r][1] = xa.y; x[r][2] = xb.x; x[r][3] = xb.y;
-          y[r][0] = ya.x; y[r][1] = ya.y; y[r][2] = yb.x; y[r][3] = yb.y;
+          const int o = 2 * (r - 1) * PW;
+          const float4 xa = *reinterpret_cast<const float4*>(xpl + o), xb = *reinterpret_cast<const float4*>(xpl + o + 4);
+          const float4 ya = *reinterpret_cast<const float4*>(ypl + o), yb = *reinterpret_cast<const float4*>(ypl + o + 4);
+          const float2 x[4] = {lo2(xa), hi2(xa), lo2(xb), hi2(xb)}, y[4] = {lo2(ya), hi2(ya), lo2(yb), hi2(yb)};
+          float2 xx[4], yy[4], xy[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            xx[r][k] = mul_rn(x[r][k], x[r][k]);
-            yy[r][k] = mul_rn(y[r][k], y[r][k]);
-            xy[r][k] = mul_rn(x[r][k], y[r][k]);
-          }
-        }
-        float cA[2] = {0.f, 0.f}, cB[2] = {0.f, 0.f}, cC[2] = {0.f, 0.f};
+          for (int k = 0; k < 4; ++k) { xx[k] = mul2(x[k], x[k]); yy[k] = mul2(y[k], y[k]); xy[k] = mul2(x[k], y[k]); }
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          // both windows are evaluated unconditionally (a window centred outside the image sees zero planes: finite values) and
-          // masked afterwards: no divergent region around 60 % of the phase's arithmetic
-          const bool in = (o == 0 ? in0 : in1);
-          Moments m = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int r = 0; r < 3; ++r)
+          for (int w = 0; w < 2; ++w)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              m.sx = add_rn(m.sx, x[r][o + k]); m.sy = add_rn(m.sy, y[r][o + k]);
-              m.sxx = add_rn(m.sxx, xx[r][o + k]); m.syy = add_rn(m.syy, yy[r][o + k]); m.sxy = add_rn(m.sxy, xy[r][o + k]);
+              if (r == 0 && k == 0) {     // 0 + v == v: the first tap initialises the sums
+                m[w].sx = x[w]; m[w].sy = y[w]; m[w].sxx = xx[w]; m[w].syy = yy[w]; m[w].sxy = xy[w];
+              } else {
+                m[w].sx = add2(m[w].sx, x[w + k]); m[w].sy = add2(m[w].sy, y[w + k]);
+                m[w].sxx = acc2_rn(m[w].sxx, xx[w + k], one); m[w].syy = acc2_rn(m[w].syy, yy[w + k], one); m[w].sxy = acc2_rn(m[w].sxy, xy[w + k], one);
+              }
             }
-          const SsimTerms t = ssim_terms<false>(m);
-          const float v = mul_rn(sub_rn(1.0f, t.S), 0.5f);
-          const float g = (in && v >= 0.f && v <= 1.f) ? -0.5f : 0.f;      // g = 0 zeroes every coefficient of a masked window
-          float ax, bx;
-          ssim_partials(t, g, ax, bx, cA[o], cB[o], cC[o]);
-          const bool interior = in && (ly >= 1 && ly <= TH && lx + o >= 1 && lx + o <= TW);
-          ssim_sum += interior ? (v < 0.f ? 0.f : (v > 1.f ? 1.f : v)) : 0.f;
         }
-        float* oc = sm + kOffCoef + (c * 3) * CN + ly * CW + lx;
-        *reinterpret_cast<float2*>(oc) = make_float2(cA[0], cA[1]);
-        *reinterpret_cast<float2*>(oc + CN) = make_float2(cB[0], cB[1]);
-        *reinterpret_cast<float2*>(oc + 2 * CN) = make_float2(cC[0], cC[1]);
+        float2 cA[2], cB[2], cC[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          // both windows are evaluated unconditionally (a window centred outside the image sees zero planes: finite values) and
+          // masked afterwards: no divergent region around 60 % of the phase's arithmetic
+          const bool in = (w == 0 ? in0 : in1);
+          const SsimTerms2 t = ssim_terms2(m[w], one);
+          const float2 v = mul2(sub2(splat2(1.0f), t.S), splat2(0.5f));
+          // g = 0 zeroes every coefficient of a masked window
+          const float2 g = make_float2((in && v.x >= 0.f && v.x <= 1.f) ? -0.5f : 0.f, (in && v.y >= 0.f && v.y <= 1.f) ? -0.5f : 0.f);
+          ssim_partials2(t, g, cA[w], cB[w], cC[w]);
+          const bool interior = in && (ly >= 1 && ly <= TH && lx + w >= 1 && lx + w <= TW);
+          ssim_sum.x += interior ? (v.x < 0.f ? 0.f : (v.x > 1.f ? 1.f : v.x)) : 0.f;
+          ssim_sum.y += interior ? (v.y < 0.f ? 0.f : (v.y > 1.f ? 1.f : v.y)) : 0.f;
+        }
+        float* oc = sm + kOffCoef + 2 * (ly * CW + lx);
+        *reinterpret_cast<float4*>(oc) = make_float4(cA[0].x, cA[0].y, cA[1].x, cA[1].y);
+        *reinterpret_cast<float4*>(oc + 2 * CN) = make_float4(cB[0].x, cB[0].y, cB[1].x, cB[1].y);
+        *reinterpret_cast<float4*>(oc + 4 * CN) = make_float4(cC[0].x, cC[0].y, cC[1].x, cC[1].y);
       } else {
         float wx[2] = {0.f, 0.f}, wy[2] = {0.f, 0.f};
 #pragma unroll
@@ -464,71 +466,104 @@ struct FlowGradTile {
         *reinterpret_cast<float2*>(sm + kOffEdge + ly * CW + lx) = make_float2(wx[0], wx[1]);
         *reinterpret_cast<float2*>(sm + kOffEdge + CN + ly * CW + lx) = make_float2(wy[0], wy[1]);
       }
-      }
     }
-    if (dir == 0) acc[FA_SSIM_F] += ssim_sum; else acc[FA_SSIM_B] += ssim_sum;
+    acc[FA_SSIM_F] += ssim_sum.x;
+    acc[FA_SSIM_B] += ssim_sum.y;
   }
 
-  // phase 3 (per direction): 1x2 strips over the interior: 3x3 box sums of the coefficients (vertical sums shared by
-  // the two outputs), chain through the warp Jacobian, store the L1 and SSIM basis of this direction
-  static UGL_HD void phase3(const FlowGradParams& gp, const TileCoord& tc, int dir, int tid, int nt, const float* sm) {
+  // phase 3 works on 1x2 strips of the interior; a thread owns strips tid, tid + nt, ... (kP3 of them) and keeps their SSIM
+  // gradient sums g[n] = {gsu(left), gsu(right), gsv(left), gsv(right)} (direction pairs) in registers across the channel passes
+  static constexpr int kP3 = ((TW / 2) * TH + NT - 1) / NT;
+
+  // phase 3, channel c: 3x3 box sums of this channel's coefficient pairs (vertical sums shared by the strip's two outputs),
+  // chained through the warp Jacobian of channel c into the running sums
+  static UGL_HD void phase3_accumulate(const FlowGradParams& gp, const TileCoord& tc, int c, int tid, int nt, const float* sm, float2 (*g)[4]) {
+    const FlowLevelDesc& L = gp.base.lv[tc.level];
+    constexpr int SW = TW / 2;
+    int n = 0;
+    for (int s = tid; s < SW * TH; s += nt, ++n) {
+      const int ty = s / SW, tx = (s - ty * SW) * 2;
+      if (tc.y0 + ty >= L.h || tc.x0 + tx >= L.w) continue;
+      const int c0 = (ty + R) * PW + (tx + R);       // photometry planes, left pixel (even)
+      const int q0 = (ty + 1) * CW + (tx + 1);       // coefficient planes, left pixel (odd)
+      const int t0 = ty * TW + tx;
+      float2 sum[3][2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {                 // A, B, C planes
+        const float* cf = sm + kOffCoef + k * 2 * CN + 2 * (q0 - 1);
+        float2 col[4];
+#pragma unroll
+        for (int r = -1; r <= 1; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(cf + 2 * r * CW);
+          const float4 b2 = *reinterpret_cast<const float4*>(cf + 2 * r * CW + 4);
+          if (r == -1) { col[0] = lo2(a); col[1] = hi2(a); col[2] = lo2(b2); col[3] = hi2(b2); }
+          else { col[0] = add2(col[0], lo2(a)); col[1] = add2(col[1], hi2(a)); col[2] = add2(col[2], lo2(b2)); col[3] = add2(col[3], hi2(b2)); }
+        }
+        const float2 mid = add2(col[1], col[2]);
+        sum[k][0] = add2(col[0], mid);
+        sum[k][1] = add2(mid, col[3]);
+      }
+      const float4 wq = *reinterpret_cast<const float4*>(sm + GP_W2 * PN + 2 * c0);
+      const float4 Xv = *reinterpret_cast<const float4*>(sm + (GP_X2 + 2 * c) * PN + 2 * c0);
+      const float4 Yv = *reinterpret_cast<const float4*>(sm + (GP_Y2 + 2 * c) * PN + 2 * c0);
+      const float4 du = *reinterpret_cast<const float4*>(sm + kOffDW + (2 * c) * 2 * TN + 2 * t0);
+      const float4 dv = *reinterpret_cast<const float4*>(sm + kOffDW + (2 * c + 1) * 2 * TN + 2 * t0);
+      const float2 wv[2] = {lo2(wq), hi2(wq)}, X2[2] = {lo2(Xv), hi2(Xv)}, Y2[2] = {lo2(Yv), hi2(Yv)};
+      const float2 du2[2] = {lo2(du), hi2(du)}, dv2[2] = {lo2(dv), hi2(dv)};
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        // A + 2 y B + x C cancels heavily where the warp matches the frame: fused multiply-adds keep the rounding noise down
+        const float2 gW = mul2(fma2(X2[o], sum[2][o], fma2(add2(Y2[o], Y2[o]), sum[1][o], sum[0][o])), wv[o]);
+        g[n][o] = fma2(gW, du2[o], g[n][o]);
+        g[n][2 + o] = fma2(gW, dv2[o], g[n][2 + o]);
+      }
+    }
+  }
+
+  // phase 3, closing: the L1 basis (sign sums x weight) and the accumulated SSIM basis of both directions -> global memory
+  static UGL_HD void phase3_store(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, const float* sm, const float2 (*g)[4]) {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     const int plane = L.h * L.w;
-    float* basis = gp.basis[tc.level] + ((long)tc.b * kPlanes + kDirStride * dir) * plane;
+    float* basis = gp.basis[tc.level] + (long)tc.b * kPlanes * plane;
     constexpr int SW = TW / 2;
-    for (int s = tid; s < SW * TH; s += nt) {
+    const bool vec = (L.w & 1) == 0;                  // even width: the strip's two pixels are one aligned 64-bit store
+    int n = 0;
+    for (int s = tid; s < SW * TH; s += nt, ++n) {
       const int ty = s / SW, tx = (s - ty * SW) * 2;
       const int i = tc.y0 + ty, j = tc.x0 + tx;
       if (i >= L.h || j >= L.w) continue;
-      const int c0 = (ty + R) * PW + (tx + R);       // photometry planes, left pixel
-      const int q0 = (ty + 1) * CW + (tx + 1);       // coefficient planes, left pixel
+      const int c0 = (ty + R) * PW + (tx + R);
       const int t0 = ty * TW + tx;
-      const float2 wq = *reinterpret_cast<const float2*>(sm + (GP_WF + dir) * PN + c0);
-      const float wv[2] = {wq.x, wq.y};
-      float gsu[2] = {0.f, 0.f}, gsv[2] = {0.f, 0.f};
-#pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
-        float sum[3][2];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {                 // A, B, C planes
-          const float* cf = sm + kOffCoef + (c * 3 + k) * CN + q0 - 1;
-          float col[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int r = -1; r <= 1; ++r) {
-            const float2 a = *reinterpret_cast<const float2*>(cf + r * CW);
-            const float2 b2 = *reinterpret_cast<const float2*>(cf + r * CW + 2);
-            col[0] += a.x; col[1] += a.y; col[2] += b2.x; col[3] += b2.y;
-          }
-          sum[k][0] = col[0] + col[1] + col[2];
-          sum[k][1] = col[1] + col[2] + col[3];
-        }
-        const float2 Xv = *reinterpret_cast<const float2*>(sm + (GP_X0 + 6 * dir + c) * PN + c0);
-        const float2 Yv = *reinterpret_cast<const float2*>(sm + (GP_Y0 + 6 * dir + c) * PN + c0);
-        const float2 du = *reinterpret_cast<const float2*>(sm + kOffDW + (6 * dir + 2 * c) * TN + t0);
-        const float2 dv = *reinterpret_cast<const float2*>(sm + kOffDW + (6 * dir + 2 * c + 1) * TN + t0);
-        const float X2[2] = {Xv.x, Xv.y}, Y2[2] = {Yv.x, Yv.y}, du2[2] = {du.x, du.y}, dv2[2] = {dv.x, dv.y};
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          const float gW = (sum[0][o] + 2.0f * Y2[o] * sum[1][o] + X2[o] * sum[2][o]) * wv[o];
-          gsu[o] += gW * du2[o];
-          gsv[o] += gW * dv2[o];
-        }
-      }
-      const float2 pu = *reinterpret_cast<const float2*>(sm + kOffDW + (12 + 2 * dir) * TN + t0);
-      const float2 pv = *reinterpret_cast<const float2*>(sm + kOffDW + (13 + 2 * dir) * TN + t0);
+      const float4 wq = *reinterpret_cast<const float4*>(sm + GP_W2 * PN + 2 * c0);
+      const float4 pu = *reinterpret_cast<const float4*>(sm + kOffDW + 12 * TN + 2 * t0);
+      const float4 pv = *reinterpret_cast<const float4*>(sm + kOffDW + 14 * TN + 2 * t0);
+      const float2 gpu[2] = {mul2(lo2(pu), lo2(wq)), mul2(hi2(pu), hi2(wq))}, gpv[2] = {mul2(lo2(pv), lo2(wq)), mul2(hi2(pv), hi2(wq))};
+      const float2 *gsu = g[n], *gsv = g[n] + 2;
       const int pix = i * L.w + j;
-      const bool two = (j + 1 < L.w);
-      basis[0 * plane + pix] = pu.x * wv[0]; basis[1 * plane + pix] = pv.x * wv[0];
-      basis[2 * plane + pix] = gsu[0];       basis[3 * plane + pix] = gsv[0];
-      if (two) {
-        basis[0 * plane + pix + 1] = pu.y * wv[1]; basis[1 * plane + pix + 1] = pv.y * wv[1];
-        basis[2 * plane + pix + 1] = gsu[1];       basis[3 * plane + pix + 1] = gsv[1];
+      float* b0 = basis + pix;                               // direction 0 planes 0..3, direction 1 planes kDirStride + 0..3
+      float* b1 = basis + (long)kDirStride * plane + pix;
+      if (vec) {                                             // j even, width even: j + 1 < w and pix is even
+        *reinterpret_cast<float2*>(b0) = make_float2(gpu[0].x, gpu[1].x);
+        *reinterpret_cast<float2*>(b0 + plane) = make_float2(gpv[0].x, gpv[1].x);
+        *reinterpret_cast<float2*>(b0 + 2 * (long)plane) = make_float2(gsu[0].x, gsu[1].x);
+        *reinterpret_cast<float2*>(b0 + 3 * (long)plane) = make_float2(gsv[0].x, gsv[1].x);
+        *reinterpret_cast<float2*>(b1) = make_float2(gpu[0].y, gpu[1].y);
+        *reinterpret_cast<float2*>(b1 + plane) = make_float2(gpv[0].y, gpv[1].y);
+        *reinterpret_cast<float2*>(b1 + 2 * (long)plane) = make_float2(gsu[0].y, gsu[1].y);
+        *reinterpret_cast<float2*>(b1 + 3 * (long)plane) = make_float2(gsv[0].y, gsv[1].y);
+      } else {
+        b0[0] = gpu[0].x; b0[plane] = gpv[0].x; b0[2 * (long)plane] = gsu[0].x; b0[3 * (long)plane] = gsv[0].x;
+        b1[0] = gpu[0].y; b1[plane] = gpv[0].y; b1[2 * (long)plane] = gsu[0].y; b1[3 * (long)plane] = gsv[0].y;
+        if (j + 1 < L.w) {
+          b0[1] = gpu[1].x; b0[plane + 1] = gpv[1].x; b0[2 * (long)plane + 1] = gsu[1].x; b0[3 * (long)plane + 1] = gsv[1].x;
+          b1[1] = gpu[1].y; b1[plane + 1] = gpv[1].y; b1[2 * (long)plane + 1] = gsu[1].y; b1[3 * (long)plane + 1] = gsv[1].y;
+        }
       }
     }
   }
 
   // phase 4a: every centre of the halo-1 region computes its signed, edge-weighted second differences ONCE
-  // (s = w * sign(d2 f) per flow component and axis, 8 planes written over the no longer needed coefficient planes);
+  // (s = w * sign(d2 f) per flow component and axis, 8 planes written over the no longer needed X / Y pair planes);
   // interior centres also add the smoothness loss value.  phase 4b then gathers 3 taps per axis instead of re-deriving
   // the second differences of its neighbours.
   static UGL_HD void phase4a(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, float* sm, float* acc) {
@@ -544,8 +579,8 @@ struct FlowGradTile {
         // the edge weight is 0 for centres whose neighbours fall outside the image, so the reads below stay inside the
         // halo-2 planes and contribute nothing there
         const float dxx = second_diff(f, 1), dyy = second_diff(f, PW);
-        sm[kOffCoef + (2 * f4) * CN + idx] = wx * sgnf(dxx);
-        sm[kOffCoef + (2 * f4 + 1) * CN + idx] = wy * sgnf(dyy);
+        sm[kOffS4 + (2 * f4) * CN + idx] = wx * sgnf(dxx);
+        sm[kOffS4 + (2 * f4 + 1) * CN + idx] = wy * sgnf(dyy);
         if (interior) {
           acc[f4 < 2 ? FA_SMX_F : FA_SMX_B] += wx * fabsf(dxx);
           acc[f4 < 2 ? FA_SMY_F : FA_SMY_B] += wy * fabsf(dyy);
@@ -567,8 +602,8 @@ struct FlowGradTile {
       float g[4];
 #pragma unroll
       for (int f4 = 0; f4 < 4; ++f4) {
-        const float* sx = sm + kOffCoef + (2 * f4) * CN + q0;
-        const float* sy = sm + kOffCoef + (2 * f4 + 1) * CN + q0;
+        const float* sx = sm + kOffS4 + (2 * f4) * CN + q0;
+        const float* sy = sm + kOffS4 + (2 * f4 + 1) * CN + q0;
         g[f4] = (sx[-1] - 2.0f * sx[0] + sx[1]) * inx + (sy[-CW] - 2.0f * sy[0] + sy[CW]) * iny;
       }
       const int pix = i * L.w + j;

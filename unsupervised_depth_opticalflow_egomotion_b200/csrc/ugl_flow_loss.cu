@@ -143,13 +143,20 @@ __global__ void __launch_bounds__(NT, UGL_BMINB) flow_loss_fwdgrad_kernel(const 
   if (kMode == kModeDepth) Tile::phase1_depth(gp, tc, threadIdx.x, NT, sm, acc, mats);
   else Tile::phase1(gp, tc, threadIdx.x, NT, sm, acc, mats);
   __syncthreads();
+  float2 g3[Tile::kP3][4];
+#pragma unroll
+  for (int n = 0; n < Tile::kP3; ++n)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g3[n][k] = make_float2(0.f, 0.f);
 #pragma unroll 1
-  for (int dir = 0; dir < 2; ++dir) {          // rolled: one copy of the stencil phases in the instruction cache
-    Tile::phase2(gp, tc, dir, threadIdx.x, NT, sm, acc);
+  for (int c = 0; c < 3; ++c) {      // channel by channel (rolled: one copy of the stencil phases in the instruction cache)
+    Tile::phase2(gp, tc, c, threadIdx.x, NT, sm, acc);
+    if (c == 0 && kMode != kModeDepth) Tile::phase2(gp, tc, 3, threadIdx.x, NT, sm, acc);   // smoothness edge weights
     __syncthreads();
-    Tile::phase3(gp, tc, dir, threadIdx.x, NT, sm);
-    __syncthreads();                 // the coefficient planes are reused by the second direction / by phase 4
+    Tile::phase3_accumulate(gp, tc, c, threadIdx.x, NT, sm, g3);
+    __syncthreads();                 // the coefficient planes are reused by the next channel; phase 4a overwrites the X / Y planes
   }
+  Tile::phase3_store(gp, tc, threadIdx.x, NT, sm, g3);
   if (kMode != kModeDepth) {         // flow smoothness (flow / geom modes)
     Tile::phase4a(gp, tc, threadIdx.x, NT, sm, acc);
     __syncthreads();

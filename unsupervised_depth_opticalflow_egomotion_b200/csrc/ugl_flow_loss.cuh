@@ -27,7 +27,7 @@ namespace ugl {
 #define UGL_BTW 32
 #endif
 #ifndef UGL_BTH
-#define UGL_BTH 12     /* swept on B200 (profiles/r1e_tile_sweep.txt): 32x12x256 is the fastest single-pass tile */
+#define UGL_BTH 13     /* swept on B200 (profiles/r1e_tile_sweep.txt, r1m): 32x13x256 is the fastest single-pass tile that keeps two CTAs inside the 196 KB carve-out */
 #endif
 #ifndef UGL_BMINB
 #define UGL_BMINB 2
