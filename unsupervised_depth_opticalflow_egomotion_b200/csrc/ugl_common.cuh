@@ -84,7 +84,9 @@ UGL_HD float sqrt_rn(float a) {
   return sqrtf(a);
 #endif
 }
-UGL_HD float sgnf(float v) { return (float)((v > 0.f) - (v < 0.f)); }
+// sign(v) in {-1, 0, +1}: two float-valued compares (FSET.BF) and a subtraction: 3 instructions instead of the 6 of the
+// integer form (float)((v > 0) - (v < 0))
+UGL_HD float sgnf(float v) { return (v > 0.f ? 1.0f : 0.0f) - (v < 0.f ? 1.0f : 0.0f); }
 
 // ---- packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2 = add/mul/fma.rn.f32x2) ---------------------------------------
 // One instruction produces two individually IEEE-rounded fp32 results from 64-bit register pairs.  The fp32 pipe still
@@ -147,13 +149,18 @@ UGL_HD float div_c(float a, float c, float rc) {
 }
 // approximate quotient / reciprocal (MUFU.RCP, ~1 ulp) for values that do not feed masks, floor() or
 // cancellation-prone differences
-UGL_HD float fast_div(float a, float b) {
+// One MUFU.RCP (+ one FMUL): __fdividef wraps the same reciprocal in a range fix-up for |b| > 2^126 that costs four more
+// instructions per use; no divisor on this path gets near that (they are sums of squares of image-scale numbers).
+UGL_HD float fast_rcp(float b) {
 #if defined(__CUDA_ARCH__)
-  return __fdividef(a, b);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return r;
 #else
-  return a / b;
+  return 1.0f / b;
 #endif
 }
+UGL_HD float fast_div(float a, float b) { return a * fast_rcp(b); }
 
 // Fixed-point scale exponent of the deterministic scatter (ugl_scatter.cuh): |sum| * 2^e < 2^61 for up
 // to n_contrib contributions of magnitude <= max_abs.
@@ -296,7 +303,7 @@ UGL_HD SsimTerms ssim_terms(const Moments& m) {
   // kExactDiv = false: the moments stay bit-identical to ATen's, only the last quotient uses the ~1-ulp
   // reciprocal (2 instructions instead of the ~15 of the IEEE division subroutine)
   const float dd = mul_rn(t.d1, t.d2);
-  t.rD = fast_div(1.0f, dd);
+  t.rD = fast_rcp(dd);
   t.S = kExactDiv ? div_rn(mul_rn(t.n1, t.n2), dd) : mul_rn(mul_rn(t.n1, t.n2), t.rD);
   return t;
 }
@@ -349,7 +356,7 @@ UGL_HD SsimTerms2 ssim_terms2(const Moments2& m, float2 one) {
   t.d1 = add2(acc2_rn(myy, mxx, one), splat2(kC1));     // mxx + myy: a sum of products (see acc2_rn)
   t.d2 = add2(add2(vx, vy), splat2(kC2));
   const float2 dd = mul2(t.d1, t.d2);
-  t.rD = make_float2(fast_div(1.0f, dd.x), fast_div(1.0f, dd.y));
+  t.rD = make_float2(fast_rcp(dd.x), fast_rcp(dd.y));
   t.S = mul2(mul2(t.n1, t.n2), t.rD);
   return t;
 }

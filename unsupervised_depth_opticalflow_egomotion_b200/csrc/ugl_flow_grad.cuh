@@ -593,7 +593,7 @@ struct FlowGradTile {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     const int plane = L.h * L.w;
     float* basis = gp.basis[tc.level] + (long)tc.b * kBasisPlanes * plane;
-    const float inx = 1.0f / (2.0f * (float)L.h * (float)(L.w - 2)), iny = 1.0f / (2.0f * (float)(L.h - 2) * (float)L.w);
+    const float inx = fast_rcp(2.0f * (float)L.h * (float)(L.w - 2)), iny = fast_rcp(2.0f * (float)(L.h - 2) * (float)L.w);   // scales of a gradient basis: 1e-4 contract
     for (int idx = tid; idx < TN; idx += nt) {
       const int ty = idx / TW, tx = idx - ty * TW;
       const int i = tc.y0 + ty, j = tc.x0 + tx;

@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(NT, UGL_BMINB) flow_loss_fwdgrad_kernel(const 
   constexpr bool kMats = (kMode != kModeFlow);
   __shared__ float red[(NT / 32) * FA_COUNT];
   __shared__ float mats[kMats ? 33 : 1];   // geom / depth modes: K^-1, P[0], P[1] of this tile's sample and level
-  const int tile = blockIdx.x;
-  const TileCoord tc = decode_tile<TW, TH>(gp.base, tile);
+  int tile;
+  const TileCoord tc = decode_tile_2d<TW, TH>(gp.base, blockIdx.x, blockIdx.y, tile);
   if (kMats) {
     if (threadIdx.x < 9) mats[threadIdx.x] = gp.Kinv[tc.level][tc.b * 9 + threadIdx.x];
     else if (threadIdx.x < 21) mats[threadIdx.x] = gp.P[0][tc.level][tc.b * 12 + threadIdx.x - 9];
@@ -341,7 +341,7 @@ extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) {
   static_assert(smem <= 227 * 1024, "single-pass tile does not fit in shared memory");
   auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, kModeFlow>;
   if ((rc = opt_in_smem(kern, smem))) return rc;
-  kern<<<gp.base.total_tiles, kBNT, smem, st>>>(gp);
+  kern<<<dim3(gp.base.total_tiles / gp.base.B, gp.base.B), kBNT, smem, st>>>(gp);
   if ((rc = check_launch("flow_loss_fwdgrad_kernel"))) return rc;
   return launch_finalize(gp.base, st);
 }
@@ -383,7 +383,7 @@ extern "C" int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* g) {
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
   auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, kModeGeom>;
   if ((rc = opt_in_smem(kern, smem))) return rc;
-  kern<<<gp.base.total_tiles, kBNT, smem, st>>>(gp);
+  kern<<<dim3(gp.base.total_tiles / gp.base.B, gp.base.B), kBNT, smem, st>>>(gp);
   if ((rc = check_launch("flow_loss_fwdgrad_kernel<geom>"))) return rc;
   return launch_finalize<kModeGeom>(gp.base, st);
 }
@@ -485,7 +485,7 @@ extern "C" int ugl_depth_ssim_forward_grad(const UglDepthSsimArgs* g) {
   auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, kModeDepth>;
   int rc;
   if ((rc = opt_in_smem(kern, smem))) return rc;
-  kern<<<p.total_tiles, kBNT, smem, st>>>(gp);
+  kern<<<dim3(p.total_tiles / p.B, p.B), kBNT, smem, st>>>(gp);
   if ((rc = check_launch("flow_loss_fwdgrad_kernel<depth>"))) return rc;
   return launch_finalize<kModeDepth>(p, st);
 }

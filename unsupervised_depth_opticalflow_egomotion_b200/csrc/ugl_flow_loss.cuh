@@ -95,6 +95,28 @@ UGL_HD TileCoord decode_tile(const FlowLossParams& p, int tile) {
   return tc;
 }
 
+// The single-pass kernel is launched on a (tiles per sample over all levels, B) grid: the sample is blockIdx.y, so the decode
+// needs one integer division (row / column of the tile) instead of three.  tile_id keeps the (level, b, ty, tx) order of the
+// partial-sum rows the finalize kernel reads.
+template <int TW, int TH>
+UGL_HD TileCoord decode_tile_2d(const FlowLossParams& p, int r, int b, int& tile_id) {
+  TileCoord tc;
+  int l = 0, per_img = p.lv[0].tiles_x * p.lv[0].tiles_y;
+  while (l + 1 < p.scales && r >= per_img) {     // r counts this sample's tiles over all levels
+    r -= per_img;
+    ++l;
+    per_img = p.lv[l].tiles_x * p.lv[l].tiles_y;
+  }
+  const FlowLevelDesc& L = p.lv[l];
+  tile_id = L.tile_begin + b * per_img + r;
+  const int ty = r / L.tiles_x;
+  tc.level = l;
+  tc.b = b;
+  tc.y0 = ty * TH;
+  tc.x0 = (r - ty * L.tiles_x) * TW;
+  return tc;
+}
+
 // ---- per-pixel photometry shared by forward and backward ----------------------------------------
 struct Photo {
   float I[3], Wf[3], Wb[3];   // centre image, warped-from-right (fwd flow), warped-from-left (bwd flow)
