@@ -130,8 +130,19 @@ UGL_HD float2 acc2_rn(float2 acc, float2 prod, float2 one) {
   return make_float2(add_rn(acc.x, prod.x), add_rn(acc.y, prod.y));
 #endif
 }
-// a - b with one rounding: fma(b, -1, a) (the product is exact)
+// a - b where b is the (separately rounded) result of a mul2: the opaque form of acc2_rn
+UGL_HD float2 sub2_rn(float2 a, float2 b, float2 one);
+// a - b with one rounding: fma(b, -1, a) (the product is exact).  NOT for a b that is itself a bare mul2 result (ptxas would
+// contract it): use sub2_rn there.
 UGL_HD float2 sub2(float2 a, float2 b) { return fma2(b, splat2(-1.0f), a); }
+UGL_HD float2 sub2_rn(float2 a, float2 b, float2 one) {
+#if defined(__CUDA_ARCH__)
+  return __ffma2_rn(b, make_float2(-one.x, -one.y), a);
+#else
+  (void)one;
+  return make_float2(sub_rn(a.x, b.x), sub_rn(a.y, b.y));
+#endif
+}
 UGL_HD float2 div_c2(float2 a, float c, float rc) {
   const float2 q = mul2(a, splat2(rc));
   return fma2(fma2(splat2(-c), q, a), splat2(rc), q);
@@ -255,12 +266,11 @@ UGL_HD Corners tap_fetch(const float* __restrict__ plane, int W, const Tap& t) {
   return c;
 }
 
+// ATen's CUDA sampler accumulates `out += value * weight` corner by corner (nw, ne, sw, se), which nvcc contracts into
+// RN(nw w_nw) -> fma(ne, w_ne, .) -> fma(sw, w_sw, .) -> fma(se, w_se, .).  Written out explicitly: left to the compiler, the
+// scalar expression was contracted as fma(nw, w_nw, RN(ne w_ne)) instead (seen in the SASS), one ulp off on some pixels.
 UGL_HD float corners_value(const Corners& c, const Tap& t) {
-  float o = c.nw * t.wnw;
-  o += c.ne * t.wne;
-  o += c.sw * t.wsw;
-  o += c.se * t.wse;
-  return o;
+  return fma_rn(c.se, t.wse, fma_rn(c.sw, t.wsw, fma_rn(c.ne, t.wne, mul_rn(c.nw, t.wnw))));
 }
 // d value / d ix and d value / d iy (ATen grid_sampler_2d_backward: out-of-range corners count as 0)
 UGL_HD float corners_ddx(const Corners& c, const Tap& t) { return (c.ne - c.nw) * (1.0f - t.ty) + (c.se - c.sw) * t.ty; }
@@ -348,18 +358,22 @@ UGL_HD SsimTerms2 ssim_terms2(const Moments2& m, float2 one) {
   t.mx = div_c2(m.sx, 9.0f, r9);
   t.my = div_c2(m.sy, 9.0f, r9);
   const float2 mxx = mul2(t.mx, t.mx), myy = mul2(t.my, t.my), mxy = mul2(t.mx, t.my);
-  const float2 vx = sub2(div_c2(m.sxx, 9.0f, r9), mxx);
-  const float2 vy = sub2(div_c2(m.syy, 9.0f, r9), myy);
-  const float2 cxy = sub2(div_c2(m.sxy, 9.0f, r9), mxy);
-  t.n1 = fma2(splat2(2.0f), mxy, splat2(kC1));
+  // differences and sums whose operand is a bare product go through the opaque 1.0 (see acc2_rn): E - mxx must not become
+  // fma(-mx, mx, E)
+  const float2 vx = sub2_rn(div_c2(m.sxx, 9.0f, r9), mxx, one);
+  const float2 vy = sub2_rn(div_c2(m.syy, 9.0f, r9), myy, one);
+  const float2 cxy = sub2_rn(div_c2(m.sxy, 9.0f, r9), mxy, one);
+  t.n1 = acc2_rn(splat2(kC1), mul2(splat2(2.0f), mxy), one);
   t.n2 = fma2(splat2(2.0f), cxy, splat2(kC2));
-  t.d1 = add2(acc2_rn(myy, mxx, one), splat2(kC1));     // mxx + myy: a sum of products (see acc2_rn)
+  t.d1 = add2(acc2_rn(myy, mxx, one), splat2(kC1));     // mxx + myy: a sum of products
   t.d2 = add2(add2(vx, vy), splat2(kC2));
   const float2 dd = mul2(t.d1, t.d2);
   t.rD = make_float2(fast_rcp(dd.x), fast_rcp(dd.y));
   t.S = mul2(mul2(t.n1, t.n2), t.rD);
   return t;
 }
+// loss value before the clamp, (1 - S) / 2, of both windows (S is a bare product: opaque subtraction)
+UGL_HD float2 ssim_half_one_minus2(float2 S, float2 one) { return mul2(sub2_rn(splat2(1.0f), S, one), splat2(0.5f)); }
 // g * dS/d(mu_y), g * dS/d(E[y^2]), g * dS/d(E[xy]) of both windows (ssim_partials' ay, by, cxy)
 UGL_HD void ssim_partials2(const SsimTerms2& t, float2 g, float2& cA, float2& cB, float2& cC) {
   const float2 invD = mul2(g, t.rD), invD2 = mul2(invD, splat2(2.0f));

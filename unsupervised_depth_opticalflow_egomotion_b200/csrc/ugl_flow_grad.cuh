@@ -80,6 +80,73 @@ UGL_HD TapC flow_tap_clamped(int j, int i, float u, float v, const WarpGeom& g) 
   return tap_clamped_norm<kGrad>(gx, gy, g);
 }
 
+// ---- the same gather set-up for BOTH warp directions of a pixel as packed fp32 pairs (.x = forward flow / right frame,
+// .y = backward flow / left frame): identical roundings (every packed op is the .rn form of the scalar one; where ptxas may
+// contract a product into a sum the product is by an exact 0 / 1 factor), half the fp32 instructions.  The clamps, floor,
+// float->int conversions and integer compares stay per lane.
+struct TapC2 {
+  int off[2];                    // ya * W + xa per direction
+  float2 w[4];                   // nw, ne, sw, se weights of the loaded block
+  float2 dx[4], dy[4];           // d w / d ix, d w / d iy
+  float2 keep;
+};
+
+UGL_HD float flag(bool b) { return b ? 1.0f : 0.0f; }
+
+template <bool kGrad>
+UGL_HD TapC2 tap_clamped_norm2(float2 gx, float2 gy, const WarpGeom& g) {
+  const float2 one = splat2(1.0f);
+  float2 ix = fma2(add2(gx, one), splat2(0.5f * (float)g.W), splat2(-0.5f));     // unnormalize(), both directions
+  float2 iy = fma2(add2(gy, one), splat2(0.5f * (float)g.H), splat2(-0.5f));
+  const float xhi = (float)g.W + 1.0f, yhi = (float)g.H + 1.0f;                  // beyond that every corner is out of range anyway
+  ix = make_float2(fminf(fmaxf(ix.x, -2.0f), xhi), fminf(fmaxf(ix.y, -2.0f), xhi));
+  iy = make_float2(fminf(fmaxf(iy.x, -2.0f), yhi), fminf(fmaxf(iy.y, -2.0f), yhi));
+  const float2 fx = make_float2(floorf(ix.x), floorf(ix.y)), fy = make_float2(floorf(iy.x), floorf(iy.y));
+  const int x0[2] = {(int)fx.x, (int)fx.y}, y0[2] = {(int)fy.x, (int)fy.y};
+  const float2 tx = sub2(ix, fx), ty = sub2(iy, fy);
+  const float2 ox = sub2(add2(fx, one), ix), oy = sub2(add2(fy, one), iy);
+  TapC2 t;
+  float l0[2], r0[2], l1[2], r1[2], t0[2], b0[2], t1[2], b1[2], mnw[2], mne[2], msw[2], mse[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const int xa = imin(imax(x0[d], 0), g.W - 2), ya = imin(imax(y0[d], 0), g.H - 2);
+    t.off[d] = ya * g.W + xa;
+    // column xa holds x0 (weight ox) or x0+1 (weight tx) or neither; column xa+1 likewise
+    l0[d] = flag(x0[d] == xa); r0[d] = flag(x0[d] + 1 == xa); l1[d] = flag(x0[d] == xa + 1); r1[d] = l0[d];
+    t0[d] = flag(y0[d] == ya); b0[d] = flag(y0[d] + 1 == ya); t1[d] = flag(y0[d] == ya + 1); b1[d] = t0[d];
+    const bool xl = x0[d] >= 0 && x0[d] < g.W, xr = x0[d] + 1 >= 0 && x0[d] + 1 < g.W;
+    const bool yt = y0[d] >= 0 && y0[d] < g.H, yb = y0[d] + 1 >= 0 && y0[d] + 1 < g.H;
+    mnw[d] = flag(xl && yt); mne[d] = flag(xr && yt); msw[d] = flag(xl && yb); mse[d] = flag(xr && yb);
+  }
+  const float2 L0 = make_float2(l0[0], l0[1]), R0 = make_float2(r0[0], r0[1]), L1 = make_float2(l1[0], l1[1]), R1 = make_float2(r1[0], r1[1]);
+  const float2 T0 = make_float2(t0[0], t0[1]), B0 = make_float2(b0[0], b0[1]), T1 = make_float2(t1[0], t1[1]), B1 = make_float2(b1[0], b1[1]);
+  // per-corner weights as ATen forms them: (x-part) * (y-part); exactly one of the two terms of a part is non-zero
+  const float2 cx0 = fma2(ox, L0, mul2(tx, R0)), cx1 = fma2(ox, L1, mul2(tx, R1));
+  const float2 ry0 = fma2(oy, T0, mul2(ty, B0)), ry1 = fma2(oy, T1, mul2(ty, B1));
+  t.w[0] = mul2(cx0, ry0); t.w[1] = mul2(cx1, ry0); t.w[2] = mul2(cx0, ry1); t.w[3] = mul2(cx1, ry1);
+  // coverage = sum of the in-bounds weights in ATen's corner order (nw, ne, sw, se of the ORIGINAL footprint)
+  const float2 wnw = mul2(mul2(ox, oy), make_float2(mnw[0], mnw[1])), wne = mul2(mul2(tx, oy), make_float2(mne[0], mne[1]));
+  const float2 wsw = mul2(mul2(ox, ty), make_float2(msw[0], msw[1])), wse = mul2(mul2(tx, ty), make_float2(mse[0], mse[1]));
+  const float2 cov = add2(add2(add2(wnw, wne), wsw), wse);
+  t.keep = make_float2(flag(cov.x >= 0.9999f), flag(cov.y >= 0.9999f));
+  if (kGrad) {
+    const float2 dcx0 = sub2(R0, L0), dcx1 = sub2(R1, L1);          // d cx / d ix  (d ox = -1, d tx = +1)
+    const float2 dry0 = sub2(B0, T0), dry1 = sub2(B1, T1);
+    t.dx[0] = mul2(dcx0, ry0); t.dx[1] = mul2(dcx1, ry0); t.dx[2] = mul2(dcx0, ry1); t.dx[3] = mul2(dcx1, ry1);
+    t.dy[0] = mul2(cx0, dry0); t.dy[1] = mul2(cx1, dry0); t.dy[2] = mul2(cx0, dry1); t.dy[3] = mul2(cx1, dry1);
+  }
+  return t;
+}
+
+// both flow warps of pixel (j, i): u = (u_fwd, u_bwd), v likewise
+template <bool kGrad>
+UGL_HD TapC2 flow_tap_clamped2(int j, int i, float2 u, float2 v, const WarpGeom& g) {
+  const float2 two = splat2(2.0f), one = splat2(1.0f);
+  const float2 gx = sub2(div_c2(mul2(two, add2(splat2((float)j), u)), g.dw, g.rdw), one);
+  const float2 gy = sub2(div_c2(mul2(two, add2(splat2((float)i), v)), g.dh, g.rdh), one);
+  return tap_clamped_norm2<kGrad>(gx, gy, g);
+}
+
 struct DirectLoads { float uf, vf, ub, vb, I[3]; bool inside; };
 
 // the coalesced (non-gather) loads of one halo pixel: issued one pixel ahead of use to overlap their latency
@@ -108,25 +175,25 @@ UGL_HD void flow_photo_pixel_c(const FlowLevelDesc& L, int b, int i, int j, cons
   const int plane = L.h * L.w, W = L.w;
   const float* ir = L.img_r + (long)b * 3 * plane;
   const float* il = L.img_l + (long)b * 3 * plane;
-  const TapC tf = flow_tap_clamped<kGrad>(j, i, d.uf, d.vf, L.geom);
-  const TapC tb = flow_tap_clamped<kGrad>(j, i, d.ub, d.vb, L.geom);
-  const float* pr = ir + tf.off;
-  const float* pl = il + tb.off;
+  const TapC2 t = flow_tap_clamped2<kGrad>(j, i, make_float2(d.uf, d.ub), make_float2(d.vf, d.vb), L.geom);
+  const float* pr = ir + t.off[0];
+  const float* pl = il + t.off[1];
+  const float2 ksx = mul2(t.keep, splat2(L.geom.sx)), ksy = mul2(t.keep, splat2(L.geom.sy));
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     P.I[c] = d.I[c];
-    const float f0 = pr[0], f1 = pr[1], f2 = pr[W], f3 = pr[W + 1];
-    const float b0 = pl[0], b1 = pl[1], b2 = pl[W], b3 = pl[W + 1];
+    // the four taps of both directions as pairs; the fused multiply-add chain is the one nvcc contracts the scalar form
+    // (and ATen's CUDA sampler) into: v = nw * w_nw; v = fma(ne, w_ne, v); ...
+    const float2 q0 = make_float2(pr[0], pl[0]), q1 = make_float2(pr[1], pl[1]), q2 = make_float2(pr[W], pl[W]), q3 = make_float2(pr[W + 1], pl[W + 1]);
     pr += plane; pl += plane;
-    float vfw = f0 * tf.w[0]; vfw += f1 * tf.w[1]; vfw += f2 * tf.w[2]; vfw += f3 * tf.w[3];
-    float vbw = b0 * tb.w[0]; vbw += b1 * tb.w[1]; vbw += b2 * tb.w[2]; vbw += b3 * tb.w[3];
-    P.Wf[c] = vfw * tf.keep;
-    P.Wb[c] = vbw * tb.keep;
+    const float2 v = mul2(fma2(q3, t.w[3], fma2(q2, t.w[2], fma2(q1, t.w[1], mul2(q0, t.w[0])))), t.keep);
+    P.Wf[c] = v.x;
+    P.Wb[c] = v.y;
     if (kGrad) {
-      dW[2 * c + 0] = tf.keep * L.geom.sx * (f0 * tf.dx[0] + f1 * tf.dx[1] + f2 * tf.dx[2] + f3 * tf.dx[3]);
-      dW[2 * c + 1] = tf.keep * L.geom.sy * (f0 * tf.dy[0] + f1 * tf.dy[1] + f2 * tf.dy[2] + f3 * tf.dy[3]);
-      dW[6 + 2 * c + 0] = tb.keep * L.geom.sx * (b0 * tb.dx[0] + b1 * tb.dx[1] + b2 * tb.dx[2] + b3 * tb.dx[3]);
-      dW[6 + 2 * c + 1] = tb.keep * L.geom.sy * (b0 * tb.dy[0] + b1 * tb.dy[1] + b2 * tb.dy[2] + b3 * tb.dy[3]);
+      const float2 gu = mul2(ksx, fma2(q3, t.dx[3], fma2(q2, t.dx[2], fma2(q1, t.dx[1], mul2(q0, t.dx[0])))));
+      const float2 gv = mul2(ksy, fma2(q3, t.dy[3], fma2(q2, t.dy[2], fma2(q1, t.dy[1], mul2(q0, t.dy[0])))));
+      dW[2 * c + 0] = gu.x; dW[6 + 2 * c + 0] = gu.y;
+      dW[2 * c + 1] = gv.x; dW[6 + 2 * c + 1] = gv.y;
     }
   }
   const float valid_f = (P.Wf[0] == 0.f && P.Wf[1] == 0.f && P.Wf[2] == 0.f) ? 0.f : 1.f;
@@ -434,7 +501,7 @@ struct FlowGradTile {
           // masked afterwards: no divergent region around 60 % of the phase's arithmetic
           const bool in = (w == 0 ? in0 : in1);
           const SsimTerms2 t = ssim_terms2(m[w], one);
-          const float2 v = mul2(sub2(splat2(1.0f), t.S), splat2(0.5f));
+          const float2 v = ssim_half_one_minus2(t.S, one);
           // g = 0 zeroes every coefficient of a masked window
           const float2 g = make_float2((in && v.x >= 0.f && v.x <= 1.f) ? -0.5f : 0.f, (in && v.y >= 0.f && v.y <= 1.f) ? -0.5f : 0.f);
           ssim_partials2(t, g, cA[w], cB[w], cC[w]);
