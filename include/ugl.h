@@ -168,6 +168,13 @@ uint64_t ugl_forward_splat_workspace_bytes(int32_t batch, int32_t channels, int3
 int ugl_forward_splat(const float* x, const float* flow, int32_t batch, int32_t channels, int32_t height, int32_t width,
                       int32_t clamp01, float* out, void* workspace, uint64_t workspace_bytes, void* stream);
 
+/* Device self-test of the packed fp32 pair arithmetic (FADD2 / FMUL2 / FFMA2) the single-pass kernels run their SSIM stencil on:
+ * `windows_per_thread` random 3x3 windows per thread (blocks x 128 threads, two windows per pair) are evaluated with the packed
+ * pair functions and with the scalar functions of the per-method / recompute kernels; mismatch[2][14] (device, uint64) counts,
+ * per pair lane, the windows whose sx, sy, sxx, syy, sxy, mu_x, n1, n2, d1, d2, S, cA, cB, cC differ in ANY bit.  All zeros is
+ * the contract (ptxas contracts packed .rn products into sums unless prevented, see ugl_common.cuh: acc2_rn). */
+int ugl_selftest_packed_pairs(uint64_t* mismatch, int32_t blocks, int32_t windows_per_thread, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Generic per-sample reductions: workspace for every *_forward / *_backward below that takes one
  * (>= ugl_reduce_workspace_bytes(B,H,W) bytes, 8-byte aligned).

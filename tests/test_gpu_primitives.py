@@ -123,3 +123,12 @@ def test_cost_volume_vs_oracle(cuda_device, B, C, H, W, d):
     f3 = f2c.detach().to(cuda_device)
     g1b, = torch.autograd.grad((ops.cost_volume(f1, f3, d) * go.to(cuda_device)).sum(), [f1])
     assert torch.equal(g1b, g1)
+
+
+def test_packed_pair_ssim_is_bit_identical_to_scalar(cuda_device):
+    """The FADD2 / FMUL2 / FFMA2 forms of the SSIM moments, terms and backward coefficients (both warp directions per
+    instruction) must reproduce the scalar forms bit for bit: ptxas contracts packed `.rn` products into sums unless the
+    code prevents it (ugl_common.cuh: acc2_rn / sub2_rn), which this test would catch as sxx / syy / sxy / d2 / S mismatches."""
+    bad = ops.selftest_packed_pairs(cuda_device, blocks=64, windows_per_thread=500)
+    assert bad.shape == (2, 14)
+    assert int(bad.sum()) == 0, bad.cpu().tolist()

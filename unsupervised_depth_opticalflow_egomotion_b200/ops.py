@@ -1131,6 +1131,15 @@ def forward_splat(x: Tensor, flow: Tensor, clamp01: bool = False) -> Tensor:
     return out
 
 
+def selftest_packed_pairs(device, blocks: int = 64, windows_per_thread: int = 500) -> Tensor:
+    """Device self-test of the packed fp32 pair arithmetic of the single-pass kernels (``ugl_selftest_packed_pairs``):
+    returns a (2, 14) int64 tensor of bit-mismatch counts against the scalar SSIM functions; all zeros is the contract."""
+    out = torch.zeros(2, 14, dtype=torch.int64, device=device)
+    with torch.cuda.device(out.device):
+        _call("ugl_selftest_packed_pairs", out.data_ptr(), int(blocks), int(windows_per_thread), _stream_ptr(), launches=1)
+    return out
+
+
 # ================================================================================================
 # fused reprojection-photometric term (depth / geom modes)
 # ================================================================================================
