@@ -27,3 +27,5 @@ ops.forward_splat(torch.ones(2, 1, 40, 72, device=dev), t.flows_fwd[0].detach(),
 x = torch.rand(1, 8, 20, 30, device=dev, requires_grad=True); fl = (3 * torch.randn(1, 2, 20, 30, device=dev)).requires_grad_(True)
 ops.warp_flow(x, fl, True).sum().backward()
 torch.cuda.synchronize(); print("sanitizer workload done")
+assert int(ops.selftest_packed_pairs(dev, blocks=2, windows_per_thread=4).sum()) == 0
+torch.cuda.synchronize(); print("sanitizer workload done (incl. packed-pair self-test)")
