@@ -520,11 +520,23 @@ def main():
     e2e_total = e2e_run(n_e2e)
     e2e_ms = [e2e_total / n_e2e] * n_e2e
 
+    # extra (not the contract value): the same step with the three frames shipped as uint8 and `img / 255.0` of the reference's
+    # dataset (kitti_prepared.py:89) done on the device -- the frames are bytes at the source; 4x less PCIe traffic for them
+    h_imgs_f32, stepper_f32 = h_imgs, stepper
+    h_imgs = [pin((x * 255.0).round().clamp(0, 255).to(torch.uint8)) for x in (host.img_l, host.img, host.img_r)]
+    stepper = FlowLossStep(B, H, W, LEVELS, device=dev, frame_dtype=torch.uint8)
+    e2e_run(3)
+    if world > 1:
+        dist.barrier()
+    u8_total = e2e_run(n_e2e)
+    u8_h2d = stepper.h2d_bytes
+    h_imgs, stepper = h_imgs_f32, stepper_f32
+
     # ---- max over ranks ------------------------------------------------------------------------------------
-    red = torch.tensor([total_ms, e2e_total / len(e2e_ms)], device=dev, dtype=torch.float64)
+    red = torch.tensor([total_ms, e2e_total / len(e2e_ms), u8_total / n_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms_per_step = float(red[0]), float(red[1])
+    total_ms, e2e_ms_per_step, u8_ms_per_step = float(red[0]), float(red[1]), float(red[2])
     ms_per_step = total_ms / K
     value = 2.0 * B * world / (ms_per_step * 1e-3)
     e2e_value = 2.0 * B * world / (e2e_ms_per_step * 1e-3)
@@ -557,7 +569,11 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step,
                     "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": stepper.d2h_bytes,
                     "how": "step.FlowLossStep: pinned host frames+flows -> H2D -> pyramids -> fused fwd+bwd -> D2H losses; "
-                           "2 staging slots, copy of step k+1 overlaps compute of step k; one event pair around %d steps" % n_e2e},
+                           "2 staging slots, copy of step k+1 overlaps compute of step k; one event pair around %d steps" % n_e2e,
+                    "uint8_frames": {"value": 2.0 * B * world / (u8_ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": u8_ms_per_step,
+                                     "h2d_bytes_per_step": u8_h2d,
+                                     "how": "extra, not the contract value: FlowLossStep(frame_dtype=uint8) -- frames shipped as bytes, "
+                                            "the dataset's img/255.0 evaluated on the device (bit-identical), flows fp32"}},
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "kernel": "flow_loss_%s_kernel" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full, bytes per launch)",

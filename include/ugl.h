@@ -168,6 +168,12 @@ uint64_t ugl_forward_splat_workspace_bytes(int32_t batch, int32_t channels, int3
 int ugl_forward_splat(const float* x, const float* flow, int32_t batch, int32_t channels, int32_t height, int32_t width,
                       int32_t clamp01, float* out, void* workspace, uint64_t workspace_bytes, void* stream);
 
+/* Dataset glue: uint8 frames -> fp32 frames in [0,1], the arithmetic of core/dataset/kitti_prepared.py:89
+ * (`img / 255.0` in float64, then `.float()`): for every byte value the result equals the correctly rounded fp32 quotient this
+ * computes.  Lets a trainer ship the frames over PCIe as bytes (a quarter of the traffic).  `frames` (1..4) device pointers of
+ * `elements` bytes / floats each, 16-byte aligned. */
+int ugl_frames_u8_to_float(const void* const* src, void* const* dst, int32_t frames, uint64_t elements, void* stream);
+
 /* Device self-test of the packed fp32 pair arithmetic (FADD2 / FMUL2 / FFMA2) the single-pass kernels run their SSIM stencil on:
  * `windows_per_thread` random 3x3 windows per thread (blocks x 128 threads, two windows per pair) are evaluated with the packed
  * pair functions and with the scalar functions of the per-method / recompute kernels; mismatch[2][14] (device, uint64) counts,

@@ -132,3 +132,34 @@ def test_packed_pair_ssim_is_bit_identical_to_scalar(cuda_device):
     bad = ops.selftest_packed_pairs(cuda_device, blocks=64, windows_per_thread=500)
     assert bad.shape == (2, 14)
     assert int(bad.sum()) == 0, bad.cpu().tolist()
+
+
+def test_frames_from_u8_matches_the_dataset_division(cuda_device):
+    """core/dataset/kitti_prepared.py:89: `img / 255.0` (numpy float64) then `.float()` — all 256 byte values, plus a ragged size."""
+    import numpy as np
+    k = np.arange(256, dtype=np.uint8)
+    ref = torch.from_numpy((k / 255.0).astype(np.float32))
+    x = torch.from_numpy(np.tile(k, 37)[: 256 * 37 - 5].copy()).to(cuda_device)          # not a multiple of 16
+    y = torch.from_numpy(np.roll(np.tile(k, 37), 3)[: 256 * 37 - 5].copy()).to(cuda_device)
+    ox, oy = ops.frames_from_u8([x, y])
+    assert torch.equal(ox.cpu(), ref[x.cpu().long()]) and torch.equal(oy.cpu(), ref[y.cpu().long()])
+    with pytest.raises(TypeError):
+        ops.frames_from_u8([x.float()])
+
+
+def test_flow_loss_step_uint8_frames_equal_float_frames(cuda_device):
+    from unsupervised_depth_opticalflow_egomotion_b200.step import FlowLossStep
+    from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
+    t = make_triplet(2, 64, 96, 3, 1, seed=11)
+    u8 = [(x * 255.0).round().clamp(0, 255).to(torch.uint8).pin_memory() for x in (t.img_l, t.img, t.img_r)]
+    f32 = [(x.double() / 255.0).float().pin_memory() for x in u8]
+    ff, fb = [f.detach().pin_memory() for f in t.flows_fwd], [f.detach().pin_memory() for f in t.flows_bwd]
+    a = FlowLossStep(2, 64, 96, 3, device=cuda_device, frame_dtype=torch.uint8)
+    b = FlowLossStep(2, 64, 96, 3, device=cuda_device)
+    la = a(u8[0], u8[1], u8[2], ff, fb).clone()
+    lb = b(f32[0], f32[1], f32[2], ff, fb).clone()
+    assert torch.equal(la, lb)
+    assert all(torch.equal(x, y) for x, y in zip(a.grads, b.grads))
+    assert a.h2d_bytes < b.h2d_bytes
+    with pytest.raises(TypeError):
+        a(f32[0], f32[1], f32[2], ff, fb)

@@ -157,6 +157,7 @@ SIGNATURES.update({
     "ugl_forward_splat_workspace_bytes": (_u64, [_i, _i, _i, _i]),
     "ugl_forward_splat": (C.c_int, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _u64, _p]),
     "ugl_selftest_packed_pairs": (C.c_int, [_p, _i, _i, _p]),
+    "ugl_frames_u8_to_float": (C.c_int, [_pp, _pp, _i, _u64, _p]),
     "ugl_depth_photo_workspace_bytes": (_u64, [C.POINTER(UglDepthPhotoArgs)]),
     "ugl_depth_photo_forward": (C.c_int, [C.POINTER(UglDepthPhotoArgs)]),
     "ugl_depth_photo_backward": (C.c_int, [C.POINTER(UglDepthPhotoArgs)]),

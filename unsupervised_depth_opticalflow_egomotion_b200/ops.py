@@ -1131,6 +1131,23 @@ def forward_splat(x: Tensor, flow: Tensor, clamp01: bool = False) -> Tensor:
     return out
 
 
+def frames_from_u8(frames: Sequence[Tensor], out: Optional[Sequence[Tensor]] = None) -> List[Tensor]:
+    """uint8 frames (same shape, up to four) -> fp32 frames in [0,1] in ONE launch: the reference dataset's ``img / 255.0``
+    (core/dataset/kitti_prepared.py:89) evaluated on the device, bit-identical to it for every byte value."""
+    frames = [_dev_u8(f, "frame") for f in frames]
+    if not frames or len(frames) > 4:
+        raise ValueError("frames_from_u8 takes 1..4 frames")
+    for f in frames:
+        if f.shape != frames[0].shape:
+            raise ValueError("frames_from_u8: frames must have one shape")
+    outs = list(out) if out is not None else [torch.empty(f.shape, dtype=torch.float32, device=f.device) for f in frames]
+    src = (C.c_void_p * len(frames))(*[f.data_ptr() for f in frames])
+    dst = (C.c_void_p * len(frames))(*[o.data_ptr() for o in outs])
+    with torch.cuda.device_of(frames[0]):
+        _call("ugl_frames_u8_to_float", src, dst, len(frames), frames[0].numel(), _stream_ptr(), launches=1)
+    return outs
+
+
 def selftest_packed_pairs(device, blocks: int = 64, windows_per_thread: int = 500) -> Tensor:
     """Device self-test of the packed fp32 pair arithmetic of the single-pass kernels (``ugl_selftest_packed_pairs``):
     returns a (2, 14) int64 tensor of bit-mismatch counts against the scalar SSIM functions; all zeros is the contract."""

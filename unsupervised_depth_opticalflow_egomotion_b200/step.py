@@ -27,9 +27,12 @@ def weight_matrix(weights: Dict[str, float], keys: Sequence[str], batch: int, de
 class _Slot:
     """One set of device staging buffers + the events that order its reuse."""
 
-    def __init__(self, batch, height, width, levels, device):
+    def __init__(self, batch, height, width, levels, device, frame_dtype=torch.float32):
         f32 = torch.float32
         self.imgs = [torch.empty((batch, 3, height, width), device=device, dtype=f32) for _ in range(3)]
+        # uint8 frames: staged as bytes, converted on the device (ops.frames_from_u8) into self.imgs
+        self.imgs_u8 = ([torch.empty((batch, 3, height, width), device=device, dtype=torch.uint8) for _ in range(3)]
+                        if frame_dtype == torch.uint8 else None)
         self.ff = [torch.empty((batch, 2, height >> l, width >> l), device=device, dtype=f32) for l in range(levels)]
         self.fb = [torch.empty((batch, 2, height >> l, width >> l), device=device, dtype=f32) for l in range(levels)]
         self.h_loss = torch.empty((4, batch), dtype=f32).pin_memory()
@@ -44,21 +47,29 @@ class FlowLossStep:
 
     Two staging slots and a copy stream: ``submit`` enqueues the H2D copy of a step on the copy stream and its
     pyramids + fused forward/backward + D2H of the losses on the compute stream, so the copy of step k+1 overlaps
-    the kernels of step k.  ``result(slot)`` waits for that step only.  ``__call__`` = submit + result."""
+    the kernels of step k.  ``result(slot)`` waits for that step only.  ``__call__`` = submit + result.
+
+    ``frame_dtype=torch.uint8``: the three frames arrive as bytes (what the image decoder produces) and the dataset's
+    ``img / 255.0`` (core/dataset/kitti_prepared.py:89) runs on the device, bit-identical to the host division: the frames then
+    cost a quarter of the PCIe traffic (the step from host buffers is PCIe-bound)."""
 
     def __init__(self, batch: int, height: int, width: int, levels: int = 4, num_scales: Optional[int] = None,
-                 weights: Optional[Dict[str, float]] = None, device="cuda:0"):
+                 weights: Optional[Dict[str, float]] = None, device="cuda:0", frame_dtype=torch.float32):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("FlowLossStep needs a CUDA device: the loss path has no CPU implementation")
         self.B, self.H, self.W, self.L = batch, height, width, levels
         self.scales = levels if num_scales is None else num_scales
         with torch.cuda.device(self.device):
-            self.slots = [_Slot(batch, height, width, levels, self.device) for _ in range(2)]
+            if frame_dtype not in (torch.float32, torch.uint8):
+                raise TypeError("frame_dtype must be torch.float32 or torch.uint8")
+            self.frame_dtype = frame_dtype
+            self.slots = [_Slot(batch, height, width, levels, self.device, frame_dtype) for _ in range(2)]
             self.copy_stream = torch.cuda.Stream()
         self.wmat = weight_matrix(weights or FLOW_WEIGHTS, ops.FLOW_LOSS_KEYS, batch, self.device)
         s0 = self.slots[0]
-        self.h2d_bytes = sum(t.numel() * 4 for t in s0.imgs + s0.ff + s0.fb)
+        frames = s0.imgs_u8 if s0.imgs_u8 is not None else s0.imgs
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in frames + s0.ff + s0.fb)
         self.d2h_bytes = s0.h_loss.numel() * 4
         self._next = 0
 
@@ -72,12 +83,16 @@ class FlowLossStep:
         if sl.busy:
             self.copy_stream.wait_event(sl.compute_done)          # the slot's previous step must have consumed its buffers
         with torch.cuda.stream(self.copy_stream):
-            for dst, src in zip(sl.imgs, (h_img_l, h_img, h_img_r)):
+            for dst, src in zip(sl.imgs_u8 if sl.imgs_u8 is not None else sl.imgs, (h_img_l, h_img, h_img_r)):
+                if src.dtype != dst.dtype:
+                    raise TypeError("FlowLossStep(frame_dtype=%s) got %s frames" % (dst.dtype, src.dtype))
                 dst.copy_(src, non_blocking=True)
             for dst, src in zip(sl.ff + sl.fb, list(h_flows_fwd) + list(h_flows_bwd)):
                 dst.copy_(src, non_blocking=True)
             sl.h2d_done.record(self.copy_stream)
         main.wait_event(sl.h2d_done)
+        if sl.imgs_u8 is not None:
+            ops.frames_from_u8(sl.imgs_u8, out=sl.imgs)            # one launch for the three frames
         pl, pc, pr = (d["box"] for d in ops.image_pyramids(sl.imgs, self.L, ("box", "box", "box")))     # one launch
         ff = [f.detach().requires_grad_(True) for f in sl.ff]       # fresh leaves over the staging buffers
         fb = [f.detach().requires_grad_(True) for f in sl.fb]
