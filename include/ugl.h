@@ -341,6 +341,20 @@ uint64_t ugl_depth_photo_workspace_bytes(const UglDepthPhotoArgs* args);
 int ugl_depth_photo_forward(const UglDepthPhotoArgs* args);
 int ugl_depth_photo_backward(const UglDepthPhotoArgs* args);
 
+/* Single-pass variant of the above (what the autograd wrapper uses when a gradient is needed): forward_grad also writes the
+ * UN-normalised d loss / d disparity through each direction, basis[l] (B,2,h,w), and the un-normalised d loss / d P sums,
+ * psum (B,scales,2,12), while the taps are in registers; combine (element-wise) applies grad_loss (B,) and the normalisers:
+ * grad_disp[l] (B,1,h,w), grad_P[dir][l] (B,3,4).  One gather kernel per step instead of two.  Workspace: >= ..._grad_workspace_bytes. */
+typedef struct UglDepthPhotoGradArgs {
+  UglDepthPhotoArgs photo;
+  float* basis[UGL_MAX_LEVELS];
+  float* psum;
+} UglDepthPhotoGradArgs;
+
+uint64_t ugl_depth_photo_grad_workspace_bytes(const UglDepthPhotoGradArgs* args);
+int ugl_depth_photo_forward_grad(const UglDepthPhotoGradArgs* args);
+int ugl_depth_photo_combine(const UglDepthPhotoGradArgs* args);
+
 /* Depth-consistency term of the depth mode for both source frames and all levels: compute_consis_loss (unmasked,
  * model_depth.py:154-163; enabled at model_depth_texture.py:308-309) on the projected / computed depths of inverse_warp2
  * (structures/inverse_warp.py:263-303): loss (B,) = sum_{frames, levels} mean(clamp(|comp - proj| / |comp + proj|, 0, 1)).

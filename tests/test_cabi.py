@@ -57,6 +57,7 @@ def test_struct_layouts_match_the_c_compiler(tmp_path):
     structs = {"UglFlowLossArgs": _cabi.UglFlowLossArgs, "UglDepthPhotoArgs": _cabi.UglDepthPhotoArgs, "UglGeomFlowArgs": _cabi.UglGeomFlowArgs,
                "UglDispSmoothArgs": _cabi.UglDispSmoothArgs, "UglGeomRigidArgs": _cabi.UglGeomRigidArgs,
                "UglPyramidArgs": _cabi.UglPyramidArgs, "UglDepthSsimArgs": _cabi.UglDepthSsimArgs,
+               "UglDepthPhotoGradArgs": _cabi.UglDepthPhotoGradArgs,
                "UglDepthConsisArgs": _cabi.UglDepthConsisArgs}
     lines = []
     for name, cls in structs.items():

@@ -347,6 +347,35 @@ def test_fused_depth_branch_equals_composed(cuda_device):
         assert rel_err(a, b) < (2e-5 if i < 4 else GRAD_RTOL), i      # flow gradients: SSIM sums in a different order
 
 
+def test_depth_photo_single_pass_equals_recompute(cuda_device):
+    """reprojection-photometric term: forward_grad + element-wise combine against forward + recompute backward (depth and geom modes,
+    odd sizes so the scalar combine path runs too)"""
+    for (Hh, Ww) in ((64, 208), (40, 72)):
+        t = make_triplet(2, Hh, Ww, 4, 3, seed=63, flow_mode="rigid", oob_fraction=0.1).to(cuda_device)
+        res = {}
+        for single in (True, False):
+            ops.DEPTH_PHOTO_SINGLE_PASS = single
+            try:
+                disp, disp_l, disp_r = _leaf_list(t.disp, cuda_device), _leaf_list(t.disp_l, cuda_device), _leaf_list(t.disp_r, cuda_device)
+                pose = t.pose.detach().clone().requires_grad_(True)
+                loss, masks = losses.DepthLoss(3, "live").forward_losses(t.img_l, t.img, t.img_r, disp, disp_l, disp_r, pose, t.K)
+                g = torch.autograd.grad(loss["loss_depth_pixel"].mean(), disp + [pose])
+                ff, fb = _leaf_list(t.flows_fwd, cuda_device), _leaf_list(t.flows_bwd, cuda_device)
+                disp2 = _leaf_list(t.disp, cuda_device)
+                pose2 = t.pose.detach().clone().requires_grad_(True)
+                gl, gm = losses.GeometryLoss(3).forward_losses(t.img_l, t.img, t.img_r, ff, fb, disp2, disp_l, disp_r, pose2, t.K, t.K_inv)
+                g2 = torch.autograd.grad(gl["loss_depth_pixel"].mean(), disp2 + [pose2])
+            finally:
+                ops.DEPTH_PHOTO_SINGLE_PASS = True
+            res[single] = (loss["loss_depth_pixel"], masks, g, gl["loss_depth_pixel"], g2)
+        assert loss_rel_err(res[True][0], res[False][0]) < 1e-6 and loss_rel_err(res[True][3], res[False][3]) < 1e-6
+        for k in ("valid_l", "valid_r", "tex_b", "tex_f"):
+            for a, b in zip(res[True][1][k], res[False][1][k]):
+                assert torch.equal(a, b), k
+        for a, b in zip(res[True][2] + res[True][4], res[False][2] + res[False][4]):
+            assert rel_err(a, b) < 3e-5      # the scale is applied after instead of before the chain through the projection
+
+
 @pytest.mark.parametrize("n,S,want_F", [(2, 3, True), (1, 4, False), (2, 1, True)])
 def test_pose_setup_vs_composed_torch(cuda_device, n, S, want_F):
     """ops.pose_setup (one launch fwd, one bwd) against the reference's chain of small torch ops (structures.projection_pyramid,

@@ -80,6 +80,12 @@ class UglDepthSsimArgs(C.Structure):
                 ("grad_loss4", C.c_void_p)]
 
 
+class UglDepthPhotoGradArgs(C.Structure):
+    """Mirror of ``struct UglDepthPhotoGradArgs`` (include/ugl.h)."""
+
+    _fields_ = [("photo", UglDepthPhotoArgs), ("basis", C.c_void_p * MAX_LEVELS), ("psum", C.c_void_p)]
+
+
 class UglGeomFlowArgs(C.Structure):
     """Mirror of ``struct UglGeomFlowArgs`` (include/ugl.h)."""
 
@@ -161,6 +167,9 @@ SIGNATURES.update({
     "ugl_depth_photo_workspace_bytes": (_u64, [C.POINTER(UglDepthPhotoArgs)]),
     "ugl_depth_photo_forward": (C.c_int, [C.POINTER(UglDepthPhotoArgs)]),
     "ugl_depth_photo_backward": (C.c_int, [C.POINTER(UglDepthPhotoArgs)]),
+    "ugl_depth_photo_grad_workspace_bytes": (_u64, [C.POINTER(UglDepthPhotoGradArgs)]),
+    "ugl_depth_photo_forward_grad": (C.c_int, [C.POINTER(UglDepthPhotoGradArgs)]),
+    "ugl_depth_photo_combine": (C.c_int, [C.POINTER(UglDepthPhotoGradArgs)]),
     "ugl_reduce_workspace_bytes": (_u64, [_i, _i, _i]),
     "ugl_masked_mean_forward": (C.c_int, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _u64, _p]),
     "ugl_masked_mean_backward": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),

@@ -45,11 +45,15 @@ struct DepthPhotoParams {
   float* loss;                 // (B,)
   const float* gloss;          // (B,)            [backward]
   float* grad_P[2][kMaxLevels];// (B,3,4)         [backward]
+  // single-pass mode (ugl_depth_photo_forward_grad / _combine)
+  float* basis[kMaxLevels];    // (B,2,h,w) un-normalised d loss / d disparity through direction 0 / 1
+  float* psum;                 // [B][scales][2][12] un-normalised d loss / d P sums
 };
 
 struct DepthPixel {
   float I[3], rec[3];
   float mask;                  // fused {0,1} mask of this direction
+  float tex;                   // texture mask
   Projected pr;
   NormCoord nc;
   Tap tap;
@@ -81,6 +85,7 @@ __device__ __forceinline__ void depth_pixel(const DepthPhotoLevel& L, const floa
   if (L.ext_bytes) base = ((unsigned)L.ext_bytes[(long)b * plane + p] & L.ext_need[dir]) == L.ext_need[dir] ? 1.f : 0.f;
   else if (L.ext_mask[dir]) base = L.ext_mask[dir][(long)b * plane + p];
   o.mask = mul_rn(base, tex);
+  o.tex = tex;
   if (!kGrad) {
     if (L.valid_out[dir]) L.valid_out[dir][(long)b * plane + p] = valid;
     if (L.tex_out[dir]) L.tex_out[dir][(long)b * plane + p] = tex;
@@ -179,6 +184,97 @@ __global__ void __launch_bounds__(kRedThreads, UGL_DP_BWD_MINB) depth_photo_bwd_
   }
   const float v = block_reduce_n<kRedThreads, 12>(acc, red);
   if (threadIdx.x < 12) p.partials[(((long)b * p.scales + l) * p.chunks + blockIdx.x) * 24 + 12 * dir + threadIdx.x] = v;
+}
+
+// ---- single-pass variant ---------------------------------------------------------------------------------------------
+// The backward kernel above repeats the whole forward (projection, gathers, masks) to get at the per-pixel derivatives.  Like the
+// flow kernel, this variant computes them in the forward launch while the taps are in registers: it writes the UN-normalised
+// d loss / d disparity of each direction (one float per pixel and direction) and reduces the un-normalised d loss / d P sums; the
+// per-sample normaliser 1 / mean(mask) and the upstream gradient are applied afterwards by an element-wise combine.  One gather
+// kernel per step instead of two.  Partial rows: [B][scales][chunks][2][14] = {sum |I - rec| mask, sum mask, 12 P sums}.
+constexpr int kDpAcc = 14;
+__global__ void __launch_bounds__(kRedThreads, UGL_DP_BWD_MINB) depth_photo_fwdgrad_kernel(const __grid_constant__ DepthPhotoParams p) {
+  __shared__ float sK[9], sP[12];
+  __shared__ float red[(kRedThreads / 32) * kDpAcc];
+  const int b = blockIdx.y, l = blockIdx.z >> 1, dir = blockIdx.z & 1;
+  const DepthPhotoLevel& L = p.lv[l];
+  if (threadIdx.x < 9) sK[threadIdx.x] = L.Kinv[b * 9 + threadIdx.x];
+  if (threadIdx.x < 12) sP[threadIdx.x] = L.P[dir][b * 12 + threadIdx.x];
+  __syncthreads();
+  const WarpGeom g = make_warp_geom(L.w, L.h);
+  const long plane = (long)L.h * L.w;
+  float* basis = p.basis[l] + ((long)b * 2 + dir) * plane;
+  float acc[kDpAcc];
+#pragma unroll
+  for (int k = 0; k < kDpAcc; ++k) acc[k] = 0.f;
+  for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
+    const int i = (int)(px / L.w), j = (int)(px % L.w);
+    DepthPixel o;
+    float gix, giy;
+    depth_pixel<true>(L, sK, sP, b, dir, i, j, px, g, o, &gix, &giy, 1.0f);
+    if (L.valid_out[dir]) L.valid_out[dir][(long)b * plane + px] = (fabsf(o.nc.gx) <= 1.0f && fabsf(o.nc.gy) <= 1.0f) ? 1.f : 0.f;
+    if (L.tex_out[dir]) L.tex_out[dir][(long)b * plane + px] = o.tex;
+    acc[12] += (fabsf(o.I[0] - o.rec[0]) + fabsf(o.I[1] - o.rec[1]) + fabsf(o.I[2] - o.rec[2])) * o.mask;
+    acc[13] += o.mask;
+    const float g_u = o.nc.ox ? 0.f : gix * g.sx;
+    const float g_v = o.nc.oy ? 0.f : giy * g.sy;
+    basis[px] = project_backward(o.pr, sP, g_u, g_v, 0.f, acc);      // adds the 12 P partials into acc[0..11]
+  }
+  const float v = block_reduce_n<kRedThreads, kDpAcc>(acc, red);
+  if (threadIdx.x < kDpAcc) p.partials[((((long)b * p.scales + l) * p.chunks + blockIdx.x) * 2 + dir) * kDpAcc + threadIdx.x] = v;
+}
+
+// one warp per sample: fixed-order fp64 sums of the chunk partials -> den, loss and the un-normalised P sums
+__global__ void depth_photo_fwdgrad_finalize_kernel(const __grid_constant__ DepthPhotoParams p) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= p.B) return;
+  float total = 0.f;
+  for (int l = 0; l < p.scales; ++l) {
+    const float hw = (float)p.lv[l].h * (float)p.lv[l].w;
+    // lanes 0..27 own one (direction, accumulator) column each and add the chunks in order
+    double s = 0.0;
+    if (lane < 2 * kDpAcc) {
+      const int dir = lane / kDpAcc, k = lane % kDpAcc;
+      for (int c = 0; c < p.chunks; ++c) s += (double)p.partials[((((long)b * p.scales + l) * p.chunks + c) * 2 + dir) * kDpAcc + k];
+      if (k < 12) p.psum[(((long)b * p.scales + l) * 2 + dir) * 12 + k] = (float)s;
+    }
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      const double s_abs = __shfl_sync(0xffffffffu, s, dir * kDpAcc + 12), s_m = __shfl_sync(0xffffffffu, s, dir * kDpAcc + 13);
+      if (lane == 0) {
+        const float den = (float)(s_m / hw) + 1e-12f;
+        p.den[((long)b * p.scales + l) * 2 + dir] = den;
+        total += (float)(s_abs / (3.0 * hw)) / den;
+      }
+    }
+  }
+  if (lane == 0) p.loss[b] = total;
+}
+
+// element-wise backward of the single-pass variant: grid (chunks, B, levels)
+__global__ void __launch_bounds__(kRedThreads) depth_photo_combine_kernel(const __grid_constant__ DepthPhotoParams p) {
+  const int b = blockIdx.y, l = blockIdx.z;
+  const DepthPhotoLevel& L = p.lv[l];
+  const long plane = (long)L.h * L.w;
+  const float hw = (float)L.h * (float)L.w;
+  const float k0 = p.gloss[b] / (3.0f * hw) / p.den[((long)b * p.scales + l) * 2 + 0];
+  const float k1 = p.gloss[b] / (3.0f * hw) / p.den[((long)b * p.scales + l) * 2 + 1];
+  const float* b0 = p.basis[l] + (long)b * 2 * plane;
+  const float* b1 = b0 + plane;
+  float* gd = L.grad_disp + (long)b * plane;
+  if ((plane & 3) == 0) {
+    const long q = plane >> 2;
+    for (long i = blockIdx.x * (long)kRedThreads + threadIdx.x; i < q; i += (long)gridDim.x * kRedThreads) {
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(b0) + i), y = __ldcs(reinterpret_cast<const float4*>(b1) + i);
+      reinterpret_cast<float4*>(gd)[i] = make_float4(k0 * x.x + k1 * y.x, k0 * x.y + k1 * y.y, k0 * x.z + k1 * y.z, k0 * x.w + k1 * y.w);
+    }
+  } else {
+    for (long i = blockIdx.x * (long)kRedThreads + threadIdx.x; i < plane; i += (long)gridDim.x * kRedThreads) gd[i] = k0 * b0[i] + k1 * b1[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 24) {
+    const int dir = threadIdx.x / 12, k = threadIdx.x % 12;
+    p.grad_P[dir][l][b * 12 + k] = (dir == 0 ? k0 : k1) * p.psum[(((long)b * p.scales + l) * 2 + dir) * 12 + k];
+  }
 }
 
 // backward of the depth-mode single-pass kernel (ugl_depth_ssim_forward_grad): the saved basis holds the un-normalised
@@ -346,4 +442,68 @@ extern "C" int ugl_depth_ssim_combine(const UglDepthSsimArgs* g) {
   if (rc) return rc;
   depth_photo_bwd_finalize_kernel<<<(p.B * p.scales + 3) / 4, 128, 0, st>>>(p);
   return check_launch("depth_photo_bwd_finalize_kernel");
+}
+
+// ---- single-pass variant: forward_grad + combine --------------------------------------------------------------------
+static uint64_t depth_photo_grad_need(int B, int scales, int chunks) { return (uint64_t)B * scales * chunks * 2 * ugl::kDpAcc * sizeof(float); }
+
+extern "C" uint64_t ugl_depth_photo_grad_workspace_bytes(const UglDepthPhotoGradArgs* g) {
+  if (!g) return 0;
+  const UglDepthPhotoArgs* a = &g->photo;
+  long max_plane = 0;
+  for (int l = 0; l < a->scales && l < UGL_MAX_LEVELS; ++l) {
+    const long pl = (long)a->height[l] * a->width[l];
+    max_plane = pl > max_plane ? pl : max_plane;
+  }
+  const uint64_t base = ugl_depth_photo_workspace_bytes(a), need = depth_photo_grad_need(a->batch, a->scales, reduce_chunks(max_plane));
+  return need > base ? need : base;
+}
+
+extern "C" int ugl_depth_photo_forward_grad(const UglDepthPhotoGradArgs* g) {
+  if (!g) return fail(UGL_EINVAL, "depth_photo_forward_grad: null args");
+  const UglDepthPhotoArgs* a = &g->photo;
+  DepthPhotoParams p;
+  int rc = depth_photo_fill(a, false, p);
+  if (rc) return rc;
+  if (!a->loss || !g->psum) return fail(UGL_EINVAL, "depth_photo_forward_grad: null loss / psum");
+  if (a->workspace_bytes < depth_photo_grad_need(p.B, p.scales, p.chunks))
+    return fail(UGL_EWORKSPACE, "depth_photo_forward_grad: workspace too small (%llu bytes)", (unsigned long long)a->workspace_bytes);
+  for (int l = 0; l < p.scales; ++l) {
+    if (!g->basis[l]) return fail(UGL_EINVAL, "depth_photo_forward_grad: null basis at level %d", l);
+    p.basis[l] = g->basis[l];
+  }
+  p.psum = g->psum;
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  depth_photo_fwdgrad_kernel<<<dim3(p.chunks, p.B, 2 * p.scales), kRedThreads, 0, st>>>(p);
+  if ((rc = check_launch("depth_photo_fwdgrad_kernel"))) return rc;
+  depth_photo_fwdgrad_finalize_kernel<<<(p.B + 3) / 4, 128, 0, st>>>(p);
+  return check_launch("depth_photo_fwdgrad_finalize_kernel");
+}
+
+extern "C" int ugl_depth_photo_combine(const UglDepthPhotoGradArgs* g) {
+  if (!g) return fail(UGL_EINVAL, "depth_photo_combine: null args");
+  const UglDepthPhotoArgs* a = &g->photo;
+  if (a->batch <= 0 || a->batch > 65535 || a->scales <= 0 || a->scales > UGL_MAX_LEVELS)
+    return fail(UGL_EINVAL, "depth_photo_combine: bad batch/scales (%d/%d)", a->batch, a->scales);
+  if (!a->grad_loss || !a->den || !g->psum) return fail(UGL_EINVAL, "depth_photo_combine: null grad_loss / den / psum");
+  DepthPhotoParams p;
+  p.B = a->batch; p.scales = a->scales; p.den = a->den; p.gloss = a->grad_loss; p.psum = g->psum;
+  long max_plane = 0;
+  for (int l = 0; l < a->scales; ++l) {
+    DepthPhotoLevel& L = p.lv[l];
+    L.h = a->height[l]; L.w = a->width[l]; L.grad_disp = a->grad_disp[l];
+    p.basis[l] = g->basis[l];
+    if (L.h < 2 || L.w < 2 || !L.grad_disp || !p.basis[l]) return fail(UGL_EINVAL, "depth_photo_combine: bad level %d", l);
+    if ((reinterpret_cast<uintptr_t>(L.grad_disp) | reinterpret_cast<uintptr_t>(p.basis[l])) & 15u)
+      return fail(UGL_EALIGN, "depth_photo_combine: level %d not 16-byte aligned", l);
+    for (int d = 0; d < 2; ++d) {
+      p.grad_P[d][l] = a->grad_P[d][l];
+      if (!p.grad_P[d][l]) return fail(UGL_EINVAL, "depth_photo_combine: null grad_P at level %d", l);
+    }
+    const long pl = (long)L.h * L.w;
+    max_plane = pl > max_plane ? pl : max_plane;
+  }
+  p.chunks = reduce_chunks(max_plane);
+  depth_photo_combine_kernel<<<dim3(p.chunks, p.B, p.scales), kRedThreads, 0, static_cast<cudaStream_t>(a->stream)>>>(p);
+  return check_launch("depth_photo_combine_kernel");
 }

@@ -1186,6 +1186,11 @@ def _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, loss, den, ws, vali
     return a
 
 
+DEPTH_PHOTO_SINGLE_PASS = True
+"""reprojection-photometric term: True = the forward launch also emits the gradient basis and backward is an element-wise combine
+(ugl_depth_photo_forward_grad / _combine); False = backward recomputes the gathers (ugl_depth_photo_backward; saves nothing per pixel)."""
+
+
 class _DepthPhotoFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, S, has_ext, ext_need, *ts):
@@ -1207,13 +1212,33 @@ class _DepthPhotoFn(torch.autograd.Function):
         mk = lambda: [[torch.empty((B, 1) + tuple(img[l].shape[2:]), device=dev, dtype=torch.float32) for l in range(S)] for _ in range(2)]
         valid_out, tex_out = mk(), mk()
         a = _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, loss, den, None, valid_out, tex_out, ext_bytes=ext_bytes, ext_need=ext_need)
-        n = int(_cabi.lib().ugl_depth_photo_workspace_bytes(C.byref(a)))
-        ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
-        a.workspace, a.workspace_bytes = ws.data_ptr(), _nbytes(ws)
-        with torch.cuda.device_of(img[0]):
-            _call("ugl_depth_photo_forward", C.byref(a), launches=2)
-        ctx.save_for_backward(den, *ts, *(ext_bytes or []))
-        ctx.S, ctx.has_ext, ctx.ext_need = S, has_ext, ext_need
+        # a gradient will be asked for: single-pass variant (the forward launch also emits the un-normalised derivatives while
+        # its taps are in registers; backward = an element-wise combine instead of a second gather kernel)
+        single = DEPTH_PHOTO_SINGLE_PASS and any(ctx.needs_input_grad[3:])
+        ctx.single = single
+        if single:
+            g = _cabi.UglDepthPhotoGradArgs()
+            g.photo = a
+            basis = [torch.empty((B, 2) + tuple(img[l].shape[2:]), device=dev, dtype=torch.float32) for l in range(S)]
+            psum = torch.empty((B, S, 2, 12), device=dev, dtype=torch.float32)
+            for l in range(S):
+                g.basis[l] = basis[l].data_ptr()
+            g.psum = psum.data_ptr()
+            n = int(_cabi.lib().ugl_depth_photo_grad_workspace_bytes(C.byref(g)))
+            ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
+            g.photo.workspace, g.photo.workspace_bytes = ws.data_ptr(), _nbytes(ws)
+            with torch.cuda.device_of(img[0]):
+                _call("ugl_depth_photo_forward_grad", C.byref(g), launches=2)
+            ctx.save_for_backward(den, psum, *basis, *disp, *P[0], *P[1])
+        else:
+            n = int(_cabi.lib().ugl_depth_photo_workspace_bytes(C.byref(a)))
+            ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), _nbytes(ws)
+            with torch.cuda.device_of(img[0]):
+                _call("ugl_depth_photo_forward", C.byref(a), launches=2)
+            if any(ctx.needs_input_grad[3:]):            # recompute mode: backward re-runs the gathers from the inputs
+                ctx.save_for_backward(den, *ts, *(ext_bytes or []))
+        ctx.S, ctx.has_ext, ctx.n_in, ctx.ext_need = S, has_ext, len(ts) + nb, ext_need
         masks = [m for grp in (valid_out, tex_out) for d in grp for m in d]
         ctx.mark_non_differentiable(*masks)
         ctx.set_materialize_grads(False)
@@ -1221,25 +1246,29 @@ class _DepthPhotoFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gloss, *unused):
-        den, *ts = ctx.saved_tensors
         S = ctx.S
-        if gloss is None:
-            return (None,) * (3 + len(ts))
-        ext_bytes = ts[len(ts) - S:] if ctx.has_ext == 2 else None
-        g = lambda k: ts[k * S:(k + 1) * S]
-        img, area, bil, disp, Kinv, P = g(0), (g(1), g(2)), (g(3), g(4)), g(5), g(6), (g(7), g(8))
-        ext = (g(9), g(10)) if ctx.has_ext == 1 else None
-        B, dev = img[0].shape[0], img[0].device
+        if gloss is None or not ctx.saved_tensors:
+            return (None,) * (3 + ctx.n_in)
+        if not ctx.single:
+            return _DepthPhotoFn._backward_recompute(ctx, gloss)
+        den, psum, *rest = ctx.saved_tensors
+        basis, disp, P = rest[0:S], rest[S:2 * S], (rest[2 * S:3 * S], rest[3 * S:4 * S])
+        B, dev = disp[0].shape[0], disp[0].device
         gloss = _dev(gloss, "grad_loss")
         gdisp = [torch.empty_like(d) for d in disp]
         gP = [[torch.empty((B, 3, 4), device=dev, dtype=torch.float32) for _ in range(S)] for _ in range(2)]
-        a = _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, None, den, None, gloss=gloss, gdisp=gdisp, gP=gP,
-                              ext_bytes=ext_bytes, ext_need=ctx.ext_need)
-        n = int(_cabi.lib().ugl_depth_photo_workspace_bytes(C.byref(a)))
-        ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
-        a.workspace, a.workspace_bytes = ws.data_ptr(), _nbytes(ws)
+        g = _cabi.UglDepthPhotoGradArgs()
+        a = g.photo
+        a.batch, a.scales = B, S
+        for l in range(S):
+            a.height[l], a.width[l] = disp[l].shape[2], disp[l].shape[3]
+            a.grad_disp[l] = gdisp[l].data_ptr()
+            g.basis[l] = basis[l].data_ptr()
+            for d in range(2):
+                a.grad_P[d][l] = gP[d][l].data_ptr()
+        a.den, a.grad_loss, g.psum, a.stream = den.data_ptr(), gloss.data_ptr(), psum.data_ptr(), _stream_ptr()
         with torch.cuda.device_of(gloss):
-            _call("ugl_depth_photo_backward", C.byref(a), launches=2)
+            _call("ugl_depth_photo_combine", C.byref(g), launches=1)
         none = [None] * S
         out = [None, None, None, *none, *none, *none, *none, *none, *gdisp, *none, *gP[0], *gP[1]]
         if ctx.has_ext == 1:
@@ -1247,6 +1276,36 @@ class _DepthPhotoFn(torch.autograd.Function):
         elif ctx.has_ext == 2:
             out += none
         return tuple(out)
+
+
+def _depth_photo_backward_recompute(ctx, gloss):
+    den, *ts = ctx.saved_tensors
+    S = ctx.S
+    ext_bytes = ts[len(ts) - S:] if ctx.has_ext == 2 else None
+    g = lambda k: ts[k * S:(k + 1) * S]
+    img, area, bil, disp, Kinv, P = g(0), (g(1), g(2)), (g(3), g(4)), g(5), g(6), (g(7), g(8))
+    ext = (g(9), g(10)) if ctx.has_ext == 1 else None
+    B, dev = img[0].shape[0], img[0].device
+    gloss = _dev(gloss, "grad_loss")
+    gdisp = [torch.empty_like(d) for d in disp]
+    gP = [[torch.empty((B, 3, 4), device=dev, dtype=torch.float32) for _ in range(S)] for _ in range(2)]
+    a = _depth_photo_args(S, img, area, bil, disp, Kinv, P, ext, None, den, None, gloss=gloss, gdisp=gdisp, gP=gP,
+                          ext_bytes=ext_bytes, ext_need=ctx.ext_need)
+    n = int(_cabi.lib().ugl_depth_photo_workspace_bytes(C.byref(a)))
+    ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), _nbytes(ws)
+    with torch.cuda.device_of(gloss):
+        _call("ugl_depth_photo_backward", C.byref(a), launches=2)
+    none = [None] * S
+    out = [None, None, None, *none, *none, *none, *none, *none, *gdisp, *none, *gP[0], *gP[1]]
+    if ctx.has_ext == 1:
+        out += none + none
+    elif ctx.has_ext == 2:
+        out += none
+    return tuple(out)
+
+
+_DepthPhotoFn._backward_recompute = staticmethod(_depth_photo_backward_recompute)
 
 
 class _DepthConsisFn(torch.autograd.Function):
