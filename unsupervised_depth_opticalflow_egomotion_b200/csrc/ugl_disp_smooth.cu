@@ -44,6 +44,8 @@ __device__ __forceinline__ DsTap ds_tap(int dst, int n_in, float scale) {
 __global__ void __launch_bounds__(kDsNT) disp_smooth_fwdgrad_kernel(const __grid_constant__ DsParams p) {
   __shared__ float sI[3][kDsPN], sWx[kDsPN], sWy[kDsPN], sU[kDsPN];
   __shared__ float red[(kDsNT / 32) * 2];
+  __shared__ int sXi[2][kDsPW], sYo[2][kDsPH];        // column indices / row offsets of the current level's up-sampling taps
+  __shared__ float sXl[2][kDsPW], sYl[2][kDsPH];      // and their weights
   const int tile = blockIdx.x, b = blockIdx.y, li = blockIdx.z;
   const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
   const int x0 = tx * kDsTW, y0 = ty * kDsTH, H = p.H, W = p.W;
@@ -86,7 +88,20 @@ __global__ void __launch_bounds__(kDsNT) disp_smooth_fwdgrad_kernel(const __grid
     const float* d = p.disp[li][l] + (long)b * h * w;
     const bool full = (h == H && w == W);
     const float sy = (float)h / (float)H, sx = (float)w / (float)W;
-    __syncthreads();                       // weights ready (first level) / previous level's sU consumed
+    // the up-sampling taps are separable: the 34 column taps and 18 row taps of the tile are formed once per level (the previous
+    // level's taps are dead since its mid barrier) instead of twice per halo pixel
+    if (!full) {
+      if (threadIdx.x < kDsPW) {
+        const int X = x0 - 1 + (int)threadIdx.x;
+        const DsTap t = ds_tap(X < 0 ? 0 : (X >= W ? W - 1 : X), w, sx);
+        sXi[0][threadIdx.x] = t.i0; sXi[1][threadIdx.x] = t.i1; sXl[0][threadIdx.x] = t.l0; sXl[1][threadIdx.x] = t.l1;
+      } else if (threadIdx.x >= 64 && threadIdx.x < 64 + kDsPH) {
+        const int r = (int)threadIdx.x - 64, Y = y0 - 1 + r;
+        const DsTap t = ds_tap(Y < 0 ? 0 : (Y >= H ? H - 1 : Y), h, sy);
+        sYo[0][r] = t.i0 * w; sYo[1][r] = t.i1 * w; sYl[0][r] = t.l0; sYl[1][r] = t.l1;
+      }
+    }
+    __syncthreads();                       // weights ready (first level) / previous level's sU consumed / taps ready
     for (int idx = threadIdx.x; idx < kDsPN; idx += kDsNT) {
       const int ly = idx / kDsPW, lx = idx - ly * kDsPW;
       const int Y = y0 - 1 + ly, X = x0 - 1 + lx;
@@ -95,10 +110,11 @@ __global__ void __launch_bounds__(kDsNT) disp_smooth_fwdgrad_kernel(const __grid
         if (full) {
           v = d[(long)Y * W + X];
         } else {
-          const DsTap ty_ = ds_tap(Y, h, sy), tx_ = ds_tap(X, w, sx);
-          const float* r0 = d + (long)ty_.i0 * w;
-          const float* r1 = d + (long)ty_.i1 * w;
-          v = ty_.l0 * (tx_.l0 * r0[tx_.i0] + tx_.l1 * r0[tx_.i1]) + ty_.l1 * (tx_.l0 * r1[tx_.i0] + tx_.l1 * r1[tx_.i1]);
+          const float* r0 = d + sYo[0][ly];
+          const float* r1 = d + sYo[1][ly];
+          const int i0 = sXi[0][lx], i1 = sXi[1][lx];
+          const float xl0 = sXl[0][lx], xl1 = sXl[1][lx];
+          v = sYl[0][ly] * (xl0 * r0[i0] + xl1 * r0[i1]) + sYl[1][ly] * (xl0 * r1[i0] + xl1 * r1[i1]);
         }
       }
       sU[idx] = v;
