@@ -224,31 +224,43 @@ __global__ void __launch_bounds__(kRedThreads, UGL_DP_BWD_MINB) depth_photo_fwdg
   if (threadIdx.x < kDpAcc) p.partials[((((long)b * p.scales + l) * p.chunks + blockIdx.x) * 2 + dir) * kDpAcc + threadIdx.x] = v;
 }
 
-// one warp per sample: fixed-order fp64 sums of the chunk partials -> den, loss and the un-normalised P sums
-__global__ void depth_photo_fwdgrad_finalize_kernel(const __grid_constant__ DepthPhotoParams p) {
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (b >= p.B) return;
+// one CTA per sample: fixed-order fp64 sums of the chunk partials -> den, loss and the un-normalised P sums.  The 28 (direction,
+// accumulator) columns of a level are summed by 9 thread groups over interleaved chunks, then across the groups in group order.
+constexpr int kDpFinGroups = 9, kDpFinThreads = 256;
+__global__ void __launch_bounds__(kDpFinThreads) depth_photo_fwdgrad_finalize_kernel(const __grid_constant__ DepthPhotoParams p) {
+  __shared__ double part[kDpFinGroups][2 * kDpAcc];
+  __shared__ double tot[2 * kDpAcc];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int grp = t / (2 * kDpAcc), col = t % (2 * kDpAcc);
   float total = 0.f;
   for (int l = 0; l < p.scales; ++l) {
-    const float hw = (float)p.lv[l].h * (float)p.lv[l].w;
-    // lanes 0..27 own one (direction, accumulator) column each and add the chunks in order
-    double s = 0.0;
-    if (lane < 2 * kDpAcc) {
-      const int dir = lane / kDpAcc, k = lane % kDpAcc;
-      for (int c = 0; c < p.chunks; ++c) s += (double)p.partials[((((long)b * p.scales + l) * p.chunks + c) * 2 + dir) * kDpAcc + k];
+    if (grp < kDpFinGroups) {
+      const int dir = col / kDpAcc, k = col % kDpAcc;
+      double s = 0.0;
+      for (int c = grp; c < p.chunks; c += kDpFinGroups) s += (double)p.partials[((((long)b * p.scales + l) * p.chunks + c) * 2 + dir) * kDpAcc + k];
+      part[grp][col] = s;
+    }
+    __syncthreads();
+    if (t < 2 * kDpAcc) {
+      double s = 0.0;
+#pragma unroll
+      for (int g = 0; g < kDpFinGroups; ++g) s += part[g][t];
+      tot[t] = s;
+      const int dir = t / kDpAcc, k = t % kDpAcc;
       if (k < 12) p.psum[(((long)b * p.scales + l) * 2 + dir) * 12 + k] = (float)s;
     }
+    __syncthreads();
+    if (t == 0) {
+      const float hw = (float)p.lv[l].h * (float)p.lv[l].w;
 #pragma unroll
-    for (int dir = 0; dir < 2; ++dir) {
-      const double s_abs = __shfl_sync(0xffffffffu, s, dir * kDpAcc + 12), s_m = __shfl_sync(0xffffffffu, s, dir * kDpAcc + 13);
-      if (lane == 0) {
-        const float den = (float)(s_m / hw) + 1e-12f;
+      for (int dir = 0; dir < 2; ++dir) {
+        const float den = (float)(tot[dir * kDpAcc + 13] / hw) + 1e-12f;
         p.den[((long)b * p.scales + l) * 2 + dir] = den;
-        total += (float)(s_abs / (3.0 * hw)) / den;
+        total += (float)(tot[dir * kDpAcc + 12] / (3.0 * hw)) / den;
       }
     }
   }
-  if (lane == 0) p.loss[b] = total;
+  if (t == 0) p.loss[b] = total;
 }
 
 // element-wise backward of the single-pass variant: grid (chunks, B, levels)
@@ -476,7 +488,7 @@ extern "C" int ugl_depth_photo_forward_grad(const UglDepthPhotoGradArgs* g) {
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   depth_photo_fwdgrad_kernel<<<dim3(p.chunks, p.B, 2 * p.scales), kRedThreads, 0, st>>>(p);
   if ((rc = check_launch("depth_photo_fwdgrad_kernel"))) return rc;
-  depth_photo_fwdgrad_finalize_kernel<<<(p.B + 3) / 4, 128, 0, st>>>(p);
+  depth_photo_fwdgrad_finalize_kernel<<<p.B, kDpFinThreads, 0, st>>>(p);
   return check_launch("depth_photo_fwdgrad_finalize_kernel");
 }
 
