@@ -73,12 +73,6 @@ UGL_HD TapC tap_clamped_norm(float gx, float gy, const WarpGeom& g) {
   return t;
 }
 
-template <bool kGrad>
-UGL_HD TapC flow_tap_clamped(int j, int i, float u, float v, const WarpGeom& g) {
-  const float gx = sub_rn(div_c(mul_rn(2.0f, add_rn((float)j, u)), g.dw, g.rdw), 1.0f);
-  const float gy = sub_rn(div_c(mul_rn(2.0f, add_rn((float)i, v)), g.dh, g.rdh), 1.0f);
-  return tap_clamped_norm<kGrad>(gx, gy, g);
-}
 
 // ---- the same gather set-up for BOTH warp directions of a pixel as packed fp32 pairs (.x = forward flow / right frame,
 // .y = backward flow / left frame): identical roundings (every packed op is the .rn form of the scalar one; where ptxas may
