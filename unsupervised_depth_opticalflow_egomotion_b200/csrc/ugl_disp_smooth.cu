@@ -16,6 +16,7 @@ namespace ugl {
 constexpr int kDsTW = 32, kDsTH = 16, kDsNT = 256;
 constexpr int kDsPW = kDsTW + 2, kDsPH = kDsTH + 2, kDsPN = kDsPW * kDsPH;
 constexpr int kDsLists = UGL_DISP_SMOOTH_MAX_LISTS;
+constexpr int kDsPatch = (kDsPW / 2 + 3) * (kDsPH / 2 + 3);   // low-resolution patch of a >= 2x level: 20 x 12
 
 struct DsParams {
   int B, lists, levels, H, W, tiles_x, tiles_y;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(kDsNT) disp_smooth_fwdgrad_kernel(const __grid
   __shared__ float red[(kDsNT / 32) * 2];
   __shared__ int sXi[2][kDsPW], sYo[2][kDsPH];        // column indices / row offsets of the current level's up-sampling taps
   __shared__ float sXl[2][kDsPW], sYl[2][kDsPH];      // and their weights
+  __shared__ float sD[kDsPatch];                      // the low-resolution disparity patch under the tile
   const int tile = blockIdx.x, b = blockIdx.y, li = blockIdx.z;
   const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
   const int x0 = tx * kDsTW, y0 = ty * kDsTH, H = p.H, W = p.W;
@@ -89,19 +91,39 @@ __global__ void __launch_bounds__(kDsNT) disp_smooth_fwdgrad_kernel(const __grid
     const bool full = (h == H && w == W);
     const float sy = (float)h / (float)H, sx = (float)w / (float)W;
     // the up-sampling taps are separable: the 34 column taps and 18 row taps of the tile are formed once per level (the previous
-    // level's taps are dead since its mid barrier) instead of twice per halo pixel
+    // level's taps are dead since its mid barrier) instead of twice per halo pixel.  The low-resolution patch they address (at most
+    // 19 x 11 values for a 2x level) is staged in shared memory with coalesced loads, so the four taps of a pixel are shared-memory
+    // reads instead of four scattered global loads (the up-sampling line carried most of the kernel's long-scoreboard stalls).
+    int cx0 = 0, ry0 = 0, pw = 0, ph = 0;
+    if (!full) {
+      const int Xa = x0 - 1 < 0 ? 0 : x0 - 1, Xb = x0 - 2 + kDsPW >= W ? W - 1 : x0 - 2 + kDsPW;
+      const int Ya = y0 - 1 < 0 ? 0 : y0 - 1, Yb = y0 - 2 + kDsPH >= H ? H - 1 : y0 - 2 + kDsPH;
+      cx0 = ds_tap(Xa, w, sx).i0; pw = ds_tap(Xb, w, sx).i1 - cx0 + 1;
+      ry0 = ds_tap(Ya, h, sy).i0; ph = ds_tap(Yb, h, sy).i1 - ry0 + 1;
+    }
+    const bool patch = !full && pw * ph <= kDsPatch;          // uniform over the CTA
     if (!full) {
       if (threadIdx.x < kDsPW) {
         const int X = x0 - 1 + (int)threadIdx.x;
         const DsTap t = ds_tap(X < 0 ? 0 : (X >= W ? W - 1 : X), w, sx);
-        sXi[0][threadIdx.x] = t.i0; sXi[1][threadIdx.x] = t.i1; sXl[0][threadIdx.x] = t.l0; sXl[1][threadIdx.x] = t.l1;
+        sXi[0][threadIdx.x] = t.i0 - (patch ? cx0 : 0); sXi[1][threadIdx.x] = t.i1 - (patch ? cx0 : 0);
+        sXl[0][threadIdx.x] = t.l0; sXl[1][threadIdx.x] = t.l1;
       } else if (threadIdx.x >= 64 && threadIdx.x < 64 + kDsPH) {
         const int r = (int)threadIdx.x - 64, Y = y0 - 1 + r;
         const DsTap t = ds_tap(Y < 0 ? 0 : (Y >= H ? H - 1 : Y), h, sy);
-        sYo[0][r] = t.i0 * w; sYo[1][r] = t.i1 * w; sYl[0][r] = t.l0; sYl[1][r] = t.l1;
+        sYo[0][r] = patch ? (t.i0 - ry0) * pw : t.i0 * w; sYo[1][r] = patch ? (t.i1 - ry0) * pw : t.i1 * w;
+        sYl[0][r] = t.l0; sYl[1][r] = t.l1;
       }
     }
-    __syncthreads();                       // weights ready (first level) / previous level's sU consumed / taps ready
+    __syncthreads();                       // weights ready (first level) / previous level's sU and patch consumed / taps ready
+    if (patch) {
+      for (int k = threadIdx.x; k < pw * ph; k += kDsNT) {
+        const int r = k / pw, c = k - r * pw;
+        sD[k] = d[(long)(ry0 + r) * w + cx0 + c];
+      }
+      __syncthreads();
+    }
+    const float* src = patch ? sD : d;
     for (int idx = threadIdx.x; idx < kDsPN; idx += kDsNT) {
       const int ly = idx / kDsPW, lx = idx - ly * kDsPW;
       const int Y = y0 - 1 + ly, X = x0 - 1 + lx;
@@ -110,8 +132,8 @@ __global__ void __launch_bounds__(kDsNT) disp_smooth_fwdgrad_kernel(const __grid
         if (full) {
           v = d[(long)Y * W + X];
         } else {
-          const float* r0 = d + sYo[0][ly];
-          const float* r1 = d + sYo[1][ly];
+          const float* r0 = src + sYo[0][ly];
+          const float* r1 = src + sYo[1][ly];
           const int i0 = sXi[0][lx], i1 = sXi[1][lx];
           const float xl0 = sXl[0][lx], xl1 = sXl[1][lx];
           v = sYl[0][ly] * (xl0 * r0[i0] + xl1 * r0[i1]) + sYl[1][ly] * (xl0 * r1[i0] + xl1 * r1[i1]);
