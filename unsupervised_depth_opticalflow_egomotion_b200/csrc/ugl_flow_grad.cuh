@@ -3,9 +3,16 @@
 // then an element-wise combine  grad = sum_k scale_k(sample, level) * basis_k  once the per-sample
 // normalisers (mean of the occlusion weights) and the upstream gradients are known.
 //
-// Why: the kernels are instruction-issue bound (profiles/), and the recompute scheme of ugl_flow_loss.cuh
-// executes the photometry and the SSIM moments twice (forward, then backward).  This variant executes them
+// Why: the kernels are bound by fp32 instruction issue and latency, not by HBM (profiles/), and the recompute scheme of
+// ugl_flow_loss.cuh executes the photometry and the SSIM moments twice (forward, then backward).  This variant executes them
 // once, trading 14 floats/pixel of extra HBM traffic (far from binding) for ~1/3 fewer instructions.
+//
+// The two warp directions of a pixel (.x = forward flow / right frame / frame 0, .y = backward flow / left frame / frame 1) travel
+// through every phase as ONE packed fp32 pair: sm_100a's FADD2 / FMUL2 / FFMA2 give two individually IEEE-rounded results per
+// instruction, so the fp32 instruction count halves while every rounding of the scalar formulation is kept (ugl_common.cuh:
+// add2 / mul2 / fma2 and the contraction-proof acc2_rn / sub2_rn).  Phase order per tile: phase 1 (photometry, halo 2) ->
+// per channel [phase 2 (SSIM windows -> coefficient pairs) -> phase 3 accumulate (box sums x Jacobian)] -> phase 3 store +
+// phase 4a (signed second differences) -> phase 4b (smoothness gather) -> block reduction.
 //
 // Basis planes per level, layout (B, 14, h, w):
 //   0,1  Gp_f  = w_f * sum_c sign(Wf_c - I_c) * keep * dWf_c/d(u,v)            x g_pix  / (3 hw den_f)
