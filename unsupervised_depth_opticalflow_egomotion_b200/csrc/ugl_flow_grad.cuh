@@ -150,6 +150,14 @@ UGL_HD TapC2 flow_tap_clamped2(int j, int i, float2 u, float2 v, const WarpGeom&
 
 struct DirectLoads { float uf, vf, ub, vb, I[3]; bool inside; };
 
+UGL_HD float ld_once(const float* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+
 // the coalesced (non-gather) loads of one halo pixel: issued one pixel ahead of use to overlap their latency
 template <int PW, int R>
 UGL_HD DirectLoads load_direct(const FlowLevelDesc& L, const TileCoord& tc, int idx, int& i, int& j) {
@@ -163,9 +171,10 @@ UGL_HD DirectLoads load_direct(const FlowLevelDesc& L, const TileCoord& tc, int 
     const float* ff = L.flow_f + (long)tc.b * 2 * plane;
     const float* fb = L.flow_b + (long)tc.b * 2 * plane;
     const float* ic = L.img + (long)tc.b * 3 * plane;
-    d.uf = ff[pix]; d.vf = ff[plane + pix];
-    d.ub = fb[pix]; d.vb = fb[plane + pix];
-    d.I[0] = ic[pix]; d.I[1] = ic[plane + pix]; d.I[2] = ic[2 * plane + pix];
+    // read once per CTA: bypass L1 so its 56 KB stay with the gather rows of the two resident CTAs
+    d.uf = ld_once(ff + pix); d.vf = ld_once(ff + plane + pix);
+    d.ub = ld_once(fb + pix); d.vb = ld_once(fb + plane + pix);
+    d.I[0] = ld_once(ic + pix); d.I[1] = ld_once(ic + plane + pix); d.I[2] = ld_once(ic + 2 * plane + pix);
   }
   return d;
 }
