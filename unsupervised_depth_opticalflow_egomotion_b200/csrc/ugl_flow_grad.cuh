@@ -227,8 +227,9 @@ UGL_HD void flow_photo_pixel_c(const FlowLevelDesc& L, int b, int i, int j, cons
 // shared-memory planes of the single-pass kernel (halo-2 tile).  x = I*w and y = W*w are stored pre-multiplied, and the two
 // warp directions of a pixel sit side by side as one float2 (.x = direction 0: forward flow / frame 0, .y = direction 1), the
 // operand form of the packed fp32 instructions (add2 / mul2 / fma2) the stencil phases run on.
-//   scalar planes: I (3), pre-scaled flows (4);  pair planes (2 floats per pixel): X[c], Y[c] (c = 0..2), W
-enum GradPlane { GP_I0 = 0, GP_UF = 3, GP_VF, GP_UB, GP_VB, GP_X2 = 7 /* pair planes X[c] at GP_X2 + 2c */, GP_Y2 = 13, GP_W2 = 19, GP_COUNT = 21 };
+//   scalar planes: I (3);  pair planes (2 floats per pixel): X[c], Y[c] (c = 0..2), W over the directions; the pre-scaled
+//   flows as (u, v) pairs per direction (the smoothness phases run on them)
+enum GradPlane { GP_I0 = 0, GP_F2 = 3 /* pair plane (u, v) / 20 of the forward flow */, GP_B2 = 5 /* of the backward flow */, GP_X2 = 7 /* pair planes X[c] at GP_X2 + 2c */, GP_Y2 = 13, GP_W2 = 19, GP_COUNT = 21 };
 
 template <int PN>
 UGL_HD void store_grad_planes(float* sm, int idx, const Photo& P, float uf, float vf, float ub, float vb) {
@@ -241,10 +242,8 @@ UGL_HD void store_grad_planes(float* sm, int idx, const Photo& P, float uf, floa
   }
   *reinterpret_cast<float2*>(sm + GP_W2 * PN + 2 * idx) = w2;
   constexpr float r20 = 1.0f / 20.0f;
-  sm[GP_UF * PN + idx] = div_c(uf, 20.0f, r20);
-  sm[GP_VF * PN + idx] = div_c(vf, 20.0f, r20);
-  sm[GP_UB * PN + idx] = div_c(ub, 20.0f, r20);
-  sm[GP_VB * PN + idx] = div_c(vb, 20.0f, r20);
+  *reinterpret_cast<float2*>(sm + GP_F2 * PN + 2 * idx) = div_c2(make_float2(uf, vf), 20.0f, r20);
+  *reinterpret_cast<float2*>(sm + GP_B2 * PN + 2 * idx) = div_c2(make_float2(ub, vb), 20.0f, r20);
 }
 
 struct FlowGradParams {
@@ -651,16 +650,21 @@ struct FlowGradTile {
       const float wx = sm[kOffEdge + idx], wy = sm[kOffEdge + CN + idx];      // zero where the centre does not exist
       const bool interior = (ly >= 1 && ly <= TH && lx >= 1 && lx <= TW) && (tc.y0 + ly - 1 < L.h) && (tc.x0 + lx - 1 < L.w);
 #pragma unroll
-      for (int f4 = 0; f4 < 4; ++f4) {
-        const float* f = sm + (GP_UF + f4) * PN + c0;
+      for (int d = 0; d < 2; ++d) {                    // forward / backward flow, (u, v) as one packed pair
+        const float* f = sm + (GP_F2 + 2 * d) * PN + 2 * c0;
         // the edge weight is 0 for centres whose neighbours fall outside the image, so the reads below stay inside the
         // halo-2 planes and contribute nothing there
-        const float dxx = second_diff(f, 1), dyy = second_diff(f, PW);
-        sm[kOffS4 + (2 * f4) * CN + idx] = wx * sgnf(dxx);
-        sm[kOffS4 + (2 * f4 + 1) * CN + idx] = wy * sgnf(dyy);
+        const float2 c = *reinterpret_cast<const float2*>(f);
+        const float2 xm = *reinterpret_cast<const float2*>(f - 2), xp = *reinterpret_cast<const float2*>(f + 2);
+        const float2 ym = *reinterpret_cast<const float2*>(f - 2 * PW), yp = *reinterpret_cast<const float2*>(f + 2 * PW);
+        const float2 dxx = sub2(sub2(xp, c), sub2(c, xm)), dyy = sub2(sub2(yp, c), sub2(c, ym));       // second_diff's order
+        *reinterpret_cast<float2*>(sm + kOffS4 + (2 * d) * 2 * CN + 2 * idx) = make_float2(wx * sgnf(dxx.x), wx * sgnf(dxx.y));
+        *reinterpret_cast<float2*>(sm + kOffS4 + (2 * d + 1) * 2 * CN + 2 * idx) = make_float2(wy * sgnf(dyy.x), wy * sgnf(dyy.y));
         if (interior) {
-          acc[f4 < 2 ? FA_SMX_F : FA_SMX_B] += wx * fabsf(dxx);
-          acc[f4 < 2 ? FA_SMY_F : FA_SMY_B] += wy * fabsf(dyy);
+          acc[d == 0 ? FA_SMX_F : FA_SMX_B] += wx * fabsf(dxx.x);
+          acc[d == 0 ? FA_SMY_F : FA_SMY_B] += wy * fabsf(dyy.x);
+          acc[d == 0 ? FA_SMX_F : FA_SMX_B] += wx * fabsf(dxx.y);
+          acc[d == 0 ? FA_SMY_F : FA_SMY_B] += wy * fabsf(dyy.y);
         }
       }
     }
@@ -670,22 +674,26 @@ struct FlowGradTile {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     const int plane = L.h * L.w;
     float* basis = gp.basis[tc.level] + (long)tc.b * kBasisPlanes * plane;
-    const float inx = fast_rcp(2.0f * (float)L.h * (float)(L.w - 2)), iny = fast_rcp(2.0f * (float)(L.h - 2) * (float)L.w);   // scales of a gradient basis: 1e-4 contract
+    // scales of a gradient basis: 1e-4 contract
+    const float2 inx = splat2(fast_rcp(2.0f * (float)L.h * (float)(L.w - 2))), iny = splat2(fast_rcp(2.0f * (float)(L.h - 2) * (float)L.w));
     for (int idx = tid; idx < TN; idx += nt) {
       const int ty = idx / TW, tx = idx - ty * TW;
       const int i = tc.y0 + ty, j = tc.x0 + tx;
       if (i >= L.h || j >= L.w) continue;
       const int q0 = (ty + 1) * CW + (tx + 1);
-      float g[4];
+      float2 g[2];
 #pragma unroll
-      for (int f4 = 0; f4 < 4; ++f4) {
-        const float* sx = sm + kOffS4 + (2 * f4) * CN + q0;
-        const float* sy = sm + kOffS4 + (2 * f4 + 1) * CN + q0;
-        g[f4] = (sx[-1] - 2.0f * sx[0] + sx[1]) * inx + (sy[-CW] - 2.0f * sy[0] + sy[CW]) * iny;
+      for (int d = 0; d < 2; ++d) {
+        const float* sx = sm + kOffS4 + (2 * d) * 2 * CN + 2 * q0;
+        const float* sy = sm + kOffS4 + (2 * d + 1) * 2 * CN + 2 * q0;
+        const float2 xc = *reinterpret_cast<const float2*>(sx), yc = *reinterpret_cast<const float2*>(sy);
+        const float2 gx = add2(fma2(xc, splat2(-2.0f), *reinterpret_cast<const float2*>(sx - 2)), *reinterpret_cast<const float2*>(sx + 2));
+        const float2 gy = add2(fma2(yc, splat2(-2.0f), *reinterpret_cast<const float2*>(sy - 2 * CW)), *reinterpret_cast<const float2*>(sy + 2 * CW));
+        g[d] = fma2(gy, iny, mul2(gx, inx));
       }
       const int pix = i * L.w + j;
-      basis[4 * plane + pix] = g[0]; basis[5 * plane + pix] = g[1];
-      basis[12 * plane + pix] = g[2]; basis[13 * plane + pix] = g[3];
+      basis[4 * plane + pix] = g[0].x; basis[5 * plane + pix] = g[0].y;
+      basis[12 * plane + pix] = g[1].x; basis[13 * plane + pix] = g[1].y;
     }
   }
 };
