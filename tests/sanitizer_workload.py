@@ -28,4 +28,9 @@ x = torch.rand(1, 8, 20, 30, device=dev, requires_grad=True); fl = (3 * torch.ra
 ops.warp_flow(x, fl, True).sum().backward()
 torch.cuda.synchronize(); print("sanitizer workload done")
 assert int(ops.selftest_packed_pairs(dev, blocks=2, windows_per_thread=4).sum()) == 0
+ops.frames_from_u8([(255 * torch.rand(2, 3, 40, 72, device=dev)).to(torch.uint8) for _ in range(3)])
+ops.DEPTH_PHOTO_SINGLE_PASS = False
+loss, _ = losses.DepthLoss(3, "live").forward_losses(t.img_l, t.img, t.img_r, d, dl, dr, pose, t.K)
+sum(v.mean() for v in loss.values()).backward()
+ops.DEPTH_PHOTO_SINGLE_PASS = True
 torch.cuda.synchronize(); print("sanitizer workload done (incl. packed-pair self-test)")
