@@ -81,6 +81,18 @@ int ugl_flow_loss_launches(int backward);
  * photometry / SSIM work executed once instead of twice; costs 14 floats per pixel of saved state. */
 #define UGL_FLOW_BASIS_PLANES 14
 int ugl_flow_loss_forward_grad(const UglFlowLossArgs* args);
+/* The single-pass forward exists in several internal forms with the same interface and the same results (tests cross-check
+ * them); ugl_flow_loss_forward_grad / ugl_geom_flow_forward_grad use UGL_SINGLE_PASS_SPLIT.
+ *   FUSED      one tile kernel: photometry on the tile + 2-pixel halo, then the stencils, all in shared memory (round-1 kernel)
+ *   SPLIT      photometry kernel (one thread per pixel, no halo) -> photometry planes in the workspace -> stencil kernel that
+ *              stages them with TMA (cp.async.bulk.tensor, zero fill outside the image) when every level's width is a
+ *              multiple of 4 and the bases are 16-byte aligned, with plain loads otherwise
+ *   SPLIT_PLAIN / SPLIT_TMA   force the staging form (SPLIT_TMA fails with UGL_EUNSUPPORTED where TMA is not possible) */
+#define UGL_SINGLE_PASS_FUSED 0
+#define UGL_SINGLE_PASS_SPLIT 1
+#define UGL_SINGLE_PASS_SPLIT_PLAIN 2
+#define UGL_SINGLE_PASS_SPLIT_TMA 3
+int ugl_flow_loss_forward_grad_ex(const UglFlowLossArgs* args, int32_t variant);
 int ugl_flow_loss_combine(const UglFlowLossArgs* args);
 
 /* ---------------------------------------------------------------------------------------------
@@ -112,6 +124,7 @@ typedef struct UglGeomFlowArgs {
   float alpha, beta;                           /* flow_consist_alpha / flow_consist_beta */
 } UglGeomFlowArgs;
 int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* args);
+int ugl_geom_flow_forward_grad_ex(const UglGeomFlowArgs* args, int32_t variant);   /* variant: UGL_SINGLE_PASS_* */
 int ugl_geom_flow_combine(const UglGeomFlowArgs* args);
 
 /* ---------------------------------------------------------------------------------------------

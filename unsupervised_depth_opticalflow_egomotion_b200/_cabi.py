@@ -13,6 +13,8 @@ MAX_LEVELS = 6
 FLOW_NSTATS = 12
 GEOM_NSTATS = 16
 FLOW_BASIS_PLANES = 14
+# internal forms of the single-pass forward (include/ugl.h: UGL_SINGLE_PASS_*)
+SINGLE_PASS_VARIANTS = {"fused": 0, "split": 1, "split_plain": 2, "split_tma": 3}
 DEPTH_BASIS_PLANES = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -144,8 +146,10 @@ SIGNATURES = {
     "ugl_depth_ssim_forward_grad": (C.c_int, [C.POINTER(UglDepthSsimArgs)]),
     "ugl_depth_ssim_combine": (C.c_int, [C.POINTER(UglDepthSsimArgs)]),
     "ugl_geom_flow_forward_grad": (C.c_int, [C.POINTER(UglGeomFlowArgs)]),
+    "ugl_geom_flow_forward_grad_ex": (C.c_int, [C.POINTER(UglGeomFlowArgs), C.c_int32]),
     "ugl_geom_flow_combine": (C.c_int, [C.POINTER(UglGeomFlowArgs)]),
     "ugl_flow_loss_forward_grad": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
+    "ugl_flow_loss_forward_grad_ex": (C.c_int, [C.POINTER(UglFlowLossArgs), C.c_int32]),
     "ugl_flow_loss_combine": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_image_pyramid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.POINTER(C.c_void_p), C.c_void_p]),

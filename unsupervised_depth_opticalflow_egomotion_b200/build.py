@@ -45,15 +45,43 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+OBJ_DIR = os.path.join(HERE, "build")
+
+
+def _headers():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+
+
+def _compile_one(src: str, obj: str, flags, verbose: bool) -> str:
+    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + list(flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode:
+        raise RuntimeError("nvcc failed on %s (exit %d)\n%s" % (os.path.basename(src), res.returncode, res.stdout + res.stderr))
+    return res.stdout + res.stderr
+
+
 def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = LIB) -> str:
+    """One object per translation unit (compiled in parallel, re-used while neither the source nor any header changed), then a
+    link.  ``extra_flags`` / a non-default ``out`` build into their own object directory."""
     if not force and out == LIB and not _stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode:
-        sys.stderr.write(res.stdout + res.stderr)
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = OBJ_DIR if (out == LIB and not extra_flags) else out + ".objs"
+    os.makedirs(obj_dir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append((src, obj))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        logs = list(pool.map(lambda j: _compile_one(j[0], j[1], extra_flags, verbose), jobs))
+    if verbose:
+        sys.stderr.write("".join(logs))
+    res = subprocess.run([_nvcc(), "-shared", "-o", out] + objs, capture_output=True, text=True)
     if res.returncode:
-        raise RuntimeError("nvcc failed (exit %d)" % res.returncode)
+        raise RuntimeError("link failed (exit %d)\n%s" % (res.returncode, res.stdout + res.stderr))
     return out
 
 

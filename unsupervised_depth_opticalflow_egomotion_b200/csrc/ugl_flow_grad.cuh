@@ -250,6 +250,7 @@ struct FlowGradParams {
   FlowLossParams base;
   float one = 1.0f;           // an opaque 1.0 for acc2_rn (ugl_common.cuh): keeps ptxas from contracting packed products into their sums
   float* basis[kMaxLevels];   // (B, 14, h, w) per level
+  float* scratch[kMaxLevels]; // split kernels (ugl_flow_split.cuh): (B, 10, h, w, 2) photometry pair planes per level
   // geom mode only (Model_geometry): in-kernel rigid flow -> dynamic mask, packed masks out
   const float* disp[kMaxLevels];          // (B,1,h,w) centre disparity
   const float* Kinv[kMaxLevels];          // (B,3,3)

@@ -3,6 +3,7 @@
 #include "ugl_flow_loss.cuh"
 #include "ugl_flow_grad.cuh"
 #include "ugl_host.cuh"
+#include "ugl_flow_split_host.cuh"
 
 namespace ugl {
 
@@ -292,18 +293,23 @@ static int build_params(const UglFlowLossArgs* a, bool backward, FlowLossParams&
 
 using namespace ugl;
 
-extern "C" uint64_t ugl_flow_loss_workspace_bytes(const UglFlowLossArgs* a) {
-  if (!a) return 0;
+// tile partials + [B][scales][4] level losses + B ticket counters (finalize scratch)
+static uint64_t flow_partials_bytes(const UglFlowLossArgs* a) {
   uint64_t tf = 0, tb = 0;   // only the shapes matter here; cover the forward and the single-pass tile shapes
   for (int l = 0; l < a->scales && l < UGL_MAX_LEVELS; ++l) {
     tf += (uint64_t)((a->width[l] + kFTW - 1) / kFTW) * ((a->height[l] + kFTH - 1) / kFTH) * a->batch;
     tb += (uint64_t)((a->width[l] + kBTW - 1) / kBTW) * ((a->height[l] + kBTH - 1) / kBTH) * a->batch;
   }
-  // tile partials + [B][scales][4] level losses + B ticket counters (finalize scratch)
   return (tf > tb ? tf : tb) * GA_COUNT * sizeof(float) + (uint64_t)a->batch * a->scales * 4 * sizeof(float) + (uint64_t)a->batch * sizeof(unsigned);
 }
 
-extern "C" int ugl_flow_loss_launches(int backward) { return backward ? 1 : 2; }
+// + the photometry planes the split single-pass kernels hand from the photometry kernel to the stencil kernel
+extern "C" uint64_t ugl_flow_loss_workspace_bytes(const UglFlowLossArgs* a) {
+  if (!a) return 0;
+  return flow_partials_bytes(a) + flow_split_scratch_bytes(a->height, a->width, a->scales, a->batch);
+}
+
+extern "C" int ugl_flow_loss_launches(int backward) { return backward ? 1 : 2; }   // recompute mode; single-pass: 3 forward (photometry, stencil, finalize), 1 combine
 
 extern "C" int ugl_flow_loss_forward(const UglFlowLossArgs* a) {
   FlowLossParams p;
@@ -323,11 +329,12 @@ extern "C" int ugl_flow_loss_forward(const UglFlowLossArgs* a) {
   return launch_finalize(p, st);
 }
 
-extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) {
+extern "C" int ugl_flow_loss_forward_grad_ex(const UglFlowLossArgs* a, int variant) {
   FlowGradParams gp;
   int rc = build_params<kBTW, kBTH>(a, false, gp.base);
   if (rc) return rc;
   if (!a->loss) return fail(UGL_EINVAL, "flow_loss_forward_grad: null loss");
+  if (variant < UGL_SINGLE_PASS_FUSED || variant > UGL_SINGLE_PASS_SPLIT_TMA) return fail(UGL_EINVAL, "flow_loss_forward_grad: unknown variant %d", variant);
   for (int l = 0; l < a->scales; ++l) {
     if (!a->basis[l]) return fail(UGL_EINVAL, "flow_loss_forward_grad: null basis pointer at level %d", l);
     if (reinterpret_cast<uintptr_t>(a->basis[l]) & 7u) return fail(UGL_EALIGN, "flow_loss_forward_grad: basis not 8-byte aligned");
@@ -336,6 +343,11 @@ extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) {
   if (!a->workspace || a->workspace_bytes < ugl_flow_loss_workspace_bytes(a))
     return fail(UGL_EWORKSPACE, "flow_loss_forward_grad: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  if (variant != UGL_SINGLE_PASS_FUSED) {
+    flow_split_assign_scratch(gp, static_cast<char*>(a->workspace) + flow_partials_bytes(a));
+    if ((rc = launch_flow_split<false>(gp, st, variant == UGL_SINGLE_PASS_SPLIT ? 1 : (variant == UGL_SINGLE_PASS_SPLIT_TMA ? 2 : 0)))) return rc;
+    return launch_finalize(gp.base, st);
+  }
   using Tile = FlowGradTile<kBTW, kBTH, kBNT>;
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
   static_assert(smem <= 227 * 1024, "single-pass tile does not fit in shared memory");
@@ -345,6 +357,8 @@ extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) {
   if ((rc = check_launch("flow_loss_fwdgrad_kernel"))) return rc;
   return launch_finalize(gp.base, st);
 }
+
+extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) { return ugl_flow_loss_forward_grad_ex(a, UGL_SINGLE_PASS_SPLIT); }
 
 // ---- geom mode (Model_geometry's flow branch) -----------------------------------------------------
 static int geom_params(const UglGeomFlowArgs* g, bool backward, FlowGradParams& gp) {
@@ -370,15 +384,21 @@ static int geom_params(const UglGeomFlowArgs* g, bool backward, FlowGradParams& 
   return UGL_OK;
 }
 
-extern "C" int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* g) {
+extern "C" int ugl_geom_flow_forward_grad_ex(const UglGeomFlowArgs* g, int variant) {
   FlowGradParams gp;
   int rc = geom_params(g, false, gp);
   if (rc) return rc;
   const UglFlowLossArgs* a = &g->flow;
   if (!a->loss) return fail(UGL_EINVAL, "geom_flow_forward_grad: null loss");
+  if (variant < UGL_SINGLE_PASS_FUSED || variant > UGL_SINGLE_PASS_SPLIT_TMA) return fail(UGL_EINVAL, "geom_flow_forward_grad: unknown variant %d", variant);
   if (!a->workspace || a->workspace_bytes < ugl_flow_loss_workspace_bytes(a))
     return fail(UGL_EWORKSPACE, "geom_flow_forward_grad: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  if (variant != UGL_SINGLE_PASS_FUSED) {
+    flow_split_assign_scratch(gp, static_cast<char*>(a->workspace) + flow_partials_bytes(a));
+    if ((rc = launch_flow_split<true>(gp, st, variant == UGL_SINGLE_PASS_SPLIT ? 1 : (variant == UGL_SINGLE_PASS_SPLIT_TMA ? 2 : 0)))) return rc;
+    return launch_finalize<kModeGeom>(gp.base, st);
+  }
   using Tile = FlowGradTile<kBTW, kBTH, kBNT, kModeGeom>;
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
   auto kern = flow_loss_fwdgrad_kernel<kBTW, kBTH, kBNT, kModeGeom>;
@@ -387,6 +407,8 @@ extern "C" int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* g) {
   if ((rc = check_launch("flow_loss_fwdgrad_kernel<geom>"))) return rc;
   return launch_finalize<kModeGeom>(gp.base, st);
 }
+
+extern "C" int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* g) { return ugl_geom_flow_forward_grad_ex(g, UGL_SINGLE_PASS_SPLIT); }
 
 extern "C" int ugl_geom_flow_combine(const UglGeomFlowArgs* g) {
   FlowGradParams gp;

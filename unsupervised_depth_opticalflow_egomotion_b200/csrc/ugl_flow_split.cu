@@ -1,0 +1,260 @@
+// CUDA kernels + host launchers of the split single-pass flow-mode / geom-mode loss (ugl_flow_split.cuh): photometry kernel ->
+// TMA-staged stencil kernel -> finalize (ugl_flow_loss.cu).  Called by ugl_flow_loss_forward_grad / ugl_geom_flow_forward_grad.
+#include <cuda.h>
+#include <string.h>
+
+#include "ugl_flow_split.cuh"
+#include "ugl_flow_split_host.cuh"
+
+namespace ugl {
+
+// ---- TMA / mbarrier primitives (PTX; sm_90+) --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  const uint32_t a = smem_u32(bar);
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+// generic-proxy accesses (the threads' loads / stores) before, async-proxy accesses (TMA writes) after
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one box of a rank-3 tensor (x = innermost element, y = row, z = plane) -> shared memory; out-of-range elements arrive as zeros
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- photometry kernel: one thread per pixel of the tile ----------------------------------------------------------------
+template <int TW, int TH, bool kGeom>
+__global__ void __launch_bounds__(TW* TH, kPhotoMinBlocks) flow_photo_kernel(const __grid_constant__ FlowGradParams gp) {
+  constexpr int NT = TW * TH;
+  static_assert(NT % 32 == 0, "whole warps");
+  using Px = FlowPhotoPixel<kGeom>;
+  constexpr int NA = Px::kAcc;
+  constexpr int ROW = kGeom ? (int)GA_COUNT : (int)FA_COUNT;
+  __shared__ float red[(NT / 32) * NA];
+  __shared__ float mats[kGeom ? 33 : 1];
+  int tile;
+  const TileCoord tc = decode_tile_2d<TW, TH>(gp.base, blockIdx.x, blockIdx.y, tile);
+  if (kGeom) {
+    if (threadIdx.x < 9) mats[threadIdx.x] = gp.Kinv[tc.level][tc.b * 9 + threadIdx.x];
+    else if (threadIdx.x < 21) mats[threadIdx.x] = gp.P[0][tc.level][tc.b * 12 + threadIdx.x - 9];
+    else if (threadIdx.x < 33) mats[threadIdx.x] = gp.P[1][tc.level][tc.b * 12 + threadIdx.x - 21];
+    __syncthreads();
+  }
+  const FlowLevelDesc& L = gp.base.lv[tc.level];
+  const int ty = threadIdx.x / TW, tx = threadIdx.x - ty * TW;
+  const int i = tc.y0 + ty, j = tc.x0 + tx;
+  float acc[NA];
+#pragma unroll
+  for (int k = 0; k < NA; ++k) acc[k] = 0.f;
+  if (i < L.h && j < L.w) Px::run(gp, tc.level, tc.b, i, j, acc, mats);
+  const float v = block_reduce_n<NT, NA>(acc, red);
+  if (threadIdx.x < NA) gp.base.partials[(long)tile * ROW + Px::column(threadIdx.x)] = v;
+}
+
+// ---- stencil kernel -------------------------------------------------------------------------------------------------------
+template <int TW, int TH, int NT, bool kGeom>
+__global__ void __launch_bounds__(NT, kStencilMinBlocks)
+flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_constant__ FlowTmaMaps tm) {
+  using Tile = FlowStencilTile<TW, TH, NT, kGeom>;
+  constexpr int NA = Tile::kAcc;
+  constexpr int ROW = kGeom ? (int)GA_COUNT : (int)FA_COUNT;
+  extern __shared__ float sm_raw[];
+  // TMA destinations must be 128-byte aligned.  The offset is added to the array (not to an integer) so the compiler keeps
+  // treating `sm` as a shared-memory pointer (LDS / STS instead of generic LD / ST).
+  float* sm = sm_raw + (((128u - (smem_u32(sm_raw) & 127u)) & 127u) >> 2);
+  __shared__ float red[(NT / 32) * NA];
+  __shared__ __align__(8) uint64_t bars[4];
+  int tile;
+  const TileCoord tc = decode_tile_2d<TW, TH>(gp.base, blockIdx.x, blockIdx.y, tile);
+  const int tid = threadIdx.x;
+  const bool kTma = tm.use_tma[tc.level] != 0;   // per level (CTA-uniform): TMA staging where the level's strides allow it
+
+  // copy group g (see FlowStencilTile::load_group_plain): issued by one thread, completion counted in bytes on bars[g]
+  auto issue = [&](int g) {
+    if (kTma) {
+      if (tid == 0) {
+        constexpr uint32_t kHaloPair = 2 * Tile::PN * 4, kHaloScal = Tile::SPN * 4, kTilePair = 2 * Tile::TN * 4;
+        fence_proxy_async();
+        const int x0 = tc.x0 - Tile::R, y0 = tc.y0 - Tile::R;   // pair planes: element 2 * x0 (16-byte aligned: x0 is even)
+        const int xs = x0 - Tile::kScalX;                         // scalar planes start two columns further left (16-byte aligned)
+        const int zs = tc.b * kPhotoPairs;
+        uint64_t* bar = &bars[g];
+        if (g == 0) {
+          mbar_expect_tx(bar, 2 * kHaloPair + 3 * kHaloScal + 2 * kTilePair);
+          tma_load_3d(sm + Tile::kOffW, &tm.scr_halo[tc.level], 2 * x0, y0, zs + PP_W, bar);
+          for (int c = 0; c < 3; ++c) tma_load_3d(sm + Tile::kOffI + c * Tile::kScalP, &tm.img[tc.level], xs, y0, tc.b * 3 + c, bar);
+        } else if (g < 3) {
+          mbar_expect_tx(bar, kHaloPair + 2 * kTilePair);
+        } else {
+          mbar_expect_tx(bar, 4 * kHaloScal);
+        }
+        if (g < 3) {
+          float* st = Tile::stage(sm, g);
+          tma_load_3d(st, &tm.scr_halo[tc.level], 2 * x0, y0, zs + PP_W0 + g, bar);
+          tma_load_3d(st + Tile::kPairP, &tm.scr_tile[tc.level], 2 * tc.x0, tc.y0, zs + PP_DW0 + 2 * g, bar);
+          tma_load_3d(st + Tile::kPairP + Tile::kPairT, &tm.scr_tile[tc.level], 2 * tc.x0, tc.y0, zs + PP_DW0 + 2 * g + 1, bar);
+        } else {
+          float* raw = sm + Tile::kOffRawFlow;
+          tma_load_3d(raw, &tm.flow_f[tc.level], xs, y0, tc.b * 2, bar);
+          tma_load_3d(raw + Tile::kScalP, &tm.flow_f[tc.level], xs, y0, tc.b * 2 + 1, bar);
+          tma_load_3d(raw + 2 * Tile::kScalP, &tm.flow_b[tc.level], xs, y0, tc.b * 2, bar);
+          tma_load_3d(raw + 3 * Tile::kScalP, &tm.flow_b[tc.level], xs, y0, tc.b * 2 + 1, bar);
+        }
+      }
+    } else {
+      Tile::load_group_plain(gp, tc, g, tid, NT, sm);
+    }
+  };
+  auto arrived = [&](int g) {
+    if (kTma) mbar_wait(&bars[g], 0);   // every barrier is used for exactly one phase
+  };
+
+  if (kTma) {
+    if (tid == 0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) mbar_init(&bars[g], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  issue(0);
+  issue(1);
+  float acc[NA];
+#pragma unroll
+  for (int k = 0; k < NA; ++k) acc[k] = 0.f;
+  float2 g3[Tile::kP3][4];
+#pragma unroll
+  for (int n = 0; n < Tile::kP3; ++n)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g3[n][k] = make_float2(0.f, 0.f);
+  if (!kTma) __syncthreads();
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    arrived(c);
+    Tile::convert_channel(c, tid, NT, sm);
+    __syncthreads();
+    Tile::phase2(gp, tc, c, tid, NT, sm, acc);
+    if (c == 0) Tile::phase2(gp, tc, 3, tid, NT, sm, acc);   // smoothness edge weights
+    __syncthreads();
+    Tile::phase3_accumulate(gp, tc, c, tid, NT, sm, g3);
+    __syncthreads();                   // ring slot c & 1, the x plane and the coefficient planes are free again
+    if (c < 2) issue(c + 2);           // channel 2 -> slot 0; the raw flow planes -> slot 1
+  }
+  Tile::phase3_store(gp, tc, tid, NT, g3);
+  arrived(3);
+  Tile::convert_flows(tid, NT, sm);
+  __syncthreads();
+  Tile::phase4a(gp, tc, tid, NT, sm, acc);
+  __syncthreads();
+  Tile::phase4b(gp, tc, tid, NT, sm);
+  const float v = block_reduce_n<NT, NA>(acc, red);
+  if (tid < NA) gp.base.partials[(long)tile * ROW + Tile::column(tid)] = v;
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  // resolved through the runtime (no link-time dependency on libcuda); the pointer is process-wide and immutable once set
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// rank-3 fp32 tensor (inner, rows, planes) with box (box_inner, box_rows, 1); zero fill outside
+static bool encode3(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t planes, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {inner, rows, planes};
+  const cuuint64_t strides[2] = {inner * 4, inner * rows * 4};
+  const cuuint32_t box[3] = {box_inner, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// TMA needs 16-byte aligned bases, 16-byte multiples for every global stride (scalar planes -> width % 4 == 0) and a box that starts on
+// a 16-byte boundary of its row (probed on B200: a start column of x0 - 2 floats raises `illegal instruction`; scratch/tma_probe.cu).
+// Decided per level; returns the number of levels staged by TMA.
+template <int TW, int TH, int NT, bool kGeom>
+static int build_tma_maps(const FlowGradParams& gp, FlowTmaMaps& tm) {
+  using Tile = FlowStencilTile<TW, TH, NT, kGeom>;
+  static_assert(2 * Tile::PW <= 256 && Tile::PH <= 256, "TMA box dimensions are limited to 256 elements");
+  const FlowLossParams& p = gp.base;
+  int n = 0;
+  for (int l = 0; l < p.scales; ++l) {
+    const FlowLevelDesc& L = p.lv[l];
+    tm.use_tma[l] = 0;
+    if ((L.w & 3) != 0) continue;
+    if (!aligned16(gp.scratch[l]) || !aligned16(L.img) || !aligned16(L.flow_f) || !aligned16(L.flow_b)) continue;
+    const uint64_t w = (uint64_t)L.w, h = (uint64_t)L.h, B = (uint64_t)p.B;
+    if (!encode3(&tm.scr_halo[l], gp.scratch[l], 2 * w, h, kPhotoPairs * B, 2 * Tile::PW, Tile::PH)) continue;
+    if (!encode3(&tm.scr_tile[l], gp.scratch[l], 2 * w, h, kPhotoPairs * B, 2 * TW, TH)) continue;
+    if (!encode3(&tm.img[l], L.img, w, h, 3 * B, Tile::SPW, Tile::PH)) continue;
+    if (!encode3(&tm.flow_f[l], L.flow_f, w, h, 2 * B, Tile::SPW, Tile::PH)) continue;
+    if (!encode3(&tm.flow_b[l], L.flow_b, w, h, 2 * B, Tile::SPW, Tile::PH)) continue;
+    tm.use_tma[l] = 1;
+    ++n;
+  }
+  return n;
+}
+
+uint64_t flow_split_scratch_bytes(const int32_t* height, const int32_t* width, int scales, int batch) {
+  uint64_t n = 0;
+  for (int l = 0; l < scales && l < kMaxLevels; ++l) {
+    n += ((uint64_t)batch * kPhotoFloats * height[l] * width[l] * sizeof(float) + 255) & ~(uint64_t)255;
+  }
+  return n + 256;
+}
+
+void flow_split_assign_scratch(FlowGradParams& gp, void* base) {
+  uintptr_t p = (reinterpret_cast<uintptr_t>(base) + 255) & ~(uintptr_t)255;
+  for (int l = 0; l < gp.base.scales; ++l) {
+    gp.scratch[l] = reinterpret_cast<float*>(p);
+    p += ((uint64_t)gp.base.B * kPhotoFloats * gp.base.lv[l].h * gp.base.lv[l].w * sizeof(float) + 255) & ~(uint64_t)255;
+  }
+}
+
+template <bool kGeom>
+int launch_flow_split(const FlowGradParams& gp, cudaStream_t st, int tma_mode) {
+  constexpr int TW = kBTW, TH = kBTH, NT = kSplitNT;
+  using Tile = FlowStencilTile<TW, TH, NT, kGeom>;
+  const dim3 grid(gp.base.total_tiles / gp.base.B, gp.base.B);
+  flow_photo_kernel<TW, TH, kGeom><<<grid, TW * TH, 0, st>>>(gp);
+  int rc = check_launch("flow_photo_kernel");
+  if (rc) return rc;
+  constexpr size_t smem = Tile::kSmemFloats * sizeof(float) + 128;
+  static_assert(smem <= 227 * 1024, "stencil tile does not fit in shared memory");
+  FlowTmaMaps tm;
+  memset(&tm, 0, sizeof(tm));
+  const int n_tma = tma_mode != 0 ? build_tma_maps<TW, TH, NT, kGeom>(gp, tm) : 0;
+  if (tma_mode == 2 && n_tma != gp.base.scales)
+    return fail(UGL_EUNSUPPORTED, "flow_loss: TMA staging requested but only %d of %d levels allow it (width %% 4, 16-byte alignment, driver entry point)",
+                n_tma, gp.base.scales);
+  auto kern = flow_stencil_kernel<TW, TH, NT, kGeom>;
+  if ((rc = opt_in_smem(kern, smem))) return rc;
+  kern<<<grid, NT, smem, st>>>(gp, tm);
+  return check_launch("flow_stencil_kernel");
+}
+
+template int launch_flow_split<false>(const FlowGradParams&, cudaStream_t, int);
+template int launch_flow_split<true>(const FlowGradParams&, cudaStream_t, int);
+
+}  // namespace ugl

@@ -1,0 +1,45 @@
+// Host-side interface of the split single-pass kernels (ugl_flow_split.cu) for the C-ABI translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ugl_flow_grad.cuh"
+#include "ugl_host.cuh"
+
+namespace ugl {
+
+#ifndef UGL_SPLIT_NT
+#define UGL_SPLIT_NT 256
+#endif
+#ifndef UGL_STENCIL_MINB
+#define UGL_STENCIL_MINB 3
+#endif
+#ifndef UGL_PHOTO_MINB
+#define UGL_PHOTO_MINB 2
+#endif
+constexpr int kSplitNT = UGL_SPLIT_NT;                 // threads per CTA of the stencil kernel
+constexpr int kStencilMinBlocks = UGL_STENCIL_MINB;    // resident CTAs per SM the register allocation aims at
+constexpr int kPhotoMinBlocks = UGL_PHOTO_MINB;
+
+#if defined(CUDA_VERSION) || defined(__cuda_cuda_h__)
+// tensor maps of the stencil kernel's TMA copies, one set per level (kernel parameter, __grid_constant__)
+struct FlowTmaMaps {
+  CUtensorMap scr_halo[kMaxLevels];   // photometry pair planes (2w, h, 10 B), box = tile + 2-pixel halo
+  CUtensorMap scr_tile[kMaxLevels];   // same tensor, box = tile
+  CUtensorMap img[kMaxLevels];        // centre frame (w, h, 3 B), halo box
+  CUtensorMap flow_f[kMaxLevels];     // (w, h, 2 B), halo box
+  CUtensorMap flow_b[kMaxLevels];
+  int use_tma[kMaxLevels];            // 0: this level is staged with plain loads (strides / alignment do not allow TMA)
+};
+#endif
+
+// bytes of the photometry planes for these levels (what ugl_*_workspace_bytes adds behind the tile partials)
+uint64_t flow_split_scratch_bytes(const int32_t* height, const int32_t* width, int scales, int batch);
+// gp.scratch[l] <- 256-byte aligned slices of `base`
+void flow_split_assign_scratch(FlowGradParams& gp, void* base);
+// photometry kernel + stencil kernel on `st`.  tma_mode: 0 = plain-load staging, 1 = TMA where the shapes allow it, 2 = TMA or fail
+template <bool kGeom>
+int launch_flow_split(const FlowGradParams& gp, cudaStream_t st, int tma_mode);
+
+}  // namespace ugl

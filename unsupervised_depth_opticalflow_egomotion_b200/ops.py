@@ -198,6 +198,15 @@ def cost_volume(input1: Tensor, input2: Tensor, d: int = 4) -> Tensor:
 # ================================================================================================
 FLOW_LOSS_KEYS = ("loss_flow_pixel", "loss_flow_ssim", "loss_flow_smooth", "loss_flow_consis")
 
+"""internal form of the single-pass forward (flow and geom modes): 'split' (photometry kernel + TMA-staged stencil kernel, the
+default), 'split_plain' / 'split_tma' (force the staging form), 'fused' (the one-kernel form).  Same results; a test / profiling knob."""
+SINGLE_PASS_VARIANT = "split"
+
+
+def _variant() -> int:
+    return _cabi.SINGLE_PASS_VARIANTS[SINGLE_PASS_VARIANT]
+
+
 
 def _flow_args(img_l, img, img_r, ff, fb, scales, loss, stats, ws, gloss=None, gf=None, gb=None, basis=None) -> _cabi.UglFlowLossArgs:
     a = _cabi.UglFlowLossArgs()
@@ -251,7 +260,7 @@ class _FlowLossFn(torch.autograd.Function):
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
         with torch.cuda.device_of(img[0]):
             if single:
-                _call("ugl_flow_loss_forward_grad", C.byref(a), launches=2)
+                _call("ugl_flow_loss_forward_grad_ex", C.byref(a), _variant(), launches=2 if SINGLE_PASS_VARIANT == "fused" else 3)
             else:
                 _call("ugl_flow_loss_forward", C.byref(a), launches=2)
         if single:
@@ -306,7 +315,7 @@ def flow_loss_step(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r
     with torch.cuda.device_of(img[0]):
         if out["basis"] is not None:
             if fwd:
-                _cabi.check(_cabi.lib().ugl_flow_loss_forward_grad(C.byref(a)), "ugl_flow_loss_forward_grad")
+                _cabi.check(_cabi.lib().ugl_flow_loss_forward_grad_ex(C.byref(a), _variant()), "ugl_flow_loss_forward_grad")
             if bwd:
                 _cabi.check(_cabi.lib().ugl_flow_loss_combine(C.byref(a)), "ugl_flow_loss_combine")
         else:
@@ -314,7 +323,7 @@ def flow_loss_step(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r
                 _cabi.check(_cabi.lib().ugl_flow_loss_forward(C.byref(a)), "ugl_flow_loss_forward")
             if bwd:
                 _cabi.check(_cabi.lib().ugl_flow_loss_backward(C.byref(a)), "ugl_flow_loss_backward")
-    _count((2 if fwd else 0) + (1 if bwd else 0))
+    _count(((3 if out["basis"] is not None and SINGLE_PASS_VARIANT != "fused" else 2) if fwd else 0) + (1 if bwd else 0))
     return out
 
 
@@ -382,7 +391,7 @@ class _GeomFlowLossFn(torch.autograd.Function):
         ws = torch.empty(max(int(_cabi.lib().ugl_flow_loss_workspace_bytes(C.byref(g.flow))) // 4, 1), device=dev, dtype=torch.float32)
         g.flow.workspace, g.flow.workspace_bytes = ws.data_ptr(), ws.numel() * 4
         with torch.cuda.device_of(img[0]):
-            _call("ugl_geom_flow_forward_grad", C.byref(g), launches=2)
+            _call("ugl_geom_flow_forward_grad_ex", C.byref(g), _variant(), launches=2 if SINGLE_PASS_VARIANT == "fused" else 3)
         ctx.save_for_backward(stats, *ts, *basis, *masks)
         ctx.S, ctx.L, ctx.ab = S, L, (alpha, beta)
         ctx.mark_non_differentiable(*masks)
