@@ -467,7 +467,7 @@ def main():
         stats_ms = {"fwd": [], "bwd": []}
         halves = {}
         for name in ("forward", "backward"):
-            fn = (lambda ph=name: ops.flow_loss_step(pl, pc, pr, ff, fb, wmat, LEVELS, out=state["out"], phase=ph))
+            fn = (lambda ph=name: state.__setitem__("out_sp", ops.flow_loss_step(pl, pc, pr, ff, fb, wmat, LEVELS, out=state.get("out_sp"), phase=ph, mode="single_pass")))
             if graph is not None:
                 gh = torch.cuda.CUDAGraph()
                 side = torch.cuda.Stream()

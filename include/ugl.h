@@ -93,6 +93,12 @@ int ugl_flow_loss_forward_grad(const UglFlowLossArgs* args);
 #define UGL_SINGLE_PASS_SPLIT_PLAIN 2
 #define UGL_SINGLE_PASS_SPLIT_TMA 3
 int ugl_flow_loss_forward_grad_ex(const UglFlowLossArgs* args, int32_t variant);
+/* Fused forward + backward for a training step, where the upstream gradient is known before the forward runs (train.py:211-215:
+ * d total / d loss_k[b] = w_k / B): loss (4,B) AND grad_flow_fwd/bwd[l] in four launches (photometry kernel, weight sums, stencil
+ * kernel, finalize).  The per-sample normalisers only depend on the photometry kernel's sums, so the stencil kernel scales and
+ * adds the four gradient terms itself: no basis planes (args->basis is ignored), no combine launch.  Same results as
+ * ugl_flow_loss_forward_grad + ugl_flow_loss_combine. */
+int ugl_flow_loss_step(const UglFlowLossArgs* args);
 int ugl_flow_loss_combine(const UglFlowLossArgs* args);
 
 /* ---------------------------------------------------------------------------------------------

@@ -150,6 +150,7 @@ SIGNATURES = {
     "ugl_geom_flow_combine": (C.c_int, [C.POINTER(UglGeomFlowArgs)]),
     "ugl_flow_loss_forward_grad": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_forward_grad_ex": (C.c_int, [C.POINTER(UglFlowLossArgs), C.c_int32]),
+    "ugl_flow_loss_step": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_combine": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_image_pyramid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.POINTER(C.c_void_p), C.c_void_p]),

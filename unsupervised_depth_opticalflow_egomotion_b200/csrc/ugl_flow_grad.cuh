@@ -251,6 +251,17 @@ struct FlowGradParams {
   float one = 1.0f;           // an opaque 1.0 for acc2_rn (ugl_common.cuh): keeps ptxas from contracting packed products into their sums
   float* basis[kMaxLevels];   // (B, 14, h, w) per level
   float* scratch[kMaxLevels]; // split kernels (ugl_flow_split.cuh): (B, 10, h, w, 2) photometry pair planes per level
+  // split kernels: the photometry kernel has its own tile grid (PhotoTiling) and its own partial-sum rows
+  struct PhotoTiling {
+    int tiles_x[kMaxLevels], tile_begin[kMaxLevels];   // tiles per row; first tile id of the level (ids ordered level, sample, ty, tx)
+    int per_img[kMaxLevels];                           // tiles per sample of the level
+    int per_sample;                                    // tiles of one sample over all levels (grid.x)
+    int nacc;                                          // floats per partial row
+    float* partials;                                   // [tiles][nacc]; nullptr: the stencil-tile rows hold every column (fused kernel)
+  } photo;
+  float* step_scales = nullptr;   // step mode: [B][scales][8] = FlowCombineScales of every (sample, level), written by flow_photo_norm_kernel
+  int step = 0;               // split kernels, fused forward + backward (ugl_flow_loss_step): 1 = the photometry kernel hands its L1 /
+                              // consistency gradient bases to the stencil kernel (3 more pair planes), which writes d loss / d flow itself
   // geom mode only (Model_geometry): in-kernel rigid flow -> dynamic mask, packed masks out
   const float* disp[kMaxLevels];          // (B,1,h,w) centre disparity
   const float* Kinv[kMaxLevels];          // (B,3,3)

@@ -3,6 +3,7 @@
 #include "ugl_flow_loss.cuh"
 #include "ugl_flow_grad.cuh"
 #include "ugl_host.cuh"
+#include "ugl_flow_split.cuh"
 #include "ugl_flow_split_host.cuh"
 
 namespace ugl {
@@ -38,7 +39,7 @@ constexpr int kFinThreads = 256;
 template <int kMode>
 __global__ void __launch_bounds__(kFinThreads)
 flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __restrict__ lvl_loss /* [B][scales][4] */,
-                          unsigned* __restrict__ tickets /* [B] */) {
+                          unsigned* __restrict__ tickets /* [B] */, const __grid_constant__ FlowGradParams::PhotoTiling pt) {
   constexpr int FA_COUNT = kMode == kModeFlow ? (int)ugl::FA_COUNT : (int)GA_COUNT;   // geom / depth modes carry four more sums
   __shared__ double red[kFinThreads / 32][FA_COUNT];
   __shared__ bool last;
@@ -49,9 +50,20 @@ flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __res
   double s[FA_COUNT];
 #pragma unroll
   for (int k = 0; k < FA_COUNT; ++k) s[k] = 0.0;
+  // split kernels: the photometry kernel's columns (L1 / weight / consistency sums) live in its own partial rows
+  using Px = FlowPhotoPixel<kMode == kModeGeom>;
+  const bool split = (kMode != kModeDepth) && pt.partials != nullptr;
   for (int t = threadIdx.x; t < per_img; t += kFinThreads) {
 #pragma unroll
-    for (int k = 0; k < FA_COUNT; ++k) s[k] += (double)base[(long)t * FA_COUNT + k];
+    for (int k = 0; k < FA_COUNT; ++k)
+      if (!(split && Px::is_photo_column(k))) s[k] += (double)base[(long)t * FA_COUNT + k];
+  }
+  if (split) {
+    const float* pb = pt.partials + ((long)pt.tile_begin[l] + (long)b * pt.per_img[l]) * Px::kAcc;
+    for (int t = threadIdx.x; t < pt.per_img[l]; t += kFinThreads) {
+#pragma unroll
+      for (int k = 0; k < Px::kAcc; ++k) s[Px::column(k)] += (double)pb[(long)t * Px::kAcc + k];
+    }
   }
 #pragma unroll
   for (int k = 0; k < FA_COUNT; ++k) {
@@ -90,13 +102,15 @@ flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __res
 }
 
 template <int kMode = kModeFlow>
-static int launch_finalize(const FlowLossParams& p, cudaStream_t st) {
+static int launch_finalize(const FlowLossParams& p, cudaStream_t st, const FlowGradParams::PhotoTiling* photo = nullptr) {
+  FlowGradParams::PhotoTiling pt;
+  if (photo) pt = *photo; else pt.partials = nullptr;
   // scratch behind the tile partials: [B][scales][4] level losses, then B ticket counters
   float* lvl_loss = p.partials + (size_t)p.total_tiles * (kMode == kModeFlow ? (int)FA_COUNT : (int)GA_COUNT);
   unsigned* tickets = reinterpret_cast<unsigned*>(lvl_loss + (size_t)p.B * p.scales * 4);
   const cudaError_t e = cudaMemsetAsync(tickets, 0, sizeof(unsigned) * p.B, st);
   if (e != cudaSuccess) return fail((int)e, "flow_loss finalize: memset: %s", cudaGetErrorString(e));
-  flow_loss_finalize_kernel<kMode><<<dim3(p.scales, p.B), kFinThreads, 0, st>>>(p, lvl_loss, tickets);
+  flow_loss_finalize_kernel<kMode><<<dim3(p.scales, p.B), kFinThreads, 0, st>>>(p, lvl_loss, tickets, pt);
   return check_launch("flow_loss_finalize_kernel");
 }
 
@@ -303,10 +317,17 @@ static uint64_t flow_partials_bytes(const UglFlowLossArgs* a) {
   return (tf > tb ? tf : tb) * GA_COUNT * sizeof(float) + (uint64_t)a->batch * a->scales * 4 * sizeof(float) + (uint64_t)a->batch * sizeof(unsigned);
 }
 
+// workspace layout: [tile partials, level losses, tickets] [photometry-kernel partial rows, 256-byte aligned] [photometry planes]
+static char* split_photo_partials(const UglFlowLossArgs* a) {
+  const uintptr_t p = reinterpret_cast<uintptr_t>(a->workspace) + flow_partials_bytes(a);
+  return reinterpret_cast<char*>((p + 255) & ~(uintptr_t)255);
+}
+
 // + the photometry planes the split single-pass kernels hand from the photometry kernel to the stencil kernel
 extern "C" uint64_t ugl_flow_loss_workspace_bytes(const UglFlowLossArgs* a) {
   if (!a) return 0;
-  return flow_partials_bytes(a) + flow_split_scratch_bytes(a->height, a->width, a->scales, a->batch);
+  return flow_partials_bytes(a) + 256 + flow_split_photo_partials_bytes(a->height, a->width, a->scales, a->batch) +
+         flow_split_scratch_bytes(a->height, a->width, a->scales, a->batch);
 }
 
 extern "C" int ugl_flow_loss_launches(int backward) { return backward ? 1 : 2; }   // recompute mode; single-pass: 3 forward (photometry, stencil, finalize), 1 combine
@@ -344,9 +365,10 @@ extern "C" int ugl_flow_loss_forward_grad_ex(const UglFlowLossArgs* a, int varia
     return fail(UGL_EWORKSPACE, "flow_loss_forward_grad: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   if (variant != UGL_SINGLE_PASS_FUSED) {
-    flow_split_assign_scratch(gp, static_cast<char*>(a->workspace) + flow_partials_bytes(a));
-    if ((rc = launch_flow_split<false>(gp, st, variant == UGL_SINGLE_PASS_SPLIT ? 1 : (variant == UGL_SINGLE_PASS_SPLIT_TMA ? 2 : 0)))) return rc;
-    return launch_finalize(gp.base, st);
+    char* pp = split_photo_partials(a);
+    flow_split_assign_scratch(gp, pp + flow_split_photo_partials_bytes(a->height, a->width, a->scales, a->batch));
+    if ((rc = launch_flow_split<false>(gp, pp, st, variant == UGL_SINGLE_PASS_SPLIT ? 1 : (variant == UGL_SINGLE_PASS_SPLIT_TMA ? 2 : 0)))) return rc;
+    return launch_finalize(gp.base, st, &gp.photo);
   }
   using Tile = FlowGradTile<kBTW, kBTH, kBNT>;
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float);
@@ -359,6 +381,26 @@ extern "C" int ugl_flow_loss_forward_grad_ex(const UglFlowLossArgs* a, int varia
 }
 
 extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) { return ugl_flow_loss_forward_grad_ex(a, UGL_SINGLE_PASS_SPLIT); }
+
+// fused forward + backward for a known upstream gradient: photometry kernel -> weight sums -> stencil kernel (writes the flow gradients)
+// -> finalize (losses).  No basis planes, no combine launch.
+extern "C" int ugl_flow_loss_step(const UglFlowLossArgs* a) {
+  FlowGradParams gp;
+  int rc = build_params<kBTW, kBTH>(a, true, gp.base);
+  if (rc) return rc;
+  if (!a->loss || !a->grad_loss) return fail(UGL_EINVAL, "flow_loss_step: null loss / grad_loss");
+  if (!a->workspace || a->workspace_bytes < ugl_flow_loss_workspace_bytes(a))
+    return fail(UGL_EWORKSPACE, "flow_loss_step: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
+  for (int l = 0; l < a->scales; ++l)
+    if ((reinterpret_cast<uintptr_t>(a->grad_flow_fwd[l]) | reinterpret_cast<uintptr_t>(a->grad_flow_bwd[l])) & 7u)
+      return fail(UGL_EALIGN, "flow_loss_step: grad_flow not 8-byte aligned at level %d", l);
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  gp.step = 1;
+  char* pp = split_photo_partials(a);
+  flow_split_assign_scratch(gp, pp + flow_split_photo_partials_bytes(a->height, a->width, a->scales, a->batch));
+  if ((rc = launch_flow_split<false>(gp, pp, st, 1))) return rc;
+  return launch_finalize(gp.base, st, &gp.photo);
+}
 
 // ---- geom mode (Model_geometry's flow branch) -----------------------------------------------------
 static int geom_params(const UglGeomFlowArgs* g, bool backward, FlowGradParams& gp) {
@@ -395,9 +437,10 @@ extern "C" int ugl_geom_flow_forward_grad_ex(const UglGeomFlowArgs* g, int varia
     return fail(UGL_EWORKSPACE, "geom_flow_forward_grad: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   if (variant != UGL_SINGLE_PASS_FUSED) {
-    flow_split_assign_scratch(gp, static_cast<char*>(a->workspace) + flow_partials_bytes(a));
-    if ((rc = launch_flow_split<true>(gp, st, variant == UGL_SINGLE_PASS_SPLIT ? 1 : (variant == UGL_SINGLE_PASS_SPLIT_TMA ? 2 : 0)))) return rc;
-    return launch_finalize<kModeGeom>(gp.base, st);
+    char* pp = split_photo_partials(a);
+    flow_split_assign_scratch(gp, pp + flow_split_photo_partials_bytes(a->height, a->width, a->scales, a->batch));
+    if ((rc = launch_flow_split<true>(gp, pp, st, variant == UGL_SINGLE_PASS_SPLIT ? 1 : (variant == UGL_SINGLE_PASS_SPLIT_TMA ? 2 : 0)))) return rc;
+    return launch_finalize<kModeGeom>(gp.base, st, &gp.photo);
   }
   using Tile = FlowGradTile<kBTW, kBTH, kBNT, kModeGeom>;
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float);

@@ -32,39 +32,104 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
-// ---- photometry kernel: one thread per pixel of the tile ----------------------------------------------------------------
-template <int TW, int TH, bool kGeom>
-__global__ void __launch_bounds__(TW* TH, kPhotoMinBlocks) flow_photo_kernel(const __grid_constant__ FlowGradParams gp) {
-  constexpr int NT = TW * TH;
-  static_assert(NT % 32 == 0, "whole warps");
+// ---- photometry kernel: one thread per pixel ------------------------------------------------------------------------------
+// Own tile grid (kPhotoTW x kPhotoTH pixels per CTA, independent of the stencil tiles).  A warp covers a kPatchW x kPatchH
+// patch, not a 32 x 1 row segment: the gathers of a warp then fall into a compact window of the source frame (the flow varies
+// less across 8 x 4 pixels than along 32), fewer distinct 32-byte sectors per request; the coalesced loads / stores of a
+// patch row are still whole sectors (8 floats = 32 bytes, 8 pairs = 64 bytes).
+// A CTA of NT threads covers its TW x TH tile in TH / PASS_H passes of TW x PASS_H pixels, top to bottom: consecutive passes gather
+// from overlapping rows of the source frames (L1 reuse), the coalesced loads of pass k + 1 are in flight under the work of pass k,
+// and the tile's sums are reduced once.
+template <int TW, int TH, int NT, int PW_, int PH_, bool kGeom>
+__global__ void __launch_bounds__(NT, kPhotoMinBlocks) flow_photo_kernel(const __grid_constant__ FlowGradParams gp) {
+  constexpr int PASS_H = NT / TW;
+  static_assert(NT % 32 == 0 && PW_ * PH_ == 32 && TW % PW_ == 0 && PASS_H % PH_ == 0 && TH % PASS_H == 0 && PASS_H * TW == NT,
+                "whole warps, one patch per warp, whole passes");
   using Px = FlowPhotoPixel<kGeom>;
   constexpr int NA = Px::kAcc;
-  constexpr int ROW = kGeom ? (int)GA_COUNT : (int)FA_COUNT;
   __shared__ float red[(NT / 32) * NA];
   __shared__ float mats[kGeom ? 33 : 1];
-  int tile;
-  const TileCoord tc = decode_tile_2d<TW, TH>(gp.base, blockIdx.x, blockIdx.y, tile);
+  // tile decode: blockIdx.x counts this sample's photometry tiles over all levels
+  int r = blockIdx.x, lv = 0;
+  while (lv + 1 < gp.base.scales && r >= gp.photo.per_img[lv]) { r -= gp.photo.per_img[lv]; ++lv; }
+  const int b = blockIdx.y;
+  const int tile = gp.photo.tile_begin[lv] + b * gp.photo.per_img[lv] + r;
+  const int tyi = r / gp.photo.tiles_x[lv], txi = r - tyi * gp.photo.tiles_x[lv];
   if (kGeom) {
-    if (threadIdx.x < 9) mats[threadIdx.x] = gp.Kinv[tc.level][tc.b * 9 + threadIdx.x];
-    else if (threadIdx.x < 21) mats[threadIdx.x] = gp.P[0][tc.level][tc.b * 12 + threadIdx.x - 9];
-    else if (threadIdx.x < 33) mats[threadIdx.x] = gp.P[1][tc.level][tc.b * 12 + threadIdx.x - 21];
+    if (threadIdx.x < 9) mats[threadIdx.x] = gp.Kinv[lv][b * 9 + threadIdx.x];
+    else if (threadIdx.x < 21) mats[threadIdx.x] = gp.P[0][lv][b * 12 + threadIdx.x - 9];
+    else if (threadIdx.x < 33) mats[threadIdx.x] = gp.P[1][lv][b * 12 + threadIdx.x - 21];
     __syncthreads();
   }
-  const FlowLevelDesc& L = gp.base.lv[tc.level];
-  const int ty = threadIdx.x / TW, tx = threadIdx.x - ty * TW;
-  const int i = tc.y0 + ty, j = tc.x0 + tx;
+  const FlowLevelDesc& L = gp.base.lv[lv];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int PPR = TW / PW_;                      // patches per tile row
+  const int py = warp / PPR, px = warp - py * PPR;
+  const int ly = lane / PW_, lx = lane - ly * PW_;
+  const int i0 = tyi * TH + py * PH_ + ly, j = txi * TW + px * PW_ + lx;
   float acc[NA];
 #pragma unroll
   for (int k = 0; k < NA; ++k) acc[k] = 0.f;
-  if (i < L.h && j < L.w) Px::run(gp, tc.level, tc.b, i, j, acc, mats);
+  DirectLoads cur = {};
+  if (i0 < L.h && j < L.w) cur = Px::load(gp, lv, b, i0, j);
+#pragma unroll 1
+  for (int pass = 0; pass < TH / PASS_H; ++pass) {
+    const int i = i0 + pass * PASS_H;
+    DirectLoads nxt = cur;
+    if (pass + 1 < TH / PASS_H && i + PASS_H < L.h && j < L.w) nxt = Px::load(gp, lv, b, i + PASS_H, j);
+    if (i < L.h && j < L.w) Px::run(gp, lv, b, i, j, cur, acc, mats);
+    cur = nxt;
+  }
   const float v = block_reduce_n<NT, NA>(acc, red);
-  if (threadIdx.x < NA) gp.base.partials[(long)tile * ROW + Px::column(threadIdx.x)] = v;
+  if (threadIdx.x < NA) gp.photo.partials[(long)tile * NA + threadIdx.x] = v;
 }
 
 // ---- stencil kernel -------------------------------------------------------------------------------------------------------
-template <int TW, int TH, int NT, bool kGeom>
+// ---- step mode: the photometry kernel's weight sums -> stats columns, before the stencil kernel needs the normalisers ----------
+// Same summation order as flow_loss_finalize_kernel (ugl_flow_loss.cu), which later rewrites the same columns with the same bits.
+template <bool kGeom>
+__global__ void __launch_bounds__(256) flow_photo_norm_kernel(const __grid_constant__ FlowGradParams gp) {
+  using Px = FlowPhotoPixel<kGeom>;
+  constexpr int NA = Px::kAcc;
+  constexpr int ROW = kGeom ? (int)GA_COUNT : (int)FA_COUNT;
+  __shared__ double red[256 / 32][NA];
+  const int l = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* pb = gp.photo.partials + ((long)gp.photo.tile_begin[l] + (long)b * gp.photo.per_img[l]) * NA;
+  double s[NA];
+#pragma unroll
+  for (int k = 0; k < NA; ++k) s[k] = 0.0;
+  for (int t = threadIdx.x; t < gp.photo.per_img[l]; t += 256) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) s[k] += (double)pb[(long)t * NA + k];
+  }
+#pragma unroll
+  for (int k = 0; k < NA; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_down_sync(0xffffffffu, s[k], o);
+    if (lane == 0) red[warp][k] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < NA) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 256 / 32; ++w) v += red[w][threadIdx.x];
+    gp.base.stats[((long)b * gp.base.scales + l) * ROW + Px::column(threadIdx.x)] = (float)v;
+  }
+  if (!kGeom && gp.step_scales) {   // the closing divisions once per (sample, level) instead of once per stencil thread
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const FlowLevelDesc& L = gp.base.lv[l];
+      const FlowCombineScales k = flow_combine_scales(gp.base.stats + ((long)b * gp.base.scales + l) * FA_COUNT, L.h, L.w, gp.base.gloss, gp.base.B, b);
+      float* o = gp.step_scales + ((long)b * gp.base.scales + l) * 8;
+      o[0] = k.pix[0]; o[1] = k.pix[1]; o[2] = k.ssim[0]; o[3] = k.ssim[1]; o[4] = k.sm; o[5] = k.cons; o[6] = 0.f; o[7] = 0.f;
+    }
+  }
+}
+
+template <int TW, int TH, int NT, bool kGeom, bool kStep>
 __global__ void __launch_bounds__(NT, kStencilMinBlocks)
 flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_constant__ FlowTmaMaps tm) {
+  static_assert(!(kStep && kGeom), "the fused step exists for the flow mode only");
   using Tile = FlowStencilTile<TW, TH, NT, kGeom>;
   constexpr int NA = Tile::kAcc;
   constexpr int ROW = kGeom ? (int)GA_COUNT : (int)FA_COUNT;
@@ -83,15 +148,15 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
   auto issue = [&](int g) {
     if (kTma) {
       if (tid == 0) {
-        constexpr uint32_t kHaloPair = 2 * Tile::PN * 4, kHaloScal = Tile::SPN * 4, kTilePair = 2 * Tile::TN * 4;
+        constexpr uint32_t kHaloPair = 2 * Tile::SPN * 4, kHaloScal = Tile::SPN * 4, kTilePair = 2 * Tile::TN * 4;
         fence_proxy_async();
-        const int x0 = tc.x0 - Tile::R, y0 = tc.y0 - Tile::R;   // pair planes: element 2 * x0 (16-byte aligned: x0 is even)
-        const int xs = x0 - Tile::kScalX;                         // scalar planes start two columns further left (16-byte aligned)
+        const int y0 = tc.y0 - Tile::R;
+        const int xs = tc.x0 - Tile::R - Tile::kScalX;           // halo planes start at column x0 - 4 (16-byte aligned rows of the box)
         const int zs = tc.b * kPhotoPairs;
         uint64_t* bar = &bars[g];
         if (g == 0) {
           mbar_expect_tx(bar, 2 * kHaloPair + 3 * kHaloScal + 2 * kTilePair);
-          tma_load_3d(sm + Tile::kOffW, &tm.scr_halo[tc.level], 2 * x0, y0, zs + PP_W, bar);
+          tma_load_3d(sm + Tile::kOffW, &tm.scr_halo[tc.level], 2 * xs, y0, zs + PP_W, bar);
           for (int c = 0; c < 3; ++c) tma_load_3d(sm + Tile::kOffI + c * Tile::kScalP, &tm.img[tc.level], xs, y0, tc.b * 3 + c, bar);
         } else if (g < 3) {
           mbar_expect_tx(bar, kHaloPair + 2 * kTilePair);
@@ -100,7 +165,7 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
         }
         if (g < 3) {
           float* st = Tile::stage(sm, g);
-          tma_load_3d(st, &tm.scr_halo[tc.level], 2 * x0, y0, zs + PP_W0 + g, bar);
+          tma_load_3d(st, &tm.scr_halo[tc.level], 2 * xs, y0, zs + PP_W0 + g, bar);
           tma_load_3d(st + Tile::kPairP, &tm.scr_tile[tc.level], 2 * tc.x0, tc.y0, zs + PP_DW0 + 2 * g, bar);
           tma_load_3d(st + Tile::kPairP + Tile::kPairT, &tm.scr_tile[tc.level], 2 * tc.x0, tc.y0, zs + PP_DW0 + 2 * g + 1, bar);
         } else {
@@ -150,13 +215,23 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
     __syncthreads();                   // ring slot c & 1, the x plane and the coefficient planes are free again
     if (c < 2) issue(c + 2);           // channel 2 -> slot 0; the raw flow planes -> slot 1
   }
-  Tile::phase3_store(gp, tc, tid, NT, g3);
+  float4 pre[kStep ? Tile::kP3 : 1][3];
+  if (kStep) Tile::prefetch_step(gp, tc, tid, NT, pre);   // in flight under the smoothness phases
+  else Tile::phase3_store(gp, tc, tid, NT, g3);
   arrived(3);
   Tile::convert_flows(tid, NT, sm);
   __syncthreads();
   Tile::phase4a(gp, tc, tid, NT, sm, acc);
   __syncthreads();
-  Tile::phase4b(gp, tc, tid, NT, sm);
+  if (kStep) {
+    const float4* ks = reinterpret_cast<const float4*>(gp.step_scales + ((long)tc.b * gp.base.scales + tc.level) * 8);
+    const float4 k0 = __ldg(ks), k1 = __ldg(ks + 1);
+    FlowCombineScales k;
+    k.pix[0] = k0.x; k.pix[1] = k0.y; k.ssim[0] = k0.z; k.ssim[1] = k0.w; k.sm = k1.x; k.cons = k1.y;
+    Tile::phase4b_step(gp, tc, k, tid, NT, sm, g3, pre);
+  } else {
+    Tile::phase4b(gp, tc, tid, NT, sm);
+  }
   const float v = block_reduce_n<NT, NA>(acc, red);
   if (tid < NA) gp.base.partials[(long)tile * ROW + Tile::column(tid)] = v;
 }
@@ -196,7 +271,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 template <int TW, int TH, int NT, bool kGeom>
 static int build_tma_maps(const FlowGradParams& gp, FlowTmaMaps& tm) {
   using Tile = FlowStencilTile<TW, TH, NT, kGeom>;
-  static_assert(2 * Tile::PW <= 256 && Tile::PH <= 256, "TMA box dimensions are limited to 256 elements");
+  static_assert(2 * Tile::SPW <= 256 && Tile::PH <= 256, "TMA box dimensions are limited to 256 elements");
   const FlowLossParams& p = gp.base;
   int n = 0;
   for (int l = 0; l < p.scales; ++l) {
@@ -205,7 +280,7 @@ static int build_tma_maps(const FlowGradParams& gp, FlowTmaMaps& tm) {
     if ((L.w & 3) != 0) continue;
     if (!aligned16(gp.scratch[l]) || !aligned16(L.img) || !aligned16(L.flow_f) || !aligned16(L.flow_b)) continue;
     const uint64_t w = (uint64_t)L.w, h = (uint64_t)L.h, B = (uint64_t)p.B;
-    if (!encode3(&tm.scr_halo[l], gp.scratch[l], 2 * w, h, kPhotoPairs * B, 2 * Tile::PW, Tile::PH)) continue;
+    if (!encode3(&tm.scr_halo[l], gp.scratch[l], 2 * w, h, kPhotoPairs * B, 2 * Tile::SPW, Tile::PH)) continue;
     if (!encode3(&tm.scr_tile[l], gp.scratch[l], 2 * w, h, kPhotoPairs * B, 2 * TW, TH)) continue;
     if (!encode3(&tm.img[l], L.img, w, h, 3 * B, Tile::SPW, Tile::PH)) continue;
     if (!encode3(&tm.flow_f[l], L.flow_f, w, h, 2 * B, Tile::SPW, Tile::PH)) continue;
@@ -232,29 +307,68 @@ void flow_split_assign_scratch(FlowGradParams& gp, void* base) {
   }
 }
 
+uint64_t flow_split_photo_partials_bytes(const int32_t* height, const int32_t* width, int scales, int batch) {
+  uint64_t tiles = 0;
+  for (int l = 0; l < scales && l < kMaxLevels; ++l)
+    tiles += (uint64_t)((width[l] + kPhotoTW - 1) / kPhotoTW) * ((height[l] + kPhotoTH - 1) / kPhotoTH) * batch;
+  // + [B][scales][8] step-mode scale factors in front of the rows
+  return (((uint64_t)batch * scales * 8 * sizeof(float) + 255) & ~(uint64_t)255) + (((tiles * 10 * sizeof(float)) + 255) & ~(uint64_t)255);
+}
+
+// fills gp.photo (tiling + partial rows at `partials`)
 template <bool kGeom>
-int launch_flow_split(const FlowGradParams& gp, cudaStream_t st, int tma_mode) {
+static void assign_photo_tiling(FlowGradParams& gp, void* partials) {
+  int tiles = 0, per_sample = 0;
+  for (int l = 0; l < gp.base.scales; ++l) {
+    const FlowLevelDesc& L = gp.base.lv[l];
+    const int tx = (L.w + kPhotoTW - 1) / kPhotoTW, ty = (L.h + kPhotoTH - 1) / kPhotoTH;
+    gp.photo.tiles_x[l] = tx;
+    gp.photo.per_img[l] = tx * ty;
+    gp.photo.tile_begin[l] = tiles;
+    tiles += tx * ty * gp.base.B;
+    per_sample += tx * ty;
+  }
+  gp.photo.per_sample = per_sample;
+  gp.photo.nacc = FlowPhotoPixel<kGeom>::kAcc;
+  gp.step_scales = static_cast<float*>(partials);
+  gp.photo.partials = reinterpret_cast<float*>(static_cast<char*>(partials) + (((uint64_t)gp.base.B * gp.base.scales * 8 * sizeof(float) + 255) & ~(uint64_t)255));
+}
+
+template <bool kGeom>
+int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st, int tma_mode) {
   constexpr int TW = kBTW, TH = kBTH, NT = kSplitNT;
   using Tile = FlowStencilTile<TW, TH, NT, kGeom>;
+  assign_photo_tiling<kGeom>(gp, photo_partials);
   const dim3 grid(gp.base.total_tiles / gp.base.B, gp.base.B);
-  flow_photo_kernel<TW, TH, kGeom><<<grid, TW * TH, 0, st>>>(gp);
+  flow_photo_kernel<kPhotoTW, kPhotoTH, kPhotoNT, kPatchW, kPatchH, kGeom><<<dim3(gp.photo.per_sample, gp.base.B), kPhotoNT, 0, st>>>(gp);
   int rc = check_launch("flow_photo_kernel");
   if (rc) return rc;
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float) + 128;
   static_assert(smem <= 227 * 1024, "stencil tile does not fit in shared memory");
+  if (gp.step) {
+    flow_photo_norm_kernel<kGeom><<<dim3(gp.base.scales, gp.base.B), 256, 0, st>>>(gp);
+    if ((rc = check_launch("flow_photo_norm_kernel"))) return rc;
+  }
   FlowTmaMaps tm;
   memset(&tm, 0, sizeof(tm));
   const int n_tma = tma_mode != 0 ? build_tma_maps<TW, TH, NT, kGeom>(gp, tm) : 0;
   if (tma_mode == 2 && n_tma != gp.base.scales)
     return fail(UGL_EUNSUPPORTED, "flow_loss: TMA staging requested but only %d of %d levels allow it (width %% 4, 16-byte alignment, driver entry point)",
                 n_tma, gp.base.scales);
-  auto kern = flow_stencil_kernel<TW, TH, NT, kGeom>;
-  if ((rc = opt_in_smem(kern, smem))) return rc;
-  kern<<<grid, NT, smem, st>>>(gp, tm);
+  if (gp.step) {
+    if (kGeom) return fail(UGL_EUNSUPPORTED, "flow_loss_step: flow mode only");
+    auto kern = flow_stencil_kernel<TW, TH, NT, false, true>;
+    if ((rc = opt_in_smem(kern, smem))) return rc;
+    kern<<<grid, NT, smem, st>>>(gp, tm);
+  } else {
+    auto kern = flow_stencil_kernel<TW, TH, NT, kGeom, false>;
+    if ((rc = opt_in_smem(kern, smem))) return rc;
+    kern<<<grid, NT, smem, st>>>(gp, tm);
+  }
   return check_launch("flow_stencil_kernel");
 }
 
-template int launch_flow_split<false>(const FlowGradParams&, cudaStream_t, int);
-template int launch_flow_split<true>(const FlowGradParams&, cudaStream_t, int);
+template int launch_flow_split<false>(FlowGradParams&, void*, cudaStream_t, int);
+template int launch_flow_split<true>(FlowGradParams&, void*, cudaStream_t, int);
 
 }  // namespace ugl

@@ -26,9 +26,11 @@
 
 namespace ugl {
 
-constexpr int kPhotoPairs = 10;          // pair planes per sample and level: w, W[0..2], wdW[2c+uv] (c = 0..2, uv = 0,1)
+// pair planes per sample and level: w, W[0..2], wdW[2c+uv] (c = 0..2, uv = 0,1); step mode only: the L1 basis (Gp_u, Gp_v as
+// (fwd, bwd) pairs) and the consistency basis (u, v)
+constexpr int kPhotoPairs = 13;
 constexpr int kPhotoFloats = 2 * kPhotoPairs;
-enum PhotoPair { PP_W = 0, PP_W0 = 1, PP_DW0 = 4 };
+enum PhotoPair { PP_W = 0, PP_W0 = 1, PP_DW0 = 4, PP_GPU = 10, PP_GPV = 11, PP_GC = 12 };
 
 // ---- photometry kernel: one pixel -----------------------------------------------------------------------------------
 // acc slots of the photometry kernel (subset of FlowAcc / GeomAcc written by this kernel; the stencil kernel writes the rest
@@ -42,20 +44,29 @@ struct FlowPhotoPixel {
     return k < 6 ? flow_cols[k] : (int)GA_PIXD_F + (k - 6);
   }
 
+  static UGL_HD bool is_photo_column(int col) {
+    return col == FA_PIX_F || col == FA_W_F || col == FA_PIX_B || col == FA_W_B || col == FA_CONS || col == FA_CONS_W || (kGeom && col >= (int)GA_PIXD_F);
+  }
+
   // pixel (i, j) of sample b, level lv; mats (geom mode): K^-1 (9), P_bwd (12), P_fwd (12)
-  static UGL_HD void run(const FlowGradParams& gp, int lv, int b, int i, int j, float* acc, const float* mats) {
+  // the coalesced loads of pixel (i, j): issued one pass ahead of their use by the kernel's loop
+  static UGL_HD DirectLoads load(const FlowGradParams& gp, int lv, int b, int i, int j) {
     const FlowLevelDesc& L = gp.base.lv[lv];
     const int plane = L.h * L.w, pix = i * L.w + j;
     DirectLoads d;
-    {
-      const float* ff = L.flow_f + (long)b * 2 * plane;
-      const float* fb = L.flow_b + (long)b * 2 * plane;
-      const float* ic = L.img + (long)b * 3 * plane;
-      d.inside = true;
-      d.uf = ld_once(ff + pix); d.vf = ld_once(ff + plane + pix);
-      d.ub = ld_once(fb + pix); d.vb = ld_once(fb + plane + pix);
-      d.I[0] = ic[pix]; d.I[1] = ic[plane + pix]; d.I[2] = ic[2 * plane + pix];   // re-read by the stencil kernel: keep in L2
-    }
+    const float* ff = L.flow_f + (long)b * 2 * plane;
+    const float* fb = L.flow_b + (long)b * 2 * plane;
+    const float* ic = L.img + (long)b * 3 * plane;
+    d.inside = true;
+    d.uf = ld_once(ff + pix); d.vf = ld_once(ff + plane + pix);
+    d.ub = ld_once(fb + pix); d.vb = ld_once(fb + plane + pix);
+    d.I[0] = ic[pix]; d.I[1] = ic[plane + pix]; d.I[2] = ic[2 * plane + pix];   // re-read by the stencil kernel: keep in L2
+    return d;
+  }
+
+  static UGL_HD void run(const FlowGradParams& gp, int lv, int b, int i, int j, const DirectLoads& d, float* acc, const float* mats) {
+    const FlowLevelDesc& L = gp.base.lv[lv];
+    const int plane = L.h * L.w, pix = i * L.w + j;
     Photo P;
     float dW[12];
     flow_photo_pixel_c<true, kGeom>(L, b, i, j, d, P, dW);
@@ -69,7 +80,7 @@ struct FlowPhotoPixel {
 #pragma unroll
     for (int k = 0; k < 6; ++k) *reinterpret_cast<float2*>(scr + (PP_DW0 + k) * pp) = mul2(make_float2(dW[k], dW[6 + k]), w2);
     // L1 basis: w * sum_c sign(W_c - I_c) * keep * dW_c/d(u,v)
-    float* basis = gp.basis[lv] + (long)b * kBasisPlanes * plane;
+    float gpu[2], gpv[2];
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
       float su = 0.f, sv = 0.f;
@@ -80,8 +91,16 @@ struct FlowPhotoPixel {
         sv += sg * dW[6 * dir + 2 * c + 1];
       }
       const float w = dir == 0 ? P.w_f : P.w_b;
-      basis[(8 * dir + 0) * (long)plane + pix] = su * w;
-      basis[(8 * dir + 1) * (long)plane + pix] = sv * w;
+      gpu[dir] = su * w;
+      gpv[dir] = sv * w;
+    }
+    float* basis = gp.step ? nullptr : gp.basis[lv] + (long)b * kBasisPlanes * plane;
+    if (gp.step) {
+      *reinterpret_cast<float2*>(scr + PP_GPU * pp) = make_float2(gpu[0], gpu[1]);
+      *reinterpret_cast<float2*>(scr + PP_GPV * pp) = make_float2(gpv[0], gpv[1]);
+    } else {
+      basis[0 * (long)plane + pix] = gpu[0]; basis[1 * (long)plane + pix] = gpv[0];
+      basis[8 * (long)plane + pix] = gpu[1]; basis[9 * (long)plane + pix] = gpv[1];
     }
     float om;   // mask of the direction-consistency term: 1 - w_f (flow mode) / 1 - occ_f (geom mode)
     if (kGeom) {
@@ -114,8 +133,13 @@ struct FlowPhotoPixel {
     const float su = sgnf(cu) * om, sv = sgnf(cv) * om;
     const float gn = -(su * uf + sv * vf) * inf_ * inf_;
     const float ir = rf > 0.f ? fast_div(1.0f, rf) : 0.f;
-    basis[6 * (long)plane + pix] = su * inf_ + gn * uf * ir;
-    basis[7 * (long)plane + pix] = sv * inf_ + gn * vf * ir;
+    const float gcu = su * inf_ + gn * uf * ir, gcv = sv * inf_ + gn * vf * ir;
+    if (gp.step) {
+      *reinterpret_cast<float2*>(scr + PP_GC * pp) = make_float2(gcu, gcv);
+    } else {
+      basis[6 * (long)plane + pix] = gcu;
+      basis[7 * (long)plane + pix] = gcv;
+    }
   }
 };
 
@@ -137,12 +161,13 @@ struct FlowStencilTile {
   static constexpr int PW = TW + 2 * R, PH = TH + 2 * R, PN = PW * PH;
   static constexpr int CW = TW + 2, CH = TH + 2, CN = CW * CH;
   static constexpr int TN = TW * TH;
-  // scalar (one float per pixel) halo planes: a TMA box must start on a 16-byte boundary of the global row, and column
-  // x0 - 2 of a 4-byte element is not one, so these planes are staged from column x0 - 4 with a row pitch of TW + 8; the
-  // halo-2 pixel (ly, lx) sits at ly * SPW + lx + kScalX
+  // Halo planes: a TMA box must start on a 16-byte boundary of the global row, and column x0 - 2 of a 4-byte element is not
+  // one, so every halo plane (scalar and pair alike: one index for all of them) is staged from column x0 - 4 with a row
+  // pitch of SPW = TW + 8 pixels; the halo-2 pixel (ly, lx) sits at hp(ly, lx) = ly * SPW + lx + kScalX
   static constexpr int SPW = TW + 8, SPN = SPW * PH, kScalX = 2;
+  static UGL_HD int hp(int ly, int lx) { return ly * SPW + lx + kScalX; }
   static constexpr int pad32(int n) { return (n + 31) & ~31; }
-  static constexpr int kPairP = pad32(2 * PN), kScalP = pad32(SPN), kPairC = pad32(2 * CN), kScalC = pad32(CN), kPairT = pad32(2 * TN);
+  static constexpr int kPairP = pad32(2 * SPN), kScalP = pad32(SPN), kPairC = pad32(2 * CN), kScalC = pad32(CN), kPairT = pad32(2 * TN);
   static constexpr int kOffW = 0;
   static constexpr int kOffI = kOffW + kPairP;
   static constexpr int kOffStage = kOffI + 3 * kScalP;
@@ -156,7 +181,7 @@ struct FlowStencilTile {
   static constexpr int kOffS4 = kOffX;                            // 4 pair planes of signed weights (halo 1)
   static_assert(4 * kScalP <= kStage && 2 * kPairP <= kStage, "flow planes must fit a ring slot");
   static_assert(4 * kPairC <= kPairP + 3 * kPairC, "phase-4 planes must fit over the x + coefficient planes");
-  static_assert(PW % 2 == 0 && CW % 2 == 0, "pair planes are read as float4 (two pixels x two directions)");
+  static_assert(SPW % 2 == 0 && kScalX % 2 == 0 && CW % 2 == 0, "pair planes are read as float4 (two pixels x two directions)");
   static constexpr int kAcc = 6;                                  // SSIM_F, SSIM_B, SMX_F, SMY_F, SMX_B, SMY_B
   static UGL_HD int column(int k) { return (int)FA_SSIM_F + k; }
   static_assert(FA_SSIM_B == FA_SSIM_F + 1 && FA_SMX_F == FA_SSIM_F + 2 && FA_SMY_B == FA_SSIM_F + 5, "stencil sums are contiguous columns");
@@ -166,9 +191,9 @@ struct FlowStencilTile {
 
   // ---- plain-load staging (levels whose width does not allow TMA strides; also the host emulator) ----
   static UGL_HD void load_pair_halo(float* dst, const float* src /* (h, w, 2) */, const FlowLevelDesc& L, const TileCoord& tc, int tid, int nt) {
-    for (int idx = tid; idx < PN; idx += nt) {
-      const int ly = idx / PW, lx = idx - ly * PW;
-      const int i = tc.y0 - R + ly, j = tc.x0 - R + lx;
+    for (int idx = tid; idx < SPN; idx += nt) {
+      const int ly = idx / SPW, lx = idx - ly * SPW;
+      const int i = tc.y0 - R + ly, j = tc.x0 - R - kScalX + lx;
       float2 v = make_float2(0.f, 0.f);
       if (i >= 0 && i < L.h && j >= 0 && j < L.w) v = *reinterpret_cast<const float2*>(src + 2 * ((long)i * L.w + j));
       *reinterpret_cast<float2*>(dst + 2 * idx) = v;
@@ -218,23 +243,24 @@ struct FlowStencilTile {
   static UGL_HD void convert_channel(int c, int tid, int nt, float* sm) {
     float* yp = stage(sm, c);
     const float* ip = sm + kOffI + c * kScalP;
-    for (int idx = tid; idx < PN; idx += nt) {
-      const int ly = idx / PW, lx = idx - ly * PW;
-      const float2 w2 = *reinterpret_cast<const float2*>(sm + kOffW + 2 * idx);
-      const float2 W2 = *reinterpret_cast<const float2*>(yp + 2 * idx);
-      *reinterpret_cast<float2*>(sm + kOffX + 2 * idx) = mul2(splat2(ip[ly * SPW + lx + kScalX]), w2);
-      *reinterpret_cast<float2*>(yp + 2 * idx) = mul2(W2, w2);
+    static_assert(SPN % 2 == 0, "two pixels per iteration");
+    for (int idx = 2 * tid; idx < SPN; idx += 2 * nt) {      // flat over the staged planes (same index in all of them)
+      const float4 w4 = *reinterpret_cast<const float4*>(sm + kOffW + 2 * idx);
+      const float4 W4 = *reinterpret_cast<const float4*>(yp + 2 * idx);
+      const float2 I2 = *reinterpret_cast<const float2*>(ip + idx);
+      const float2 xa = mul2(splat2(I2.x), lo2(w4)), xb = mul2(splat2(I2.y), hi2(w4));
+      const float2 ya = mul2(lo2(W4), lo2(w4)), yb = mul2(hi2(W4), hi2(w4));
+      *reinterpret_cast<float4*>(sm + kOffX + 2 * idx) = make_float4(xa.x, xa.y, xb.x, xb.y);
+      *reinterpret_cast<float4*>(yp + 2 * idx) = make_float4(ya.x, ya.y, yb.x, yb.y);
     }
   }
   // raw flow planes (slot 1) -> (u, v) / 20 pair planes of both flows (slot 0): `flow / 20.0` of model_flow.py:177
   static UGL_HD void convert_flows(int tid, int nt, float* sm) {
     constexpr float r20 = 1.0f / 20.0f;
     const float* raw = sm + kOffRawFlow;
-    for (int idx = tid; idx < PN; idx += nt) {
-      const int ly = idx / PW, lx = idx - ly * PW;
-      const int q = ly * SPW + lx + kScalX;
-      *reinterpret_cast<float2*>(sm + kOffF2 + 2 * idx) = div_c2(make_float2(raw[q], raw[kScalP + q]), 20.0f, r20);
-      *reinterpret_cast<float2*>(sm + kOffF2 + kPairP + 2 * idx) = div_c2(make_float2(raw[2 * kScalP + q], raw[3 * kScalP + q]), 20.0f, r20);
+    for (int idx = tid; idx < SPN; idx += nt) {
+      *reinterpret_cast<float2*>(sm + kOffF2 + 2 * idx) = div_c2(make_float2(raw[idx], raw[kScalP + idx]), 20.0f, r20);
+      *reinterpret_cast<float2*>(sm + kOffF2 + kPairP + 2 * idx) = div_c2(make_float2(raw[2 * kScalP + idx], raw[3 * kScalP + idx]), 20.0f, r20);
     }
   }
 
@@ -249,7 +275,7 @@ struct FlowStencilTile {
     for (int s = tid; s < NS; s += nt) {
       const int ly = s / SW, lx = (s - ly * SW) * 2;
       const int i = tc.y0 - 1 + ly, j0 = tc.x0 - 1 + lx;
-      const int c0 = (ly + 1) * PW + (lx + 1);
+      const int c0 = hp(ly + 1, lx + 1);                    // staged-plane index of the left centre
       const bool row_in = (i >= 0 && i < L.h);
       const bool in0 = row_in && j0 >= 0 && j0 < L.w, in1 = row_in && j0 + 1 >= 0 && j0 + 1 < L.w;
       if (c < 3) {
@@ -258,7 +284,7 @@ struct FlowStencilTile {
         Moments2 m[2];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          const int o = 2 * (r - 1) * PW;
+          const int o = 2 * (r - 1) * SPW;
           const float4 xa = *reinterpret_cast<const float4*>(xpl + o), xb = *reinterpret_cast<const float4*>(xpl + o + 4);
           const float4 ya = *reinterpret_cast<const float4*>(ypl + o), yb = *reinterpret_cast<const float4*>(ypl + o + 4);
           const float2 x[4] = {lo2(xa), hi2(xa), lo2(xb), hi2(xb)}, y[4] = {lo2(ya), hi2(ya), lo2(yb), hi2(yb)};
@@ -299,7 +325,7 @@ struct FlowStencilTile {
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
           if (o == 0 ? in0 : in1) {
-            const int cc = (ly + 1) * SPW + (lx + 1) + kScalX + o, j = j0 + o;   // scalar-plane index of this centre
+            const int cc = c0 + o, j = j0 + o;
             const float Ic[3] = {I0[cc], I1[cc], I2[cc]};
             if (j >= 1 && j <= L.w - 2) {
               const float Iq[3] = {I0[cc + 1], I1[cc + 1], I2[cc + 1]};
@@ -330,7 +356,7 @@ struct FlowStencilTile {
     for (int s = tid; s < SW * TH; s += nt, ++n) {
       const int ty = s / SW, tx = (s - ty * SW) * 2;
       if (tc.y0 + ty >= L.h || tc.x0 + tx >= L.w) continue;
-      const int c0 = (ty + R) * PW + (tx + R);
+      const int c0 = hp(ty + R, tx + R);
       const int q0 = (ty + 1) * CW + (tx + 1);
       const int t0 = ty * TW + tx;
       float2 sum[3][2];
@@ -397,7 +423,7 @@ struct FlowStencilTile {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     for (int idx = tid; idx < CN; idx += nt) {
       const int ly = idx / CW, lx = idx - ly * CW;
-      const int c0 = (ly + 1) * PW + (lx + 1);
+      const int c0 = hp(ly + 1, lx + 1);
       const float wx = sm[kOffEdge + idx], wy = sm[kOffEdge + kScalC + idx];
       const bool interior = (ly >= 1 && ly <= TH && lx >= 1 && lx <= TW) && (tc.y0 + ly - 1 < L.h) && (tc.x0 + lx - 1 < L.w);
 #pragma unroll
@@ -405,7 +431,7 @@ struct FlowStencilTile {
         const float* f = sm + kOffF2 + d * kPairP + 2 * c0;
         const float2 c = *reinterpret_cast<const float2*>(f);
         const float2 xm = *reinterpret_cast<const float2*>(f - 2), xp = *reinterpret_cast<const float2*>(f + 2);
-        const float2 ym = *reinterpret_cast<const float2*>(f - 2 * PW), yp = *reinterpret_cast<const float2*>(f + 2 * PW);
+        const float2 ym = *reinterpret_cast<const float2*>(f - 2 * SPW), yp = *reinterpret_cast<const float2*>(f + 2 * SPW);
         const float2 dxx = sub2(sub2(xp, c), sub2(c, xm)), dyy = sub2(sub2(yp, c), sub2(c, ym));
         *reinterpret_cast<float2*>(sm + kOffS4 + (2 * d) * kPairC + 2 * idx) = make_float2(wx * sgnf(dxx.x), wx * sgnf(dxx.y));
         *reinterpret_cast<float2*>(sm + kOffS4 + (2 * d + 1) * kPairC + 2 * idx) = make_float2(wy * sgnf(dyy.x), wy * sgnf(dyy.y));
@@ -415,6 +441,85 @@ struct FlowStencilTile {
           acc[2 + 2 * d] += wx * fabsf(dxx.y);
           acc[3 + 2 * d] += wy * fabsf(dyy.y);
         }
+      }
+    }
+  }
+
+  // ---- fused forward + backward (step mode): the per-sample normalisers are known before this kernel starts (the photometry
+  // kernel's weight sums), so the strips' owners combine the four gradient terms themselves and write d loss / d flow: no basis
+  // planes, no combine launch.  pre[n][0..2]: the strip's L1 basis (u), L1 basis (v) as (fwd, bwd) pairs of its two pixels and
+  // the consistency basis (u, v) of its two pixels, loaded from the photometry planes before phase 4a.
+  static UGL_HD void prefetch_step(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, float4 (*pre)[3]) {
+    const FlowLevelDesc& L = gp.base.lv[tc.level];
+    const long plane = (long)L.h * L.w;
+    const float* scr = gp.scratch[tc.level] + (long)tc.b * kPhotoFloats * plane;
+    constexpr int SW = TW / 2;
+    int n = 0;
+    for (int s = tid; s < SW * TH; s += nt, ++n) {
+      const int ty = s / SW, tx = (s - ty * SW) * 2;
+      const int i = tc.y0 + ty, j = tc.x0 + tx;
+      if (i >= L.h || j >= L.w) continue;
+      const long pix = (long)i * L.w + j;
+      const bool two = j + 1 < L.w;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float* q = scr + (PP_GPU + k) * 2 * plane + 2 * pix;
+        if (two && (L.w & 1) == 0) {
+          pre[n][k] = *reinterpret_cast<const float4*>(q);           // pix even, plane base 16-byte aligned
+        } else {
+          const float2 a = *reinterpret_cast<const float2*>(q);
+          const float2 c = two ? *reinterpret_cast<const float2*>(q + 2) : make_float2(0.f, 0.f);
+          pre[n][k] = make_float4(a.x, a.y, c.x, c.y);
+        }
+      }
+    }
+  }
+
+  static UGL_HD void phase4b_step(const FlowGradParams& gp, const TileCoord& tc, const FlowCombineScales& k, int tid, int nt, const float* sm,
+                                  const float2 (*g)[4], const float4 (*pre)[3]) {
+    const FlowLevelDesc& L = gp.base.lv[tc.level];
+    const long plane = (long)L.h * L.w;
+    float* gf = L.gflow_f + (long)tc.b * 2 * plane;
+    float* gb = L.gflow_b + (long)tc.b * 2 * plane;
+    const float2 inx = splat2(fast_rcp(2.0f * (float)L.h * (float)(L.w - 2))), iny = splat2(fast_rcp(2.0f * (float)(L.h - 2) * (float)L.w));
+    constexpr int SW = TW / 2;
+    const bool vec = (L.w & 1) == 0;
+    int n = 0;
+    for (int s = tid; s < SW * TH; s += nt, ++n) {
+      const int ty = s / SW, tx = (s - ty * SW) * 2;
+      const int i = tc.y0 + ty, j = tc.x0 + tx;
+      if (i >= L.h || j >= L.w) continue;
+      float o_fu[2], o_fv[2], o_bu[2], o_bv[2];
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const int q0 = (ty + 1) * CW + (tx + o + 1);
+        float2 gm[2];
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const float* sx = sm + kOffS4 + (2 * d) * kPairC + 2 * q0;
+          const float* sy = sm + kOffS4 + (2 * d + 1) * kPairC + 2 * q0;
+          const float2 xc = *reinterpret_cast<const float2*>(sx), yc = *reinterpret_cast<const float2*>(sy);
+          const float2 gx = add2(fma2(xc, splat2(-2.0f), *reinterpret_cast<const float2*>(sx - 2)), *reinterpret_cast<const float2*>(sx + 2));
+          const float2 gy = add2(fma2(yc, splat2(-2.0f), *reinterpret_cast<const float2*>(sy - 2 * CW)), *reinterpret_cast<const float2*>(sy + 2 * CW));
+          gm[d] = fma2(gy, iny, mul2(gx, inx));
+        }
+        const float2 gpu = o == 0 ? lo2(pre[n][0]) : hi2(pre[n][0]), gpv = o == 0 ? lo2(pre[n][1]) : hi2(pre[n][1]);
+        const float2 gc = o == 0 ? lo2(pre[n][2]) : hi2(pre[n][2]);
+        const float2 gsu = g[n][o], gsv = g[n][2 + o];
+        o_fu[o] = k.pix[0] * gpu.x + k.ssim[0] * gsu.x + k.sm * gm[0].x + k.cons * gc.x;
+        o_fv[o] = k.pix[0] * gpv.x + k.ssim[0] * gsv.x + k.sm * gm[0].y + k.cons * gc.y;
+        o_bu[o] = k.pix[1] * gpu.y + k.ssim[1] * gsu.y + k.sm * gm[1].x;
+        o_bv[o] = k.pix[1] * gpv.y + k.ssim[1] * gsv.y + k.sm * gm[1].y;
+      }
+      const long pix = (long)i * L.w + j;
+      if (vec) {
+        *reinterpret_cast<float2*>(gf + pix) = make_float2(o_fu[0], o_fu[1]);
+        *reinterpret_cast<float2*>(gf + plane + pix) = make_float2(o_fv[0], o_fv[1]);
+        *reinterpret_cast<float2*>(gb + pix) = make_float2(o_bu[0], o_bu[1]);
+        *reinterpret_cast<float2*>(gb + plane + pix) = make_float2(o_bv[0], o_bv[1]);
+      } else {
+        gf[pix] = o_fu[0]; gf[plane + pix] = o_fv[0]; gb[pix] = o_bu[0]; gb[plane + pix] = o_bv[0];
+        if (j + 1 < L.w) { gf[pix + 1] = o_fu[1]; gf[plane + pix + 1] = o_fv[1]; gb[pix + 1] = o_bu[1]; gb[plane + pix + 1] = o_bv[1]; }
       }
     }
   }

@@ -16,11 +16,26 @@ namespace ugl {
 #define UGL_STENCIL_MINB 3
 #endif
 #ifndef UGL_PHOTO_MINB
-#define UGL_PHOTO_MINB 2
+#define UGL_PHOTO_MINB 3
 #endif
 constexpr int kSplitNT = UGL_SPLIT_NT;                 // threads per CTA of the stencil kernel
 constexpr int kStencilMinBlocks = UGL_STENCIL_MINB;    // resident CTAs per SM the register allocation aims at
 constexpr int kPhotoMinBlocks = UGL_PHOTO_MINB;
+#ifndef UGL_PHOTO_TW
+#define UGL_PHOTO_TW 32
+#endif
+#ifndef UGL_PHOTO_TH
+#define UGL_PHOTO_TH 32
+#endif
+#ifndef UGL_PHOTO_NT
+#define UGL_PHOTO_NT 256
+#endif
+#ifndef UGL_PATCH_W
+#define UGL_PATCH_W 8
+#endif
+constexpr int kPhotoTW = UGL_PHOTO_TW, kPhotoTH = UGL_PHOTO_TH;   // tile of a photometry-kernel CTA
+constexpr int kPhotoNT = UGL_PHOTO_NT;                            // its threads: one pixel each per pass (tile height / (NT / width) passes)
+constexpr int kPatchW = UGL_PATCH_W, kPatchH = 32 / UGL_PATCH_W;  // pixels a warp covers
 
 #if defined(CUDA_VERSION) || defined(__cuda_cuda_h__)
 // tensor maps of the stencil kernel's TMA copies, one set per level (kernel parameter, __grid_constant__)
@@ -38,8 +53,11 @@ struct FlowTmaMaps {
 uint64_t flow_split_scratch_bytes(const int32_t* height, const int32_t* width, int scales, int batch);
 // gp.scratch[l] <- 256-byte aligned slices of `base`
 void flow_split_assign_scratch(FlowGradParams& gp, void* base);
-// photometry kernel + stencil kernel on `st`.  tma_mode: 0 = plain-load staging, 1 = TMA where the shapes allow it, 2 = TMA or fail
+// bytes of the photometry kernel's partial-sum rows
+uint64_t flow_split_photo_partials_bytes(const int32_t* height, const int32_t* width, int scales, int batch);
+// photometry kernel + stencil kernel on `st`; fills gp.photo (the finalize kernel reads it).
+// tma_mode: 0 = plain-load staging, 1 = TMA where the shapes allow it, 2 = TMA or fail
 template <bool kGeom>
-int launch_flow_split(const FlowGradParams& gp, cudaStream_t st, int tma_mode);
+int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st, int tma_mode);
 
 }  // namespace ugl

@@ -289,12 +289,15 @@ class _FlowLossFn(torch.autograd.Function):
 
 def flow_loss_step(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r_pyr: Sequence[Tensor],
                    flows_fwd: Sequence[Tensor], flows_bwd: Sequence[Tensor], grad_loss: Tensor,
-                   num_scales: Optional[int] = None, out: Optional[dict] = None, mode: str = "single_pass", phase: str = "both"):
+                   num_scales: Optional[int] = None, out: Optional[dict] = None, mode: str = "fused_step", phase: str = "both"):
     """Forward + backward of the fused flow-mode loss in one call, without the autograd engine: for
     the training step where the upstream gradient is known up front (``train.py:211-215``:
-    ``d total / d loss_k[b] = w_k / B``).  Returns ``(loss (4,B), grads_fwd, grads_bwd)``; pass the
-    previous result as ``out`` to reuse its buffers (CUDA-graph friendly: 3 kernel launches, no
-    allocation)."""
+    ``d total / d loss_k[b] = w_k / B``).  Returns ``{'loss': (4,B), 'gf': [...], 'gb': [...], ...}``; pass the
+    previous result as ``out`` to reuse its buffers (CUDA-graph friendly: no allocation).
+
+    ``mode='fused_step'`` (default): ``ugl_flow_loss_step`` -- photometry kernel, weight sums, stencil kernel writing the
+    flow gradients, finalize: 4 launches, nothing saved per pixel.  ``'single_pass'``: forward_grad + combine through the
+    14 basis planes (what autograd uses, 4 launches).  ``'recompute'``: forward, finalize, recompute backward."""
     L = len(flows_fwd)
     scales = L if num_scales is None else int(num_scales)
     ts = [_dev(t, "input") for t in (*img_l_pyr[:L], *img_pyr[:L], *img_r_pyr[:L], *flows_fwd, *flows_bwd)]
@@ -305,13 +308,22 @@ def flow_loss_step(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r
         out = {"loss": torch.empty((4, B), device=dev, dtype=torch.float32),
                "stats": torch.empty((B, scales, _cabi.FLOW_NSTATS), device=dev, dtype=torch.float32),
                "gf": [torch.empty_like(ff[l]) for l in range(scales)], "gb": [torch.empty_like(fb[l]) for l in range(scales)],
-               "basis": _alloc_basis(ff, scales) if mode == "single_pass" else None}
+               "basis": _alloc_basis(ff, scales) if mode == "single_pass" else None, "mode": mode}
         a = _flow_args(img_l, img, img_r, ff, fb, scales, out["loss"], out["stats"], None)
         out["ws"] = torch.empty(max(int(_cabi.lib().ugl_flow_loss_workspace_bytes(C.byref(a))) // 4, 1), device=dev,
                                 dtype=torch.float32)
     a = _flow_args(img_l, img, img_r, ff, fb, scales, out["loss"], out["stats"], out["ws"], gloss, out["gf"], out["gb"],
                    basis=out["basis"])
     fwd, bwd = phase in ("both", "forward"), phase in ("both", "backward")   # 'forward'/'backward': one half only (kernel timing)
+    if out.get("mode", mode) != mode:
+        raise ValueError("flow_loss_step: `out` was allocated for mode %r" % out.get("mode"))
+    if mode == "fused_step":
+        if phase != "both":
+            raise ValueError("flow_loss_step: mode 'fused_step' has no separate halves")
+        with torch.cuda.device_of(img[0]):
+            _cabi.check(_cabi.lib().ugl_flow_loss_step(C.byref(a)), "ugl_flow_loss_step")
+        _count(4)
+        return out
     with torch.cuda.device_of(img[0]):
         if out["basis"] is not None:
             if fwd:
