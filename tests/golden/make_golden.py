@@ -170,6 +170,14 @@ def main():
     _run("depth_mode_texture", mk(seed=105, flow_mode="rigid"), GEOM_W, dl, lambda t: R.reference_depth_mode(t, 3, True))
     _run("geom_mode_s3", mk(seed=106, flow_mode="rigid"), GEOM_W, ["flows_fwd", "flows_bwd"] + dl,
          lambda t: R.reference_geom_mode(t, 3))
+    # multi-tile fixtures (round 2): 112 x 168, batch 1 -- several 32x13 / 32x32 tiles in both directions with ragged
+    # remainders, level widths 168 / 84 / 42 / 21 (odd: no vector stores, no TMA staging at the two small levels)
+    mt = lambda **kw: make_triplet(1, 112, 168, 4, 3, **kw)
+    _run("flow_mode_s4_mt", mt(seed=111, flow_px=4.0, oob_fraction=0.05), FLOW_W, ["flows_fwd", "flows_bwd"], lambda t: R.reference_flow_mode(t, 4))
+    _run("depth_mode_live_mt", mt(seed=114, flow_mode="rigid"), GEOM_W, dl, lambda t: R.reference_depth_mode(t, 3, False))
+    _run("depth_mode_texture_mt", mt(seed=115, flow_mode="rigid"), GEOM_W, dl, lambda t: R.reference_depth_mode(t, 3, True))
+    _run("geom_mode_s3_mt", mt(seed=116, flow_mode="rigid"), GEOM_W, ["flows_fwd", "flows_bwd"] + dl,
+         lambda t: R.reference_geom_mode(t, 3))
     primitives()
     cost_volume()
     return 0

@@ -60,7 +60,7 @@ def test_flow_loss_vs_oracle(cuda_device, B, Hh, W, L, scales, px, oob, mode):
             _assert_grad("%s bwd%d" % (kernel_mode, l), gb[l], rb[l], rb64[l])
 
 
-@pytest.mark.parametrize("name,scales", [("flow_mode_s4", 4), ("flow_mode_s4_oob", 4), ("flow_mode_s3", 3)])
+@pytest.mark.parametrize("name,scales", [("flow_mode_s4", 4), ("flow_mode_s4_oob", 4), ("flow_mode_s3", 3), ("flow_mode_s4_mt", 4)])
 def test_flow_loss_vs_reference_golden(cuda_device, name, scales):
     d = load_golden(name)
     t = golden_triplet(d)

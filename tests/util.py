@@ -64,8 +64,9 @@ def assert_loss_close(name, got, ref32, ref64=None, rtol=LOSS_RTOL):
     assert e_got <= 1.5 * e_ref + 1e-7, "%s: loss rel err %.3e (vs fp64: %.3e, oracle fp32 vs fp64: %.3e)" % (name, e, e_got, e_ref)
 
 
-def assert_grad_close(name, got, ref32, ref64=None, rtol=GRAD_RTOL, max_outlier_frac=3e-5):
+def assert_grad_close(name, got, ref32, ref64=None, rtol=GRAD_RTOL, max_outlier_frac=3e-5, max_outlier_scale=4.0, fp64_factor=1.25):
     got, ref32 = got.detach().double().cpu(), ref32.detach().double().cpu()
+    assert bool(torch.isfinite(got).all()), "%s: non-finite gradient values" % name
     scale = max(float(ref32.abs().max()), 1e-30)
     diff = (got - ref32).abs()
     e = float(diff.max()) / scale
@@ -73,10 +74,12 @@ def assert_grad_close(name, got, ref32, ref64=None, rtol=GRAD_RTOL, max_outlier_
         return
     if ref64 is not None:
         r64 = ref64.detach().double().cpu()
-        if float((got - r64).abs().max()) <= 1.25 * float((ref32 - r64).abs().max()):
+        if float((got - r64).abs().max()) <= fp64_factor * float((ref32 - r64).abs().max()):
             return
     # knife edges (a bilinear cell boundary, the sign of |a-b| at a-b ~ 0) flip a single element's gradient by O(1):
-    # every element except at most a handful of isolated ones must be within tolerance
-    n_bad = int((diff > rtol * scale).sum())
+    # every element except at most a handful of isolated ones must be within tolerance ...
+    n_bad = int((~(diff <= rtol * scale)).sum())          # written so that a NaN would count as bad
     allowed = max(2, int(max_outlier_frac * got.numel()))
     assert n_bad <= allowed, "%s: max rel err %.3e, %d/%d elements beyond %.0e (allowed %d)" % (name, e, n_bad, got.numel(), rtol, allowed)
+    # ... and a flipped sign or cell moves an element by a few times the gradient scale at most, never by orders of magnitude
+    assert e <= max_outlier_scale, "%s: an outlier of %.3e x the largest reference gradient" % (name, e)

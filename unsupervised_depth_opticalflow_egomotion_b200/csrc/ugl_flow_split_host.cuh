@@ -31,7 +31,7 @@ constexpr int kPhotoMinBlocks = UGL_PHOTO_MINB;
 #define UGL_PHOTO_NT 256
 #endif
 #ifndef UGL_PATCH_W
-#define UGL_PATCH_W 8
+#define UGL_PATCH_W 32
 #endif
 constexpr int kPhotoTW = UGL_PHOTO_TW, kPhotoTH = UGL_PHOTO_TH;   // tile of a photometry-kernel CTA
 constexpr int kPhotoNT = UGL_PHOTO_NT;                            // its threads: one pixel each per pass (tile height / (NT / width) passes)
