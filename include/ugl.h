@@ -99,6 +99,14 @@ int ugl_flow_loss_forward_grad_ex(const UglFlowLossArgs* args, int32_t variant);
  * adds the four gradient terms itself: no basis planes (args->basis is ignored), no combine launch.  Same results as
  * ugl_flow_loss_forward_grad + ugl_flow_loss_combine. */
 int ugl_flow_loss_step(const UglFlowLossArgs* args);
+/* The same step launching only the selected kernels (bit mask), in order -- for per-kernel timing with events around each
+ * launch (bench.py's roofline); the kernels of a later part read what the earlier parts of a previous call left in the workspace. */
+#define UGL_STEP_PHOTO 1
+#define UGL_STEP_NORM 2
+#define UGL_STEP_STENCIL 4
+#define UGL_STEP_FINALIZE 8
+#define UGL_STEP_ALL 15
+int ugl_flow_loss_step_parts(const UglFlowLossArgs* args, int32_t parts);
 int ugl_flow_loss_combine(const UglFlowLossArgs* args);
 
 /* ---------------------------------------------------------------------------------------------

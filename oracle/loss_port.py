@@ -452,11 +452,13 @@ def rigid_masks(dist: Tensor, rigid_thres: float = 0.5, inlier_thres: float = 0.
 # per-mode assembly (T0)
 # ----------------------------------------------------------------------------------------------
 def flow_mode_loss(img_l: Tensor, img: Tensor, img_r: Tensor, flows_fwd: Sequence[Tensor],
-                   flows_bwd: Sequence[Tensor], scales: int, return_aux: bool = False):
+                   flows_bwd: Sequence[Tensor], scales: int, return_aux: bool = False, pyramids=None):
     """T0/flow — model_flow.py:232-254.  ``scales`` plays the role of
-    ``self.num_scales``; pyramids have ``len(flows_fwd)`` levels."""
+    ``self.num_scales``; pyramids have ``len(flows_fwd)`` levels.  ``pyramids=(pl, pc, pr)``: the three image pyramids
+    (model_flow.py:232-234) already built -- bench.py's CPU legs time the loss on materialised pyramids, the form the
+    algorithmic-bytes figure of SURVEY 8(d) and the GPU arm's ``value`` use."""
     L = len(flows_fwd)
-    pl, pc, pr = box_pyramid(img_l, L), box_pyramid(img, L), box_pyramid(img_r, L)
+    pl, pc, pr = pyramids if pyramids is not None else (box_pyramid(img_l, L), box_pyramid(img, L), box_pyramid(img_r, L))
     from_l = [flow_backwarp(pl[s], flows_bwd[s], use_mask=True) for s in range(L)]
     from_r = [flow_backwarp(pr[s], flows_fwd[s], use_mask=True) for s in range(L)]
     occ = occlusion_weights(from_l, pc, from_r, scales, soft=True)

@@ -156,10 +156,48 @@ def test_flow_loss_step_uint8_frames_equal_float_frames(cuda_device):
     ff, fb = [f.detach().pin_memory() for f in t.flows_fwd], [f.detach().pin_memory() for f in t.flows_bwd]
     a = FlowLossStep(2, 64, 96, 3, device=cuda_device, frame_dtype=torch.uint8)
     b = FlowLossStep(2, 64, 96, 3, device=cuda_device)
-    la = a(u8[0], u8[1], u8[2], ff, fb).clone()
-    lb = b(f32[0], f32[1], f32[2], ff, fb).clone()
+    la = a(u8[0], u8[1], u8[2], ff, fb)
+    lb = b(f32[0], f32[1], f32[2], ff, fb)
     assert torch.equal(la, lb)
-    assert all(torch.equal(x, y) for x, y in zip(a.grads, b.grads))
-    assert a.h2d_bytes < b.h2d_bytes
+    assert all(torch.equal(x, y) for x, y in zip(a.grads(0), b.grads(0))) and len(a.grads(0)) == 6
+    assert a.h2d_bytes < b.h2d_bytes and a.h2d_copies_per_step == 1
     with pytest.raises(TypeError):
         a(f32[0], f32[1], f32[2], ff, fb)
+
+
+def test_flow_loss_step_staged_pipeline_and_guards(cuda_device):
+    """The staged form (inputs written into the slot's pinned views, one H2D per step), two steps in flight, against the
+    resident-input path; a slot may not be re-submitted before its result was read; results are private copies."""
+    from unsupervised_depth_opticalflow_egomotion_b200.step import FlowLossStep, FLOW_WEIGHTS, weight_matrix
+    from unsupervised_depth_opticalflow_egomotion_b200.synth import make_triplet
+    B, H, W, L = 2, 64, 96, 3
+    ts = [make_triplet(B, H, W, L, 1, seed=s) for s in (21, 22, 23)]
+    st = FlowLossStep(B, H, W, L, device=cuda_device)
+    wmat = weight_matrix(FLOW_WEIGHTS, ops.FLOW_LOSS_KEYS, B, cuda_device)
+
+    def fill(slot, t):
+        hv = st.host_views(slot)
+        hv["img_l"].copy_(t.img_l); hv["img"].copy_(t.img); hv["img_r"].copy_(t.img_r)
+        for l in range(L):
+            hv["ff%d" % l].copy_(t.flows_fwd[l].detach()); hv["fb%d" % l].copy_(t.flows_bwd[l].detach())
+
+    def resident(t):
+        td = t.to(cuda_device)
+        pyr = [ops.image_pyramid(x, L, "box") for x in (td.img_l, td.img, td.img_r)]
+        out = ops.flow_loss_step(pyr[0], pyr[1], pyr[2], td.flows_fwd, td.flows_bwd, wmat, L)
+        return out["loss"].cpu(), [g.cpu() for g in out["gf"] + out["gb"]]
+
+    s0 = st.next_slot(); fill(s0, ts[0]); assert st.submit_staged() == s0
+    s1 = st.next_slot(); fill(s1, ts[1]); assert st.submit_staged() == s1 and s1 != s0
+    with pytest.raises(RuntimeError, match="re-submitted before result"):
+        st.submit_staged()                                  # slot s0 again: its result is still unread
+    r0 = st.result(s0)
+    g0 = [g.cpu() for g in st.grads(s0)]
+    fill(s0, ts[2]); st.submit_staged()                     # now legal; must not disturb r0 (a private copy)
+    r1, r2 = st.result(s1), st.result(s0)
+    for r, t in ((r0, ts[0]), (r1, ts[1]), (r2, ts[2])):
+        ref_l, _ = resident(t)
+        assert torch.equal(r, ref_l)
+    assert all(torch.equal(a, b) for a, b in zip(g0, resident(ts[0])[1]))
+    with pytest.raises(RuntimeError, match="nothing was submitted"):
+        FlowLossStep(B, H, W, L, device=cuda_device).result(0)

@@ -26,7 +26,13 @@ def _worker(rank, world, port, q):
     local = P.flow_mode_loss(sl(t.img_l), sl(t.img), sl(t.img_r), [sl(f) for f in t.flows_fwd], [sl(f) for f in t.flows_bwd], 3)
     means = parallel.global_loss_means(local, B)
     total = parallel.weighted_total(means, P.FLOW_WEIGHTS)
-    q.put((rank, (a, b), {k: v.clone() for k, v in local.items()}, {k: float(v) for k, v in means.items()}, float(total)))
+    # the preallocated, graph-capturable form of the same collective: (K, B_local) matrix -> (K,) global means
+    keys = list(P.FLOW_WEIGHTS)
+    lar = parallel.LossAllReduce(len(keys), B, "cpu")
+    vec = lar(torch.stack([local[k].detach() for k in keys]))
+    # plain Python payloads: tensors in a Queue travel as file descriptors, which break if the sender exits first
+    q.put((rank, (a, b), {k: v.tolist() for k, v in local.items()}, {k: float(v) for k, v in means.items()}, float(total),
+           {k: float(vec[i]) for i, k in enumerate(keys)}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,9 +59,10 @@ def test_sharded_losses_match_unsharded():
     torch.set_num_threads(1)
     t = make_triplet(5, 32, 64, 3, 1, seed=9, flow_px=2.0)
     full = P.flow_mode_loss(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd, 3)
-    for rank, (a, b), local, means, total in res:
+    for rank, (a, b), local, means, total, vec in res:
         for k in full:
-            assert torch.allclose(local[k], full[k][a:b], rtol=1e-6, atol=0), k      # per-sample values do not depend on the shard
+            assert torch.allclose(torch.tensor(local[k]), full[k][a:b], rtol=1e-6, atol=0), k      # per-sample values do not depend on the shard
             assert abs(means[k] - float(full[k].mean())) <= 1e-6 * abs(float(full[k].mean())), k
+            assert abs(vec[k] - means[k]) <= 1e-6 * abs(means[k]), k                                # LossAllReduce == global_loss_means
         assert abs(total - float(P.weighted_total(full, P.FLOW_WEIGHTS))) <= 1e-6 * abs(total)
     assert res[0][3] == res[1][3]                                                    # every rank holds the same global means

@@ -15,6 +15,7 @@ GEOM_NSTATS = 16
 FLOW_BASIS_PLANES = 14
 # internal forms of the single-pass forward (include/ugl.h: UGL_SINGLE_PASS_*)
 SINGLE_PASS_VARIANTS = {"fused": 0, "split": 1, "split_plain": 2, "split_tma": 3}
+STEP_PARTS = {"photo": 1, "norm": 2, "stencil": 4, "finalize": 8, "all": 15}     # include/ugl.h: UGL_STEP_*
 DEPTH_BASIS_PLANES = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -151,6 +152,7 @@ SIGNATURES = {
     "ugl_flow_loss_forward_grad": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_forward_grad_ex": (C.c_int, [C.POINTER(UglFlowLossArgs), C.c_int32]),
     "ugl_flow_loss_step": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
+    "ugl_flow_loss_step_parts": (C.c_int, [C.POINTER(UglFlowLossArgs), C.c_int32]),
     "ugl_flow_loss_combine": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_image_pyramid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.POINTER(C.c_void_p), C.c_void_p]),

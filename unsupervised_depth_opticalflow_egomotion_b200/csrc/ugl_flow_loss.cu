@@ -384,7 +384,9 @@ extern "C" int ugl_flow_loss_forward_grad(const UglFlowLossArgs* a) { return ugl
 
 // fused forward + backward for a known upstream gradient: photometry kernel -> weight sums -> stencil kernel (writes the flow gradients)
 // -> finalize (losses).  No basis planes, no combine launch.
-extern "C" int ugl_flow_loss_step(const UglFlowLossArgs* a) {
+extern "C" int ugl_flow_loss_step(const UglFlowLossArgs* a) { return ugl_flow_loss_step_parts(a, UGL_STEP_ALL); }
+
+extern "C" int ugl_flow_loss_step_parts(const UglFlowLossArgs* a, int parts) {
   FlowGradParams gp;
   int rc = build_params<kBTW, kBTH>(a, true, gp.base);
   if (rc) return rc;
@@ -398,8 +400,8 @@ extern "C" int ugl_flow_loss_step(const UglFlowLossArgs* a) {
   gp.step = 1;
   char* pp = split_photo_partials(a);
   flow_split_assign_scratch(gp, pp + flow_split_photo_partials_bytes(a->height, a->width, a->scales, a->batch));
-  if ((rc = launch_flow_split<false>(gp, pp, st, 1))) return rc;
-  return launch_finalize(gp.base, st, &gp.photo);
+  if ((rc = launch_flow_split<false>(gp, pp, st, 1, parts & 7))) return rc;
+  return (parts & UGL_STEP_FINALIZE) ? launch_finalize(gp.base, st, &gp.photo) : UGL_OK;
 }
 
 // ---- geom mode (Model_geometry's flow branch) -----------------------------------------------------

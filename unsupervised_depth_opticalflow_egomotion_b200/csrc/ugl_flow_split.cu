@@ -335,20 +335,23 @@ static void assign_photo_tiling(FlowGradParams& gp, void* partials) {
 }
 
 template <bool kGeom>
-int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st, int tma_mode) {
+int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st, int tma_mode, int parts) {
   constexpr int TW = kBTW, TH = kBTH, NT = kSplitNT;
   using Tile = FlowStencilTile<TW, TH, NT, kGeom>;
   assign_photo_tiling<kGeom>(gp, photo_partials);
   const dim3 grid(gp.base.total_tiles / gp.base.B, gp.base.B);
-  flow_photo_kernel<kPhotoTW, kPhotoTH, kPhotoNT, kPatchW, kPatchH, kGeom><<<dim3(gp.photo.per_sample, gp.base.B), kPhotoNT, 0, st>>>(gp);
-  int rc = check_launch("flow_photo_kernel");
-  if (rc) return rc;
+  int rc = UGL_OK;
+  if (parts & 1) {
+    flow_photo_kernel<kPhotoTW, kPhotoTH, kPhotoNT, kPatchW, kPatchH, kGeom><<<dim3(gp.photo.per_sample, gp.base.B), kPhotoNT, 0, st>>>(gp);
+    if ((rc = check_launch("flow_photo_kernel"))) return rc;
+  }
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float) + 128;
   static_assert(smem <= 227 * 1024, "stencil tile does not fit in shared memory");
-  if (gp.step) {
+  if (gp.step && (parts & 2)) {
     flow_photo_norm_kernel<kGeom><<<dim3(gp.base.scales, gp.base.B), 256, 0, st>>>(gp);
     if ((rc = check_launch("flow_photo_norm_kernel"))) return rc;
   }
+  if (!(parts & 4)) return UGL_OK;
   FlowTmaMaps tm;
   memset(&tm, 0, sizeof(tm));
   const int n_tma = tma_mode != 0 ? build_tma_maps<TW, TH, NT, kGeom>(gp, tm) : 0;
@@ -368,7 +371,7 @@ int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st,
   return check_launch("flow_stencil_kernel");
 }
 
-template int launch_flow_split<false>(FlowGradParams&, void*, cudaStream_t, int);
-template int launch_flow_split<true>(FlowGradParams&, void*, cudaStream_t, int);
+template int launch_flow_split<false>(FlowGradParams&, void*, cudaStream_t, int, int);
+template int launch_flow_split<true>(FlowGradParams&, void*, cudaStream_t, int, int);
 
 }  // namespace ugl

@@ -57,7 +57,8 @@ void flow_split_assign_scratch(FlowGradParams& gp, void* base);
 uint64_t flow_split_photo_partials_bytes(const int32_t* height, const int32_t* width, int scales, int batch);
 // photometry kernel + stencil kernel on `st`; fills gp.photo (the finalize kernel reads it).
 // tma_mode: 0 = plain-load staging, 1 = TMA where the shapes allow it, 2 = TMA or fail
+// parts: bit 0 photometry kernel, bit 1 weight sums (step mode), bit 2 stencil kernel (per-kernel timing launches a subset)
 template <bool kGeom>
-int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st, int tma_mode);
+int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st, int tma_mode, int parts = 7);
 
 }  // namespace ugl

@@ -318,11 +318,11 @@ def flow_loss_step(img_l_pyr: Sequence[Tensor], img_pyr: Sequence[Tensor], img_r
     if out.get("mode", mode) != mode:
         raise ValueError("flow_loss_step: `out` was allocated for mode %r" % out.get("mode"))
     if mode == "fused_step":
-        if phase != "both":
-            raise ValueError("flow_loss_step: mode 'fused_step' has no separate halves")
+        # phase: 'both' = the whole step; 'photo' / 'norm' / 'stencil' / 'finalize' = that kernel only (per-kernel timing)
+        parts = _cabi.STEP_PARTS["all" if phase == "both" else phase]
         with torch.cuda.device_of(img[0]):
-            _cabi.check(_cabi.lib().ugl_flow_loss_step(C.byref(a)), "ugl_flow_loss_step")
-        _count(4)
+            _cabi.check(_cabi.lib().ugl_flow_loss_step_parts(C.byref(a), parts), "ugl_flow_loss_step")
+        _count(bin(parts).count("1"))
         return out
     with torch.cuda.device_of(img[0]):
         if out["basis"] is not None:
