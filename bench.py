@@ -253,8 +253,10 @@ def mode_step(workload: str, batch: int, height: int, width: int, dev, steps: in
     if workload == "geom":
         mod = losses.GeometryLoss(S)
         fwd = lambda: mod.forward_losses(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd, t.disp, t.disp_l, t.disp_r, t.pose, t.K, t.K_inv)[0]
-    elif workload in ("depth", "depth-live"):
-        mod = losses.DepthLoss(S, "texture" if workload == "depth" else "live")
+    elif workload in ("depth", "depth-texture", "depth-live"):
+        # depth = BASELINE configs[2] (model_depth_texture.py:296-307, reprojection L1 + SSIM + smoothness);
+        # depth-texture = that file's whole loss (+ the depth-consistency term, :309-310); depth-live = model_depth.py
+        mod = losses.DepthLoss(S, {"depth": "ssim", "depth-texture": "texture", "depth-live": "live"}[workload])
         fwd = lambda: mod.forward_losses(t.img_l, t.img, t.img_r, t.disp, t.disp_l, t.disp_r, t.pose, t.K)[0]
     else:   # flow+depth (BASELINE configs[4]): the flow-mode loss (4 levels) and the live depth-mode loss on the same triplet
         fmod, dmod = losses.FlowLoss(4), losses.DepthLoss(S, "live")
@@ -404,7 +406,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs[2..4] extras of the contract line")
-    ap.add_argument("--workload", default="flow", choices=["flow", "depth", "depth-live", "geom", "flow+depth", "costvolume"],
+    ap.add_argument("--workload", default="flow", choices=["flow", "depth", "depth-texture", "depth-live", "geom", "flow+depth", "costvolume"],
                     help="flow = BASELINE configs[1] (the driver's line).  Extras: depth (model_depth_texture spec) / depth-live (model_depth) "
                          "= configs[2], geom = configs[3], flow+depth = configs[4] (use --height 384 --width 1280)")
     ap.add_argument("--height", type=int, default=H, help="extras only (the driver's line is always 256x832)")
@@ -624,7 +626,8 @@ def main():
         state["out"] = None
         torch.cuda.empty_cache()
         gb32, gb64 = max(1, 32 // world), max(1, 64 // world)
-        for name, wl, b_, h_, w_ in (("depth", "depth", B, H, W), ("depth_live", "depth-live", B, H, W), ("geom", "geom", B, H, W),
+        for name, wl, b_, h_, w_ in (("depth", "depth", B, H, W), ("depth_texture_full", "depth-texture", B, H, W),
+                                     ("depth_live", "depth-live", B, H, W), ("geom", "geom", B, H, W),
                                      ("geom_strong_b32", "geom", gb32, H, W), ("highres_b64", "flow+depth", gb64, 384, 1280)):
             try:
                 extras[name] = mode_step(wl, b_, h_, w_, dev, min(K, 10), 3, flush, rank, not args.no_graph, world, dist if world > 1 else None)

@@ -255,6 +255,19 @@ int ugl_mask_product(const float* const* masks, const int32_t* invert, int32_t n
 int ugl_rigid_mask(const float* dist, int64_t n, float rigid_thres, float inlier_thres, float* rigid, float* inlier, float* score,
                    void* stream);
 
+/* Step glue of the mode assemblies (T0; model_geometry.py:883-951 + train.py:211-214) without library kernels:
+ *   ugl_accumulate_multi      dst[i] += src[3 i] (+ src[3 i + 1] + src[3 i + 2], null = absent) for up to 24 distinct destinations in one
+ *                             launch -- the gradient accumulation autograd performs with one `add` launch per contribution when a
+ *                             tensor (disparity, flow, K[R|t]) feeds several loss terms; `src` holds 3 n pointers;
+ *   ugl_weighted_total_*      total = sum_k weights[k] * mean_b loss[k][b] over a (terms, batch) matrix, and grad_loss[k][b] =
+ *                             grad_out * weights[k] / batch;
+ *   ugl_assemble_rows         dst[i][b] = sum_{r < nsum[i]} src[i][r * batch + b]: the (B,) outputs of the per-term kernels -> rows of
+ *                             one (n, batch) loss matrix (nsum > 1: the three compute_smooth_loss calls, summed in call order). */
+int ugl_accumulate_multi(float* const* dst, const float* const* src, const int64_t* numel, int32_t n, void* stream);
+int ugl_assemble_rows(const float* const* src, const int32_t* nsum, int32_t n, int32_t batch, float* dst, void* stream);
+int ugl_weighted_total_forward(const float* loss, const float* weights, int32_t terms, int32_t batch, float* out, void* stream);
+int ugl_weighted_total_backward(const float* grad_out, const float* weights, int32_t terms, int32_t batch, float* grad_loss, void* stream);
+
 /* cal_grad2_error(flow/20, img) for one level (model_geometry.py:254-279, model_flow.py:156-181) -> (B,) */
 int ugl_flow_smooth_forward(const float* flow, const float* img, int32_t batch, int32_t height, int32_t width, float* out,
                             void* workspace, uint64_t workspace_bytes, void* stream);

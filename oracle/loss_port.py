@@ -492,9 +492,10 @@ def depth_mode_loss(img_l: Tensor, img: Tensor, img_r: Tensor, disp: Sequence[Te
         "loss_depth_smooth": disparity_smooth_loss(img, disp, scales) + disparity_smooth_loss(img_l, disp_l, scales)
                              + disparity_smooth_loss(img_r, disp_r, scales),
     }
-    if variant == "texture":
+    if variant in ("texture", "ssim"):      # 'ssim': model_depth_texture.py:296-307 only (no consistency term) = BASELINE configs[2]
         loss["loss_depth_ssim"] = ssim_loss(pc, rec_l, val_l, scales) + ssim_loss(pc, rec_r, val_r, scales)
-        loss["loss_depth_consis"] = depth_consistency_loss(proj_l, comp_l, scales) + depth_consistency_loss(proj_r, comp_r, scales)
+        loss["loss_depth_consis"] = (depth_consistency_loss(proj_l, comp_l, scales) + depth_consistency_loss(proj_r, comp_r, scales)
+                                     if variant == "texture" else torch.zeros([2], device=img.device))
     else:
         loss["loss_depth_ssim"] = torch.zeros([2], device=img.device)
         loss["loss_depth_consis"] = torch.zeros([2], device=img.device)

@@ -37,8 +37,8 @@ def _oracle_depth(t, variant, S, dtype):
     return loss, aux, keys, g
 
 
-@pytest.mark.parametrize("variant,B,H,W", [("live", 2, 128, 416), ("texture", 2, 128, 416), ("live", 1, 256, 832), ("texture", 1, 256, 832),
-                                           ("live", 1, 384, 1280)])
+@pytest.mark.parametrize("variant,B,H,W", [("live", 2, 128, 416), ("texture", 2, 128, 416), ("ssim", 2, 128, 416), ("live", 1, 256, 832),
+                                           ("texture", 1, 256, 832), ("ssim", 1, 256, 832), ("live", 1, 384, 1280)])
 def test_depth_mode_vs_oracle(cuda_device, variant, B, H, W):
     """model_depth.py:281-335 ('live') / model_depth_texture.py:296-311 ('texture') through losses.DepthLoss (fused kernels):
     masks bit-exact, losses 1e-5, disparity gradients 1e-4, pose gradient against the fp64 twin."""
@@ -413,3 +413,59 @@ def test_fused_step_vs_oracle_and_autograd(cuda_device, B, H, W, L, scales):
     assert loss_rel_err(st["loss"], al) < 1e-6
     for a, b in zip(st["gf"] + st["gb"], ag):
         assert rel_err(a, b) < 2e-6
+
+
+# ---- one autograd node per mode (mode_steps.py) against the same kernels as separate autograd Functions ----------------------
+def test_geom_step_node_equals_op_by_op(cuda_device):
+    """losses.GeometryLoss(fused=True) runs the fused kernels inside ONE autograd node (gradient accumulation and the weighted total
+    as single launches); fused='ops' runs the same kernels as separate Functions under the autograd engine.  Same kernels, same
+    inputs: losses and masks bit-identical, gradients equal up to the order of the additions."""
+    t = make_triplet(2, 64, 208, 4, 3, seed=91, flow_mode="rigid").to(cuda_device)
+    mod = losses.GeometryLoss(3)
+    res = {}
+    for fused in (True, "ops"):
+        ff, fb = _leaf_list(t.flows_fwd, cuda_device), _leaf_list(t.flows_bwd, cuda_device)
+        disp, disp_l, disp_r = _leaf_list(t.disp, cuda_device), _leaf_list(t.disp_l, cuda_device), _leaf_list(t.disp_r, cuda_device)
+        pose = t.pose.detach().clone().requires_grad_(True)
+        loss, masks = mod.forward_losses(t.img_l, t.img, t.img_r, ff, fb, disp, disp_l, disp_r, pose, t.K, t.K_inv, fused=fused)
+        total = losses.total_loss(loss, P.GEOM_WEIGHTS)
+        g = torch.autograd.grad(total, ff[:3] + fb[:3] + disp + disp_l + disp_r + [pose])
+        res[fused] = (loss, masks, total, g)
+    a, b = res[True], res["ops"]
+    assert set(a[0]) == set(b[0])
+    for k in b[0]:
+        assert a[0][k].shape == b[0][k].shape and torch.equal(a[0][k].detach(), b[0][k].detach()), k
+    for key in ("occ_b", "occ_f", "valid_b", "valid_f", "dyn_b", "dyn_f", "tex_b", "tex_f", "val_l", "val_r", "fwd_mask", "bwd_mask"):
+        for l in range(3):
+            assert torch.equal(a[1][key][l], b[1][key][l]), (key, l)
+    assert rel_err(a[1]["dist_f"], b[1]["dist_f"]) == 0.0
+    assert abs(float(a[2].detach()) - float(b[2].detach())) <= 1e-6 * abs(float(b[2].detach()))
+    for x, y in zip(a[3], b[3]):
+        assert rel_err(x, y) < 1e-6
+    assert ff[3].grad is None      # level 3 of the flow pyramids carries no loss in geom mode (model_geometry.py loops over num_scales)
+
+
+@pytest.mark.parametrize("variant", ["live", "ssim", "texture"])
+def test_depth_step_node_equals_op_by_op(cuda_device, variant):
+    t = make_triplet(2, 64, 208, 4, 3, seed=93, flow_mode="rigid").to(cuda_device)
+    mod = losses.DepthLoss(3, variant)
+    res = {}
+    for fused in (True, "ops"):
+        disp, disp_l, disp_r = _leaf_list(t.disp, cuda_device), _leaf_list(t.disp_l, cuda_device), _leaf_list(t.disp_r, cuda_device)
+        pose = t.pose.detach().clone().requires_grad_(True)
+        loss, masks = mod.forward_losses(t.img_l, t.img, t.img_r, disp, disp_l, disp_r, pose, t.K, fused=fused)
+        total = losses.total_loss(loss, P.GEOM_WEIGHTS)
+        g = torch.autograd.grad(total, disp + disp_l + disp_r + [pose], allow_unused=True)
+        res[fused] = (loss, masks, total, g)
+    a, b = res[True], res["ops"]
+    assert set(a[0]) == set(b[0])
+    for k in b[0]:
+        assert a[0][k].shape == b[0][k].shape and torch.equal(a[0][k].detach(), b[0][k].detach()), k
+    for key in ("valid_l", "valid_r", "tex_b", "tex_f"):
+        for l in range(3):
+            assert torch.equal(a[1][key][l], b[1][key][l]), (key, l)
+    assert abs(float(a[2].detach()) - float(b[2].detach())) <= 1e-6 * abs(float(b[2].detach()))
+    for x, y in zip(a[3], b[3]):
+        assert (x is None) == (y is None)
+        if x is not None:
+            assert rel_err(x, y) < 1e-6

@@ -186,6 +186,10 @@ SIGNATURES.update({
     "ugl_dynamic_mask_forward": (C.c_int, [_p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p]),
     "ugl_abs_diff_backward": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
     "ugl_mask_product": (C.c_int, [_pp, _ip, _i, _i64, _p, _p]),
+    "ugl_accumulate_multi": (C.c_int, [_pp, _pp, C.POINTER(C.c_int64), _i, _p]),
+    "ugl_assemble_rows": (C.c_int, [_pp, _ip, _i, _i, _p, _p]),
+    "ugl_weighted_total_forward": (C.c_int, [_p, _p, _i, _i, _p, _p]),
+    "ugl_weighted_total_backward": (C.c_int, [_p, _p, _i, _i, _p, _p]),
     "ugl_rigid_mask": (C.c_int, [_p, _i64, _f, _f, _p, _p, _p, _p]),
     "ugl_flow_smooth_forward": (C.c_int, [_p, _p, _i, _i, _i, _p, _p, _u64, _p]),
     "ugl_flow_smooth_backward": (C.c_int, [_p, _p, _p, _i, _i, _i, _p, _p]),

@@ -527,6 +527,112 @@ extern "C" int ugl_rigid_mask(const float* dist, int64_t n, float rigid_thres, f
   return launch_pointwise(f, (long)n, static_cast<cudaStream_t>(stream), "rigid_mask");
 }
 
+// ---- step glue: gradient accumulation over several tensors, weighted total -----------------------------------------------
+// dst[i] += src[i][0] (+ src[i][1] + src[i][2]) for up to kAccumulateMax destinations in ONE launch (grid.y = destination): what
+// autograd's engine does with one `add` launch per contribution when a tensor feeds several loss terms.  Each destination appears
+// once (its contributions are added in the order given: deterministic).
+constexpr int kAccumulateMax = 24, kAccumulateSrc = 3;
+struct AccumulateParams { float* dst[kAccumulateMax]; const float* src[kAccumulateMax][kAccumulateSrc]; long n[kAccumulateMax]; };
+
+__global__ void __launch_bounds__(256) accumulate_multi_kernel(const __grid_constant__ AccumulateParams p) {
+  const int k = blockIdx.y;
+  float* __restrict__ d = p.dst[k];
+  const float* __restrict__ s0 = p.src[k][0];
+  const float* __restrict__ s1 = p.src[k][1];
+  const float* __restrict__ s2 = p.src[k][2];
+  const long n = p.n[k];
+  const long stride = (long)gridDim.x * blockDim.x, t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(s0) | reinterpret_cast<uintptr_t>(s1) | reinterpret_cast<uintptr_t>(s2);
+  if ((n & 3) == 0 && (bits & 15u) == 0) {
+    float4* d4 = reinterpret_cast<float4*>(d);
+    for (long i = t0; i < (n >> 2); i += stride) {
+      float4 a = d4[i];
+      const float4 b = reinterpret_cast<const float4*>(s0)[i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      if (s1) { const float4 c = reinterpret_cast<const float4*>(s1)[i]; a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; }
+      if (s2) { const float4 c = reinterpret_cast<const float4*>(s2)[i]; a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; }
+      d4[i] = a;
+    }
+  } else {
+    for (long i = t0; i < n; i += stride) {
+      float a = d[i] + s0[i];
+      if (s1) a += s1[i];
+      if (s2) a += s2[i];
+      d[i] = a;
+    }
+  }
+}
+
+extern "C" int ugl_accumulate_multi(float* const* dst, const float* const* src, const int64_t* numel, int32_t n, void* stream) {
+  UGL_REQUIRE(dst && src && numel && n >= 1 && n <= kAccumulateMax, UGL_EINVAL, "accumulate_multi: 1..%d destinations", kAccumulateMax);
+  AccumulateParams p;
+  long nmax = 0;
+  for (int k = 0; k < n; ++k) {
+    UGL_REQUIRE(dst[k] && src[kAccumulateSrc * k] && numel[k] >= 0, UGL_EINVAL, "accumulate_multi: null pointer / negative size at %d", k);
+    for (int j = 0; j < k; ++j) UGL_REQUIRE(dst[j] != dst[k], UGL_EINVAL, "accumulate_multi: destination %d listed twice", k);
+    p.dst[k] = dst[k]; p.n[k] = (long)numel[k];
+    for (int j = 0; j < kAccumulateSrc; ++j) p.src[k][j] = src[kAccumulateSrc * k + j];
+    nmax = numel[k] > nmax ? (long)numel[k] : nmax;
+  }
+  long chunks = (nmax / 4 + 255) / 256;
+  chunks = chunks < 1 ? 1 : (chunks > 148 * 4 ? 148 * 4 : chunks);
+  accumulate_multi_kernel<<<dim3((unsigned)chunks, (unsigned)n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("accumulate_multi_kernel");
+}
+
+// dst[i][b] = sum_{r < nsum[i]} src[i][r * B + b]: the (B,) outputs of the per-term kernels gathered into the rows of one (n,B) loss
+// matrix (nsum[i] > 1: e.g. the three compute_smooth_loss calls of model_geometry.py:938-940 summed in call order).
+constexpr int kAssembleMax = 16;
+struct AssembleParams { const float* src[kAssembleMax]; int nsum[kAssembleMax]; int n, B; float* dst; };
+__global__ void assemble_rows_kernel(const __grid_constant__ AssembleParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n * p.B) return;
+  const int k = i / p.B, b = i - k * p.B;
+  float v = p.src[k][b];
+  for (int r = 1; r < p.nsum[k]; ++r) v += p.src[k][r * p.B + b];
+  p.dst[i] = v;
+}
+extern "C" int ugl_assemble_rows(const float* const* src, const int32_t* nsum, int32_t n, int32_t batch, float* dst, void* stream) {
+  UGL_REQUIRE(src && nsum && dst && n >= 1 && n <= kAssembleMax && batch >= 1, UGL_EINVAL, "assemble_rows: 1..%d rows", kAssembleMax);
+  AssembleParams p;
+  for (int k = 0; k < n; ++k) {
+    UGL_REQUIRE(src[k] && nsum[k] >= 1, UGL_EINVAL, "assemble_rows: null row / empty sum at %d", k);
+    p.src[k] = src[k]; p.nsum[k] = nsum[k];
+  }
+  p.n = n; p.B = batch; p.dst = dst;
+  assemble_rows_kernel<<<(n * batch + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("assemble_rows_kernel");
+}
+
+// total = sum_k w[k] * mean_b loss[k][b] (train.py:211-214) in one launch, fixed order (deterministic); and its backward
+// grad[k][b] = g * w[k] / B.
+__global__ void weighted_total_kernel(const float* __restrict__ loss, const float* __restrict__ w, int K, int B, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float tot = 0.f;
+    for (int k = 0; k < K; ++k) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += loss[k * B + b];
+      tot += w[k] * (s / (float)B);
+    }
+    out[0] = tot;
+  }
+}
+__global__ void weighted_total_grad_kernel(const float* __restrict__ g, const float* __restrict__ w, int K, int B, float* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * B) grad[i] = g[0] * (w[i / B] / (float)B);
+}
+
+extern "C" int ugl_weighted_total_forward(const float* loss, const float* weights, int32_t terms, int32_t batch, float* out, void* stream) {
+  UGL_REQUIRE(loss && weights && out && terms >= 1 && batch >= 1, UGL_EINVAL, "weighted_total_forward: null pointer / empty matrix");
+  weighted_total_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(loss, weights, terms, batch, out);
+  return check_launch("weighted_total_kernel");
+}
+extern "C" int ugl_weighted_total_backward(const float* grad_out, const float* weights, int32_t terms, int32_t batch, float* grad_loss, void* stream) {
+  UGL_REQUIRE(grad_out && weights && grad_loss && terms >= 1 && batch >= 1, UGL_EINVAL, "weighted_total_backward: null pointer / empty matrix");
+  weighted_total_grad_kernel<<<(terms * batch + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, weights, terms, batch, grad_loss);
+  return check_launch("weighted_total_grad_kernel");
+}
+
 // ---- flow regularisers --------------------------------------------------------------------------------
 extern "C" int ugl_flow_smooth_forward(const float* flow, const float* img, int32_t B, int32_t H, int32_t W, float* out, void* ws,
                                        uint64_t ws_bytes, void* stream) {

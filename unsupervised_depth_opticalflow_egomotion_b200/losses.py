@@ -18,9 +18,16 @@ from .structures import (calculate_rigid_flow, compute_essential_matrix, inv3x3,
 Tensor = torch.Tensor
 
 
+_ZEROS2: Dict[str, Tensor] = {}
+
+
 def _zeros2(like: Tensor) -> Tensor:
-    """The reference's disabled-term placeholder ``torch.zeros([2]).to(device).requires_grad_()``."""
-    return torch.zeros([2], device=like.device).requires_grad_()
+    """The reference's disabled-term placeholder ``torch.zeros([2]).to(device).requires_grad_()``: a fresh leaf per call over one
+    constant buffer per device (no fill launch inside a captured step)."""
+    z = _ZEROS2.get(str(like.device))
+    if z is None:
+        z = _ZEROS2[str(like.device)] = torch.zeros([2], device=like.device)
+    return z.detach().requires_grad_()
 
 
 class _LossBase:
@@ -144,12 +151,14 @@ class FlowLoss(_LossBase):
 
 
 class DepthLoss(_LossBase):
-    """Loss methods of ``Model_depth`` (model_depth.py; ``variant='texture'`` = model_depth_texture.py:296-311)."""
+    """Loss methods of ``Model_depth`` (model_depth.py).  ``variant='live'``: model_depth.py:281-335 (L1 + smoothness);
+    ``'texture'``: model_depth_texture.py:296-311 (L1 + SSIM + smoothness + unmasked depth consistency); ``'ssim'``: the same file
+    without its consistency term (:296-307) -- BASELINE configs[2] as SURVEY 8(d) spells it out: reprojection + SSIM + smoothness."""
 
     def __init__(self, num_scales: int, variant: str = "live"):
         super().__init__(num_scales)
-        if variant not in ("live", "texture"):
-            raise ValueError("variant must be 'live' or 'texture'")
+        if variant not in ("live", "texture", "ssim"):
+            raise ValueError("variant must be 'live', 'texture' or 'ssim'")
         self.variant = variant
 
     def generate_img_pyramid(self, img, num_pyramid):
@@ -164,11 +173,20 @@ class DepthLoss(_LossBase):
         """model_depth.py:154-163 (unmasked)"""
         return sum(ops.masked_mean(ops.depth_diff(computed_depth_list[s], predicted_depth_list[s]), None) for s in range(self.num_scales))
 
-    def forward_losses(self, img_l, img, img_r, disp_list, disp_l_list, disp_r_list, pose_vectors, K, fused: bool = True) -> Tuple[Dict[str, Tensor], Dict]:
-        """Loss body of ``Model_depth.forward`` (model_depth.py:281-335) / model_depth_texture.py:262-311.  ``fused=True``
-        (live variant) runs the reprojection + texture mask + masked L1 of both directions and all levels as one kernel."""
+    def forward_losses(self, img_l, img, img_r, disp_list, disp_l_list, disp_r_list, pose_vectors, K, fused=True) -> Tuple[Dict[str, Tensor], Dict]:
+        """Loss body of ``Model_depth.forward`` (model_depth.py:281-335) / model_depth_texture.py:262-311.  ``fused=True``: the fused
+        kernels as one autograd node; ``fused="ops"``: the same kernels as separate autograd Functions; ``fused=False``: one kernel per
+        reference method."""
         S = self.num_scales
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
+        if fused is True:
+            # the whole loss body as ONE autograd node (mode_steps.py): the fused kernels below, their gradient accumulation in one
+            # launch, no library kernels in between.  fused="ops" keeps the same kernels as separate autograd Functions.
+            from . import mode_steps
+            mat, valid, tex = mode_steps.depth_step(S, self.variant, img_l, img, img_r, disp_list, disp_l_list, disp_r_list, pose_vectors, K)
+            keys = mode_steps.DEPTH_KEYS[self.variant]
+            ph = {k: _zeros2(img) for k in ("loss_depth_pixel", "loss_depth_ssim", "loss_depth_consis", "loss_depth_smooth") if k not in keys}
+            return mode_steps.LossPack(mat, keys, ph), dict(valid_l=valid[0], valid_r=valid[1], tex_b=tex[0], tex_f=tex[1])
         if fused:
             Kinv, (P_b, P_f), _ = self._pose_setup(img.size(2), K, disp_list, pose_vectors)
             pyr = ops.image_pyramids((img, img_l, img_r), S, ("bilinear", ("bilinear", "area"), ("bilinear", "area")))   # one launch
@@ -182,12 +200,13 @@ class DepthLoss(_LossBase):
             loss = {"loss_depth_pixel": pix, "loss_depth_ssim": _zeros2(img), "loss_depth_consis": _zeros2(img),
                     "loss_depth_smooth": self.compute_smooth_loss3((img, img_l, img_r), (disp_list, disp_l_list, disp_r_list))}
             return loss, dict(valid_l=valid[0], valid_r=valid[1], tex_b=tex[0], tex_f=tex[1])
-        if fused and self.variant == "texture":
+        if fused and self.variant in ("texture", "ssim"):
             # L1 + SSIM of both source frames and all levels: the single-pass tile kernel in depth mode; the depth-consistency term
             # (disabled in the live Model_depth, model_depth.py:333-335): one forward / backward kernel set for all levels
             area = (pyr[1]["area"], pyr[2]["area"])
             l2, valid, tex = ops.depth_ssim_loss(pc, area, (pl, pr), list(disp_list[:S]), Kinv, (P_b, P_f))
-            consis = ops.depth_consis_loss(list(disp_list[:S]), (list(disp_l_list[:S]), list(disp_r_list[:S])), Kinv, (P_b, P_f))
+            consis = (ops.depth_consis_loss(list(disp_list[:S]), (list(disp_l_list[:S]), list(disp_r_list[:S])), Kinv, (P_b, P_f))
+                      if self.variant == "texture" else _zeros2(img))
             loss = {"loss_depth_pixel": l2[0], "loss_depth_ssim": l2[1], "loss_depth_consis": consis,
                     "loss_depth_smooth": self.compute_smooth_loss3((img, img_l, img_r), (disp_list, disp_l_list, disp_r_list))}
             return loss, dict(valid_l=valid[0], valid_r=valid[1], tex_b=tex[0], tex_f=tex[1])
@@ -197,9 +216,10 @@ class DepthLoss(_LossBase):
         tex_f = self.compute_texture_mask(pc, rec_r, pr)
         m_b, m_f = self.fusion_mask(val_l, tex_b), self.fusion_mask(val_r, tex_f)
         loss = {"loss_depth_pixel": self.compute_photometric_loss(pc, rec_l, m_b) + self.compute_photometric_loss(pc, rec_r, m_f)}
-        if self.variant == "texture":
+        if self.variant in ("texture", "ssim"):
             loss["loss_depth_ssim"] = self.compute_ssim_loss(pc, rec_l, val_l) + self.compute_ssim_loss(pc, rec_r, val_r)
-            loss["loss_depth_consis"] = self.compute_consis_loss(proj_l, comp_l) + self.compute_consis_loss(proj_r, comp_r)
+            loss["loss_depth_consis"] = (self.compute_consis_loss(proj_l, comp_l) + self.compute_consis_loss(proj_r, comp_r)
+                                         if self.variant == "texture" else _zeros2(img))
         else:
             loss["loss_depth_ssim"] = _zeros2(img)
             loss["loss_depth_consis"] = _zeros2(img)
@@ -220,6 +240,8 @@ def total_loss(loss_pack: Dict[str, Tensor], weights: Dict[str, float]) -> Tenso
     ``(B,)`` terms are stacked, averaged, weighted and summed at once.  The reference's constant ``zeros([2])`` placeholders add
     exactly 0 and carry no gradient, so they are skipped.  Gradients are bit-identical to the per-key loop
     (``d total / d loss_k[b] = fl(w_k / B)``)."""
+    if hasattr(loss_pack, "total"):          # mode_steps.LossPack: the live terms are rows of one matrix -> one launch
+        return loss_pack.total(weights)
     items = list(loss_pack.items())
     B = max(v.numel() for _, v in items)
     live = [(k, v) for k, v in items if v.numel() == B]          # B == 2: the placeholders stack like any other term
@@ -362,12 +384,21 @@ class GeometryLoss(_LossBase):
         return loss, GeomMasks(mbytes, dict(tex_b=tex_b, tex_f=tex_f, val_l=val_l, val_r=val_r), self, (flows_bwd[0], flows_fwd[0], Fm))
 
     def forward_losses(self, img_l, img, img_r, optical_flows_fwd, optical_flows_bwd, disp_list, disp_l_list, disp_r_list,
-                       pose_vectors, K, K_inv, fused: bool = True) -> Tuple[Dict[str, Tensor], Dict]:
+                       pose_vectors, K, K_inv, fused=True) -> Tuple[Dict[str, Tensor], Dict]:
         """Loss body of ``Model_geometry.forward`` (model_geometry.py:777-951) given the network outputs.
         The second return value holds the device-side masks (the reference's ``mask_pack`` without its
         unconditional D2H copies, :871-880)."""
         S = self.num_scales
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
+        if fused is True:
+            from . import mode_steps
+            mat, mbytes, (val_l, val_r), (tex_b, tex_f), Fm = mode_steps.geom_step(
+                S, self.flow_consist_alpha, self.flow_consist_beta, img_l, img, img_r, list(optical_flows_fwd), list(optical_flows_bwd),
+                disp_list, disp_l_list, disp_r_list, pose_vectors, K, K_inv)
+            ph = {k: _zeros2(img) for k in ("loss_depth_ssim", "loss_depth_consis", "loss_triangle", "loss_pnp", "loss_eight_point")}
+            return (mode_steps.LossPack(mat, mode_steps.GEOM_KEYS, ph),
+                    GeomMasks(mbytes, dict(tex_b=tex_b, tex_f=tex_f, val_l=val_l, val_r=val_r), self,
+                              (optical_flows_bwd[0], optical_flows_fwd[0], list(Fm))))
         if fused:
             Kinv, (P_b, P_f), Fm = self._pose_setup(img.size(2), K, disp_list, pose_vectors, K_inv, fundamental=True)
             pyr = ops.image_pyramids((img, img_l, img_r), S, ("bilinear", ("bilinear", "area"), ("bilinear", "area")))   # one launch
