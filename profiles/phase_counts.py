@@ -4,7 +4,9 @@ usage: ncu -i X.ncu-rep --page source --csv | python profiles/phase_counts.py [p
 import csv, sys, collections
 pixels = float(sys.argv[1]) if len(sys.argv) > 1 else 2263040.0
 rows = list(csv.reader(sys.stdin))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
+his = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
+hi = his[0]
+rows = rows[:his[1]] if len(his) > 1 else rows      # `--kernel-name` exports repeat the table: keep the first copy
 h = rows[hi]
 col = {n: i for i, n in enumerate(h)}
 stall_cols = [n for n in h if n.startswith('stall_') and 'Not Issued' not in n]
