@@ -1,4 +1,4 @@
-"""build tuning variants of the library into variants/ (git-ignored): python scratch/build_variants.py name:FLAG,FLAG ..."""
+"""build tuning variants of the library into variants/ (git-ignored): python profiles/scripts/build_variants.py name:FLAG,FLAG ..."""
 import sys, os
 sys.path.insert(0, ".")
 from unsupervised_depth_opticalflow_egomotion_b200 import build

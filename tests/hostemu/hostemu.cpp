@@ -14,6 +14,7 @@
 #include "../../include/ugl.h"
 #include "../../unsupervised_depth_opticalflow_egomotion_b200/csrc/ugl_flow_loss.cuh"
 #include "../../unsupervised_depth_opticalflow_egomotion_b200/csrc/ugl_flow_grad.cuh"
+#include "../../unsupervised_depth_opticalflow_egomotion_b200/csrc/ugl_flow_split.cuh"
 #include "../../unsupervised_depth_opticalflow_egomotion_b200/csrc/ugl_primitives.cuh"
 
 using namespace ugl;
@@ -137,6 +138,125 @@ extern "C" int emu_flow_loss_forward_grad(const UglFlowLossArgs* a) {
   }
   emu_finalize(gp.base, partials);
   return 0;
+}
+
+// split form (ugl_flow_split.cuh): photometry pixel by pixel -> photometry planes -> stencil tiles staged by the plain loader (the TMA copy
+// engine fills the same shared-memory layout on the device).  step = 0: basis planes out (then emu_flow_loss_combine); step = 1: the fused
+// training step, gradients written by the stencil tiles.  Photometry sums go through their own partial rows (here: one row per pixel row).
+template <bool kGeom>
+static int emu_flow_split(FlowGradParams& gp, int step) {
+  constexpr int TW = kBTW, TH = kBTH;
+  using Px = FlowPhotoPixel<kGeom>;
+  using Tile = FlowStencilTile<TW, TH, 1, kGeom>;
+  constexpr int ROW = kGeom ? (int)GA_COUNT : (int)FA_COUNT;
+  FlowLossParams& p = gp.base;
+  gp.step = step;
+  std::vector<std::vector<float>> scratch(p.scales);
+  for (int l = 0; l < p.scales; ++l) {
+    scratch[l].assign((size_t)p.B * kPhotoFloats * p.lv[l].h * p.lv[l].w, 0.f);
+    gp.scratch[l] = scratch[l].data();
+  }
+  // photometry: per (level, sample) sums in fp64 over per-row partials (any fixed order is a valid kernel schedule)
+  std::vector<double> psum((size_t)p.B * p.scales * ROW, 0.0);
+  for (int l = 0; l < p.scales; ++l)
+    for (int b = 0; b < p.B; ++b) {
+      float mats[33] = {0};
+      if (kGeom) {
+        for (int k = 0; k < 9; ++k) mats[k] = gp.Kinv[l][b * 9 + k];
+        for (int k = 0; k < 12; ++k) { mats[9 + k] = gp.P[0][l][b * 12 + k]; mats[21 + k] = gp.P[1][l][b * 12 + k]; }
+      }
+      for (int i = 0; i < p.lv[l].h; ++i) {
+        float acc[Px::kAcc] = {0};
+        for (int j = 0; j < p.lv[l].w; ++j) {
+          const DirectLoads d = Px::load(gp, l, b, i, j);
+          Px::run(gp, l, b, i, j, d, acc, mats);
+        }
+        for (int k = 0; k < Px::kAcc; ++k) psum[((size_t)b * p.scales + l) * ROW + Px::column(k)] += acc[k];
+      }
+    }
+  std::vector<float> scales_buf((size_t)p.B * p.scales * 8, 0.f);
+  if (step) {
+    for (int b = 0; b < p.B; ++b)
+      for (int l = 0; l < p.scales; ++l) {
+        float S[ROW];
+        for (int k = 0; k < ROW; ++k) S[k] = (float)psum[((size_t)b * p.scales + l) * ROW + k];
+        const FlowCombineScales k = flow_combine_scales(S, p.lv[l].h, p.lv[l].w, p.gloss, p.B, b);
+        float* o = scales_buf.data() + ((size_t)b * p.scales + l) * 8;
+        o[0] = k.pix[0]; o[1] = k.pix[1]; o[2] = k.ssim[0]; o[3] = k.ssim[1]; o[4] = k.sm; o[5] = k.cons;
+      }
+  }
+  // stencil tiles
+  std::vector<float> sm(Tile::kSmemFloats);
+  std::vector<double> ssum((size_t)p.B * p.scales * ROW, 0.0);
+  for (int tile = 0; tile < p.total_tiles; ++tile) {
+    const TileCoord tc = decode_tile<TW, TH>(p, tile);
+    float acc[Tile::kAcc] = {0};
+    std::vector<float2> g3v((size_t)Tile::kP3 * 4, make_float2(0.f, 0.f));
+    float2 (*g3)[4] = reinterpret_cast<float2 (*)[4]>(g3v.data());
+    Tile::load_group_plain(gp, tc, 0, 0, 1, sm.data());
+    Tile::load_group_plain(gp, tc, 1, 0, 1, sm.data());
+    for (int c = 0; c < 3; ++c) {
+      Tile::convert_channel(c, 0, 1, sm.data());
+      Tile::phase2(gp, tc, c, 0, 1, sm.data(), acc);
+      if (c == 0) Tile::phase2(gp, tc, 3, 0, 1, sm.data(), acc);
+      Tile::phase3_accumulate(gp, tc, c, 0, 1, sm.data(), g3);
+      if (c < 2) Tile::load_group_plain(gp, tc, c + 2, 0, 1, sm.data());
+    }
+    std::vector<float4> prev((size_t)Tile::kP3 * 3);
+    float4 (*pre)[3] = reinterpret_cast<float4 (*)[3]>(prev.data());
+    if (step) Tile::prefetch_step(gp, tc, 0, 1, pre);
+    else Tile::phase3_store(gp, tc, 0, 1, g3);
+    Tile::convert_flows(0, 1, sm.data());
+    Tile::phase4a(gp, tc, 0, 1, sm.data(), acc);
+    if (step) {
+      const float* o = scales_buf.data() + ((size_t)tc.b * p.scales + tc.level) * 8;
+      FlowCombineScales k;
+      k.pix[0] = o[0]; k.pix[1] = o[1]; k.ssim[0] = o[2]; k.ssim[1] = o[3]; k.sm = o[4]; k.cons = o[5];
+      Tile::phase4b_step(gp, tc, k, 0, 1, sm.data(), g3, pre);
+    } else {
+      Tile::phase4b(gp, tc, 0, 1, sm.data());
+    }
+    for (int k = 0; k < Tile::kAcc; ++k) ssum[((size_t)tc.b * p.scales + tc.level) * ROW + Tile::column(k)] += acc[k];
+  }
+  for (int b = 0; b < p.B; ++b) {
+    float tot[4] = {0, 0, 0, 0};
+    for (int l = 0; l < p.scales; ++l) {
+      float S[ROW], out[4];
+      for (int k = 0; k < ROW; ++k) {
+        S[k] = (float)(Px::is_photo_column(k) ? psum[((size_t)b * p.scales + l) * ROW + k] : ssum[((size_t)b * p.scales + l) * ROW + k]);
+        p.stats[((size_t)b * p.scales + l) * ROW + k] = S[k];
+      }
+      if (kGeom) geom_level_losses(S, p.lv[l].h, p.lv[l].w, out); else flow_level_losses(S, p.lv[l].h, p.lv[l].w, out);
+      for (int k = 0; k < 4; ++k) tot[k] += out[k];
+    }
+    for (int k = 0; k < 4; ++k) p.loss[k * p.B + b] = tot[k];
+  }
+  return 0;
+}
+
+extern "C" int emu_flow_loss_split_forward_grad(const UglFlowLossArgs* a) {
+  FlowGradParams gp;
+  fill_params<kBTW, kBTH>(a, false, gp.base);
+  for (int l = 0; l < a->scales; ++l) gp.basis[l] = a->basis[l];
+  return emu_flow_split<false>(gp, 0);
+}
+
+extern "C" int emu_flow_loss_step(const UglFlowLossArgs* a) {
+  FlowGradParams gp;
+  fill_params<kBTW, kBTH>(a, true, gp.base);
+  return emu_flow_split<false>(gp, 1);
+}
+
+extern "C" int emu_geom_flow_split_forward_grad(const UglGeomFlowArgs* g) {
+  const UglFlowLossArgs* a = &g->flow;
+  FlowGradParams gp;
+  fill_params<kBTW, kBTH>(a, false, gp.base);
+  for (int l = 0; l < a->scales; ++l) {
+    gp.basis[l] = a->basis[l]; gp.disp[l] = g->disp[l]; gp.Kinv[l] = g->Kinv[l];
+    gp.P[0][l] = g->P_bwd[l]; gp.P[1][l] = g->P_fwd[l]; gp.mask_bytes[l] = g->mask_bytes[l];
+  }
+  gp.alpha = g->alpha; gp.beta = g->beta;
+  return emu_flow_split<true>(gp, 0);
 }
 
 extern "C" int emu_flow_loss_combine(const UglFlowLossArgs* a) {

@@ -75,7 +75,35 @@ def emu_flow_loss_single_pass(img_l, img, img_r, flows_fwd, flows_bwd, scales, g
     return loss, gf, gb, stats
 
 
-def emu_geom_flow(img_l, img, img_r, flows_fwd, flows_bwd, disp, Kinv, P_b, P_f, alpha, beta, scales, gloss):
+def emu_flow_loss_split(img_l, img, img_r, flows_fwd, flows_bwd, scales, gloss):
+    """split form (photometry pixels -> photometry planes -> stencil tiles) + combine via the host emulator"""
+    B = img[0].shape[0]
+    loss = torch.zeros(4, B)
+    stats = torch.zeros(B, scales, _cabi.FLOW_NSTATS)
+    gf = [torch.zeros_like(f) for f in flows_fwd[:scales]]
+    gb = [torch.zeros_like(f) for f in flows_bwd[:scales]]
+    basis = [torch.zeros(B, _cabi.FLOW_BASIS_PLANES, f.shape[2], f.shape[3]) for f in flows_fwd[:scales]]
+    a = flow_loss_args(img_l, img, img_r, flows_fwd, flows_bwd, scales, loss, stats, gloss, gf, gb)
+    for l in range(scales):
+        a.basis[l] = basis[l].data_ptr()
+    emu().emu_flow_loss_split_forward_grad(C.byref(a))
+    emu().emu_flow_loss_combine(C.byref(a))
+    return loss, gf, gb, stats
+
+
+def emu_flow_loss_step(img_l, img, img_r, flows_fwd, flows_bwd, scales, gloss):
+    """the fused training step (stencil tiles write the flow gradients) via the host emulator"""
+    B = img[0].shape[0]
+    loss = torch.zeros(4, B)
+    stats = torch.zeros(B, scales, _cabi.FLOW_NSTATS)
+    gf = [torch.zeros_like(f) for f in flows_fwd[:scales]]
+    gb = [torch.zeros_like(f) for f in flows_bwd[:scales]]
+    a = flow_loss_args(img_l, img, img_r, flows_fwd, flows_bwd, scales, loss, stats, gloss, gf, gb)
+    emu().emu_flow_loss_step(C.byref(a))
+    return loss, gf, gb, stats
+
+
+def emu_geom_flow(img_l, img, img_r, flows_fwd, flows_bwd, disp, Kinv, P_b, P_f, alpha, beta, scales, gloss, split=False):
     """geom-mode flow branch (forward_grad + combine) via the host emulator -> loss (4,B), grads, mask bytes"""
     B = img[0].shape[0]
     loss = torch.zeros(4, B)
@@ -91,7 +119,7 @@ def emu_geom_flow(img_l, img, img_r, flows_fwd, flows_bwd, disp, Kinv, P_b, P_f,
         g.disp[l], g.Kinv[l], g.P_bwd[l], g.P_fwd[l] = disp[l].data_ptr(), Kinv[l].data_ptr(), P_b[l].data_ptr(), P_f[l].data_ptr()
         g.mask_bytes[l] = masks[l].data_ptr()
     g.alpha, g.beta = alpha, beta
-    emu().emu_geom_flow_forward_grad(C.byref(g))
+    (emu().emu_geom_flow_split_forward_grad if split else emu().emu_geom_flow_forward_grad)(C.byref(g))
     emu().emu_geom_flow_combine(C.byref(g))
     return loss, gf, gb, masks
 

@@ -33,7 +33,8 @@ def test_flow_loss_tiles_vs_oracle(B, Hh, W, scales, px, oob):
     pl, pc, pr = P.box_pyramid(t.img_l, L), P.box_pyramid(t.img, L), P.box_pyramid(t.img_r, L)
     ff = [f.detach().contiguous() for f in t.flows_fwd]
     fb = [f.detach().contiguous() for f in t.flows_bwd]
-    for emu_fn in (H.emu_flow_loss, H.emu_flow_loss_single_pass):       # recompute kernels, single-pass kernels
+    # recompute kernels, fused single-pass tile kernel, split kernels (+ combine), split kernels as the fused training step
+    for emu_fn in (H.emu_flow_loss, H.emu_flow_loss_single_pass, H.emu_flow_loss_split, H.emu_flow_loss_step):
         el, egf, egb, _ = emu_fn(pl, pc, pr, ff, fb, scales, gl)
         for k in range(4):
             assert loss_rel_err(el[k], loss[KEYS[k]]) < LOSS_RTOL, KEYS[k]
@@ -107,9 +108,11 @@ def _geom_projections(t, S):
     return Kinv, Pb, Pf
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("B,Hh,W,S", [(2, 48, 96, 3), (1, 40, 72, 2), (1, 34, 50, 1)])
-def test_geom_flow_tiles_vs_oracle(B, Hh, W, S):
-    """geom-mode variant of the single-pass kernel: flow-branch losses, flow gradients and the packed masks"""
+def test_geom_flow_tiles_vs_oracle(B, Hh, W, S, split):
+    """geom-mode variant of the single-pass kernel (split=False: fused tile kernel; True: photometry pixels + stencil tiles):
+    flow-branch losses, flow gradients and the packed masks"""
     t = make_triplet(B, Hh, W, flow_levels=S, depth_scales=S, seed=11, flow_mode="rigid", flow_px=1.5)
     keys = ("loss_flow_pixel", "loss_flow_ssim", "loss_flow_smooth", "loss_flow_consis")
     gl = torch.rand(4, B, generator=torch.Generator().manual_seed(2)) + 0.5
@@ -120,7 +123,7 @@ def test_geom_flow_tiles_vs_oracle(B, Hh, W, S):
     pl, pc, pr = P.bilinear_pyramid(t.img_l, S), P.bilinear_pyramid(t.img, S), P.bilinear_pyramid(t.img_r, S)
     Kinv, Pb, Pf = _geom_projections(t, S)
     el, egf, egb, masks = H.emu_geom_flow(pl, pc, pr, [f.detach().contiguous() for f in ff], [f.detach().contiguous() for f in fb],
-                                          [d.detach().contiguous() for d in t.disp[:S]], Kinv, Pb, Pf, 0.01, 0.5, S, gl)
+                                          [d.detach().contiguous() for d in t.disp[:S]], Kinv, Pb, Pf, 0.01, 0.5, S, gl, split=split)
     for bit, name in ((1, "valid_b"), (2, "valid_f"), (4, "occ_b"), (8, "occ_f"), (16, "dyn_b"), (32, "dyn_f")):
         for s in range(S):
             got = ((masks[s] & bit) != 0).float().unsqueeze(1)
