@@ -198,7 +198,6 @@ static int emu_flow_split(FlowGradParams& gp, int step) {
     for (int c = 0; c < 3; ++c) {
       Tile::convert_channel(c, 0, 1, sm.data());
       Tile::phase2(gp, tc, c, 0, 1, sm.data(), acc);
-      if (c == 0) Tile::phase2(gp, tc, 3, 0, 1, sm.data(), acc);
       Tile::phase3_accumulate(gp, tc, c, 0, 1, sm.data(), g3);
       if (c < 2) Tile::load_group_plain(gp, tc, c + 2, 0, 1, sm.data());
     }
@@ -207,6 +206,7 @@ static int emu_flow_split(FlowGradParams& gp, int step) {
     if (step) Tile::prefetch_step(gp, tc, 0, 1, pre);
     else Tile::phase3_store(gp, tc, 0, 1, g3);
     Tile::convert_flows(0, 1, sm.data());
+    Tile::phase2(gp, tc, 3, 0, 1, sm.data(), acc);
     Tile::phase4a(gp, tc, 0, 1, sm.data(), acc);
     if (step) {
       const float* o = scales_buf.data() + ((size_t)tc.b * p.scales + tc.level) * 8;

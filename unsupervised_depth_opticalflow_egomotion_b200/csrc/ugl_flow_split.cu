@@ -209,7 +209,6 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
     Tile::convert_channel(c, tid, NT, sm);
     __syncthreads();
     Tile::phase2(gp, tc, c, tid, NT, sm, acc);
-    if (c == 0) Tile::phase2(gp, tc, 3, tid, NT, sm, acc);   // smoothness edge weights
     __syncthreads();
     Tile::phase3_accumulate(gp, tc, c, tid, NT, sm, g3);
     __syncthreads();                   // ring slot c & 1, the x plane and the coefficient planes are free again
@@ -220,6 +219,8 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
   else Tile::phase3_store(gp, tc, tid, NT, g3);
   arrived(3);
   Tile::convert_flows(tid, NT, sm);
+  __syncthreads();
+  Tile::phase2(gp, tc, 3, tid, NT, sm, acc);   // smoothness edge weights, over the raw flow planes (converted above)
   __syncthreads();
   Tile::phase4a(gp, tc, tid, NT, sm, acc);
   __syncthreads();

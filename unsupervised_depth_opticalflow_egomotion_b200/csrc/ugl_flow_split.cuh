@@ -151,9 +151,9 @@ struct FlowPhotoPixel {
 //   kOffStage  2 slots x { W[c] pair plane (halo 2) -> y = W * w in place ; 2 pair planes w dW[c]/d(u|v) (no halo) }
 //   kOffX      x pair plane of the current channel (halo 2)
 //   kOffCoef   3 pair planes A, B, C of the current channel (halo 1)
-//   kOffEdge   2 scalar planes wx, wy (halo 1)
 // Smoothness phases (after the last channel): the four raw flow planes arrive in slot 1, are divided by 20 and interleaved into
-// two (u, v) pair planes in slot 0; the signed second differences (4 pair planes, halo 1) go over x + coefficient planes.
+// two (u, v) pair planes in slot 0; then the edge weights wx, wy (2 scalar planes, halo 1) are formed from I over the dead raw flow
+// planes; the signed second differences (4 pair planes, halo 1) go over x + coefficient planes.  56 KB in all: four CTAs per SM.
 template <int TW, int TH, int NT, bool kGeom>
 struct FlowStencilTile {
   static_assert(TW % 2 == 0, "1x2 micro-tiles need an even tile width");
@@ -174,12 +174,12 @@ struct FlowStencilTile {
   static constexpr int kStage = kPairP + 2 * kPairT;
   static constexpr int kOffX = kOffStage + 2 * kStage;
   static constexpr int kOffCoef = kOffX + kPairP;
-  static constexpr int kOffEdge = kOffCoef + 3 * kPairC;
-  static constexpr int kSmemFloats = kOffEdge + 2 * kScalC;
+  static constexpr int kSmemFloats = kOffCoef + 3 * kPairC;
   static constexpr int kOffRawFlow = kOffStage + kStage;          // 4 scalar planes (uf, vf, ub, vb), halo 2, in slot 1
+  static constexpr int kOffEdge = kOffRawFlow;                    // wx, wy (halo 1): over the raw flow planes once those are converted
   static constexpr int kOffF2 = kOffStage;                        // 2 pair planes (u, v) / 20 of the fwd / bwd flow, in slot 0
   static constexpr int kOffS4 = kOffX;                            // 4 pair planes of signed weights (halo 1)
-  static_assert(4 * kScalP <= kStage && 2 * kPairP <= kStage, "flow planes must fit a ring slot");
+  static_assert(4 * kScalP <= kStage && 2 * kPairP <= kStage && 2 * kScalC <= kStage, "flow planes / edge planes must fit a ring slot");
   static_assert(4 * kPairC <= kPairP + 3 * kPairC, "phase-4 planes must fit over the x + coefficient planes");
   static_assert(SPW % 2 == 0 && kScalX % 2 == 0 && CW % 2 == 0, "pair planes are read as float4 (two pixels x two directions)");
   static constexpr int kAcc = 6;                                  // SSIM_F, SSIM_B, SMX_F, SMY_F, SMX_B, SMY_B

@@ -13,7 +13,7 @@ namespace ugl {
 #define UGL_SPLIT_NT 256
 #endif
 #ifndef UGL_STENCIL_MINB
-#define UGL_STENCIL_MINB 3
+#define UGL_STENCIL_MINB 4
 #endif
 #ifndef UGL_PHOTO_MINB
 #define UGL_PHOTO_MINB 3
