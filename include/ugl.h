@@ -175,6 +175,13 @@ int ugl_warp_flow_forward(const float* x, const float* flow, int32_t batch, int3
 int ugl_warp_flow_backward(const float* x, const float* flow, const float* grad_out, int32_t batch, int32_t channels,
                            int32_t height, int32_t width, int32_t use_mask, float* grad_flow, float* grad_x,
                            void* workspace, uint64_t workspace_bytes, void* stream);
+/* scatter form of grad_x (same bits either way; the global form is kept as the cross-check): TILE_LOCAL accumulates a CTA's taps in
+ * a shared-memory window (tile + 8 pixels) and touches each global cell once; GLOBAL issues one 64-bit global atomic per tap corner. */
+#define UGL_SCATTER_TILE_LOCAL 0
+#define UGL_SCATTER_GLOBAL 1
+int ugl_warp_flow_backward_ex(const float* x, const float* flow, const float* grad_out, int32_t batch, int32_t channels,
+                              int32_t height, int32_t width, int32_t use_mask, float* grad_flow, float* grad_x,
+                              void* workspace, uint64_t workspace_bytes, int32_t scatter, void* stream);
 uint64_t ugl_warp_flow_backward_workspace_bytes(int32_t batch, int32_t channels, int32_t height, int32_t width,
                                                 int32_t need_grad_x);
 
@@ -194,6 +201,8 @@ int ugl_cost_volume_backward(const float* f1, const float* f2, const float* grad
 uint64_t ugl_forward_splat_workspace_bytes(int32_t batch, int32_t channels, int32_t height, int32_t width);
 int ugl_forward_splat(const float* x, const float* flow, int32_t batch, int32_t channels, int32_t height, int32_t width,
                       int32_t clamp01, float* out, void* workspace, uint64_t workspace_bytes, void* stream);
+int ugl_forward_splat_ex(const float* x, const float* flow, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                      int32_t clamp01, float* out, void* workspace, uint64_t workspace_bytes, int32_t scatter, void* stream);
 
 /* Dataset glue: uint8 frames -> fp32 frames in [0,1], the arithmetic of core/dataset/kitti_prepared.py:89
  * (`img / 255.0` in float64, then `.float()`): for every byte value the result equals the correctly rounded fp32 quotient this

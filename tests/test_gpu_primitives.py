@@ -42,6 +42,28 @@ def test_warp_flow_vs_oracle(cuda_device, B, C, H, W, px):
         assert torch.equal(gx, gx2)                               # deterministic scatter (no fp atomics)
 
 
+@pytest.mark.parametrize("B,C,H,W,px", [(2, 3, 64, 208, 2.0), (1, 33, 32, 104, 6.0), (2, 1, 17, 23, 30.0), (1, 130, 16, 52, 1.0),
+                                        (1, 6, 45, 70, 12.0)])
+def test_scatter_forms_same_bits(cuda_device, monkeypatch, B, C, H, W, px):
+    """The tile-local scatter (shared-memory window per CTA, lo/hi 32-bit words with carry) and the global-atomic form sum the same
+    64-bit fixed-point terms: grad_x of warp_flow and the forward splat are bit-identical, whatever leaves the window (px > 8)."""
+    g = torch.Generator().manual_seed(B * 100 + C)
+    x = torch.rand(B, C, H, W, generator=g).to(cuda_device)
+    flow = (px * torch.randn(B, 2, H, W, generator=g)).to(cuda_device)
+    flow[:, :, : H // 3] *= 0.05                                   # a sub-pixel region: every tap of a tile lands in a few cells (carries)
+    go = (1e3 * torch.randn(B, C, H, W, generator=g)).to(cuda_device)
+    res = {}
+    for form in ("tile_local", "global"):
+        monkeypatch.setattr(ops, "SCATTER_FORM", form)
+        for use_mask in (False, True):
+            xd = x.clone().requires_grad_(True)
+            res[form, use_mask], = torch.autograd.grad((ops.warp_flow(xd, flow, use_mask) * go).sum(), [xd])
+        res[form, "splat"] = ops.forward_splat(x, flow)
+    for key in (False, True, "splat"):
+        assert torch.equal(res["tile_local", key], res["global", key]), key
+    assert res["tile_local", False].abs().max() > 0
+
+
 @pytest.mark.parametrize("mode", ["box", "bilinear"])
 def test_image_pyramid_bit_exact(cuda_device, mode):
     img = torch.rand(2, 3, 256, 832, generator=torch.Generator().manual_seed(4))

@@ -160,8 +160,11 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "ugl_warp_flow_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "ugl_warp_flow_backward_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]),
     "ugl_warp_flow_backward_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
 }
+SCATTER_FORMS = {"tile_local": 0, "global": 1}     # include/ugl.h: UGL_SCATTER_*
 
 _i, _u64, _p, _f, _i64 = C.c_int32, C.c_uint64, C.c_void_p, C.c_float, C.c_int64
 _pp = C.POINTER(C.c_void_p)
@@ -169,6 +172,7 @@ _ip = C.POINTER(C.c_int32)
 SIGNATURES.update({
     "ugl_forward_splat_workspace_bytes": (_u64, [_i, _i, _i, _i]),
     "ugl_forward_splat": (C.c_int, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _u64, _p]),
+    "ugl_forward_splat_ex": (C.c_int, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _u64, _i, _p]),
     "ugl_selftest_packed_pairs": (C.c_int, [_p, _i, _i, _p]),
     "ugl_frames_u8_to_float": (C.c_int, [_pp, _pp, _i, _u64, _p]),
     "ugl_depth_photo_workspace_bytes": (_u64, [C.POINTER(UglDepthPhotoArgs)]),

@@ -89,6 +89,74 @@ splat_scatter_kernel(const float* __restrict__ x, const float* __restrict__ flow
   }
 }
 
+// Tile-local form of the two scatters above (ugl_scatter.cuh: ScatterWindow): a CTA takes a 32 x 8 tile of source pixels of one
+// sample and a chunk of channels; four channels share one pass over the window.  kSplat: the forward splat (values x, tap at the
+// pixel-unit target) instead of the warp backward (values grad_out * keep, tap of the normalised grid).  Bit-identical to the global
+// form: integer sums.
+constexpr int kScTW = 32, kScTH = 8, kScM = 8, kScCP = 4;
+using WarpScatterWindow = ScatterWindow<kScTW, kScTH, kScM, kScCP>;
+
+template <bool kSplat>
+__global__ void __launch_bounds__(kScTW* kScTH)
+scatter_tiled_kernel(const float* __restrict__ flow, const float* __restrict__ val, int B, int C, int H, int W, int use_mask,
+                     const unsigned* __restrict__ maxbits, unsigned long long* __restrict__ acc, int tiles_x, int tiles_y, int cchunk) {
+  __shared__ unsigned win[WarpScatterWindow::kWords];
+  const long plane = (long)H * W;
+  const int e = fixed_point_exponent(__uint_as_float(*maxbits), plane);
+  const int tid = threadIdx.x, nt = kScTW * kScTH;
+  int tile = blockIdx.x;
+  const int b = tile / (tiles_x * tiles_y);
+  tile -= b * tiles_x * tiles_y;
+  const int x0 = (tile % tiles_x) * kScTW, y0 = (tile / tiles_x) * kScTH;
+  const int wx0 = x0 - kScM, wy0 = y0 - kScM;
+  const int c_begin = blockIdx.y * cchunk, c_end = min(C, c_begin + cchunk);
+  const int j = x0 + (tid & (kScTW - 1)), i = y0 + tid / kScTW;
+  const long pix = (long)i * W + j;
+  Tap t;
+  t.inb = 0u;
+  float keep = 0.f;
+  if (j < W && i < H) {
+    const float u = flow[((long)b * 2) * plane + pix], v = flow[((long)b * 2 + 1) * plane + pix];
+    if (kSplat) {
+      t = make_tap(add_rn((float)j, u), add_rn((float)i, v), W, H);
+      keep = 1.0f;
+    } else {
+      t = flow_tap(j, i, u, v, make_warp_geom(W, H));
+      keep = use_mask ? tap_keep(t) : 1.0f;
+    }
+  }
+  const bool active = keep != 0.f && t.inb != 0u;
+  const bool local = WarpScatterWindow::local(t, wx0, wy0);
+  WarpScatterWindow::clear(win, tid, nt);
+  __syncthreads();
+  for (int c0 = c_begin; c0 < c_end; c0 += kScCP) {
+    const int ncp = min(kScCP, c_end - c0);
+    unsigned long long* plane0 = acc + ((long)b * C + c0) * plane;
+    if (active) {
+      for (int k = 0; k < ncp; ++k) {
+        const float g = val[((long)b * C + c0 + k) * plane + pix] * keep;
+        if (local) WarpScatterWindow::add_local(win, k, wx0, wy0, t, g, e);
+        else scatter_tap(plane0 + k * plane, W, t, g, e);
+      }
+    }
+    __syncthreads();
+    WarpScatterWindow::flush(win, ncp, wx0, wy0, plane0, plane, W, tid, nt);
+    __syncthreads();
+  }
+}
+
+// grid of the tiled scatter: tiles x channel chunks, at least ~8 CTAs per SM when the channels allow it
+static void scatter_tiled_grid(int B, int C, int H, int W, dim3& grid, int& tiles_x, int& tiles_y, int& cchunk) {
+  tiles_x = (W + kScTW - 1) / kScTW;
+  tiles_y = (H + kScTH - 1) / kScTH;
+  const long tiles = (long)B * tiles_x * tiles_y;
+  long chunks = (148L * 8 + tiles - 1) / tiles;
+  const long max_chunks = (C + kScCP - 1) / kScCP;
+  chunks = chunks < 1 ? 1 : (chunks > max_chunks ? max_chunks : chunks);
+  cchunk = (int)(((C + chunks - 1) / chunks + kScCP - 1) / kScCP * kScCP);
+  grid = dim3((unsigned)tiles, (unsigned)((C + cchunk - 1) / cchunk), 1);
+}
+
 __global__ void __launch_bounds__(kPrimThreads)
 fixed_to_float_clamp_kernel(const unsigned long long* __restrict__ acc, long n, long n_contrib, const unsigned* __restrict__ maxbits,
                             int clamp01, float* __restrict__ out) {
@@ -284,7 +352,15 @@ extern "C" uint64_t ugl_warp_flow_backward_workspace_bytes(int32_t B, int32_t C,
 extern "C" int ugl_warp_flow_backward(const float* x, const float* flow, const float* grad_out, int32_t B, int32_t C,
                                       int32_t H, int32_t W, int32_t use_mask, float* grad_flow, float* grad_x,
                                       void* workspace, uint64_t workspace_bytes, void* stream) {
+  return ugl_warp_flow_backward_ex(x, flow, grad_out, B, C, H, W, use_mask, grad_flow, grad_x, workspace, workspace_bytes,
+                                   UGL_SCATTER_TILE_LOCAL, stream);
+}
+
+extern "C" int ugl_warp_flow_backward_ex(const float* x, const float* flow, const float* grad_out, int32_t B, int32_t C,
+                                         int32_t H, int32_t W, int32_t use_mask, float* grad_flow, float* grad_x,
+                                         void* workspace, uint64_t workspace_bytes, int32_t scatter, void* stream) {
   if (!x || !flow || !grad_out) return fail(UGL_EINVAL, "warp_flow_backward: null pointer");
+  if (scatter != UGL_SCATTER_TILE_LOCAL && scatter != UGL_SCATTER_GLOBAL) return fail(UGL_EINVAL, "warp_flow_backward: unknown scatter form %d", scatter);
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(UGL_EINVAL, "warp_flow_backward: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long n = (long)B * H * W;
@@ -304,8 +380,16 @@ extern "C" int ugl_warp_flow_backward(const float* x, const float* flow, const f
     if (e != cudaSuccess) return fail((int)e, "warp_flow_backward: memset: %s", cudaGetErrorString(e));
     absmax_kernel<<<grid_for(nx), kPrimThreads, 0, st>>>(grad_out, nx, maxbits);
     if ((rc = check_launch("absmax_kernel"))) return rc;
-    warp_bwd_scatter_kernel<<<grid_for(n), kPrimThreads, 0, st>>>(flow, grad_out, B, C, H, W, use_mask, maxbits, acc);
-    if ((rc = check_launch("warp_bwd_scatter_kernel"))) return rc;
+    if (scatter == UGL_SCATTER_GLOBAL) {
+      warp_bwd_scatter_kernel<<<grid_for(n), kPrimThreads, 0, st>>>(flow, grad_out, B, C, H, W, use_mask, maxbits, acc);
+      if ((rc = check_launch("warp_bwd_scatter_kernel"))) return rc;
+    } else {
+      dim3 grid;
+      int tx, ty, cchunk;
+      scatter_tiled_grid(B, C, H, W, grid, tx, ty, cchunk);
+      scatter_tiled_kernel<false><<<grid, kScTW * kScTH, 0, st>>>(flow, grad_out, B, C, H, W, use_mask, maxbits, acc, tx, ty, cchunk);
+      if ((rc = check_launch("scatter_tiled_kernel<warp backward>"))) return rc;
+    }
     fixed_to_float_kernel<<<grid_for(nx), kPrimThreads, 0, st>>>(acc, nx, (long)H * W, maxbits, grad_x);
     if ((rc = check_launch("fixed_to_float_kernel"))) return rc;
   }
@@ -318,7 +402,13 @@ extern "C" uint64_t ugl_forward_splat_workspace_bytes(int32_t B, int32_t C, int3
 
 extern "C" int ugl_forward_splat(const float* x, const float* flow, int32_t B, int32_t C, int32_t H, int32_t W, int32_t clamp01,
                                  float* out, void* workspace, uint64_t workspace_bytes, void* stream) {
+  return ugl_forward_splat_ex(x, flow, B, C, H, W, clamp01, out, workspace, workspace_bytes, UGL_SCATTER_TILE_LOCAL, stream);
+}
+
+extern "C" int ugl_forward_splat_ex(const float* x, const float* flow, int32_t B, int32_t C, int32_t H, int32_t W, int32_t clamp01,
+                                    float* out, void* workspace, uint64_t workspace_bytes, int32_t scatter, void* stream) {
   if (!x || !flow || !out) return fail(UGL_EINVAL, "forward_splat: null pointer");
+  if (scatter != UGL_SCATTER_TILE_LOCAL && scatter != UGL_SCATTER_GLOBAL) return fail(UGL_EINVAL, "forward_splat: unknown scatter form %d", scatter);
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(UGL_EINVAL, "forward_splat: bad shape");
   const uint64_t need = ugl_forward_splat_workspace_bytes(B, C, H, W);
   if (!workspace || workspace_bytes < need) return fail(UGL_EWORKSPACE, "forward_splat: workspace too small");
@@ -332,8 +422,16 @@ extern "C" int ugl_forward_splat(const float* x, const float* flow, int32_t B, i
   int rc;
   absmax_kernel<<<grid_for(nx), kPrimThreads, 0, st>>>(x, nx, maxbits);
   if ((rc = check_launch("absmax_kernel"))) return rc;
-  splat_scatter_kernel<<<grid_for(n), kPrimThreads, 0, st>>>(x, flow, B, C, H, W, maxbits, acc);
-  if ((rc = check_launch("splat_scatter_kernel"))) return rc;
+  if (scatter == UGL_SCATTER_GLOBAL) {
+    splat_scatter_kernel<<<grid_for(n), kPrimThreads, 0, st>>>(x, flow, B, C, H, W, maxbits, acc);
+    if ((rc = check_launch("splat_scatter_kernel"))) return rc;
+  } else {
+    dim3 grid;
+    int tx, ty, cchunk;
+    scatter_tiled_grid(B, C, H, W, grid, tx, ty, cchunk);
+    scatter_tiled_kernel<true><<<grid, kScTW * kScTH, 0, st>>>(flow, x, B, C, H, W, 0, maxbits, acc, tx, ty, cchunk);
+    if ((rc = check_launch("scatter_tiled_kernel<splat>"))) return rc;
+  }
   fixed_to_float_clamp_kernel<<<grid_for(nx), kPrimThreads, 0, st>>>(acc, nx, (long)H * W, maxbits, clamp01, out);
   return check_launch("fixed_to_float_clamp_kernel");
 }

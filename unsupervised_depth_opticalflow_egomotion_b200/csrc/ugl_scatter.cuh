@@ -45,6 +45,61 @@ __device__ __forceinline__ void scatter_tap(unsigned long long* __restrict__ pla
   }
 }
 
+// ---- tile-local form --------------------------------------------------------------------------------------------------------
+// A CTA owns a TW x TH tile of SOURCE pixels.  Warps are local: most taps land within a few pixels of their source, so the CTA
+// accumulates them in a shared-memory window (the tile plus a margin of M pixels) and sends each touched window cell to the global
+// 64-bit plane ONCE; only taps that leave the window use a global atomic of their own.  The arithmetic is the same 64-bit fixed point
+// as scatter_tap (integer sums: the split into window and global adds cannot change the result, bit for bit).  Shared memory has no
+// native 64-bit add (ATOMS.CAST.SPIN loop), so a cell is two 32-bit words: `lo` wraps, and the ONE add that observes the wrap carries
+// into `hi`: sum = hi * 2^32 + lo exactly, whatever the order.
+template <int TW, int TH, int M, int CP>
+struct ScatterWindow {
+  static constexpr int WW = TW + 2 * M, WH = TH + 2 * M, N = WW * WH;   // window cells per channel
+  static constexpr int kWords = 2 * CP * N;                             // lo[CP][N] then hi[CP][N]
+
+  __device__ static __forceinline__ long long to_fixed(float v, int e) { return __double2ll_rn(ldexp((double)v, e)); }
+
+  // all four corners of the tap inside the window whose cell (0,0) is image pixel (wx0, wy0)?
+  __device__ static __forceinline__ bool local(const Tap& t, int wx0, int wy0) {
+    const int wx = t.x0 - wx0, wy = t.y0 - wy0;
+    return wx >= 0 && wx < WW - 1 && wy >= 0 && wy < WH - 1;
+  }
+
+  __device__ static __forceinline__ void add_local(unsigned* __restrict__ win, int k, int wx0, int wy0, const Tap& t, float g, int e) {
+    const float wgt[4] = {t.wnw, t.wne, t.wsw, t.wse};
+    const int off[4] = {0, 1, WW, WW + 1};
+    unsigned* lo = win + k * N + (t.y0 - wy0) * WW + (t.x0 - wx0);
+    unsigned* hi = lo + CP * N;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (t.inb & (1u << c)) {
+        const long long q = to_fixed(g * wgt[c], e);
+        if (q == 0) continue;
+        const unsigned ql = (unsigned)q, qh = (unsigned)((unsigned long long)q >> 32);
+        const unsigned old = atomicAdd(lo + off[c], ql);
+        atomicAdd(hi + off[c], qh + ((unsigned)(old + ql) < ql ? 1u : 0u));
+      }
+    }
+  }
+
+  __device__ static __forceinline__ void clear(unsigned* __restrict__ win, int tid, int nt) {
+    for (int idx = tid; idx < kWords; idx += nt) win[idx] = 0u;
+  }
+
+  // send the touched cells of channels [0, ncp) to their global planes (plane k = plane0 + k * plane_stride) and clear them
+  __device__ static __forceinline__ void flush(unsigned* __restrict__ win, int ncp, int wx0, int wy0, unsigned long long* __restrict__ plane0,
+                                               long plane_stride, int W, int tid, int nt) {
+    for (int idx = tid; idx < ncp * N; idx += nt) {
+      const unsigned lo = win[idx], hi = win[CP * N + idx];
+      if ((lo | hi) == 0u) continue;
+      const int k = idx / N, r = idx - k * N, wy = r / WW, wx = r - wy * WW;
+      atomicAdd(plane0 + k * plane_stride + (long)(wy0 + wy) * W + (wx0 + wx), ((unsigned long long)hi << 32) | lo);
+      win[idx] = 0u;
+      win[CP * N + idx] = 0u;
+    }
+  }
+};
+
 inline int scatter_grid(long n) {
   long g = (n + 255) / 256;
   const long cap = 148L * 16;

@@ -134,9 +134,10 @@ class _WarpFlowFn(torch.autograd.Function):
         ws_bytes = int(_cabi.lib().ugl_warp_flow_backward_workspace_bytes(B, Cc, H, W, int(need_x)))
         ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.int64, device=x.device) if ws_bytes else None
         with torch.cuda.device_of(x):
-            rc = _cabi.lib().ugl_warp_flow_backward(x.data_ptr(), flow.data_ptr(), gout.data_ptr(), B, Cc, H, W,
-                                                    int(ctx.use_mask), _ptr(gflow), _ptr(gx), _ptr(ws), ws_bytes, _stream_ptr())
-        _cabi.check(rc, "ugl_warp_flow_backward")
+            rc = _cabi.lib().ugl_warp_flow_backward_ex(x.data_ptr(), flow.data_ptr(), gout.data_ptr(), B, Cc, H, W,
+                                                       int(ctx.use_mask), _ptr(gflow), _ptr(gx), _ptr(ws), ws_bytes,
+                                                       _cabi.SCATTER_FORMS[SCATTER_FORM], _stream_ptr())
+        _cabi.check(rc, "ugl_warp_flow_backward_ex")
         _count((1 if need_f else 0) + (4 if need_x else 0))
         return gx, gflow, None
 
@@ -201,6 +202,9 @@ FLOW_LOSS_KEYS = ("loss_flow_pixel", "loss_flow_ssim", "loss_flow_smooth", "loss
 """internal form of the single-pass forward (flow and geom modes): 'split' (photometry kernel + TMA-staged stencil kernel, the
 default), 'split_plain' / 'split_tma' (force the staging form), 'fused' (the one-kernel form).  Same results; a test / profiling knob."""
 SINGLE_PASS_VARIANT = "split"
+SCATTER_FORM = "tile_local"
+"""How warp_flow's grad_x and forward_splat accumulate (include/ugl.h UGL_SCATTER_*): ``tile_local`` (shared-memory window per CTA, each
+global cell touched once) or ``global`` (one 64-bit global atomic per tap corner; the cross-check).  Same bits."""
 
 
 def _variant() -> int:
@@ -1147,8 +1151,8 @@ def forward_splat(x: Tensor, flow: Tensor, clamp01: bool = False) -> Tensor:
     n = int(_cabi.lib().ugl_forward_splat_workspace_bytes(B, Cc, H, W))
     ws = torch.empty((n + 7) // 8, dtype=torch.int64, device=x.device)
     with torch.cuda.device_of(x):
-        _call("ugl_forward_splat", x.data_ptr(), flow.data_ptr(), B, Cc, H, W, int(clamp01), out.data_ptr(), ws.data_ptr(), _nbytes(ws),
-              _stream_ptr(), launches=3)
+        _call("ugl_forward_splat_ex", x.data_ptr(), flow.data_ptr(), B, Cc, H, W, int(clamp01), out.data_ptr(), ws.data_ptr(), _nbytes(ws),
+              _cabi.SCATTER_FORMS[SCATTER_FORM], _stream_ptr(), launches=3)
     return out
 
 
