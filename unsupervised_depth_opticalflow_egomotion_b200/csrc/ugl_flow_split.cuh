@@ -270,15 +270,27 @@ struct FlowStencilTile {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     constexpr int SW = CW / 2;
     constexpr int NS = SW * CH;
+    if (c >= 3) {
+      edge_weights(gp, tc, tid, nt, sm);
+      return;
+    }
+    // Strip order: the first SW - 1 strips of every row, row by row, then the last strip of every row.  With SW - 1 a multiple
+    // of 8 (TW = 32: 16) a quarter-warp's eight 16-byte reads stay inside one row = 128 contiguous bytes; the row-major order
+    // (17 strips per row of pitch 320 bytes) split 45 % of the quarter-warps over two rows whose banks overlap (5.6 wavefronts
+    // per LDS.128 instead of 4).
+    constexpr bool kSplitRows = ((SW - 1) % 8) == 0;
+    constexpr int SM = kSplitRows ? SW - 1 : SW;
     float2 ssim_sum = make_float2(0.f, 0.f);
     const float2 one = splat2(gp.one);
     for (int s = tid; s < NS; s += nt) {
-      const int ly = s / SW, lx = (s - ly * SW) * 2;
+      int ly, lx;
+      if (s < SM * CH) { ly = s / SM; lx = (s - ly * SM) * 2; }
+      else { ly = s - SM * CH; lx = 2 * SM; }
       const int i = tc.y0 - 1 + ly, j0 = tc.x0 - 1 + lx;
       const int c0 = hp(ly + 1, lx + 1);                    // staged-plane index of the left centre
       const bool row_in = (i >= 0 && i < L.h);
       const bool in0 = row_in && j0 >= 0 && j0 < L.w, in1 = row_in && j0 + 1 >= 0 && j0 + 1 < L.w;
-      if (c < 3) {
+      {
         const float* xpl = sm + kOffX + 2 * (c0 - 1);
         const float* ypl = stage(sm, c) + 2 * (c0 - 1);
         Moments2 m[2];
@@ -319,30 +331,36 @@ struct FlowStencilTile {
         *reinterpret_cast<float4*>(oc) = make_float4(cA[0].x, cA[0].y, cA[1].x, cA[1].y);
         *reinterpret_cast<float4*>(oc + kPairC) = make_float4(cB[0].x, cB[0].y, cB[1].x, cB[1].y);
         *reinterpret_cast<float4*>(oc + 2 * kPairC) = make_float4(cC[0].x, cC[0].y, cC[1].x, cC[1].y);
-      } else {
-        float wx[2] = {0.f, 0.f}, wy[2] = {0.f, 0.f};
-        const float* I0 = sm + kOffI, *I1 = I0 + kScalP, *I2 = I1 + kScalP;
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          if (o == 0 ? in0 : in1) {
-            const int cc = c0 + o, j = j0 + o;
-            const float Ic[3] = {I0[cc], I1[cc], I2[cc]};
-            if (j >= 1 && j <= L.w - 2) {
-              const float Iq[3] = {I0[cc + 1], I1[cc + 1], I2[cc + 1]};
-              wx[o] = edge_weight10(Ic, Iq);
-            }
-            if (i >= 1 && i <= L.h - 2) {
-              const float Iq[3] = {I0[cc + SPW], I1[cc + SPW], I2[cc + SPW]};
-              wy[o] = edge_weight10(Ic, Iq);
-            }
-          }
-        }
-        *reinterpret_cast<float2*>(sm + kOffEdge + ly * CW + lx) = make_float2(wx[0], wx[1]);
-        *reinterpret_cast<float2*>(sm + kOffEdge + kScalC + ly * CW + lx) = make_float2(wy[0], wy[1]);
       }
     }
     acc[0] += ssim_sum.x;
     acc[1] += ssim_sum.y;
+  }
+
+  // smoothness edge weights wx, wy of every pixel of the halo-1 region, one pixel per thread (consecutive lanes read consecutive
+  // words of the three image planes: the 1x2 strips of the SSIM passes read them with stride 2 = twice the wavefronts)
+  static UGL_HD void edge_weights(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, float* sm) {
+    const FlowLevelDesc& L = gp.base.lv[tc.level];
+    const float* I0 = sm + kOffI, *I1 = I0 + kScalP, *I2 = I1 + kScalP;
+    for (int s = tid; s < CN; s += nt) {
+      const int ly = s / CW, lx = s - ly * CW;
+      const int i = tc.y0 - 1 + ly, j = tc.x0 - 1 + lx;
+      float wx = 0.f, wy = 0.f;
+      if (i >= 0 && i < L.h && j >= 0 && j < L.w) {
+        const int cc = hp(ly + 1, lx + 1);
+        const float Ic[3] = {I0[cc], I1[cc], I2[cc]};
+        if (j >= 1 && j <= L.w - 2) {
+          const float Iq[3] = {I0[cc + 1], I1[cc + 1], I2[cc + 1]};
+          wx = edge_weight10(Ic, Iq);
+        }
+        if (i >= 1 && i <= L.h - 2) {
+          const float Iq[3] = {I0[cc + SPW], I1[cc + SPW], I2[cc + SPW]};
+          wy = edge_weight10(Ic, Iq);
+        }
+      }
+      sm[kOffEdge + s] = wx;
+      sm[kOffEdge + kScalC + s] = wy;
+    }
   }
 
   static constexpr int kP3 = ((TW / 2) * TH + NT - 1) / NT;
