@@ -196,7 +196,6 @@ static int emu_flow_split(FlowGradParams& gp, int step) {
     Tile::load_group_plain(gp, tc, 0, 0, 1, sm.data());
     Tile::load_group_plain(gp, tc, 1, 0, 1, sm.data());
     for (int c = 0; c < 3; ++c) {
-      Tile::convert_channel(c, 0, 1, sm.data());
       Tile::phase2(gp, tc, c, 0, 1, sm.data(), acc);
       Tile::phase3_accumulate(gp, tc, c, 0, 1, sm.data(), g3);
       if (c < 2) Tile::load_group_plain(gp, tc, c + 2, 0, 1, sm.data());

@@ -15,7 +15,7 @@ GEOM_NSTATS = 16
 FLOW_BASIS_PLANES = 14
 # internal forms of the single-pass forward (include/ugl.h: UGL_SINGLE_PASS_*)
 SINGLE_PASS_VARIANTS = {"fused": 0, "split": 1, "split_plain": 2, "split_tma": 3}
-STEP_PARTS = {"photo": 1, "norm": 2, "stencil": 4, "finalize": 8, "all": 15}     # include/ugl.h: UGL_STEP_*
+STEP_PARTS = {"photo": 1, "norm": 2, "stencil": 4, "finalize": 8, "no_finalize": 7, "all": 15}     # include/ugl.h: UGL_STEP_*
 DEPTH_BASIS_PLANES = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

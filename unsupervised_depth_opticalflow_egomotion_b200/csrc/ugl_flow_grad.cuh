@@ -158,6 +158,21 @@ UGL_HD float ld_once(const float* p) {
 #endif
 }
 
+UGL_HD float2 ld_once2(const float* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(reinterpret_cast<const float2*>(p));
+#else
+  return *reinterpret_cast<const float2*>(p);
+#endif
+}
+UGL_HD float4 ld_once4(const float* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(reinterpret_cast<const float4*>(p));
+#else
+  return *reinterpret_cast<const float4*>(p);
+#endif
+}
+
 // the coalesced (non-gather) loads of one halo pixel: issued one pixel ahead of use to overlap their latency
 template <int PW, int R>
 UGL_HD DirectLoads load_direct(const FlowLevelDesc& L, const TileCoord& tc, int idx, int& i, int& j) {

@@ -46,6 +46,7 @@ flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __res
   const int l = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const FlowLevelDesc& L = p.lv[l];
   const int per_img = L.tiles_x * L.tiles_y;
+  griddep_wait();   // launched as a programmatic dependent of the stencil kernel in the fused step (resident under its last wave)
   const float* base = p.partials + ((long)L.tile_begin + (long)b * per_img) * FA_COUNT;
   double s[FA_COUNT];
 #pragma unroll
@@ -101,17 +102,29 @@ flow_loss_finalize_kernel(const __grid_constant__ FlowLossParams p, float* __res
   }
 }
 
+// scratch behind the tile partials: [B][scales][4] level losses, then B ticket counters
+template <int kMode>
+static float* finalize_level_losses(const FlowLossParams& p) { return p.partials + (size_t)p.total_tiles * (kMode == kModeFlow ? (int)FA_COUNT : (int)GA_COUNT); }
+
 template <int kMode = kModeFlow>
-static int launch_finalize(const FlowLossParams& p, cudaStream_t st, const FlowGradParams::PhotoTiling* photo = nullptr) {
-  FlowGradParams::PhotoTiling pt;
-  if (photo) pt = *photo; else pt.partials = nullptr;
-  // scratch behind the tile partials: [B][scales][4] level losses, then B ticket counters
-  float* lvl_loss = p.partials + (size_t)p.total_tiles * (kMode == kModeFlow ? (int)FA_COUNT : (int)GA_COUNT);
-  unsigned* tickets = reinterpret_cast<unsigned*>(lvl_loss + (size_t)p.B * p.scales * 4);
+static int finalize_reset_tickets(const FlowLossParams& p, cudaStream_t st) {
+  unsigned* tickets = reinterpret_cast<unsigned*>(finalize_level_losses<kMode>(p) + (size_t)p.B * p.scales * 4);
   const cudaError_t e = cudaMemsetAsync(tickets, 0, sizeof(unsigned) * p.B, st);
   if (e != cudaSuccess) return fail((int)e, "flow_loss finalize: memset: %s", cudaGetErrorString(e));
-  flow_loss_finalize_kernel<kMode><<<dim3(p.scales, p.B), kFinThreads, 0, st>>>(p, lvl_loss, tickets, pt);
-  return check_launch("flow_loss_finalize_kernel");
+  return UGL_OK;
+}
+
+// chained = true: the tickets were reset before the first kernel of the step (finalize_reset_tickets) and the launch is a programmatic
+// dependent of the kernel before it on the stream (a memset node in between would break the chain)
+template <int kMode = kModeFlow>
+static int launch_finalize(const FlowLossParams& p, cudaStream_t st, const FlowGradParams::PhotoTiling* photo = nullptr, bool chained = false) {
+  FlowGradParams::PhotoTiling pt;
+  if (photo) pt = *photo; else pt.partials = nullptr;
+  float* lvl_loss = finalize_level_losses<kMode>(p);
+  unsigned* tickets = reinterpret_cast<unsigned*>(lvl_loss + (size_t)p.B * p.scales * 4);
+  int rc;
+  if (!chained && (rc = finalize_reset_tickets<kMode>(p, st))) return rc;
+  return launch_kernel("flow_loss_finalize_kernel", flow_loss_finalize_kernel<kMode>, dim3(p.scales, p.B), dim3(kFinThreads), 0, st, chained, p, lvl_loss, tickets, pt);
 }
 
 template <int TW, int TH, int NT>
@@ -400,8 +413,10 @@ extern "C" int ugl_flow_loss_step_parts(const UglFlowLossArgs* a, int parts) {
   gp.step = 1;
   char* pp = split_photo_partials(a);
   flow_split_assign_scratch(gp, pp + flow_split_photo_partials_bytes(a->height, a->width, a->scales, a->batch));
+  const bool chained = parts == UGL_STEP_ALL;
+  if (chained && (rc = finalize_reset_tickets(gp.base, st))) return rc;
   if ((rc = launch_flow_split<false>(gp, pp, st, 1, parts & 7))) return rc;
-  return (parts & UGL_STEP_FINALIZE) ? launch_finalize(gp.base, st, &gp.photo) : UGL_OK;
+  return (parts & UGL_STEP_FINALIZE) ? launch_finalize(gp.base, st, &gp.photo, chained) : UGL_OK;
 }
 
 // ---- geom mode (Model_geometry's flow branch) -----------------------------------------------------

@@ -6,6 +6,10 @@
 #include "ugl_flow_split.cuh"
 #include "ugl_flow_split_host.cuh"
 
+#ifndef UGL_STENCIL_REVERSE
+#define UGL_STENCIL_REVERSE 1
+#endif
+
 namespace ugl {
 
 // ---- TMA / mbarrier primitives (PTX; sm_90+) --------------------------------------------------------------------------
@@ -94,6 +98,8 @@ __global__ void __launch_bounds__(256) flow_photo_norm_kernel(const __grid_const
   constexpr int ROW = kGeom ? (int)GA_COUNT : (int)FA_COUNT;
   __shared__ double red[256 / 32][NA];
   const int l = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  griddep_wait();                 // the photometry kernel is complete
+  griddep_launch_dependents();    // the stencil kernel may start: it needs this kernel's output only for its last phase
   const float* pb = gp.photo.partials + ((long)gp.photo.tile_begin[l] + (long)b * gp.photo.per_img[l]) * NA;
   double s[NA];
 #pragma unroll
@@ -140,9 +146,17 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
   __shared__ float red[(NT / 32) * NA];
   __shared__ __align__(8) uint64_t bars[4];
   int tile;
+#if UGL_STENCIL_REVERSE
+  // last sample / last tiles first: what the photometry kernel wrote last is what the L2 still holds
+  const TileCoord tc = decode_tile_2d<TW, TH>(gp.base, gridDim.x - 1 - blockIdx.x, gridDim.y - 1 - blockIdx.y, tile);
+#else
   const TileCoord tc = decode_tile_2d<TW, TH>(gp.base, blockIdx.x, blockIdx.y, tile);
+#endif
   const int tid = threadIdx.x;
   const bool kTma = tm.use_tma[tc.level] != 0;   // per level (CTA-uniform): TMA staging where the level's strides allow it
+  // Step mode: launched as a programmatic dependent of the weight-sum kernel, which releases it as soon as it has itself seen the
+  // photometry kernel complete: the photometry planes are final, the scale factors are not (waited for before phase 4b).
+  if (!kStep) griddep_wait();
 
   // copy group g (see FlowStencilTile::load_group_plain): issued by one thread, completion counted in bytes on bars[g]
   auto issue = [&](int g) {
@@ -156,18 +170,18 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
         uint64_t* bar = &bars[g];
         if (g == 0) {
           mbar_expect_tx(bar, 2 * kHaloPair + 3 * kHaloScal + 2 * kTilePair);
-          tma_load_3d(sm + Tile::kOffW, &tm.scr_halo[tc.level], 2 * xs, y0, zs + PP_W, bar);
           for (int c = 0; c < 3; ++c) tma_load_3d(sm + Tile::kOffI + c * Tile::kScalP, &tm.img[tc.level], xs, y0, tc.b * 3 + c, bar);
         } else if (g < 3) {
-          mbar_expect_tx(bar, kHaloPair + 2 * kTilePair);
+          mbar_expect_tx(bar, 2 * kHaloPair + 2 * kTilePair);
         } else {
           mbar_expect_tx(bar, 4 * kHaloScal);
         }
         if (g < 3) {
           float* st = Tile::stage(sm, g);
-          tma_load_3d(st, &tm.scr_halo[tc.level], 2 * xs, y0, zs + PP_W0 + g, bar);
-          tma_load_3d(st + Tile::kPairP, &tm.scr_tile[tc.level], 2 * tc.x0, tc.y0, zs + PP_DW0 + 2 * g, bar);
-          tma_load_3d(st + Tile::kPairP + Tile::kPairT, &tm.scr_tile[tc.level], 2 * tc.x0, tc.y0, zs + PP_DW0 + 2 * g + 1, bar);
+          tma_load_3d(st, &tm.scr_halo[tc.level], 2 * xs, y0, zs + PP_X0 + g, bar);
+          tma_load_3d(st + Tile::kSlotY, &tm.scr_halo[tc.level], 2 * xs, y0, zs + PP_Y0 + g, bar);
+          tma_load_3d(st + Tile::kSlotDu, &tm.scr_tile[tc.level], 2 * tc.x0, tc.y0, zs + PP_DW0 + 2 * g, bar);
+          tma_load_3d(st + Tile::kSlotDv, &tm.scr_tile[tc.level], 2 * tc.x0, tc.y0, zs + PP_DW0 + 2 * g + 1, bar);
         } else {
           float* raw = sm + Tile::kOffRawFlow;
           tma_load_3d(raw, &tm.flow_f[tc.level], xs, y0, tc.b * 2, bar);
@@ -206,8 +220,6 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
 #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
     arrived(c);
-    Tile::convert_channel(c, tid, NT, sm);
-    __syncthreads();
     Tile::phase2(gp, tc, c, tid, NT, sm, acc);
     __syncthreads();
     Tile::phase3_accumulate(gp, tc, c, tid, NT, sm, g3);
@@ -225,8 +237,9 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
   Tile::phase4a(gp, tc, tid, NT, sm, acc);
   __syncthreads();
   if (kStep) {
+    griddep_wait();                  // the weight-sum kernel is complete: scale factors final
     const float4* ks = reinterpret_cast<const float4*>(gp.step_scales + ((long)tc.b * gp.base.scales + tc.level) * 8);
-    const float4 k0 = __ldg(ks), k1 = __ldg(ks + 1);
+    const float4 k0 = __ldcg(ks), k1 = __ldcg(ks + 1);
     FlowCombineScales k;
     k.pix[0] = k0.x; k.pix[1] = k0.y; k.ssim[0] = k0.z; k.ssim[1] = k0.w; k.sm = k1.x; k.cons = k1.y;
     Tile::phase4b_step(gp, tc, k, tid, NT, sm, g3, pre);
@@ -342,15 +355,15 @@ int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st,
   assign_photo_tiling<kGeom>(gp, photo_partials);
   const dim3 grid(gp.base.total_tiles / gp.base.B, gp.base.B);
   int rc = UGL_OK;
+  const bool chain = (parts & 7) == 7;   // the whole sequence: programmatic dependent launches between its kernels
   if (parts & 1) {
-    flow_photo_kernel<kPhotoTW, kPhotoTH, kPhotoNT, kPatchW, kPatchH, kGeom><<<dim3(gp.photo.per_sample, gp.base.B), kPhotoNT, 0, st>>>(gp);
-    if ((rc = check_launch("flow_photo_kernel"))) return rc;
+    if ((rc = launch_kernel("flow_photo_kernel", flow_photo_kernel<kPhotoTW, kPhotoTH, kPhotoNT, kPatchW, kPatchH, kGeom>,
+                            dim3(gp.photo.per_sample, gp.base.B), dim3(kPhotoNT), 0, st, false, gp))) return rc;
   }
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float) + 128;
   static_assert(smem <= 227 * 1024, "stencil tile does not fit in shared memory");
   if (gp.step && (parts & 2)) {
-    flow_photo_norm_kernel<kGeom><<<dim3(gp.base.scales, gp.base.B), 256, 0, st>>>(gp);
-    if ((rc = check_launch("flow_photo_norm_kernel"))) return rc;
+    if ((rc = launch_kernel("flow_photo_norm_kernel", flow_photo_norm_kernel<kGeom>, dim3(gp.base.scales, gp.base.B), dim3(256), 0, st, chain, gp))) return rc;
   }
   if (!(parts & 4)) return UGL_OK;
   FlowTmaMaps tm;
@@ -363,13 +376,11 @@ int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st,
     if (kGeom) return fail(UGL_EUNSUPPORTED, "flow_loss_step: flow mode only");
     auto kern = flow_stencil_kernel<TW, TH, NT, false, true>;
     if ((rc = opt_in_smem(kern, smem))) return rc;
-    kern<<<grid, NT, smem, st>>>(gp, tm);
-  } else {
-    auto kern = flow_stencil_kernel<TW, TH, NT, kGeom, false>;
-    if ((rc = opt_in_smem(kern, smem))) return rc;
-    kern<<<grid, NT, smem, st>>>(gp, tm);
+    return launch_kernel("flow_stencil_kernel", kern, grid, dim3(NT), smem, st, chain, gp, tm);
   }
-  return check_launch("flow_stencil_kernel");
+  auto kern = flow_stencil_kernel<TW, TH, NT, kGeom, false>;
+  if ((rc = opt_in_smem(kern, smem))) return rc;
+  return launch_kernel("flow_stencil_kernel", kern, grid, dim3(NT), smem, st, chain, gp, tm);
 }
 
 template int launch_flow_split<false>(FlowGradParams&, void*, cudaStream_t, int, int);

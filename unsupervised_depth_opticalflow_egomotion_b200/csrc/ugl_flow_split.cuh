@@ -3,8 +3,9 @@
 //
 //   photometry kernel  (FlowPhotoPixel)   one thread per pixel, no shared memory tile, no halo: both backward warps of the
 //       pixel (24 bilinear taps), validity / occlusion weights, warp Jacobians, the L1 and consistency terms with their
-//       gradient basis, the tile's L1 / weight / consistency sums.  Writes per pixel 10 (direction 0, direction 1) pairs of
-//       "photometry planes" for the stencil kernel:  w,  W[c] (c = 0..2),  w * keep * dW[c]/d(u|v)  (6 pairs).
+//       gradient basis, the tile's L1 / weight / consistency sums.  Writes per pixel 12 (direction 0, direction 1) pairs of
+//       "photometry planes" for the stencil kernel:  x[c] = I[c] * w,  y[c] = W[c] * w (c = 0..2: the SSIM operands),
+//       w * keep * dW[c]/d(u|v)  (6 pairs).
 //   stencil kernel     (FlowStencilTile)  stages the photometry planes of a tile + 2-pixel halo in shared memory — with TMA
 //       (cp.async.bulk.tensor, out-of-image elements zero-filled by the copy engine) where the level's width allows 16-byte
 //       global strides, with plain coalesced loads otherwise, identical shared-memory contents either way — and runs the
@@ -14,11 +15,12 @@
 // Why (profiles/r1v_*): fused, the photometry phase recomputed 1.47 pixels per pixel (2-pixel halo of a 32x13 tile), ran at
 // 16 warps per SM next to 94 KB of stencil planes, and was 49 % of the kernel's time (long-scoreboard stalls on its gathers).
 // Split, every pixel's photometry runs once in a kernel with no shared-memory footprint (occupancy bound by registers
-// only), and the stencil kernel's footprint drops to 56 KB per CTA.  The price is 20 floats per pixel written and read
+// only), and the stencil kernel's footprint drops to 56 KB per CTA.  The price is 24 floats per pixel written and read
 // back (mostly through L2); the step was nowhere near the HBM roofline.
 //
-// Same arithmetic as the fused kernel: x = I * w and y = W * w are formed from the staged planes with the same packed
-// multiplies, the SSIM moments / terms / coefficients are the same functions, the L1 and consistency bases are the same
+// Same arithmetic as the fused kernel: x = I * w and y = W * w are the same packed products (formed by the photometry kernel:
+// the stencil kernel's shared-memory pipe is its binding resource, a conversion pass over the staged planes cost 15 % of its
+// traffic), the SSIM moments / terms / coefficients are the same functions, the L1 and consistency bases are the same
 // expressions.  The only re-association is w * (keep dW) being formed before instead of after the box sums (gradient only).
 #pragma once
 
@@ -26,11 +28,11 @@
 
 namespace ugl {
 
-// pair planes per sample and level: w, W[0..2], wdW[2c+uv] (c = 0..2, uv = 0,1); step mode only: the L1 basis (Gp_u, Gp_v as
+// pair planes per sample and level: x[0..2], y[0..2], wdW[2c+uv] (c = 0..2, uv = 0,1); step mode only: the L1 basis (Gp_u, Gp_v as
 // (fwd, bwd) pairs) and the consistency basis (u, v)
-constexpr int kPhotoPairs = 13;
+constexpr int kPhotoPairs = 15;
 constexpr int kPhotoFloats = 2 * kPhotoPairs;
-enum PhotoPair { PP_W = 0, PP_W0 = 1, PP_DW0 = 4, PP_GPU = 10, PP_GPV = 11, PP_GC = 12 };
+enum PhotoPair { PP_X0 = 0, PP_Y0 = 3, PP_DW0 = 6, PP_GPU = 12, PP_GPV = 13, PP_GC = 14 };
 
 // ---- photometry kernel: one pixel -----------------------------------------------------------------------------------
 // acc slots of the photometry kernel (subset of FlowAcc / GeomAcc written by this kernel; the stencil kernel writes the rest
@@ -74,9 +76,11 @@ struct FlowPhotoPixel {
     const float2 w2 = make_float2(P.w_f, P.w_b);
     float* scr = gp.scratch[lv] + (long)b * kPhotoFloats * plane + 2 * (long)pix;
     const long pp = 2 * (long)plane;                                           // floats per pair plane
-    *reinterpret_cast<float2*>(scr + PP_W * pp) = w2;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) *reinterpret_cast<float2*>(scr + (PP_W0 + c) * pp) = make_float2(P.Wf[c], P.Wb[c]);
+    for (int c = 0; c < 3; ++c) {
+      *reinterpret_cast<float2*>(scr + (PP_X0 + c) * pp) = mul2(splat2(P.I[c]), w2);
+      *reinterpret_cast<float2*>(scr + (PP_Y0 + c) * pp) = mul2(make_float2(P.Wf[c], P.Wb[c]), w2);
+    }
 #pragma unroll
     for (int k = 0; k < 6; ++k) *reinterpret_cast<float2*>(scr + (PP_DW0 + k) * pp) = mul2(make_float2(dW[k], dW[6 + k]), w2);
     // L1 basis: w * sum_c sign(W_c - I_c) * keep * dW_c/d(u,v)
@@ -146,14 +150,13 @@ struct FlowPhotoPixel {
 // ---- stencil kernel: tile logic ---------------------------------------------------------------------------------------
 // Shared-memory plan (floats; every slot starts 128-byte aligned: a TMA destination).  PN / CN / TN = pixels of the tile with
 // halo 2 / halo 1 / no halo.
-//   kOffW      w pair plane (halo 2)                               [whole kernel]
-//   kOffI      3 scalar planes I[c] (halo 2)                       [whole kernel; edge weights, x = I * w]
-//   kOffStage  2 slots x { W[c] pair plane (halo 2) -> y = W * w in place ; 2 pair planes w dW[c]/d(u|v) (no halo) }
-//   kOffX      x pair plane of the current channel (halo 2)
+//   kOffI      3 scalar planes I[c] (halo 2)                       [whole kernel; edge weights of the smoothness term]
+//   kOffStage  2 slots x { x[c], y[c] pair planes (halo 2) ; 2 pair planes w dW[c]/d(u|v) (no halo) }
 //   kOffCoef   3 pair planes A, B, C of the current channel (halo 1)
 // Smoothness phases (after the last channel): the four raw flow planes arrive in slot 1, are divided by 20 and interleaved into
 // two (u, v) pair planes in slot 0; then the edge weights wx, wy (2 scalar planes, halo 1) are formed from I over the dead raw flow
-// planes; the signed second differences (4 pair planes, halo 1) go over x + coefficient planes.  56 KB in all: four CTAs per SM.
+// planes; the signed second differences (4 pair planes, halo 1) follow them, over the rest of slot 1 and the coefficient planes.
+// 56 KB in all: four CTAs per SM.
 template <int TW, int TH, int NT, bool kGeom>
 struct FlowStencilTile {
   static_assert(TW % 2 == 0, "1x2 micro-tiles need an even tile width");
@@ -168,19 +171,18 @@ struct FlowStencilTile {
   static UGL_HD int hp(int ly, int lx) { return ly * SPW + lx + kScalX; }
   static constexpr int pad32(int n) { return (n + 31) & ~31; }
   static constexpr int kPairP = pad32(2 * SPN), kScalP = pad32(SPN), kPairC = pad32(2 * CN), kScalC = pad32(CN), kPairT = pad32(2 * TN);
-  static constexpr int kOffW = 0;
-  static constexpr int kOffI = kOffW + kPairP;
+  static constexpr int kOffI = 0;
   static constexpr int kOffStage = kOffI + 3 * kScalP;
-  static constexpr int kStage = kPairP + 2 * kPairT;
-  static constexpr int kOffX = kOffStage + 2 * kStage;
-  static constexpr int kOffCoef = kOffX + kPairP;
+  static constexpr int kStage = 2 * kPairP + 2 * kPairT;          // x, y (halo 2), w dW/du, w dW/dv (tile)
+  static constexpr int kSlotY = kPairP, kSlotDu = 2 * kPairP, kSlotDv = 2 * kPairP + kPairT;
+  static constexpr int kOffCoef = kOffStage + 2 * kStage;
   static constexpr int kSmemFloats = kOffCoef + 3 * kPairC;
   static constexpr int kOffRawFlow = kOffStage + kStage;          // 4 scalar planes (uf, vf, ub, vb), halo 2, in slot 1
   static constexpr int kOffEdge = kOffRawFlow;                    // wx, wy (halo 1): over the raw flow planes once those are converted
   static constexpr int kOffF2 = kOffStage;                        // 2 pair planes (u, v) / 20 of the fwd / bwd flow, in slot 0
-  static constexpr int kOffS4 = kOffX;                            // 4 pair planes of signed weights (halo 1)
+  static constexpr int kOffS4 = kOffEdge + 2 * kScalC;            // 4 pair planes of signed weights (halo 1)
   static_assert(4 * kScalP <= kStage && 2 * kPairP <= kStage && 2 * kScalC <= kStage, "flow planes / edge planes must fit a ring slot");
-  static_assert(4 * kPairC <= kPairP + 3 * kPairC, "phase-4 planes must fit over the x + coefficient planes");
+  static_assert(kOffS4 + 4 * kPairC <= kSmemFloats, "phase-4 planes must fit behind the edge weights (rest of slot 1 + coefficient planes)");
   static_assert(SPW % 2 == 0 && kScalX % 2 == 0 && CW % 2 == 0, "pair planes are read as float4 (two pixels x two directions)");
   static constexpr int kAcc = 6;                                  // SSIM_F, SSIM_B, SMX_F, SMY_F, SMX_B, SMY_B
   static UGL_HD int column(int k) { return (int)FA_SSIM_F + k; }
@@ -215,21 +217,21 @@ struct FlowStencilTile {
       *reinterpret_cast<float2*>(dst + 2 * idx) = v;
     }
   }
-  // copy groups: 0 = w + I[0..2] + channel 0 -> slot 0; 1 = channel 1 -> slot 1; 2 = channel 2 -> slot 0; 3 = raw flows -> slot 1
+  // copy groups: 0 = I[0..2] + channel 0 -> slot 0; 1 = channel 1 -> slot 1; 2 = channel 2 -> slot 0; 3 = raw flows -> slot 1
   static UGL_HD void load_group_plain(const FlowGradParams& gp, const TileCoord& tc, int group, int tid, int nt, float* sm) {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     const long plane = (long)L.h * L.w;
     const float* scr = gp.scratch[tc.level] + (long)tc.b * kPhotoFloats * plane;
     if (group == 0) {
-      load_pair_halo(sm + kOffW, scr + PP_W * 2 * plane, L, tc, tid, nt);
       for (int c = 0; c < 3; ++c) load_scalar_halo(sm + kOffI + c * kScalP, L.img + ((long)tc.b * 3 + c) * plane, L, tc, tid, nt);
     }
     if (group < 3) {
       const int c = group;
       float* st = stage(sm, c);
-      load_pair_halo(st, scr + (PP_W0 + c) * 2 * plane, L, tc, tid, nt);
-      load_pair_interior(st + kPairP, scr + (PP_DW0 + 2 * c) * 2 * plane, L, tc, tid, nt);
-      load_pair_interior(st + kPairP + kPairT, scr + (PP_DW0 + 2 * c + 1) * 2 * plane, L, tc, tid, nt);
+      load_pair_halo(st, scr + (PP_X0 + c) * 2 * plane, L, tc, tid, nt);
+      load_pair_halo(st + kSlotY, scr + (PP_Y0 + c) * 2 * plane, L, tc, tid, nt);
+      load_pair_interior(st + kSlotDu, scr + (PP_DW0 + 2 * c) * 2 * plane, L, tc, tid, nt);
+      load_pair_interior(st + kSlotDv, scr + (PP_DW0 + 2 * c + 1) * 2 * plane, L, tc, tid, nt);
     } else {
       float* raw = sm + kOffRawFlow;
       load_scalar_halo(raw, L.flow_f + (long)tc.b * 2 * plane, L, tc, tid, nt);
@@ -239,21 +241,6 @@ struct FlowStencilTile {
     }
   }
 
-  // x = I[c] * w -> x plane; y = W[c] * w in place (the operand form of the SSIM phases; same products as the fused kernel)
-  static UGL_HD void convert_channel(int c, int tid, int nt, float* sm) {
-    float* yp = stage(sm, c);
-    const float* ip = sm + kOffI + c * kScalP;
-    static_assert(SPN % 2 == 0, "two pixels per iteration");
-    for (int idx = 2 * tid; idx < SPN; idx += 2 * nt) {      // flat over the staged planes (same index in all of them)
-      const float4 w4 = *reinterpret_cast<const float4*>(sm + kOffW + 2 * idx);
-      const float4 W4 = *reinterpret_cast<const float4*>(yp + 2 * idx);
-      const float2 I2 = *reinterpret_cast<const float2*>(ip + idx);
-      const float2 xa = mul2(splat2(I2.x), lo2(w4)), xb = mul2(splat2(I2.y), hi2(w4));
-      const float2 ya = mul2(lo2(W4), lo2(w4)), yb = mul2(hi2(W4), hi2(w4));
-      *reinterpret_cast<float4*>(sm + kOffX + 2 * idx) = make_float4(xa.x, xa.y, xb.x, xb.y);
-      *reinterpret_cast<float4*>(yp + 2 * idx) = make_float4(ya.x, ya.y, yb.x, yb.y);
-    }
-  }
   // raw flow planes (slot 1) -> (u, v) / 20 pair planes of both flows (slot 0): `flow / 20.0` of model_flow.py:177
   static UGL_HD void convert_flows(int tid, int nt, float* sm) {
     constexpr float r20 = 1.0f / 20.0f;
@@ -291,8 +278,8 @@ struct FlowStencilTile {
       const bool row_in = (i >= 0 && i < L.h);
       const bool in0 = row_in && j0 >= 0 && j0 < L.w, in1 = row_in && j0 + 1 >= 0 && j0 + 1 < L.w;
       {
-        const float* xpl = sm + kOffX + 2 * (c0 - 1);
-        const float* ypl = stage(sm, c) + 2 * (c0 - 1);
+        const float* xpl = stage(sm, c) + 2 * (c0 - 1);
+        const float* ypl = xpl + kSlotY;
         Moments2 m[2];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -393,10 +380,10 @@ struct FlowStencilTile {
         sum[k][0] = add2(col[0], mid);
         sum[k][1] = add2(mid, col[3]);
       }
-      const float4 Xv = *reinterpret_cast<const float4*>(sm + kOffX + 2 * c0);
-      const float4 Yv = *reinterpret_cast<const float4*>(st + 2 * c0);
-      const float4 du = *reinterpret_cast<const float4*>(st + kPairP + 2 * t0);
-      const float4 dv = *reinterpret_cast<const float4*>(st + kPairP + kPairT + 2 * t0);
+      const float4 Xv = *reinterpret_cast<const float4*>(st + 2 * c0);
+      const float4 Yv = *reinterpret_cast<const float4*>(st + kSlotY + 2 * c0);
+      const float4 du = *reinterpret_cast<const float4*>(st + kSlotDu + 2 * t0);
+      const float4 dv = *reinterpret_cast<const float4*>(st + kSlotDv + 2 * t0);
       const float2 X2[2] = {lo2(Xv), hi2(Xv)}, Y2[2] = {lo2(Yv), hi2(Yv)};
       const float2 du2[2] = {lo2(du), hi2(du)}, dv2[2] = {lo2(dv), hi2(dv)};
 #pragma unroll
@@ -483,10 +470,10 @@ struct FlowStencilTile {
       for (int k = 0; k < 3; ++k) {
         const float* q = scr + (PP_GPU + k) * 2 * plane + 2 * pix;
         if (two && (L.w & 1) == 0) {
-          pre[n][k] = *reinterpret_cast<const float4*>(q);           // pix even, plane base 16-byte aligned
+          pre[n][k] = ld_once4(q);                                   // pix even, plane base 16-byte aligned
         } else {
-          const float2 a = *reinterpret_cast<const float2*>(q);
-          const float2 c = two ? *reinterpret_cast<const float2*>(q + 2) : make_float2(0.f, 0.f);
+          const float2 a = ld_once2(q);
+          const float2 c = two ? ld_once2(q + 2) : make_float2(0.f, 0.f);
           pre[n][k] = make_float4(a.x, a.y, c.x, c.y);
         }
       }

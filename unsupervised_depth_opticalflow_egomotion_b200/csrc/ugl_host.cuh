@@ -36,6 +36,29 @@ inline int opt_in_smem(K kernel, size_t bytes) {
   return UGL_OK;
 }
 
+// Programmatic dependent launch (griddepcontrol.*; sm_90+).  A kernel launched with `pdl` may start while its stream predecessor is still
+// running; it must call griddep_wait() before it touches anything the predecessor (or, transitively, an earlier kernel of the chain)
+// wrote.  Without the attribute both calls are no-ops.
+#ifndef UGL_PDL
+#define UGL_PDL 1
+#endif
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline int launch_kernel(const char* what, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && UGL_PDL) ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+  return UGL_OK;
+}
+
 inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
 // Warp reduction of N per-thread accumulators by recursive halving: at shuffle distance o the lanes with bit o clear keep
