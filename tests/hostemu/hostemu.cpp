@@ -195,9 +195,11 @@ static int emu_flow_split(FlowGradParams& gp, int step) {
     float2 (*g3)[4] = reinterpret_cast<float2 (*)[4]>(g3v.data());
     Tile::load_group_plain(gp, tc, 0, 0, 1, sm.data());
     Tile::load_group_plain(gp, tc, 1, 0, 1, sm.data());
+    std::vector<unsigned> geo2(Tile::kP2), geo3(Tile::kP3);
+    Tile::strip_geometry(gp, tc, 0, 1, geo2.data(), geo3.data());
     for (int c = 0; c < 3; ++c) {
-      Tile::phase2(gp, tc, c, 0, 1, sm.data(), acc);
-      Tile::phase3_accumulate(gp, tc, c, 0, 1, sm.data(), g3);
+      Tile::phase2(gp, tc, c, 0, 1, sm.data(), acc, geo2.data());
+      Tile::phase3_accumulate(gp, tc, c, 0, 1, sm.data(), g3, geo3.data());
       if (c < 2) Tile::load_group_plain(gp, tc, c + 2, 0, 1, sm.data());
     }
     std::vector<float4> prev((size_t)Tile::kP3 * 3);
@@ -205,7 +207,7 @@ static int emu_flow_split(FlowGradParams& gp, int step) {
     if (step) Tile::prefetch_step(gp, tc, 0, 1, pre);
     else Tile::phase3_store(gp, tc, 0, 1, g3);
     Tile::convert_flows(0, 1, sm.data());
-    Tile::phase2(gp, tc, 3, 0, 1, sm.data(), acc);
+    Tile::phase2(gp, tc, 3, 0, 1, sm.data(), acc, geo2.data());
     Tile::phase4a(gp, tc, 0, 1, sm.data(), acc);
     if (step) {
       const float* o = scales_buf.data() + ((size_t)tc.b * p.scales + tc.level) * 8;

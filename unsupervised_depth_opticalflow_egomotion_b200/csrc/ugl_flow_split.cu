@@ -216,13 +216,15 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
   for (int n = 0; n < Tile::kP3; ++n)
 #pragma unroll
     for (int k = 0; k < 4; ++k) g3[n][k] = make_float2(0.f, 0.f);
+  unsigned geo2[Tile::kP2], geo3[Tile::kP3];
+  Tile::strip_geometry(gp, tc, tid, NT, geo2, geo3);
   if (!kTma) __syncthreads();
 #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
     arrived(c);
-    Tile::phase2(gp, tc, c, tid, NT, sm, acc);
+    Tile::phase2(gp, tc, c, tid, NT, sm, acc, geo2);
     __syncthreads();
-    Tile::phase3_accumulate(gp, tc, c, tid, NT, sm, g3);
+    Tile::phase3_accumulate(gp, tc, c, tid, NT, sm, g3, geo3);
     __syncthreads();                   // ring slot c & 1, the x plane and the coefficient planes are free again
     if (c < 2) issue(c + 2);           // channel 2 -> slot 0; the raw flow planes -> slot 1
   }
@@ -232,7 +234,7 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
   arrived(3);
   Tile::convert_flows(tid, NT, sm);
   __syncthreads();
-  Tile::phase2(gp, tc, 3, tid, NT, sm, acc);   // smoothness edge weights, over the raw flow planes (converted above)
+  Tile::phase2(gp, tc, 3, tid, NT, sm, acc, geo2);   // smoothness edge weights, over the raw flow planes (converted above)
   __syncthreads();
   Tile::phase4a(gp, tc, tid, NT, sm, acc);
   __syncthreads();

@@ -251,25 +251,26 @@ struct FlowStencilTile {
     }
   }
 
-  // SSIM of channel c (c < 3) for every 1x2 strip of the halo-1 region -> coefficient pairs + loss sums; c == 3: the smoothness
-  // edge weights.  FlowGradTile::phase2 on the split kernel's planes.
-  static UGL_HD void phase2(const FlowGradParams& gp, const TileCoord& tc, int c, int tid, int nt, float* sm, float* acc) {
+  // Per-thread strip geometry of phases 2 and 3: the same for the three channels, so it is decoded once per tile (the channel loop is
+  // rolled around CTA barriers: the compiler re-derived the divisions, plane offsets and bounds tests in every channel) and kept packed
+  // in one register per strip.
+  //   phase 2: bits 0..11 float offset / 2 of the strip's window in a halo-2 pair plane, 12..22 float offset / 2 of its coefficients,
+  //            23 / 24 pixel 0 / 1 inside the image, 25 / 26 pixel 0 / 1 inside the tile as well (counts towards the SSIM sum)
+  //   phase 3: bits 0..10 halo-2 index of the strip's left pixel, 11..20 halo-1 index, 21..30 tile index, 31 strip inside the image
+  static constexpr int kNS2 = (CW / 2) * CH, kNS3 = (TW / 2) * TH;
+  static constexpr int kP2 = (kNS2 + NT - 1) / NT, kP3 = (kNS3 + NT - 1) / NT;
+  static_assert(SPN < 4096 && CN < 2048 && SPN < 2048 && CN < 1024 && TN < 1024, "packed strip geometry");
+  static UGL_HD void strip_geometry(const FlowGradParams& gp, const TileCoord& tc, int tid, int nt, unsigned* p2, unsigned* p3) {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     constexpr int SW = CW / 2;
-    constexpr int NS = SW * CH;
-    if (c >= 3) {
-      edge_weights(gp, tc, tid, nt, sm);
-      return;
-    }
-    // Strip order: the first SW - 1 strips of every row, row by row, then the last strip of every row.  With SW - 1 a multiple
-    // of 8 (TW = 32: 16) a quarter-warp's eight 16-byte reads stay inside one row = 128 contiguous bytes; the row-major order
-    // (17 strips per row of pitch 320 bytes) split 45 % of the quarter-warps over two rows whose banks overlap (5.6 wavefronts
-    // per LDS.128 instead of 4).
+    // Strip order of phase 2: the first SW - 1 strips of every row, row by row, then the last strip of every row.  With SW - 1 a
+    // multiple of 8 (TW = 32: 16) a quarter-warp's eight 16-byte reads stay inside one row = 128 contiguous bytes; the row-major
+    // order (17 strips per row of pitch 320 bytes) split 45 % of the quarter-warps over two rows whose banks overlap (5.6
+    // wavefronts per LDS.128 instead of 4).
     constexpr bool kSplitRows = ((SW - 1) % 8) == 0;
     constexpr int SM = kSplitRows ? SW - 1 : SW;
-    float2 ssim_sum = make_float2(0.f, 0.f);
-    const float2 one = splat2(gp.one);
-    for (int s = tid; s < NS; s += nt) {
+    int n = 0;
+    for (int s = tid; s < kNS2; s += nt, ++n) {
       int ly, lx;
       if (s < SM * CH) { ly = s / SM; lx = (s - ly * SM) * 2; }
       else { ly = s - SM * CH; lx = 2 * SM; }
@@ -277,8 +278,33 @@ struct FlowStencilTile {
       const int c0 = hp(ly + 1, lx + 1);                    // staged-plane index of the left centre
       const bool row_in = (i >= 0 && i < L.h);
       const bool in0 = row_in && j0 >= 0 && j0 < L.w, in1 = row_in && j0 + 1 >= 0 && j0 + 1 < L.w;
+      const bool t0 = in0 && ly >= 1 && ly <= TH && lx >= 1 && lx <= TW, t1 = in1 && ly >= 1 && ly <= TH && lx + 1 >= 1 && lx + 1 <= TW;
+      p2[n] = (unsigned)(c0 - 1) | ((unsigned)(ly * CW + lx) << 12) | (in0 ? 1u << 23 : 0u) | (in1 ? 1u << 24 : 0u) | (t0 ? 1u << 25 : 0u) | (t1 ? 1u << 26 : 0u);
+    }
+    n = 0;
+    constexpr int SW3 = TW / 2;
+    for (int s = tid; s < kNS3; s += nt, ++n) {
+      const int ty = s / SW3, tx = (s - ty * SW3) * 2;
+      const bool in = tc.y0 + ty < L.h && tc.x0 + tx < L.w;
+      p3[n] = (unsigned)hp(ty + R, tx + R) | ((unsigned)((ty + 1) * CW + (tx + 1)) << 11) | ((unsigned)(ty * TW + tx) << 21) | (in ? 1u << 31 : 0u);
+    }
+  }
+
+  // SSIM of channel c (c < 3) for every 1x2 strip of the halo-1 region -> coefficient pairs + loss sums; c == 3: the smoothness
+  // edge weights.  FlowGradTile::phase2 on the split kernel's planes.
+  static UGL_HD void phase2(const FlowGradParams& gp, const TileCoord& tc, int c, int tid, int nt, float* sm, float* acc, const unsigned* p2) {
+    if (c >= 3) {
+      edge_weights(gp, tc, tid, nt, sm);
+      return;
+    }
+    float2 ssim_sum = make_float2(0.f, 0.f);
+    const float2 one = splat2(gp.one);
+    int n = 0;
+    for (int s = tid; s < kNS2; s += nt, ++n) {
+      const unsigned geo = p2[n];
+      const bool in0 = (geo >> 23) & 1u, in1 = (geo >> 24) & 1u;
       {
-        const float* xpl = stage(sm, c) + 2 * (c0 - 1);
+        const float* xpl = stage(sm, c) + 2 * (int)(geo & 4095u);
         const float* ypl = xpl + kSlotY;
         Moments2 m[2];
 #pragma unroll
@@ -310,11 +336,11 @@ struct FlowStencilTile {
           const float2 v = ssim_half_one_minus2(t.S, one);
           const float2 g = make_float2((in && v.x >= 0.f && v.x <= 1.f) ? -0.5f : 0.f, (in && v.y >= 0.f && v.y <= 1.f) ? -0.5f : 0.f);
           ssim_partials2(t, g, cA[w], cB[w], cC[w]);
-          const bool interior = in && (ly >= 1 && ly <= TH && lx + w >= 1 && lx + w <= TW);
+          const bool interior = (geo >> (25 + w)) & 1u;
           ssim_sum.x += interior ? (v.x < 0.f ? 0.f : (v.x > 1.f ? 1.f : v.x)) : 0.f;
           ssim_sum.y += interior ? (v.y < 0.f ? 0.f : (v.y > 1.f ? 1.f : v.y)) : 0.f;
         }
-        float* oc = sm + kOffCoef + 2 * (ly * CW + lx);
+        float* oc = sm + kOffCoef + 2 * (int)((geo >> 12) & 2047u);
         *reinterpret_cast<float4*>(oc) = make_float4(cA[0].x, cA[0].y, cA[1].x, cA[1].y);
         *reinterpret_cast<float4*>(oc + kPairC) = make_float4(cB[0].x, cB[0].y, cB[1].x, cB[1].y);
         *reinterpret_cast<float4*>(oc + 2 * kPairC) = make_float4(cC[0].x, cC[0].y, cC[1].x, cC[1].y);
@@ -350,20 +376,17 @@ struct FlowStencilTile {
     }
   }
 
-  static constexpr int kP3 = ((TW / 2) * TH + NT - 1) / NT;
-
   // 3x3 box sums of channel c's coefficient pairs, chained through w * keep * dW[c]/d(u, v) into the running sums
-  static UGL_HD void phase3_accumulate(const FlowGradParams& gp, const TileCoord& tc, int c, int tid, int nt, const float* sm, float2 (*g)[4]) {
-    const FlowLevelDesc& L = gp.base.lv[tc.level];
-    constexpr int SW = TW / 2;
+  static UGL_HD void phase3_accumulate(const FlowGradParams& gp, const TileCoord& tc, int c, int tid, int nt, const float* sm, float2 (*g)[4],
+                                       const unsigned* p3) {
     const float* st = stage(sm, c);
     int n = 0;
-    for (int s = tid; s < SW * TH; s += nt, ++n) {
-      const int ty = s / SW, tx = (s - ty * SW) * 2;
-      if (tc.y0 + ty >= L.h || tc.x0 + tx >= L.w) continue;
-      const int c0 = hp(ty + R, tx + R);
-      const int q0 = (ty + 1) * CW + (tx + 1);
-      const int t0 = ty * TW + tx;
+    for (int s = tid; s < kNS3; s += nt, ++n) {
+      const unsigned geo = p3[n];
+      if (!(geo >> 31)) continue;
+      const int c0 = (int)(geo & 2047u);
+      const int q0 = (int)((geo >> 11) & 1023u);
+      const int t0 = (int)((geo >> 21) & 1023u);
       float2 sum[3][2];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
