@@ -59,12 +59,45 @@ struct DepthPixel {
   Tap tap;
 };
 
+// the coalesced loads of one pixel and direction: issued one loop iteration ahead of their use (the kernels are bound by the latency
+// of their loads, not by bytes)
+struct DepthDirect {
+  float disp, I[3], bil[3], base;
+};
+
+__device__ __forceinline__ DepthDirect depth_direct(const DepthPhotoLevel& L, int b, int dir, long p) {
+  const long plane = (long)L.h * L.w;
+  DepthDirect d;
+  d.disp = L.disp[(long)b * plane + p];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const long o3 = ((long)b * 3 + c) * plane;
+    d.I[c] = L.img[o3 + p];
+    d.bil[c] = L.src_bil[dir][o3 + p];
+  }
+  d.base = -1.f;                                 // < 0: the reprojection valid mask
+  if (L.ext_bytes) d.base = ((unsigned)L.ext_bytes[(long)b * plane + p] & L.ext_need[dir]) == L.ext_need[dir] ? 1.f : 0.f;
+  else if (L.ext_mask[dir]) d.base = L.ext_mask[dir][(long)b * plane + p];
+  return d;
+}
+
+// The pixels of a (sample, level, direction) are split into gridDim.x contiguous chunks (a multiple of the CTA size each); a CTA walks
+// its chunk front to back, so consecutive iterations gather from the same rows of the source frame (L1 reuse).
+struct ChunkRange { long begin, end; };
+__device__ __forceinline__ ChunkRange chunk_range(long plane) {
+  const long per = (((plane + gridDim.x - 1) / gridDim.x) + kRedThreads - 1) / kRedThreads * kRedThreads;
+  ChunkRange r;
+  r.begin = blockIdx.x * per;
+  r.end = r.begin + per < plane ? r.begin + per : plane;
+  return r;
+}
+
 // everything the forward and the backward need for one pixel and one direction
 template <bool kGrad>
 __device__ __forceinline__ void depth_pixel(const DepthPhotoLevel& L, const float* sK, const float* sP, int b, int dir, int i, int j,
-                                            long p, const WarpGeom& g, DepthPixel& o, float* gix, float* giy, float k_scale) {
+                                            long p, const WarpGeom& g, const DepthDirect& dl, DepthPixel& o, float* gix, float* giy, float k_scale) {
   const long plane = (long)L.h * L.w;
-  o.pr = project_pixel(sK, sP, L.disp[(long)b * plane + p], j, i);
+  o.pr = project_pixel(sK, sP, dl.disp, j, i);
   o.nc = normalise(o.pr, g);
   o.tap = make_tap(unnormalize(o.nc.gx, L.w), unnormalize(o.nc.gy, L.h), L.w, L.h);
   const float valid = (fabsf(o.nc.gx) <= 1.0f && fabsf(o.nc.gy) <= 1.0f) ? 1.f : 0.f;
@@ -73,17 +106,15 @@ __device__ __forceinline__ void depth_pixel(const DepthPhotoLevel& L, const floa
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const long o3 = ((long)b * 3 + c) * plane;
-    o.I[c] = L.img[o3 + p];
+    o.I[c] = dl.I[c];
     cs[c] = tap_fetch(L.src_area[dir] + o3, L.w, o.tap);
     o.rec[c] = corners_value(cs[c], o.tap);
     a = add_rn(a, fabsf(sub_rn(o.I[c], o.rec[c])));
-    s = add_rn(s, fabsf(sub_rn(o.I[c], L.src_bil[dir][o3 + p])));
+    s = add_rn(s, fabsf(sub_rn(o.I[c], dl.bil[c])));
   }
   const float r3 = 1.0f / 3.0f;
   const float tex = div_c(a, 3.0f, r3) < div_c(s, 3.0f, r3) ? 1.f : 0.f;
-  float base = valid;
-  if (L.ext_bytes) base = ((unsigned)L.ext_bytes[(long)b * plane + p] & L.ext_need[dir]) == L.ext_need[dir] ? 1.f : 0.f;
-  else if (L.ext_mask[dir]) base = L.ext_mask[dir][(long)b * plane + p];
+  const float base = dl.base < 0.f ? valid : dl.base;
   o.mask = mul_rn(base, tex);
   o.tex = tex;
   if (!kGrad) {
@@ -114,10 +145,17 @@ __global__ void __launch_bounds__(kRedThreads, UGL_DP_FWD_MINB) depth_photo_fwd_
   const WarpGeom g = make_warp_geom(L.w, L.h);
   const long plane = (long)L.h * L.w;
   float acc[2] = {0.f, 0.f};
-  for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
+  const ChunkRange cr = chunk_range(plane);
+  long px = cr.begin + threadIdx.x;
+  DepthDirect nxt = {};
+  if (px < cr.end) nxt = depth_direct(L, b, dir, px);
+#pragma unroll 1
+  for (; px < cr.end; px += kRedThreads) {
+    const DepthDirect dl = nxt;
+    if (px + kRedThreads < cr.end) nxt = depth_direct(L, b, dir, px + kRedThreads);
     const int i = (int)(px / L.w), j = (int)(px % L.w);
     DepthPixel o;
-    depth_pixel<false>(L, sK, sP, b, dir, i, j, px, g, o, nullptr, nullptr, 0.f);
+    depth_pixel<false>(L, sK, sP, b, dir, i, j, px, g, dl, o, nullptr, nullptr, 0.f);
     acc[0] += (fabsf(o.I[0] - o.rec[0]) + fabsf(o.I[1] - o.rec[1]) + fabsf(o.I[2] - o.rec[2])) * o.mask;
     acc[1] += o.mask;
   }
@@ -172,11 +210,18 @@ __global__ void __launch_bounds__(kRedThreads, UGL_DP_BWD_MINB) depth_photo_bwd_
   float acc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.f;
-  for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
+  const ChunkRange cr = chunk_range(plane);
+  long px = cr.begin + threadIdx.x;
+  DepthDirect nxt = {};
+  if (px < cr.end) nxt = depth_direct(L, b, dir, px);
+#pragma unroll 1
+  for (; px < cr.end; px += kRedThreads) {
+    const DepthDirect dl = nxt;
+    if (px + kRedThreads < cr.end) nxt = depth_direct(L, b, dir, px + kRedThreads);
     const int i = (int)(px / L.w), j = (int)(px % L.w);
     DepthPixel o;
     float gix, giy;
-    depth_pixel<true>(L, sK, sP, b, dir, i, j, px, g, o, &gix, &giy, ks);
+    depth_pixel<true>(L, sK, sP, b, dir, i, j, px, g, dl, o, &gix, &giy, ks);
     const float g_u = o.nc.ox ? 0.f : gix * g.sx;
     const float g_v = o.nc.oy ? 0.f : giy * g.sy;
     const float gD = project_backward(o.pr, sP, g_u, g_v, 0.f, acc);
@@ -207,11 +252,18 @@ __global__ void __launch_bounds__(kRedThreads, UGL_DP_BWD_MINB) depth_photo_fwdg
   float acc[kDpAcc];
 #pragma unroll
   for (int k = 0; k < kDpAcc; ++k) acc[k] = 0.f;
-  for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
+  const ChunkRange cr = chunk_range(plane);
+  long px = cr.begin + threadIdx.x;
+  DepthDirect nxt = {};
+  if (px < cr.end) nxt = depth_direct(L, b, dir, px);
+#pragma unroll 1
+  for (; px < cr.end; px += kRedThreads) {
+    const DepthDirect dl = nxt;
+    if (px + kRedThreads < cr.end) nxt = depth_direct(L, b, dir, px + kRedThreads);
     const int i = (int)(px / L.w), j = (int)(px % L.w);
     DepthPixel o;
     float gix, giy;
-    depth_pixel<true>(L, sK, sP, b, dir, i, j, px, g, o, &gix, &giy, 1.0f);
+    depth_pixel<true>(L, sK, sP, b, dir, i, j, px, g, dl, o, &gix, &giy, 1.0f);
     if (L.valid_out[dir]) L.valid_out[dir][(long)b * plane + px] = (fabsf(o.nc.gx) <= 1.0f && fabsf(o.nc.gy) <= 1.0f) ? 1.f : 0.f;
     if (L.tex_out[dir]) L.tex_out[dir][(long)b * plane + px] = o.tex;
     acc[12] += (fabsf(o.I[0] - o.rec[0]) + fabsf(o.I[1] - o.rec[1]) + fabsf(o.I[2] - o.rec[2])) * o.mask;

@@ -12,6 +12,7 @@ per tensor that feeds several terms (disparities, level-0 flows, K[R|t]), zero f
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -43,6 +44,50 @@ def _run(fn, args, grad_from: int, need: bool):
     with torch.no_grad():
         out = fn.forward(ctx, *args)
     return ctx, out
+
+
+class _Side:
+    """Independent branches of a mode step on side streams: ``with _Side(k):`` runs its body on the device's k-th side stream, ordered
+    after everything issued so far on the current stream; ``_Side.join()`` makes the current stream wait for every side stream used
+    since the last join.  Fork / join by stream waits only (no host synchronisation): captures into a CUDA graph as parallel branches.
+    Tensors allocated inside a branch are only used on the main stream after the join, and every later use of a side stream starts
+    with a wait on the main stream, so the caching allocator's per-stream reuse stays ordered.  ``UGL_MODE_STREAMS=0`` disables it
+    (everything on the current stream, as before)."""
+    _streams: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
+    _open: Dict[int, "torch.cuda.Stream"] = {}
+    enabled = os.environ.get("UGL_MODE_STREAMS", "1") != "0"
+
+    def __init__(self, k: int):
+        self.k = k
+
+    def __enter__(self):
+        if not _Side.enabled:
+            self.ctx = None
+            return self
+        main = torch.cuda.current_stream()
+        key = (main.device.index if main.device.index is not None else torch.cuda.current_device(), self.k)
+        st = _Side._streams.get(key)
+        if st is None:
+            st = _Side._streams[key] = torch.cuda.Stream(device=main.device)
+        st.wait_stream(main)
+        _Side._open[self.k] = st
+        self.ctx = torch.cuda.stream(st)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+    @staticmethod
+    def join(*ks: int):
+        """the current stream waits for side streams ``ks`` (default: every one used since its last join)"""
+        main = torch.cuda.current_stream()
+        for k in (ks or tuple(_Side._open)):
+            st = _Side._open.pop(k, None)
+            if st is not None:
+                main.wait_stream(st)
 
 
 def _accumulate(pairs: List[Tuple[Tensor, Tensor]]) -> None:
@@ -149,21 +194,26 @@ class _GeomStepFn(torch.autograd.Function):
         need_any = need_flow or need_disp or need_pose
         H = img.shape[2]
         downs = tuple(H / d.shape[2] for d in disp)
-        c_pose, out = _run(ops._PoseSetupFn, (pose, K, K_inv, downs, True), 0, need_pose)
+        with _Side(0):      # the disparity smoothness needs nothing the other branches produce
+            c_smooth, sm3 = _run(ops._DispSmoothMultiFn, (3, S, img, img_l, img_r, *disp, *disp_l, *disp_r), 2 + 3, need_disp)
+        with _Side(1):
+            c_pose, out = _run(ops._PoseSetupFn, (pose, K, K_inv, downs, True), 0, need_pose)
         Kinv, P_b, P_f, Fm = list(out[:S]), list(out[S:2 * S]), list(out[2 * S:3 * S]), list(out[3 * S:])
         pyr = ops.image_pyramids((img, img_l, img_r), S, ("bilinear", ("bilinear", "area"), ("bilinear", "area")))
+        _Side.join(1)
         pc, pl, pr = (d["bilinear"] for d in pyr)
         area = (pyr[1]["area"], pyr[2]["area"])
         c_flow, out = _run(ops._GeomFlowLossFn, (S, S, float(alpha), float(beta), *pl[:S], *pc[:S], *pr[:S], *ff[:S], *fb[:S], *disp, *Kinv,
                                                   *P_b, *P_f), 4 + 3 * S, need_flow)
         flow4, mbytes = out[0], list(out[1:])
+        with _Side(1):      # the level-0 rigid terms and the reprojection term both start from the flow branch's mask bytes
+            c_rigid, out_r = _run(ops._GeomRigidFn, (fb[0], ff[0], disp[0], mbytes[0], Kinv[0], P_b[0], P_f[0], Fm[0], Fm[1],
+                                                      (ops.MASK_ALL_BWD, ops.MASK_ALL_FWD)), 0, need_any)
         c_photo, out = _run(ops._DepthPhotoFn, (S, 2, (ops.MASK_ALL_BWD, ops.MASK_ALL_FWD), *pc[:S], *area[0][:S], *area[1][:S], *pl[:S],
                                                  *pr[:S], *disp, *Kinv, *P_b, *P_f, *mbytes), 3, need_disp or need_pose)
         depth_pixel, pmasks = out[0], out[1:]
-        c_rigid, out = _run(ops._GeomRigidFn, (fb[0], ff[0], disp[0], mbytes[0], Kinv[0], P_b[0], P_f[0], Fm[0], Fm[1],
-                                                (ops.MASK_ALL_BWD, ops.MASK_ALL_FWD)), 0, need_any)
-        dfc, epi = out
-        c_smooth, sm3 = _run(ops._DispSmoothMultiFn, (3, S, img, img_l, img_r, *disp, *disp_l, *disp_r), 2 + 3, need_disp)
+        dfc, epi = out_r
+        _Side.join()
         B = img.shape[0]
         mat = _assemble([(depth_pixel, 1), (sm3, 3), (flow4[0], 1), (flow4[1], 1), (flow4[2], 1), (flow4[3], 1), (dfc, 1), (epi, 1)], B, img.device)
         ctx.sub = (c_pose, c_flow, c_photo, c_rigid, c_smooth)
@@ -184,10 +234,13 @@ class _GeomStepFn(torch.autograd.Function):
         need_flow, need_disp, need_pose = ctx.flags
         gmat = gmat.contiguous()
         with torch.no_grad():
-            gsm = ops._DispSmoothMultiFn.backward(c_smooth, gmat[1].unsqueeze(0).expand(3, -1).contiguous())
-            g_rigid = ops._GeomRigidFn.backward(c_rigid, gmat[6].contiguous(), gmat[7].contiguous())
+            with _Side(0):
+                gsm = ops._DispSmoothMultiFn.backward(c_smooth, gmat[1].unsqueeze(0).expand(3, -1).contiguous())
+            with _Side(1):
+                g_rigid = ops._GeomRigidFn.backward(c_rigid, gmat[6].contiguous(), gmat[7].contiguous())
             g_photo = ops._DepthPhotoFn.backward(c_photo, gmat[0].contiguous())
             g_flow = ops._GeomFlowLossFn.backward(c_flow, gmat[2:6].contiguous())
+            _Side.join()
             # unpack by the sub-Functions' own input layouts
             gfb0, gff0, gd0, _, _, gPb0, gPf0, gFb, gFf, _ = g_rigid
             gdisp = list(g_photo[3 + 5 * S:3 + 6 * S])
@@ -238,9 +291,13 @@ class _DepthStepFn(torch.autograd.Function):
         need_disp, need_pose = any(needs[3:3 + 3 * S]), needs[3 + 3 * S]
         H = img.shape[2]
         downs = tuple(H / d.shape[2] for d in disp)
-        c_pose, out = _run(ops._PoseSetupFn, (pose, K, None, downs, False), 0, need_pose)
+        with _Side(0):      # the disparity smoothness needs nothing the other terms produce
+            c_smooth, sm3 = _run(ops._DispSmoothMultiFn, (3, S, img, img_l, img_r, *disp, *disp_l, *disp_r), 2 + 3, need_disp)
+        with _Side(1):
+            c_pose, out = _run(ops._PoseSetupFn, (pose, K, None, downs, False), 0, need_pose)
         Kinv, P_b, P_f = list(out[:S]), list(out[S:2 * S]), list(out[2 * S:3 * S])
         pyr = ops.image_pyramids((img, img_l, img_r), S, ("bilinear", ("bilinear", "area"), ("bilinear", "area")))
+        _Side.join(1)
         pc, pl, pr = (d["bilinear"] for d in pyr)
         area = (pyr[1]["area"], pyr[2]["area"])
         flat = (*pc[:S], *area[0][:S], *area[1][:S], *pl[:S], *pr[:S], *disp, *Kinv, *P_b, *P_f)
@@ -253,11 +310,11 @@ class _DepthStepFn(torch.autograd.Function):
             c_photo, out = _run(ops._DepthSsimFn, (S, *flat), 1, need_disp or need_pose)
             rows += [(out[0][0], 1), (out[0][1], 1)]
         masks = out[1:]
-        c_smooth, sm3 = _run(ops._DispSmoothMultiFn, (3, S, img, img_l, img_r, *disp, *disp_l, *disp_r), 2 + 3, need_disp)
         rows.append((sm3, 3))
         if variant == "texture":
             c_consis, cons = _run(ops._DepthConsisFn, (S, *disp, *disp_l, *disp_r, *Kinv, *P_b, *P_f), 1, need_disp or need_pose)
             rows.append((cons, 1))
+        _Side.join()
         mat = _assemble(rows, B, img.device)
         ctx.sub = (c_pose, c_photo, c_consis, c_smooth)
         ctx.S, ctx.variant, ctx.flags = S, variant, (need_disp, need_pose)
@@ -276,7 +333,8 @@ class _DepthStepFn(torch.autograd.Function):
         keys = DEPTH_KEYS[variant]
         gmat = gmat.contiguous()
         with torch.no_grad():
-            gsm = ops._DispSmoothMultiFn.backward(c_smooth, gmat[keys.index("loss_depth_smooth")].unsqueeze(0).expand(3, -1).contiguous())
+            with _Side(0):
+                gsm = ops._DispSmoothMultiFn.backward(c_smooth, gmat[keys.index("loss_depth_smooth")].unsqueeze(0).expand(3, -1).contiguous())
             if variant == "live":
                 g_photo = ops._DepthPhotoFn.backward(c_photo, gmat[0].contiguous())
                 base = 3
@@ -287,6 +345,7 @@ class _DepthStepFn(torch.autograd.Function):
             gPb, gPf = list(g_photo[base + 7 * S:base + 8 * S]), list(g_photo[base + 8 * S:base + 9 * S])
             gsm_c, gsm_l, gsm_r = list(gsm[5:5 + S]), list(gsm[5 + S:5 + 2 * S]), list(gsm[5 + 2 * S:5 + 3 * S])
             pairs = [(gdisp[l], gsm_c[l]) for l in range(S)]
+            _Side.join()
             if c_consis is not None:
                 g_c = ops._DepthConsisFn.backward(c_consis, gmat[3].contiguous())
                 # (None, gdisp[S], gref_l[S], gref_r[S], None[S], gP_b[S], gP_f[S])
