@@ -8,12 +8,12 @@ import csv
 import sys
 
 
-def main(path, marker):
+def main(path, marker, exclude=()):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     hdr, data = rows[0], rows[1:]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     idx = [i for i, r in enumerate(data) if marker in r[ki]]
-    step = data[idx[-2]:idx[-1]]
+    step = [r for r in data[idx[-2]:idx[-1]] if not any(x in r[ki] for x in exclude)]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for r in step:
         v = float(r[vi].replace(",", "")) / (1000.0 if r[ui] == "ns" else 1.0)
@@ -26,4 +26,4 @@ def main(path, marker):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], tuple(sys.argv[3:]))   # further arguments: kernel-name substrings to leave out (the L2-flush fill between steps)

@@ -469,3 +469,64 @@ def test_depth_step_node_equals_op_by_op(cuda_device, variant):
         assert (x is None) == (y is None)
         if x is not None:
             assert rel_err(x, y) < 1e-6
+
+
+# ---- programmatic dependent launches / side streams: same bits, no stale data ---------------------------------------------------
+def test_fused_step_graph_replay_tracks_inputs(cuda_device):
+    """The fused step's kernels are chained by programmatic dependent launches (the stencil kernel starts under the weight-sum kernel,
+    the finalize under the stencil kernel's tail).  One captured graph replayed on inputs changed in place must give, every time,
+    exactly what a fresh eager call gives on the same inputs: nothing read before its producer finished, nothing stale in a cache."""
+    dev = cuda_device
+    B, H, W, L = 2, 128, 416, 4
+    t = make_triplet(B, H, W, L, 1, seed=97, flow_px=6.0).to(dev)
+    pl, pc, pr = (ops.image_pyramid(x, L, "box") for x in (t.img_l, t.img, t.img_r))
+    gl = (torch.rand(4, B, generator=torch.Generator().manual_seed(5)) + 0.5).to(dev)
+    out = ops.flow_loss_step(pl, pc, pr, t.flows_fwd, t.flows_bwd, gl, L)
+    g, s = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ops.flow_loss_step(pl, pc, pr, t.flows_fwd, t.flows_bwd, gl, L, out=out)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            ops.flow_loss_step(pl, pc, pr, t.flows_fwd, t.flows_bwd, gl, L, out=out)
+    torch.cuda.synchronize()
+    for k in range(4):
+        for f in t.flows_fwd + t.flows_bwd:
+            f.mul_(0.8)
+        for x in pc + pl:
+            x.mul_(0.97)
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        got = [out["loss"].clone()] + [x.clone() for x in out["gf"] + out["gb"]]
+        fresh = ops.flow_loss_step(pl, pc, pr, t.flows_fwd, t.flows_bwd, gl, L)
+        torch.cuda.synchronize()
+        for a, b in zip(got, [fresh["loss"]] + fresh["gf"] + fresh["gb"]):
+            assert torch.equal(a, b), k
+
+
+def test_mode_steps_side_streams_same_bits(cuda_device):
+    """mode_steps runs independent branches of a geom / depth step on side streams (fork / join by stream waits).  Same kernels, same
+    inputs: every loss and gradient bit-identical with the single-stream order."""
+    from unsupervised_depth_opticalflow_egomotion_b200 import mode_steps
+    t = make_triplet(2, 64, 208, 4, 3, seed=99, flow_mode="rigid").to(cuda_device)
+    res = {}
+    saved = mode_steps._Side.enabled
+    try:
+        for enabled in (True, False):
+            mode_steps._Side.enabled = enabled
+            ff, fb = _leaf_list(t.flows_fwd, cuda_device), _leaf_list(t.flows_bwd, cuda_device)
+            disp, disp_l, disp_r = _leaf_list(t.disp, cuda_device), _leaf_list(t.disp_l, cuda_device), _leaf_list(t.disp_r, cuda_device)
+            pose = t.pose.detach().clone().requires_grad_(True)
+            loss, _ = losses.GeometryLoss(3).forward_losses(t.img_l, t.img, t.img_r, ff, fb, disp, disp_l, disp_r, pose, t.K, t.K_inv)
+            total = losses.total_loss(loss, P.GEOM_WEIGHTS)
+            g = torch.autograd.grad(total, ff[:3] + fb[:3] + disp + disp_l + disp_r + [pose])
+            d2, d2l, d2r = _leaf_list(t.disp, cuda_device), _leaf_list(t.disp_l, cuda_device), _leaf_list(t.disp_r, cuda_device)
+            pose2 = t.pose.detach().clone().requires_grad_(True)
+            dl, _ = losses.DepthLoss(3, "texture").forward_losses(t.img_l, t.img, t.img_r, d2, d2l, d2r, pose2, t.K)
+            dg = torch.autograd.grad(losses.total_loss(dl, P.GEOM_WEIGHTS), d2 + d2l + d2r + [pose2], allow_unused=True)
+            torch.cuda.synchronize()
+            res[enabled] = ([total.detach()] + [x.detach() for x in g], [dl[k].detach() for k in sorted(dl) if dl[k].numel() > 2] + [x for x in dg if x is not None])
+    finally:
+        mode_steps._Side.enabled = saved
+    for a, b in zip(res[True][0] + res[True][1], res[False][0] + res[False][1]):
+        assert torch.equal(a, b)

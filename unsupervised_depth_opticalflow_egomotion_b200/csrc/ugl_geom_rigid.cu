@@ -38,6 +38,23 @@ __device__ __forceinline__ void rigid_load_mats(const RigidTermsParams& p, int b
   __syncthreads();
 }
 
+// the coalesced loads of one pixel and direction, issued one loop iteration ahead of their use
+struct RigidDirect { float D, u, v; unsigned bits; };
+__device__ __forceinline__ RigidDirect rigid_direct(const RigidTermsParams& p, int b, int d, long plane, long px) {
+  RigidDirect r;
+  r.D = p.disp[(long)b * plane + px];
+  r.bits = p.mask[(long)b * plane + px];
+  r.u = p.flow[d][((long)b * 2) * plane + px];
+  r.v = p.flow[d][((long)b * 2 + 1) * plane + px];
+  return r;
+}
+// contiguous chunk of the sample's pixels for this CTA (a multiple of the CTA size), walked front to back
+__device__ __forceinline__ void rigid_chunk(long plane, long& begin, long& end) {
+  const long per = (((plane + gridDim.x - 1) / gridDim.x) + kRedThreads - 1) / kRedThreads * kRedThreads;
+  begin = blockIdx.x * per;
+  end = begin + per < plane ? begin + per : plane;
+}
+
 // grid (chunks, B, 2): one direction per CTA (the kernels are latency-bound: half the live state, twice the CTAs in flight)
 __global__ void __launch_bounds__(kRedThreads, 3) rigid_terms_fwd_kernel(const __grid_constant__ RigidTermsParams p) {
   __shared__ float sm[51];
@@ -46,11 +63,18 @@ __global__ void __launch_bounds__(kRedThreads, 3) rigid_terms_fwd_kernel(const _
   rigid_load_mats(p, b, sm);
   const long plane = (long)p.H * p.W;
   float acc[3] = {0.f, 0.f, 0.f};
-  for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
+  long px, end;
+  rigid_chunk(plane, px, end);
+  px += threadIdx.x;
+  RigidDirect nxt = {};
+  if (px < end) nxt = rigid_direct(p, b, d, plane, px);
+#pragma unroll 1
+  for (; px < end; px += kRedThreads) {
+    const RigidDirect cur = nxt;
+    if (px + kRedThreads < end) nxt = rigid_direct(p, b, d, plane, px + kRedThreads);
     const int i = (int)(px / p.W), j = (int)(px % p.W);
-    const float D = p.disp[(long)b * plane + px];
-    const unsigned bits = p.mask[(long)b * plane + px];
-    const float u = p.flow[d][((long)b * 2) * plane + px], v = p.flow[d][((long)b * 2 + 1) * plane + px];
+    const float D = cur.D, u = cur.u, v = cur.v;
+    const unsigned bits = cur.bits;
     const Projected r = project_pixel(sm, sm + 9 + 12 * d, D, j, i);
     const float du = fabsf(sub_rn(sub_rn(r.u, (float)j), u)), dv = fabsf(sub_rn(sub_rn(r.v, (float)i), v));
     const float m = (bits & p.need[d]) == p.need[d] ? 1.f : 0.f;
@@ -88,11 +112,18 @@ __global__ void __launch_bounds__(kRedThreads, 2) rigid_terms_bwd_kernel(const _
   float acc[21];                                    // P (12), F (9) of this direction
 #pragma unroll
   for (int k = 0; k < 21; ++k) acc[k] = 0.f;
-  for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
+  long px, end;
+  rigid_chunk(plane, px, end);
+  px += threadIdx.x;
+  RigidDirect nxt = {};
+  if (px < end) nxt = rigid_direct(p, b, d, plane, px);
+#pragma unroll 1
+  for (; px < end; px += kRedThreads) {
+    const RigidDirect cur = nxt;
+    if (px + kRedThreads < end) nxt = rigid_direct(p, b, d, plane, px + kRedThreads);
     const int i = (int)(px / p.W), j = (int)(px % p.W);
-    const float D = p.disp[(long)b * plane + px];
-    const unsigned bits = p.mask[(long)b * plane + px];
-    const float u = p.flow[d][((long)b * 2) * plane + px], v = p.flow[d][((long)b * 2 + 1) * plane + px];
+    const float D = cur.D, u = cur.u, v = cur.v;
+    const unsigned bits = cur.bits;
     const Projected r = project_pixel(sm, Pd, D, j, i);
     const float m = (bits & p.need[d]) == p.need[d] ? 1.f : 0.f;
     const float k = kd * m;
