@@ -568,3 +568,35 @@ GEOM_WEIGHTS = {"loss_flow_pixel": 0.15, "loss_flow_ssim": 0.85, "loss_flow_smoo
 def weighted_total(loss_pack: Dict[str, Tensor], weights: Dict[str, float]) -> Tensor:
     """train.py:211-214: sum_k w_k * mean_B(loss_k)."""
     return sum(weights[k] * v.mean() for k, v in loss_pack.items())
+
+
+def warm_up(height: int = 64, width: int = 208) -> None:
+    """Evaluate every oracle path once (forward + backward, fp32) on a small seeded input and throw the results away.
+
+    Why: on some GPU boxes of the pool the FIRST evaluation of a torch CPU expression in a process was observed to come back with
+    ~1e-4 relative error (``2 * exp(-(w - 0.5)**2 / 0.03)`` of ``occlusion_weights``: 530 of 26,624 elements off by up to 2e-4; the same
+    call repeated in the same process is bit-identical to the fp64 value rounded, as on every other box) -- a property of the host
+    (KVM guest, AVX-512 torch kernels), not of the inputs.  The checker therefore runs its op set once before anything is compared
+    against it (``tests/conftest.py``, ``__graft_entry__.smoke``).  Sizes are above torch's parallel grain so the intra-op thread
+    pool is exercised too."""
+    g = torch.Generator().manual_seed(0)
+    B, L, S = 2, 2, 2
+    rnd = lambda *s: torch.rand(*s, generator=g)
+    img_l, img, img_r = rnd(B, 3, height, width), rnd(B, 3, height, width), rnd(B, 3, height, width)
+    mk = lambda c, scale: [((rnd(B, c, height >> l, width >> l) - 0.5) * scale).requires_grad_(True) for l in range(L)]
+    ff, fb = mk(2, 6.0), mk(2, 6.0)
+    disp, disp_l, disp_r = ([(rnd(B, 1, height >> l, width >> l) * 0.3 + 0.05).requires_grad_(True) for l in range(S)] for _ in range(3))
+    pose = ((rnd(B, 2, 6) - 0.5) * 0.02).requires_grad_(True)
+    K = torch.tensor([[0.58 * width, 0.0, 0.5 * width], [0.0, 1.92 * height, 0.5 * height], [0.0, 0.0, 1.0]]).expand(B, 3, 3).contiguous()
+    for _ in range(2):
+        out = flow_mode_loss(img_l, img, img_r, ff, fb, L)
+        sum(v.sum() for v in out.values()).backward()
+        fl = flow_backwarp(img_l, fb[0].detach(), True)
+        fr = flow_backwarp(img_r, ff[0].detach(), True)
+        for soft in (False, True):
+            occlusion_weights([fl], [img], [fr], 1, soft=soft)
+        for variant in ("live", "texture"):
+            out = depth_mode_loss(img_l, img, img_r, disp, disp_l, disp_r, pose, K, S, variant)
+            sum(v.sum() for v in out.values() if v.requires_grad).backward()
+        out = geom_mode_loss(img_l, img, img_r, ff, fb, disp, disp_l, disp_r, pose, K, torch.linalg.inv(K), S)
+        sum(v.sum() for v in out.values() if v.requires_grad).backward()
