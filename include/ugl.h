@@ -95,7 +95,8 @@ int ugl_flow_loss_forward_grad(const UglFlowLossArgs* args);
 int ugl_flow_loss_forward_grad_ex(const UglFlowLossArgs* args, int32_t variant);
 /* Fused forward + backward for a training step, where the upstream gradient is known before the forward runs (train.py:211-215:
  * d total / d loss_k[b] = w_k / B): loss (4,B) AND grad_flow_fwd/bwd[l] in four launches (photometry kernel, weight sums, stencil
- * kernel, finalize).  The per-sample normalisers only depend on the photometry kernel's sums, so the stencil kernel scales and
+ * kernel, finalize) chained by programmatic dependent launch on args->stream (the stencil kernel starts under the weight sums and
+ * waits for them before its last phase; stream order towards other work is unchanged).  The per-sample normalisers only depend on the photometry kernel's sums, so the stencil kernel scales and
  * adds the four gradient terms itself: no basis planes (args->basis is ignored), no combine launch.  Same results as
  * ugl_flow_loss_forward_grad + ugl_flow_loss_combine. */
 int ugl_flow_loss_step(const UglFlowLossArgs* args);
