@@ -325,6 +325,8 @@ typedef struct UglDispSmoothArgs {
   void* workspace;
   uint64_t workspace_bytes;
   void* stream;
+  int32_t grad_out_shared;                                       /* [combine] 1: grad_out is ONE (B,) row used by every list (the three
+                                                                    compute_smooth_loss calls of model_geometry.py:938-940 share one weight) */
 } UglDispSmoothArgs;
 uint64_t ugl_disp_smooth_fused_workspace_bytes(const UglDispSmoothArgs* args);
 int ugl_disp_smooth_forward_grad(const UglDispSmoothArgs* args);

@@ -109,7 +109,7 @@ class UglDispSmoothArgs(C.Structure):
         ("batch", C.c_int32), ("lists", C.c_int32), ("levels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
         ("lheight", C.c_int32 * MAX_LEVELS), ("lwidth", C.c_int32 * MAX_LEVELS),
         ("img", C.c_void_p * MAX_LISTS), ("disp", _LL), ("out", C.c_void_p), ("G", _LL), ("grad_out", C.c_void_p), ("grad_disp", _LL),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("stream", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("stream", C.c_void_p), ("grad_out_shared", C.c_int32),
     ]
 
 

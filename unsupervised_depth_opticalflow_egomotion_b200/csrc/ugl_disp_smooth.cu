@@ -30,7 +30,8 @@ struct DsParams {
   const float* disp[kDsLists][kMaxLevels];
   float* G[kDsLists][kMaxLevels];
   float* partials;              // [lists*B][tiles][2]
-  const float* gout;            // (lists,B)
+  const float* gout;            // (lists,B), or one (B,) row for all lists (gout_stride = 0)
+  int gout_stride;
   float* gdisp[kDsLists][kMaxLevels];
 };
 
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(256) disp_smooth_combine_tiled_kernel(const __
     sR[r][j] = acc;
   }
   __syncthreads();
-  const float g = p.gout[li * p.B + b];
+  const float g = p.gout[li * p.gout_stride + b];
   float* gd = p.gdisp[li][l] + (long)b * h * w;
   for (int k = threadIdx.x; k < LH * LW; k += 256) {           // (b) low-resolution pixels
     const int i = k / LW, j = k - i * LW;
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(256) disp_smooth_combine_kernel(const __grid_c
   const int h = p.h[l], w = p.w[l], H = p.H, W = p.W;
   const float* G = p.G[li][l] + (long)b * H * W;
   float* gd = p.gdisp[li][l] + (long)b * h * w;
-  const float g = p.gout[li * p.B + b];
+  const float g = p.gout[li * p.gout_stride + b];
   const int n = h * w;
   if (h == H && w == W) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) gd[i] = g * G[i];
@@ -388,6 +389,7 @@ extern "C" int ugl_disp_smooth_combine(const UglDispSmoothArgs* a) {
   if (rc) return rc;
   if (!a->grad_out) return fail(UGL_EINVAL, "disp_smooth_combine: null grad_out");
   p.gout = a->grad_out;
+  p.gout_stride = a->grad_out_shared ? 0 : p.B;
   for (int li = 0; li < a->lists; ++li)
     for (int l = 0; l < a->levels; ++l) {
       if (!a->G[li][l] || !a->grad_disp[li][l]) return fail(UGL_EINVAL, "disp_smooth_combine: null G / grad_disp (list %d, level %d)", li, l);

@@ -235,7 +235,7 @@ class _GeomStepFn(torch.autograd.Function):
         gmat = gmat.contiguous()
         with torch.no_grad():
             with _Side(0):
-                gsm = ops._DispSmoothMultiFn.backward(c_smooth, gmat[1].unsqueeze(0).expand(3, -1).contiguous())
+                gsm = ops._DispSmoothMultiFn.backward(c_smooth, gmat[1])
             with _Side(1):
                 g_rigid = ops._GeomRigidFn.backward(c_rigid, gmat[6].contiguous(), gmat[7].contiguous())
             g_photo = ops._DepthPhotoFn.backward(c_photo, gmat[0].contiguous())
@@ -334,7 +334,7 @@ class _DepthStepFn(torch.autograd.Function):
         gmat = gmat.contiguous()
         with torch.no_grad():
             with _Side(0):
-                gsm = ops._DispSmoothMultiFn.backward(c_smooth, gmat[keys.index("loss_depth_smooth")].unsqueeze(0).expand(3, -1).contiguous())
+                gsm = ops._DispSmoothMultiFn.backward(c_smooth, gmat[keys.index("loss_depth_smooth")])
             if variant == "live":
                 g_photo = ops._DepthPhotoFn.backward(c_photo, gmat[0].contiguous())
                 base = 3

@@ -942,7 +942,7 @@ class _DispSmoothMultiFn(torch.autograd.Function):
         if not Gs:
             return (None,) * (2 + nl + nl * L)
         G = [list(Gs[i * L:(i + 1) * L]) for i in range(nl)]
-        gout = _dev(gout, "grad_out")
+        gout = _dev(gout, "grad_out")             # (nl,B), or ONE (B,) row shared by all lists (mode_steps: no expand + copy launch)
         dev = gout.device
         gd = [[torch.empty(ctx.shapes[l], device=dev, dtype=torch.float32) for l in range(L)] for _ in range(nl)]
 
@@ -952,6 +952,7 @@ class _DispSmoothMultiFn(torch.autograd.Function):
 
         B, H, W = ctx.full
         a = _disp_smooth_args([_Shape((B, 3, H, W))] * nl, [[_Shape(s) for s in ctx.shapes]] * nl, None, G, gout, gd)
+        a.grad_out_shared = 1 if gout.dim() == 1 else 0
         with torch.cuda.device_of(gout):
             _call("ugl_disp_smooth_combine", C.byref(a))
         return (None, None, *([None] * nl), *[g for row in gd for g in row])
