@@ -58,21 +58,20 @@ __device__ __forceinline__ int ds_idx(int ly, int lx) { return ly * kDsPitch + l
 //   pixels, adds |d| * w to the loss sums and writes G = d loss / d U for both pixels (one 64-bit store).
 // Every staging pass maps a warp to a row and its lanes to the columns (no division per element), and everything that depends only on
 // (tile, level) -- the patch bounds, the tap tables of the 34 columns and 18 rows -- is formed once per CTA for all levels by a handful
-// of threads before the first barrier (the kernel is bound by instruction issue: r2e profile, 765 warp-instructions per 32 pixels, 39 %
-// of them per-level set-up that every thread repeated).
+// of threads before the first barrier.  The levels are staged TOGETHER: all patches, then all up-sampled tiles, then all pair sums --
+// four CTA barriers per tile instead of 3 per level + 2 (the kernel is paced by its barriers: 12 % fewer instructions had bought 2.5 %).
 // Zero weights stand in for every bounds test: a weight is 0 where the edge it belongs to leaves the image, and U is 0 outside.
 // This term feeds no mask: exp() is the fast intrinsic (relative error ~1e-7 on [-1, 0]), well inside the 1e-5 loss tolerance.
 constexpr int kDsNW = kDsNT / 32;
 __global__ void __launch_bounds__(kDsNT) disp_smooth_fwdgrad_kernel(const __grid_constant__ DsParams p) {
   __shared__ __align__(16) float sI[3][kDsPlane];
-  __shared__ __align__(16) float sWx[kDsPlane], sWy[kDsPlane], sU[kDsPlane];
-  __shared__ __align__(16) float sT[kDsPatchH][kDsPitch];
+  __shared__ __align__(16) float sWx[kDsPlane], sWy[kDsPlane], sU[kMaxLevels][kDsPlane];
   __shared__ float red[(kDsNT / 32) * 2];
   // per level: patch column / row of the two up-sampling taps of every tile column / row, their weights, the patch bounds
   __shared__ int sXi[kMaxLevels][2][kDsPW], sYr[kMaxLevels][2][kDsPH];
   __shared__ float sXl[kMaxLevels][2][kDsPW], sYl[kMaxLevels][2][kDsPH];
   __shared__ int sBnd[kMaxLevels][4];                 // cx0, pw, ry0, ph
-  __shared__ float sD[kDsPatch];                      // the low-resolution disparity patch under the tile
+  __shared__ float sD[kMaxLevels][kDsPatch];          // the low-resolution disparity patches under the tile
   const int tile = blockIdx.x, b = blockIdx.y, li = blockIdx.z;
   const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
   const int x0 = tx * kDsTW, y0 = ty * kDsTH, H = p.H, W = p.W;
@@ -154,6 +153,47 @@ __global__ void __launch_bounds__(kDsNT) disp_smooth_fwdgrad_kernel(const __grid
   for (int k = 0; k < (kDsPH + kDsNW - 1) / kDsNW; ++k)
     if (warp + k * kDsNW < kDsPH) edge(warp + k * kDsNW, lane);
   if (threadIdx.x < 2 * kDsPH) edge(threadIdx.x >> 1, 32 + (threadIdx.x & 1));
+  // the low-resolution patches of all sub-sampled levels
+  for (int l = 0; l < p.levels; ++l) {
+    const int h = p.h[l], w = p.w[l];
+    if (h == H && w == W) continue;
+    const float* d = p.disp[li][l] + (long)b * h * w;
+    const int cx0 = sBnd[l][0], pw = sBnd[l][1], ry0 = sBnd[l][2], ph = sBnd[l][3];
+    for (int r = warp; r < ph; r += kDsNW)
+      if (lane < pw) sD[l][r * pw + lane] = d[(long)(ry0 + r) * w + cx0 + lane];
+  }
+  __syncthreads();                         // weights and patches ready
+  // the up-sampled tiles (+1 halo) of all levels, 0 outside the image: horizontal interpolation of the two patch rows a tile row
+  // touches, then the vertical one (the same two roundings as a pass over interpolated rows)
+  for (int l = 0; l < p.levels; ++l) {
+    const int h = p.h[l], w = p.w[l];
+    const float* d = p.disp[li][l] + (long)b * h * w;
+    const bool full = (h == H && w == W);
+    const int pw = full ? 0 : sBnd[l][1];
+    auto upsample = [&](int ly, int lx) {
+      const int Y = y0 - 1 + ly, X = x0 - 1 + lx;
+      float v = 0.f;
+      if (Y >= 0 && Y < H && X >= 0 && X < W) {
+        if (full) {
+          v = d[(long)Y * W + X];
+        } else {
+          const float* r0 = sD[l] + sYr[l][0][ly] * pw;
+          const float* r1 = sD[l] + sYr[l][1][ly] * pw;
+          const int c0 = sXi[l][0][lx], c1 = sXi[l][1][lx];
+          const float a0 = sXl[l][0][lx], a1 = sXl[l][1][lx];
+          const float t0 = a0 * r0[c0] + a1 * r0[c1];
+          const float t1 = a0 * r1[c0] + a1 * r1[c1];
+          v = sYl[l][0][ly] * t0 + sYl[l][1][ly] * t1;
+        }
+      }
+      sU[l][ds_idx(ly, lx)] = v;
+    };
+#pragma unroll
+    for (int k = 0; k < (kDsPH + kDsNW - 1) / kDsNW; ++k)
+      if (warp + k * kDsNW < kDsPH) upsample(warp + k * kDsNW, lane);
+    if (threadIdx.x < 2 * kDsPH) upsample(threadIdx.x >> 1, 32 + (threadIdx.x & 1));
+  }
+  __syncthreads();
   // this thread's pixel pair
   const int pty = threadIdx.x / (kDsTW / 2), ptx = (threadIdx.x - pty * (kDsTW / 2)) * 2;
   const int PY = y0 + pty, PX = x0 + ptx;
@@ -161,49 +201,15 @@ __global__ void __launch_bounds__(kDsNT) disp_smooth_fwdgrad_kernel(const __grid
   const bool in0 = PY < H && PX < W, in1 = PY < H && PX + 1 < W;
   float acc[2] = {0.f, 0.f};
   const float inx = 1.0f / ((float)H * (float)(W - 1)), iny = 1.0f / ((float)(H - 1) * (float)W);
+  const float2 wx = *reinterpret_cast<const float2*>(sWx + pq), wy = *reinterpret_cast<const float2*>(sWy + pq);
+  const float wxl = sWx[pq - 1];
+  const float2 wyu = *reinterpret_cast<const float2*>(sWy + pq - kDsPitch);
   for (int l = 0; l < p.levels; ++l) {
-    const int h = p.h[l], w = p.w[l];
-    const float* d = p.disp[li][l] + (long)b * h * w;
-    const bool full = (h == H && w == W);
-    int pw = 0, ph = 0;
-    if (!full) {
-      const int cx0 = sBnd[l][0], ry0 = sBnd[l][2];
-      pw = sBnd[l][1]; ph = sBnd[l][3];
-      // sD was last read before the previous level's mid barriers
-      for (int r = warp; r < ph; r += kDsNW)
-        if (lane < pw) sD[r * pw + lane] = d[(long)(ry0 + r) * w + cx0 + lane];
-    }
-    __syncthreads();                       // weights ready (first level) / previous level's sU consumed / patch ready
-    if (!full) {
-      for (int r = warp; r < ph; r += kDsNW) {                     // horizontal interpolation of every patch row
-        const float* row = sD + r * pw;
-        sT[r][lane + 1] = sXl[l][0][lane] * row[sXi[l][0][lane]] + sXl[l][1][lane] * row[sXi[l][1][lane]];
-        if (lane < kDsPW - 32) {
-          const int lx = lane + 32;
-          sT[r][lx + 1] = sXl[l][0][lx] * row[sXi[l][0][lx]] + sXl[l][1][lx] * row[sXi[l][1][lx]];
-        }
-      }
-      __syncthreads();
-    }
-    auto upsample = [&](int ly, int lx) {                          // vertical interpolation -> the up-sampled tile (0 outside the image)
-      const int Y = y0 - 1 + ly, X = x0 - 1 + lx;
-      float v = 0.f;
-      if (Y >= 0 && Y < H && X >= 0 && X < W)
-        v = full ? d[(long)Y * W + X] : sYl[l][0][ly] * sT[sYr[l][0][ly]][lx + 1] + sYl[l][1][ly] * sT[sYr[l][1][ly]][lx + 1];
-      sU[ds_idx(ly, lx)] = v;
-    };
-#pragma unroll
-    for (int k = 0; k < (kDsPH + kDsNW - 1) / kDsNW; ++k)
-      if (warp + k * kDsNW < kDsPH) upsample(warp + k * kDsNW, lane);
-    if (threadIdx.x < 2 * kDsPH) upsample(threadIdx.x >> 1, 32 + (threadIdx.x & 1));
-    __syncthreads();
+    const float* sUl = sU[l];
     {
-      const float2 c = *reinterpret_cast<const float2*>(sU + pq);
-      const float ul = sU[pq - 1], ur = sU[pq + 2];
-      const float2 up = *reinterpret_cast<const float2*>(sU + pq - kDsPitch), dn = *reinterpret_cast<const float2*>(sU + pq + kDsPitch);
-      const float2 wx = *reinterpret_cast<const float2*>(sWx + pq), wy = *reinterpret_cast<const float2*>(sWy + pq);
-      const float wxl = sWx[pq - 1];
-      const float2 wyu = *reinterpret_cast<const float2*>(sWy + pq - kDsPitch);
+      const float2 c = *reinterpret_cast<const float2*>(sUl + pq);
+      const float ul = sUl[pq - 1], ur = sUl[pq + 2];
+      const float2 up = *reinterpret_cast<const float2*>(sUl + pq - kDsPitch), dn = *reinterpret_cast<const float2*>(sUl + pq + kDsPitch);
       // horizontal edges (left|c.x), (c.x|c.y), (c.y|right): signed weights once per edge
       const float a_l = ul - c.x, a_c = c.x - c.y, a_r = c.y - ur;
       const float s_l = wxl * sgnf(a_l), s_c = wx.x * sgnf(a_c), s_r = wx.y * sgnf(a_r);
