@@ -252,7 +252,9 @@ def mode_step(workload: str, batch: int, height: int, width: int, dev, steps: in
     leaves = [x.requires_grad_(True) for x in t.flows_fwd + t.flows_bwd + t.disp + t.disp_l + t.disp_r + [t.pose]]
     if workload == "geom":
         mod = losses.GeometryLoss(S)
-        fwd = lambda: mod.forward_losses(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd, t.disp, t.disp_l, t.disp_r, t.pose, t.K, t.K_inv)[0]
+        # training-step form: the weights of the total are declared up front, the flow branch writes its gradients in its forward launches
+        fwd = lambda: mod.forward_losses(t.img_l, t.img, t.img_r, t.flows_fwd, t.flows_bwd, t.disp, t.disp_l, t.disp_r, t.pose, t.K, t.K_inv,
+                                         step_weights=GEOM_WEIGHTS)[0]
     elif workload in ("depth", "depth-texture", "depth-live"):
         # depth = BASELINE configs[2] (model_depth_texture.py:296-307, reprojection L1 + SSIM + smoothness);
         # depth-texture = that file's whole loss (+ the depth-consistency term, :309-310); depth-live = model_depth.py

@@ -141,6 +141,10 @@ typedef struct UglGeomFlowArgs {
 int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* args);
 int ugl_geom_flow_forward_grad_ex(const UglGeomFlowArgs* args, int32_t variant);   /* variant: UGL_SINGLE_PASS_* */
 int ugl_geom_flow_combine(const UglGeomFlowArgs* args);
+/* Fused forward + backward of the geom-mode flow branch for a training step (the counterpart of ugl_flow_loss_step; train.py:211-215:
+ * d total / d loss_k[b] = w_k / B known before the forward runs): flow.loss (4,B), mask_bytes AND flow.grad_flow_fwd/bwd[l] in four
+ * chained launches; flow.basis is ignored, no combine launch.  Same results as ugl_geom_flow_forward_grad + ugl_geom_flow_combine. */
+int ugl_geom_flow_step(const UglGeomFlowArgs* args);
 
 /* ---------------------------------------------------------------------------------------------
  * Image pyramid — replaces generate_img_pyramid: model_flow.py:58-64 (mode 0: adaptive average

@@ -182,7 +182,7 @@ static int emu_flow_split(FlowGradParams& gp, int step) {
         for (int k = 0; k < ROW; ++k) S[k] = (float)psum[((size_t)b * p.scales + l) * ROW + k];
         const FlowCombineScales k = flow_combine_scales(S, p.lv[l].h, p.lv[l].w, p.gloss, p.B, b);
         float* o = scales_buf.data() + ((size_t)b * p.scales + l) * 8;
-        o[0] = k.pix[0]; o[1] = k.pix[1]; o[2] = k.ssim[0]; o[3] = k.ssim[1]; o[4] = k.sm; o[5] = k.cons;
+        o[0] = k.pix[0]; o[1] = k.pix[1]; o[2] = k.pix[0]; o[3] = k.pix[1]; o[4] = k.ssim[0]; o[5] = k.ssim[1]; o[6] = k.sm; o[7] = k.cons;
       }
   }
   // stencil tiles
@@ -211,9 +211,7 @@ static int emu_flow_split(FlowGradParams& gp, int step) {
     Tile::phase4a(gp, tc, 0, 1, sm.data(), acc);
     if (step) {
       const float* o = scales_buf.data() + ((size_t)tc.b * p.scales + tc.level) * 8;
-      FlowCombineScales k;
-      k.pix[0] = o[0]; k.pix[1] = o[1]; k.ssim[0] = o[2]; k.ssim[1] = o[3]; k.sm = o[4]; k.cons = o[5];
-      Tile::phase4b_step(gp, tc, k, 0, 1, sm.data(), g3, pre);
+      Tile::phase4b_step(gp, tc, o, 0, 1, sm.data(), g3, pre);
     } else {
       Tile::phase4b(gp, tc, 0, 1, sm.data());
     }

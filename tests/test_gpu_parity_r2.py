@@ -530,3 +530,34 @@ def test_mode_steps_side_streams_same_bits(cuda_device):
         mode_steps._Side.enabled = saved
     for a, b in zip(res[True][0] + res[True][1], res[False][0] + res[False][1]):
         assert torch.equal(a, b)
+
+
+def test_geom_step_weights_form_equals_autograd_form(cuda_device):
+    """GeometryLoss.forward_losses(step_weights=w): the flow branch runs as a fused training step (ugl_geom_flow_step: gradients written by
+    the forward launches, no basis planes, no combine).  Same losses and masks bit for bit, same gradients up to the association of the
+    four-term sum; the weighted total must then be formed with the same weights."""
+    t = make_triplet(2, 112, 208, 4, 3, seed=101, flow_mode="rigid").to(cuda_device)
+    mod = losses.GeometryLoss(3)
+    res = {}
+    for step in (False, True):
+        ff, fb = _leaf_list(t.flows_fwd, cuda_device), _leaf_list(t.flows_bwd, cuda_device)
+        disp, disp_l, disp_r = _leaf_list(t.disp, cuda_device), _leaf_list(t.disp_l, cuda_device), _leaf_list(t.disp_r, cuda_device)
+        pose = t.pose.detach().clone().requires_grad_(True)
+        loss, masks = mod.forward_losses(t.img_l, t.img, t.img_r, ff, fb, disp, disp_l, disp_r, pose, t.K, t.K_inv,
+                                         step_weights=P.GEOM_WEIGHTS if step else None)
+        total = losses.total_loss(loss, P.GEOM_WEIGHTS)
+        g = torch.autograd.grad(total, ff[:3] + fb[:3] + disp + disp_l + disp_r + [pose])
+        res[step] = (loss, masks, total, g)
+        if step:
+            other = dict(P.GEOM_WEIGHTS); other["loss_flow_ssim"] = 0.5
+            with pytest.raises(ValueError):
+                losses.total_loss(loss, other)
+    a, b = res[True], res[False]
+    for k in b[0]:
+        assert torch.equal(a[0][k].detach(), b[0][k].detach()), k
+    for key in ("occ_b", "occ_f", "valid_b", "valid_f", "dyn_b", "dyn_f", "tex_b", "tex_f"):
+        for l in range(3):
+            assert torch.equal(a[1][key][l], b[1][key][l]), (key, l)
+    assert torch.equal(a[2].detach(), b[2].detach())
+    for x, y in zip(a[3], b[3]):
+        assert torch.isfinite(x).all() and rel_err(x, y) < 2e-6

@@ -420,16 +420,20 @@ extern "C" int ugl_flow_loss_step_parts(const UglFlowLossArgs* a, int parts) {
 }
 
 // ---- geom mode (Model_geometry's flow branch) -----------------------------------------------------
-static int geom_params(const UglGeomFlowArgs* g, bool backward, FlowGradParams& gp) {
+// step = true: the fused training step (forward inputs AND gradient outputs, no basis planes)
+static int geom_params(const UglGeomFlowArgs* g, bool backward, FlowGradParams& gp, bool step = false) {
   if (!g) return fail(UGL_EINVAL, "geom_flow: null args");
   const UglFlowLossArgs* a = &g->flow;
-  int rc = build_params<kBTW, kBTH>(a, backward, gp.base);
+  int rc = build_params<kBTW, kBTH>(a, backward || step, gp.base);
   if (rc) return rc;
   for (int l = 0; l < a->scales; ++l) {
-    if (!a->basis[l] || !g->mask_bytes[l]) return fail(UGL_EINVAL, "geom_flow: null basis / mask_bytes pointer at level %d", l);
-    if (reinterpret_cast<uintptr_t>(a->basis[l]) & 7u) return fail(UGL_EALIGN, "geom_flow: basis not 8-byte aligned");
-    gp.basis[l] = a->basis[l];
+    if (!g->mask_bytes[l]) return fail(UGL_EINVAL, "geom_flow: null mask_bytes pointer at level %d", l);
     gp.mask_bytes[l] = g->mask_bytes[l];
+    if (!step) {
+      if (!a->basis[l]) return fail(UGL_EINVAL, "geom_flow: null basis pointer at level %d", l);
+      if (reinterpret_cast<uintptr_t>(a->basis[l]) & 7u) return fail(UGL_EALIGN, "geom_flow: basis not 8-byte aligned");
+      gp.basis[l] = a->basis[l];
+    }
     if (!backward) {
       const void* ptrs[4] = {g->disp[l], g->Kinv[l], g->P_bwd[l], g->P_fwd[l]};
       for (int k = 0; k < 4; ++k) {
@@ -469,6 +473,28 @@ extern "C" int ugl_geom_flow_forward_grad_ex(const UglGeomFlowArgs* g, int varia
 }
 
 extern "C" int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* g) { return ugl_geom_flow_forward_grad_ex(g, UGL_SINGLE_PASS_SPLIT); }
+
+// fused forward + backward of the geom-mode flow branch for a known upstream gradient (ugl_flow_loss_step's counterpart): losses,
+// packed mask bytes AND grad_flow_fwd/bwd in four chained launches, no basis planes, no combine launch
+extern "C" int ugl_geom_flow_step(const UglGeomFlowArgs* g) {
+  FlowGradParams gp;
+  int rc = geom_params(g, false, gp, true);
+  if (rc) return rc;
+  const UglFlowLossArgs* a = &g->flow;
+  if (!a->loss || !a->grad_loss) return fail(UGL_EINVAL, "geom_flow_step: null loss / grad_loss");
+  if (!a->workspace || a->workspace_bytes < ugl_flow_loss_workspace_bytes(a))
+    return fail(UGL_EWORKSPACE, "geom_flow_step: workspace too small (%llu bytes given)", (unsigned long long)a->workspace_bytes);
+  for (int l = 0; l < a->scales; ++l)
+    if ((reinterpret_cast<uintptr_t>(a->grad_flow_fwd[l]) | reinterpret_cast<uintptr_t>(a->grad_flow_bwd[l])) & 7u)
+      return fail(UGL_EALIGN, "geom_flow_step: grad_flow not 8-byte aligned at level %d", l);
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  gp.step = 1;
+  char* pp = split_photo_partials(a);
+  flow_split_assign_scratch(gp, pp + flow_split_photo_partials_bytes(a->height, a->width, a->scales, a->batch));
+  if ((rc = finalize_reset_tickets<kModeGeom>(gp.base, st))) return rc;
+  if ((rc = launch_flow_split<true>(gp, pp, st, 1))) return rc;
+  return launch_finalize<kModeGeom>(gp.base, st, &gp.photo, true);
+}
 
 extern "C" int ugl_geom_flow_combine(const UglGeomFlowArgs* g) {
   FlowGradParams gp;

@@ -121,13 +121,19 @@ __global__ void __launch_bounds__(256) flow_photo_norm_kernel(const __grid_const
     for (int w = 0; w < 256 / 32; ++w) v += red[w][threadIdx.x];
     gp.base.stats[((long)b * gp.base.scales + l) * ROW + Px::column(threadIdx.x)] = (float)v;
   }
-  if (!kGeom && gp.step_scales) {   // the closing divisions once per (sample, level) instead of once per stencil thread
+  if (gp.step_scales) {   // the closing divisions once per (sample, level) instead of once per stencil thread; layout: FlowStencilTile::phase4b_step
     __syncthreads();
     if (threadIdx.x == 0) {
       const FlowLevelDesc& L = gp.base.lv[l];
-      const FlowCombineScales k = flow_combine_scales(gp.base.stats + ((long)b * gp.base.scales + l) * FA_COUNT, L.h, L.w, gp.base.gloss, gp.base.B, b);
+      const float* S = gp.base.stats + ((long)b * gp.base.scales + l) * ROW;
       float* o = gp.step_scales + ((long)b * gp.base.scales + l) * 8;
-      o[0] = k.pix[0]; o[1] = k.pix[1]; o[2] = k.ssim[0]; o[3] = k.ssim[1]; o[4] = k.sm; o[5] = k.cons; o[6] = 0.f; o[7] = 0.f;
+      if (kGeom) {
+        const GeomCombineScales k = geom_combine_scales(S, L.h, L.w, gp.base.gloss, gp.base.B, b);
+        o[0] = k.pix_r[0]; o[1] = k.pix_r[1]; o[2] = k.pix_d[0]; o[3] = k.pix_d[1]; o[4] = k.ssim[0]; o[5] = k.ssim[1]; o[6] = k.sm; o[7] = k.cons;
+      } else {
+        const FlowCombineScales k = flow_combine_scales(S, L.h, L.w, gp.base.gloss, gp.base.B, b);
+        o[0] = k.pix[0]; o[1] = k.pix[1]; o[2] = k.pix[0]; o[3] = k.pix[1]; o[4] = k.ssim[0]; o[5] = k.ssim[1]; o[6] = k.sm; o[7] = k.cons;
+      }
     }
   }
 }
@@ -135,7 +141,6 @@ __global__ void __launch_bounds__(256) flow_photo_norm_kernel(const __grid_const
 template <int TW, int TH, int NT, bool kGeom, bool kStep>
 __global__ void __launch_bounds__(NT, kStencilMinBlocks)
 flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_constant__ FlowTmaMaps tm) {
-  static_assert(!(kStep && kGeom), "the fused step exists for the flow mode only");
   using Tile = FlowStencilTile<TW, TH, NT, kGeom>;
   constexpr int NA = Tile::kAcc;
   constexpr int ROW = kGeom ? (int)GA_COUNT : (int)FA_COUNT;
@@ -242,8 +247,7 @@ flow_stencil_kernel(const __grid_constant__ FlowGradParams gp, const __grid_cons
     griddep_wait();                  // the weight-sum kernel is complete: scale factors final
     const float4* ks = reinterpret_cast<const float4*>(gp.step_scales + ((long)tc.b * gp.base.scales + tc.level) * 8);
     const float4 k0 = __ldcg(ks), k1 = __ldcg(ks + 1);
-    FlowCombineScales k;
-    k.pix[0] = k0.x; k.pix[1] = k0.y; k.ssim[0] = k0.z; k.ssim[1] = k0.w; k.sm = k1.x; k.cons = k1.y;
+    const float k[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
     Tile::phase4b_step(gp, tc, k, tid, NT, sm, g3, pre);
   } else {
     Tile::phase4b(gp, tc, tid, NT, sm);
@@ -375,8 +379,7 @@ int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st,
     return fail(UGL_EUNSUPPORTED, "flow_loss: TMA staging requested but only %d of %d levels allow it (width %% 4, 16-byte alignment, driver entry point)",
                 n_tma, gp.base.scales);
   if (gp.step) {
-    if (kGeom) return fail(UGL_EUNSUPPORTED, "flow_loss_step: flow mode only");
-    auto kern = flow_stencil_kernel<TW, TH, NT, false, true>;
+    auto kern = flow_stencil_kernel<TW, TH, NT, kGeom, true>;
     if ((rc = opt_in_smem(kern, smem))) return rc;
     return launch_kernel("flow_stencil_kernel", kern, grid, dim3(NT), smem, st, chain, gp, tm);
   }

@@ -503,7 +503,9 @@ struct FlowStencilTile {
     }
   }
 
-  static UGL_HD void phase4b_step(const FlowGradParams& gp, const TileCoord& tc, const FlowCombineScales& k, int tid, int nt, const float* sm,
+  // ks[8]: scale factors of this (sample, level): L1 fwd / bwd (geom mode: rigid pixels), L1 fwd / bwd of the dynamic pixels (geom mode; flow
+  // mode: the same two again), SSIM fwd / bwd, smoothness, consistency -- FlowCombineScales / GeomCombineScales as written by the weight-sum kernel
+  static UGL_HD void phase4b_step(const FlowGradParams& gp, const TileCoord& tc, const float* ks, int tid, int nt, const float* sm,
                                   const float2 (*g)[4], const float4 (*pre)[3]) {
     const FlowLevelDesc& L = gp.base.lv[tc.level];
     const long plane = (long)L.h * L.w;
@@ -534,10 +536,16 @@ struct FlowStencilTile {
         const float2 gpu = o == 0 ? lo2(pre[n][0]) : hi2(pre[n][0]), gpv = o == 0 ? lo2(pre[n][1]) : hi2(pre[n][1]);
         const float2 gc = o == 0 ? lo2(pre[n][2]) : hi2(pre[n][2]);
         const float2 gsu = g[n][o], gsv = g[n][2 + o];
-        o_fu[o] = k.pix[0] * gpu.x + k.ssim[0] * gsu.x + k.sm * gm[0].x + k.cons * gc.x;
-        o_fv[o] = k.pix[0] * gpv.x + k.ssim[0] * gsv.x + k.sm * gm[0].y + k.cons * gc.y;
-        o_bu[o] = k.pix[1] * gpu.y + k.ssim[1] * gsu.y + k.sm * gm[1].x;
-        o_bv[o] = k.pix[1] * gpv.y + k.ssim[1] * gsv.y + k.sm * gm[1].y;
+        float kpf = ks[0], kpb = ks[1];
+        if (kGeom && (o == 0 || j + 1 < L.w)) {              // L1 weight 1 on rigid pixels, 2 on dynamic ones (model_geometry.py:857-876)
+          const unsigned bits = gp.mask_bytes[tc.level][(long)tc.b * plane + (long)i * L.w + j + o];
+          kpf = (bits & kMaskDynF) ? ks[0] : ks[2];
+          kpb = (bits & kMaskDynB) ? ks[1] : ks[3];
+        }
+        o_fu[o] = kpf * gpu.x + ks[4] * gsu.x + ks[6] * gm[0].x + ks[7] * gc.x;
+        o_fv[o] = kpf * gpv.x + ks[4] * gsv.x + ks[6] * gm[0].y + ks[7] * gc.y;
+        o_bu[o] = kpb * gpu.y + ks[5] * gsu.y + ks[6] * gm[1].x;
+        o_bv[o] = kpb * gpv.y + ks[5] * gsv.y + ks[6] * gm[1].y;
       }
       const long pix = (long)i * L.w + j;
       if (vec) {

@@ -384,19 +384,21 @@ class GeometryLoss(_LossBase):
         return loss, GeomMasks(mbytes, dict(tex_b=tex_b, tex_f=tex_f, val_l=val_l, val_r=val_r), self, (flows_bwd[0], flows_fwd[0], Fm))
 
     def forward_losses(self, img_l, img, img_r, optical_flows_fwd, optical_flows_bwd, disp_list, disp_l_list, disp_r_list,
-                       pose_vectors, K, K_inv, fused=True) -> Tuple[Dict[str, Tensor], Dict]:
+                       pose_vectors, K, K_inv, fused=True, step_weights: Optional[Dict[str, float]] = None) -> Tuple[Dict[str, Tensor], Dict]:
         """Loss body of ``Model_geometry.forward`` (model_geometry.py:777-951) given the network outputs.
         The second return value holds the device-side masks (the reference's ``mask_pack`` without its
-        unconditional D2H copies, :871-880)."""
+        unconditional D2H copies, :871-880).  ``step_weights`` (``fused=True`` only): the loss weights of ``train.py:211-215`` declared
+        up front -- the flow branch then evaluates its gradients in its forward launches (``mode_steps.geom_step``); ``total_loss``
+        must be taken with the same weights."""
         S = self.num_scales
         pose_fwd, pose_bwd = pose_vectors[:, 1, :], pose_vectors[:, 0, :]
         if fused is True:
             from . import mode_steps
             mat, mbytes, (val_l, val_r), (tex_b, tex_f), Fm = mode_steps.geom_step(
                 S, self.flow_consist_alpha, self.flow_consist_beta, img_l, img, img_r, list(optical_flows_fwd), list(optical_flows_bwd),
-                disp_list, disp_l_list, disp_r_list, pose_vectors, K, K_inv)
+                disp_list, disp_l_list, disp_r_list, pose_vectors, K, K_inv, step_weights=step_weights)
             ph = {k: _zeros2(img) for k in ("loss_depth_ssim", "loss_depth_consis", "loss_triangle", "loss_pnp", "loss_eight_point")}
-            return (mode_steps.LossPack(mat, mode_steps.GEOM_KEYS, ph),
+            return (mode_steps.LossPack(mat, mode_steps.GEOM_KEYS, ph, step_weights),
                     GeomMasks(mbytes, dict(tex_b=tex_b, tex_f=tex_f, val_l=val_l, val_r=val_r), self,
                               (optical_flows_bwd[0], optical_flows_fwd[0], list(Fm))))
         if fused:

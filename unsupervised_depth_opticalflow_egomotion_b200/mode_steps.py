@@ -38,9 +38,12 @@ class _Ctx:
         pass
 
 
-def _run(fn, args, grad_from: int, need: bool):
-    """``fn.forward`` with a stand-in ctx: inputs from position ``grad_from`` on count as requiring grad iff ``need``."""
+def _run(fn, args, grad_from: int, need: bool, **ctx_attrs):
+    """``fn.forward`` with a stand-in ctx: inputs from position ``grad_from`` on count as requiring grad iff ``need``; ``ctx_attrs`` are
+    set on the ctx before the call (``step_gloss``: the training-step form of ``ops._GeomFlowLossFn``)."""
     ctx = _Ctx([False] * grad_from + [need] * (len(args) - grad_from))
+    for k, v in ctx_attrs.items():
+        setattr(ctx, k, v)
     with torch.no_grad():
         out = fn.forward(ctx, *args)
     return ctx, out
@@ -157,14 +160,19 @@ class LossPack(dict):
     constant ``zeros([2])`` placeholders.  ``losses.total_loss`` recognises it and evaluates ``sum_k w_k mean(loss_k)`` on the
     matrix in one launch."""
 
-    def __init__(self, matrix: Tensor, keys: Sequence[str], placeholders: Dict[str, Tensor]):
+    def __init__(self, matrix: Tensor, keys: Sequence[str], placeholders: Dict[str, Tensor], step_weights: Optional[Dict[str, float]] = None):
         super().__init__({k: matrix[i] for i, k in enumerate(keys)})
         self.update(placeholders)
         self.matrix, self.keys_live = matrix, tuple(keys)
+        # training-step form: part of the backward was evaluated in the forward for these weights; total() must be called with the same
+        self.step_weights = None if step_weights is None else {k: float(step_weights[k]) for k in keys}
 
     _wcache: Dict[tuple, Tensor] = {}
 
     def total(self, weights: Dict[str, float]) -> Tensor:
+        if self.step_weights is not None and any(float(weights[k]) != w for k, w in self.step_weights.items()):
+            raise ValueError("LossPack.total: this pack was produced with step_weights=%r; the weighted total must use the same weights"
+                             % (self.step_weights,))
         key = (self.keys_live, tuple(float(weights[k]) for k in self.keys_live), str(self.matrix.device))
         w = LossPack._wcache.get(key)
         if w is None:       # built once per (keys, weights, device): no host-to-device copy inside a captured step
@@ -176,19 +184,31 @@ GEOM_KEYS = ("loss_depth_pixel", "loss_depth_smooth", "loss_flow_pixel", "loss_f
              "loss_depth_flow_consis", "loss_epipolar")
 
 
+def step_grad_matrix(keys: Sequence[str], weights: Dict[str, float], B: int, device) -> Tensor:
+    """(K,B) upstream gradient of ``sum_k w_k mean_b loss_k[b]`` (train.py:211-215): rows ``fl(w_k / B)``, what ``_WeightedTotalFn.backward``
+    produces for an upstream gradient of 1.  Built once per (keys, weights, B, device)."""
+    key = ("step", tuple(keys), tuple(float(weights[k]) for k in keys), int(B), str(device))
+    m = LossPack._wcache.get(key)
+    if m is None:
+        w = torch.tensor(key[2], dtype=torch.float32)
+        m = LossPack._wcache[key] = (w / float(B)).view(-1, 1).repeat(1, B).contiguous().to(device)
+    return m
+
+
 class _GeomStepFn(torch.autograd.Function):
-    """inputs: S, L, alpha, beta, then img_l, img, img_r, ff[L], fb[L], disp[S], disp_l[S], disp_r[S], pose, K, K_inv.
+    """inputs: S, L, alpha, beta, step_gmat ((8,B) upstream gradient known in advance, or None), then img_l, img, img_r, ff[L], fb[L],
+    disp[S], disp_l[S], disp_r[S], pose, K, K_inv.
     outputs: loss matrix (8,B) in GEOM_KEYS order; then (non-differentiable) mask bytes[S], val_l[S], val_r[S], tex_b[S], tex_f[S],
     F_bwd, F_fwd."""
 
     @staticmethod
-    def forward(ctx, S: int, L: int, alpha: float, beta: float, *ts: Tensor):
+    def forward(ctx, S: int, L: int, alpha: float, beta: float, step_gmat: Optional[Tensor], *ts: Tensor):
         img_l, img, img_r = ts[0:3]
         ff, fb = list(ts[3:3 + L]), list(ts[3 + L:3 + 2 * L])
         o = 3 + 2 * L
         disp, disp_l, disp_r = list(ts[o:o + S]), list(ts[o + S:o + 2 * S]), list(ts[o + 2 * S:o + 3 * S])
         pose, K, K_inv = ts[o + 3 * S:o + 3 * S + 3]
-        needs = ctx.needs_input_grad[4:]
+        needs = ctx.needs_input_grad[5:]
         need_flow, need_disp = any(needs[3:3 + 2 * L]), any(needs[o:o + 3 * S])
         need_pose = needs[o + 3 * S]
         need_any = need_flow or need_disp or need_pose
@@ -203,8 +223,10 @@ class _GeomStepFn(torch.autograd.Function):
         _Side.join(1)
         pc, pl, pr = (d["bilinear"] for d in pyr)
         area = (pyr[1]["area"], pyr[2]["area"])
+        # training-step form: the flow branch's gradients come out of its forward launches (rows 2..5 of the upstream gradient)
+        step = {} if step_gmat is None or not need_flow else {"step_gloss": step_gmat[2:6]}
         c_flow, out = _run(ops._GeomFlowLossFn, (S, S, float(alpha), float(beta), *pl[:S], *pc[:S], *pr[:S], *ff[:S], *fb[:S], *disp, *Kinv,
-                                                  *P_b, *P_f), 4 + 3 * S, need_flow)
+                                                  *P_b, *P_f), 4 + 3 * S, need_flow, **step)
         flow4, mbytes = out[0], list(out[1:])
         with _Side(1):      # the level-0 rigid terms and the reprojection term both start from the flow branch's mask bytes
             c_rigid, out_r = _run(ops._GeomRigidFn, (fb[0], ff[0], disp[0], mbytes[0], Kinv[0], P_b[0], P_f[0], Fm[0], Fm[1],
@@ -229,7 +251,7 @@ class _GeomStepFn(torch.autograd.Function):
         S, L = ctx.S, ctx.L
         n_in = 3 + 2 * L + 3 * S + 3
         if gmat is None:
-            return (None,) * (4 + n_in)
+            return (None,) * (5 + n_in)
         c_pose, c_flow, c_photo, c_rigid, c_smooth = ctx.sub
         need_flow, need_disp, need_pose = ctx.flags
         gmat = gmat.contiguous()
@@ -258,13 +280,18 @@ class _GeomStepFn(torch.autograd.Function):
             gf, gb = [None] * S, [None] * S
         if not need_disp:
             gdisp, gsm_l, gsm_r = [None] * S, [None] * S, [None] * S
-        return (None, None, None, None, None, None, None, *gf, *pad, *gb, *pad, *gdisp, *gsm_l, *gsm_r, gpose, None, None)
+        return (None, None, None, None, None, None, None, None, *gf, *pad, *gb, *pad, *gdisp, *gsm_l, *gsm_r, gpose, None, None)
 
 
-def geom_step(S: int, alpha: float, beta: float, img_l, img, img_r, flows_fwd, flows_bwd, disp, disp_l, disp_r, pose, K, K_inv):
-    """-> (LossPack-ready (8,B) matrix, mask bytes[S], (val_l, val_r), (tex_b, tex_f), (F_bwd, F_fwd))"""
+def geom_step(S: int, alpha: float, beta: float, img_l, img, img_r, flows_fwd, flows_bwd, disp, disp_l, disp_r, pose, K, K_inv,
+              step_weights: Optional[Dict[str, float]] = None):
+    """-> (LossPack-ready (8,B) matrix, mask bytes[S], (val_l, val_r), (tex_b, tex_f), (F_bwd, F_fwd)).
+    ``step_weights``: the weights of the weighted total that will be taken of these losses (train.py:211-215), declared up front: the flow
+    branch then runs as a fused training step (``ugl_geom_flow_step``: no basis planes, no combine launch).  The caller must form the total
+    with the same weights (``LossPack.total`` checks) and back-propagate an upstream gradient of 1."""
     L = len(flows_fwd)
-    out = _GeomStepFn.apply(S, L, float(alpha), float(beta), img_l, img, img_r, *flows_fwd, *flows_bwd, *disp[:S], *disp_l[:S], *disp_r[:S],
+    gmat = None if step_weights is None else step_grad_matrix(GEOM_KEYS, step_weights, img.shape[0], img.device)
+    out = _GeomStepFn.apply(S, L, float(alpha), float(beta), gmat, img_l, img, img_r, *flows_fwd, *flows_bwd, *disp[:S], *disp_l[:S], *disp_r[:S],
                             pose, K, K_inv)
     mat, rest = out[0], out[1:]
     mbytes = list(rest[0:S])

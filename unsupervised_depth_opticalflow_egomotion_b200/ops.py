@@ -401,8 +401,29 @@ class _GeomFlowLossFn(torch.autograd.Function):
                     raise ValueError("geom_flow_loss: %s[%d] has shape %s, expected %s" % (name, l, tuple(t.shape), shp))
         loss = torch.empty((4, B), device=dev, dtype=torch.float32)
         stats = torch.empty((B, S, _cabi.GEOM_NSTATS), device=dev, dtype=torch.float32)
-        basis = _alloc_basis(ff, S)
         masks = [torch.empty((B,) + tuple(img[l].shape[2:]), device=dev, dtype=torch.uint8) for l in range(S)]
+        # Training-step form (mode_steps sets ``ctx.step_gloss``: the upstream gradient d total / d loss_k[b] = w_k / B is known before
+        # the forward runs, train.py:211-215): ugl_geom_flow_step writes the flow gradients in the forward launch sequence -- no basis
+        # planes, no combine launch; backward hands them out.
+        step_gloss = getattr(ctx, "step_gloss", None)
+        ctx.step_grads = None
+        if step_gloss is not None:
+            gl = _dev(step_gloss, "step grad_loss")
+            if tuple(gl.shape) != (4, B):
+                raise ValueError("geom_flow_loss: step grad_loss must be (4,%d), got %s" % (B, tuple(gl.shape)))
+            gf = [torch.empty_like(ff[l]) for l in range(S)]
+            gb = [torch.empty_like(fb[l]) for l in range(S)]
+            g = _geom_args(S, L, img_l, img, img_r, ff, fb, disp, Kinv, P_b, P_f, masks, alpha, beta, loss, stats, None, None, gl, gf, gb)
+            ws = torch.empty(max(int(_cabi.lib().ugl_flow_loss_workspace_bytes(C.byref(g.flow))) // 4, 1), device=dev, dtype=torch.float32)
+            g.flow.workspace, g.flow.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+            with torch.cuda.device_of(img[0]):
+                _call("ugl_geom_flow_step", C.byref(g), launches=4)
+            ctx.step_grads = (gf, gb)
+            ctx.S, ctx.L, ctx.ab = S, L, (alpha, beta)
+            ctx.mark_non_differentiable(*masks)
+            ctx.set_materialize_grads(False)
+            return (loss, *masks)
+        basis = _alloc_basis(ff, S)
         g = _geom_args(S, L, img_l, img, img_r, ff, fb, disp, Kinv, P_b, P_f, masks, alpha, beta, loss, stats, None, basis)
         ws = torch.empty(max(int(_cabi.lib().ugl_flow_loss_workspace_bytes(C.byref(g.flow))) // 4, 1), device=dev, dtype=torch.float32)
         g.flow.workspace, g.flow.workspace_bytes = ws.data_ptr(), ws.numel() * 4
@@ -416,11 +437,15 @@ class _GeomFlowLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gloss, *unused):
-        stats, *rest = ctx.saved_tensors
         S, L = ctx.S, ctx.L
         n_in = 5 * L + 4 * S
         if gloss is None:
             return (None,) * (4 + n_in)
+        if getattr(ctx, "step_grads", None) is not None:      # training-step form: computed by the forward launches for ctx.step_gloss
+            gf, gb = ctx.step_grads
+            none_l, pad, none_s = [None] * L, [None] * (L - S), [None] * S
+            return (None, None, None, None, *none_l, *none_l, *none_l, *gf, *pad, *gb, *pad, *none_s, *none_s, *none_s, *none_s)
+        stats, *rest = ctx.saved_tensors
         ts, basis, masks = rest[:n_in], rest[n_in:n_in + S], rest[n_in + S:]
         img_l, img, img_r, ff, fb = (ts[k * L:(k + 1) * L] for k in range(5))
         disp, Kinv, P_b, P_f = (ts[5 * L + k * S:5 * L + (k + 1) * S] for k in range(4))
