@@ -532,11 +532,12 @@ def test_mode_steps_side_streams_same_bits(cuda_device):
         assert torch.equal(a, b)
 
 
-def test_geom_step_weights_form_equals_autograd_form(cuda_device):
+@pytest.mark.parametrize("B,H,W", [(2, 112, 208), (1, 76, 116)])     # second size: level 1 without TMA (width % 4 != 0), odd width at level 2
+def test_geom_step_weights_form_equals_autograd_form(cuda_device, B, H, W):
     """GeometryLoss.forward_losses(step_weights=w): the flow branch runs as a fused training step (ugl_geom_flow_step: gradients written by
     the forward launches, no basis planes, no combine).  Same losses and masks bit for bit, same gradients up to the association of the
     four-term sum; the weighted total must then be formed with the same weights."""
-    t = make_triplet(2, 112, 208, 4, 3, seed=101, flow_mode="rigid").to(cuda_device)
+    t = make_triplet(B, H, W, 4, 3, seed=101, flow_mode="rigid").to(cuda_device)
     mod = losses.GeometryLoss(3)
     res = {}
     for step in (False, True):
