@@ -265,7 +265,7 @@ struct FlowGradParams {
   FlowLossParams base;
   float one = 1.0f;           // an opaque 1.0 for acc2_rn (ugl_common.cuh): keeps ptxas from contracting packed products into their sums
   float* basis[kMaxLevels];   // (B, 14, h, w) per level
-  float* scratch[kMaxLevels]; // split kernels (ugl_flow_split.cuh): (B, 10, h, w, 2) photometry pair planes per level
+  float* scratch[kMaxLevels]; // split kernels (ugl_flow_split.cuh): (B, kPhotoPairs = 15, h, w, 2) photometry pair planes per level
   // split kernels: the photometry kernel has its own tile grid (PhotoTiling) and its own partial-sum rows
   struct PhotoTiling {
     int tiles_x[kMaxLevels], tile_begin[kMaxLevels];   // tiles per row; first tile id of the level (ids ordered level, sample, ty, tx)

@@ -40,7 +40,7 @@ constexpr int kPatchW = UGL_PATCH_W, kPatchH = 32 / UGL_PATCH_W;  // pixels a wa
 #if defined(CUDA_VERSION) || defined(__cuda_cuda_h__)
 // tensor maps of the stencil kernel's TMA copies, one set per level (kernel parameter, __grid_constant__)
 struct FlowTmaMaps {
-  CUtensorMap scr_halo[kMaxLevels];   // photometry pair planes (2w, h, 10 B), box = tile + 2-pixel halo
+  CUtensorMap scr_halo[kMaxLevels];   // photometry pair planes (2w, h, kPhotoPairs B), box = tile + 2-pixel halo
   CUtensorMap scr_tile[kMaxLevels];   // same tensor, box = tile
   CUtensorMap img[kMaxLevels];        // centre frame (w, h, 3 B), halo box
   CUtensorMap flow_f[kMaxLevels];     // (w, h, 2 B), halo box
