@@ -365,11 +365,26 @@ __global__ void __launch_bounds__(kRedThreads, 3) depth_ssim_combine_kernel(cons
   float acc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.f;
-  for (long px = blockIdx.x * (long)kRedThreads + threadIdx.x; px < plane; px += (long)gridDim.x * kRedThreads) {
+  // contiguous chunk per CTA, the five coalesced loads of the next iteration in flight under the current one (as the forward kernels)
+  struct Direct { float b0, b1, b2, b3, D; };
+  auto direct = [&](long q) {
+    Direct d;
+    d.b0 = __ldcs(bs + q); d.b1 = __ldcs(bs + plane + q); d.b2 = __ldcs(bs + 2 * plane + q); d.b3 = __ldcs(bs + 3 * plane + q);
+    d.D = L.disp[(long)b * plane + q];
+    return d;
+  };
+  const ChunkRange cr = chunk_range(plane);
+  long px = cr.begin + threadIdx.x;
+  Direct nxt = {};
+  if (px < cr.end) nxt = direct(px);
+#pragma unroll 1
+  for (; px < cr.end; px += kRedThreads) {
+    const Direct cur = nxt;
+    if (px + kRedThreads < cr.end) nxt = direct(px + kRedThreads);
     const int i = (int)(px / L.w), j = (int)(px % L.w);
-    const float gu = k_pix * __ldcs(bs + px) + k_ssim * __ldcs(bs + 2 * plane + px);
-    const float gv = k_pix * __ldcs(bs + plane + px) + k_ssim * __ldcs(bs + 3 * plane + px);
-    const Projected r = project_pixel(sK, sP, L.disp[(long)b * plane + px], j, i);
+    const float gu = k_pix * cur.b0 + k_ssim * cur.b2;
+    const float gv = k_pix * cur.b1 + k_ssim * cur.b3;
+    const Projected r = project_pixel(sK, sP, cur.D, j, i);
     const float gD = project_backward(r, sP, gu, gv, 0.f, acc);
     atomicAdd(&L.grad_disp[(long)b * plane + px], gD);
   }
