@@ -329,7 +329,10 @@ class _DepthStepFn(torch.autograd.Function):
         area = (pyr[1]["area"], pyr[2]["area"])
         flat = (*pc[:S], *area[0][:S], *area[1][:S], *pl[:S], *pr[:S], *disp, *Kinv, *P_b, *P_f)
         B = img.shape[0]
-        c_consis, rows = None, []
+        c_consis, cons, rows = None, None, []
+        if variant == "texture":      # the depth-consistency term only needs the disparities and the matrices: its own branch
+            with _Side(1):
+                c_consis, cons = _run(ops._DepthConsisFn, (S, *disp, *disp_l, *disp_r, *Kinv, *P_b, *P_f), 1, need_disp or need_pose)
         if variant == "live":
             c_photo, out = _run(ops._DepthPhotoFn, (S, 0, (0, 0), *flat), 3, need_disp or need_pose)
             rows.append((out[0], 1))
@@ -339,7 +342,6 @@ class _DepthStepFn(torch.autograd.Function):
         masks = out[1:]
         rows.append((sm3, 3))
         if variant == "texture":
-            c_consis, cons = _run(ops._DepthConsisFn, (S, *disp, *disp_l, *disp_r, *Kinv, *P_b, *P_f), 1, need_disp or need_pose)
             rows.append((cons, 1))
         _Side.join()
         mat = _assemble(rows, B, img.device)
@@ -362,6 +364,10 @@ class _DepthStepFn(torch.autograd.Function):
         with torch.no_grad():
             with _Side(0):
                 gsm = ops._DispSmoothMultiFn.backward(c_smooth, gmat[keys.index("loss_depth_smooth")])
+            g_c = None
+            if c_consis is not None:
+                with _Side(1):
+                    g_c = ops._DepthConsisFn.backward(c_consis, gmat[3].contiguous())
             if variant == "live":
                 g_photo = ops._DepthPhotoFn.backward(c_photo, gmat[0].contiguous())
                 base = 3
@@ -373,8 +379,7 @@ class _DepthStepFn(torch.autograd.Function):
             gsm_c, gsm_l, gsm_r = list(gsm[5:5 + S]), list(gsm[5 + S:5 + 2 * S]), list(gsm[5 + 2 * S:5 + 3 * S])
             pairs = [(gdisp[l], gsm_c[l]) for l in range(S)]
             _Side.join()
-            if c_consis is not None:
-                g_c = ops._DepthConsisFn.backward(c_consis, gmat[3].contiguous())
+            if g_c is not None:
                 # (None, gdisp[S], gref_l[S], gref_r[S], None[S], gP_b[S], gP_f[S])
                 pairs += [(gdisp[l], g_c[1 + l]) for l in range(S)]
                 pairs += [(gsm_l[l], g_c[1 + S + l]) for l in range(S)] + [(gsm_r[l], g_c[1 + 2 * S + l]) for l in range(S)]
