@@ -145,6 +145,10 @@ int ugl_geom_flow_combine(const UglGeomFlowArgs* args);
  * d total / d loss_k[b] = w_k / B known before the forward runs): flow.loss (4,B), mask_bytes AND flow.grad_flow_fwd/bwd[l] in four
  * chained launches; flow.basis is ignored, no combine launch.  Same results as ugl_geom_flow_forward_grad + ugl_geom_flow_combine. */
 int ugl_geom_flow_step(const UglGeomFlowArgs* args);
+/* The same step in two calls: parts = UGL_STEP_PHOTO (photometry kernel: mask_bytes are final when it completes), then
+ * parts = UGL_STEP_ALL & ~UGL_STEP_PHOTO (weight sums, stencil kernel, finalize).  Lets the caller start the consumers of the mask bytes
+ * (ugl_depth_photo_*, ugl_geom_rigid_*) on other streams while the stencil kernel runs.  Same results as ugl_geom_flow_step. */
+int ugl_geom_flow_step_parts(const UglGeomFlowArgs* args, int32_t parts);
 
 /* ---------------------------------------------------------------------------------------------
  * Image pyramid — replaces generate_img_pyramid: model_flow.py:58-64 (mode 0: adaptive average

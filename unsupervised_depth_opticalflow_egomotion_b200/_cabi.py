@@ -150,6 +150,7 @@ SIGNATURES = {
     "ugl_geom_flow_forward_grad_ex": (C.c_int, [C.POINTER(UglGeomFlowArgs), C.c_int32]),
     "ugl_geom_flow_combine": (C.c_int, [C.POINTER(UglGeomFlowArgs)]),
     "ugl_geom_flow_step": (C.c_int, [C.POINTER(UglGeomFlowArgs)]),
+    "ugl_geom_flow_step_parts": (C.c_int, [C.POINTER(UglGeomFlowArgs), C.c_int32]),
     "ugl_flow_loss_forward_grad": (C.c_int, [C.POINTER(UglFlowLossArgs)]),
     "ugl_flow_loss_forward_grad_ex": (C.c_int, [C.POINTER(UglFlowLossArgs), C.c_int32]),
     "ugl_flow_loss_step": (C.c_int, [C.POINTER(UglFlowLossArgs)]),

@@ -476,7 +476,11 @@ extern "C" int ugl_geom_flow_forward_grad(const UglGeomFlowArgs* g) { return ugl
 
 // fused forward + backward of the geom-mode flow branch for a known upstream gradient (ugl_flow_loss_step's counterpart): losses,
 // packed mask bytes AND grad_flow_fwd/bwd in four chained launches, no basis planes, no combine launch
-extern "C" int ugl_geom_flow_step(const UglGeomFlowArgs* g) {
+extern "C" int ugl_geom_flow_step(const UglGeomFlowArgs* g) { return ugl_geom_flow_step_parts(g, UGL_STEP_ALL); }
+
+// parts = UGL_STEP_PHOTO, then UGL_STEP_ALL & ~UGL_STEP_PHOTO: the same step in two calls, so that the caller can start what only needs the
+// photometry kernel's mask bytes (the reprojection term, the level-0 rigid terms) on other streams while the stencil kernel runs
+extern "C" int ugl_geom_flow_step_parts(const UglGeomFlowArgs* g, int parts) {
   FlowGradParams gp;
   int rc = geom_params(g, false, gp, true);
   if (rc) return rc;
@@ -491,9 +495,12 @@ extern "C" int ugl_geom_flow_step(const UglGeomFlowArgs* g) {
   gp.step = 1;
   char* pp = split_photo_partials(a);
   flow_split_assign_scratch(gp, pp + flow_split_photo_partials_bytes(a->height, a->width, a->scales, a->batch));
-  if ((rc = finalize_reset_tickets<kModeGeom>(gp.base, st))) return rc;
-  if ((rc = launch_flow_split<true>(gp, pp, st, 1))) return rc;
-  return launch_finalize<kModeGeom>(gp.base, st, &gp.photo, true);
+  if (parts != UGL_STEP_ALL && parts != UGL_STEP_PHOTO && parts != (UGL_STEP_ALL & ~UGL_STEP_PHOTO))
+    return fail(UGL_EINVAL, "geom_flow_step_parts: parts must be all, the photometry kernel, or everything after it");
+  if ((parts & UGL_STEP_PHOTO) && (rc = finalize_reset_tickets<kModeGeom>(gp.base, st))) return rc;
+  if ((rc = launch_flow_split<true>(gp, pp, st, 1, parts & 7))) return rc;
+  // chained (programmatic dependent launch): the finalize follows the stencil kernel on the stream in both forms
+  return (parts & UGL_STEP_FINALIZE) ? launch_finalize<kModeGeom>(gp.base, st, &gp.photo, true) : UGL_OK;
 }
 
 extern "C" int ugl_geom_flow_combine(const UglGeomFlowArgs* g) {

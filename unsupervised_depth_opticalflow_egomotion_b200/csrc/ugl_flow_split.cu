@@ -361,7 +361,9 @@ int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st,
   assign_photo_tiling<kGeom>(gp, photo_partials);
   const dim3 grid(gp.base.total_tiles / gp.base.B, gp.base.B);
   int rc = UGL_OK;
-  const bool chain = (parts & 7) == 7;   // the whole sequence: programmatic dependent launches between its kernels
+  // programmatic dependent launches between consecutive kernels of THIS call (a kernel launched alone orders by the stream as usual)
+  const bool pdl_norm = (parts & 1) && (parts & 2);
+  const bool pdl_stencil = gp.step ? ((parts & 2) && (parts & 4)) : ((parts & 1) && (parts & 4));
   if (parts & 1) {
     if ((rc = launch_kernel("flow_photo_kernel", flow_photo_kernel<kPhotoTW, kPhotoTH, kPhotoNT, kPatchW, kPatchH, kGeom>,
                             dim3(gp.photo.per_sample, gp.base.B), dim3(kPhotoNT), 0, st, false, gp))) return rc;
@@ -369,7 +371,7 @@ int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st,
   constexpr size_t smem = Tile::kSmemFloats * sizeof(float) + 128;
   static_assert(smem <= 227 * 1024, "stencil tile does not fit in shared memory");
   if (gp.step && (parts & 2)) {
-    if ((rc = launch_kernel("flow_photo_norm_kernel", flow_photo_norm_kernel<kGeom>, dim3(gp.base.scales, gp.base.B), dim3(256), 0, st, chain, gp))) return rc;
+    if ((rc = launch_kernel("flow_photo_norm_kernel", flow_photo_norm_kernel<kGeom>, dim3(gp.base.scales, gp.base.B), dim3(256), 0, st, pdl_norm, gp))) return rc;
   }
   if (!(parts & 4)) return UGL_OK;
   FlowTmaMaps tm;
@@ -381,11 +383,11 @@ int launch_flow_split(FlowGradParams& gp, void* photo_partials, cudaStream_t st,
   if (gp.step) {
     auto kern = flow_stencil_kernel<TW, TH, NT, kGeom, true>;
     if ((rc = opt_in_smem(kern, smem))) return rc;
-    return launch_kernel("flow_stencil_kernel", kern, grid, dim3(NT), smem, st, chain, gp, tm);
+    return launch_kernel("flow_stencil_kernel", kern, grid, dim3(NT), smem, st, pdl_stencil, gp, tm);
   }
   auto kern = flow_stencil_kernel<TW, TH, NT, kGeom, false>;
   if ((rc = opt_in_smem(kern, smem))) return rc;
-  return launch_kernel("flow_stencil_kernel", kern, grid, dim3(NT), smem, st, chain, gp, tm);
+  return launch_kernel("flow_stencil_kernel", kern, grid, dim3(NT), smem, st, pdl_stencil, gp, tm);
 }
 
 template int launch_flow_split<false>(FlowGradParams&, void*, cudaStream_t, int, int);

@@ -224,15 +224,34 @@ class _GeomStepFn(torch.autograd.Function):
         pc, pl, pr = (d["bilinear"] for d in pyr)
         area = (pyr[1]["area"], pyr[2]["area"])
         # training-step form: the flow branch's gradients come out of its forward launches (rows 2..5 of the upstream gradient)
+        def rigid_terms(masks):      # the level-0 rigid terms and the reprojection term both start from the flow branch's mask bytes
+            return _run(ops._GeomRigidFn, (fb[0], ff[0], disp[0], masks[0], Kinv[0], P_b[0], P_f[0], Fm[0], Fm[1],
+                                           (ops.MASK_ALL_BWD, ops.MASK_ALL_FWD)), 0, need_any)
+
+        def reprojection(masks):
+            return _run(ops._DepthPhotoFn, (S, 2, (ops.MASK_ALL_BWD, ops.MASK_ALL_FWD), *pc[:S], *area[0][:S], *area[1][:S], *pl[:S],
+                                            *pr[:S], *disp, *Kinv, *P_b, *P_f, *masks), 3, need_disp or need_pose)
+
+        early = {}
+
+        def after_photo(masks):      # training-step form: called between the photometry kernel and the rest of the flow branch
+            with _Side(1):
+                early["rigid"] = rigid_terms(masks)
+            with _Side(2):
+                early["photo"] = reprojection(masks)
+
         step = {} if step_gmat is None or not need_flow else {"step_gloss": step_gmat[2:6]}
+        if step and _Side.enabled:
+            step["after_photo"] = after_photo
         c_flow, out = _run(ops._GeomFlowLossFn, (S, S, float(alpha), float(beta), *pl[:S], *pc[:S], *pr[:S], *ff[:S], *fb[:S], *disp, *Kinv,
                                                   *P_b, *P_f), 4 + 3 * S, need_flow, **step)
         flow4, mbytes = out[0], list(out[1:])
-        with _Side(1):      # the level-0 rigid terms and the reprojection term both start from the flow branch's mask bytes
-            c_rigid, out_r = _run(ops._GeomRigidFn, (fb[0], ff[0], disp[0], mbytes[0], Kinv[0], P_b[0], P_f[0], Fm[0], Fm[1],
-                                                      (ops.MASK_ALL_BWD, ops.MASK_ALL_FWD)), 0, need_any)
-        c_photo, out = _run(ops._DepthPhotoFn, (S, 2, (ops.MASK_ALL_BWD, ops.MASK_ALL_FWD), *pc[:S], *area[0][:S], *area[1][:S], *pl[:S],
-                                                 *pr[:S], *disp, *Kinv, *P_b, *P_f, *mbytes), 3, need_disp or need_pose)
+        if early:
+            (c_rigid, out_r), (c_photo, out) = early["rigid"], early["photo"]
+        else:
+            with _Side(1):
+                c_rigid, out_r = rigid_terms(mbytes)
+            c_photo, out = reprojection(mbytes)
         depth_pixel, pmasks = out[0], out[1:]
         dfc, epi = out_r
         _Side.join()

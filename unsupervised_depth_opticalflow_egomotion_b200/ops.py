@@ -416,8 +416,14 @@ class _GeomFlowLossFn(torch.autograd.Function):
             g = _geom_args(S, L, img_l, img, img_r, ff, fb, disp, Kinv, P_b, P_f, masks, alpha, beta, loss, stats, None, None, gl, gf, gb)
             ws = torch.empty(max(int(_cabi.lib().ugl_flow_loss_workspace_bytes(C.byref(g.flow))) // 4, 1), device=dev, dtype=torch.float32)
             g.flow.workspace, g.flow.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+            after_photo = getattr(ctx, "after_photo", None)
             with torch.cuda.device_of(img[0]):
-                _call("ugl_geom_flow_step", C.byref(g), launches=4)
+                if after_photo is None:
+                    _call("ugl_geom_flow_step", C.byref(g), launches=4)
+                else:       # mode_steps: the consumers of the mask bytes start on side streams as soon as the photometry kernel is queued
+                    _call("ugl_geom_flow_step_parts", C.byref(g), _cabi.STEP_PARTS["photo"], launches=1)
+                    after_photo(masks)
+                    _call("ugl_geom_flow_step_parts", C.byref(g), _cabi.STEP_PARTS["all"] & ~_cabi.STEP_PARTS["photo"], launches=3)
             ctx.step_grads = (gf, gb)
             ctx.S, ctx.L, ctx.ab = S, L, (alpha, beta)
             ctx.mark_non_differentiable(*masks)
