@@ -180,9 +180,14 @@ static int emu_flow_split(FlowGradParams& gp, int step) {
       for (int l = 0; l < p.scales; ++l) {
         float S[ROW];
         for (int k = 0; k < ROW; ++k) S[k] = (float)psum[((size_t)b * p.scales + l) * ROW + k];
-        const FlowCombineScales k = flow_combine_scales(S, p.lv[l].h, p.lv[l].w, p.gloss, p.B, b);
         float* o = scales_buf.data() + ((size_t)b * p.scales + l) * 8;
-        o[0] = k.pix[0]; o[1] = k.pix[1]; o[2] = k.pix[0]; o[3] = k.pix[1]; o[4] = k.ssim[0]; o[5] = k.ssim[1]; o[6] = k.sm; o[7] = k.cons;
+        if (kGeom) {     // flow_photo_norm_kernel<true>: the eight factors of geom_combine_scales
+          const GeomCombineScales k = geom_combine_scales(S, p.lv[l].h, p.lv[l].w, p.gloss, p.B, b);
+          o[0] = k.pix_r[0]; o[1] = k.pix_r[1]; o[2] = k.pix_d[0]; o[3] = k.pix_d[1]; o[4] = k.ssim[0]; o[5] = k.ssim[1]; o[6] = k.sm; o[7] = k.cons;
+        } else {
+          const FlowCombineScales k = flow_combine_scales(S, p.lv[l].h, p.lv[l].w, p.gloss, p.B, b);
+          o[0] = k.pix[0]; o[1] = k.pix[1]; o[2] = k.pix[0]; o[3] = k.pix[1]; o[4] = k.ssim[0]; o[5] = k.ssim[1]; o[6] = k.sm; o[7] = k.cons;
+        }
       }
   }
   // stencil tiles
@@ -256,6 +261,19 @@ extern "C" int emu_geom_flow_split_forward_grad(const UglGeomFlowArgs* g) {
   }
   gp.alpha = g->alpha; gp.beta = g->beta;
   return emu_flow_split<true>(gp, 0);
+}
+
+// the fused geom training step (ugl_geom_flow_step): gradients written by the stencil tiles, L1 scale per pixel from the mask byte
+extern "C" int emu_geom_flow_step(const UglGeomFlowArgs* g) {
+  const UglFlowLossArgs* a = &g->flow;
+  FlowGradParams gp;
+  fill_params<kBTW, kBTH>(a, true, gp.base);
+  for (int l = 0; l < a->scales; ++l) {
+    gp.disp[l] = g->disp[l]; gp.Kinv[l] = g->Kinv[l];
+    gp.P[0][l] = g->P_bwd[l]; gp.P[1][l] = g->P_fwd[l]; gp.mask_bytes[l] = g->mask_bytes[l];
+  }
+  gp.alpha = g->alpha; gp.beta = g->beta;
+  return emu_flow_split<true>(gp, 1);
 }
 
 extern "C" int emu_flow_loss_combine(const UglFlowLossArgs* a) {

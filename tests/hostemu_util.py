@@ -119,6 +119,9 @@ def emu_geom_flow(img_l, img, img_r, flows_fwd, flows_bwd, disp, Kinv, P_b, P_f,
         g.disp[l], g.Kinv[l], g.P_bwd[l], g.P_fwd[l] = disp[l].data_ptr(), Kinv[l].data_ptr(), P_b[l].data_ptr(), P_f[l].data_ptr()
         g.mask_bytes[l] = masks[l].data_ptr()
     g.alpha, g.beta = alpha, beta
+    if split == "step":       # the fused training step: no basis planes, no combine
+        emu().emu_geom_flow_step(C.byref(g))
+        return loss, gf, gb, masks
     (emu().emu_geom_flow_split_forward_grad if split else emu().emu_geom_flow_forward_grad)(C.byref(g))
     emu().emu_geom_flow_combine(C.byref(g))
     return loss, gf, gb, masks

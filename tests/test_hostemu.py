@@ -108,11 +108,12 @@ def _geom_projections(t, S):
     return Kinv, Pb, Pf
 
 
-@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("split", [False, True, "step"])
 @pytest.mark.parametrize("B,Hh,W,S", [(2, 48, 96, 3), (1, 40, 72, 2), (1, 34, 50, 1)])
 def test_geom_flow_tiles_vs_oracle(B, Hh, W, S, split):
-    """geom-mode variant of the single-pass kernel (split=False: fused tile kernel; True: photometry pixels + stencil tiles):
-    flow-branch losses, flow gradients and the packed masks"""
+    """geom-mode variant of the single-pass kernel (split=False: fused tile kernel; True: photometry pixels + stencil tiles; "step": the
+    fused training step -- scale factors from the weight sums, gradients written by the stencil tiles): flow-branch losses, flow
+    gradients and the packed masks"""
     t = make_triplet(B, Hh, W, flow_levels=S, depth_scales=S, seed=11, flow_mode="rigid", flow_px=1.5)
     keys = ("loss_flow_pixel", "loss_flow_ssim", "loss_flow_smooth", "loss_flow_consis")
     gl = torch.rand(4, B, generator=torch.Generator().manual_seed(2)) + 0.5
